@@ -1,0 +1,211 @@
+/*
+ * b2asr.h -- C ABI of the B200-native acoustic-training hot path
+ * (BLSTM encoder -> CTC forward/backward loss -> decoders -> clip/optimizer).
+ *
+ * This is the drop-in boundary for the hot path of
+ * hirofumi0810/tensorflow_end2end_speech_recognition.  The reference has no
+ * FFI of its own: every entry point below replaces one TensorFlow-1.x op that
+ * the reference calls by name (file:line cited per function); the Python
+ * host mirror (tensorflow_end2end_speech_recognition_b200/) binds them with
+ * ctypes, see INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C: POD + raw DEVICE pointers + sizes; no torch / C++ types.
+ *  - every call is asynchronous on `stream` (a cudaStream_t); nothing
+ *    synchronises, nothing allocates: scratch comes from the caller
+ *    (`*_workspace_bytes` tells how much).
+ *  - return value: 0 = ok, negative = B2_ERR_*; b2_last_error() returns a
+ *    thread-local message for the last failing call.
+ *  - all activations fp32 at the boundary (the reference is fp32 end to end);
+ *    `precision` selects the arithmetic inside GEMM-shaped work.
+ */
+#ifndef B2ASR_H_
+#define B2ASR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* b2_stream_t; /* cudaStream_t */
+
+enum {
+  B2_OK = 0,
+  B2_ERR_INVALID = -1,      /* bad argument (shape, null pointer, unsupported flag) */
+  B2_ERR_WORKSPACE = -2,    /* workspace too small */
+  B2_ERR_CUDA = -3,         /* CUDA runtime error (message in b2_last_error) */
+  B2_ERR_UNSUPPORTED = -4   /* valid request the current build cannot serve */
+};
+
+/* arithmetic used inside GEMM-shaped work */
+enum {
+  B2_PREC_FP32 = 0,   /* CUDA-core fp32 FFMA: bit-for-bit deterministic, parity mode */
+  B2_PREC_BF16 = 1    /* tcgen05 tensor cores: bf16 operands, fp32 accumulate (TMEM) */
+};
+
+int b2_version(void);
+const char* b2_last_error(void);
+/* 1 when the running device is sm_100 (tcgen05/TMA paths usable) */
+int b2_device_is_sm100(void);
+
+/* ------------------------------------------------------------------------ *
+ * CTC loss + gradient                    replaces tf.nn.ctc_loss
+ *   reference call: models/ctc/ctc.py:289-297 (ignore_longer=1) and
+ *                   models/attention/joint_ctc_attention.py:308-316 (=0)
+ * logits [T,B,C] time-major, unnormalised; labels in CSR form
+ * (label_offsets[B+1] into labels_flat), the dense form of the SparseTensor
+ * built by utils/io/labels/sparsetensor.py:12-39.  blank = C-1 in the
+ * reference (ctc.py:101).  max_label_len = max_b L_b (host knows it).
+ * loss[b] = -log p(l_b | x_b) (0 for skipped utterances, +inf when no
+ * alignment exists); grad[t,b,c] = grad_scale * d loss[b] / d logits[t,b,c]
+ * (softmax - occupancy; 0 for t >= seq_len[b]); grad may be NULL.
+ * ------------------------------------------------------------------------ */
+size_t b2_ctc_workspace_bytes(int T, int B, int C, int max_label_len);
+int b2_ctc_loss_grad(const float* logits, const int32_t* labels_flat,
+                     const int32_t* label_offsets, const int32_t* seq_len,
+                     int T, int B, int C, int blank, int max_label_len,
+                     int ignore_longer_outputs_than_inputs, float grad_scale,
+                     float* loss, float* grad, void* workspace,
+                     size_t workspace_bytes, b2_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * CTC greedy decoder                     replaces tf.nn.ctc_greedy_decoder
+ *   reference call: models/ctc/ctc.py:340-342; numpy twin
+ *   models/ctc/decoders/greedy_decoder.py:19-50
+ * logits [T,B,C] (or any per-frame monotone transform of the posteriors).
+ * out_labels [B, T] int32 padded with -1; out_len [B].
+ * ------------------------------------------------------------------------ */
+int b2_ctc_greedy_decode(const float* logits, const int32_t* seq_len, int T,
+                         int B, int C, int blank, int32_t* out_labels,
+                         int32_t* out_len, b2_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * CTC prefix beam search                 replaces BeamSearchDecoder.__call__
+ *   reference: models/ctc/decoders/beam_search_decoder.py:53-152 (the decoder
+ *   examples/librispeech/evaluation/eval_ctc.py:126-131 selects, width 20)
+ * log_probs [B,T,C] natural-log posteriors (the reference takes np.log(probs)).
+ * out_labels [B, T] padded -1; out_len [B]; out_score [B] = -log score.
+ * ------------------------------------------------------------------------ */
+size_t b2_ctc_beam_workspace_bytes(int T, int B, int C, int beam_width);
+int b2_ctc_beam_decode(const float* log_probs, const int32_t* seq_len, int T,
+                       int B, int C, int blank, int beam_width,
+                       int32_t* out_labels, int32_t* out_len, float* out_score,
+                       void* workspace, size_t workspace_bytes,
+                       b2_stream_t stream);
+
+/* softmax over the last axis of [rows, C]   (CTC.posteriors, ctc.py:354-380) */
+int b2_softmax_rows(const float* x, float* y, int64_t rows, int C,
+                    b2_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * GEMM with bias epilogue   replaces MatMul/BiasAdd under
+ *   tf.contrib.layers.fully_connected (ctc.py:203,217) and the time-batched
+ *   halves of LSTMBlockCell's [x,h].W (blstm.py:287-320)
+ * C[M,N] (ldc) = alpha * op(A) . op(B) + beta * C + bias[N]
+ *   transa = 0: A is [M,K] row-major (lda)   1: A is [K,M] row-major
+ *   transb = 0: B is [K,N] row-major (ldb)   1: B is [N,K] row-major
+ * fp32 in / fp32 out.  precision = B2_PREC_BF16 rounds operands to bf16 and
+ * runs on tcgen05 (requires sm_100a; K, lda, ldb multiples of 8).
+ * ------------------------------------------------------------------------ */
+size_t b2_gemm_workspace_bytes(int M, int N, int K, int precision);
+int b2_gemm(int transa, int transb, int M, int N, int K, float alpha,
+            const float* A, int lda, const float* B, int ldb, float beta,
+            float* C, int ldc, const float* bias, int precision,
+            void* workspace, size_t workspace_bytes, b2_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * Bidirectional LSTM layer              replaces LSTMBlockCell / LSTMCell /
+ *   BasicLSTMCell under tf.nn.bidirectional_dynamic_rnn
+ *   reference: models/encoders/core/blstm.py:258-332 (block), :187-255,
+ *   :124-184; cell equations models/recurrent/layers/lstm.py:142-183
+ * One call = one layer, both directions, all T steps.
+ * ------------------------------------------------------------------------ */
+typedef struct {
+  int32_t T, B, D_in, H;      /* max time, batch, input width, num_units    */
+  int32_t use_peephole;       /* w_{i,f,o}_diag present                      */
+  float forget_bias;          /* 1.0 in every reference call                 */
+  float cell_clip;            /* <= 0: no clipping                           */
+  float keep_prob;            /* DropoutWrapper(output_keep_prob); 1 = off   */
+  uint64_t dropout_seed;      /* counter-hash seed for the mask              */
+  int32_t precision;          /* B2_PREC_*                                   */
+  int32_t need_backward;      /* 1: fill `reserve` for b2_blstm_layer_backward */
+} b2_lstm_desc;
+
+/* parameters of one direction, TF LSTMBlockCell layout:
+ * kernel [(D_in+H), 4H] rows = [x; h], gate column blocks i, g(ci), f, o */
+typedef struct {
+  const float* kernel;
+  const float* bias;        /* [4H] */
+  const float* w_i_diag;    /* [H] or NULL */
+  const float* w_f_diag;
+  const float* w_o_diag;
+} b2_lstm_params;
+
+typedef struct {
+  float* kernel;
+  float* bias;
+  float* w_i_diag;
+  float* w_f_diag;
+  float* w_o_diag;
+} b2_lstm_grads;
+
+size_t b2_blstm_reserve_bytes(const b2_lstm_desc* d);
+size_t b2_blstm_workspace_bytes(const b2_lstm_desc* d);
+
+/* x [T,B,D_in] time-major; y [T,B,2H] = concat(fw, bw) after output dropout,
+ * zero for t >= seq_len[b]; final_state [4,B,H] = c_fw, h_fw, c_bw, h_bw
+ * (may be NULL). */
+int b2_blstm_layer_forward(const b2_lstm_desc* d, const float* x,
+                           const int32_t* seq_len, const b2_lstm_params* fw,
+                           const b2_lstm_params* bw, float* y,
+                           float* final_state, void* reserve, void* workspace,
+                           size_t workspace_bytes, b2_stream_t stream);
+
+/* dy [T,B,2H]; dx [T,B,D_in] (NULL for the first layer); gradients are
+ * ACCUMULATED into g_fw / g_bw (caller zeroes them once per step). */
+int b2_blstm_layer_backward(const b2_lstm_desc* d, const float* x,
+                            const int32_t* seq_len, const b2_lstm_params* fw,
+                            const b2_lstm_params* bw, const float* dy,
+                            const void* reserve, float* dx,
+                            const b2_lstm_grads* g_fw, const b2_lstm_grads* g_bw,
+                            void* workspace, size_t workspace_bytes,
+                            b2_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * Small data-movement helpers of the step
+ * ------------------------------------------------------------------------ */
+/* [B,T,D] -> [T,B,D]  (tf.transpose at blstm.py:279) */
+int b2_transpose_01(const float* x, float* y, int d0, int d1, int d2,
+                    b2_stream_t stream);
+/* column sums: out[N] (+)= sum_m X[m, n]   (bias gradient) */
+int b2_colsum(const float* X, int64_t M, int N, int ldx, float* out,
+              int accumulate, b2_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * Gradient clipping + optimizers          replaces tf.clip_by_norm and
+ *   tf.train.*Optimizer      reference: models/model_base.py:12-20,68-95,135-166
+ * Multi-tensor: n tensors described by device arrays of pointers/sizes.
+ * ------------------------------------------------------------------------ */
+enum {
+  B2_OPT_SGD = 0, B2_OPT_MOMENTUM = 1, B2_OPT_NESTEROV = 2, B2_OPT_ADAGRAD = 3,
+  B2_OPT_ADADELTA = 4, B2_OPT_ADAM = 5, B2_OPT_RMSPROP = 6
+};
+/* per-tensor tf.clip_by_norm, in place; norms [n] is scratch/diagnostic out.
+ * post_scale is applied after clipping (1/num_towers for the tower mean). */
+int b2_clip_by_norm_multi(float* const* grads, const int64_t* sizes, int n,
+                          float clip_norm, float post_scale, float* norms,
+                          b2_stream_t stream);
+/* TF-1.x update rules; state0/state1 per tensor (may be NULL
+ * where the rule needs none); step = 1-based global step (Adam). */
+int b2_optimizer_step_multi(int kind, float* const* params,
+                            float* const* grads, float* const* state0,
+                            float* const* state1, const int64_t* sizes, int n,
+                            float learning_rate, int64_t step,
+                            b2_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2ASR_H_ */

@@ -1,0 +1,316 @@
+// CTC forward-backward loss + gradient for sm_100a.
+//
+// Replaces tf.nn.ctc_loss as called at models/ctc/ctc.py:289-297 (reference
+// arithmetic lives in TensorFlow; semantics restated in oracle/ctc.py).
+//
+// Three kernels, all HBM/latency bound (no GEMM shape anywhere):
+//   K3a ctc_lse_kernel        one warp per (t,b) row: lse[t,b] = logsumexp_c logits
+//   K3b ctc_alpha_beta_kernel one CTA per (utterance, direction): the T-step
+//                             lattice sweep in shared memory, log domain,
+//                             alpha and beta CTAs run concurrently; rows are
+//                             spilled to HBM/L2 ([B,T,S] fp32 each)
+//   K3c ctc_grad_kernel       one warp per (t,b) row: softmax - occupancy,
+//                             occupancy scattered by label in shared memory
+//
+// Algorithmic HBM bytes: 8*T*B*C (read logits, write grad) + 16*T*B*S spill.
+#include "common.cuh"
+
+namespace b2 {
+
+constexpr int kWarpsPerBlock = 8;
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+ctc_lse_kernel(const float* __restrict__ logits, const int* __restrict__ seq_len,
+               int T, int B, int C, float* __restrict__ lse) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  if (row >= (int64_t)T * B) return;
+  const int t = (int)(row / B), b = (int)(row % B);
+  if (t >= seq_len[b]) {
+    if (lane == 0) lse[row] = 0.f;
+    return;
+  }
+  const float* x = logits + row * C;
+  float m = -INFINITY;
+  for (int c = lane; c < C; c += 32) m = fmaxf(m, x[c]);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += __expf(x[c] - m);
+  s = warp_sum(s);
+  if (lane == 0) lse[row] = m + __logf(s);
+}
+
+// One CTA = one utterance x one direction (blockIdx.y: 0 alpha, 1 beta).
+// Thread tid owns lattice positions s = tid + k*blockDim.x, k < SPT.
+template <int SPT>
+__global__ void __launch_bounds__(1024)
+ctc_alpha_beta_kernel(const float* __restrict__ logits, const float* __restrict__ lse,
+                      const int* __restrict__ labels_flat, const int* __restrict__ label_offsets,
+                      const int* __restrict__ seq_len, int T, int B, int C, int blank,
+                      int S_pad, int ignore_longer, float* __restrict__ alpha,
+                      float* __restrict__ beta, float* __restrict__ logp_out,
+                      int* __restrict__ skip_out, float* __restrict__ loss) {
+  extern __shared__ float smem[];
+  const int b = blockIdx.x;
+  const bool is_beta = blockIdx.y == 1;
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const int Tb = min(seq_len[b], T);
+  const int off = label_offsets[b];
+  const int L = label_offsets[b + 1] - off;
+  const int S = 2 * L + 1;
+  const int* lab = labels_flat + off;
+
+  if (L > Tb && ignore_longer) {   // skipped utterance: loss 0, grad 0 (ctc.py:296)
+    if (tid == 0 && !is_beta) { loss[b] = 0.f; logp_out[b] = 0.f; skip_out[b] = 1; }
+    return;
+  }
+  if (Tb <= 0) {
+    if (tid == 0 && !is_beta) {
+      loss[b] = (L == 0) ? 0.f : INFINITY;
+      logp_out[b] = (L == 0) ? 0.f : -INFINITY;
+      skip_out[b] = 1;
+    }
+    return;
+  }
+  if (tid == 0 && !is_beta) skip_out[b] = 0;
+
+  const int W = S_pad + 4;          // own cell of position s is buf[s + 2]
+  float* buf0 = smem;
+  float* buf1 = smem + W;
+  for (int i = tid; i < 2 * W; i += NT) smem[i] = -INFINITY;
+
+  int cls[SPT];
+  bool skip[SPT], valid[SPT];
+#pragma unroll
+  for (int k = 0; k < SPT; ++k) {
+    const int s = tid + k * NT;
+    valid[k] = s < S;
+    cls[k] = (valid[k] && (s & 1)) ? lab[s >> 1] : blank;
+    skip[k] = false;
+    if (valid[k] && (s & 1)) {
+      if (!is_beta) skip[k] = (s >= 3) && (lab[s >> 1] != lab[(s >> 1) - 1]);
+      else          skip[k] = (s + 2 < S) && (lab[(s >> 1) + 1] != lab[s >> 1]);
+    }
+  }
+  float* out = (is_beta ? beta : alpha) + (int64_t)b * T * S_pad;
+  const int t0 = is_beta ? Tb - 1 : 0;
+  const int dt = is_beta ? -1 : 1;
+  __syncthreads();
+
+  // t = t0 (initial column)
+  {
+    const int64_t row = (int64_t)t0 * B + b;
+    const float l = lse[row];
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+      const int s = tid + k * NT;
+      if (!valid[k]) continue;
+      float v = -INFINITY;
+      const bool init = is_beta ? (s >= S - 2) : (s <= 1);
+      if (init) v = logits[row * C + cls[k]] - l;
+      buf0[s + 2] = v;
+      out[(int64_t)t0 * S_pad + s] = v;
+    }
+  }
+  __syncthreads();
+
+  constexpr int PF = 4;              // prefetch distance (steps) for the emission gather
+  float xq[PF][SPT];
+  const int nsteps = Tb - 1;
+#pragma unroll
+  for (int j = 0; j < PF; ++j) {
+    const int i = j;
+    const int t = t0 + dt * (i + 1);
+#pragma unroll
+    for (int k = 0; k < SPT; ++k) {
+      xq[j][k] = 0.f;
+      if (i < nsteps && valid[k]) {
+        const int64_t row = (int64_t)t * B + b;
+        xq[j][k] = __ldg(&logits[row * C + cls[k]]) - __ldg(&lse[row]);
+      }
+    }
+  }
+  float* prev = buf0;
+  float* cur = buf1;
+  for (int i0 = 0; i0 < nsteps; i0 += PF) {
+#pragma unroll
+    for (int j = 0; j < PF; ++j) {
+      const int i = i0 + j;
+      if (i < nsteps) {               // uniform across the CTA
+        const int t = t0 + dt * (i + 1);
+#pragma unroll
+        for (int k = 0; k < SPT; ++k) {
+          const int s = tid + k * NT;
+          if (valid[k]) {
+            const float a0 = prev[s + 2];
+            const float a1 = is_beta ? prev[s + 3] : prev[s + 1];
+            const float a2 = skip[k] ? (is_beta ? prev[s + 4] : prev[s]) : -INFINITY;
+            const float v = lse3(a0, a1, a2) + xq[j][k];
+            cur[s + 2] = v;
+            out[(int64_t)t * S_pad + s] = v;
+          }
+        }
+        // refill this ring slot with the emission PF steps ahead
+        const int ip = i + PF;
+        if (ip < nsteps) {
+          const int tp = t0 + dt * (ip + 1);
+          const int64_t row = (int64_t)tp * B + b;
+          const float l = __ldg(&lse[row]);
+#pragma unroll
+          for (int k = 0; k < SPT; ++k)
+            if (valid[k]) xq[j][k] = __ldg(&logits[row * C + cls[k]]) - l;
+        }
+        __syncthreads();
+        float* tmp = prev; prev = cur; cur = tmp;
+      }
+    }
+  }
+  if (!is_beta && tid == 0) {
+    const float a = prev[(S - 1) + 2];
+    const float c = (S > 1) ? prev[(S - 2) + 2] : -INFINITY;
+    const float lp = lse2(a, c);
+    logp_out[b] = lp;
+    loss[b] = -lp;
+  }
+}
+
+// One warp per (t,b) row.  g[c] = softmax_c - sum_{s: l'(s)=c} alpha*beta/(y*p).
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+ctc_grad_kernel(const float* __restrict__ logits, const float* __restrict__ lse,
+                const int* __restrict__ labels_flat, const int* __restrict__ label_offsets,
+                const int* __restrict__ seq_len, const float* __restrict__ alpha,
+                const float* __restrict__ beta, const float* __restrict__ logp_in,
+                const int* __restrict__ skip_in, int T, int B, int C, int blank, int S_pad,
+                float grad_scale, int warps_per_block, float* __restrict__ grad) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * warps_per_block + warp;
+  if (row >= (int64_t)T * B) return;
+  const int t = (int)(row / B), b = (int)(row % B);
+  float* g = smem + (size_t)warp * C;
+  float* out = grad + row * C;
+  const int Tb = min(seq_len[b], T);
+  if (t >= Tb || skip_in[b]) {
+    for (int c = lane; c < C; c += 32) out[c] = 0.f;
+    return;
+  }
+  const float* x = logits + row * C;
+  const float l = lse[row];
+  for (int c = lane; c < C; c += 32) g[c] = __expf(x[c] - l);
+  __syncwarp();
+  const float logp = logp_in[b];
+  if (logp != -INFINITY) {
+    const int off = label_offsets[b];
+    const int L = label_offsets[b + 1] - off;
+    const int S = 2 * L + 1;
+    const float* ar = alpha + ((int64_t)b * T + t) * S_pad;
+    const float* br = beta + ((int64_t)b * T + t) * S_pad;
+    const float xb = x[blank] - l;
+    float blank_occ = 0.f;
+    // blanks: even s, reduced in registers
+    for (int s = 2 * lane; s < S; s += 64) {
+      const float v = ar[s] + br[s];
+      if (v != -INFINITY) blank_occ += __expf(v - xb - logp);
+    }
+    // labels: odd s, scattered with shared-memory atomics
+    for (int s = 2 * lane + 1; s < S; s += 64) {
+      const float v = ar[s] + br[s];
+      if (v != -INFINITY) {
+        const int c = labels_flat[off + (s >> 1)];
+        atomicAdd(&g[c], -__expf(v - (x[c] - l) - logp));
+      }
+    }
+    blank_occ = warp_sum(blank_occ);
+    __syncwarp();
+    if (lane == 0) g[blank] -= blank_occ;
+    __syncwarp();
+  }
+  for (int c = lane; c < C; c += 32) out[c] = grad_scale * g[c];
+}
+
+struct CtcWs {
+  float* lse; float* alpha; float* beta; float* logp; int* skip; int S_pad;
+};
+
+static size_t ctc_ws_layout(int T, int B, int max_label_len, void* base, CtcWs* w) {
+  const int S_pad = (int)align_up(2 * (size_t)max_label_len + 1, 32);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+  size_t o_lse = take((size_t)T * B * 4);
+  size_t o_a = take((size_t)B * T * S_pad * 4);
+  size_t o_b = take((size_t)B * T * S_pad * 4);
+  size_t o_lp = take((size_t)B * 4);
+  size_t o_sk = take((size_t)B * 4);
+  if (w) {
+    char* p = (char*)base;
+    w->lse = (float*)(p + o_lse); w->alpha = (float*)(p + o_a); w->beta = (float*)(p + o_b);
+    w->logp = (float*)(p + o_lp); w->skip = (int*)(p + o_sk); w->S_pad = S_pad;
+  }
+  return off;
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" size_t b2_ctc_workspace_bytes(int T, int B, int C, int max_label_len) {
+  (void)C;
+  return ctc_ws_layout(T, B, max_label_len, nullptr, nullptr);
+}
+
+extern "C" int b2_ctc_loss_grad(const float* logits, const int32_t* labels_flat,
+                                const int32_t* label_offsets, const int32_t* seq_len, int T,
+                                int B, int C, int blank, int max_label_len,
+                                int ignore_longer, float grad_scale, float* loss, float* grad,
+                                void* workspace, size_t workspace_bytes, b2_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B2_CHECK_ARG(logits && labels_flat && label_offsets && seq_len && loss && workspace,
+               "b2_ctc_loss_grad: null pointer");
+  B2_CHECK_ARG(T > 0 && B > 0 && C > 1 && blank >= 0 && blank < C && max_label_len >= 0,
+               "b2_ctc_loss_grad: bad shape T=%d B=%d C=%d blank=%d Lmax=%d", T, B, C, blank,
+               max_label_len);
+  CtcWs w;
+  const size_t need = ctc_ws_layout(T, B, max_label_len, workspace, &w);
+  if (workspace_bytes < need) {
+    set_error("b2_ctc_loss_grad: workspace %zu < %zu", workspace_bytes, need);
+    return B2_ERR_WORKSPACE;
+  }
+  const int64_t rows = (int64_t)T * B;
+  ctc_lse_kernel<<<cdiv(rows, kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream>>>(
+      logits, seq_len, T, B, C, w.lse);
+  B2_LAUNCH_CHECK();
+
+  const int S_max = 2 * max_label_len + 1;
+  int NT = (int)align_up((size_t)S_max, 32);
+  int spt = 1;
+  while (NT > 1024) { spt *= 2; NT = (int)align_up((size_t)cdiv(S_max, spt), 32); }
+  B2_CHECK_ARG(spt <= 8, "b2_ctc_loss_grad: label length %d too long (max 4095)", max_label_len);
+  const size_t smem = (size_t)2 * (w.S_pad + 4) * sizeof(float);
+  dim3 grid(B, 2);
+#define LAUNCH_AB(SPT)                                                                      \
+  do {                                                                                      \
+    B2_CUDA(cudaFuncSetAttribute(ctc_alpha_beta_kernel<SPT>,                                \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    ctc_alpha_beta_kernel<SPT><<<grid, NT, smem, stream>>>(                                 \
+        logits, w.lse, labels_flat, label_offsets, seq_len, T, B, C, blank, w.S_pad,        \
+        ignore_longer, w.alpha, w.beta, w.logp, w.skip, loss);                              \
+  } while (0)
+  if (spt == 1) LAUNCH_AB(1); else if (spt == 2) LAUNCH_AB(2);
+  else if (spt == 4) LAUNCH_AB(4); else LAUNCH_AB(8);
+#undef LAUNCH_AB
+  B2_LAUNCH_CHECK();
+
+  if (grad) {
+    int wpb = kWarpsPerBlock;
+    while (wpb > 1 && (size_t)wpb * C * 4 > 160 * 1024) wpb >>= 1;
+    const size_t gsmem = (size_t)wpb * C * 4;
+    B2_CHECK_ARG(gsmem <= 200 * 1024, "b2_ctc_loss_grad: C=%d too large", C);
+    B2_CUDA(cudaFuncSetAttribute(ctc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)gsmem));
+    ctc_grad_kernel<<<cdiv(rows, wpb), wpb * 32, gsmem, stream>>>(
+        logits, w.lse, labels_flat, label_offsets, seq_len, w.alpha, w.beta, w.logp, w.skip, T,
+        B, C, blank, w.S_pad, grad_scale, wpb, grad);
+    B2_LAUNCH_CHECK();
+  }
+  return B2_OK;
+}

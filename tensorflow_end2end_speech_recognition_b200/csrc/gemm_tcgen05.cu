@@ -1,0 +1,392 @@
+// bf16 tensor-core GEMM for sm_100a: TMA-staged operands, tcgen05.mma with the
+// fp32 accumulator in TMEM, warp-specialised persistent CTAs.
+//
+// This is the time-batched half of the BLSTM gate GEMMs (the reference runs
+// them as MatMul inside LSTMBlockCell, models/encoders/core/blstm.py:287-320):
+//   forward   G  = X . Wx          (A K-major,  B K-major after weight transpose)
+//   backward  dX = dG . Wx^T       (A K-major,  B K-major)
+//   wgrad     dW = [X;H]^T . dG    (A MN-major, B MN-major, split-K, fp32 atomics)
+// and the fully_connected output layer (models/ctc/ctc.py:216-224).
+//
+// CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2-5
+// epilogue (TMEM -> registers -> smem transpose -> coalesced global stores).
+// Tile 128 x BN x 64, 4..8 smem stages, two TMEM accumulators so the epilogue of
+// tile i overlaps the MMAs of tile i+1.
+#include "common.cuh"
+#include "sm100.cuh"
+#include <mutex>
+
+namespace b2 {
+using namespace sm100;
+
+constexpr int GM = 128;   // tile M (= UMMA M, one TMEM lane per row)
+constexpr int GK = 64;    // tile K: 64 bf16 = one 128-byte swizzle atom
+constexpr int kGemmThreads = 192;
+
+enum { EPI_STORE_F32 = 0, EPI_ATOMIC_F32 = 1, EPI_STORE_BF16 = 2 };
+
+struct GemmArgs {
+  int M, N, K;
+  int ldc;
+  void* C;
+  const float* bias;
+  float alpha;
+  int m_tiles, n_tiles, k_splits, kb_per_split, kblocks;
+  int epi;
+};
+
+template <int BN> struct GemmCfg {
+  static constexpr int kStageA = GM * GK * 2;
+  static constexpr int kStageB = BN * GK * 2;
+  static constexpr int kStage = kStageA + kStageB;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
+  static constexpr int kEpiBytes = 4 * 32 * 33 * 4;
+  static constexpr int kSmem = kStages * kStage + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const GemmArgs args) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * Cfg::kStageA;
+  float* sEpi = (float*)(smem + kStages * Cfg::kStage);
+  uint64_t* bars = (uint64_t*)(smem + kStages * Cfg::kStage + Cfg::kEpiBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* tfull = bars + 2 * kStages;
+  uint64_t* tempty = bars + 2 * kStages + 2;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles = args.m_tiles * args.n_tiles;
+  const int total = tiles * args.k_splits;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int ks = w / tiles, r = w % tiles;
+        const int m0 = (r / args.n_tiles) * GM, n0 = (r % args.n_tiles) * BN;
+        const int kb0 = ks * args.kb_per_split;
+        const int kb1 = min(kb0 + args.kb_per_split, args.kblocks);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], Cfg::kStage);
+          uint8_t* a = sA + stage * Cfg::kStageA;
+          uint8_t* b = sB + stage * Cfg::kStageB;
+          if (!A_MN) {
+            tma_load_2d(a, &tmA, &full[stage], kb * GK, m0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < GM / 64; ++i)
+              tma_load_2d(a + i * (64 * GK * 2), &tmA, &full[stage], m0 + i * 64, kb * GK);
+          }
+          if (!B_MN) {
+            tma_load_2d(b, &tmB, &full[stage], kb * GK, n0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_2d(b + i * (64 * GK * 2), &tmB, &full[stage], n0 + i * 64, kb * GK);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(GM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int ks = w / tiles;
+        const int kb0 = ks * args.kb_per_split;
+        const int kb1 = min(kb0 + args.kb_per_split, args.kblocks);
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * Cfg::kStageA);
+          const uint32_t b_addr = smem_u32(sB + stage * Cfg::kStageB);
+#pragma unroll
+          for (int k = 0; k < GK / 16; ++k) {
+            // K-major: 8-row groups 1024 B apart, advance 32 B per UMMA_K inside the atom.
+            // MN-major: 64-wide MN groups one box (8 KB) apart, 8-k groups 1024 B apart,
+            //           advance 16 k-rows = 2048 B per UMMA_K.
+            const uint64_t ad = A_MN ? make_smem_desc(a_addr + k * 2048, 64 * GK * 2, 1024, 2)
+                                     : make_smem_desc(a_addr + k * 32, 16, 1024, 2);
+            const uint64_t bd = B_MN ? make_smem_desc(b_addr + k * 2048, 64 * GK * 2, 1024, 2)
+                                     : make_smem_desc(b_addr + k * 32, 16, 1024, 2);
+            mma_ss(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          mma_commit(&empty[stage]);           // smem slot free once these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        mma_commit(&tfull[acc]);               // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue
+    const int q = warp & 3;                    // TMEM lane quarter this warp may touch
+    float* st = sEpi + (warp - 2) * 32 * 33;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      const int ks = w / tiles, r = w % tiles;
+      const int m0 = (r / args.n_tiles) * GM, n0 = (r % args.n_tiles) * BN;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) st[lane * 33 + j] = __uint_as_float(v[j]);
+        __syncwarp();
+        const int col = n0 + c * 32 + lane;
+        const bool col_ok = col < args.N;
+        float bv = 0.f;
+        if (args.bias && col_ok && ks == 0) bv = args.bias[col];
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) {
+          const int row = m0 + q * 32 + rr;
+          if (row < args.M && col_ok) {
+            const float o = args.alpha * st[rr * 33 + lane] + bv;
+            const size_t idx = (size_t)row * args.ldc + col;
+            if (args.epi == EPI_STORE_F32) ((float*)args.C)[idx] = o;
+            else if (args.epi == EPI_ATOMIC_F32) atomicAdd(&((float*)args.C)[idx], o);
+            else ((__nv_bfloat16*)args.C)[idx] = __float2bfloat16(o);
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor map: inner (contiguous) extent d0, outer extent d1, row pitch ld elements.
+int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t ld,
+                   uint32_t box0, uint32_t box1) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled not available (no driver?)"); return B2_ERR_CUDA; }
+  if (((uintptr_t)base & 15) || (ld * 2) % 16) {
+    set_error("tensor map: base %p / pitch %llu not 16-byte aligned", base,
+              (unsigned long long)ld * 2);
+    return B2_ERR_INVALID;
+  }
+  cuuint64_t dims[2] = {d0, d1};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) d0=%llu d1=%llu ld=%llu box=%ux%u", (int)r,
+              (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)ld, box0, box1);
+    return B2_ERR_CUDA;
+  }
+  return B2_OK;
+}
+
+static int g_num_sms = 0;
+int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a,
+                          cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    B2_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    attr_done = true;
+  }
+  const int total = a.m_tiles * a.n_tiles * a.k_splits;
+  const int grid = total < num_sms() ? total : num_sms();
+  gemm_tc_kernel<BN, A_MN, B_MN><<<grid, kGemmThreads, Cfg::kSmem, stream>>>(tmA, tmB, a);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+// C[M,N] = alpha * op(A).op(B) (+bias) on bf16 operands.
+//   a_mn = 0: A is [M rows][K contiguous] (pitch lda)   1: A is [K rows][M contiguous]
+//   b_mn = 0: B is [N rows][K contiguous] (pitch ldb)   1: B is [K rows][N contiguous]
+//   epi: EPI_STORE_F32 | EPI_ATOMIC_F32 (C += ..., enables split-K) | EPI_STORE_BF16
+int gemm_bf16_tc(int a_mn, int b_mn, int M, int N, int K, float alpha, const __nv_bfloat16* A,
+                 int lda, const __nv_bfloat16* B, int ldb, void* C, int ldc, const float* bias,
+                 int epi, int k_splits_hint, cudaStream_t stream) {
+  B2_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_bf16_tc: bad shape %dx%dx%d", M, N, K);
+  int BN = N > 128 ? 256 : N > 64 ? 128 : N > 32 ? 64 : 32;
+  if (b_mn && BN < 64) BN = 64;
+  GemmArgs g;
+  g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.C = C; g.bias = bias; g.alpha = alpha; g.epi = epi;
+  g.m_tiles = cdiv(M, GM); g.n_tiles = cdiv(N, BN);
+  g.kblocks = cdiv(K, GK);
+  int splits = 1;
+  if (epi == EPI_ATOMIC_F32) {
+    splits = k_splits_hint > 0 ? k_splits_hint : 1;
+    if (k_splits_hint <= 0) {
+      const int tiles = g.m_tiles * g.n_tiles;
+      while (tiles * splits * 2 <= num_sms() && g.kblocks / (splits * 2) >= 8) splits *= 2;
+    }
+    if (splits > g.kblocks) splits = g.kblocks;
+  }
+  g.kb_per_split = cdiv(g.kblocks, splits);
+  g.k_splits = cdiv(g.kblocks, g.kb_per_split);
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!a_mn) rc = make_tmap_bf16(&tmA, A, K, M, lda, GK, GM);
+  else       rc = make_tmap_bf16(&tmA, A, M, K, lda, 64, GK);
+  if (rc) return rc;
+  if (!b_mn) rc = make_tmap_bf16(&tmB, B, K, N, ldb, GK, BN);
+  else       rc = make_tmap_bf16(&tmB, B, N, K, ldb, 64, GK);
+  if (rc) return rc;
+#define DISPATCH(BN_)                                                                         \
+  if (BN == BN_) {                                                                            \
+    if (!a_mn && !b_mn) return launch_gemm_tc<BN_, false, false>(tmA, tmB, g, stream);        \
+    if (a_mn && !b_mn) return launch_gemm_tc<BN_, true, false>(tmA, tmB, g, stream);          \
+    if (!a_mn && b_mn) { if (BN_ >= 64) return launch_gemm_tc<(BN_ >= 64 ? BN_ : 64), false, true>(tmA, tmB, g, stream); } \
+    if (a_mn && b_mn) { if (BN_ >= 64) return launch_gemm_tc<(BN_ >= 64 ? BN_ : 64), true, true>(tmA, tmB, g, stream); }   \
+  }
+  DISPATCH(256) DISPATCH(128) DISPATCH(64) DISPATCH(32)
+#undef DISPATCH
+  set_error("gemm_bf16_tc: no kernel for BN=%d", BN);
+  return B2_ERR_UNSUPPORTED;
+}
+
+// fp32 [rows, cols] (pitch ldi) -> bf16 [rows, ldo] with zero padding of cols..ldo
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, int64_t rows, int cols, int ldi,
+                                     __nv_bfloat16* __restrict__ out, int ldo) {
+  const int64_t n = rows * ldo;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / ldo;
+    const int c = (int)(i % ldo);
+    out[i] = __float2bfloat16(c < cols ? in[r * ldi + c] : 0.f);
+  }
+}
+
+int cast_f32_bf16(const float* in, int64_t rows, int cols, int ldi, __nv_bfloat16* out, int ldo,
+                  cudaStream_t stream) {
+  const int64_t n = rows * ldo;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+  if (blocks < 1) blocks = 1;
+  cast_f32_bf16_kernel<<<blocks, 256, 0, stream>>>(in, rows, cols, ldi, out, ldo);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+int gemm_simt(int transa, int transb, int M, int N, int K, float alpha, const float* A, int lda,
+              const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
+              cudaStream_t stream);
+
+}  // namespace b2
+
+using namespace b2;
+
+static inline int pad8(int x) { return (x + 7) / 8 * 8; }
+
+extern "C" size_t b2_gemm_workspace_bytes(int M, int N, int K, int precision) {
+  if (precision != B2_PREC_BF16) return 0;
+  // bf16 copies of both operands, pitches padded to 8 elements (16 B, TMA requirement)
+  const size_t a = (size_t)(M > K ? M : K) * pad8(M > K ? K : M) * 2 + (size_t)pad8(M) * pad8(K) * 2;
+  const size_t b = (size_t)pad8(N > 64 ? N : 64) * pad8(K) * 2 * 2;
+  return align_up(a, 256) + align_up(b, 256) + 1024;
+}
+
+extern "C" int b2_gemm(int transa, int transb, int M, int N, int K, float alpha, const float* A,
+                       int lda, const float* B, int ldb, float beta, float* C, int ldc,
+                       const float* bias, int precision, void* workspace, size_t workspace_bytes,
+                       b2_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B2_CHECK_ARG(A && B && C, "b2_gemm: null pointer");
+  B2_CHECK_ARG(M > 0 && N > 0 && K > 0, "b2_gemm: bad shape %dx%dx%d", M, N, K);
+  if (precision == B2_PREC_FP32)
+    return gemm_simt(transa, transb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, stream);
+  B2_CHECK_ARG(precision == B2_PREC_BF16, "b2_gemm: unknown precision %d", precision);
+  B2_CHECK_ARG(beta == 0.f || beta == 1.f, "b2_gemm(bf16): beta must be 0 or 1");
+  B2_CHECK_ARG(workspace != nullptr, "b2_gemm(bf16): workspace required");
+  // operand copies: A as stored ([M,K] or [K,M]); B as stored ([K,N] -> MN-major, [N,K] -> K-major)
+  const int a_rows = transa ? K : M, a_cols = transa ? M : K;
+  const int b_rows = transb ? N : K, b_cols = transb ? K : N;
+  const int a_ld = pad8(a_cols);
+  int b_ld = pad8(b_cols);
+  if (!transb && b_ld < 64) b_ld = 64;        // MN-major B needs a full 64-wide box
+  const size_t a_bytes = align_up((size_t)a_rows * a_ld * 2, 256);
+  const size_t b_bytes = align_up((size_t)b_rows * b_ld * 2, 256);
+  if (workspace_bytes < a_bytes + b_bytes) {
+    set_error("b2_gemm: workspace %zu < %zu", workspace_bytes, a_bytes + b_bytes);
+    return B2_ERR_WORKSPACE;
+  }
+  __nv_bfloat16* Ab = (__nv_bfloat16*)workspace;
+  __nv_bfloat16* Bb = (__nv_bfloat16*)((char*)workspace + a_bytes);
+  int rc = cast_f32_bf16(A, a_rows, a_cols, lda, Ab, a_ld, stream);
+  if (rc) return rc;
+  rc = cast_f32_bf16(B, b_rows, b_cols, ldb, Bb, b_ld, stream);
+  if (rc) return rc;
+  const int epi = (beta == 1.f) ? EPI_ATOMIC_F32 : EPI_STORE_F32;
+  return gemm_bf16_tc(transa ? 1 : 0, transb ? 0 : 1, M, N, K, alpha, Ab, a_ld, Bb, b_ld, C, ldc,
+                      bias, epi, 0, stream);
+}

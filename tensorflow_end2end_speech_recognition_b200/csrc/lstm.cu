@@ -1,0 +1,507 @@
+// Bidirectional LSTM layer (forward + BPTT) for sm_100a -- host orchestration and
+// the fp32 CUDA-core recurrence (B2_PREC_FP32, the parity path).
+//
+// Replaces tf.contrib.rnn.LSTMBlockCell / LSTMCell / BasicLSTMCell under
+// tf.nn.bidirectional_dynamic_rnn(sequence_length=...) as built by
+// models/encoders/core/blstm.py:258-332 (cell equations restated from
+// models/recurrent/layers/lstm.py:142-183, see oracle/lstm.py).
+//
+// Structure of one layer (both directions):
+//   1. time-batched input projection  G[T*B, 8H] = X . [Wx_fw | Wx_bw] + b      (GEMM)
+//   2. recurrence, T sequential steps per direction:
+//        z = G[t] + h_{t-1} . Wh ; gates ; c_t ; h_t ; length masking ; dropout
+//   backward mirrors it: BPTT recurrence producing dG[T*B, 8H], then the
+//   time-batched GEMMs dX = dG . Wx^T, dWx = X^T . dG, dWh = Hprev^T . dG,
+//   bias/peephole reductions.
+// With B2_PREC_BF16 the time-batched GEMMs run on tcgen05 (gemm_tcgen05.cu) and
+// the recurrence on the cluster/TMEM kernel (lstm_rec_tc.cu) when available.
+#include "common.cuh"
+
+namespace b2 {
+
+int gemm_simt(int transa, int transb, int M, int N, int K, float alpha, const float* A, int lda,
+              const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
+              cudaStream_t stream);
+int gemm_bf16_tc(int a_mn, int b_mn, int M, int N, int K, float alpha, const __nv_bfloat16* A,
+                 int lda, const __nv_bfloat16* B, int ldb, void* C, int ldc, const float* bias,
+                 int epi, int k_splits_hint, cudaStream_t stream);
+int cast_f32_bf16(const float* in, int64_t rows, int cols, int ldi, __nv_bfloat16* out, int ldo,
+                  cudaStream_t stream);
+
+// ---------------------------------------------------------------------------
+// reserve layout (saved for backward), all fp32:
+//   gates [T][B][2][4][H]   post-activation i, g, f, o
+//   cs    [T][B][2][H]      cell state after step t (carried through inactive steps)
+//   hs    [T][B][2][H]      emitted h before dropout (0 for inactive steps)
+// ---------------------------------------------------------------------------
+struct Reserve {
+  float* gates; float* cs; float* hs;
+};
+static size_t reserve_layout(const b2_lstm_desc* d, void* base, Reserve* r) {
+  const size_t n = (size_t)d->T * d->B * 2 * d->H;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+  const size_t og = take(n * 4 * sizeof(float));
+  const size_t oc = take(n * sizeof(float));
+  const size_t oh = take(n * sizeof(float));
+  if (r) {
+    char* p = (char*)base;
+    r->gates = (float*)(p + og); r->cs = (float*)(p + oc); r->hs = (float*)(p + oh);
+  }
+  return off;
+}
+
+struct Work {
+  float* G;        // [T*B, 8H] gate pre-activations (fwd) / dG (bwd)
+  float* hstate;   // [2 parity][2 dir][B][H]
+  float* cstate;   // [2 dir][B][H]   (fwd: c ; bwd: dc)
+  __nv_bfloat16* xb;   // bf16 operand copies for the tcgen05 GEMMs
+  __nv_bfloat16* wb;
+  __nv_bfloat16* gb;
+};
+static size_t pad8z(size_t x) { return (x + 7) / 8 * 8; }
+static size_t work_layout(const b2_lstm_desc* d, void* base, Work* w) {
+  const size_t TB = (size_t)d->T * d->B;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
+  const size_t oG = take(TB * 8 * d->H * sizeof(float));
+  const size_t oh = take((size_t)2 * 2 * d->B * d->H * sizeof(float));
+  const size_t oc = take((size_t)2 * d->B * d->H * sizeof(float));
+  size_t oxb = 0, owb = 0, ogb = 0;
+  if (d->precision == B2_PREC_BF16) {
+    const size_t din = pad8z((size_t)(d->D_in > 2 * d->H ? d->D_in : 2 * d->H));
+    oxb = take(TB * din * 2);                                   // X or Hs as bf16
+    owb = take((size_t)(d->D_in + d->H + 64) * 8 * d->H * 2);    // weights (both dirs) as bf16
+    ogb = take(TB * 8 * d->H * 2);                               // dG as bf16
+  }
+  if (w) {
+    char* p = (char*)base;
+    w->G = (float*)(p + oG); w->hstate = (float*)(p + oh); w->cstate = (float*)(p + oc);
+    w->xb = (__nv_bfloat16*)(p + oxb); w->wb = (__nv_bfloat16*)(p + owb);
+    w->gb = (__nv_bfloat16*)(p + ogb);
+  }
+  return off;
+}
+
+// ---------------------------------------------------------------------------
+// fp32 recurrence step kernels.  CTA tile = 16 batch x 16 units (x 4 gates),
+// 256 threads, thread (b,u).  grid = (H/16, ceil(B/16), 2 directions).
+// ---------------------------------------------------------------------------
+constexpr int RB = 16, RU = 16, RK = 32;
+
+struct StepArgs {
+  int T, B, D_in, H, step;          // step index i: fw works on t=i, bw on t=T-1-i
+  int use_peephole; float forget_bias, cell_clip, keep_prob; unsigned long long seed;
+  const float* kernel[2]; const float* wi[2]; const float* wf[2]; const float* wo[2];
+  const int* seq_len;
+  const float* G;                   // [T,B,8H]
+  float* hstate; float* cstate;
+  float* y;                         // [T,B,2H]
+  float* gates; float* cs; float* hs;   // reserve (may be null when !need_backward)
+};
+
+__global__ void __launch_bounds__(256)
+lstm_fwd_step_kernel(const StepArgs a) {
+  __shared__ float Ws[RK][4 * RU + 1];
+  __shared__ float Hs[RB][RK + 1];
+  const int dir = blockIdx.z;
+  const int u0 = blockIdx.x * RU, b0 = blockIdx.y * RB;
+  const int tu = threadIdx.x & 15, tb = threadIdx.x >> 4;
+  const int u = u0 + tu, b = b0 + tb;
+  const int H = a.H, B = a.B;
+  const int t = dir == 0 ? a.step : a.T - 1 - a.step;
+  const int par = a.step & 1;
+  const float* hprev = a.hstate + ((size_t)(par * 2 + dir) * B) * H;
+  float* hnext = a.hstate + ((size_t)((par ^ 1) * 2 + dir) * B) * H;
+  const float* Wh = a.kernel[dir] + (size_t)a.D_in * 4 * H;     // rows D_in.. are the h rows
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k0 = 0; k0 < H; k0 += RK) {
+    // Ws[k][g*RU + uu] = Wh[k0+k][g*H + u0+uu]   (RK x 64 = 2048 elems, 8 per thread)
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int e = threadIdx.x + r * 256;
+      const int col = e & 63, k = e >> 6;
+      const int g = col >> 4, uu = col & 15;
+      float v = 0.f;
+      if (k0 + k < H && u0 + uu < H) v = Wh[(size_t)(k0 + k) * 4 * H + g * H + u0 + uu];
+      Ws[k][col] = v;
+    }
+    // Hs[bb][k] = hprev[b0+bb][k0+k]   (16 x 32 = 512 elems, 2 per thread)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int e = threadIdx.x + r * 256;
+      const int k = e & 31, bb = e >> 5;
+      float v = 0.f;
+      if (b0 + bb < B && k0 + k < H) v = hprev[(size_t)(b0 + bb) * H + k0 + k];
+      Hs[bb][k] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < RK; ++k) {
+      const float hv = Hs[tb][k];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) acc[g] = fmaf(hv, Ws[k][g * RU + tu], acc[g]);
+    }
+    __syncthreads();
+  }
+  if (u >= H || b >= B) return;
+  const size_t cidx = ((size_t)dir * B + b) * H + u;
+  const bool active = t < a.seq_len[b];
+  const float c_prev = a.cstate[cidx];
+  const float h_prev = hprev[(size_t)b * H + u];
+  const size_t row = (size_t)t * B + b;
+  float h_out = 0.f, c_new = c_prev, h_state = h_prev;
+  float gi = 0.f, gg = 0.f, gf = 0.f, go = 0.f;
+  if (active) {
+    const float* Gr = a.G + row * 8 * H + (size_t)dir * 4 * H;
+    float zi = Gr[u] + acc[0], zg = Gr[H + u] + acc[1];
+    float zf = Gr[2 * H + u] + acc[2] + a.forget_bias, zo = Gr[3 * H + u] + acc[3];
+    if (a.use_peephole) { zi += a.wi[dir][u] * c_prev; zf += a.wf[dir][u] * c_prev; }
+    gi = sigmoidf_(zi); gg = tanhf_(zg); gf = sigmoidf_(zf);
+    c_new = gf * c_prev + gi * gg;
+    if (a.cell_clip > 0.f) c_new = fminf(fmaxf(c_new, -a.cell_clip), a.cell_clip);
+    if (a.use_peephole) zo += a.wo[dir][u] * c_new;
+    go = sigmoidf_(zo);
+    h_out = go * tanhf_(c_new);
+    h_state = h_out;
+  }
+  a.cstate[cidx] = c_new;
+  hnext[(size_t)b * H + u] = h_state;
+  const size_t oidx = row * 2 * H + (size_t)dir * H + u;
+  float yv = h_out;
+  if (a.keep_prob < 1.f && active)
+    yv = dropout_keep(a.seed, oidx, a.keep_prob) ? h_out / a.keep_prob : 0.f;
+  a.y[oidx] = yv;
+  if (a.gates) {
+    float* gp = a.gates + (row * 2 + dir) * 4 * H;
+    gp[u] = gi; gp[H + u] = gg; gp[2 * H + u] = gf; gp[3 * H + u] = go;
+    a.cs[(row * 2 + dir) * H + u] = c_new;
+    a.hs[(row * 2 + dir) * H + u] = h_out;
+  }
+}
+
+struct BwdStepArgs {
+  int T, B, D_in, H, step;          // step i: fw works on t=T-1-i, bw on t=i
+  int use_peephole; float cell_clip, keep_prob; unsigned long long seed;
+  const float* kernel[2]; const float* wi[2]; const float* wf[2]; const float* wo[2];
+  const int* seq_len;
+  const float* dy;                  // [T,B,2H]
+  const float* gates; const float* cs;
+  float* dG;                        // [T,B,8H]
+  float* dcstate;                   // [2][B][H]
+  const float* dfinal;              // [4,B,H] d(c_fw,h_fw,c_bw,h_bw) or null
+};
+
+__global__ void __launch_bounds__(256)
+lstm_bwd_step_kernel(const BwdStepArgs a) {
+  __shared__ float Ws[RU][RK + 1];
+  __shared__ float Zs[RB][RK + 1];
+  const int dir = blockIdx.z;
+  const int u0 = blockIdx.x * RU, b0 = blockIdx.y * RB;
+  const int tu = threadIdx.x & 15, tb = threadIdx.x >> 4;
+  const int u = u0 + tu, b = b0 + tb;
+  const int H = a.H, B = a.B, T = a.T;
+  const int t = dir == 0 ? T - 1 - a.step : a.step;
+  const int tn = dir == 0 ? t + 1 : t - 1;          // the step processed just before (in BPTT order)
+  const float* Wh = a.kernel[dir] + (size_t)a.D_in * 4 * H;
+  float acc = 0.f;
+  if (tn >= 0 && tn < T) {
+    const float* dzn = a.dG + (size_t)tn * B * 8 * H + (size_t)dir * 4 * H;   // row b: + b*8H
+    for (int k0 = 0; k0 < 4 * H; k0 += RK) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int e = threadIdx.x + r * 256;
+        const int k = e & 31, rr = e >> 5;
+        float wv = 0.f, zv = 0.f;
+        if (u0 + rr < H && k0 + k < 4 * H) wv = Wh[(size_t)(u0 + rr) * 4 * H + k0 + k];
+        if (b0 + rr < B && k0 + k < 4 * H) zv = dzn[(size_t)(b0 + rr) * 8 * H + k0 + k];
+        Ws[rr][k] = wv;
+        Zs[rr][k] = zv;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < RK; ++k) acc = fmaf(Zs[tb][k], Ws[tu][k], acc);
+      __syncthreads();
+    }
+  }
+  if (u >= H || b >= B) return;
+  const int len = a.seq_len[b];
+  const bool active = t < len;
+  const size_t row = (size_t)t * B + b;
+  float* dz = a.dG + row * 8 * H + (size_t)dir * 4 * H;
+  if (!active) {
+    dz[u] = 0.f; dz[H + u] = 0.f; dz[2 * H + u] = 0.f; dz[3 * H + u] = 0.f;
+    return;
+  }
+  const bool nb_active = (tn >= 0 && tn < T && tn < len);
+  const size_t cidx = ((size_t)dir * B + b) * H + u;
+  float dh_in, dc_in;
+  if (nb_active) { dh_in = acc; dc_in = a.dcstate[cidx]; }
+  else {
+    dh_in = a.dfinal ? a.dfinal[((size_t)(dir * 2 + 1) * B + b) * H + u] : 0.f;
+    dc_in = a.dfinal ? a.dfinal[((size_t)(dir * 2 + 0) * B + b) * H + u] : 0.f;
+  }
+  const size_t oidx = row * 2 * H + (size_t)dir * H + u;
+  float dyv = a.dy[oidx];
+  if (a.keep_prob < 1.f) dyv = dropout_keep(a.seed, oidx, a.keep_prob) ? dyv / a.keep_prob : 0.f;
+  const float dh = dyv + dh_in;
+  const float* gp = a.gates + (row * 2 + dir) * 4 * H;
+  const float gi = gp[u], gg = gp[H + u], gf = gp[2 * H + u], go = gp[3 * H + u];
+  const float c = a.cs[(row * 2 + dir) * H + u];
+  const int tp = dir == 0 ? t - 1 : t + 1;           // previous step in forward order
+  float c_prev = 0.f;
+  if (tp >= 0 && tp < T && tp < len) c_prev = a.cs[(((size_t)tp * B + b) * 2 + dir) * H + u];
+  const float tc = tanhf_(c);
+  const float dzo = dh * tc * go * (1.f - go);
+  float dc = dc_in + dh * go * (1.f - tc * tc);
+  if (a.use_peephole) dc += dzo * a.wo[dir][u];
+  if (a.cell_clip > 0.f && fabsf(c) >= a.cell_clip) dc = 0.f;   // clip_by_value passes no grad outside
+  const float dzi = dc * gg * gi * (1.f - gi);
+  const float dzg = dc * gi * (1.f - gg * gg);
+  const float dzf = dc * c_prev * gf * (1.f - gf);
+  float dc_prev = dc * gf;
+  if (a.use_peephole) dc_prev += dzi * a.wi[dir][u] + dzf * a.wf[dir][u];
+  a.dcstate[cidx] = dc_prev;
+  dz[u] = dzi; dz[H + u] = dzg; dz[2 * H + u] = dzf; dz[3 * H + u] = dzo;
+}
+
+// peephole gradients: dwi[u] += sum_{t,b} dz_i * c_prev ; dwf likewise ; dwo += dz_o * c
+// grid = (ceil(H/32), slabs, 2 dirs); block 256 = 8 row-lanes x 32 units
+__global__ void __launch_bounds__(256)
+peephole_grad_kernel(const float* __restrict__ dG, const float* __restrict__ cs,
+                     const int* __restrict__ seq_len, int T, int B, int H,
+                     float* dwi0, float* dwf0, float* dwo0, float* dwi1, float* dwf1, float* dwo1) {
+  __shared__ float sh[3][8][33];
+  const int dir = blockIdx.z;
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  const int u = blockIdx.x * 32 + lane;
+  float si = 0.f, sf = 0.f, so = 0.f;
+  if (u < H) {
+    const int64_t rows = (int64_t)T * B;
+    for (int64_t r = (int64_t)blockIdx.y * 8 + wy; r < rows; r += (int64_t)gridDim.y * 8) {
+      const int t = (int)(r / B), b = (int)(r % B);
+      const int len = seq_len[b];
+      if (t >= len) continue;
+      const float* dz = dG + r * 8 * H + (size_t)dir * 4 * H;
+      const float c = cs[(r * 2 + dir) * H + u];
+      const int tp = dir == 0 ? t - 1 : t + 1;
+      float cp = 0.f;
+      if (tp >= 0 && tp < T && tp < len) cp = cs[(((int64_t)tp * B + b) * 2 + dir) * H + u];
+      si = fmaf(dz[u], cp, si);
+      sf = fmaf(dz[2 * H + u], cp, sf);
+      so = fmaf(dz[3 * H + u], c, so);
+    }
+  }
+  sh[0][wy][lane] = si; sh[1][wy][lane] = sf; sh[2][wy][lane] = so;
+  __syncthreads();
+  if (wy == 0 && u < H) {
+#pragma unroll
+    for (int j = 1; j < 8; ++j) { si += sh[0][j][lane]; sf += sh[1][j][lane]; so += sh[2][j][lane]; }
+    atomicAdd((dir ? dwi1 : dwi0) + u, si);
+    atomicAdd((dir ? dwf1 : dwf0) + u, sf);
+    atomicAdd((dir ? dwo1 : dwo0) + u, so);
+  }
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+static int check_desc(const b2_lstm_desc* d) {
+  B2_CHECK_ARG(d != nullptr, "lstm: null descriptor");
+  B2_CHECK_ARG(d->T > 0 && d->B > 0 && d->D_in > 0 && d->H > 0, "lstm: bad shape T=%d B=%d D=%d H=%d",
+               d->T, d->B, d->D_in, d->H);
+  B2_CHECK_ARG(d->keep_prob > 0.f && d->keep_prob <= 1.f, "lstm: keep_prob %f out of (0,1]",
+               d->keep_prob);
+  B2_CHECK_ARG(d->precision == B2_PREC_FP32 || d->precision == B2_PREC_BF16,
+               "lstm: unknown precision %d", d->precision);
+  return B2_OK;
+}
+
+extern "C" size_t b2_blstm_reserve_bytes(const b2_lstm_desc* d) {
+  return d ? reserve_layout(d, nullptr, nullptr) : 0;
+}
+extern "C" size_t b2_blstm_workspace_bytes(const b2_lstm_desc* d) {
+  return d ? work_layout(d, nullptr, nullptr) : 0;
+}
+
+extern "C" int b2_blstm_layer_forward(const b2_lstm_desc* d, const float* x, const int32_t* seq_len,
+                                      const b2_lstm_params* fw, const b2_lstm_params* bw, float* y,
+                                      float* final_state, void* reserve, void* workspace,
+                                      size_t workspace_bytes, b2_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = check_desc(d);
+  if (rc) return rc;
+  B2_CHECK_ARG(x && seq_len && fw && bw && y && workspace, "blstm_forward: null pointer");
+  B2_CHECK_ARG(!d->need_backward || reserve, "blstm_forward: need_backward without reserve");
+  B2_CHECK_ARG(!d->use_peephole || (fw->w_i_diag && fw->w_f_diag && fw->w_o_diag && bw->w_i_diag &&
+                                    bw->w_f_diag && bw->w_o_diag),
+               "blstm_forward: peephole weights missing");
+  Work w;
+  const size_t need = work_layout(d, workspace, &w);
+  if (workspace_bytes < need) { set_error("blstm_forward: workspace %zu < %zu", workspace_bytes, need); return B2_ERR_WORKSPACE; }
+  Reserve r = {nullptr, nullptr, nullptr};
+  if (d->need_backward) reserve_layout(d, reserve, &r);
+  const int T = d->T, B = d->B, D = d->D_in, H = d->H;
+  const int TB = T * B;
+  const b2_lstm_params* P[2] = {fw, bw};
+
+  // 1. input projection, both directions into G [TB, 8H]
+  for (int dir = 0; dir < 2; ++dir) {
+    float* Gd = w.G + (size_t)dir * 4 * H;
+    if (d->precision == B2_PREC_BF16) {
+      const int ldx = (int)pad8z(D);
+      if (dir == 0) { rc = cast_f32_bf16(x, TB, D, D, w.xb, ldx, stream); if (rc) return rc; }
+      __nv_bfloat16* wb = w.wb + (size_t)dir * (D + 0) * 4 * H;
+      rc = cast_f32_bf16(P[dir]->kernel, D, 4 * H, 4 * H, wb, 4 * H, stream);
+      if (rc) return rc;
+      rc = gemm_bf16_tc(0, 1, TB, 4 * H, D, 1.f, w.xb, ldx, wb, 4 * H, Gd, 8 * H, P[dir]->bias,
+                        0 /*store f32*/, 0, stream);
+    } else {
+      rc = gemm_simt(0, 0, TB, 4 * H, D, 1.f, x, D, P[dir]->kernel, 4 * H, 0.f, Gd, 8 * H,
+                     P[dir]->bias, stream);
+    }
+    if (rc) return rc;
+  }
+  // 2. recurrence
+  B2_CUDA(cudaMemsetAsync(w.hstate, 0, (size_t)2 * 2 * B * H * sizeof(float), stream));
+  B2_CUDA(cudaMemsetAsync(w.cstate, 0, (size_t)2 * B * H * sizeof(float), stream));
+  StepArgs a;
+  a.T = T; a.B = B; a.D_in = D; a.H = H;
+  a.use_peephole = d->use_peephole; a.forget_bias = d->forget_bias; a.cell_clip = d->cell_clip;
+  a.keep_prob = d->keep_prob; a.seed = d->dropout_seed;
+  for (int dir = 0; dir < 2; ++dir) {
+    a.kernel[dir] = P[dir]->kernel; a.wi[dir] = P[dir]->w_i_diag; a.wf[dir] = P[dir]->w_f_diag;
+    a.wo[dir] = P[dir]->w_o_diag;
+  }
+  a.seq_len = seq_len; a.G = w.G; a.hstate = w.hstate; a.cstate = w.cstate; a.y = y;
+  a.gates = r.gates; a.cs = r.cs; a.hs = r.hs;
+  dim3 grid(cdiv(H, RU), cdiv(B, RB), 2);
+  for (int i = 0; i < T; ++i) {
+    a.step = i;
+    lstm_fwd_step_kernel<<<grid, 256, 0, stream>>>(a);
+  }
+  B2_LAUNCH_CHECK();
+  if (final_state) {
+    // hstate parity after T steps is T&1; layout [c_fw, h_fw, c_bw, h_bw] each [B,H]
+    const float* hfin = w.hstate + (size_t)((T & 1) * 2) * B * H;
+    const size_t n = (size_t)B * H * sizeof(float);
+    B2_CUDA(cudaMemcpyAsync(final_state, w.cstate, n, cudaMemcpyDeviceToDevice, stream));
+    B2_CUDA(cudaMemcpyAsync(final_state + (size_t)B * H, hfin, n, cudaMemcpyDeviceToDevice, stream));
+    B2_CUDA(cudaMemcpyAsync(final_state + (size_t)2 * B * H, w.cstate + (size_t)B * H, n, cudaMemcpyDeviceToDevice, stream));
+    B2_CUDA(cudaMemcpyAsync(final_state + (size_t)3 * B * H, hfin + (size_t)B * H, n, cudaMemcpyDeviceToDevice, stream));
+  }
+  return B2_OK;
+}
+
+extern "C" int b2_blstm_layer_backward(const b2_lstm_desc* d, const float* x, const int32_t* seq_len,
+                                       const b2_lstm_params* fw, const b2_lstm_params* bw,
+                                       const float* dy, const void* reserve, float* dx,
+                                       const b2_lstm_grads* g_fw, const b2_lstm_grads* g_bw,
+                                       void* workspace, size_t workspace_bytes, b2_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = check_desc(d);
+  if (rc) return rc;
+  B2_CHECK_ARG(x && seq_len && fw && bw && dy && reserve && g_fw && g_bw && workspace,
+               "blstm_backward: null pointer");
+  Work w;
+  const size_t need = work_layout(d, workspace, &w);
+  if (workspace_bytes < need) { set_error("blstm_backward: workspace %zu < %zu", workspace_bytes, need); return B2_ERR_WORKSPACE; }
+  Reserve r;
+  reserve_layout(d, (void*)reserve, &r);
+  const int T = d->T, B = d->B, D = d->D_in, H = d->H;
+  const int TB = T * B;
+  const b2_lstm_params* P[2] = {fw, bw};
+  const b2_lstm_grads* Gr[2] = {g_fw, g_bw};
+
+  // 1. BPTT recurrence -> dG [TB, 8H]
+  B2_CUDA(cudaMemsetAsync(w.cstate, 0, (size_t)2 * B * H * sizeof(float), stream));
+  BwdStepArgs a;
+  a.T = T; a.B = B; a.D_in = D; a.H = H;
+  a.use_peephole = d->use_peephole; a.cell_clip = d->cell_clip; a.keep_prob = d->keep_prob;
+  a.seed = d->dropout_seed;
+  for (int dir = 0; dir < 2; ++dir) {
+    a.kernel[dir] = P[dir]->kernel; a.wi[dir] = P[dir]->w_i_diag; a.wf[dir] = P[dir]->w_f_diag;
+    a.wo[dir] = P[dir]->w_o_diag;
+  }
+  a.seq_len = seq_len; a.dy = dy; a.gates = r.gates; a.cs = r.cs; a.dG = w.G; a.dcstate = w.cstate;
+  a.dfinal = nullptr;
+  dim3 grid(cdiv(H, RU), cdiv(B, RB), 2);
+  for (int i = 0; i < T; ++i) {
+    a.step = i;
+    lstm_bwd_step_kernel<<<grid, 256, 0, stream>>>(a);
+  }
+  B2_LAUNCH_CHECK();
+
+  // 2. bias + peephole reductions
+  for (int dir = 0; dir < 2; ++dir) {
+    rc = b2_colsum(w.G + (size_t)dir * 4 * H, TB, 4 * H, 8 * H, Gr[dir]->bias, 1, stream_);
+    if (rc) return rc;
+  }
+  if (d->use_peephole) {
+    int slabs = cdiv(TB, 64); if (slabs > 128) slabs = 128;
+    dim3 pg(cdiv(H, 32), slabs, 2);
+    peephole_grad_kernel<<<pg, 256, 0, stream>>>(w.G, r.cs, seq_len, T, B, H, g_fw->w_i_diag,
+                                                g_fw->w_f_diag, g_fw->w_o_diag, g_bw->w_i_diag,
+                                                g_bw->w_f_diag, g_bw->w_o_diag);
+    B2_LAUNCH_CHECK();
+  }
+
+  // 3. time-batched GEMMs
+  const bool tc = d->precision == B2_PREC_BF16;
+  if (tc) {
+    rc = cast_f32_bf16(w.G, TB, 8 * H, 8 * H, w.gb, 8 * H, stream);
+    if (rc) return rc;
+  }
+  for (int dir = 0; dir < 2; ++dir) {
+    const float* dGd = w.G + (size_t)dir * 4 * H;
+    const __nv_bfloat16* dGb = w.gb + (size_t)dir * 4 * H;
+    // dX (+)= dG_dir . Wx_dir^T            [TB,4H] x [4H,D]
+    if (dx) {
+      if (tc) {
+        __nv_bfloat16* wb = w.wb + (size_t)dir * D * 4 * H;
+        rc = cast_f32_bf16(P[dir]->kernel, D, 4 * H, 4 * H, wb, 4 * H, stream);
+        if (rc) return rc;
+        if (dir == 0) B2_CUDA(cudaMemsetAsync(dx, 0, (size_t)TB * D * sizeof(float), stream));
+        rc = gemm_bf16_tc(0, 0, TB, D, 4 * H, 1.f, dGb, 8 * H, wb, 4 * H, dx, D, nullptr,
+                          1 /*atomic*/, 1, stream);
+      } else {
+        rc = gemm_simt(0, 1, TB, D, 4 * H, 1.f, dGd, 8 * H, P[dir]->kernel, 4 * H,
+                       dir == 0 ? 0.f : 1.f, dx, D, nullptr, stream);
+      }
+      if (rc) return rc;
+    }
+    // dWx_dir += X^T . dG_dir              [D,TB] x [TB,4H]
+    // dWh_dir += Hprev^T . dG_dir          [H,(T-1)B] x [(T-1)B,4H]   (hs shifted one step)
+    const float* hs_a = r.hs + (dir == 0 ? 0 : (size_t)B * 2 * H) + (size_t)dir * H;
+    const float* dG_h = dGd + (dir == 0 ? (size_t)B * 8 * H : 0);
+    if (tc) {
+      const int ldx = (int)pad8z(D);
+      rc = cast_f32_bf16(x, TB, D, D, w.xb, ldx, stream);
+      if (rc) return rc;
+      rc = gemm_bf16_tc(1, 1, D, 4 * H, TB, 1.f, w.xb, ldx, dGb, 8 * H, Gr[dir]->kernel, 4 * H,
+                        nullptr, 1, 0, stream);
+      if (rc) return rc;
+      if (T > 1) {
+        // bf16 copy of this direction's hs columns, compact [TB, H]
+        rc = cast_f32_bf16(r.hs + (size_t)dir * H, TB, H, 2 * H, w.xb, H, stream);
+        if (rc) return rc;
+        const __nv_bfloat16* ha = w.xb + (dir == 0 ? 0 : (size_t)B * H);
+        const __nv_bfloat16* gb = dGb + (dir == 0 ? (size_t)B * 8 * H : 0);
+        rc = gemm_bf16_tc(1, 1, H, 4 * H, (T - 1) * B, 1.f, ha, H, gb, 8 * H,
+                          Gr[dir]->kernel + (size_t)D * 4 * H, 4 * H, nullptr, 1, 0, stream);
+        if (rc) return rc;
+      }
+    } else {
+      rc = gemm_simt(1, 0, D, 4 * H, TB, 1.f, x, D, dGd, 8 * H, 1.f, Gr[dir]->kernel, 4 * H,
+                     nullptr, stream);
+      if (rc) return rc;
+      if (T > 1) {
+        rc = gemm_simt(1, 0, H, 4 * H, (T - 1) * B, 1.f, hs_a, 2 * H, dG_h, 8 * H, 1.f,
+                       Gr[dir]->kernel + (size_t)D * 4 * H, 4 * H, nullptr, stream);
+        if (rc) return rc;
+      }
+    }
+  }
+  return B2_OK;
+}
