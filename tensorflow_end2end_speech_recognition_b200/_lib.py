@@ -1,0 +1,85 @@
+"""ctypes binding of the C ABI declared in ``include/b2asr.h``.
+
+The shared library is the product's only arithmetic back-end.  There is no CPU
+fallback: if ``libb2asr.so`` is missing or a call fails, a ``RuntimeError`` is
+raised (see INTEGRATION.md for the build step).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb2asr.so")
+
+PREC_FP32, PREC_BF16 = 0, 1
+OPT_KINDS = {"sgd": 0, "momentum": 1, "nestrov": 2, "adagrad": 3, "adadelta": 4, "adam": 5,
+             "rmsprop": 6}
+
+
+class LstmDesc(C.Structure):
+    _fields_ = [("T", C.c_int32), ("B", C.c_int32), ("D_in", C.c_int32), ("H", C.c_int32),
+                ("use_peephole", C.c_int32), ("forget_bias", C.c_float), ("cell_clip", C.c_float),
+                ("keep_prob", C.c_float), ("dropout_seed", C.c_uint64), ("precision", C.c_int32),
+                ("need_backward", C.c_int32)]
+
+
+class LstmParams(C.Structure):
+    _fields_ = [("kernel", C.c_void_p), ("bias", C.c_void_p), ("w_i_diag", C.c_void_p),
+                ("w_f_diag", C.c_void_p), ("w_o_diag", C.c_void_p)]
+
+
+LstmGrads = LstmParams  # same layout (non-const pointers)
+
+_p, _i, _f, _sz, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_int64
+
+# name -> (restype, argtypes); mirrors include/b2asr.h one to one
+PROTOTYPES = {
+    "b2_version": (_i, []),
+    "b2_last_error": (C.c_char_p, []),
+    "b2_device_is_sm100": (_i, []),
+    "b2_ctc_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "b2_ctc_loss_grad": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _sz, _p]),
+    "b2_ctc_greedy_decode": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "b2_ctc_beam_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "b2_ctc_beam_decode": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
+    "b2_softmax_rows": (_i, [_p, _p, _i64, _i, _p]),
+    "b2_gemm_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "b2_gemm": (_i, [_i, _i, _i, _i, _i, _f, _p, _i, _p, _i, _f, _p, _i, _p, _i, _p, _sz, _p]),
+    "b2_blstm_reserve_bytes": (_sz, [C.POINTER(LstmDesc)]),
+    "b2_blstm_workspace_bytes": (_sz, [C.POINTER(LstmDesc)]),
+    "b2_blstm_layer_forward": (_i, [C.POINTER(LstmDesc), _p, _p, C.POINTER(LstmParams),
+                                    C.POINTER(LstmParams), _p, _p, _p, _p, _sz, _p]),
+    "b2_blstm_layer_backward": (_i, [C.POINTER(LstmDesc), _p, _p, C.POINTER(LstmParams),
+                                     C.POINTER(LstmParams), _p, _p, _p, C.POINTER(LstmGrads),
+                                     C.POINTER(LstmGrads), _p, _sz, _p]),
+    "b2_transpose_01": (_i, [_p, _p, _i, _i, _i, _p]),
+    "b2_colsum": (_i, [_p, _i64, _i, _i, _p, _i, _p]),
+    "b2_clip_by_norm_multi": (_i, [_p, _p, _i, _f, _f, _p, _p]),
+    "b2_optimizer_step_multi": (_i, [_i, _p, _p, _p, _p, _p, _i, _f, _i64, _p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libb2asr.so (once) and attach prototypes.  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libb2asr.so not found at %s -- build it with "
+            "`python -m tensorflow_end2end_speech_recognition_b200.build` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)      # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().b2_last_error().decode("utf-8", "replace")
+        raise RuntimeError("%s failed (%d): %s" % (what, rc, msg))

@@ -1,0 +1,242 @@
+"""Tensor-level wrappers over the C ABI.  torch tensors are only containers
+(device memory + stream); every FLOP happens in libb2asr.so."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import LstmDesc, LstmParams, PREC_BF16, PREC_FP32  # noqa: F401
+
+_ws_cache = {}
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("b2asr ops need CUDA tensors (no CPU fallback)")
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def workspace(name, nbytes, device):
+    """Grow-only cached scratch buffer per (name, device)."""
+    key = (name, str(device))
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def pack_labels(labels):
+    """list of int sequences -> (flat int32, offsets int32[B+1], max_len)."""
+    lens = [len(l) for l in labels]
+    offs = np.zeros(len(labels) + 1, dtype=np.int32)
+    offs[1:] = np.cumsum(lens)
+    flat = np.zeros(max(int(offs[-1]), 1), dtype=np.int32)
+    if offs[-1] > 0:
+        flat[:offs[-1]] = np.concatenate([np.asarray(l, dtype=np.int32) for l in labels if len(l)])
+    return flat, offs, (max(lens) if lens else 0)
+
+
+def ctc_loss_grad(logits, labels_flat, label_offsets, seq_len, max_label_len, blank=None,
+                  ignore_longer=True, grad_scale=1.0, need_grad=True):
+    """logits [T,B,C] f32 cuda; labels_flat/label_offsets/seq_len int32 cuda.
+    Returns (loss [B], grad [T,B,C] or None)."""
+    lib = _lib.load()
+    _require_cuda(logits, labels_flat, label_offsets, seq_len)
+    assert logits.dtype == torch.float32 and logits.is_contiguous()
+    T, B, Cc = logits.shape
+    if blank is None:
+        blank = Cc - 1
+    loss = torch.empty(B, dtype=torch.float32, device=logits.device)
+    grad = torch.empty_like(logits) if need_grad else None
+    nbytes = lib.b2_ctc_workspace_bytes(T, B, Cc, int(max_label_len))
+    ws = workspace("ctc", nbytes, logits.device)
+    rc = lib.b2_ctc_loss_grad(_ptr(logits), _ptr(labels_flat), _ptr(label_offsets), _ptr(seq_len),
+                              T, B, Cc, int(blank), int(max_label_len), int(bool(ignore_longer)),
+                              float(grad_scale), _ptr(loss), _ptr(grad), _ptr(ws), nbytes, _stream())
+    _lib.check(rc, "b2_ctc_loss_grad")
+    return loss, grad
+
+
+def ctc_greedy_decode(logits, seq_len, blank=None):
+    """logits [T,B,C] -> (labels [B,T] int32 padded -1, lengths [B] int32)."""
+    lib = _lib.load()
+    _require_cuda(logits, seq_len)
+    T, B, Cc = logits.shape
+    if blank is None:
+        blank = Cc - 1
+    out = torch.empty((B, T), dtype=torch.int32, device=logits.device)
+    n = torch.empty(B, dtype=torch.int32, device=logits.device)
+    rc = lib.b2_ctc_greedy_decode(_ptr(logits.contiguous()), _ptr(seq_len), T, B, Cc, int(blank),
+                                  _ptr(out), _ptr(n), _stream())
+    _lib.check(rc, "b2_ctc_greedy_decode")
+    return out, n
+
+
+def ctc_beam_decode(log_probs, seq_len, beam_width, blank=None):
+    """log_probs [B,T,C] natural-log posteriors -> (labels [B,T], lengths [B], score [B])."""
+    lib = _lib.load()
+    _require_cuda(log_probs, seq_len)
+    B, T, Cc = log_probs.shape
+    if blank is None:
+        blank = Cc - 1
+    out = torch.empty((B, T), dtype=torch.int32, device=log_probs.device)
+    n = torch.empty(B, dtype=torch.int32, device=log_probs.device)
+    score = torch.empty(B, dtype=torch.float32, device=log_probs.device)
+    nbytes = lib.b2_ctc_beam_workspace_bytes(T, B, Cc, int(beam_width))
+    ws = workspace("beam", nbytes, log_probs.device)
+    rc = lib.b2_ctc_beam_decode(_ptr(log_probs.contiguous()), _ptr(seq_len), T, B, Cc, int(blank),
+                                int(beam_width), _ptr(out), _ptr(n), _ptr(score), _ptr(ws), nbytes,
+                                _stream())
+    _lib.check(rc, "b2_ctc_beam_decode")
+    return out, n, score
+
+
+def softmax_rows(x):
+    lib = _lib.load()
+    _require_cuda(x)
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    Cc = x.shape[-1]
+    rc = lib.b2_softmax_rows(_ptr(x), _ptr(y), x.numel() // Cc, Cc, _stream())
+    _lib.check(rc, "b2_softmax_rows")
+    return y
+
+
+def gemm(A, B, transa=False, transb=False, bias=None, precision=PREC_FP32, out=None, beta=0.0,
+         alpha=1.0):
+    """C = alpha*op(A).op(B) + beta*C + bias.  2-D f32 cuda tensors (row-major, may be strided rows)."""
+    lib = _lib.load()
+    _require_cuda(A, B, bias, out)
+    assert A.dtype == torch.float32 and B.dtype == torch.float32
+    assert A.stride(1) == 1 and B.stride(1) == 1
+    M, K = (A.shape[1], A.shape[0]) if transa else (A.shape[0], A.shape[1])
+    N = B.shape[0] if transb else B.shape[1]
+    Kb = B.shape[1] if transb else B.shape[0]
+    assert K == Kb, "inner dimensions differ"
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+        assert beta == 0.0
+    nbytes = lib.b2_gemm_workspace_bytes(M, N, K, precision)
+    ws = workspace("gemm", nbytes, A.device) if nbytes else None
+    rc = lib.b2_gemm(int(transa), int(transb), M, N, K, float(alpha), _ptr(A), A.stride(0), _ptr(B),
+                     B.stride(0), float(beta), _ptr(out), out.stride(0), _ptr(bias), int(precision),
+                     _ptr(ws), nbytes, _stream())
+    _lib.check(rc, "b2_gemm")
+    return out
+
+
+def transpose_01(x):
+    lib = _lib.load()
+    _require_cuda(x)
+    x = x.contiguous()
+    d0, d1, d2 = x.shape
+    y = torch.empty((d1, d0, d2), dtype=x.dtype, device=x.device)
+    _lib.check(lib.b2_transpose_01(_ptr(x), _ptr(y), d0, d1, d2, _stream()), "b2_transpose_01")
+    return y
+
+
+def colsum(X, out=None, accumulate=False):
+    lib = _lib.load()
+    _require_cuda(X)
+    M, N = X.shape
+    if out is None:
+        out = torch.empty(N, dtype=torch.float32, device=X.device)
+        accumulate = False
+    _lib.check(lib.b2_colsum(_ptr(X), M, N, X.stride(0), _ptr(out), int(accumulate), _stream()),
+               "b2_colsum")
+    return out
+
+
+# --------------------------------------------------------------------------- LSTM
+def _params_struct(p):
+    return LstmParams(p["kernel"].data_ptr(), p["bias"].data_ptr(),
+                      p["w_i_diag"].data_ptr() if "w_i_diag" in p else 0,
+                      p["w_f_diag"].data_ptr() if "w_f_diag" in p else 0,
+                      p["w_o_diag"].data_ptr() if "w_o_diag" in p else 0)
+
+
+def lstm_desc(T, B, D_in, H, use_peephole=True, forget_bias=1.0, cell_clip=None, keep_prob=1.0,
+              dropout_seed=0, precision=PREC_FP32, need_backward=True):
+    return LstmDesc(T, B, D_in, H, int(bool(use_peephole)), float(forget_bias),
+                    float(cell_clip) if cell_clip else 0.0, float(keep_prob), int(dropout_seed),
+                    int(precision), int(bool(need_backward)))
+
+
+def blstm_layer_forward(desc, x, seq_len, p_fw, p_bw, want_final_state=False):
+    """x [T,B,D] -> (y [T,B,2H], final_state [4,B,H] or None, reserve buffer)."""
+    lib = _lib.load()
+    _require_cuda(x, seq_len)
+    dev = x.device
+    y = torch.empty((desc.T, desc.B, 2 * desc.H), dtype=torch.float32, device=dev)
+    fs = torch.empty((4, desc.B, desc.H), dtype=torch.float32, device=dev) if want_final_state else None
+    reserve = None
+    if desc.need_backward:
+        reserve = torch.empty(lib.b2_blstm_reserve_bytes(C.byref(desc)), dtype=torch.uint8, device=dev)
+    nbytes = lib.b2_blstm_workspace_bytes(C.byref(desc))
+    ws = workspace("lstm", nbytes, dev)
+    fw, bw = _params_struct(p_fw), _params_struct(p_bw)
+    rc = lib.b2_blstm_layer_forward(C.byref(desc), _ptr(x.contiguous()), _ptr(seq_len), C.byref(fw),
+                                    C.byref(bw), _ptr(y), _ptr(fs), _ptr(reserve), _ptr(ws), nbytes,
+                                    _stream())
+    _lib.check(rc, "b2_blstm_layer_forward")
+    return y, fs, reserve
+
+
+def blstm_layer_backward(desc, x, seq_len, p_fw, p_bw, dy, reserve, g_fw, g_bw, need_dx=True):
+    """Accumulates into the gradient dicts g_fw / g_bw; returns dx [T,B,D] or None."""
+    lib = _lib.load()
+    _require_cuda(x, dy)
+    dev = x.device
+    dx = torch.empty((desc.T, desc.B, desc.D_in), dtype=torch.float32, device=dev) if need_dx else None
+    nbytes = lib.b2_blstm_workspace_bytes(C.byref(desc))
+    ws = workspace("lstm", nbytes, dev)
+    fw, bw = _params_struct(p_fw), _params_struct(p_bw)
+    gf, gb = _params_struct(g_fw), _params_struct(g_bw)
+    rc = lib.b2_blstm_layer_backward(C.byref(desc), _ptr(x.contiguous()), _ptr(seq_len), C.byref(fw),
+                                     C.byref(bw), _ptr(dy.contiguous()), _ptr(reserve), _ptr(dx),
+                                     C.byref(gf), C.byref(gb), _ptr(ws), nbytes, _stream())
+    _lib.check(rc, "b2_blstm_layer_backward")
+    return dx
+
+
+# ------------------------------------------------------------------ clip + optimizer
+class TensorList(object):
+    """Device-side arrays of pointers / sizes for the multi-tensor kernels."""
+
+    def __init__(self, tensors):
+        self.tensors = list(tensors)
+        dev = self.tensors[0].device
+        self.n = len(self.tensors)
+        self.ptrs = torch.tensor([t.data_ptr() for t in self.tensors], dtype=torch.int64, device=dev)
+        self.sizes = torch.tensor([t.numel() for t in self.tensors], dtype=torch.int64, device=dev)
+
+
+def clip_by_norm_multi(grads, clip_norm, post_scale=1.0):
+    """grads: TensorList.  In-place per-tensor tf.clip_by_norm, then *post_scale."""
+    lib = _lib.load()
+    norms = torch.empty(grads.n, dtype=torch.float32, device=grads.ptrs.device)
+    rc = lib.b2_clip_by_norm_multi(_ptr(grads.ptrs), _ptr(grads.sizes), grads.n,
+                                   float(clip_norm) if clip_norm else 0.0, float(post_scale),
+                                   _ptr(norms), _stream())
+    _lib.check(rc, "b2_clip_by_norm_multi")
+    return norms
+
+
+def optimizer_step_multi(kind, params, grads, state0, state1, learning_rate, step):
+    lib = _lib.load()
+    rc = lib.b2_optimizer_step_multi(_lib.OPT_KINDS[kind], _ptr(params.ptrs), _ptr(grads.ptrs),
+                                     _ptr(state0.ptrs) if state0 is not None else C.c_void_p(0),
+                                     _ptr(state1.ptrs) if state1 is not None else C.c_void_p(0),
+                                     _ptr(params.sizes), params.n, float(learning_rate), int(step),
+                                     _stream())
+    _lib.check(rc, "b2_optimizer_step_multi")

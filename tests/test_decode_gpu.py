@@ -1,0 +1,48 @@
+"""Greedy decoder / posteriors on the GPU vs the oracle: label indices bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import decode as odec
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("T,B,C", [(30, 4, 6), (300, 8, 62), (1000, 64, 29), (257, 3, 3001), (513, 2, 5)])
+def test_greedy_bit_exact(cuda, T, B, C):
+    from tensorflow_end2end_speech_recognition_b200 import ops
+    rng = np.random.RandomState(T + C)
+    logits = rng.randn(T, B, C).astype(np.float32)
+    # make the blank and repeats frequent so collapse/removal both matter
+    logits[:, :, C - 1] += 1.5
+    logits[1::2] = logits[0::2][: logits[1::2].shape[0]] + 0.01 * rng.randn(*logits[1::2].shape).astype(np.float32)
+    seq = np.array([T] + [int(rng.randint(1, T + 1)) for _ in range(B - 1)], np.int32)
+    lab, n = ops.ctc_greedy_decode(torch.tensor(logits, device=cuda), torch.tensor(seq, device=cuda))
+    torch.cuda.synchronize()
+    lab, n = lab.cpu().numpy(), n.cpu().numpy()
+    ref = odec.greedy_decode(np.transpose(logits, (1, 0, 2)), seq, C - 1)
+    for b in range(B):
+        assert n[b] == len(ref[b])
+        assert list(lab[b, :n[b]]) == ref[b]
+        assert np.all(lab[b, n[b]:] == -1)
+
+
+def test_greedy_ties_first_index(cuda):
+    from tensorflow_end2end_speech_recognition_b200 import ops
+    T, B, C = 6, 1, 40
+    logits = np.zeros((T, B, C), np.float32)        # all ties -> argmax 0 everywhere
+    logits[2, 0, 37] = 1.0
+    logits[3, 0, 5] = 1.0
+    logits[3, 0, 33] = 1.0                          # tie between 5 and 33 -> 5
+    lab, n = ops.ctc_greedy_decode(torch.tensor(logits, device=cuda),
+                                   torch.tensor([T], dtype=torch.int32, device=cuda))
+    assert list(lab[0, :n[0]].cpu().numpy()) == [0, 37, 5, 0]
+
+
+def test_softmax_rows(cuda):
+    from tensorflow_end2end_speech_recognition_b200 import ops
+    rng = np.random.RandomState(0)
+    x = (rng.randn(777, 29) * 3).astype(np.float32)
+    y = ops.softmax_rows(torch.tensor(x, device=cuda)).cpu().numpy()
+    e = np.exp(x.astype(np.float64) - x.max(-1, keepdims=True))
+    np.testing.assert_allclose(y, e / e.sum(-1, keepdims=True), rtol=1e-5, atol=1e-7)
