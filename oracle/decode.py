@@ -96,7 +96,9 @@ def beam_search_decode(probs_btc, seq_len, blank, beam_width):
     """[B,T,C] probabilities -> (list of label lists, list of neg-log scores)."""
     res, sc = [], []
     with np.errstate(divide="ignore"):
-        lp = np.log(np.asarray(probs_btc, dtype=np.float64))
+        # the reference takes np.log in the dtype of `probs` (float32 as returned by
+        # sess.run) and then accumulates in Python floats (beam_search_decoder.py:69)
+        lp = np.log(np.asarray(probs_btc)).astype(np.float64)
     for b in range(len(seq_len)):
         h, s = beam_search_decode_single(lp[b, :int(seq_len[b])], blank, beam_width)
         res.append(h)

@@ -1,0 +1,81 @@
+"""BLSTM-CTC model and train step, CPU restatement (torch-CPU).  TEST INFRASTRUCTURE.
+
+Follows ``models/ctc/ctc.py:175-238`` (``_build``: encoder -> output
+fully_connected -> logits [T,B,C]), ``:256-323`` (``compute_loss``: mean of
+``tf.nn.ctc_loss``), ``models/model_base.py:97-166`` (``train``: gradients ->
+per-tensor clip_by_norm -> optimizer) and ``utils/training/multi_gpu.py:13-48``.
+This is also the CPU baseline that bench.py times next to the GPU path (the real
+TF-1.x CPU path cannot run here: TensorFlow is not installable).
+"""
+import numpy as np
+import torch
+
+from . import lstm as olstm
+from . import optim as oopt
+
+
+def layers_from_variables(variables, num_layers, use_peephole=True):
+    layers = []
+    for i in range(1, num_layers + 1):
+        layer = {}
+        for d in ("fw", "bw"):
+            scope = "blstm_hidden%d/%s/lstm_cell/" % (i, d)
+            p = {"kernel": variables[scope + "kernel"], "bias": variables[scope + "bias"]}
+            if use_peephole:
+                for k in ("w_i_diag", "w_f_diag", "w_o_diag"):
+                    p[k] = variables[scope + k]
+            layer[d] = p
+        layers.append(layer)
+    return layers
+
+
+def ctc_model_forward(variables, inputs_btd, seq_len, labels, num_layers, use_peephole=True,
+                      cell_clip=None, keep_prob=1.0, dropout_masks=None):
+    """variables: dict name -> torch tensor.  Returns (mean loss, logits [T,B,C], per-utt losses)."""
+    layers = layers_from_variables(variables, num_layers, use_peephole)
+    enc, _ = olstm.blstm_forward(inputs_btd, seq_len, layers, keep_prob=keep_prob,
+                                 dropout_masks=dropout_masks, cell_clip=cell_clip)
+    T, B, E = enc.shape
+    logits = (enc.reshape(T * B, E) @ variables["output/weights"] + variables["output/biases"])
+    logits = logits.reshape(T, B, -1)
+    C = logits.shape[-1]
+    lens = torch.tensor([len(l) for l in labels], dtype=torch.long)
+    flat = torch.tensor([v for l in labels for v in l], dtype=torch.long)
+    losses = torch.nn.functional.ctc_loss(torch.log_softmax(logits, -1), flat,
+                                          torch.as_tensor(np.asarray(seq_len), dtype=torch.long), lens,
+                                          blank=C - 1, reduction="none", zero_infinity=False)
+    # ignore_longer_outputs_than_inputs=True: utterances with L > T_b contribute 0 (ctc.py:296)
+    skip = lens > torch.as_tensor(np.asarray(seq_len), dtype=torch.long)
+    losses = torch.where(skip, torch.zeros_like(losses), losses)
+    return losses.mean(), logits, losses
+
+
+class OracleTrainer(object):
+    """variables as numpy fp64/fp32 arrays; autograd for the backward pass; clip and
+    optimizer from oracle.optim (TF-1.x rules)."""
+
+    def __init__(self, variables, num_layers, optimizer="rmsprop", learning_rate=1e-3,
+                 clip_grad_norm=None, use_peephole=True, cell_clip=None, dtype=torch.float64):
+        self.names = list(variables)
+        self.params = [np.array(variables[n], dtype=np.float64 if dtype == torch.float64 else np.float32)
+                       for n in self.names]
+        self.num_layers, self.use_peephole, self.cell_clip = num_layers, use_peephole, cell_clip
+        self.clip = clip_grad_norm
+        self.opt = oopt.Optimizer(optimizer, learning_rate)
+        self.dtype = dtype
+
+    def loss_and_grads(self, inputs_btd, seq_len, labels):
+        vs = {n: torch.tensor(p, dtype=self.dtype, requires_grad=True) for n, p in zip(self.names, self.params)}
+        x = torch.tensor(np.asarray(inputs_btd), dtype=self.dtype)
+        loss, logits, losses = ctc_model_forward(vs, x, seq_len, labels, self.num_layers,
+                                                 self.use_peephole, self.cell_clip)
+        loss.backward()
+        grads = [vs[n].grad.numpy() if vs[n].grad is not None else None for n in self.names]
+        return float(loss), logits.detach().numpy(), grads
+
+    def step(self, inputs_btd, seq_len, labels, tower_grads=None):
+        loss, logits, grads = self.loss_and_grads(inputs_btd, seq_len, labels)
+        if self.clip is not None:
+            grads = [oopt.clip_by_norm(g, self.clip) if g is not None else None for g in grads]
+        self.opt.step(self.params, grads)
+        return loss, logits, grads

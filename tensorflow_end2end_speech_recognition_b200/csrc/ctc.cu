@@ -114,6 +114,15 @@ ctc_alpha_beta_kernel(const float* __restrict__ logits, const float* __restrict_
   }
   __syncthreads();
 
+  // Every kNorm steps the column is shifted by its maximum so that lattice values stay
+  // O(100) in magnitude (fp32 ulp ~1e-5) instead of O(T).  Rows spilled to HBM therefore
+  // carry arbitrary per-row offsets; the gradient kernel normalises each row locally
+  // (sum_s alpha*beta/y is the same constant p for every t), the loss adds the offsets back.
+  constexpr int kNorm = 16;
+  __shared__ float s_red[32];
+  __shared__ float s_shift;
+  double offset_sum = 0.0;           // meaningful in thread 0 only
+
   constexpr int PF = 4;              // prefetch distance (steps) for the emission gather
   float xq[PF][SPT];
   const int nsteps = Tb - 1;
@@ -162,19 +171,43 @@ ctc_alpha_beta_kernel(const float* __restrict__ logits, const float* __restrict_
         }
         __syncthreads();
         float* tmp = prev; prev = cur; cur = tmp;
+        if ((i % kNorm) == kNorm - 1) {     // uniform: renormalise the column just written
+          float m = -INFINITY;
+#pragma unroll
+          for (int k = 0; k < SPT; ++k)
+            if (valid[k]) m = fmaxf(m, prev[tid + k * NT + 2]);
+          m = warp_max(m);
+          if ((tid & 31) == 0) s_red[tid >> 5] = m;
+          __syncthreads();
+          if (tid < 32) {
+            float mm = (tid < (NT + 31) / 32) ? s_red[tid] : -INFINITY;
+            mm = warp_max(mm);
+            if (tid == 0) s_shift = mm;
+          }
+          __syncthreads();
+          const float sh = s_shift;
+          if (sh != -INFINITY) {
+#pragma unroll
+            for (int k = 0; k < SPT; ++k)
+              if (valid[k]) prev[tid + k * NT + 2] -= sh;
+            offset_sum += (double)sh;
+          }
+          __syncthreads();
+        }
       }
     }
   }
   if (!is_beta && tid == 0) {
     const float a = prev[(S - 1) + 2];
     const float c = (S > 1) ? prev[(S - 2) + 2] : -INFINITY;
-    const float lp = lse2(a, c);
+    const float lp = (float)((double)lse2(a, c) + offset_sum);
     logp_out[b] = lp;
     loss[b] = -lp;
   }
 }
 
-// One warp per (t,b) row.  g[c] = softmax_c - sum_{s: l'(s)=c} alpha*beta/(y*p).
+// One warp per (t,b) row.  g[c] = softmax_c - sum_{s: l'(s)=c} alpha*beta/(y*Z_t) with the
+// row-local normaliser Z_t = sum_s alpha*beta/y (= p, independent of per-row lattice shifts).
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 ctc_grad_kernel(const float* __restrict__ logits, const float* __restrict__ lse,
                 const int* __restrict__ labels_flat, const int* __restrict__ label_offsets,
@@ -198,32 +231,41 @@ ctc_grad_kernel(const float* __restrict__ logits, const float* __restrict__ lse,
   const float l = lse[row];
   for (int c = lane; c < C; c += 32) g[c] = __expf(x[c] - l);
   __syncwarp();
-  const float logp = logp_in[b];
-  if (logp != -INFINITY) {
+  {
     const int off = label_offsets[b];
     const int L = label_offsets[b + 1] - off;
     const int S = 2 * L + 1;
     const float* ar = alpha + ((int64_t)b * T + t) * S_pad;
     const float* br = beta + ((int64_t)b * T + t) * S_pad;
     const float xb = x[blank] - l;
-    float blank_occ = 0.f;
-    // blanks: even s, reduced in registers
-    for (int s = 2 * lane; s < S; s += 64) {
-      const float v = ar[s] + br[s];
-      if (v != -INFINITY) blank_occ += __expf(v - xb - logp);
+    // pass 1: Z = logsumexp_s (alpha + beta - lp): equals log p up to the per-row shifts
+    float m = -INFINITY;
+    for (int s = lane; s < S; s += 32) {
+      const float lp = (s & 1) ? (x[labels_flat[off + (s >> 1)]] - l) : xb;
+      m = fmaxf(m, ar[s] + br[s] - lp);
     }
-    // labels: odd s, scattered with shared-memory atomics
-    for (int s = 2 * lane + 1; s < S; s += 64) {
-      const float v = ar[s] + br[s];
-      if (v != -INFINITY) {
-        const int c = labels_flat[off + (s >> 1)];
-        atomicAdd(&g[c], -__expf(v - (x[c] - l) - logp));
+    m = warp_max(m);
+    if (m != -INFINITY) {          // -inf: no alignment passes through this frame -> grad = softmax
+      float z = 0.f;
+      for (int s = lane; s < S; s += 32) {
+        const float lp = (s & 1) ? (x[labels_flat[off + (s >> 1)]] - l) : xb;
+        z += __expf(ar[s] + br[s] - lp - m);
       }
+      z = warp_sum(z);
+      const float Z = m + __logf(z);
+      float blank_occ = 0.f;
+      // blanks: even s, reduced in registers
+      for (int s = 2 * lane; s < S; s += 64) blank_occ += __expf(ar[s] + br[s] - xb - Z);
+      // labels: odd s, scattered with shared-memory atomics
+      for (int s = 2 * lane + 1; s < S; s += 64) {
+        const int c = labels_flat[off + (s >> 1)];
+        atomicAdd(&g[c], -__expf(ar[s] + br[s] - (x[c] - l) - Z));
+      }
+      blank_occ = warp_sum(blank_occ);
+      __syncwarp();
+      if (lane == 0) g[blank] -= blank_occ;
+      __syncwarp();
     }
-    blank_occ = warp_sum(blank_occ);
-    __syncwarp();
-    if (lane == 0) g[blank] -= blank_occ;
-    __syncwarp();
   }
   for (int c = lane; c < C; c += 32) out[c] = grad_scale * g[c];
 }

@@ -1,0 +1,217 @@
+"""CTC model -- host mirror of ``models/ctc/ctc.py`` (class ``CTC``, :16-398).
+
+Same constructor signature and method names as the reference; handles are
+evaluated eagerly on CUDA tensors instead of being TF graph ops:
+
+    model = CTC(encoder_type='blstm', input_size=120, num_units=256, num_layers=2,
+                num_classes=61, ...)
+    loss, logits = model.compute_loss(inputs, labels_st, inputs_seq_len, keep_prob)
+    model.train(loss, optimizer='rmsprop', learning_rate=1e-3)
+    decoded = model.decoder(logits, inputs_seq_len, beam_width=1)   # SparseTensorValue
+    ler = model.compute_ler(decoded, labels_st)
+"""
+import numpy as np
+import torch
+
+from ... import ops
+from ...utils.io.labels.sparsetensor import SparseTensorValue, sparse_to_label_lists
+from ..encoders.load_encoder import load
+from ..model_base import ModelBase
+
+
+def _truncated_normal(rng, shape, stddev):
+    """tf.truncated_normal: re-draw until within 2 sigma (ctc.py:221-223)."""
+    x = rng.normal(0.0, stddev, size=shape)
+    bad = np.abs(x) > 2 * stddev
+    while bad.any():
+        x[bad] = rng.normal(0.0, stddev, size=int(bad.sum()))
+        bad = np.abs(x) > 2 * stddev
+    return x.astype(np.float32)
+
+
+class CTC(ModelBase):
+    def __init__(self, encoder_type, input_size, num_units, num_layers, num_classes,
+                 lstm_impl="LSTMBlockCell", use_peephole=True, splice=1, num_stack=1,
+                 parameter_init=0.1, clip_grad_norm=None, clip_activation=None, num_proj=None,
+                 weight_decay=0.0, bottleneck_dim=None, time_major=True,
+                 precision="fp32", device=None, seed=1, strict_input_size=False):
+        super(CTC, self).__init__()
+        # The reference asserts input_size % 3 == 0 (ctc.py:79) although the BLSTM path never
+        # uses it; BASELINE's 80-d features need the relaxed form.
+        if strict_input_size:
+            assert input_size % 3 == 0, \
+                "input_size must be divisible by 3 (+ delta, acceleration coefficients)."
+        assert splice % 2 == 1, "splice must be the odd number"
+        if clip_grad_norm is not None:
+            assert float(clip_grad_norm) > 0, "clip_grad_norm must be larger than 0."
+        assert float(weight_decay) >= 0, "weight_decay must not be a negative value."
+        if float(weight_decay) > 0:
+            raise NotImplementedError("weight_decay > 0 is not built yet (reference configs use 0)")
+        if bottleneck_dim not in (None, 0):
+            raise NotImplementedError("bottleneck_dim is not built yet (reference configs use 0)")
+
+        self.encoder_type = encoder_type
+        self.input_size = input_size
+        self.splice = splice
+        self.num_stack = num_stack
+        self.num_units = num_units
+        # the reference evaluates int(num_proj) before the None check (ctc.py:93)
+        self.num_proj = int(num_proj) if num_proj not in (None, 0, "0") else None
+        self.num_layers = num_layers
+        self.bottleneck_dim = bottleneck_dim
+        self.num_classes = num_classes + 1      # + blank (ctc.py:101)
+        self.lstm_impl = lstm_impl
+        self.use_peephole = use_peephole
+        self.parameter_init = parameter_init
+        self.clip_grad_norm = clip_grad_norm
+        self.clip_activation = clip_activation
+        self.weight_decay = weight_decay
+        self.summaries_train, self.summaries_dev = [], []
+        self.inputs_pl_list, self.labels_pl_list = [], []
+        self.inputs_seq_len_pl_list, self.keep_prob_pl_list = [], []
+        self.time_major = time_major
+        self.name = encoder_type + "_ctc"
+        self.precision = precision
+        self.device = torch.device(device if device is not None else "cuda:0")
+
+        if encoder_type in ["blstm"]:
+            self.encoder = load(encoder_type)(
+                num_units=num_units, num_proj=self.num_proj, num_layers=num_layers,
+                lstm_impl=lstm_impl, use_peephole=use_peephole, parameter_init=parameter_init,
+                clip_activation=clip_activation, time_major=True, precision=precision)
+        else:
+            raise NotImplementedError(
+                "encoder_type %r: only 'blstm' is on the B200 hot path so far" % (encoder_type,))
+
+        rng = np.random.RandomState(seed)
+        named = self.encoder.create_variables(input_size * num_stack * splice, rng)
+        named.append(("output/weights", _truncated_normal(rng, (2 * num_units, self.num_classes),
+                                                          parameter_init)))
+        named.append(("output/biases", np.zeros(self.num_classes, np.float32)))
+        self._allocate_variables(named, self.device)
+        self._step = 0
+        self._ctx = None
+
+    # ----------------------------------------------------------------- feeds
+    def create_placeholders(self):
+        """Graph-mode relic (ctc.py:240-254): kept so driver scripts can call it; feeds are
+        passed directly to compute_loss."""
+        self.inputs_pl_list.append(None)
+        self.labels_pl_list.append(None)
+        self.inputs_seq_len_pl_list.append(None)
+        self.keep_prob_pl_list.append(None)
+
+    def _to_device(self, inputs, inputs_seq_len):
+        if not torch.is_tensor(inputs):
+            inputs = torch.as_tensor(np.ascontiguousarray(inputs, dtype=np.float32))
+        if not inputs.is_cuda:
+            inputs = inputs.to(self.device, non_blocking=True)
+        if not torch.is_tensor(inputs_seq_len):
+            inputs_seq_len = torch.as_tensor(np.asarray(inputs_seq_len, dtype=np.int32))
+        if not inputs_seq_len.is_cuda:
+            inputs_seq_len = inputs_seq_len.to(self.device, non_blocking=True)
+        return inputs.float(), inputs_seq_len.int()
+
+    # ----------------------------------------------------------------- model
+    def _build(self, inputs, inputs_seq_len, keep_prob, is_training):
+        """encoder -> output FC -> logits [T,B,num_classes] (ctc.py:175-238)."""
+        B, T, _ = inputs.shape
+        self._step += 1
+        enc, final_state = self.encoder(inputs, inputs_seq_len, keep_prob, is_training,
+                                        variables=self.variables, dropout_seed=self._step)
+        self.encoder_outputs = enc
+        prec = ops.PREC_BF16 if self.precision == "bf16" else ops.PREC_FP32
+        logits2d = ops.gemm(enc.view(T * B, -1), self.variables["output/weights"], False, False,
+                            self.variables["output/biases"], prec)
+        return logits2d.view(T, B, self.num_classes)
+
+    def compute_loss(self, inputs, labels, inputs_seq_len, keep_prob, scope=None,
+                     softmax_temperature=1, is_training=True):
+        """-> (total_loss 0-d cuda tensor, logits [T,B,C])   (ctc.py:256-323).
+
+        labels: the SparseTensor triple (indices, values, dense_shape) of
+        ``list2sparsetensor`` or a list of label sequences."""
+        inputs, inputs_seq_len = self._to_device(inputs, inputs_seq_len)
+        B = inputs.shape[0]
+        if isinstance(labels, (list, tuple)) and len(labels) == 3 and hasattr(labels[0], "ndim") \
+                and getattr(labels[0], "ndim", 0) == 2:
+            label_lists = sparse_to_label_lists(labels, B)
+        elif isinstance(labels, SparseTensorValue):
+            label_lists = sparse_to_label_lists(labels, B)
+        else:
+            label_lists = [list(l) for l in labels]
+        logits = self._build(inputs, inputs_seq_len, keep_prob, is_training)
+        flat, offs, lmax = ops.pack_labels(label_lists)
+        d_flat = torch.as_tensor(flat).to(self.device, non_blocking=True)
+        d_offs = torch.as_tensor(offs).to(self.device, non_blocking=True)
+        scaled = logits if softmax_temperature == 1 else logits / float(softmax_temperature)
+        # grad of reduce_mean(ctc_losses) (ctc.py:298) wrt logits comes out of the same launch
+        losses, dlogits = ops.ctc_loss_grad(scaled, d_flat, d_offs, inputs_seq_len, lmax,
+                                            blank=self.num_classes - 1, ignore_longer=True,
+                                            grad_scale=1.0 / (B * float(softmax_temperature)),
+                                            need_grad=is_training)
+        self.ctc_losses = losses
+        total_loss = losses.mean()
+        self._ctx = (dlogits, inputs.shape) if is_training else None
+        return total_loss, logits
+
+    def _backward(self):
+        """Gradients of the last compute_loss into self.flat_grads."""
+        assert self._ctx is not None, "train() needs a preceding compute_loss(is_training=True)"
+        dlogits, (B, T, _) = self._ctx
+        self.flat_grads.zero_()
+        prec = ops.PREC_BF16 if self.precision == "bf16" else ops.PREC_FP32
+        enc2d = self.encoder_outputs.view(T * B, -1)
+        dl2d = dlogits.view(T * B, self.num_classes)
+        ops.gemm(enc2d, dl2d, True, False, None, prec, out=self.grads["output/weights"], beta=1.0)
+        ops.colsum(dl2d, out=self.grads["output/biases"], accumulate=True)
+        denc = ops.gemm(dl2d, self.variables["output/weights"], False, True, None, prec)
+        self.encoder.backward(denc.view(T, B, -1), self.variables, self.grads)
+        self._ctx = None
+
+    # ---------------------------------------------------------------- decode
+    def decoder(self, logits, inputs_seq_len, beam_width=1):
+        """-> SparseTensorValue(indices int64 [N,2], values int32 [N], dense_shape)  (ctc.py:325-352)"""
+        assert isinstance(beam_width, int), "beam_width must be integer."
+        assert beam_width >= 1, "beam_width must be >= 1"
+        _, inputs_seq_len = self._to_device(logits, inputs_seq_len)
+        T, B, C = logits.shape
+        if beam_width == 1:
+            lab, n = ops.ctc_greedy_decode(logits, inputs_seq_len, blank=C - 1)
+        else:
+            lp = torch.log(ops.softmax_rows(ops.transpose_01(logits)))
+            lab, n, _ = ops.ctc_beam_decode(lp, inputs_seq_len, beam_width, blank=C - 1)
+        lab, n = lab.cpu().numpy(), n.cpu().numpy()
+        idx, val = [], []
+        for b in range(B):
+            for j in range(int(n[b])):
+                idx.append((b, j))
+                val.append(lab[b, j])
+        maxlen = int(n.max()) if B else 0
+        return SparseTensorValue(np.asarray(idx, np.int64).reshape(-1, 2), np.asarray(val, np.int32),
+                                 np.asarray([B, maxlen], np.int64))
+
+    def posteriors(self, logits, blank_prior=1):
+        """softmax over classes, batch-major [B*T, num_classes]  (ctc.py:354-380)"""
+        lb = ops.transpose_01(logits)
+        return ops.softmax_rows(lb.view(-1, self.num_classes))
+
+    def compute_ler(self, decode_op, labels):
+        """mean_b edit_distance(hyp_b, ref_b)/len(ref_b)  (ctc.py:382-398)"""
+        B = int(decode_op.dense_shape[0])
+        hyp = sparse_to_label_lists(decode_op, B)
+        ref = sparse_to_label_lists(labels, B) if not isinstance(labels, list) or (
+            len(labels) == 3 and hasattr(labels[0], "ndim")) else labels
+        return float(np.mean([_edit_distance(h, r) / float(len(r)) for h, r in zip(hyp, ref)]))
+
+
+def _edit_distance(hyp, ref):
+    n, m = len(hyp), len(ref)
+    d = list(range(m + 1))
+    for i in range(1, n + 1):
+        prev, d[0] = d[0], i
+        for j in range(1, m + 1):
+            cur = d[j]
+            d[j] = min(d[j] + 1, d[j - 1] + 1, prev + (hyp[i - 1] != ref[j - 1]))
+            prev = cur
+    return d[m]

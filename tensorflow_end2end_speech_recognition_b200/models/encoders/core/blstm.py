@@ -1,0 +1,122 @@
+"""Bidirectional LSTM encoder -- host mirror of ``models/encoders/core/blstm.py``.
+
+Same constructor and call signature as the reference class (blstm.py:13-121):
+``BLSTMEncoder(num_units, num_proj, num_layers, lstm_impl, use_peephole,
+parameter_init, clip_activation, time_major)`` and
+``enc(inputs[B,T,D], inputs_seq_len[B], keep_prob, is_training) -> (outputs,
+final_state)``.  Arithmetic: ``b2_blstm_layer_forward/backward`` (CUDA, sm_100a).
+"""
+import numpy as np
+import torch
+
+from .... import ops
+
+LSTM_IMPLS = ("BasicLSTMCell", "LSTMCell", "LSTMBlockCell")
+
+
+class BLSTMEncoder(object):
+    def __init__(self, num_units, num_proj, num_layers, lstm_impl, use_peephole, parameter_init,
+                 clip_activation, time_major=True, name="lstm_encoder", precision="fp32",
+                 tf_version="1.2.0"):
+        assert num_proj != 0
+        self.num_units = num_units
+        self.num_proj = num_proj if lstm_impl == "LSTMCell" else None       # blstm.py:49-52
+        self.num_layers = num_layers
+        self.lstm_impl = lstm_impl
+        self.use_peephole = use_peephole
+        self.parameter_init = parameter_init
+        self.clip_activation = clip_activation
+        self.time_major = time_major
+        self.name = name
+        self.precision = precision
+        if lstm_impl in ("LSTMBlockFusedCell", "CudnnLSTM"):
+            raise NotImplementedError("%s is 'under implementation' in the reference "
+                                      "(blstm.py:335-473)" % lstm_impl)
+        if lstm_impl not in LSTM_IMPLS:
+            raise IndexError('lstm_impl is "BasicLSTMCell" or "LSTMCell" or ' +
+                             '"LSTMBlockCell" or "LSTMBlockFusedCell" or ' + '"CudnnLSTM".')
+        if self.num_proj:
+            raise NotImplementedError("num_proj (LSTMCell projection) is a 'next' row (SURVEY 8f.3)")
+        # BasicLSTMCell has no peephole / clip (blstm.py:148-157); the block cell only
+        # receives clip_cell when tf.__version__ == '1.3.0' (blstm.py:286-305)
+        if lstm_impl == "BasicLSTMCell":
+            self._peephole, self._clip = False, None
+        elif lstm_impl == "LSTMBlockCell":
+            self._peephole = bool(use_peephole)
+            self._clip = clip_activation if tf_version == "1.3.0" else None
+        else:
+            self._peephole, self._clip = bool(use_peephole), clip_activation
+        self._saved = None
+
+    # ------------------------------------------------------------ variables
+    def create_variables(self, input_size, rng):
+        """-> ordered list of (tf_name, numpy array); U(-init, init) kernels and peepholes
+        from the scope initializer (blstm.py:79-80,283-284), zero biases."""
+        out = []
+        d_in = input_size
+        H = self.num_units
+        for i_layer in range(1, self.num_layers + 1):
+            for d in ("fw", "bw"):
+                scope = "blstm_hidden%d/%s/lstm_cell/" % (i_layer, d)
+                a = self.parameter_init
+                out.append((scope + "kernel", rng.uniform(-a, a, (d_in + H, 4 * H)).astype(np.float32)))
+                out.append((scope + "bias", np.zeros(4 * H, np.float32)))
+                if self._peephole:
+                    for k in ("w_i_diag", "w_f_diag", "w_o_diag"):
+                        out.append((scope + k, rng.uniform(-a, a, H).astype(np.float32)))
+            d_in = 2 * H
+        return out
+
+    def _layer_params(self, variables, i_layer, d):
+        scope = "blstm_hidden%d/%s/lstm_cell/" % (i_layer, d)
+        p = {"kernel": variables[scope + "kernel"], "bias": variables[scope + "bias"]}
+        if self._peephole:
+            for k in ("w_i_diag", "w_f_diag", "w_o_diag"):
+                p[k] = variables[scope + k]
+        return p
+
+    # -------------------------------------------------------------- forward
+    def __call__(self, inputs, inputs_seq_len, keep_prob, is_training, variables=None,
+                 dropout_seed=0):
+        """inputs [B,T,D] cuda f32 -> (outputs [T,B,2H] if time_major else [B,T,2H], final_state)."""
+        assert variables is not None, "BLSTMEncoder needs the model's variable dict"
+        B, T, D = inputs.shape
+        x = ops.transpose_01(inputs)                       # blstm.py:279
+        prec = ops.PREC_BF16 if self.precision == "bf16" else ops.PREC_FP32
+        saved = []
+        fs = None
+        for i_layer in range(1, self.num_layers + 1):
+            desc = ops.lstm_desc(T, B, x.shape[2], self.num_units, use_peephole=self._peephole,
+                                 forget_bias=1.0, cell_clip=self._clip, keep_prob=float(keep_prob),
+                                 dropout_seed=dropout_seed * 131 + i_layer, precision=prec,
+                                 need_backward=is_training)
+            pf = self._layer_params(variables, i_layer, "fw")
+            pb = self._layer_params(variables, i_layer, "bw")
+            y, fs, reserve = ops.blstm_layer_forward(desc, x, inputs_seq_len, pf, pb,
+                                                     want_final_state=(i_layer == self.num_layers))
+            saved.append((desc, x, reserve, i_layer))
+            x = y
+        self._saved = (saved, inputs_seq_len)
+        outputs = x if self.time_major else ops.transpose_01(x)
+        final_state = None
+        if fs is not None:
+            final_state = ((fs[0], fs[1]), (fs[2], fs[3]))   # (fw(c,h), bw(c,h))
+        return outputs, final_state
+
+    # ------------------------------------------------------------- backward
+    def backward(self, d_outputs, variables, grads, need_dx=False, on_layer_done=None):
+        """d_outputs [T,B,2H] (time-major).  Accumulates into ``grads`` (same keys as
+        ``variables``); calls ``on_layer_done(i_layer)`` when a layer's gradients are final."""
+        saved, seq_len = self._saved
+        dy = d_outputs
+        for desc, x, reserve, i_layer in reversed(saved):
+            pf = self._layer_params(variables, i_layer, "fw")
+            pb = self._layer_params(variables, i_layer, "bw")
+            gf = self._layer_params(grads, i_layer, "fw")
+            gb = self._layer_params(grads, i_layer, "bw")
+            dy = ops.blstm_layer_backward(desc, x, seq_len, pf, pb, dy, reserve, gf, gb,
+                                          need_dx=(i_layer > 1 or need_dx))
+            if on_layer_done is not None:
+                on_layer_done(i_layer)
+        self._saved = None
+        return dy

@@ -1,0 +1,100 @@
+"""End-to-end BLSTM-CTC model (host mirror of models/ctc/ctc.py::CTC) on the GPU vs
+the torch-CPU oracle: logits, loss, gradients, and a 3-step rmsprop trajectory.
+Tolerances: fp32 path rtol 1e-3 (north star) asserted at 2e-4 for loss/logits."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import decode as odec
+from oracle import model as omodel
+
+pytestmark = pytest.mark.gpu
+
+
+def make_batch(rng, B, T, D, C, lmin, lmax):
+    x = rng.randn(B, T, D).astype(np.float32)
+    seq = np.array([T] + [int(rng.randint(T // 2, T + 1)) for _ in range(B - 1)], np.int32)
+    for b in range(B):
+        x[b, seq[b]:] = 0
+    labels = [list(rng.randint(0, C, size=int(rng.randint(lmin, lmax + 1)))) for _ in range(B)]
+    return x, seq, labels
+
+
+def build(cuda, precision, D=24, H=32, L=2, C=11, clip=5.0, **kw):
+    from tensorflow_end2end_speech_recognition_b200.models.ctc.ctc import CTC
+    return CTC(encoder_type="blstm", input_size=D, num_units=H, num_layers=L, num_classes=C,
+               parameter_init=0.1, clip_grad_norm=clip, precision=precision, device=cuda, seed=3, **kw)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 3e-2)])
+def test_loss_logits_grads(cuda, precision, tol):
+    rng = np.random.RandomState(0)
+    B, T, D, H, L, C = 6, 40, 24, 32, 2, 11
+    model = build(cuda, precision, D, H, L, C)
+    x, seq, labels = make_batch(rng, B, T, D, C, 3, 12)
+    loss, logits = model.compute_loss(x, labels, seq, keep_prob=1.0)
+    model._backward()
+    torch.cuda.synchronize()
+    vs = {v.name: v.tensor.cpu().numpy() for v in model.trainable_variables()}
+    tr = omodel.OracleTrainer(vs, L, clip_grad_norm=None)
+    l_ref, logits_ref, g_ref = tr.loss_and_grads(x, seq, labels)
+    assert abs(float(loss) - l_ref) <= tol * abs(l_ref)
+    np.testing.assert_allclose(logits.cpu().numpy(), logits_ref, rtol=tol, atol=tol)
+    for v, g in zip(model.trainable_variables(), g_ref):
+        s = max(1e-3, np.abs(g).max())
+        np.testing.assert_allclose(v.grad.cpu().numpy(), g, rtol=0, atol=5 * tol * s, err_msg=v.name)
+
+
+@pytest.mark.parametrize("opt", ["rmsprop", "adam", "momentum"])
+def test_three_step_trajectory_fp32(cuda, opt):
+    rng = np.random.RandomState(1)
+    B, T, D, H, L, C = 4, 30, 12, 16, 2, 7
+    model = build(cuda, "fp32", D, H, L, C, clip=1.0)
+    vs = {v.name: v.tensor.cpu().numpy() for v in model.trainable_variables()}
+    tr = omodel.OracleTrainer(vs, L, optimizer=opt, learning_rate=1e-2, clip_grad_norm=1.0)
+    for _ in range(3):
+        x, seq, labels = make_batch(rng, B, T, D, C, 2, 8)
+        loss, _ = model.compute_loss(x, labels, seq, keep_prob=1.0)
+        model.train(loss, opt, 1e-2)
+        l_ref, _, _ = tr.step(x, seq, labels)
+        assert abs(float(loss) - l_ref) <= 1e-3 * abs(l_ref)
+    torch.cuda.synchronize()
+    for v, p in zip(model.trainable_variables(), tr.params):
+        np.testing.assert_allclose(v.tensor.cpu().numpy(), p, rtol=2e-3, atol=2e-4, err_msg=v.name)
+
+
+def test_decode_and_ler_and_posteriors(cuda):
+    rng = np.random.RandomState(2)
+    B, T, D, H, L, C = 5, 50, 12, 16, 1, 9
+    model = build(cuda, "fp32", D, H, L, C)
+    x, seq, labels = make_batch(rng, B, T, D, C, 2, 8)
+    loss, logits = model.compute_loss(x, labels, seq, keep_prob=1.0, is_training=False)
+    dec = model.decoder(logits, seq, beam_width=1)
+    ref = odec.greedy_decode(np.transpose(logits.cpu().numpy(), (1, 0, 2)), seq, C)
+    from tensorflow_end2end_speech_recognition_b200.utils.io.labels.sparsetensor import sparse_to_label_lists
+    assert sparse_to_label_lists(dec, B) == ref
+    ler = model.compute_ler(dec, labels)
+    assert abs(ler - odec.label_error_rate(ref, labels)) < 1e-12
+    post = model.posteriors(logits).cpu().numpy()
+    assert post.shape == (B * T, C + 1)
+    np.testing.assert_allclose(post.sum(-1), 1.0, atol=1e-5)
+
+
+def test_overfit_one_utterance(cuda):
+    """the reference's own test pattern (models/test/test_ctc.py:24-240): one utterance
+    replicated B times, train until greedy LER < 0.1."""
+    rng = np.random.RandomState(4)
+    B, T, D, H, L, C = 4, 60, 20, 64, 2, 12
+    model = build(cuda, "fp32", D, H, L, C, clip=5.0)
+    x1 = rng.randn(1, T, D).astype(np.float32)
+    lab = list(rng.randint(0, C, size=14))
+    x, seq, labels = np.repeat(x1, B, 0), np.full(B, T, np.int32), [lab] * B
+    ler = 1.0
+    for step in range(300):
+        loss, logits = model.compute_loss(x, labels, seq, keep_prob=1.0)
+        model.train(loss, "adam", 5e-3)
+        if step % 10 == 9:
+            ler = model.compute_ler(model.decoder(logits, seq), labels)
+            if ler < 0.1:
+                break
+    assert ler < 0.1, "did not overfit: LER %.3f loss %.3f" % (ler, float(loss))

@@ -200,7 +200,7 @@ static void run_ts() {
   __nv_bfloat16 *dA, *dB; float *dts, *dss;
   CK(cudaMalloc(&dA, A.size() * 2)); CK(cudaMalloc(&dB, B.size() * 2)); CK(cudaMalloc(&dts, 2 * 128 * 16 * 4)); CK(cudaMalloc(&dss, 128 * 16 * 4));
   CK(cudaMemcpy(dA, A.data(), A.size() * 2, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dB, B.data(), B.size() * 2, cudaMemcpyHostToDevice));
-  for (int swap = 0; swap < 2; ++swap) {
+  for (int swap = 0; swap < 1; ++swap) {   // swap=1 (LBO<->SBO exchanged) faults: confirmed wrong on B200
     CK(cudaMemset(dts, 0, 2 * 128 * 16 * 4)); CK(cudaMemset(dss, 0, 128 * 16 * 4));
     k_ts_mma<<<1, 128, 8192>>>(dA, dB, dts, dss, swap);
     cudaError_t e = cudaDeviceSynchronize();
