@@ -115,6 +115,17 @@ int b2_gemm(int transa, int transb, int M, int N, int K, float alpha,
             float* C, int ldc, const float* bias, int precision,
             void* workspace, size_t workspace_bytes, b2_stream_t stream);
 
+/* Same GEMM on operands that are already bf16 (uint16_t storage), no casts:
+ *   a_mn = 0: A is [M rows][K contiguous] (pitch lda)   1: A is [K rows][M contiguous]
+ *   b_mn = 0: B is [N rows][K contiguous] (pitch ldb)   1: B is [K rows][N contiguous]
+ *   out_mode 0: C fp32 = alpha*A.B + bias   1: C fp32 += (split-K, fp32 atomics)
+ *            2: C bf16 = alpha*A.B + bias
+ * pitches must be multiples of 8 elements, base pointers 16-byte aligned (TMA). */
+int b2_gemm_bf16(int a_mn, int b_mn, int M, int N, int K, float alpha,
+                 const uint16_t* A, int lda, const uint16_t* B, int ldb, void* C,
+                 int ldc, const float* bias, int out_mode, int k_splits,
+                 b2_stream_t stream);
+
 /* ------------------------------------------------------------------------ *
  * Bidirectional LSTM layer              replaces LSTMBlockCell / LSTMCell /
  *   BasicLSTMCell under tf.nn.bidirectional_dynamic_rnn

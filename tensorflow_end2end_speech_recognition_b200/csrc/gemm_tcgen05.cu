@@ -390,3 +390,13 @@ extern "C" int b2_gemm(int transa, int transb, int M, int N, int K, float alpha,
   return gemm_bf16_tc(transa ? 1 : 0, transb ? 0 : 1, M, N, K, alpha, Ab, a_ld, Bb, b_ld, C, ldc,
                       bias, epi, 0, stream);
 }
+
+extern "C" int b2_gemm_bf16(int a_mn, int b_mn, int M, int N, int K, float alpha, const uint16_t* A,
+                            int lda, const uint16_t* B, int ldb, void* C, int ldc,
+                            const float* bias, int out_mode, int k_splits, b2_stream_t stream_) {
+  B2_CHECK_ARG(A && B && C, "b2_gemm_bf16: null pointer");
+  B2_CHECK_ARG(out_mode >= 0 && out_mode <= 2, "b2_gemm_bf16: bad out_mode %d", out_mode);
+  return gemm_bf16_tc(a_mn, b_mn, M, N, K, alpha, (const __nv_bfloat16*)A, lda,
+                      (const __nv_bfloat16*)B, ldb, C, ldc, bias, out_mode, k_splits,
+                      (cudaStream_t)stream_);
+}
