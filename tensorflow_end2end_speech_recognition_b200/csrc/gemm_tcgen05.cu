@@ -40,7 +40,8 @@ template <int BN> struct GemmCfg {
   static constexpr int kStageB = BN * GK * 2;
   static constexpr int kStage = kStageA + kStageB;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
-  static constexpr int kEpiBytes = 4 * 32 * 33 * 4;
+  static constexpr int kEpiPitch = 36;   // floats; 16-B aligned rows, conflict-free float4 access
+  static constexpr int kEpiBytes = 4 * 32 * kEpiPitch * 4;
   static constexpr int kSmem = kStages * kStage + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
 };
@@ -154,7 +155,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ---------------------------------------------------------------- epilogue
     const int q = warp & 3;                    // TMEM lane quarter this warp may touch
-    float* st = sEpi + (warp - 2) * 32 * 33;
+    float* st = sEpi + (warp - 2) * 32 * Cfg::kEpiPitch;
+    const bool vec_ok = (args.ldc % 4 == 0) && (((uintptr_t)args.C & 15) == 0);
     int acc = 0; uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int ks = w / tiles, r = w % tiles;
@@ -167,21 +169,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) st[lane * 33 + j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 8; ++j)
+          *(float4*)&st[lane * Cfg::kEpiPitch + 4 * j] =
+              make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                          __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
         __syncwarp();
-        const int col = n0 + c * 32 + lane;
-        const bool col_ok = col < args.N;
-        float bv = 0.f;
-        if (args.bias && col_ok && ks == 0) bv = args.bias[col];
-#pragma unroll 4
-        for (int rr = 0; rr < 32; ++rr) {
+        // lane -> (row group lane/8, 4-column group lane%8): every store instruction writes
+        // 4 rows x 128 contiguous bytes
+        const int cg = lane & 7;
+        const int col = n0 + c * 32 + cg * 4;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (args.bias && ks == 0) {
+          if (col + 0 < args.N) bv.x = args.bias[col + 0];
+          if (col + 1 < args.N) bv.y = args.bias[col + 1];
+          if (col + 2 < args.N) bv.z = args.bias[col + 2];
+          if (col + 3 < args.N) bv.w = args.bias[col + 3];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + (lane >> 3);
           const int row = m0 + q * 32 + rr;
-          if (row < args.M && col_ok) {
-            const float o = args.alpha * st[rr * 33 + lane] + bv;
-            const size_t idx = (size_t)row * args.ldc + col;
-            if (args.epi == EPI_STORE_F32) ((float*)args.C)[idx] = o;
-            else if (args.epi == EPI_ATOMIC_F32) atomicAdd(&((float*)args.C)[idx], o);
-            else ((__nv_bfloat16*)args.C)[idx] = __float2bfloat16(o);
+          if (row >= args.M || col >= args.N) continue;
+          float4 o = *(const float4*)&st[rr * Cfg::kEpiPitch + cg * 4];
+          o.x = args.alpha * o.x + bv.x; o.y = args.alpha * o.y + bv.y;
+          o.z = args.alpha * o.z + bv.z; o.w = args.alpha * o.w + bv.w;
+          const size_t idx = (size_t)row * args.ldc + col;
+          const bool full4 = col + 3 < args.N;
+          if (args.epi == EPI_STORE_F32) {
+            float* p = (float*)args.C + idx;
+            if (full4 && vec_ok) *(float4*)p = o;
+            else {
+              p[0] = o.x;
+              if (col + 1 < args.N) p[1] = o.y;
+              if (col + 2 < args.N) p[2] = o.z;
+              if (col + 3 < args.N) p[3] = o.w;
+            }
+          } else if (args.epi == EPI_ATOMIC_F32) {
+            float* p = (float*)args.C + idx;
+            atomicAdd(p, o.x);
+            if (col + 1 < args.N) atomicAdd(p + 1, o.y);
+            if (col + 2 < args.N) atomicAdd(p + 2, o.z);
+            if (col + 3 < args.N) atomicAdd(p + 3, o.w);
+          } else {
+            __nv_bfloat16* p = (__nv_bfloat16*)args.C + idx;
+            if (full4 && vec_ok) {
+              __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+              uint2 pk; pk.x = *(uint32_t*)&lo; pk.y = *(uint32_t*)&hi;
+              *(uint2*)p = pk;
+            } else {
+              p[0] = __float2bfloat16(o.x);
+              if (col + 1 < args.N) p[1] = __float2bfloat16(o.y);
+              if (col + 2 < args.N) p[2] = __float2bfloat16(o.z);
+              if (col + 3 < args.N) p[3] = __float2bfloat16(o.w);
+            }
           }
         }
         __syncwarp();
@@ -236,6 +276,27 @@ int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, 
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) d0=%llu d1=%llu ld=%llu box=%ux%u", (int)r,
               (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)ld, box0, box1);
+    return B2_ERR_CUDA;
+  }
+  return B2_OK;
+}
+
+// generic tiled tensor map (rank <= 5), fp32 or bf16, optional 128-byte swizzle
+int make_tmap_generic(CUtensorMap* tm, int dtype_is_f32, const void* base, int rank,
+                      const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                      int swizzle128) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled not available (no driver?)"); return B2_ERR_CUDA; }
+  cuuint64_t d[5], st[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
+  CUresult r = fn(tm, dtype_is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                  (cuuint32_t)rank, (void*)base, d, st, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(rank %d) failed (%d)", rank, (int)r);
     return B2_ERR_CUDA;
   }
   return B2_OK;

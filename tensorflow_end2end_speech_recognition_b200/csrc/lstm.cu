@@ -16,6 +16,7 @@
 // With B2_PREC_BF16 the time-batched GEMMs run on tcgen05 (gemm_tcgen05.cu) and
 // the recurrence on the cluster/TMEM kernel (lstm_rec_tc.cu) when available.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace b2 {
 
@@ -27,6 +28,33 @@ int gemm_bf16_tc(int a_mn, int b_mn, int M, int N, int K, float alpha, const __n
                  int epi, int k_splits_hint, cudaStream_t stream);
 int cast_f32_bf16(const float* in, int64_t rows, int cols, int ldi, __nv_bfloat16* out, int ldo,
                   cudaStream_t stream);
+
+// tcgen05 persistent recurrence (lstm_rec_tc.cu)
+struct RecFwdArgs {
+  int T, B, H, NG;
+  int D_unused;
+  const int* seq_len;
+  const uint16_t* wpack;
+  const float* wi[2]; const float* wf[2]; const float* wo[2];
+  int use_peephole; float forget_bias, cell_clip, keep_prob; unsigned long long seed;
+  float* y;
+  float* gates; float* cs; float* hs;
+  float* final_state;
+};
+bool rec_tc_supported(int H);
+size_t rec_tc_wpack_bytes(int H);
+int rec_tc_pack_weights(const float* kernel_fw, const float* kernel_bw, int D, int H,
+                        uint16_t* wpack, cudaStream_t stream);
+int rec_tc_forward(RecFwdArgs a, const float* G, int nchain, cudaStream_t stream);
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+static bool use_rec_tc(const b2_lstm_desc* d) {
+  return d->precision == B2_PREC_BF16 && rec_tc_supported(d->H) && env_int("B2_REC_TC", 1) &&
+         b2_device_is_sm100();
+}
 
 // ---------------------------------------------------------------------------
 // reserve layout (saved for backward), all fp32:
@@ -58,6 +86,7 @@ struct Work {
   __nv_bfloat16* xb;   // bf16 operand copies for the tcgen05 GEMMs
   __nv_bfloat16* wb;
   __nv_bfloat16* gb;
+  uint16_t* wpack;     // packed recurrent weights for the tcgen05 recurrence
 };
 static size_t pad8z(size_t x) { return (x + 7) / 8 * 8; }
 static size_t work_layout(const b2_lstm_desc* d, void* base, Work* w) {
@@ -67,8 +96,9 @@ static size_t work_layout(const b2_lstm_desc* d, void* base, Work* w) {
   const size_t oG = take(TB * 8 * d->H * sizeof(float));
   const size_t oh = take((size_t)2 * 2 * d->B * d->H * sizeof(float));
   const size_t oc = take((size_t)2 * d->B * d->H * sizeof(float));
-  size_t oxb = 0, owb = 0, ogb = 0;
+  size_t oxb = 0, owb = 0, ogb = 0, owp = 0;
   if (d->precision == B2_PREC_BF16) {
+    owp = take((size_t)2 * 4 * d->H * d->H * 2);
     const size_t din = pad8z((size_t)(d->D_in > 2 * d->H ? d->D_in : 2 * d->H));
     oxb = take(TB * din * 2);                                   // X or Hs as bf16
     owb = take((size_t)(d->D_in + d->H + 64) * 8 * d->H * 2);    // weights (both dirs) as bf16
@@ -79,6 +109,7 @@ static size_t work_layout(const b2_lstm_desc* d, void* base, Work* w) {
     w->G = (float*)(p + oG); w->hstate = (float*)(p + oh); w->cstate = (float*)(p + oc);
     w->xb = (__nv_bfloat16*)(p + oxb); w->wb = (__nv_bfloat16*)(p + owb);
     w->gb = (__nv_bfloat16*)(p + ogb);
+    w->wpack = (uint16_t*)(p + owp);
   }
   return off;
 }
@@ -364,6 +395,20 @@ extern "C" int b2_blstm_layer_forward(const b2_lstm_desc* d, const float* x, con
     if (rc) return rc;
   }
   // 2. recurrence
+  if (use_rec_tc(d)) {
+    rc = rec_tc_pack_weights(fw->kernel, bw->kernel, D, H, w.wpack, stream);
+    if (rc) return rc;
+    RecFwdArgs ra;
+    ra.T = T; ra.B = B; ra.H = H; ra.NG = 0; ra.D_unused = D; ra.seq_len = seq_len;
+    ra.wpack = w.wpack;
+    for (int dir = 0; dir < 2; ++dir) {
+      ra.wi[dir] = P[dir]->w_i_diag; ra.wf[dir] = P[dir]->w_f_diag; ra.wo[dir] = P[dir]->w_o_diag;
+    }
+    ra.use_peephole = d->use_peephole; ra.forget_bias = d->forget_bias; ra.cell_clip = d->cell_clip;
+    ra.keep_prob = d->keep_prob; ra.seed = d->dropout_seed;
+    ra.y = y; ra.gates = r.gates; ra.cs = r.cs; ra.hs = r.hs; ra.final_state = final_state;
+    return rec_tc_forward(ra, w.G, env_int("B2_REC_NCHAIN", 0), stream);
+  }
   B2_CUDA(cudaMemsetAsync(w.hstate, 0, (size_t)2 * 2 * B * H * sizeof(float), stream));
   B2_CUDA(cudaMemsetAsync(w.cstate, 0, (size_t)2 * B * H * sizeof(float), stream));
   StepArgs a;

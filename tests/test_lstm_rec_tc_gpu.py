@@ -1,0 +1,48 @@
+"""tcgen05 persistent recurrence (lstm_rec_tc.cu) behind b2_blstm_layer_forward with
+precision=bf16: encoder states vs the fp64 oracle.  Operands of the step GEMM (Wh, h)
+are rounded to bf16, so the tolerance is that of a bf16-operand recurrence;
+gradients go through the shared reserve layout and the fp32 BPTT."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.test_lstm_gpu import compare, run_layer
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("nchain", [1, 2])
+@pytest.mark.parametrize("T,B,D,H", [(6, 16, 32, 32), (12, 24, 40, 64), (20, 32, 64, 256),
+                                     (16, 64, 80, 512), (9, 5, 24, 128)])
+def test_rec_tc_forward_backward(cuda, nchain, T, B, D, H):
+    from tensorflow_end2end_speech_recognition_b200 import ops
+    os.environ["B2_REC_NCHAIN"] = str(nchain)
+    try:
+        seq = [T] + list(np.random.RandomState(T + B).randint(max(T // 2, 1), T + 1, size=B - 1))
+        got, ref = run_layer(cuda, T, B, D, H, seq, ops.PREC_BF16, seed=11)
+    finally:
+        os.environ.pop("B2_REC_NCHAIN", None)
+    compare(got, ref, 3e-2, 6e-2)
+
+
+def test_rec_tc_matches_fp32_step_kernels_long(cuda):
+    """T=300: drift of the bf16 recurrence against the fp32 CUDA-core recurrence stays bounded."""
+    import torch
+    from tensorflow_end2end_speech_recognition_b200 import ops
+    from oracle import lstm as olstm
+    T, B, D, H = 300, 32, 80, 256
+    rng = np.random.RandomState(0)
+    layer = olstm.init_blstm_params(D, H, 1, parameter_init=0.1, seed=0)[0]
+    P = {d: {k: torch.tensor(v, device=cuda) for k, v in layer[d].items()} for d in layer}
+    x = torch.tensor(rng.randn(T, B, D).astype(np.float32), device=cuda)
+    seq = torch.tensor(np.sort(rng.randint(T // 2, T + 1, size=B))[::-1].astype(np.int32).copy(), device=cuda)
+    ys = {}
+    for name, prec in (("fp32", ops.PREC_FP32), ("bf16", ops.PREC_BF16)):
+        desc = ops.lstm_desc(T, B, D, H, precision=prec, need_backward=False)
+        y, fs, _ = ops.blstm_layer_forward(desc, x, seq, P["fw"], P["bw"], want_final_state=True)
+        torch.cuda.synchronize()
+        ys[name] = (y.cpu().numpy(), fs.cpu().numpy())
+    err = np.abs(ys["fp32"][0] - ys["bf16"][0]).max()
+    assert err < 2e-2, err
+    assert np.abs(ys["fp32"][1] - ys["bf16"][1]).max() < 3e-2

@@ -16,9 +16,19 @@ using namespace b2::sm100;
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1);} } while (0)
 
 // ---------------------------------------------------------------- probe 2
-template <int MODE>   // 0: bulk copy smem->cluster smem + complete_tx ; 1: st.shared::cluster + arrive
+__device__ __forceinline__ void bulk_g2s_multicast(void* smem_dst, const void* gsrc, uint32_t bytes,
+                                                   uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes),
+      "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+// 0: bulk copy smem->cluster smem + complete_tx ; 1: st.shared::cluster + arrive ;
+// 2: st.global own slice + fence.proxy.async + multicast bulk load global->all CTAs
+template <int MODE>
 __global__ void __launch_bounds__(192, 1)
-k_allgather(int iters, int slice, long long* out) {
+k_allgather(int iters, int slice, long long* out, uint8_t* gbuf) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t rank = cluster_ctarank();
   uint32_t csize;
@@ -28,8 +38,8 @@ k_allgather(int iters, int slice, long long* out) {
   uint64_t* full = (uint64_t*)(stage + slice);  // [2]
   const int tid = threadIdx.x;
   if (tid == 0) {
-    mbar_init(&full[0], MODE == 0 ? 1 : csize);
-    mbar_init(&full[1], MODE == 0 ? 1 : csize);
+    mbar_init(&full[0], MODE == 1 ? csize : 1);
+    mbar_init(&full[1], MODE == 1 ? csize : 1);
     fence_mbar_init();
   }
   for (int i = tid; i < slice / 4; i += blockDim.x) ((uint32_t*)stage)[i] = rank * 1000 + i;
@@ -44,6 +54,19 @@ k_allgather(int iters, int slice, long long* out) {
     if (MODE == 0) {
       if (tid == 0) mbar_expect_tx(&full[p], csize * slice);
       if (tid < csize) bulk_s2cluster(dst, stage, slice, &full[p], tid);
+    } else if (MODE == 2) {
+      uint8_t* g = gbuf + ((size_t)(blockIdx.x / csize) * 2 + p) * csize * slice + rank * slice;
+      if (tid == 0) mbar_expect_tx(&full[p], csize * slice);
+      if (tid < 64) {
+        for (int o = tid * 16; o < slice; o += 64 * 16) {
+          uint4 v = *(const uint4*)(stage + o);
+          v.x += it;
+          *(uint4*)(g + o) = v;
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+        if (tid == 0) bulk_g2s_multicast(dst, g, slice, &full[p], (uint16_t)((1u << csize) - 1));
+      }
     } else {
       // 64 threads x 16 B = 1 KB per pass over the slice
       const uint32_t d0 = smem_u32(dst);
@@ -65,7 +88,7 @@ k_allgather(int iters, int slice, long long* out) {
     if (tid >= 64 || MODE == 0) { /* all threads wait */ }
     mbar_wait_cluster(&full[p], ph[p]);
     ph[p] ^= 1;
-    if (MODE == 1) asm volatile("bar.sync 2, 192;" ::: "memory");
+    if (MODE != 0) asm volatile("bar.sync 2, 192;" ::: "memory");
   }
   long long t1 = clock64();
   // checksum so nothing is optimised away
@@ -78,6 +101,7 @@ k_allgather(int iters, int slice, long long* out) {
 template <int MODE>
 static void run_allgather(int csize, int nclusters, int slice, int iters) {
   long long* d_out; CK(cudaMalloc(&d_out, 64 * sizeof(long long)));
+  uint8_t* gbuf; CK(cudaMalloc(&gbuf, (size_t)64 * 2 * 16 * 8192)); CK(cudaMemset(gbuf, 0, (size_t)64 * 2 * 16 * 8192));
   CK(cudaMemset(d_out, 0, 64 * sizeof(long long)));
   size_t smem = 2 * (size_t)csize * slice + slice + 64;
   CK(cudaFuncSetAttribute(k_allgather<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -94,7 +118,7 @@ static void run_allgather(int csize, int nclusters, int slice, int iters) {
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   for (int rep = 0; rep < 2; ++rep) {
     CK(cudaEventRecord(e0));
-    e = cudaLaunchKernelEx(&cfg, k_allgather<MODE>, iters, slice, d_out);
+    e = cudaLaunchKernelEx(&cfg, k_allgather<MODE>, iters, slice, d_out, gbuf);
     if (e != cudaSuccess) { printf("  launch failed: %s\n", cudaGetErrorString(e)); cudaGetLastError(); return; }
     CK(cudaEventRecord(e1));
     CK(cudaDeviceSynchronize());
@@ -103,7 +127,7 @@ static void run_allgather(int csize, int nclusters, int slice, int iters) {
   long long h[64]; CK(cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost));
   printf("  %d clusters x %d iters: %.3f ms total, %.1f ns/iter, cluster0 %.0f cycles/iter (checksum %lld)\n",
          nclusters, iters, ms, ms * 1e6 / iters, (double)h[0] / iters, h[1]);
-  CK(cudaFree(d_out));
+  CK(cudaFree(d_out)); CK(cudaFree(gbuf));
 }
 
 // ---------------------------------------------------------------- probe 3
@@ -219,10 +243,12 @@ int main(int argc, char** argv) {
   run_ts();
   const int iters = 2000;
   for (int cs : {16, 8}) {
-    for (int slice : {1024, 2048, 4096}) {
+    for (int slice : {1024, 2048}) {
       run_allgather<0>(cs, 1, slice, iters);
-      run_allgather<0>(cs, cs == 16 ? 8 : 16, slice, iters);
-      run_allgather<1>(cs, cs == 16 ? 8 : 16, slice, iters);
+      run_allgather<2>(cs, 1, slice, iters);
+      run_allgather<0>(cs, 4, slice, iters);
+      run_allgather<2>(cs, 4, slice, iters);
+      run_allgather<2>(cs, cs == 16 ? 7 : 16, slice, iters);
     }
   }
   return 0;
