@@ -40,6 +40,7 @@ struct RecFwdArgs {
   float* y;
   float* gates; float* cs; float* hs;
   float* final_state;
+  long long* dbg;
 };
 bool rec_tc_supported(int H);
 size_t rec_tc_wpack_bytes(int H);
@@ -407,6 +408,20 @@ extern "C" int b2_blstm_layer_forward(const b2_lstm_desc* d, const float* x, con
     ra.use_peephole = d->use_peephole; ra.forget_bias = d->forget_bias; ra.cell_clip = d->cell_clip;
     ra.keep_prob = d->keep_prob; ra.seed = d->dropout_seed;
     ra.y = y; ra.gates = r.gates; ra.cs = r.cs; ra.hs = r.hs; ra.final_state = final_state;
+    ra.dbg = nullptr;
+    if (env_int("B2_REC_DBG", 0)) {
+      static long long* dbg_buf = nullptr;
+      if (!dbg_buf) { cudaMalloc(&dbg_buf, 64 * sizeof(long long)); }
+      cudaMemsetAsync(dbg_buf, 0, 64 * sizeof(long long), stream);
+      ra.dbg = dbg_buf;
+      int rc2 = rec_tc_forward(ra, w.G, env_int("B2_REC_NCHAIN", 0), stream);
+      long long hbuf[8];
+      cudaMemcpyAsync(hbuf, dbg_buf, sizeof(hbuf), cudaMemcpyDeviceToHost, stream);
+      cudaStreamSynchronize(stream);
+      fprintf(stderr, "[rec dbg] cycles/step: mma_wait_h=%lld mma_issue=%lld | epi wait_acc=%lld ld+transpose=%lld wait_G=%lld math+stores=%lld fence+bar=%lld send=%lld\n",
+              hbuf[0] / T, hbuf[1] / T, hbuf[2] / T, hbuf[3] / T, hbuf[4] / T, hbuf[5] / T, hbuf[6] / T, hbuf[7] / T);
+      return rc2;
+    }
     return rec_tc_forward(ra, w.G, env_int("B2_REC_NCHAIN", 0), stream);
   }
   B2_CUDA(cudaMemsetAsync(w.hstate, 0, (size_t)2 * 2 * B * H * sizeof(float), stream));

@@ -45,6 +45,7 @@ struct RecFwdArgs {
   float* y;                   // [T,B,2H]
   float* gates; float* cs; float* hs;   // reserve, fp32 ([T,B,2,4,H], [T,B,2,H], [T,B,2,H]) or null
   float* final_state;         // [4,B,H] or null
+  long long* dbg;             // optional phase timers (clock64 sums), cluster 0 / CTA 0 only
 };
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
@@ -88,7 +89,7 @@ struct RecSmem {
 };
 
 // warp roles: 0 = MMA issuer, 1 = G producer, 2.. = epilogue (4 warps per chain)
-template <int NCHAIN>
+template <int NCHAIN, int KS>     // KS = H/16 MMA k-steps per time step
 __global__ void __launch_bounds__(64 + 128 * NCHAIN, 1)
 lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a) {
   using L = RecSmem<NCHAIN>;
@@ -100,7 +101,6 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
   const int dir = cluster_id & 1;
   const int gbase = (cluster_id >> 1) * NCHAIN;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int KS = H / 16;                       // MMA k-steps per time step
   const uint32_t hbytes = 32u * H;             // bytes of one h buffer (16 batch x H bf16)
   const uint32_t hall = (uint32_t)CS * 1024u;  // == hbytes
 
@@ -154,22 +154,30 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
     // ------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, RN, 0, 0);
-      uint32_t hph[NCHAIN][2];
-#pragma unroll
-      for (int c = 0; c < NCHAIN; ++c) { hph[c][0] = 0; hph[c][1] = 0; }
+      uint32_t hphase = 0;                       // bit (c*2+p): parity of hfull[c][p]
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(smem + L::kHbufOff), 256, 128, 0);
       for (int t = 0; t < T; ++t) {
 #pragma unroll
         for (int c = 0; c < NCHAIN; ++c) {
           if (gbase + c >= a.NG) continue;
           const int p = t & 1;
-          if (t > 0) { mbar_wait_cluster(&hfull[c * 2 + p], hph[c][p]); hph[c][p] ^= 1; }
-          tc_fence_after();
-          const uint32_t hb = smem_u32(smem + L::kHbufOff + (c * 2 + p) * L::kHbufBytes);
-          for (int k = 0; k < KS; ++k) {
-            const uint64_t bd = make_smem_desc(hb + k * 512, 256, 128, 0);
-            mma_ts(tAcc + c * RN, tA + k * 8, bd, idesc, k > 0 ? 1u : 0u);
+          const long long m0 = clock64();
+          if (t > 0) {
+            mbar_wait_cluster(&hfull[c * 2 + p], (hphase >> (c * 2 + p)) & 1u);
+            hphase ^= 1u << (c * 2 + p);
           }
+          tc_fence_after();
+          const long long m1 = clock64();
+          // one descriptor per buffer; the k-th step only moves the start address by 512 B
+          const uint64_t bd0 = bdesc0 + (uint64_t)((c * 2 + p) * (L::kHbufBytes >> 4));
+#pragma unroll
+          for (int k = 0; k < KS; ++k)
+            mma_ts(tAcc + c * RN, tA + k * 8, bd0 + (uint64_t)(k * 32), idesc, k > 0 ? 1u : 0u);
           mma_commit(&accfull[c]);
+          if (a.dbg && blockIdx.x == 0 && c == 0) {
+            a.dbg[0] += m1 - m0;               // wait for h
+            a.dbg[1] += clock64() - m1;        // issue 32 MMAs + commit
+          }
         }
       }
     }
@@ -215,8 +223,11 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
       int stage = 0; uint32_t gph = 0;
       for (int t = 0; t < T; ++t) {
         const int td = dir ? T - 1 - t : t;
+        const bool dbg = a.dbg && blockIdx.x == 0 && ctid == 0 && c == 0;
+        const long long e0 = clock64();
         mbar_wait(&accfull[c], t & 1);
         tc_fence_after();
+        const long long e1 = clock64();
         uint32_t v[16];
         tmem_ld_32x32b_x16(tAcc + c * RN + ((uint32_t)(q * 32) << 16), v);
         tmem_ld_wait();
@@ -234,7 +245,9 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
           z[g][0] = f.x; z[g][1] = f.y; z[g][2] = f.z; z[g][3] = f.w;
         }
         __syncwarp();
+        const long long e2 = clock64();
         mbar_wait(&gfull[c * RGS + stage], gph);
+        const long long e3 = clock64();
         const float* Gs = (const float*)(smem + L::kGOff + (c * RGS + stage) * 8192);
         const int p = t & 1;
         uint8_t* stg = stage_base + p * 1024;
@@ -244,27 +257,29 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
           const float* Gb = Gs + bl * 128 + ul;   // [b][gate][32 u]
           const bool active = td < len[j];
           const float c_prev = cst[j];
-          float gi = 0.f, gg = 0.f, gf = 0.f, go = 0.f, c_new = c_prev, h_out = 0.f;
-          if (active) {
-            float zi = z[0][j] + Gb[0], zg = z[1][j] + Gb[32];
-            float zf = z[2][j] + Gb[64] + a.forget_bias, zo = z[3][j] + Gb[96];
-            zi = fmaf(pwi, c_prev, zi); zf = fmaf(pwf, c_prev, zf);
-            // three activations share one reciprocal: 1/((1+Ei)(1+Ef)(1+Eg))
-            const float Ei = __expf(fminf(-zi, 25.f)), Ef = __expf(fminf(-zf, 25.f));
-            const float Eg = __expf(fminf(-2.f * zg, 25.f));
-            const float ai = 1.f + Ei, af = 1.f + Ef, ag = 1.f + Eg;
-            const float r = fast_rcp(ai * af * ag);
-            gi = r * af * ag; gf = r * ai * ag; gg = (1.f - Eg) * r * ai * af;
-            c_new = fmaf(gf, c_prev, gi * gg);
-            if (a.cell_clip > 0.f) c_new = fminf(fmaxf(c_new, -a.cell_clip), a.cell_clip);
-            zo = fmaf(pwo, c_new, zo);
-            const float Eo = __expf(fminf(-zo, 25.f)), Ec = __expf(fminf(-2.f * c_new, 25.f));
-            const float ao = 1.f + Eo, ac = 1.f + Ec;
-            const float r2 = fast_rcp(ao * ac);
-            go = r2 * ac;
-            h_out = go * (1.f - Ec) * r2 * ao;
-            cst[j] = c_new; hst[j] = h_out;
-          }
+          // branch-free so that the four cells of a thread interleave (ILP); inactive steps
+          // (t >= seq_len) discard the result below
+          float zi = z[0][j] + Gb[0], zg = z[1][j] + Gb[32];
+          float zf = z[2][j] + Gb[64] + a.forget_bias, zo = z[3][j] + Gb[96];
+          zi = fmaf(pwi, c_prev, zi); zf = fmaf(pwf, c_prev, zf);
+          // three activations share one reciprocal: 1/((1+Ei)(1+Ef)(1+Eg))
+          const float Ei = __expf(fminf(-zi, 25.f)), Ef = __expf(fminf(-zf, 25.f));
+          const float Eg = __expf(fminf(-2.f * zg, 25.f));
+          const float ai = 1.f + Ei, af = 1.f + Ef, ag = 1.f + Eg;
+          const float r = fast_rcp(ai * af * ag);
+          float gi = r * af * ag, gf = r * ai * ag, gg = (1.f - Eg) * r * ai * af;
+          float c_new = fmaf(gf, c_prev, gi * gg);
+          if (a.cell_clip > 0.f) c_new = fminf(fmaxf(c_new, -a.cell_clip), a.cell_clip);
+          zo = fmaf(pwo, c_new, zo);
+          const float Eo = __expf(fminf(-zo, 25.f)), Ec = __expf(fminf(-2.f * c_new, 25.f));
+          const float ao = 1.f + Eo, ac = 1.f + Ec;
+          const float r2 = fast_rcp(ao * ac);
+          float go = r2 * ac;
+          float h_out = go * (1.f - Ec) * r2 * ao;
+          c_new = active ? c_new : c_prev;
+          h_out = active ? h_out : 0.f;
+          cst[j] = c_new;
+          hst[j] = active ? h_out : hst[j];
           // state h (carried through inactive steps) feeds the next step's GEMM
           const int off = (ul >> 3) * 256 + (bl >> 3) * 128 + (bl & 7) * 16 + (ul & 7) * 2;
           *(__nv_bfloat16*)(stg + off) = __float2bfloat16(hst[j]);
@@ -283,18 +298,31 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
             }
           }
         }
+        const long long e4 = clock64();
         fence_proxy_async_smem();                 // staged h visible to the bulk-copy engine
         named_bar_sync(1 + c, 128);
-        if (ctid < 32) {
-          if (ctid == 0) {
-            mbar_arrive(&gempty[c * RGS + stage]);
-            if (t + 1 < T) mbar_expect_tx(&hfull[c * 2 + (p ^ 1)], hall);
-          }
-          __syncwarp();
-          if (t + 1 < T && ctid < CS) {
+        const long long e5 = clock64();
+        if (ctid == 0) {
+          mbar_arrive(&gempty[c * RGS + stage]);
+          if (t + 1 < T) mbar_expect_tx(&hfull[c * 2 + (p ^ 1)], hall);
+        }
+        // 4 lanes in each of the chain's 4 warps issue the CS bulk copies (one per peer):
+        // spreading the issue over warps costs ~250 cycles instead of ~850 from one warp
+        {
+          const int dstcta = q * 4 + lane;
+          if (t + 1 < T && lane < 4 && dstcta < CS) {
             uint8_t* dst = smem + L::kHbufOff + (c * 2 + (p ^ 1)) * L::kHbufBytes + cta * 1024;
-            bulk_s2cluster(dst, stg, 1024, &hfull[c * 2 + (p ^ 1)], (uint32_t)ctid);
+            bulk_s2cluster(dst, stg, 1024, &hfull[c * 2 + (p ^ 1)], (uint32_t)dstcta);
           }
+        }
+        if (dbg) {
+          const long long e6 = clock64();
+          a.dbg[2] += e1 - e0;   // wait accumulator
+          a.dbg[3] += e2 - e1;   // tmem ld + transpose
+          a.dbg[4] += e3 - e2;   // wait G
+          a.dbg[5] += e4 - e3;   // gate math + stores
+          a.dbg[6] += e5 - e4;   // fence + named barrier
+          a.dbg[7] += e6 - e5;   // issue sends
         }
         if (++stage == RGS) { stage = 0; gph ^= 1; }
       }
@@ -348,11 +376,11 @@ int rec_tc_pack_weights(const float* kernel_fw, const float* kernel_bw, int D, i
   return B2_OK;
 }
 
-template <int NCHAIN>
+template <int NCHAIN, int KS>
 static int launch_rec_fwd(const CUtensorMap& tmG, const RecFwdArgs& a, int nclusters, int CS,
                           cudaStream_t stream) {
   using L = RecSmem<NCHAIN>;
-  auto kern = lstm_rec_fwd_kernel<NCHAIN>;
+  auto kern = lstm_rec_fwd_kernel<NCHAIN, KS>;
   B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes));
   if (CS > 8) B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
@@ -381,8 +409,15 @@ int rec_tc_forward(RecFwdArgs a, const float* G, int nchain, cudaStream_t stream
   const uint32_t box[4] = {RU, 4, 1, RN};
   int rc = make_tmap_generic(&tmG, 1, G, 4, dims, strides, box, 0);
   if (rc) return rc;
-  if (nchain == 2) return launch_rec_fwd<2>(tmG, a, nclusters, CS, stream);
-  return launch_rec_fwd<1>(tmG, a, nclusters, CS, stream);
+#define B2_REC_DISPATCH(KS_)                                                          \
+  if (H / 16 == KS_) {                                                               \
+    if (nchain == 2) return launch_rec_fwd<2, KS_>(tmG, a, nclusters, CS, stream);  \
+    return launch_rec_fwd<1, KS_>(tmG, a, nclusters, CS, stream);                   \
+  }
+  B2_REC_DISPATCH(2) B2_REC_DISPATCH(4) B2_REC_DISPATCH(8) B2_REC_DISPATCH(16) B2_REC_DISPATCH(32)
+#undef B2_REC_DISPATCH
+  set_error("rec_tc_forward: unsupported H=%d", H);
+  return B2_ERR_UNSUPPORTED;
 }
 
 }  // namespace b2

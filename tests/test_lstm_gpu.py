@@ -28,10 +28,11 @@ def oracle_layer(x_tbd, seq, layer, dy, cell_clip=None, masks=None, keep_prob=1.
     return y.detach().numpy(), fs, x.grad.numpy(), grads
 
 
-def run_layer(dev, T, B, D, H, seq, precision, peephole=True, cell_clip=None, seed=0, keep_prob=1.0):
+def run_layer(dev, T, B, D, H, seq, precision, peephole=True, cell_clip=None, seed=0, keep_prob=1.0,
+              parameter_init=0.3):
     from tensorflow_end2end_speech_recognition_b200 import ops
     rng = np.random.RandomState(seed)
-    layer = olstm.init_blstm_params(D, H, 1, parameter_init=0.3, use_peephole=peephole, seed=seed)[0]
+    layer = olstm.init_blstm_params(D, H, 1, parameter_init=parameter_init, use_peephole=peephole, seed=seed)[0]
     for d in layer:
         layer[d]["bias"] = (rng.randn(4 * H) * 0.1).astype(np.float32)
     x = rng.randn(T, B, D).astype(np.float32)
