@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""Headline benchmark: frames/s of one BLSTM-CTC training step (BASELINE.json config 2:
+5x512 BLSTM, 80-d input, T=1000, B=64 per GPU, 28 chars + blank), data-parallel over N GPUs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" = forward (5 BLSTM layers + output FC) + CTC loss/grad + backward (BPTT + weight
+gradients) + per-tensor clip_by_norm + gradient all-reduce (N>1) + RMSProp update.
+`value`  : frames/s with the batch already resident in HBM (device-timed, CUDA events).
+`e2e`    : the same step through the public model API with HOST (pinned) buffers: the H2D
+           copy of the batch and the D2H read of the loss are inside the timed region.
+`--impl reference` times the CPU restatement of the reference's TF-1.x step
+(oracle/model.py, torch-CPU, all host threads) on a bounded sample -- the real TF1 CPU
+path cannot run here (TensorFlow is not installable).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CFG = dict(input_size=80, num_units=512, num_layers=5, num_classes=28, T=1000, B=64,
+           label_min=150, label_max=250, optimizer="rmsprop", lr=1e-3, clip=5.0)
+# forward MAC count of the gate GEMMs, x3 for training
+FWD_FLOP_PER_FRAME = 2 * 2 * (80 + 512) * 2048 + 4 * 2 * 2 * (1024 + 512) * 2048   # 55.18 M
+
+
+def make_batch(seed, B, T, D, C, lmin, lmax):
+    rng = np.random.RandomState(seed)
+    x = rng.randn(B, T, D).astype(np.float32)
+    seq = np.full(B, T, np.int32)
+    labels = [list(rng.randint(0, C, size=int(rng.randint(lmin, lmax + 1)))) for _ in range(B)]
+    return x, seq, labels
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                    "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_baseline(B_s, T_s, threads=None, steps=1):
+    """CPU restatement of the same train step on a bounded sample (B_s utterances x T_s frames,
+    full 5x512 model).  Returns frames/s."""
+    import torch
+    from oracle import model as omodel
+    from oracle import lstm as olstm
+    if threads:
+        torch.set_num_threads(threads)
+    rng = np.random.RandomState(0)
+    layers = olstm.init_blstm_params(CFG["input_size"], CFG["num_units"], CFG["num_layers"], seed=0)
+    vs = {}
+    for i, l in enumerate(layers, 1):
+        for d in ("fw", "bw"):
+            for k, v in l[d].items():
+                vs["blstm_hidden%d/%s/lstm_cell/%s" % (i, d, k)] = v
+    C = CFG["num_classes"] + 1
+    vs["output/weights"] = (rng.randn(2 * CFG["num_units"], C) * 0.1).astype(np.float32)
+    vs["output/biases"] = np.zeros(C, np.float32)
+    tr = omodel.OracleTrainer(vs, CFG["num_layers"], optimizer=CFG["optimizer"], learning_rate=CFG["lr"],
+                              clip_grad_norm=CFG["clip"], dtype=torch.float32)
+    lmax = max(2, int(CFG["label_max"] * T_s / CFG["T"]))
+    lmin = max(1, int(CFG["label_min"] * T_s / CFG["T"]))
+    x, seq, labels = make_batch(1, B_s, T_s, CFG["input_size"], CFG["num_classes"], lmin, lmax)
+    t0 = time.time()
+    for _ in range(steps):
+        tr.step(x, seq, labels)
+    dt = (time.time() - t0) / steps
+    return B_s * T_s / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: CPU port of the reference step, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    threads = min(cores, 64)
+    B_s, T_s = 64, 64
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, dt = cpu_baseline(B_s, T_s, threads=threads, steps=1)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    v = float(np.mean([a for a, _ in vals]))
+    ms = float(np.mean([b for _, b in vals])) * 1e3
+    sample = "B=%d x T=%d frames of the config-2 model (5x512 BLSTM, 80-d, CTC), full train step" % (B_s, T_s)
+    out = {"impl": "reference", "metric": "frames/sec BLSTM-CTC train", "value": v, "unit": "frames/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic",
+           "config": {"workload": "BASELINE configs[1]: LibriSpeech-shape char CTC, 5x512 BLSTM, 80-d, "
+                                  "T=1000, B=64 (CPU arm: bounded sample, see cpu_baseline.sample)"},
+           "cpu_baseline": {"value": v, "unit": "frames/s", "cores": threads, "kind": "port",
+                            "sample": sample,
+                            "note": "torch-CPU restatement of the TF-1.x step (oracle/model.py); "
+                                    "TensorFlow itself is not installable here"},
+           "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from tensorflow_end2end_speech_recognition_b200 import _lib, ops
+    from tensorflow_end2end_speech_recognition_b200.models.ctc.ctc import CTC
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    B, T, D = CFG["B"], CFG["T"], CFG["input_size"]
+    model = CTC(encoder_type="blstm", input_size=D, num_units=CFG["num_units"],
+                num_layers=CFG["num_layers"], num_classes=CFG["num_classes"],
+                lstm_impl="LSTMBlockCell", use_peephole=True, parameter_init=0.1,
+                clip_grad_norm=CFG["clip"], precision=args.precision, device=dev, seed=1)
+    model.set_data_parallel(world)
+    # weak scaling: every rank gets its own 64-utterance shard (np.array_split of a 64*N batch,
+    # utils/dataset/ctc.py:171-177)
+    x, seq, labels = make_batch(1234 + rank, B, T, D, CFG["num_classes"], CFG["label_min"], CFG["label_max"])
+    x_host = torch.from_numpy(x).pin_memory()
+    seq_host = torch.from_numpy(seq).pin_memory()
+    x_dev, seq_dev = x_host.to(dev), seq_host.to(dev)
+
+    def step(xin, sin):
+        loss, _ = model.compute_loss(xin, labels, sin, keep_prob=1.0)
+        model.train(loss, CFG["optimizer"], CFG["lr"])
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step(x_dev, seq_dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.b2_launch_count()
+    ms_dev = timed(lambda: step(x_dev, seq_dev), args.steps)
+    launches = (lib.b2_launch_count() - l0) // max(args.steps, 1)
+
+    last = {}
+
+    def e2e_step():
+        loss = step(x_host, seq_host)          # H2D of the batch inside (CTC._to_device)
+        last["loss"] = float(loss.item())      # D2H read of the step's result
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    frames = B * T * world
+    value = frames * args.steps / (ms_dev / 1e3)
+    e2e = frames * args.steps / (ms_e2e / 1e3)
+    ms_step = ms_dev / args.steps
+
+    # ---- rooflines of the three kernel families, timed live with CUDA events (rank 0)
+    roof = {}
+    if rank == 0:
+        peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+        try:
+            pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peaks.update({k: pk[k] for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained") if k in pk})
+            peaks["src"] = "measured"
+        except Exception:
+            pass
+
+        def time_ms(fn, n=5):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / n
+        import ctypes as C
+        TB, H = B * T, CFG["num_units"]
+        A = torch.randn(TB, 2 * H, device=dev).bfloat16()
+        W = torch.randn(8 * H, 2 * H, device=dev).bfloat16()
+        Cm = torch.empty(TB, 8 * H, device=dev)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        t_gemm = time_ms(lambda: lib.b2_gemm_bf16(0, 0, TB, 8 * H, 2 * H, 1.0, C.c_void_p(A.data_ptr()), 2 * H,
+                                                  C.c_void_p(W.data_ptr()), 2 * H, C.c_void_p(Cm.data_ptr()),
+                                                  8 * H, C.c_void_p(0), 0, 0, st))
+        fl = 2.0 * TB * 8 * H * 2 * H
+        roof["blstm_gate_gemm"] = {"kernel": "gemm_tc_kernel<256> (time-batched gate GEMM, layers 2-5 forward)",
+                                   "bound": "tensor", "achieved": fl / t_gemm / 1e9, "peak": peaks["bf16_tflops"],
+                                   "unit": "TFLOP/s", "frac": fl / t_gemm / 1e9 / peaks["bf16_tflops"],
+                                   "traffic": None, "ms": t_gemm, "peak_src": peaks["src"] + " burst"}
+        del A, W, Cm
+        # CTC at the bench shape
+        Cc = CFG["num_classes"] + 1
+        lg = torch.randn(T, B, Cc, device=dev)
+        flat, offs, lmax = ops.pack_labels(labels)
+        dflat, doffs = torch.tensor(flat, device=dev), torch.tensor(offs, device=dev)
+        t_ctc = time_ms(lambda: ops.ctc_loss_grad(lg, dflat, doffs, seq_dev, lmax))
+        s_pad = (2 * lmax + 1 + 31) // 32 * 32
+        by = 8.0 * T * B * Cc + 16.0 * T * B * s_pad
+        roof["ctc_alpha_beta"] = {"kernel": "ctc_lse + ctc_alpha_beta + ctc_grad", "bound": "hbm",
+                                  "achieved": by / t_ctc / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                  "frac": by / t_ctc / 1e6 / peaks["hbm_gbs"], "traffic": None, "ms": t_ctc,
+                                  "note": "latency-bound at C=29 (T sequential lattice steps); bytes = "
+                                          "8*T*B*C + 16*T*B*S spill", "peak_src": peaks["src"]}
+        # whole step against the tensor roofline (algorithmic gate-GEMM FLOPs / step time)
+        step_fl = 3.0 * FWD_FLOP_PER_FRAME * B * T
+        roof["step_blended"] = {"kernel": "whole training step (algorithmic gate-GEMM FLOPs / step time)",
+                                "bound": "tensor", "achieved": step_fl / ms_step / 1e9,
+                                "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                                "frac": step_fl / ms_step / 1e9 / peaks["bf16_tflops_sustained"],
+                                "traffic": None, "peak_src": peaks["src"] + " sustained"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = min(os.cpu_count() or 1, 64)
+        v, dt = cpu_baseline(64, 64, threads=cores, steps=1)
+        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": "one train step on B=64 x T=64 frames of the same 5x512 model (%.1f s)" % dt,
+               "note": "torch-CPU restatement of the TF-1.x step; TensorFlow itself cannot be installed here"}
+
+    if rank == 0:
+        out = {"metric": "frames/sec BLSTM-CTC train", "value": value, "unit": "frames/s", "n_gpus": world,
+               "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision,
+               "data": "synthetic",
+               "config": {"workload": "BASELINE configs[1]: LibriSpeech-shape char CTC, 5x512 BLSTM "
+                                      "(LSTMBlockCell, peephole), 80-d input, T=1000, B=64 per GPU, "
+                                      "28 chars + blank, labels 150-250, rmsprop lr 1e-3, clip_by_norm 5",
+                          "global_batch": B * world, "parallelism": "dp%d" % world,
+                          "l2": "per-step working set (reserve + gate buffers, >8 GB) >> 126 MB L2, "
+                                "no explicit flush"},
+               "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
+                       "h2d_bytes_per_step": int(x_host.numel() * 4 + seq_host.numel() * 4 + sum(len(l) for l in labels) * 4 + (B + 1) * 4),
+                       "d2h_bytes_per_step": 4, "loss": last.get("loss")},
+               "gpu_launches": int(launches),
+               "clocks": clocks,
+               "roofline": roof.get("blstm_gate_gemm"),
+               "rooflines": roof,
+               "cpu_baseline": cpu}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -49,6 +49,8 @@ int b2_version(void);
 const char* b2_last_error(void);
 /* 1 when the running device is sm_100 (tcgen05/TMA paths usable) */
 int b2_device_is_sm100(void);
+/* number of CUDA kernels this library has launched in this process (bench bookkeeping) */
+unsigned long long b2_launch_count(void);
 
 /* ------------------------------------------------------------------------ *
  * CTC loss + gradient                    replaces tf.nn.ctc_loss
@@ -167,16 +169,20 @@ size_t b2_blstm_workspace_bytes(const b2_lstm_desc* d);
 
 /* x [T,B,D_in] time-major; y [T,B,2H] = concat(fw, bw) after output dropout,
  * zero for t >= seq_len[b]; final_state [4,B,H] = c_fw, h_fw, c_bw, h_bw
- * (may be NULL). */
-int b2_blstm_layer_forward(const b2_lstm_desc* d, const float* x,
+ * (may be NULL).  x_lp: optional bf16 shadow of x ([T*B, D_in], pitch D_in) as
+ * returned by b2_blstm_reserve_y_lp of the layer below (saves one cast pass in
+ * the bf16 path); NULL is always valid. */
+int b2_blstm_layer_forward(const b2_lstm_desc* d, const float* x, const void* x_lp,
                            const int32_t* seq_len, const b2_lstm_params* fw,
                            const b2_lstm_params* bw, float* y,
                            float* final_state, void* reserve, void* workspace,
                            size_t workspace_bytes, b2_stream_t stream);
+/* bf16 copy of the layer output kept inside `reserve` (bf16 path), else NULL */
+const void* b2_blstm_reserve_y_lp(const b2_lstm_desc* d, const void* reserve);
 
 /* dy [T,B,2H]; dx [T,B,D_in] (NULL for the first layer); gradients are
  * ACCUMULATED into g_fw / g_bw (caller zeroes them once per step). */
-int b2_blstm_layer_backward(const b2_lstm_desc* d, const float* x,
+int b2_blstm_layer_backward(const b2_lstm_desc* d, const float* x, const void* x_lp,
                             const int32_t* seq_len, const b2_lstm_params* fw,
                             const b2_lstm_params* bw, const float* dy,
                             const void* reserve, float* dx,

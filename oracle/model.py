@@ -71,7 +71,7 @@ class OracleTrainer(object):
                                                  self.use_peephole, self.cell_clip)
         loss.backward()
         grads = [vs[n].grad.numpy() if vs[n].grad is not None else None for n in self.names]
-        return float(loss), logits.detach().numpy(), grads
+        return float(loss.detach()), logits.detach().numpy(), grads
 
     def step(self, inputs_btd, seq_len, labels, tower_grads=None):
         loss, logits, grads = self.loss_and_grads(inputs_btd, seq_len, labels)

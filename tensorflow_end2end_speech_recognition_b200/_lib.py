@@ -36,6 +36,7 @@ PROTOTYPES = {
     "b2_version": (_i, []),
     "b2_last_error": (C.c_char_p, []),
     "b2_device_is_sm100": (_i, []),
+    "b2_launch_count": (C.c_ulonglong, []),
     "b2_ctc_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "b2_ctc_loss_grad": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _sz, _p]),
     "b2_ctc_greedy_decode": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
@@ -47,9 +48,10 @@ PROTOTYPES = {
     "b2_gemm_bf16": (_i, [_i, _i, _i, _i, _i, _f, _p, _i, _p, _i, _p, _i, _p, _i, _i, _p]),
     "b2_blstm_reserve_bytes": (_sz, [C.POINTER(LstmDesc)]),
     "b2_blstm_workspace_bytes": (_sz, [C.POINTER(LstmDesc)]),
-    "b2_blstm_layer_forward": (_i, [C.POINTER(LstmDesc), _p, _p, C.POINTER(LstmParams),
+    "b2_blstm_layer_forward": (_i, [C.POINTER(LstmDesc), _p, _p, _p, C.POINTER(LstmParams),
                                     C.POINTER(LstmParams), _p, _p, _p, _p, _sz, _p]),
-    "b2_blstm_layer_backward": (_i, [C.POINTER(LstmDesc), _p, _p, C.POINTER(LstmParams),
+    "b2_blstm_reserve_y_lp": (_p, [C.POINTER(LstmDesc), _p]),
+    "b2_blstm_layer_backward": (_i, [C.POINTER(LstmDesc), _p, _p, _p, C.POINTER(LstmParams),
                                      C.POINTER(LstmParams), _p, _p, _p, C.POINTER(LstmGrads),
                                      C.POINTER(LstmGrads), _p, _sz, _p]),
     "b2_transpose_01": (_i, [_p, _p, _i, _i, _i, _p]),

@@ -10,8 +10,12 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static unsigned long long g_launches = 0;
+void count_launches(int n) { g_launches += (unsigned long long)n; }
+unsigned long long get_launches() { return g_launches; }
 }  // namespace b2
 
+extern "C" unsigned long long b2_launch_count(void) { return b2::get_launches(); }
 extern "C" int b2_version(void) { return 100; }
 extern "C" const char* b2_last_error(void) { return b2::g_err; }
 extern "C" int b2_device_is_sm100(void) {

@@ -10,6 +10,7 @@
 namespace b2 {
 
 void set_error(const char* fmt, ...);
+void count_launches(int n);   // bookkeeping for bench.py's gpu_launches (b2_launch_count)
 
 #define B2_CHECK_ARG(cond, ...)                                   \
   do {                                                            \
@@ -29,7 +30,7 @@ void set_error(const char* fmt, ...);
     }                                                                         \
   } while (0)
 
-#define B2_LAUNCH_CHECK() B2_CUDA(cudaGetLastError())
+#define B2_LAUNCH_CHECK() do { b2::count_launches(1); B2_CUDA(cudaGetLastError()); } while (0)
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

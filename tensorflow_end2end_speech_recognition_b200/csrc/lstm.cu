@@ -15,70 +15,11 @@
 //   bias/peephole reductions.
 // With B2_PREC_BF16 the time-batched GEMMs run on tcgen05 (gemm_tcgen05.cu) and
 // the recurrence on the cluster/TMEM kernel (lstm_rec_tc.cu) when available.
-#include "common.cuh"
+#include "lstm_internal.cuh"
+#include <cuda.h>
 #include <stdlib.h>
 
 namespace b2 {
-
-int gemm_simt(int transa, int transb, int M, int N, int K, float alpha, const float* A, int lda,
-              const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
-              cudaStream_t stream);
-int gemm_bf16_tc(int a_mn, int b_mn, int M, int N, int K, float alpha, const __nv_bfloat16* A,
-                 int lda, const __nv_bfloat16* B, int ldb, void* C, int ldc, const float* bias,
-                 int epi, int k_splits_hint, cudaStream_t stream);
-int cast_f32_bf16(const float* in, int64_t rows, int cols, int ldi, __nv_bfloat16* out, int ldo,
-                  cudaStream_t stream);
-
-// tcgen05 persistent recurrence (lstm_rec_tc.cu)
-struct RecFwdArgs {
-  int T, B, H, NG;
-  int D_unused;
-  const int* seq_len;
-  const uint16_t* wpack;
-  const float* wi[2]; const float* wf[2]; const float* wo[2];
-  int use_peephole; float forget_bias, cell_clip, keep_prob; unsigned long long seed;
-  float* y;
-  float* gates; float* cs; float* hs;
-  float* final_state;
-  long long* dbg;
-};
-bool rec_tc_supported(int H);
-size_t rec_tc_wpack_bytes(int H);
-int rec_tc_pack_weights(const float* kernel_fw, const float* kernel_bw, int D, int H,
-                        uint16_t* wpack, cudaStream_t stream);
-int rec_tc_forward(RecFwdArgs a, const float* G, int nchain, cudaStream_t stream);
-
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
-static bool use_rec_tc(const b2_lstm_desc* d) {
-  return d->precision == B2_PREC_BF16 && rec_tc_supported(d->H) && env_int("B2_REC_TC", 1) &&
-         b2_device_is_sm100();
-}
-
-// ---------------------------------------------------------------------------
-// reserve layout (saved for backward), all fp32:
-//   gates [T][B][2][4][H]   post-activation i, g, f, o
-//   cs    [T][B][2][H]      cell state after step t (carried through inactive steps)
-//   hs    [T][B][2][H]      emitted h before dropout (0 for inactive steps)
-// ---------------------------------------------------------------------------
-struct Reserve {
-  float* gates; float* cs; float* hs;
-};
-static size_t reserve_layout(const b2_lstm_desc* d, void* base, Reserve* r) {
-  const size_t n = (size_t)d->T * d->B * 2 * d->H;
-  size_t off = 0;
-  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
-  const size_t og = take(n * 4 * sizeof(float));
-  const size_t oc = take(n * sizeof(float));
-  const size_t oh = take(n * sizeof(float));
-  if (r) {
-    char* p = (char*)base;
-    r->gates = (float*)(p + og); r->cs = (float*)(p + oc); r->hs = (float*)(p + oh);
-  }
-  return off;
-}
 
 struct Work {
   float* G;        // [T*B, 8H] gate pre-activations (fwd) / dG (bwd)
@@ -87,7 +28,6 @@ struct Work {
   __nv_bfloat16* xb;   // bf16 operand copies for the tcgen05 GEMMs
   __nv_bfloat16* wb;
   __nv_bfloat16* gb;
-  uint16_t* wpack;     // packed recurrent weights for the tcgen05 recurrence
 };
 static size_t pad8z(size_t x) { return (x + 7) / 8 * 8; }
 static size_t work_layout(const b2_lstm_desc* d, void* base, Work* w) {
@@ -97,9 +37,8 @@ static size_t work_layout(const b2_lstm_desc* d, void* base, Work* w) {
   const size_t oG = take(TB * 8 * d->H * sizeof(float));
   const size_t oh = take((size_t)2 * 2 * d->B * d->H * sizeof(float));
   const size_t oc = take((size_t)2 * d->B * d->H * sizeof(float));
-  size_t oxb = 0, owb = 0, ogb = 0, owp = 0;
+  size_t oxb = 0, owb = 0, ogb = 0;
   if (d->precision == B2_PREC_BF16) {
-    owp = take((size_t)2 * 4 * d->H * d->H * 2);
     const size_t din = pad8z((size_t)(d->D_in > 2 * d->H ? d->D_in : 2 * d->H));
     oxb = take(TB * din * 2);                                   // X or Hs as bf16
     owb = take((size_t)(d->D_in + d->H + 64) * 8 * d->H * 2);    // weights (both dirs) as bf16
@@ -110,7 +49,6 @@ static size_t work_layout(const b2_lstm_desc* d, void* base, Work* w) {
     w->G = (float*)(p + oG); w->hstate = (float*)(p + oh); w->cstate = (float*)(p + oc);
     w->xb = (__nv_bfloat16*)(p + oxb); w->wb = (__nv_bfloat16*)(p + owb);
     w->gb = (__nv_bfloat16*)(p + ogb);
-    w->wpack = (uint16_t*)(p + owp);
   }
   return off;
 }
@@ -205,8 +143,7 @@ lstm_fwd_step_kernel(const StepArgs a) {
     yv = dropout_keep(a.seed, oidx, a.keep_prob) ? h_out / a.keep_prob : 0.f;
   a.y[oidx] = yv;
   if (a.gates) {
-    float* gp = a.gates + (row * 2 + dir) * 4 * H;
-    gp[u] = gi; gp[H + u] = gg; gp[2 * H + u] = gf; gp[3 * H + u] = go;
+    *(float4*)(a.gates + ((row * 2 + dir) * H + u) * 4) = make_float4(gi, gg, gf, go);
     a.cs[(row * 2 + dir) * H + u] = c_new;
     a.hs[(row * 2 + dir) * H + u] = h_out;
   }
@@ -277,8 +214,8 @@ lstm_bwd_step_kernel(const BwdStepArgs a) {
   float dyv = a.dy[oidx];
   if (a.keep_prob < 1.f) dyv = dropout_keep(a.seed, oidx, a.keep_prob) ? dyv / a.keep_prob : 0.f;
   const float dh = dyv + dh_in;
-  const float* gp = a.gates + (row * 2 + dir) * 4 * H;
-  const float gi = gp[u], gg = gp[H + u], gf = gp[2 * H + u], go = gp[3 * H + u];
+  const float4 g4 = *(const float4*)(a.gates + ((row * 2 + dir) * H + u) * 4);
+  const float gi = g4.x, gg = g4.y, gf = g4.z, go = g4.w;
   const float c = a.cs[(row * 2 + dir) * H + u];
   const int tp = dir == 0 ? t - 1 : t + 1;           // previous step in forward order
   float c_prev = 0.f;
@@ -354,16 +291,32 @@ extern "C" size_t b2_blstm_reserve_bytes(const b2_lstm_desc* d) {
   return d ? reserve_layout(d, nullptr, nullptr) : 0;
 }
 extern "C" size_t b2_blstm_workspace_bytes(const b2_lstm_desc* d) {
-  return d ? work_layout(d, nullptr, nullptr) : 0;
+  if (!d) return 0;
+  if (tc_layer_supported(d)) return tc_layer_workspace_bytes(d);
+  return work_layout(d, nullptr, nullptr);
 }
 
-extern "C" int b2_blstm_layer_forward(const b2_lstm_desc* d, const float* x, const int32_t* seq_len,
-                                      const b2_lstm_params* fw, const b2_lstm_params* bw, float* y,
-                                      float* final_state, void* reserve, void* workspace,
-                                      size_t workspace_bytes, b2_stream_t stream_) {
+extern "C" const void* b2_blstm_reserve_y_lp(const b2_lstm_desc* d, const void* reserve) {
+  if (!d || !reserve || !tc_layer_supported(d)) return nullptr;
+  Reserve r;
+  reserve_layout(d, (void*)reserve, &r);
+  return r.y_lp;
+}
+
+extern "C" int b2_blstm_layer_forward(const b2_lstm_desc* d, const float* x, const void* x_lp,
+                                      const int32_t* seq_len, const b2_lstm_params* fw,
+                                      const b2_lstm_params* bw, float* y, float* final_state,
+                                      void* reserve, void* workspace, size_t workspace_bytes,
+                                      b2_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   int rc = check_desc(d);
   if (rc) return rc;
+  if (tc_layer_supported(d)) {
+    B2_CHECK_ARG(x && seq_len && fw && bw && y && workspace, "blstm_forward: null pointer");
+    B2_CHECK_ARG(reserve, "blstm_forward(bf16): reserve required");
+    return tc_layer_forward(d, x, (const __nv_bfloat16*)x_lp, seq_len, fw, bw, y, final_state,
+                            reserve, workspace, workspace_bytes, stream);
+  }
   B2_CHECK_ARG(x && seq_len && fw && bw && y && workspace, "blstm_forward: null pointer");
   B2_CHECK_ARG(!d->need_backward || reserve, "blstm_forward: need_backward without reserve");
   B2_CHECK_ARG(!d->use_peephole || (fw->w_i_diag && fw->w_f_diag && fw->w_o_diag && bw->w_i_diag &&
@@ -372,7 +325,7 @@ extern "C" int b2_blstm_layer_forward(const b2_lstm_desc* d, const float* x, con
   Work w;
   const size_t need = work_layout(d, workspace, &w);
   if (workspace_bytes < need) { set_error("blstm_forward: workspace %zu < %zu", workspace_bytes, need); return B2_ERR_WORKSPACE; }
-  Reserve r = {nullptr, nullptr, nullptr};
+  Reserve r = {nullptr, nullptr, nullptr, nullptr, nullptr};
   if (d->need_backward) reserve_layout(d, reserve, &r);
   const int T = d->T, B = d->B, D = d->D_in, H = d->H;
   const int TB = T * B;
@@ -396,34 +349,6 @@ extern "C" int b2_blstm_layer_forward(const b2_lstm_desc* d, const float* x, con
     if (rc) return rc;
   }
   // 2. recurrence
-  if (use_rec_tc(d)) {
-    rc = rec_tc_pack_weights(fw->kernel, bw->kernel, D, H, w.wpack, stream);
-    if (rc) return rc;
-    RecFwdArgs ra;
-    ra.T = T; ra.B = B; ra.H = H; ra.NG = 0; ra.D_unused = D; ra.seq_len = seq_len;
-    ra.wpack = w.wpack;
-    for (int dir = 0; dir < 2; ++dir) {
-      ra.wi[dir] = P[dir]->w_i_diag; ra.wf[dir] = P[dir]->w_f_diag; ra.wo[dir] = P[dir]->w_o_diag;
-    }
-    ra.use_peephole = d->use_peephole; ra.forget_bias = d->forget_bias; ra.cell_clip = d->cell_clip;
-    ra.keep_prob = d->keep_prob; ra.seed = d->dropout_seed;
-    ra.y = y; ra.gates = r.gates; ra.cs = r.cs; ra.hs = r.hs; ra.final_state = final_state;
-    ra.dbg = nullptr;
-    if (env_int("B2_REC_DBG", 0)) {
-      static long long* dbg_buf = nullptr;
-      if (!dbg_buf) { cudaMalloc(&dbg_buf, 64 * sizeof(long long)); }
-      cudaMemsetAsync(dbg_buf, 0, 64 * sizeof(long long), stream);
-      ra.dbg = dbg_buf;
-      int rc2 = rec_tc_forward(ra, w.G, env_int("B2_REC_NCHAIN", 0), stream);
-      long long hbuf[8];
-      cudaMemcpyAsync(hbuf, dbg_buf, sizeof(hbuf), cudaMemcpyDeviceToHost, stream);
-      cudaStreamSynchronize(stream);
-      fprintf(stderr, "[rec dbg] cycles/step: mma_wait_h=%lld mma_issue=%lld | epi wait_acc=%lld ld+transpose=%lld wait_G=%lld math+stores=%lld fence+bar=%lld send=%lld\n",
-              hbuf[0] / T, hbuf[1] / T, hbuf[2] / T, hbuf[3] / T, hbuf[4] / T, hbuf[5] / T, hbuf[6] / T, hbuf[7] / T);
-      return rc2;
-    }
-    return rec_tc_forward(ra, w.G, env_int("B2_REC_NCHAIN", 0), stream);
-  }
   B2_CUDA(cudaMemsetAsync(w.hstate, 0, (size_t)2 * 2 * B * H * sizeof(float), stream));
   B2_CUDA(cudaMemsetAsync(w.cstate, 0, (size_t)2 * B * H * sizeof(float), stream));
   StepArgs a;
@@ -441,6 +366,7 @@ extern "C" int b2_blstm_layer_forward(const b2_lstm_desc* d, const float* x, con
     a.step = i;
     lstm_fwd_step_kernel<<<grid, 256, 0, stream>>>(a);
   }
+  count_launches(T - 1);
   B2_LAUNCH_CHECK();
   if (final_state) {
     // hstate parity after T steps is T&1; layout [c_fw, h_fw, c_bw, h_bw] each [B,H]
@@ -454,14 +380,21 @@ extern "C" int b2_blstm_layer_forward(const b2_lstm_desc* d, const float* x, con
   return B2_OK;
 }
 
-extern "C" int b2_blstm_layer_backward(const b2_lstm_desc* d, const float* x, const int32_t* seq_len,
-                                       const b2_lstm_params* fw, const b2_lstm_params* bw,
-                                       const float* dy, const void* reserve, float* dx,
-                                       const b2_lstm_grads* g_fw, const b2_lstm_grads* g_bw,
-                                       void* workspace, size_t workspace_bytes, b2_stream_t stream_) {
+extern "C" int b2_blstm_layer_backward(const b2_lstm_desc* d, const float* x, const void* x_lp,
+                                       const int32_t* seq_len, const b2_lstm_params* fw,
+                                       const b2_lstm_params* bw, const float* dy,
+                                       const void* reserve, float* dx, const b2_lstm_grads* g_fw,
+                                       const b2_lstm_grads* g_bw, void* workspace,
+                                       size_t workspace_bytes, b2_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   int rc = check_desc(d);
   if (rc) return rc;
+  if (tc_layer_supported(d)) {
+    B2_CHECK_ARG(x && seq_len && fw && bw && dy && reserve && g_fw && g_bw && workspace,
+                 "blstm_backward: null pointer");
+    return tc_layer_backward(d, x, (const __nv_bfloat16*)x_lp, seq_len, fw, bw, dy, reserve, dx,
+                             g_fw, g_bw, workspace, workspace_bytes, stream);
+  }
   B2_CHECK_ARG(x && seq_len && fw && bw && dy && reserve && g_fw && g_bw && workspace,
                "blstm_backward: null pointer");
   Work w;
@@ -491,6 +424,7 @@ extern "C" int b2_blstm_layer_backward(const b2_lstm_desc* d, const float* x, co
     a.step = i;
     lstm_bwd_step_kernel<<<grid, 256, 0, stream>>>(a);
   }
+  count_launches(T - 1);
   B2_LAUNCH_CHECK();
 
   // 2. bias + peephole reductions

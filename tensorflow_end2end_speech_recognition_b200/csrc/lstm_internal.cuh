@@ -1,0 +1,74 @@
+// Shared between lstm.cu (fp32 path + API dispatch), lstm_tc.cu (bf16 orchestration) and
+// lstm_rec_tc.cu (tcgen05 recurrence kernels).
+#pragma once
+#include "common.cuh"
+#include <cuda.h>
+#include <stdlib.h>
+
+namespace b2 {
+
+// reserve (saved by forward for backward), one per layer:
+//   gates [T][B][2][H][4] f32  post-activation i, g, f, o of every cell (gate innermost)
+//   cs    [T][B][2][H]    f32  cell state after step t (carried through inactive steps)
+//   hs    [T][B][2][H]    f32  emitted h before dropout, fp32 path only
+//   hs_lp [T*B][2H]       bf16 same, bf16 path (operand of the dWh GEMM)
+//   y_lp  [T*B][2H]       bf16 layer output after dropout (= next layer's GEMM operand);
+//                              aliases hs_lp when keep_prob == 1
+bool tc_layer_supported(const b2_lstm_desc* d);
+
+struct Reserve {
+  float* gates; float* cs; float* hs;
+  __nv_bfloat16* hs_lp; __nv_bfloat16* y_lp;
+};
+
+inline size_t reserve_layout(const b2_lstm_desc* d, void* base, Reserve* r) {
+  const size_t n = (size_t)d->T * d->B * 2 * d->H;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
+  const size_t og = take(n * 4 * sizeof(float));
+  const size_t oc = take(n * sizeof(float));
+  const bool lp = tc_layer_supported(d);   // bf16 shadows only when the tcgen05 recurrence runs
+  const size_t oh = lp ? 0 : take(n * sizeof(float));
+  const size_t ohl = lp ? take(n * 2) : 0;
+  const size_t oyl = lp ? (d->keep_prob < 1.f ? take(n * 2) : ohl) : 0;
+  if (r) {
+    char* p = (char*)base;
+    r->gates = (float*)(p + og); r->cs = (float*)(p + oc);
+    r->hs = lp ? nullptr : (float*)(p + oh);
+    r->hs_lp = lp ? (__nv_bfloat16*)(p + ohl) : nullptr;
+    r->y_lp = lp ? (__nv_bfloat16*)(p + oyl) : nullptr;
+  }
+  return off;
+}
+
+int gemm_simt(int transa, int transb, int M, int N, int K, float alpha, const float* A, int lda,
+              const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
+              cudaStream_t stream);
+int gemm_bf16_tc(int a_mn, int b_mn, int M, int N, int K, float alpha, const __nv_bfloat16* A,
+                 int lda, const __nv_bfloat16* B, int ldb, void* C, int ldc, const float* bias,
+                 int epi, int k_splits_hint, cudaStream_t stream);
+int cast_f32_bf16(const float* in, int64_t rows, int cols, int ldi, __nv_bfloat16* out, int ldo,
+                  cudaStream_t stream);
+int make_tmap_generic(CUtensorMap* tm, int dtype_is_f32, const void* base, int rank,
+                      const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                      int swizzle128);
+int num_sms();
+
+// bf16 / tcgen05 layer (lstm_tc.cu)
+size_t tc_layer_workspace_bytes(const b2_lstm_desc* d);
+int tc_layer_forward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16* x_lp,
+                     const int32_t* seq_len, const b2_lstm_params* fw, const b2_lstm_params* bw,
+                     float* y, float* final_state, void* reserve, void* workspace,
+                     size_t workspace_bytes, cudaStream_t stream);
+int tc_layer_backward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16* x_lp,
+                      const int32_t* seq_len, const b2_lstm_params* fw, const b2_lstm_params* bw,
+                      const float* dy, const void* reserve, float* dx, const b2_lstm_grads* g_fw,
+                      const b2_lstm_grads* g_bw, void* workspace, size_t workspace_bytes,
+                      cudaStream_t stream);
+
+inline int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+}  // namespace b2

@@ -1,59 +1,45 @@
-// Persistent BLSTM recurrence on tcgen05 for sm_100a (B2_PREC_BF16).
+// Persistent BLSTM recurrence kernels on tcgen05 for sm_100a (B2_PREC_BF16).
 //
 // The strictly sequential half of the LSTM gate GEMMs: z_t = G_t + h_{t-1} . Wh for
-// T steps (reference: the LSTMBlockCell inside tf.nn.bidirectional_dynamic_rnn,
-// models/encoders/core/blstm.py:287-320).  One launch runs a whole layer:
+// T steps, and its BPTT mirror (reference: LSTMBlockCell inside
+// tf.nn.bidirectional_dynamic_rnn, models/encoders/core/blstm.py:287-320).  One launch
+// runs a whole layer, both directions:
 //
-//   * one thread-block CLUSTER of CS = H/32 CTAs per (direction, batch group);
+//   * one thread-block CLUSTER of CS = H/32 CTAs per (direction, batch groups);
 //     CTA `r` owns hidden units [32r, 32r+32) = 128 gate rows (unit-major, gate-minor);
-//   * the CTA's slice of Wh (128 x H, bf16) is loaded ONCE into TENSOR MEMORY and
-//     stays there for all T steps: the step GEMM is tcgen05.mma with A from TMEM
-//     and B = h_{t-1} (16 batch columns, bf16, K-major no-swizzle) from shared memory,
-//     fp32 accumulator in TMEM  (swap-AB: gates are the MMA M dimension);
-//   * the four gates of one unit come out of the accumulator in four adjacent TMEM
-//     lanes; a 4x4 transpose through shared memory gives each thread (unit, 4 batches,
-//     all gates); gate math in fp32 with c kept in registers for the whole sequence;
-//   * h_t (bf16) is all-gathered across the cluster with cp.async.bulk
-//     shared::cta -> shared::cluster, completion counted on the receivers' mbarriers
-//     (no cluster barrier on the critical path); double-buffered by step parity;
-//   * G_t (time-batched input projection, fp32) is prefetched by TMA into a ring;
+//   * the CTA's slice of Wh (bf16) is loaded ONCE into TENSOR MEMORY and stays there
+//     for all T steps: the step GEMM is tcgen05.mma with A from TMEM and B (16 batch
+//     columns, bf16, K-major no-swizzle) from shared memory, fp32 accumulators in TMEM
+//     (swap-AB: gate rows / units are the MMA M dimension);
+//   * a tcgen05.mma costs >= ~53 cycles to issue from one thread whatever its N
+//     (measured, tools/microbench4/5), so the 32 MMAs of a step are issued by FOUR
+//     warps into four accumulators that the gate-math warps add up (680 vs 1530 cycles);
+//   * the four gates of a unit sit in four adjacent TMEM lanes; a 4x4 transpose through
+//     shared memory gives each thread (unit, 4 batches, all gates); gate math in fp32,
+//     c stays in registers for the whole sequence;
+//   * h_t (forward) / partial dh (backward) travel across the cluster with
+//     cp.async.bulk shared::cta -> shared::cluster, counted on the receivers' mbarriers
+//     (no cluster barrier on the critical path), double-buffered by step parity;
+//   * time-batched operands (G_t, saved gates, dy) are prefetched by TMA into rings;
 //   * NCHAIN independent batch groups per cluster are interleaved so that one chain's
 //     DSMEM exchange overlaps the other chain's MMA + gate math.
-#include "common.cuh"
+#include "lstm_internal.cuh"
 #include "sm100.cuh"
+#include "lstm_rec_tc.cuh"
 
 namespace b2 {
 using namespace sm100;
 
-int make_tmap_generic(CUtensorMap* tm, int dtype_is_f32, const void* base, int rank,
-                      const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
-                      int swizzle128);
-int num_sms();
-
-constexpr int RU = 32;        // hidden units per CTA
-constexpr int RN = 16;        // batch columns per chain (MMA N)
-constexpr int RGS = 3;        // G ring stages
+constexpr int RGS = 3;        // TMA ring stages
 constexpr int RPITCH = 20;    // transpose scratch pitch (floats)
+constexpr int NISSW = 4;      // MMA issuer warps
 
-struct RecFwdArgs {
-  int T, B, H, NG;            // NG = number of 16-wide batch groups per direction
-  int D_unused;
-  const int* seq_len;
-  const uint16_t* wpack;      // [2][CS][128][H] bf16, row r = unit_local*4 + gate
-  const float* wi[2]; const float* wf[2]; const float* wo[2];
-  int use_peephole; float forget_bias, cell_clip, keep_prob; unsigned long long seed;
-  float* y;                   // [T,B,2H]
-  float* gates; float* cs; float* hs;   // reserve, fp32 ([T,B,2,4,H], [T,B,2,H], [T,B,2,H]) or null
-  float* final_state;         // [4,B,H] or null
-  long long* dbg;             // optional phase timers (clock64 sums), cluster 0 / CTA 0 only
-};
-
-__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
-                                            int c0, int c1, int c2, int c3) {
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
+                                            int c0, int c1, int c2) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes "
-      "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem_dst)),
-      "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -77,6 +63,7 @@ __device__ __forceinline__ float fast_rcp(float x) {
   return r;
 }
 
+// ======================================================================== forward
 template <int NCHAIN>
 struct RecSmem {
   static constexpr int kHbufOff = 0;                                   // [NCHAIN][2][32*H]  (H<=512 -> 16 KB)
@@ -88,11 +75,13 @@ struct RecSmem {
   static constexpr int kBytes = kBarOff + 512;
 };
 
-// warp roles: 0 = MMA issuer, 1 = G producer, 2.. = epilogue (4 warps per chain)
+// warp roles: 0..3 = MMA issuers, 4 = G producer, 5.. = gate math (4 warps per chain)
 template <int NCHAIN, int KS>     // KS = H/16 MMA k-steps per time step
-__global__ void __launch_bounds__(64 + 128 * NCHAIN, 1)
+__global__ void __launch_bounds__(160 + 128 * NCHAIN, 1)
 lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a) {
   using L = RecSmem<NCHAIN>;
+  constexpr int NISS = KS < NISSW ? KS : NISSW;      // issuer warps actually used
+  constexpr int KPER = KS / NISS;                    // k-steps per issuer
   extern __shared__ __align__(1024) uint8_t smem[];
   const int H = a.H, T = a.T, B = a.B;
   const int CS = H / RU;
@@ -101,8 +90,7 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
   const int dir = cluster_id & 1;
   const int gbase = (cluster_id >> 1) * NCHAIN;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t hbytes = 32u * H;             // bytes of one h buffer (16 batch x H bf16)
-  const uint32_t hall = (uint32_t)CS * 1024u;  // == hbytes
+  const uint32_t hall = (uint32_t)CS * 1024u;  // bytes of one h buffer (16 batch x H bf16)
 
   uint64_t* bars = (uint64_t*)(smem + L::kBarOff);
   uint64_t* hfull = bars;                      // [NCHAIN][2]
@@ -113,7 +101,7 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NCHAIN * 2; ++i) mbar_init(&hfull[i], 1);
-    for (int i = 0; i < NCHAIN; ++i) mbar_init(&accfull[i], 1);
+    for (int i = 0; i < NCHAIN; ++i) mbar_init(&accfull[i], NISS);
     for (int i = 0; i < NCHAIN * RGS; ++i) { mbar_init(&gfull[i], 1); mbar_init(&gempty[i], 1); }
     fence_mbar_init();
   }
@@ -127,18 +115,20 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tA = tmem;                    // columns [0, H/2): the weight slice
-  const uint32_t tAcc = tmem + 256;            // 16 columns per chain
+  const uint32_t tAcc = tmem + 256;            // [NCHAIN][NISS] accumulators of 16 columns
 
-  // ---- load this CTA's 128 x H bf16 weight slice into TMEM (chain-0 epilogue warps)
-  if (warp >= 2 && warp < 6) {
+  // ---- load this CTA's 128 x H bf16 weight slice into TMEM (chain-0 gate-math warps)
+  if (warp >= 5 && warp < 9) {
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const uint4* src = (const uint4*)(a.wpack + (((size_t)dir * CS + cta) * 128 + r) * H);
     for (int c0 = 0; c0 < H / 2; c0 += 32) {   // 32 TMEM columns = 64 bf16 = 8 x uint4
       uint32_t v[32];
+      const int nvec = (H / 2 - c0) >= 32 ? 8 : (H / 2 - c0) / 4;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const uint4 u = __ldg(&src[c0 / 4 + j]);
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (j < nvec) u = __ldg(&src[c0 / 4 + j]);
         v[4 * j] = u.x; v[4 * j + 1] = u.y; v[4 * j + 2] = u.z; v[4 * j + 3] = u.w;
       }
       tmem_st_32x32b_x32(tA + ((uint32_t)(q * 32) << 16) + c0, v);
@@ -150,9 +140,9 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
   tc_fence_after();
   cluster_sync();                              // every CTA has its barriers + zeroed buffers
 
-  if (warp == 0) {
-    // ------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+  if (warp < NISSW) {
+    // ------------------------------------------------------------- MMA issuers
+    if (lane == 0 && warp < NISS) {
       const uint32_t idesc = make_idesc_bf16(128, RN, 0, 0);
       uint32_t hphase = 0;                       // bit (c*2+p): parity of hfull[c][p]
       const uint64_t bdesc0 = make_smem_desc(smem_u32(smem + L::kHbufOff), 256, 128, 0);
@@ -170,18 +160,21 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
           const long long m1 = clock64();
           // one descriptor per buffer; the k-th step only moves the start address by 512 B
           const uint64_t bd0 = bdesc0 + (uint64_t)((c * 2 + p) * (L::kHbufBytes >> 4));
+          const uint32_t acc = tAcc + (c * NISS + warp) * RN;
 #pragma unroll
-          for (int k = 0; k < KS; ++k)
-            mma_ts(tAcc + c * RN, tA + k * 8, bd0 + (uint64_t)(k * 32), idesc, k > 0 ? 1u : 0u);
+          for (int kk = 0; kk < KPER; ++kk) {
+            const int k = warp * KPER + kk;
+            mma_ts(acc, tA + k * 8, bd0 + (uint64_t)(k * 32), idesc, kk > 0 ? 1u : 0u);
+          }
           mma_commit(&accfull[c]);
-          if (a.dbg && blockIdx.x == 0 && c == 0) {
+          if (a.dbg && blockIdx.x == 0 && c == 0 && warp == 0) {
             a.dbg[0] += m1 - m0;               // wait for h
-            a.dbg[1] += clock64() - m1;        // issue 32 MMAs + commit
+            a.dbg[1] += clock64() - m1;        // issue MMAs + commit
           }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 4) {
     // ------------------------------------------------------------- G producer (TMA)
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
@@ -192,23 +185,23 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
           if (gbase + c >= a.NG) continue;
           mbar_wait(&gempty[c * RGS + stage], phase ^ 1);
           mbar_expect_tx(&gfull[c * RGS + stage], 8192);
-          tma_load_4d(smem + L::kGOff + (c * RGS + stage) * 8192, &tmG, &gfull[c * RGS + stage],
-                      cta * RU, 0, dir, td * B + (gbase + c) * RN);
+          tma_load_3d(smem + L::kGOff + (c * RGS + stage) * 8192, &tmG, &gfull[c * RGS + stage],
+                      cta * 128, dir, td * B + (gbase + c) * RN);
         }
         if (++stage == RGS) { stage = 0; phase ^= 1; }
       }
     }
   } else {
     // ------------------------------------------------------------- gate math
-    const int c = (warp - 2) >> 2;              // chain of this warp
+    const int c = (warp - 5) >> 2;              // chain of this warp
     const int grp = gbase + c;
     if (grp < a.NG) {
       const int q = warp & 3;                   // TMEM lane quarter
       const int ug = lane >> 2, gq = lane & 3;
       const int ul = q * 8 + ug;                // unit inside the CTA
       const int u = cta * RU + ul;              // unit inside the layer
-      const int ctid = threadIdx.x - 64 - c * 128;   // 0..127 inside the chain
-      float* scr = (float*)(smem + L::kScrOff) + (size_t)(warp - 2) * 32 * RPITCH;
+      const int ctid = threadIdx.x - 160 - c * 128;   // 0..127 inside the chain
+      float* scr = (float*)(smem + L::kScrOff) + (size_t)(warp - 5) * 32 * RPITCH;
       uint8_t* stage_base = smem + L::kStageOff + c * 2 * 1024;
       int bidx[4], len[4];
       float cst[4], hst[4];
@@ -218,6 +211,9 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
         len[j] = bidx[j] < B ? a.seq_len[bidx[j]] : 0;
         cst[j] = 0.f; hst[j] = 0.f;
       }
+      // cooperative output store: thread ctid < 64 owns (batch row ob, 8-unit chunk okc)
+      const int ob = grp * RN + (ctid >> 2), okc = ctid & 3;
+      const int olen = (ctid < 64 && ob < B) ? a.seq_len[ob] : 0;
       float pwi = 0.f, pwf = 0.f, pwo = 0.f;
       if (a.use_peephole) { pwi = a.wi[dir][u]; pwf = a.wf[dir][u]; pwo = a.wo[dir][u]; }
       int stage = 0; uint32_t gph = 0;
@@ -228,15 +224,26 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
         mbar_wait(&accfull[c], t & 1);
         tc_fence_after();
         const long long e1 = clock64();
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(tAcc + c * RN + ((uint32_t)(q * 32) << 16), v);
-        tmem_ld_wait();
+        float v[16];
+        {
+          uint32_t w0[16];
+          tmem_ld_32x32b_x16(tAcc + (c * NISS) * RN + ((uint32_t)(q * 32) << 16), w0);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(w0[i]);
+#pragma unroll
+          for (int s = 1; s < NISS; ++s) {
+            uint32_t w1[16];
+            tmem_ld_32x32b_x16(tAcc + (c * NISS + s) * RN + ((uint32_t)(q * 32) << 16), w1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(w1[i]);
+          }
+        }
         // 4x4 transpose inside each 4-lane group through shared memory
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          *(float4*)&scr[lane * RPITCH + 4 * j] =
-              make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                          __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          *(float4*)&scr[lane * RPITCH + 4 * j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         __syncwarp();
         float z[4][4];                           // [gate][batch j]
 #pragma unroll
@@ -254,48 +261,38 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int bl = gq * 4 + j;
-          const float* Gb = Gs + bl * 128 + ul;   // [b][gate][32 u]
+          const float4 G4 = *(const float4*)(Gs + bl * 128 + ul * 4);   // [b][u][gate]
           const bool active = td < len[j];
           const float c_prev = cst[j];
           // branch-free so that the four cells of a thread interleave (ILP); inactive steps
           // (t >= seq_len) discard the result below
-          float zi = z[0][j] + Gb[0], zg = z[1][j] + Gb[32];
-          float zf = z[2][j] + Gb[64] + a.forget_bias, zo = z[3][j] + Gb[96];
+          float zi = z[0][j] + G4.x, zg = z[1][j] + G4.y;
+          float zf = z[2][j] + G4.z + a.forget_bias, zo = z[3][j] + G4.w;
           zi = fmaf(pwi, c_prev, zi); zf = fmaf(pwf, c_prev, zf);
           // three activations share one reciprocal: 1/((1+Ei)(1+Ef)(1+Eg))
           const float Ei = __expf(fminf(-zi, 25.f)), Ef = __expf(fminf(-zf, 25.f));
           const float Eg = __expf(fminf(-2.f * zg, 25.f));
           const float ai = 1.f + Ei, af = 1.f + Ef, ag = 1.f + Eg;
           const float r = fast_rcp(ai * af * ag);
-          float gi = r * af * ag, gf = r * ai * ag, gg = (1.f - Eg) * r * ai * af;
+          const float gi = r * af * ag, gf = r * ai * ag, gg = (1.f - Eg) * r * ai * af;
           float c_new = fmaf(gf, c_prev, gi * gg);
           if (a.cell_clip > 0.f) c_new = fminf(fmaxf(c_new, -a.cell_clip), a.cell_clip);
           zo = fmaf(pwo, c_new, zo);
           const float Eo = __expf(fminf(-zo, 25.f)), Ec = __expf(fminf(-2.f * c_new, 25.f));
           const float ao = 1.f + Eo, ac = 1.f + Ec;
           const float r2 = fast_rcp(ao * ac);
-          float go = r2 * ac;
-          float h_out = go * (1.f - Ec) * r2 * ao;
+          const float go = r2 * ac;
+          const float h_out = go * (1.f - Ec) * r2 * ao;
           c_new = active ? c_new : c_prev;
-          h_out = active ? h_out : 0.f;
           cst[j] = c_new;
           hst[j] = active ? h_out : hst[j];
           // state h (carried through inactive steps) feeds the next step's GEMM
           const int off = (ul >> 3) * 256 + (bl >> 3) * 128 + (bl & 7) * 16 + (ul & 7) * 2;
           *(__nv_bfloat16*)(stg + off) = __float2bfloat16(hst[j]);
-          if (bidx[j] < B) {
-            const size_t row = (size_t)td * B + bidx[j];
-            const size_t oidx = row * 2 * H + (size_t)dir * H + u;
-            float yv = h_out;
-            if (a.keep_prob < 1.f && active)
-              yv = dropout_keep(a.seed, oidx, a.keep_prob) ? h_out / a.keep_prob : 0.f;
-            a.y[oidx] = yv;
-            if (a.gates) {
-              float* gp = a.gates + (row * 2 + dir) * 4 * H;
-              gp[u] = gi; gp[H + u] = gg; gp[2 * H + u] = gf; gp[3 * H + u] = go;
-              a.cs[(row * 2 + dir) * H + u] = c_new;
-              a.hs[(row * 2 + dir) * H + u] = h_out;
-            }
+          if (a.gates && bidx[j] < B) {
+            const size_t cell = (((size_t)td * B + bidx[j]) * 2 + dir) * H + u;
+            *(float4*)(a.gates + cell * 4) = make_float4(gi, gg, gf, go);
+            a.cs[cell] = c_new;
           }
         }
         const long long e4 = clock64();
@@ -315,14 +312,47 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
             bulk_s2cluster(dst, stg, 1024, &hfull[c * 2 + (p ^ 1)], (uint32_t)dstcta);
           }
         }
+        // cooperative, coalesced output store off the critical path: 64 threads x 8 units
+        if (ctid < 64 && ob < B) {
+          const uint4 raw = *(const uint4*)(stg + okc * 256 + ((ctid >> 2) >> 3) * 128 + ((ctid >> 2) & 7) * 16);
+          const bool oact = td < olen;
+          const uint4 hv = oact ? raw : make_uint4(0, 0, 0, 0);
+          const size_t o0 = ((size_t)td * B + ob) * 2 * H + (size_t)dir * H + cta * RU + okc * 8;
+          if (a.hs_lp) *(uint4*)(a.hs_lp + o0) = hv;
+          const uint32_t w[4] = {hv.x, hv.y, hv.z, hv.w};
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            f[2 * i] = __uint_as_float(w[i] << 16);
+            f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+          }
+          if (a.keep_prob < 1.f) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              f[i] = dropout_keep(a.seed, o0 + i, a.keep_prob) ? f[i] / a.keep_prob : 0.f;
+            if (a.y_lp) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                __nv_bfloat162 b2v = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+                pk[i] = *(uint32_t*)&b2v;
+              }
+              *(uint4*)(a.y_lp + o0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          } else if (a.y_lp && a.y_lp != a.hs_lp) {
+            *(uint4*)(a.y_lp + o0) = hv;
+          }
+          *(float4*)(a.y + o0) = make_float4(f[0], f[1], f[2], f[3]);
+          *(float4*)(a.y + o0 + 4) = make_float4(f[4], f[5], f[6], f[7]);
+        }
         if (dbg) {
           const long long e6 = clock64();
           a.dbg[2] += e1 - e0;   // wait accumulator
           a.dbg[3] += e2 - e1;   // tmem ld + transpose
           a.dbg[4] += e3 - e2;   // wait G
-          a.dbg[5] += e4 - e3;   // gate math + stores
+          a.dbg[5] += e4 - e3;   // gate math + saves
           a.dbg[6] += e5 - e4;   // fence + named barrier
-          a.dbg[7] += e6 - e5;   // issue sends
+          a.dbg[7] += e6 - e5;   // sends + output store
         }
         if (++stage == RGS) { stage = 0; gph ^= 1; }
       }
@@ -336,44 +366,16 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
       }
     }
   }
-  (void)hbytes;
   tc_fence_before();
   __syncthreads();
   cluster_sync();                                // nobody exits while peers may still write here
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-// Wh [H, 4H] fp32 (rows D.. of the TF kernel) -> bf16 [CS][128][H], row = unit_local*4 + gate
-__global__ void pack_wh_kernel(const float* __restrict__ Wh, int H, uint16_t* __restrict__ out) {
-  const int64_t n = (int64_t)4 * H * H;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int k = (int)(i % H);
-    const int64_t rr = i / H;                  // cta*128 + r
-    const int r = (int)(rr % 128), cta = (int)(rr / 128);
-    const int ul = r >> 2, gate = r & 3;
-    const __nv_bfloat16 v = __float2bfloat16(Wh[(size_t)k * 4 * H + (size_t)gate * H + cta * RU + ul]);
-    out[i] = __bfloat16_as_ushort(v);
-  }
-}
-
 bool rec_tc_supported(int H) {
   if (H % RU) return false;
   const int cs = H / RU;
   return cs == 1 || cs == 2 || cs == 4 || cs == 8 || cs == 16;
-}
-
-size_t rec_tc_wpack_bytes(int H) { return (size_t)2 * 4 * H * H * 2; }
-
-int rec_tc_pack_weights(const float* kernel_fw, const float* kernel_bw, int D, int H,
-                        uint16_t* wpack, cudaStream_t stream) {
-  const float* k[2] = {kernel_fw, kernel_bw};
-  for (int dir = 0; dir < 2; ++dir) {
-    pack_wh_kernel<<<num_sms() * 4, 256, 0, stream>>>(k[dir] + (size_t)D * 4 * H, H,
-                                                      wpack + (size_t)dir * 4 * H * H);
-  }
-  B2_LAUNCH_CHECK();
-  return B2_OK;
 }
 
 template <int NCHAIN, int KS>
@@ -385,7 +387,7 @@ static int launch_rec_fwd(const CUtensorMap& tmG, const RecFwdArgs& a, int nclus
   if (CS > 8) B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(nclusters * CS);
-  cfg.blockDim = dim3(64 + 128 * NCHAIN);
+  cfg.blockDim = dim3(160 + 128 * NCHAIN);
   cfg.dynamicSmemBytes = L::kBytes;
   cfg.stream = stream;
   cudaLaunchAttribute at[1];
@@ -393,10 +395,11 @@ static int launch_rec_fwd(const CUtensorMap& tmG, const RecFwdArgs& a, int nclus
   at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   B2_CUDA(cudaLaunchKernelEx(&cfg, kern, tmG, a));
+  count_launches(1);
   return B2_OK;
 }
 
-// G: [T*B, 8H] fp32 gate pre-activations (column = dir*4H + gate*H + u)
+// G: [T*B, 8H] fp32 gate pre-activations, column = dir*4H + u*4 + gate (packed order)
 int rec_tc_forward(RecFwdArgs a, const float* G, int nchain, cudaStream_t stream) {
   const int H = a.H, CS = H / RU;
   a.NG = cdiv(a.B, RN);
@@ -404,10 +407,10 @@ int rec_tc_forward(RecFwdArgs a, const float* G, int nchain, cudaStream_t stream
   if (nchain > 2) nchain = 2;
   const int nclusters = 2 * cdiv(a.NG, nchain);
   CUtensorMap tmG;
-  const uint64_t dims[4] = {(uint64_t)H, 4, 2, (uint64_t)a.T * a.B};
-  const uint64_t strides[3] = {(uint64_t)H * 4, (uint64_t)4 * H * 4, (uint64_t)8 * H * 4};
-  const uint32_t box[4] = {RU, 4, 1, RN};
-  int rc = make_tmap_generic(&tmG, 1, G, 4, dims, strides, box, 0);
+  const uint64_t dims[3] = {(uint64_t)4 * H, 2, (uint64_t)a.T * a.B};
+  const uint64_t strides[2] = {(uint64_t)4 * H * 4, (uint64_t)8 * H * 4};
+  const uint32_t box[3] = {128, 1, RN};
+  int rc = make_tmap_generic(&tmG, 1, G, 3, dims, strides, box, 0);
   if (rc) return rc;
 #define B2_REC_DISPATCH(KS_)                                                          \
   if (H / 16 == KS_) {                                                               \
@@ -418,6 +421,309 @@ int rec_tc_forward(RecFwdArgs a, const float* G, int nchain, cudaStream_t stream
 #undef B2_REC_DISPATCH
   set_error("rec_tc_forward: unsupported H=%d", H);
   return B2_ERR_UNSUPPORTED;
+}
+
+// ======================================================================== backward
+// BPTT mirror.  Per step and chain:
+//   A) gate-math warps: dh = dy_t + sum over the 16 peers' partial (dz_{next} . Wh^T) slices,
+//      gate derivatives -> dz_t (bf16) into the local B-operand buffer and into dG (HBM);
+//   B) issuer warp m: D_m[128 units x 16] = Wh[128m.., this CTA's 128 gate cols] . dz_t^T
+//      (8 MMAs, A = transposed weight slice resident in TMEM);
+//   C) gate-math warps: accumulators -> bf16 -> one 1 KB slice per peer (its 32 units),
+//      bulk-copied into the peers' receive buffers (reduce-scatter over DSMEM).
+constexpr int BGS = 2;                        // TMA ring stages (backward)
+constexpr int BSTAGE = 8192 + 3 * 2048;       // gates | cs_t | cs_prev | dy
+
+template <int NCHAIN>
+struct RecBwdSmem {
+  static constexpr int kRecvOff = 0;                                     // [NCHAIN][2][16 KB]
+  static constexpr int kSendOff = kRecvOff + NCHAIN * 2 * 16384;         // [NCHAIN][2][16 KB]
+  static constexpr int kBopOff = kSendOff + NCHAIN * 2 * 16384;          // [NCHAIN][4 KB]
+  static constexpr int kRingOff = kBopOff + NCHAIN * 4096;               // [NCHAIN][BGS][BSTAGE]
+  static constexpr int kBarOff = kRingOff + NCHAIN * BGS * BSTAGE;
+  static constexpr int kBytes = kBarOff + 512;
+};
+
+template <int NCHAIN>
+__global__ void __launch_bounds__(160 + 128 * NCHAIN, 1)
+lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_constant__ CUtensorMap tmCs,
+                    const __grid_constant__ CUtensorMap tmDy, const RecBwdArgs a) {
+  using L = RecBwdSmem<NCHAIN>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int H = a.H, T = a.T, B = a.B;
+  const int CS = H / RU;
+  const int MT = (H + 127) / 128;              // M tiles of 128 "unit-in" rows
+  const uint32_t cta = cluster_ctarank();
+  const int cluster_id = blockIdx.x / CS;
+  const int dir = cluster_id & 1;
+  const int gbase = (cluster_id >> 1) * NCHAIN;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rall = (uint32_t)CS * 1024u;
+
+  uint64_t* bars = (uint64_t*)(smem + L::kBarOff);
+  uint64_t* rfull = bars;                      // [NCHAIN][2]  partial slices arrived
+  uint64_t* bready = bars + NCHAIN * 2;        // [NCHAIN]     dz_t staged for the MMA
+  uint64_t* accfull = bready + NCHAIN;         // [NCHAIN]
+  uint64_t* gfull = accfull + NCHAIN;          // [NCHAIN][BGS]
+  uint64_t* gempty = gfull + NCHAIN * BGS;     // [NCHAIN][BGS]
+  uint32_t* tmem_slot = (uint32_t*)(gempty + NCHAIN * BGS);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NCHAIN * 2; ++i) mbar_init(&rfull[i], 1);
+    for (int i = 0; i < NCHAIN; ++i) { mbar_init(&bready[i], 1); mbar_init(&accfull[i], MT); }
+    for (int i = 0; i < NCHAIN * BGS; ++i) { mbar_init(&gfull[i], 1); mbar_init(&gempty[i], 1); }
+    fence_mbar_init();
+  }
+  if (warp == 0) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tA = tmem;                    // tile m at columns [64m, 64m+64)
+  const uint32_t tAcc = tmem + 256;            // [NCHAIN][4] x 16 columns
+
+  if (warp >= 5 && warp < 9) {                 // transposed weight slice -> TMEM
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    for (int m = 0; m < MT; ++m) {
+      const uint4* src = (const uint4*)(a.wpackT + ((((size_t)dir * CS + cta) * 4 + m) * 128 + row) * 128);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 u = __ldg(&src[half * 8 + j]);
+          v[4 * j] = u.x; v[4 * j + 1] = u.y; v[4 * j + 2] = u.z; v[4 * j + 3] = u.w;
+        }
+        tmem_st_32x32b_x32(tA + ((uint32_t)(q * 32) << 16) + m * 64 + half * 32, v);
+      }
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  cluster_sync();
+
+  if (warp < NISSW) {
+    // ------------------------------------------------------------- MMA issuers (one M tile each)
+    if (lane == 0 && warp < MT) {
+      const uint32_t idesc = make_idesc_bf16(128, RN, 0, 0);
+      for (int s = 0; s + 1 < T; ++s) {
+#pragma unroll
+        for (int c = 0; c < NCHAIN; ++c) {
+          if (gbase + c >= a.NG) continue;
+          mbar_wait(&bready[c], s & 1);
+          tc_fence_after();
+          const uint64_t bd0 = make_smem_desc(smem_u32(smem + L::kBopOff + c * 4096), 256, 128, 0);
+          const uint32_t acc = tAcc + (c * 4 + warp) * RN;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            mma_ts(acc, tA + warp * 64 + kk * 8, bd0 + (uint64_t)(kk * 32), idesc, kk > 0 ? 1u : 0u);
+          mma_commit(&accfull[c]);
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int s = 0; s < T; ++s) {
+        const int td = dir ? s : T - 1 - s;
+        const int tp = dir ? td + 1 : td - 1;          // previous step in forward order
+#pragma unroll
+        for (int c = 0; c < NCHAIN; ++c) {
+          if (gbase + c >= a.NG) continue;
+          const int idx = c * BGS + stage;
+          mbar_wait(&gempty[idx], phase ^ 1);
+          mbar_expect_tx(&gfull[idx], BSTAGE);
+          uint8_t* st = smem + L::kRingOff + idx * BSTAGE;
+          const int row0 = td * B + (gbase + c) * RN;
+          const int rowp = ((tp >= 0 && tp < T) ? tp : td) * B + (gbase + c) * RN;
+          tma_load_3d(st, &tmGates, &gfull[idx], cta * 128, dir, row0);
+          tma_load_3d(st + 8192, &tmCs, &gfull[idx], cta * RU, dir, row0);
+          tma_load_3d(st + 8192 + 2048, &tmCs, &gfull[idx], cta * RU, dir, rowp);
+          tma_load_3d(st + 8192 + 4096, &tmDy, &gfull[idx], cta * RU, dir, row0);
+        }
+        if (++stage == BGS) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------- gate math
+    const int c = (warp - 5) >> 2;
+    const int grp = gbase + c;
+    if (grp < a.NG) {
+      const int q = warp & 3;
+      const int ug = lane >> 2, gq = lane & 3;
+      const int ul = q * 8 + ug;
+      const int u = cta * RU + ul;
+      const int ctid = threadIdx.x - 160 - c * 128;
+      int bidx[4], len[4];
+      float dcs[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        bidx[j] = grp * RN + gq * 4 + j;
+        len[j] = bidx[j] < B ? a.seq_len[bidx[j]] : 0;
+        dcs[j] = 0.f;
+      }
+      float pwi = 0.f, pwf = 0.f, pwo = 0.f;
+      if (a.use_peephole) { pwi = a.wi[dir][u]; pwf = a.wf[dir][u]; pwo = a.wo[dir][u]; }
+      uint8_t* bop = smem + L::kBopOff + c * 4096;
+      int stage = 0; uint32_t gph = 0;
+      uint32_t rph = 0;                          // bit p: parity of rfull[c][p]
+      for (int s = 0; s < T; ++s) {
+        const int td = dir ? s : T - 1 - s;
+        const int tn = dir ? td - 1 : td + 1;    // step processed just before (BPTT order)
+        const int tp = dir ? td + 1 : td - 1;    // previous step in forward order
+        const int p = s & 1;
+        // ---- A) dh_rec = sum of the peers' partial slices
+        float dh_rec[4] = {0.f, 0.f, 0.f, 0.f};
+        if (s > 0) {
+          mbar_wait_cluster(&rfull[c * 2 + p], (rph >> p) & 1u);
+          rph ^= 1u << p;
+          const uint8_t* rb = smem + L::kRecvOff + (c * 2 + p) * 16384 + (ul * 16 + gq * 4) * 2;
+          for (int src = 0; src < CS; ++src) {
+            const uint2 raw = *(const uint2*)(rb + src * 1024);
+            dh_rec[0] += __uint_as_float(raw.x << 16);
+            dh_rec[1] += __uint_as_float(raw.x & 0xffff0000u);
+            dh_rec[2] += __uint_as_float(raw.y << 16);
+            dh_rec[3] += __uint_as_float(raw.y & 0xffff0000u);
+          }
+        }
+        mbar_wait(&gfull[c * BGS + stage], gph);
+        const float* Rs = (const float*)(smem + L::kRingOff + (c * BGS + stage) * BSTAGE);
+        const bool tp_ok = tp >= 0 && tp < T;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int bl = gq * 4 + j;
+          const float4 g4 = *(const float4*)(Rs + bl * 128 + ul * 4);
+          const float cc = Rs[2048 + bl * 32 + ul];
+          const float c_prev = tp_ok ? Rs[2048 + 512 + bl * 32 + ul] : 0.f;
+          float dyv = Rs[2048 + 1024 + bl * 32 + ul];
+          const bool active = td < len[j];
+          const bool nb_active = s > 0 && tn >= 0 && tn < T && tn < len[j];
+          if (a.keep_prob < 1.f) {
+            const size_t oidx = ((size_t)td * B + bidx[j]) * 2 * H + (size_t)dir * H + u;
+            dyv = dropout_keep(a.seed, oidx, a.keep_prob) ? dyv / a.keep_prob : 0.f;
+          }
+          const float dh = dyv + (nb_active ? dh_rec[j] : 0.f);
+          const float dc_in = nb_active ? dcs[j] : 0.f;
+          const float gi = g4.x, gg = g4.y, gf = g4.z, go = g4.w;
+          const float Ec = __expf(fminf(-2.f * cc, 25.f));
+          const float tc = (1.f - Ec) * fast_rcp(1.f + Ec);
+          const float dzo = dh * tc * go * (1.f - go);
+          float dc = dc_in + dh * go * (1.f - tc * tc);
+          dc = fmaf(dzo, pwo, dc);
+          if (a.cell_clip > 0.f && fabsf(cc) >= a.cell_clip) dc = 0.f;
+          float dzi = dc * gg * gi * (1.f - gi);
+          float dzg = dc * gi * (1.f - gg * gg);
+          float dzf = dc * c_prev * gf * (1.f - gf);
+          const float dc_prev = fmaf(dzf, pwf, fmaf(dzi, pwi, dc * gf));
+          dcs[j] = active ? dc_prev : dcs[j];
+          dzi = active ? dzi : 0.f; dzg = active ? dzg : 0.f;
+          const float dzf2 = active ? dzf : 0.f, dzo2 = active ? dzo : 0.f;
+          __nv_bfloat162 lo = __floats2bfloat162_rn(dzi, dzg), hi = __floats2bfloat162_rn(dzf2, dzo2);
+          uint2 pk; pk.x = *(uint32_t*)&lo; pk.y = *(uint32_t*)&hi;
+          *(uint2*)(bop + (ul >> 1) * 256 + (bl >> 3) * 128 + (bl & 7) * 16 + (ul & 1) * 8) = pk;
+          if (bidx[j] < B)
+            *(uint2*)(a.dG + ((size_t)td * B + bidx[j]) * 8 * H + (size_t)dir * 4 * H + u * 4) = pk;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1 + c, 128);
+        if (ctid == 0) {
+          mbar_arrive(&gempty[c * BGS + stage]);
+          if (s + 1 < T) mbar_arrive(&bready[c]);
+        }
+        if (++stage == BGS) { stage = 0; gph ^= 1; }
+        if (s + 1 >= T) break;
+        // ---- C) partial dh of this step -> bf16 slices for the peers
+        mbar_wait(&accfull[c], s & 1);
+        tc_fence_after();
+        uint8_t* sst = smem + L::kSendOff + (c * 2 + (p ^ 1)) * 16384;
+        for (int m = 0; m < MT; ++m) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(tAcc + (c * 4 + m) * RN + ((uint32_t)(q * 32) << 16), v);
+          tmem_ld_wait();
+          const int dest = m * 4 + q;
+          if (dest < CS) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __nv_bfloat162 b2v = __floats2bfloat162_rn(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+              pk[i] = *(uint32_t*)&b2v;
+            }
+            uint4* d4 = (uint4*)(sst + dest * 1024 + lane * 32);
+            d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        named_bar_sync(1 + c, 128);
+        if (ctid == 0) mbar_expect_tx(&rfull[c * 2 + (p ^ 1)], rall);
+        {
+          const int dstcta = q * 4 + lane;
+          if (lane < 4 && dstcta < CS) {
+            uint8_t* dst = smem + L::kRecvOff + (c * 2 + (p ^ 1)) * 16384 + cta * 1024;
+            bulk_s2cluster(dst, sst + dstcta * 1024, 1024, &rfull[c * 2 + (p ^ 1)], (uint32_t)dstcta);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <int NCHAIN>
+static int launch_rec_bwd(const CUtensorMap& tg, const CUtensorMap& tc, const CUtensorMap& td,
+                          const RecBwdArgs& a, int nclusters, int CS, cudaStream_t stream) {
+  using L = RecBwdSmem<NCHAIN>;
+  auto kern = lstm_rec_bwd_kernel<NCHAIN>;
+  B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes));
+  if (CS > 8) B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nclusters * CS);
+  cfg.blockDim = dim3(160 + 128 * NCHAIN);
+  cfg.dynamicSmemBytes = L::kBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  B2_CUDA(cudaLaunchKernelEx(&cfg, kern, tg, tc, td, a));
+  count_launches(1);
+  return B2_OK;
+}
+
+int rec_tc_backward(RecBwdArgs a, const float* dy, int nchain, cudaStream_t stream) {
+  const int H = a.H, CS = H / RU;
+  a.NG = cdiv(a.B, RN);
+  if (nchain < 1) nchain = (a.NG >= 2) ? 2 : 1;
+  if (nchain > 2) nchain = 2;
+  const int nclusters = 2 * cdiv(a.NG, nchain);
+  const uint64_t TB = (uint64_t)a.T * a.B;
+  CUtensorMap tg, tc, td;
+  {
+    const uint64_t dims[3] = {(uint64_t)4 * H, 2, TB};
+    const uint64_t strides[2] = {(uint64_t)4 * H * 4, (uint64_t)8 * H * 4};
+    const uint32_t box[3] = {128, 1, RN};
+    int rc = make_tmap_generic(&tg, 1, a.gates, 3, dims, strides, box, 0);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)H, 2, TB};
+    const uint64_t strides[2] = {(uint64_t)H * 4, (uint64_t)2 * H * 4};
+    const uint32_t box[3] = {RU, 1, RN};
+    int rc = make_tmap_generic(&tc, 1, a.cs, 3, dims, strides, box, 0);
+    if (rc) return rc;
+    rc = make_tmap_generic(&td, 1, dy, 3, dims, strides, box, 0);
+    if (rc) return rc;
+  }
+  if (nchain == 2) return launch_rec_bwd<2>(tg, tc, td, a, nclusters, CS, stream);
+  return launch_rec_bwd<1>(tg, tc, td, a, nclusters, CS, stream);
 }
 
 }  // namespace b2

@@ -1,0 +1,324 @@
+// bf16 / tcgen05 BLSTM layer: orchestration of the time-batched GEMMs (gemm_tcgen05.cu)
+// around the persistent recurrence kernels (lstm_rec_tc.cu), plus the weight packing that
+// puts every operand in the order those kernels want.
+//
+// Packed gate order: column n' = dir*4H + u*4 + gate (unit-major, gate-minor) instead of
+// TensorFlow's dir / gate*H + u (models/encoders/core/blstm.py:287-305 via LSTMBlockCell):
+// a CTA that owns 32 units then reads/writes one contiguous 128-float segment per frame.
+// The permutation is applied once per step to the (small) weights; activations, gate
+// pre-activations G and gate gradients dG live only in packed order.
+#include "lstm_rec_tc.cuh"
+
+namespace b2 {
+
+enum { EPI_STORE_F32 = 0, EPI_ATOMIC_F32 = 1, EPI_STORE_BF16 = 2 };
+
+static size_t pad8(size_t x) { return (x + 7) / 8 * 8; }
+
+struct TcWork {
+  float* G;                  // [TB, 8H] fp32 gate pre-activations (forward)
+  __nv_bfloat16* dG;         // [TB, 8H] bf16 gate gradients (backward)
+  __nv_bfloat16* xb;         // [TB, pad8(D)] bf16 copy of x when the caller has none
+  __nv_bfloat16* wx;         // [D, 8H] packed input weights
+  float* bias;               // [8H] packed bias
+  uint16_t* wh;              // forward recurrent pack  [2][CS][128][H]
+  uint16_t* whT;             // backward recurrent pack [2][CS][4][128][128]
+  float* dwx;                // [D, 8H] fp32 packed weight gradient (scratch)
+  float* dwh;                // [2][H, 4H] fp32 packed recurrent weight gradient (scratch)
+  float* dbias;              // [8H]
+};
+
+static size_t tc_work_layout(const b2_lstm_desc* d, void* base, TcWork* w) {
+  const size_t TB = (size_t)d->T * d->B, H = d->H, D = d->D_in;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
+  // G (forward) and dG (backward) are never live together
+  const size_t oG = take(TB * 8 * H * 4);
+  const size_t oxb = take(TB * pad8(D) * 2);
+  const size_t owx = take(D * 8 * H * 2);
+  const size_t ob = take(8 * H * 4);
+  const size_t owh = take(2 * 4 * H * H * 2);
+  const size_t owt = take(2 * 4 * H * H * 2);
+  const size_t odwx = take(D * 8 * H * 4);
+  const size_t odwh = take(2 * H * 4 * H * 4);
+  const size_t odb = take(8 * H * 4);
+  if (w) {
+    char* p = (char*)base;
+    w->G = (float*)(p + oG); w->dG = (__nv_bfloat16*)(p + oG); w->xb = (__nv_bfloat16*)(p + oxb);
+    w->wx = (__nv_bfloat16*)(p + owx); w->bias = (float*)(p + ob); w->wh = (uint16_t*)(p + owh);
+    w->whT = (uint16_t*)(p + owt); w->dwx = (float*)(p + odwx); w->dwh = (float*)(p + odwh);
+    w->dbias = (float*)(p + odb);
+  }
+  return off;
+}
+
+// ---------------------------------------------------------------- packing kernels
+// kernel_dir [(D+H), 4H] fp32 (TF layout) ->
+//   wx  [D, 8H] bf16   wx[k][dir*4H + u*4 + g]          = kernel_dir[k][g*H + u]
+//   bias[8H]    fp32   bias[dir*4H + u*4 + g]           = bias_dir[g*H + u]
+//   wh  [2][CS][128][H]      wh[dir][cta][ul*4+g][k]    = kernel_dir[D + k][g*H + cta*32 + ul]
+//   whT [2][CS][4][128][128] whT[dir][cta][m][i][ul*4+g] = kernel_dir[D + 128m + i][g*H + cta*32 + ul]
+__global__ void pack_lstm_weights_kernel(const float* __restrict__ k0, const float* __restrict__ k1,
+                                         const float* __restrict__ b0, const float* __restrict__ b1,
+                                         int D, int H, __nv_bfloat16* __restrict__ wx,
+                                         float* __restrict__ bias, uint16_t* __restrict__ wh,
+                                         uint16_t* __restrict__ whT) {
+  const int64_t n_wx = (int64_t)D * 8 * H, n_wh = (int64_t)2 * 4 * H * H;
+  const int64_t total = n_wx + 8 * H + n_wh + (whT ? n_wh : 0);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < n_wx) {
+      const int col = (int)(i % (8 * H)); const int k = (int)(i / (8 * H));
+      const int dir = col / (4 * H), r = col % (4 * H), u = r >> 2, g = r & 3;
+      wx[i] = __float2bfloat16((dir ? k1 : k0)[(size_t)k * 4 * H + g * H + u]);
+    } else if (i < n_wx + 8 * H) {
+      const int col = (int)(i - n_wx);
+      const int dir = col / (4 * H), r = col % (4 * H), u = r >> 2, g = r & 3;
+      bias[col] = (dir ? b1 : b0)[g * H + u];
+    } else if (i < n_wx + 8 * H + n_wh) {
+      const int64_t j = i - n_wx - 8 * H;
+      const int k = (int)(j % H); const int64_t rr = j / H;          // rr = dir*4H + cta*128 + r
+      const int dir = (int)(rr / (4 * H)); const int q = (int)(rr % (4 * H));
+      const int cta = q / 128, r = q % 128, ul = r >> 2, g = r & 3;
+      const float v = (dir ? k1 : k0)[(size_t)(D + k) * 4 * H + g * H + cta * 32 + ul];
+      wh[j] = __bfloat16_as_ushort(__float2bfloat16(v));
+    } else {
+      const int64_t j = i - n_wx - 8 * H - n_wh;
+      const int r = (int)(j % 128); const int64_t t1 = j / 128;
+      const int row = (int)(t1 % 128); const int64_t t2 = t1 / 128;
+      const int m = (int)(t2 % 4); const int64_t t3 = t2 / 4;
+      const int CS = H / 32;
+      const int cta = (int)(t3 % CS), dir = (int)(t3 / CS);
+      const int ul = r >> 2, g = r & 3;
+      float v = 0.f;
+      if (128 * m + row < H)
+        v = (dir ? k1 : k0)[(size_t)(D + 128 * m + row) * 4 * H + g * H + cta * 32 + ul];
+      whT[j] = __bfloat16_as_ushort(__float2bfloat16(v));
+    }
+  }
+}
+
+// scatter-add packed gradients back into the TF layout:
+//   gk_dir[k][g*H+u]      += dwx[k][dir*4H + u*4 + g]              k < D
+//   gk_dir[D+k][g*H+u]    += dwh[dir][k][u*4 + g]
+//   gb_dir[g*H+u]         += dbias[dir*4H + u*4 + g]
+__global__ void unpack_lstm_grads_kernel(const float* __restrict__ dwx, const float* __restrict__ dwh,
+                                         const float* __restrict__ dbias, int D, int H,
+                                         float* __restrict__ gk0, float* __restrict__ gk1,
+                                         float* __restrict__ gb0, float* __restrict__ gb1) {
+  const int64_t n_wx = (int64_t)D * 8 * H, n_wh = (int64_t)2 * H * 4 * H;
+  const int64_t total = n_wx + n_wh + 8 * H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < n_wx) {
+      const int col = (int)(i % (8 * H)); const int k = (int)(i / (8 * H));
+      const int dir = col / (4 * H), r = col % (4 * H), u = r >> 2, g = r & 3;
+      (dir ? gk1 : gk0)[(size_t)k * 4 * H + g * H + u] += dwx[i];
+    } else if (i < n_wx + n_wh) {
+      const int64_t j = i - n_wx;
+      const int r = (int)(j % (4 * H)); const int64_t t1 = j / (4 * H);
+      const int k = (int)(t1 % H), dir = (int)(t1 / H);
+      const int u = r >> 2, g = r & 3;
+      (dir ? gk1 : gk0)[(size_t)(D + k) * 4 * H + g * H + u] += dwh[j];
+    } else {
+      const int col = (int)(i - n_wx - n_wh);
+      const int dir = col / (4 * H), r = col % (4 * H), u = r >> 2, g = r & 3;
+      (dir ? gb1 : gb0)[g * H + u] += dbias[col];
+    }
+  }
+}
+
+// bias + peephole gradients from the packed bf16 dG and the saved cell states
+// grid = (ceil(H/32), slabs, 2 dirs); block 256 = 8 row-lanes x 32 units
+__global__ void __launch_bounds__(256)
+tc_small_grads_kernel(const __nv_bfloat16* __restrict__ dG, const float* __restrict__ cs,
+                      const int* __restrict__ seq_len, int T, int B, int H, int use_peephole,
+                      float* __restrict__ dbias, float* dwi0, float* dwf0, float* dwo0,
+                      float* dwi1, float* dwf1, float* dwo1) {
+  __shared__ float sh[7][8][33];
+  const int dir = blockIdx.z;
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  const int u = blockIdx.x * 32 + lane;
+  float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // db_i, db_g, db_f, db_o, dwi, dwf, dwo
+  if (u < H) {
+    const int64_t rows = (int64_t)T * B;
+    for (int64_t r = (int64_t)blockIdx.y * 8 + wy; r < rows; r += (int64_t)gridDim.y * 8) {
+      const int t = (int)(r / B), b = (int)(r % B);
+      const int len = seq_len[b];
+      if (t >= len) continue;
+      const uint2 raw = *(const uint2*)(dG + r * 8 * H + (size_t)dir * 4 * H + u * 4);
+      const float dzi = __uint_as_float(raw.x << 16), dzg = __uint_as_float(raw.x & 0xffff0000u);
+      const float dzf = __uint_as_float(raw.y << 16), dzo = __uint_as_float(raw.y & 0xffff0000u);
+      acc[0] += dzi; acc[1] += dzg; acc[2] += dzf; acc[3] += dzo;
+      if (use_peephole) {
+        const float c = cs[(r * 2 + dir) * H + u];
+        const int tp = dir == 0 ? t - 1 : t + 1;
+        float cp = 0.f;
+        if (tp >= 0 && tp < T && tp < len) cp = cs[(((int64_t)tp * B + b) * 2 + dir) * H + u];
+        acc[4] = fmaf(dzi, cp, acc[4]); acc[5] = fmaf(dzf, cp, acc[5]); acc[6] = fmaf(dzo, c, acc[6]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 7; ++k) sh[k][wy][lane] = acc[k];
+  __syncthreads();
+  if (wy == 0 && u < H) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+      for (int j = 1; j < 8; ++j) acc[k] += sh[k][j][lane];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) atomicAdd(&dbias[(size_t)dir * 4 * H + u * 4 + g], acc[g]);
+    if (use_peephole) {
+      atomicAdd((dir ? dwi1 : dwi0) + u, acc[4]);
+      atomicAdd((dir ? dwf1 : dwf0) + u, acc[5]);
+      atomicAdd((dir ? dwo1 : dwo0) + u, acc[6]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ layer entry points
+bool tc_layer_supported(const b2_lstm_desc* d) {
+  static int sm100 = -1;
+  if (d->precision != B2_PREC_BF16 || !rec_tc_supported(d->H)) return false;
+  if (!env_int("B2_REC_TC", 1)) return false;
+  if (sm100 < 0) sm100 = b2_device_is_sm100();
+  return sm100 == 1;
+}
+
+size_t tc_layer_workspace_bytes(const b2_lstm_desc* d) { return tc_work_layout(d, nullptr, nullptr); }
+
+static int pack_weights(const b2_lstm_desc* d, const b2_lstm_params* fw, const b2_lstm_params* bw,
+                        const TcWork& w, bool need_T, cudaStream_t stream) {
+  pack_lstm_weights_kernel<<<num_sms() * 8, 256, 0, stream>>>(
+      fw->kernel, bw->kernel, fw->bias, bw->bias, d->D_in, d->H, w.wx, w.bias, w.wh,
+      need_T ? w.whT : nullptr);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+int tc_layer_forward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16* x_lp,
+                     const int32_t* seq_len, const b2_lstm_params* fw, const b2_lstm_params* bw,
+                     float* y, float* final_state, void* reserve, void* workspace,
+                     size_t workspace_bytes, cudaStream_t stream) {
+  TcWork w;
+  const size_t need = tc_work_layout(d, workspace, &w);
+  if (workspace_bytes < need) { set_error("tc_layer_forward: workspace %zu < %zu", workspace_bytes, need); return B2_ERR_WORKSPACE; }
+  Reserve r;
+  reserve_layout(d, reserve, &r);
+  const int T = d->T, B = d->B, D = d->D_in, H = d->H, TB = T * B;
+  int rc = pack_weights(d, fw, bw, w, false, stream);
+  if (rc) return rc;
+  const __nv_bfloat16* xa = x_lp;
+  int ldx = D;
+  if (!xa || (D % 8)) {
+    ldx = (int)pad8(D);
+    rc = cast_f32_bf16(x, TB, D, D, w.xb, ldx, stream);
+    if (rc) return rc;
+    xa = w.xb;
+  }
+  // G[TB, 8H] = X . Wx_packed + bias_packed   (both directions in one GEMM)
+  rc = gemm_bf16_tc(0, 1, TB, 8 * H, D, 1.f, xa, ldx, w.wx, 8 * H, w.G, 8 * H, w.bias,
+                    EPI_STORE_F32, 0, stream);
+  if (rc) return rc;
+  RecFwdArgs ra;
+  ra.T = T; ra.B = B; ra.H = H; ra.NG = 0; ra.seq_len = seq_len; ra.wpack = w.wh;
+  const b2_lstm_params* P[2] = {fw, bw};
+  for (int dir = 0; dir < 2; ++dir) {
+    ra.wi[dir] = P[dir]->w_i_diag; ra.wf[dir] = P[dir]->w_f_diag; ra.wo[dir] = P[dir]->w_o_diag;
+  }
+  ra.use_peephole = d->use_peephole; ra.forget_bias = d->forget_bias; ra.cell_clip = d->cell_clip;
+  ra.keep_prob = d->keep_prob; ra.seed = d->dropout_seed;
+  ra.y = y; ra.hs_lp = r.hs_lp; ra.y_lp = r.y_lp;
+  ra.gates = d->need_backward ? r.gates : nullptr; ra.cs = d->need_backward ? r.cs : nullptr;
+  ra.final_state = final_state; ra.dbg = nullptr;
+  if (env_int("B2_REC_DBG", 0)) {
+    static long long* dbg_buf = nullptr;
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 64 * sizeof(long long));
+    cudaMemsetAsync(dbg_buf, 0, 64 * sizeof(long long), stream);
+    ra.dbg = dbg_buf;
+    rc = rec_tc_forward(ra, w.G, env_int("B2_REC_NCHAIN", 0), stream);
+    long long hb[8];
+    cudaMemcpyAsync(hb, dbg_buf, sizeof(hb), cudaMemcpyDeviceToHost, stream);
+    cudaStreamSynchronize(stream);
+    fprintf(stderr, "[rec fwd dbg] cycles/step: mma_wait_h=%lld mma_issue=%lld | epi wait_acc=%lld "
+            "ld+transpose=%lld wait_G=%lld math+saves=%lld fence+bar=%lld send+store=%lld\n",
+            hb[0] / T, hb[1] / T, hb[2] / T, hb[3] / T, hb[4] / T, hb[5] / T, hb[6] / T, hb[7] / T);
+    return rc;
+  }
+  return rec_tc_forward(ra, w.G, env_int("B2_REC_NCHAIN", 0), stream);
+}
+
+int tc_layer_backward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16* x_lp,
+                      const int32_t* seq_len, const b2_lstm_params* fw, const b2_lstm_params* bw,
+                      const float* dy, const void* reserve, float* dx, const b2_lstm_grads* g_fw,
+                      const b2_lstm_grads* g_bw, void* workspace, size_t workspace_bytes,
+                      cudaStream_t stream) {
+  TcWork w;
+  const size_t need = tc_work_layout(d, workspace, &w);
+  if (workspace_bytes < need) { set_error("tc_layer_backward: workspace %zu < %zu", workspace_bytes, need); return B2_ERR_WORKSPACE; }
+  Reserve r;
+  reserve_layout(d, (void*)reserve, &r);
+  const int T = d->T, B = d->B, D = d->D_in, H = d->H, TB = T * B;
+  int rc = pack_weights(d, fw, bw, w, true, stream);
+  if (rc) return rc;
+  // 1. BPTT recurrence -> dG (bf16, packed order)
+  RecBwdArgs ba;
+  ba.T = T; ba.B = B; ba.H = H; ba.NG = 0; ba.seq_len = seq_len; ba.wpackT = w.whT;
+  const b2_lstm_params* P[2] = {fw, bw};
+  for (int dir = 0; dir < 2; ++dir) {
+    ba.wi[dir] = P[dir]->w_i_diag; ba.wf[dir] = P[dir]->w_f_diag; ba.wo[dir] = P[dir]->w_o_diag;
+  }
+  ba.use_peephole = d->use_peephole; ba.cell_clip = d->cell_clip; ba.keep_prob = d->keep_prob;
+  ba.seed = d->dropout_seed; ba.gates = r.gates; ba.cs = r.cs; ba.dG = w.dG; ba.dfinal = nullptr;
+  ba.dbg = nullptr;
+  rc = rec_tc_backward(ba, dy, env_int("B2_REC_NCHAIN", 0), stream);
+  if (rc) return rc;
+  // 2. bias + peephole gradients
+  B2_CUDA(cudaMemsetAsync(w.dbias, 0, (size_t)8 * H * 4, stream));
+  {
+    int slabs = cdiv(TB, 64); if (slabs > 128) slabs = 128;
+    dim3 pg(cdiv(H, 32), slabs, 2);
+    tc_small_grads_kernel<<<pg, 256, 0, stream>>>(w.dG, r.cs, seq_len, T, B, H, d->use_peephole,
+                                                 w.dbias, g_fw->w_i_diag, g_fw->w_f_diag,
+                                                 g_fw->w_o_diag, g_bw->w_i_diag, g_bw->w_f_diag,
+                                                 g_bw->w_o_diag);
+    B2_LAUNCH_CHECK();
+  }
+  // 3. time-batched GEMMs on packed operands
+  const __nv_bfloat16* xa = x_lp;
+  int ldx = D;
+  if (!xa || (D % 8)) {
+    ldx = (int)pad8(D);
+    rc = cast_f32_bf16(x, TB, D, D, w.xb, ldx, stream);
+    if (rc) return rc;
+    xa = w.xb;
+  }
+  if (dx) {   // dX[TB, D] = dG[TB, 8H] . Wx_packed^T  (sums both directions)
+    rc = gemm_bf16_tc(0, 0, TB, D, 8 * H, 1.f, w.dG, 8 * H, w.wx, 8 * H, dx, D, nullptr,
+                      EPI_STORE_F32, 0, stream);
+    if (rc) return rc;
+  }
+  // dWx_packed[D, 8H] = X^T . dG
+  B2_CUDA(cudaMemsetAsync(w.dwx, 0, (size_t)D * 8 * H * 4, stream));
+  rc = gemm_bf16_tc(1, 1, D, 8 * H, TB, 1.f, xa, ldx, w.dG, 8 * H, w.dwx, 8 * H, nullptr,
+                    EPI_ATOMIC_F32, 0, stream);
+  if (rc) return rc;
+  // dWh_packed[dir][H, 4H] = Hprev_dir^T . dG_dir   (hs shifted by one step)
+  B2_CUDA(cudaMemsetAsync(w.dwh, 0, (size_t)2 * H * 4 * H * 4, stream));
+  if (T > 1) {
+    for (int dir = 0; dir < 2; ++dir) {
+      const __nv_bfloat16* ha = r.hs_lp + (size_t)dir * H + (dir == 0 ? 0 : (size_t)B * 2 * H);
+      const __nv_bfloat16* gb = w.dG + (size_t)dir * 4 * H + (dir == 0 ? (size_t)B * 8 * H : 0);
+      rc = gemm_bf16_tc(1, 1, H, 4 * H, (T - 1) * B, 1.f, ha, 2 * H, gb, 8 * H,
+                        w.dwh + (size_t)dir * H * 4 * H, 4 * H, nullptr, EPI_ATOMIC_F32, 0, stream);
+      if (rc) return rc;
+    }
+  }
+  unpack_lstm_grads_kernel<<<num_sms() * 8, 256, 0, stream>>>(w.dwx, w.dwh, w.dbias, D, H,
+                                                            g_fw->kernel, g_bw->kernel, g_fw->bias,
+                                                            g_bw->bias);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+}  // namespace b2

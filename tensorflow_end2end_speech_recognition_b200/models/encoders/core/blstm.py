@@ -85,6 +85,7 @@ class BLSTMEncoder(object):
         prec = ops.PREC_BF16 if self.precision == "bf16" else ops.PREC_FP32
         saved = []
         fs = None
+        x_lp = 0
         for i_layer in range(1, self.num_layers + 1):
             desc = ops.lstm_desc(T, B, x.shape[2], self.num_units, use_peephole=self._peephole,
                                  forget_bias=1.0, cell_clip=self._clip, keep_prob=float(keep_prob),
@@ -93,9 +94,11 @@ class BLSTMEncoder(object):
             pf = self._layer_params(variables, i_layer, "fw")
             pb = self._layer_params(variables, i_layer, "bw")
             y, fs, reserve = ops.blstm_layer_forward(desc, x, inputs_seq_len, pf, pb,
-                                                     want_final_state=(i_layer == self.num_layers))
-            saved.append((desc, x, reserve, i_layer))
+                                                     want_final_state=(i_layer == self.num_layers),
+                                                     x_lp=x_lp)
+            saved.append((desc, x, reserve, i_layer, x_lp))
             x = y
+            x_lp = ops.reserve_y_lp(desc, reserve)   # bf16 shadow feeds the next layer's GEMM
         self._saved = (saved, inputs_seq_len)
         outputs = x if self.time_major else ops.transpose_01(x)
         final_state = None
@@ -109,13 +112,13 @@ class BLSTMEncoder(object):
         ``variables``); calls ``on_layer_done(i_layer)`` when a layer's gradients are final."""
         saved, seq_len = self._saved
         dy = d_outputs
-        for desc, x, reserve, i_layer in reversed(saved):
+        for desc, x, reserve, i_layer, x_lp in reversed(saved):
             pf = self._layer_params(variables, i_layer, "fw")
             pb = self._layer_params(variables, i_layer, "bw")
             gf = self._layer_params(grads, i_layer, "fw")
             gb = self._layer_params(grads, i_layer, "bw")
             dy = ops.blstm_layer_backward(desc, x, seq_len, pf, pb, dy, reserve, gf, gb,
-                                          need_dx=(i_layer > 1 or need_dx))
+                                          need_dx=(i_layer > 1 or need_dx), x_lp=x_lp)
             if on_layer_done is not None:
                 on_layer_done(i_layer)
         self._saved = None

@@ -172,27 +172,35 @@ def lstm_desc(T, B, D_in, H, use_peephole=True, forget_bias=1.0, cell_clip=None,
                     int(precision), int(bool(need_backward)))
 
 
-def blstm_layer_forward(desc, x, seq_len, p_fw, p_bw, want_final_state=False):
-    """x [T,B,D] -> (y [T,B,2H], final_state [4,B,H] or None, reserve buffer)."""
+def blstm_layer_forward(desc, x, seq_len, p_fw, p_bw, want_final_state=False, x_lp=0):
+    """x [T,B,D] -> (y [T,B,2H], final_state [4,B,H] or None, reserve buffer).
+    x_lp: raw device pointer of a bf16 shadow of x (from reserve_y_lp of the layer below) or 0."""
     lib = _lib.load()
     _require_cuda(x, seq_len)
     dev = x.device
     y = torch.empty((desc.T, desc.B, 2 * desc.H), dtype=torch.float32, device=dev)
     fs = torch.empty((4, desc.B, desc.H), dtype=torch.float32, device=dev) if want_final_state else None
-    reserve = None
-    if desc.need_backward:
-        reserve = torch.empty(lib.b2_blstm_reserve_bytes(C.byref(desc)), dtype=torch.uint8, device=dev)
+    # the bf16 path keeps its bf16 output shadow in `reserve` even for inference
+    reserve = torch.empty(lib.b2_blstm_reserve_bytes(C.byref(desc)), dtype=torch.uint8, device=dev)
     nbytes = lib.b2_blstm_workspace_bytes(C.byref(desc))
     ws = workspace("lstm", nbytes, dev)
     fw, bw = _params_struct(p_fw), _params_struct(p_bw)
-    rc = lib.b2_blstm_layer_forward(C.byref(desc), _ptr(x.contiguous()), _ptr(seq_len), C.byref(fw),
+    rc = lib.b2_blstm_layer_forward(C.byref(desc), _ptr(x.contiguous()), C.c_void_p(x_lp or 0),
+                                    _ptr(seq_len), C.byref(fw),
                                     C.byref(bw), _ptr(y), _ptr(fs), _ptr(reserve), _ptr(ws), nbytes,
                                     _stream())
     _lib.check(rc, "b2_blstm_layer_forward")
     return y, fs, reserve
 
 
-def blstm_layer_backward(desc, x, seq_len, p_fw, p_bw, dy, reserve, g_fw, g_bw, need_dx=True):
+def reserve_y_lp(desc, reserve):
+    """raw device pointer (int) of the bf16 layer output kept in `reserve`, or 0."""
+    if reserve is None:
+        return 0
+    return _lib.load().b2_blstm_reserve_y_lp(C.byref(desc), _ptr(reserve)) or 0
+
+
+def blstm_layer_backward(desc, x, seq_len, p_fw, p_bw, dy, reserve, g_fw, g_bw, need_dx=True, x_lp=0):
     """Accumulates into the gradient dicts g_fw / g_bw; returns dx [T,B,D] or None."""
     lib = _lib.load()
     _require_cuda(x, dy)
@@ -202,7 +210,8 @@ def blstm_layer_backward(desc, x, seq_len, p_fw, p_bw, dy, reserve, g_fw, g_bw, 
     ws = workspace("lstm", nbytes, dev)
     fw, bw = _params_struct(p_fw), _params_struct(p_bw)
     gf, gb = _params_struct(g_fw), _params_struct(g_bw)
-    rc = lib.b2_blstm_layer_backward(C.byref(desc), _ptr(x.contiguous()), _ptr(seq_len), C.byref(fw),
+    rc = lib.b2_blstm_layer_backward(C.byref(desc), _ptr(x.contiguous()), C.c_void_p(x_lp or 0),
+                                     _ptr(seq_len), C.byref(fw),
                                      C.byref(bw), _ptr(dy.contiguous()), _ptr(reserve), _ptr(dx),
                                      C.byref(gf), C.byref(gb), _ptr(ws), nbytes, _stream())
     _lib.check(rc, "b2_blstm_layer_backward")
