@@ -258,16 +258,20 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
         const float* Gs = (const float*)(smem + L::kGOff + (c * RGS + stage) * 8192);
         const int p = t & 1;
         uint8_t* stg = stage_base + p * 1024;
+        // loads first, stores last: a shared-memory store between two cells would serialise
+        // them (the compiler must assume it aliases the next cell's loads)
+        float4 G4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) G4[j] = *(const float4*)(Gs + (gq * 4 + j) * 128 + ul * 4);   // [b][u][gate]
+        float4 gsv[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int bl = gq * 4 + j;
-          const float4 G4 = *(const float4*)(Gs + bl * 128 + ul * 4);   // [b][u][gate]
           const bool active = td < len[j];
           const float c_prev = cst[j];
           // branch-free so that the four cells of a thread interleave (ILP); inactive steps
           // (t >= seq_len) discard the result below
-          float zi = z[0][j] + G4.x, zg = z[1][j] + G4.y;
-          float zf = z[2][j] + G4.z + a.forget_bias, zo = z[3][j] + G4.w;
+          float zi = z[0][j] + G4[j].x, zg = z[1][j] + G4[j].y;
+          float zf = z[2][j] + G4[j].z + a.forget_bias, zo = z[3][j] + G4[j].w;
           zi = fmaf(pwi, c_prev, zi); zf = fmaf(pwf, c_prev, zf);
           // three activations share one reciprocal: 1/((1+Ei)(1+Ef)(1+Eg))
           const float Ei = __expf(fminf(-zi, 25.f)), Ef = __expf(fminf(-zf, 25.f));
@@ -283,17 +287,25 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
           const float r2 = fast_rcp(ao * ac);
           const float go = r2 * ac;
           const float h_out = go * (1.f - Ec) * r2 * ao;
-          c_new = active ? c_new : c_prev;
-          cst[j] = c_new;
+          cst[j] = active ? c_new : c_prev;
           hst[j] = active ? h_out : hst[j];
+          gsv[j] = make_float4(gi, gg, gf, go);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int bl = gq * 4 + j;
           // state h (carried through inactive steps) feeds the next step's GEMM
           const int off = (ul >> 3) * 256 + (bl >> 3) * 128 + (bl & 7) * 16 + (ul & 7) * 2;
           *(__nv_bfloat16*)(stg + off) = __float2bfloat16(hst[j]);
-          if (a.gates && bidx[j] < B) {
-            const size_t cell = (((size_t)td * B + bidx[j]) * 2 + dir) * H + u;
-            *(float4*)(a.gates + cell * 4) = make_float4(gi, gg, gf, go);
-            a.cs[cell] = c_new;
-          }
+        }
+        if (a.gates) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (bidx[j] < B) {
+              const size_t cell = (((size_t)td * B + bidx[j]) * 2 + dir) * H + u;
+              *(float4*)(a.gates + cell * 4) = gsv[j];
+              a.cs[cell] = cst[j];
+            }
         }
         const long long e4 = clock64();
         fence_proxy_async_smem();                 // staged h visible to the bulk-copy engine
@@ -593,13 +605,22 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
         mbar_wait(&gfull[c * BGS + stage], gph);
         const float* Rs = (const float*)(smem + L::kRingOff + (c * BGS + stage) * BSTAGE);
         const bool tp_ok = tp >= 0 && tp < T;
+        // loads first, stores last (see the forward kernel)
+        float4 g4[4];
+        float ccv[4], cpv[4], dyq[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int bl = gq * 4 + j;
-          const float4 g4 = *(const float4*)(Rs + bl * 128 + ul * 4);
-          const float cc = Rs[2048 + bl * 32 + ul];
-          const float c_prev = tp_ok ? Rs[2048 + 512 + bl * 32 + ul] : 0.f;
-          float dyv = Rs[2048 + 1024 + bl * 32 + ul];
+          g4[j] = *(const float4*)(Rs + bl * 128 + ul * 4);
+          ccv[j] = Rs[2048 + bl * 32 + ul];
+          cpv[j] = tp_ok ? Rs[2048 + 512 + bl * 32 + ul] : 0.f;
+          dyq[j] = Rs[2048 + 1024 + bl * 32 + ul];
+        }
+        uint2 pkv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float cc = ccv[j], c_prev = cpv[j];
+          float dyv = dyq[j];
           const bool active = td < len[j];
           const bool nb_active = s > 0 && tn >= 0 && tn < T && tn < len[j];
           if (a.keep_prob < 1.f) {
@@ -608,7 +629,7 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
           }
           const float dh = dyv + (nb_active ? dh_rec[j] : 0.f);
           const float dc_in = nb_active ? dcs[j] : 0.f;
-          const float gi = g4.x, gg = g4.y, gf = g4.z, go = g4.w;
+          const float gi = g4[j].x, gg = g4[j].y, gf = g4[j].z, go = g4[j].w;
           const float Ec = __expf(fminf(-2.f * cc, 25.f));
           const float tc = (1.f - Ec) * fast_rcp(1.f + Ec);
           const float dzo = dh * tc * go * (1.f - go);
@@ -623,10 +644,14 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
           dzi = active ? dzi : 0.f; dzg = active ? dzg : 0.f;
           const float dzf2 = active ? dzf : 0.f, dzo2 = active ? dzo : 0.f;
           __nv_bfloat162 lo = __floats2bfloat162_rn(dzi, dzg), hi = __floats2bfloat162_rn(dzf2, dzo2);
-          uint2 pk; pk.x = *(uint32_t*)&lo; pk.y = *(uint32_t*)&hi;
-          *(uint2*)(bop + (ul >> 1) * 256 + (bl >> 3) * 128 + (bl & 7) * 16 + (ul & 1) * 8) = pk;
+          pkv[j].x = *(uint32_t*)&lo; pkv[j].y = *(uint32_t*)&hi;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int bl = gq * 4 + j;
+          *(uint2*)(bop + (ul >> 1) * 256 + (bl >> 3) * 128 + (bl & 7) * 16 + (ul & 1) * 8) = pkv[j];
           if (bidx[j] < B)
-            *(uint2*)(a.dG + ((size_t)td * B + bidx[j]) * 8 * H + (size_t)dir * 4 * H + u * 4) = pk;
+            *(uint2*)(a.dG + ((size_t)td * B + bidx[j]) * 8 * H + (size_t)dir * 4 * H + u * 4) = pkv[j];
         }
         fence_proxy_async_smem();
         named_bar_sync(1 + c, 128);

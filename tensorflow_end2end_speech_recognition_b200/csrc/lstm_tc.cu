@@ -38,7 +38,7 @@ static size_t tc_work_layout(const b2_lstm_desc* d, void* base, TcWork* w) {
   const size_t owx = take(D * 8 * H * 2);
   const size_t ob = take(8 * H * 4);
   const size_t owh = take(2 * 4 * H * H * 2);
-  const size_t owt = take(2 * 4 * H * H * 2);
+  const size_t owt = take((size_t)2 * (H / 32) * 4 * 128 * 128 * 2);   // whT: 4 zero-padded M tiles
   const size_t odwx = take(D * 8 * H * 4);
   const size_t odwh = take(2 * H * 4 * H * 4);
   const size_t odb = take(8 * H * 4);
@@ -64,7 +64,8 @@ __global__ void pack_lstm_weights_kernel(const float* __restrict__ k0, const flo
                                          float* __restrict__ bias, uint16_t* __restrict__ wh,
                                          uint16_t* __restrict__ whT) {
   const int64_t n_wx = (int64_t)D * 8 * H, n_wh = (int64_t)2 * 4 * H * H;
-  const int64_t total = n_wx + 8 * H + n_wh + (whT ? n_wh : 0);
+  const int64_t n_wt = (int64_t)2 * (H / 32) * 4 * 128 * 128;
+  const int64_t total = n_wx + 8 * H + n_wh + (whT ? n_wt : 0);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     if (i < n_wx) {
