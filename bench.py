@@ -207,7 +207,18 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    last = {}
+
+    def e2e_step():
+        loss = step(x_host, seq_host)          # H2D of the batch inside (CTC._to_device)
+        last["loss"] = float(loss.item())      # D2H read of the step's result
+
+    # warm up BOTH step flavours (allocator pools, module attributes, clocks) before timing
     for _ in range(max(args.warmup, 3)):
+        step(x_dev, seq_dev)
+    for _ in range(2):
+        e2e_step()
+    for _ in range(2):
         step(x_dev, seq_dev)
     sampler = ClockSampler(local)
     if rank == 0:
@@ -216,12 +227,6 @@ def main():
     ms_dev = timed(lambda: step(x_dev, seq_dev), args.steps)
     launches = (lib.b2_launch_count() - l0) // max(args.steps, 1)
 
-    last = {}
-
-    def e2e_step():
-        loss = step(x_host, seq_host)          # H2D of the batch inside (CTC._to_device)
-        last["loss"] = float(loss.item())      # D2H read of the step's result
-    e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
