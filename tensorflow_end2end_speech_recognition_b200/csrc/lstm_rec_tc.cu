@@ -221,7 +221,7 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
         const int td = dir ? T - 1 - t : t;
         const bool dbg = a.dbg && blockIdx.x == 0 && ctid == 0 && c == 0;
         const long long e0 = clock64();
-        mbar_wait(&accfull[c], t & 1);
+        mbar_wait_warp(&accfull[c], t & 1);
         tc_fence_after();
         const long long e1 = clock64();
         float v[16];
@@ -253,7 +253,7 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
         }
         __syncwarp();
         const long long e2 = clock64();
-        mbar_wait(&gfull[c * RGS + stage], gph);
+        mbar_wait_warp(&gfull[c * RGS + stage], gph);
         const long long e3 = clock64();
         const float* Gs = (const float*)(smem + L::kGOff + (c * RGS + stage) * 8192);
         const int p = t & 1;
@@ -591,7 +591,7 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
         // ---- A) dh_rec = sum of the peers' partial slices
         float dh_rec[4] = {0.f, 0.f, 0.f, 0.f};
         if (s > 0) {
-          mbar_wait_cluster(&rfull[c * 2 + p], (rph >> p) & 1u);
+          mbar_wait_cluster_warp(&rfull[c * 2 + p], (rph >> p) & 1u);
           rph ^= 1u << p;
           const uint8_t* rb = smem + L::kRecvOff + (c * 2 + p) * 16384 + (ul * 16 + gq * 4) * 2;
           for (int src = 0; src < CS; ++src) {
@@ -602,7 +602,7 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
             dh_rec[3] += __uint_as_float(raw.y & 0xffff0000u);
           }
         }
-        mbar_wait(&gfull[c * BGS + stage], gph);
+        mbar_wait_warp(&gfull[c * BGS + stage], gph);
         const float* Rs = (const float*)(smem + L::kRingOff + (c * BGS + stage) * BSTAGE);
         const bool tp_ok = tp >= 0 && tp < T;
         // loads first, stores last (see the forward kernel)
@@ -662,7 +662,7 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
         if (++stage == BGS) { stage = 0; gph ^= 1; }
         if (s + 1 >= T) break;
         // ---- C) partial dh of this step -> bf16 slices for the peers
-        mbar_wait(&accfull[c], s & 1);
+        mbar_wait_warp(&accfull[c], s & 1);
         tc_fence_after();
         uint8_t* sst = smem + L::kSendOff + (c * 2 + (p ^ 1)) * 16384;
         for (int m = 0; m < MT; ++m) {

@@ -64,6 +64,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Whole-warp wait where only lane 0 polls: 32 spinning lanes steal issue slots from the
+// MMA-issuer warp that shares the SM sub-partition.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
 // acquire at cluster scope: needed when the producers are other CTAs (DSMEM writes)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok = 0;
@@ -76,6 +82,11 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
   }
+}
+
+__device__ __forceinline__ void mbar_wait_cluster_warp(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait_cluster(bar, parity);
+  __syncwarp();
 }
 
 // --------------------------------------------------------------------- TMA
