@@ -72,7 +72,7 @@ struct RecSmem {
   static constexpr int kGOff = kStageOff + NCHAIN * 2 * 1024;          // [NCHAIN][RGS][8 KB]
   static constexpr int kScrOff = kGOff + NCHAIN * RGS * 8192;          // [NCHAIN*4][32*RPITCH*4]
   static constexpr int kBarOff = kScrOff + NCHAIN * 4 * 32 * RPITCH * 4;
-  static constexpr int kBytes = kBarOff + 512;
+  static constexpr int kBytes = kBarOff + 1024;
 };
 
 // warp roles: 0..3 = MMA issuers, 4 = G producer, 5.. = gate math (4 warps per chain)
@@ -93,14 +93,14 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
   const uint32_t hall = (uint32_t)CS * 1024u;  // bytes of one h buffer (16 batch x H bf16)
 
   uint64_t* bars = (uint64_t*)(smem + L::kBarOff);
-  uint64_t* hfull = bars;                      // [NCHAIN][2]
-  uint64_t* accfull = bars + NCHAIN * 2;       // [NCHAIN]
+  uint64_t* hfull = bars;                      // [NCHAIN][2][16]: one per (buffer, source CTA slice)
+  uint64_t* accfull = bars + NCHAIN * 2 * 16;  // [NCHAIN]
   uint64_t* gfull = accfull + NCHAIN;          // [NCHAIN][RGS]
   uint64_t* gempty = gfull + NCHAIN * RGS;     // [NCHAIN][RGS]
   uint32_t* tmem_slot = (uint32_t*)(gempty + NCHAIN * RGS);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NCHAIN * 2; ++i) mbar_init(&hfull[i], 1);
+    for (int i = 0; i < NCHAIN * 2 * 16; ++i) mbar_init(&hfull[i], 1);
     for (int i = 0; i < NCHAIN; ++i) mbar_init(&accfull[i], NISS);
     for (int i = 0; i < NCHAIN * RGS; ++i) { mbar_init(&gfull[i], 1); mbar_init(&gempty[i], 1); }
     fence_mbar_init();
@@ -146,31 +146,56 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
       const uint32_t idesc = make_idesc_bf16(128, RN, 0, 0);
       uint32_t hphase = 0;                       // bit (c*2+p): parity of hfull[c][p]
       const uint64_t bdesc0 = make_smem_desc(smem_u32(smem + L::kHbufOff), 256, 128, 0);
-      for (int t = 0; t < T; ++t) {
+      // the chains drift against each other: poll both and serve whichever has its h ready
+      int tc[NCHAIN];
+      int remaining = 0;
+#pragma unroll
+      for (int c = 0; c < NCHAIN; ++c) {
+        tc[c] = (gbase + c < a.NG) ? 0 : T;
+        remaining += T - tc[c];
+      }
+      while (remaining > 0) {
 #pragma unroll
         for (int c = 0; c < NCHAIN; ++c) {
-          if (gbase + c >= a.NG) continue;
+          const int t = tc[c];
+          if (t >= T) continue;
           const int p = t & 1;
-          const long long m0 = clock64();
+          // h arrives slice by slice (one 32-unit slice per source CTA, own mbarrier each):
+          // the two MMAs of a slice are issued as soon as that slice has landed, so the
+          // tensor pipe works underneath the DSMEM all-gather instead of after it
+          constexpr int SL0 = (0 * KPER) >> 1;
+          const int sl_first = (warp * KPER) >> 1;
           if (t > 0) {
-            mbar_wait_cluster(&hfull[c * 2 + p], (hphase >> (c * 2 + p)) & 1u);
-            hphase ^= 1u << (c * 2 + p);
+            uint32_t ok;
+            asm volatile(
+                "{\n\t.reg .pred P;\n\t"
+                "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, P;\n\t}"
+                : "=r"(ok)
+                : "r"(smem_u32(&hfull[(c * 2 + p) * 16 + sl_first])), "r"((hphase >> ((c * 2 + p) * 4)) & 1u)
+                : "memory");
+            if (!ok) continue;
+            hphase ^= 1u << ((c * 2 + p) * 4);
           }
+          (void)SL0;
           tc_fence_after();
-          const long long m1 = clock64();
           // one descriptor per buffer; the k-th step only moves the start address by 512 B
           const uint64_t bd0 = bdesc0 + (uint64_t)((c * 2 + p) * (L::kHbufBytes >> 4));
           const uint32_t acc = tAcc + (c * NISS + warp) * RN;
 #pragma unroll
           for (int kk = 0; kk < KPER; ++kk) {
             const int k = warp * KPER + kk;
+            const int ls = (k >> 1) - sl_first;          // local slice index of this issuer (0..3)
+            if (t > 0 && ls > 0 && (kk == 0 || ((k - 1) >> 1) != (k >> 1))) {
+              mbar_wait_cluster(&hfull[(c * 2 + p) * 16 + (k >> 1)], (hphase >> ((c * 2 + p) * 4 + ls)) & 1u);
+              hphase ^= 1u << ((c * 2 + p) * 4 + ls);
+              tc_fence_after();
+            }
             mma_ts(acc, tA + k * 8, bd0 + (uint64_t)(k * 32), idesc, kk > 0 ? 1u : 0u);
           }
           mma_commit(&accfull[c]);
-          if (a.dbg && blockIdx.x == 0 && c == 0 && warp == 0) {
-            a.dbg[0] += m1 - m0;               // wait for h
-            a.dbg[1] += clock64() - m1;        // issue MMAs + commit
-          }
+          tc[c] = t + 1;
+          --remaining;
         }
       }
     }
@@ -221,7 +246,7 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
         const int td = dir ? T - 1 - t : t;
         const bool dbg = a.dbg && blockIdx.x == 0 && ctid == 0 && c == 0;
         const long long e0 = clock64();
-        mbar_wait_warp(&accfull[c], t & 1);
+        mbar_wait(&accfull[c], t & 1);
         tc_fence_after();
         const long long e1 = clock64();
         float v[16];
@@ -253,7 +278,7 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
         }
         __syncwarp();
         const long long e2 = clock64();
-        mbar_wait_warp(&gfull[c * RGS + stage], gph);
+        mbar_wait(&gfull[c * RGS + stage], gph);
         const long long e3 = clock64();
         const float* Gs = (const float*)(smem + L::kGOff + (c * RGS + stage) * 8192);
         const int p = t & 1;
@@ -311,17 +336,15 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
         fence_proxy_async_smem();                 // staged h visible to the bulk-copy engine
         named_bar_sync(1 + c, 128);
         const long long e5 = clock64();
-        if (ctid == 0) {
-          mbar_arrive(&gempty[c * RGS + stage]);
-          if (t + 1 < T) mbar_expect_tx(&hfull[c * 2 + (p ^ 1)], hall);
-        }
+        if (ctid == 0) mbar_arrive(&gempty[c * RGS + stage]);
+        if (t + 1 < T && ctid < CS) mbar_expect_tx(&hfull[(c * 2 + (p ^ 1)) * 16 + ctid], 1024);
         // 4 lanes in each of the chain's 4 warps issue the CS bulk copies (one per peer):
         // spreading the issue over warps costs ~250 cycles instead of ~850 from one warp
         {
           const int dstcta = q * 4 + lane;
           if (t + 1 < T && lane < 4 && dstcta < CS) {
             uint8_t* dst = smem + L::kHbufOff + (c * 2 + (p ^ 1)) * L::kHbufBytes + cta * 1024;
-            bulk_s2cluster(dst, stg, 1024, &hfull[c * 2 + (p ^ 1)], (uint32_t)dstcta);
+            bulk_s2cluster(dst, stg, 1024, &hfull[(c * 2 + (p ^ 1)) * 16 + cta], (uint32_t)dstcta);
           }
         }
         // cooperative, coalesced output store off the critical path: 64 threads x 8 units
@@ -521,11 +544,19 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
     // ------------------------------------------------------------- MMA issuers (one M tile each)
     if (lane == 0 && warp < MT) {
       const uint32_t idesc = make_idesc_bf16(128, RN, 0, 0);
-      for (int s = 0; s + 1 < T; ++s) {
+      int sc[NCHAIN];
+      int remaining = 0;
+#pragma unroll
+      for (int c = 0; c < NCHAIN; ++c) {
+        sc[c] = (gbase + c < a.NG) ? 0 : T - 1;
+        remaining += (T - 1) - sc[c];
+      }
+      while (remaining > 0) {
 #pragma unroll
         for (int c = 0; c < NCHAIN; ++c) {
-          if (gbase + c >= a.NG) continue;
-          mbar_wait(&bready[c], s & 1);
+          const int s = sc[c];
+          if (s + 1 >= T) continue;
+          if (!mbar_try_wait(&bready[c], s & 1)) continue;
           tc_fence_after();
           const uint64_t bd0 = make_smem_desc(smem_u32(smem + L::kBopOff + c * 4096), 256, 128, 0);
           const uint32_t acc = tAcc + (c * 4 + warp) * RN;
@@ -533,6 +564,8 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
           for (int kk = 0; kk < 8; ++kk)
             mma_ts(acc, tA + warp * 64 + kk * 8, bd0 + (uint64_t)(kk * 32), idesc, kk > 0 ? 1u : 0u);
           mma_commit(&accfull[c]);
+          sc[c] = s + 1;
+          --remaining;
         }
       }
     }
@@ -591,7 +624,7 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
         // ---- A) dh_rec = sum of the peers' partial slices
         float dh_rec[4] = {0.f, 0.f, 0.f, 0.f};
         if (s > 0) {
-          mbar_wait_cluster_warp(&rfull[c * 2 + p], (rph >> p) & 1u);
+          mbar_wait_cluster(&rfull[c * 2 + p], (rph >> p) & 1u);
           rph ^= 1u << p;
           const uint8_t* rb = smem + L::kRecvOff + (c * 2 + p) * 16384 + (ul * 16 + gq * 4) * 2;
           for (int src = 0; src < CS; ++src) {
@@ -602,7 +635,7 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
             dh_rec[3] += __uint_as_float(raw.y & 0xffff0000u);
           }
         }
-        mbar_wait_warp(&gfull[c * BGS + stage], gph);
+        mbar_wait(&gfull[c * BGS + stage], gph);
         const float* Rs = (const float*)(smem + L::kRingOff + (c * BGS + stage) * BSTAGE);
         const bool tp_ok = tp >= 0 && tp < T;
         // loads first, stores last (see the forward kernel)
@@ -662,7 +695,7 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
         if (++stage == BGS) { stage = 0; gph ^= 1; }
         if (s + 1 >= T) break;
         // ---- C) partial dh of this step -> bf16 slices for the peers
-        mbar_wait_warp(&accfull[c], s & 1);
+        mbar_wait(&accfull[c], s & 1);
         tc_fence_after();
         uint8_t* sst = smem + L::kSendOff + (c * 2 + (p ^ 1)) * 16384;
         for (int m = 0; m < MT; ++m) {
