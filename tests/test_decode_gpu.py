@@ -46,3 +46,42 @@ def test_softmax_rows(cuda):
     y = ops.softmax_rows(torch.tensor(x, device=cuda)).cpu().numpy()
     e = np.exp(x.astype(np.float64) - x.max(-1, keepdims=True))
     np.testing.assert_allclose(y, e / e.sum(-1, keepdims=True), rtol=1e-5, atol=1e-7)
+
+
+def _beam_gpu(probs, seq, beam, cuda):
+    from tensorflow_end2end_speech_recognition_b200 import ops
+    with np.errstate(divide="ignore"):
+        lp = np.log(probs)                      # float32 log like the reference (np.log(probs))
+    lab, n, sc = ops.ctc_beam_decode(torch.tensor(lp, device=cuda),
+                                     torch.tensor(np.asarray(seq, np.int32), device=cuda), beam)
+    torch.cuda.synchronize()
+    lab, n, sc = lab.cpu().numpy(), n.cpu().numpy(), sc.cpu().numpy()
+    return [list(lab[b, :n[b]]) for b in range(len(seq))], sc
+
+
+def test_beam_search_matches_reference_golden_vectors(cuda):
+    """bit-exact label indices against the vectors produced by the reference's own numpy
+    BeamSearchDecoder (tests/golden/make_golden.py)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ctc_decoders.npz"))
+    for i in range(int(z["n"])):
+        p = z["probs_%d" % i]
+        T = p.shape[1]
+        labs, sc = _beam_gpu(p, [T], int(z["beam_%d" % i]), cuda)
+        assert labs[0] == list(z["beam_labels_%d" % i]), "case %d" % i
+        assert abs(sc[0] - float(z["beam_score_%d" % i])) < 1e-4 * max(1.0, abs(sc[0]))
+
+
+@pytest.mark.parametrize("T,B,C,beam,peaky", [(40, 6, 29, 20, 3.0), (60, 4, 12, 5, 1.0), (100, 3, 29, 20, 6.0),
+                                              (30, 5, 62, 10, 2.0), (25, 4, 5, 1, 1.0)])
+def test_beam_search_random_vs_oracle(cuda, T, B, C, beam, peaky):
+    rng = np.random.RandomState(T * 3 + C)
+    x = rng.randn(B, T, C) * peaky
+    x[..., C - 1] += 0.5 * peaky
+    p = np.exp(x - x.max(-1, keepdims=True))
+    p = (p / p.sum(-1, keepdims=True)).astype(np.float32)
+    seq = [T] + [int(rng.randint(T // 2, T + 1)) for _ in range(B - 1)]
+    labs, sc = _beam_gpu(p, seq, beam, cuda)
+    ref, rsc = odec.beam_search_decode(p, seq, C - 1, beam)
+    assert labs == ref
+    np.testing.assert_allclose(sc, np.asarray(rsc), rtol=1e-5, atol=1e-4)
