@@ -75,9 +75,10 @@ struct RecSmem {
   static constexpr int kBytes = kBarOff + 1024;
 };
 
-// warp roles: 0..3 = MMA issuers, 4 = G producer, 5.. = gate math (4 warps per chain)
+// warp roles: 0..3 = MMA issuers, 4 = G producer, 5.. = gate math (4 warps per chain),
+// then one output-store warp per chain
 template <int NCHAIN, int KS>     // KS = H/16 MMA k-steps per time step
-__global__ void __launch_bounds__(160 + 128 * NCHAIN, 1)
+__global__ void __launch_bounds__(160 + 160 * NCHAIN, 1)
 lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a) {
   using L = RecSmem<NCHAIN>;
   constexpr int NISS = KS < NISSW ? KS : NISSW;      // issuer warps actually used
@@ -97,9 +98,12 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
   uint64_t* accfull = bars + NCHAIN * 2 * 16;  // [NCHAIN]
   uint64_t* gfull = accfull + NCHAIN;          // [NCHAIN][RGS]
   uint64_t* gempty = gfull + NCHAIN * RGS;     // [NCHAIN][RGS]
-  uint32_t* tmem_slot = (uint32_t*)(gempty + NCHAIN * RGS);
+  uint64_t* stfull = gempty + NCHAIN * RGS;    // [NCHAIN][2] staged h ready for the store warp
+  uint64_t* stfree = stfull + NCHAIN * 2;      // [NCHAIN][2] store warp done with the staging buffer
+  uint32_t* tmem_slot = (uint32_t*)(stfree + NCHAIN * 2);
 
   if (threadIdx.x == 0) {
+    for (int i = 0; i < NCHAIN * 2; ++i) { mbar_init(&stfull[i], 1); mbar_init(&stfree[i], 1); }
     for (int i = 0; i < NCHAIN * 2 * 16; ++i) mbar_init(&hfull[i], 1);
     for (int i = 0; i < NCHAIN; ++i) mbar_init(&accfull[i], NISS);
     for (int i = 0; i < NCHAIN * RGS; ++i) { mbar_init(&gfull[i], 1); mbar_init(&gempty[i], 1); }
@@ -216,6 +220,63 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
         if (++stage == RGS) { stage = 0; phase ^= 1; }
       }
     }
+  } else if (warp >= 5 + 4 * NCHAIN) {
+    // ------------------------------------------------------------- output store warp
+    const int c = warp - 5 - 4 * NCHAIN;
+    const int grp = gbase + c;
+    if (grp < a.NG) {
+      uint8_t* stage_base = smem + L::kStageOff + c * 2 * 1024;
+      int ob[2], okc[2], olen[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int ch = lane + 32 * i;             // 64 chunks of 8 units x 1 batch row
+        ob[i] = grp * RN + (ch >> 2); okc[i] = ch & 3;
+        olen[i] = ob[i] < B ? a.seq_len[ob[i]] : 0;
+      }
+      for (int t = 0; t < T; ++t) {
+        const int td = dir ? T - 1 - t : t;
+        const int p = t & 1;
+        mbar_wait(&stfull[c * 2 + p], (t >> 1) & 1);
+        const uint8_t* stg = stage_base + p * 1024;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          if (ob[i] >= B) continue;
+          const int bl = (lane + 32 * i) >> 2;
+          const uint4 raw = *(const uint4*)(stg + okc[i] * 256 + (bl >> 3) * 128 + (bl & 7) * 16);
+          const bool oact = td < olen[i];
+          const uint4 hv = oact ? raw : make_uint4(0, 0, 0, 0);
+          const size_t o0 = ((size_t)td * B + ob[i]) * 2 * H + (size_t)dir * H + cta * RU + okc[i] * 8;
+          if (a.hs_lp) *(uint4*)(a.hs_lp + o0) = hv;
+          const uint32_t w[4] = {hv.x, hv.y, hv.z, hv.w};
+          float f[8];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            f[2 * k] = __uint_as_float(w[k] << 16);
+            f[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+          }
+          if (a.keep_prob < 1.f) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              f[k] = dropout_keep(a.seed, o0 + k, a.keep_prob) ? f[k] / a.keep_prob : 0.f;
+            if (a.y_lp) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                __nv_bfloat162 b2v = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+                pk[k] = *(uint32_t*)&b2v;
+              }
+              *(uint4*)(a.y_lp + o0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          } else if (a.y_lp && a.y_lp != a.hs_lp) {
+            *(uint4*)(a.y_lp + o0) = hv;
+          }
+          *(float4*)(a.y + o0) = make_float4(f[0], f[1], f[2], f[3]);
+          *(float4*)(a.y + o0 + 4) = make_float4(f[4], f[5], f[6], f[7]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&stfree[c * 2 + p]);
+      }
+    }
   } else {
     // ------------------------------------------------------------- gate math
     const int c = (warp - 5) >> 2;              // chain of this warp
@@ -236,9 +297,6 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
         len[j] = bidx[j] < B ? a.seq_len[bidx[j]] : 0;
         cst[j] = 0.f; hst[j] = 0.f;
       }
-      // cooperative output store: thread ctid < 64 owns (batch row ob, 8-unit chunk okc)
-      const int ob = grp * RN + (ctid >> 2), okc = ctid & 3;
-      const int olen = (ctid < 64 && ob < B) ? a.seq_len[ob] : 0;
       float pwi = 0.f, pwf = 0.f, pwo = 0.f;
       if (a.use_peephole) { pwi = a.wi[dir][u]; pwf = a.wf[dir][u]; pwo = a.wo[dir][u]; }
       int stage = 0; uint32_t gph = 0;
@@ -246,23 +304,32 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
         const int td = dir ? T - 1 - t : t;
         const bool dbg = a.dbg && blockIdx.x == 0 && ctid == 0 && c == 0;
         const long long e0 = clock64();
+        const int p = t & 1;
+        // off the critical path (the MMAs of this step are still running): G_t into registers,
+        // and make sure the store warp is done with the staging buffer we are about to reuse
+        mbar_wait(&gfull[c * RGS + stage], gph);
+        const float* Gs = (const float*)(smem + L::kGOff + (c * RGS + stage) * 8192);
+        float4 G4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) G4[j] = *(const float4*)(Gs + (gq * 4 + j) * 128 + ul * 4);   // [b][u][gate]
+        if (t >= 2) mbar_wait(&stfree[c * 2 + p], ((t >> 1) - 1) & 1);
+        const long long e1 = clock64();
         mbar_wait(&accfull[c], t & 1);
         tc_fence_after();
-        const long long e1 = clock64();
+        const long long e2 = clock64();
         float v[16];
         {
-          uint32_t w0[16];
-          tmem_ld_32x32b_x16(tAcc + (c * NISS) * RN + ((uint32_t)(q * 32) << 16), w0);
+          uint32_t w[NISS][16];
+#pragma unroll
+          for (int s2 = 0; s2 < NISS; ++s2)
+            tmem_ld_32x32b_x16(tAcc + (c * NISS + s2) * RN + ((uint32_t)(q * 32) << 16), w[s2]);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(w0[i]);
+          for (int i = 0; i < 16; ++i) {
+            float acc = __uint_as_float(w[0][i]);
 #pragma unroll
-          for (int s = 1; s < NISS; ++s) {
-            uint32_t w1[16];
-            tmem_ld_32x32b_x16(tAcc + (c * NISS + s) * RN + ((uint32_t)(q * 32) << 16), w1);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(w1[i]);
+            for (int s2 = 1; s2 < NISS; ++s2) acc += __uint_as_float(w[s2][i]);
+            v[i] = acc;
           }
         }
         // 4x4 transpose inside each 4-lane group through shared memory
@@ -277,17 +344,10 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
           z[g][0] = f.x; z[g][1] = f.y; z[g][2] = f.z; z[g][3] = f.w;
         }
         __syncwarp();
-        const long long e2 = clock64();
-        mbar_wait(&gfull[c * RGS + stage], gph);
         const long long e3 = clock64();
-        const float* Gs = (const float*)(smem + L::kGOff + (c * RGS + stage) * 8192);
-        const int p = t & 1;
         uint8_t* stg = stage_base + p * 1024;
         // loads first, stores last: a shared-memory store between two cells would serialise
         // them (the compiler must assume it aliases the next cell's loads)
-        float4 G4[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) G4[j] = *(const float4*)(Gs + (gq * 4 + j) * 128 + ul * 4);   // [b][u][gate]
         float4 gsv[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -336,7 +396,7 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
         fence_proxy_async_smem();                 // staged h visible to the bulk-copy engine
         named_bar_sync(1 + c, 128);
         const long long e5 = clock64();
-        if (ctid == 0) mbar_arrive(&gempty[c * RGS + stage]);
+        if (ctid == 0) { mbar_arrive(&gempty[c * RGS + stage]); mbar_arrive(&stfull[c * 2 + p]); }
         if (t + 1 < T && ctid < CS) mbar_expect_tx(&hfull[(c * 2 + (p ^ 1)) * 16 + ctid], 1024);
         // 4 lanes in each of the chain's 4 warps issue the CS bulk copies (one per peer):
         // spreading the issue over warps costs ~250 cycles instead of ~850 from one warp
@@ -347,44 +407,11 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
             bulk_s2cluster(dst, stg, 1024, &hfull[(c * 2 + (p ^ 1)) * 16 + cta], (uint32_t)dstcta);
           }
         }
-        // cooperative, coalesced output store off the critical path: 64 threads x 8 units
-        if (ctid < 64 && ob < B) {
-          const uint4 raw = *(const uint4*)(stg + okc * 256 + ((ctid >> 2) >> 3) * 128 + ((ctid >> 2) & 7) * 16);
-          const bool oact = td < olen;
-          const uint4 hv = oact ? raw : make_uint4(0, 0, 0, 0);
-          const size_t o0 = ((size_t)td * B + ob) * 2 * H + (size_t)dir * H + cta * RU + okc * 8;
-          if (a.hs_lp) *(uint4*)(a.hs_lp + o0) = hv;
-          const uint32_t w[4] = {hv.x, hv.y, hv.z, hv.w};
-          float f[8];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            f[2 * i] = __uint_as_float(w[i] << 16);
-            f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-          }
-          if (a.keep_prob < 1.f) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              f[i] = dropout_keep(a.seed, o0 + i, a.keep_prob) ? f[i] / a.keep_prob : 0.f;
-            if (a.y_lp) {
-              uint32_t pk[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                __nv_bfloat162 b2v = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-                pk[i] = *(uint32_t*)&b2v;
-              }
-              *(uint4*)(a.y_lp + o0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            }
-          } else if (a.y_lp && a.y_lp != a.hs_lp) {
-            *(uint4*)(a.y_lp + o0) = hv;
-          }
-          *(float4*)(a.y + o0) = make_float4(f[0], f[1], f[2], f[3]);
-          *(float4*)(a.y + o0 + 4) = make_float4(f[4], f[5], f[6], f[7]);
-        }
         if (dbg) {
           const long long e6 = clock64();
-          a.dbg[2] += e1 - e0;   // wait accumulator
-          a.dbg[3] += e2 - e1;   // tmem ld + transpose
-          a.dbg[4] += e3 - e2;   // wait G
+          a.dbg[2] += e2 - e1;   // wait accumulator
+          a.dbg[3] += e3 - e2;   // tmem ld + transpose
+          a.dbg[4] += e1 - e0;   // G prefetch + staging-free wait (overlaps the MMAs)
           a.dbg[5] += e4 - e3;   // gate math + saves
           a.dbg[6] += e5 - e4;   // fence + named barrier
           a.dbg[7] += e6 - e5;   // sends + output store
@@ -422,7 +449,7 @@ static int launch_rec_fwd(const CUtensorMap& tmG, const RecFwdArgs& a, int nclus
   if (CS > 8) B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(nclusters * CS);
-  cfg.blockDim = dim3(160 + 128 * NCHAIN);
+  cfg.blockDim = dim3(160 + 160 * NCHAIN);
   cfg.dynamicSmemBytes = L::kBytes;
   cfg.stream = stream;
   cudaLaunchAttribute at[1];
@@ -605,6 +632,7 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
       const int ctid = threadIdx.x - 160 - c * 128;
       int bidx[4], len[4];
       float dcs[4];
+      float gacc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // db_i, db_g, db_f, db_o, dw_i, dw_f, dw_o
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         bidx[j] = grp * RN + gq * 4 + j;
@@ -621,6 +649,8 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
         const int tn = dir ? td - 1 : td + 1;    // step processed just before (BPTT order)
         const int tp = dir ? td + 1 : td - 1;    // previous step in forward order
         const int p = s & 1;
+        const bool dbg = a.dbg && blockIdx.x == 0 && ctid == 0 && c == 0;
+        const long long b0 = clock64();
         // ---- A) dh_rec = sum of the peers' partial slices
         float dh_rec[4] = {0.f, 0.f, 0.f, 0.f};
         if (s > 0) {
@@ -635,7 +665,9 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
             dh_rec[3] += __uint_as_float(raw.y & 0xffff0000u);
           }
         }
+        const long long b1 = clock64();
         mbar_wait(&gfull[c * BGS + stage], gph);
+        const long long b2 = clock64();
         const float* Rs = (const float*)(smem + L::kRingOff + (c * BGS + stage) * BSTAGE);
         const bool tp_ok = tp >= 0 && tp < T;
         // loads first, stores last (see the forward kernel)
@@ -676,6 +708,10 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
           dcs[j] = active ? dc_prev : dcs[j];
           dzi = active ? dzi : 0.f; dzg = active ? dzg : 0.f;
           const float dzf2 = active ? dzf : 0.f, dzo2 = active ? dzo : 0.f;
+          // bias and peephole gradients accumulate in registers over the whole sequence
+          gacc[0] += dzi; gacc[1] += dzg; gacc[2] += dzf2; gacc[3] += dzo2;
+          gacc[4] = fmaf(dzi, c_prev, gacc[4]); gacc[5] = fmaf(dzf2, c_prev, gacc[5]);
+          gacc[6] = fmaf(dzo2, cc, gacc[6]);
           __nv_bfloat162 lo = __floats2bfloat162_rn(dzi, dzg), hi = __floats2bfloat162_rn(dzf2, dzo2);
           pkv[j].x = *(uint32_t*)&lo; pkv[j].y = *(uint32_t*)&hi;
         }
@@ -686,6 +722,7 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
           if (bidx[j] < B)
             *(uint2*)(a.dG + ((size_t)td * B + bidx[j]) * 8 * H + (size_t)dir * 4 * H + u * 4) = pkv[j];
         }
+        const long long b3 = clock64();
         fence_proxy_async_smem();
         named_bar_sync(1 + c, 128);
         if (ctid == 0) {
@@ -695,26 +732,34 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
         if (++stage == BGS) { stage = 0; gph ^= 1; }
         if (s + 1 >= T) break;
         // ---- C) partial dh of this step -> bf16 slices for the peers
+        const long long b4 = clock64();
         mbar_wait(&accfull[c], s & 1);
         tc_fence_after();
+        const long long b5 = clock64();
         uint8_t* sst = smem + L::kSendOff + (c * 2 + (p ^ 1)) * 16384;
-        for (int m = 0; m < MT; ++m) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(tAcc + (c * 4 + m) * RN + ((uint32_t)(q * 32) << 16), v);
-          tmem_ld_wait();
-          const int dest = m * 4 + q;
-          if (dest < CS) {
-            uint32_t pk[8];
+        {
+          uint32_t v[4][16];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              __nv_bfloat162 b2v = __floats2bfloat162_rn(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-              pk[i] = *(uint32_t*)&b2v;
+          for (int m = 0; m < 4; ++m)
+            if (m < MT) tmem_ld_32x32b_x16(tAcc + (c * 4 + m) * RN + ((uint32_t)(q * 32) << 16), v[m]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const int dest = m * 4 + q;
+            if (m < MT && dest < CS) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                __nv_bfloat162 b2v = __floats2bfloat162_rn(__uint_as_float(v[m][2 * i]), __uint_as_float(v[m][2 * i + 1]));
+                pk[i] = *(uint32_t*)&b2v;
+              }
+              uint4* d4 = (uint4*)(sst + dest * 1024 + lane * 32);
+              d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             }
-            uint4* d4 = (uint4*)(sst + dest * 1024 + lane * 32);
-            d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
         }
+        const long long b6 = clock64();
         tc_fence_before();
         fence_proxy_async_smem();
         named_bar_sync(1 + c, 128);
@@ -725,6 +770,26 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
             uint8_t* dst = smem + L::kRecvOff + (c * 2 + (p ^ 1)) * 16384 + cta * 1024;
             bulk_s2cluster(dst, sst + dstcta * 1024, 1024, &rfull[c * 2 + (p ^ 1)], (uint32_t)dstcta);
           }
+        }
+        if (dbg) {
+          const long long b7 = clock64();
+          a.dbg[0] += b1 - b0;   // wait partials + sum
+          a.dbg[1] += b2 - b1;   // wait ring
+          a.dbg[2] += b3 - b2;   // math + stores
+          a.dbg[3] += b4 - b3;   // fence + bar + arrive
+          a.dbg[4] += b5 - b4;   // wait MMA
+          a.dbg[5] += b6 - b5;   // tmem ld + convert + stage
+          a.dbg[6] += b7 - b6;   // fence + bar + sends
+        }
+      }
+      // flush the register-accumulated bias / peephole gradients (4 batch quads x chains x clusters)
+      if (a.dbias) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) atomicAdd(&a.dbias[(size_t)dir * 4 * H + u * 4 + g], gacc[g]);
+        if (a.use_peephole) {
+          atomicAdd(&a.dwi[dir][u], gacc[4]);
+          atomicAdd(&a.dwf[dir][u], gacc[5]);
+          atomicAdd(&a.dwo[dir][u], gacc[6]);
         }
       }
     }

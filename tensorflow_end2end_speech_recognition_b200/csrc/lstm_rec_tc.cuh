@@ -31,6 +31,8 @@ struct RecBwdArgs {
   const float* gates; const float* cs;   // reserve
   __nv_bfloat16* dG;          // [T*B, 8H] bf16, column = dir*4H + u*4 + gate
   const float* dfinal;        // [4,B,H] or null
+  float* dbias;               // [8H] packed bias gradient (+=), or null
+  float* dwi[2]; float* dwf[2]; float* dwo[2];   // peephole gradients (+=)
   long long* dbg;
 };
 

@@ -271,20 +271,30 @@ int tc_layer_backward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16
   }
   ba.use_peephole = d->use_peephole; ba.cell_clip = d->cell_clip; ba.keep_prob = d->keep_prob;
   ba.seed = d->dropout_seed; ba.gates = r.gates; ba.cs = r.cs; ba.dG = w.dG; ba.dfinal = nullptr;
-  ba.dbg = nullptr;
-  rc = rec_tc_backward(ba, dy, env_int("B2_REC_NCHAIN", 0), stream);
-  if (rc) return rc;
-  // 2. bias + peephole gradients
   B2_CUDA(cudaMemsetAsync(w.dbias, 0, (size_t)8 * H * 4, stream));
-  {
-    int slabs = cdiv(TB, 64); if (slabs > 128) slabs = 128;
-    dim3 pg(cdiv(H, 32), slabs, 2);
-    tc_small_grads_kernel<<<pg, 256, 0, stream>>>(w.dG, r.cs, seq_len, T, B, H, d->use_peephole,
-                                                 w.dbias, g_fw->w_i_diag, g_fw->w_f_diag,
-                                                 g_fw->w_o_diag, g_bw->w_i_diag, g_bw->w_f_diag,
-                                                 g_bw->w_o_diag);
-    B2_LAUNCH_CHECK();
+  ba.dbias = w.dbias;
+  const b2_lstm_grads* GR[2] = {g_fw, g_bw};
+  for (int dir = 0; dir < 2; ++dir) {
+    ba.dwi[dir] = GR[dir]->w_i_diag; ba.dwf[dir] = GR[dir]->w_f_diag; ba.dwo[dir] = GR[dir]->w_o_diag;
   }
+  ba.dbg = nullptr;
+  if (env_int("B2_REC_DBG", 0)) {
+    static long long* dbg_buf = nullptr;
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 64 * sizeof(long long));
+    cudaMemsetAsync(dbg_buf, 0, 64 * sizeof(long long), stream);
+    ba.dbg = dbg_buf;
+    rc = rec_tc_backward(ba, dy, env_int("B2_REC_NCHAIN", 0), stream);
+    long long hb[8];
+    cudaMemcpyAsync(hb, dbg_buf, sizeof(hb), cudaMemcpyDeviceToHost, stream);
+    cudaStreamSynchronize(stream);
+    fprintf(stderr, "[rec bwd dbg] cycles/step: wait_partials+sum=%lld wait_ring=%lld math+stores=%lld "
+            "bar1=%lld wait_mma=%lld ld+convert=%lld bar2+send=%lld\n",
+            hb[0] / T, hb[1] / T, hb[2] / T, hb[3] / T, hb[4] / T, hb[5] / T, hb[6] / T);
+  } else {
+    rc = rec_tc_backward(ba, dy, env_int("B2_REC_NCHAIN", 0), stream);
+  }
+  if (rc) return rc;
+  // 2. bias + peephole gradients: accumulated inside the recurrence kernel (registers -> atomics)
   // 3. time-batched GEMMs on packed operands
   const __nv_bfloat16* xa = x_lp;
   int ldx = D;
