@@ -191,6 +191,31 @@ int b2_blstm_layer_backward(const b2_lstm_desc* d, const float* x, const void* x
                             b2_stream_t stream);
 
 /* ------------------------------------------------------------------------ *
+ * Attention step (energy + masked softmax + context)   replaces
+ *   AttentionLayer.__call__, models/attention/decoders/attention_layer.py:45-347
+ * One decoder step over all T encoder states; the key projection is hoisted
+ * out of the step (b2_gemm once per batch):
+ *   mode 0 additive:       e_t = sum_a v_a*tanh(keys[t,a] + q[a] + loc[t,a])
+ *                          (bahdanau_content, hybrid, location, luong_concat)
+ *   mode 1 multiplicative: e_t = sum_a keys[t,a]*q[a]
+ *                          (dot_product, luong_dot, luong_general)
+ *   loc = conv1d_SAME(prev_alpha, conv_filter[filter_width,10]) . w_filter[10,A]
+ *         + b_filter (NULL conv_filter = no location term; keys may be NULL
+ *         for pure `location`)
+ * enc [B,T,E], keys [B,T,A], q [B,A], prev_alpha [B,T], enc_len [B];
+ * energies of t >= enc_len are float32.min, then *sharpening_factor, then
+ * softmax (or sigmoid / sum when sigmoid_smoothing).  alpha [B,T], context [B,E].
+ * ------------------------------------------------------------------------ */
+int b2_attention_step_forward(int mode, const float* enc, const float* keys,
+                              const float* q, const float* prev_alpha,
+                              const int32_t* enc_len, const float* conv_filter,
+                              int filter_width, const float* w_filter,
+                              const float* b_filter, const float* v_a, int B,
+                              int T, int E, int A, float sharpening_factor,
+                              int sigmoid_smoothing, float* alpha,
+                              float* context, b2_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
  * Small data-movement helpers of the step
  * ------------------------------------------------------------------------ */
 /* [B,T,D] -> [T,B,D]  (tf.transpose at blstm.py:279) */

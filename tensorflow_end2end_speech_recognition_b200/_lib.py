@@ -54,6 +54,8 @@ PROTOTYPES = {
     "b2_blstm_layer_backward": (_i, [C.POINTER(LstmDesc), _p, _p, _p, C.POINTER(LstmParams),
                                      C.POINTER(LstmParams), _p, _p, _p, C.POINTER(LstmGrads),
                                      C.POINTER(LstmGrads), _p, _sz, _p]),
+    "b2_attention_step_forward": (_i, [_i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _f,
+                                       _i, _p, _p, _p]),
     "b2_transpose_01": (_i, [_p, _p, _i, _i, _i, _p]),
     "b2_colsum": (_i, [_p, _i64, _i, _i, _p, _i, _p]),
     "b2_clip_by_norm_multi": (_i, [_p, _p, _i, _f, _f, _p, _p]),
