@@ -14,8 +14,8 @@
 //                         luong_dot, luong_general)
 // loc[t,:] = conv1d_SAME(alpha_prev, F[k,10])[t,:] . W_filter + b_filter  (location / hybrid).
 // HBM-bound: per step it must read keys (4*B*T*A) and the encoder states (4*B*T*E) once.
-// grid = (B, ESPLIT): every CTA recomputes the (cheap) weights of its utterance and reduces
-// its slice of the context, so B*ESPLIT CTAs keep all SMs streaming.
+// Two launches: attention_step_kernel (one CTA per utterance: energies, mask, normalise) and
+// attention_context_kernel (B x E/256 CTAs streaming the encoder states once).
 #include "common.cuh"
 #include <float.h>
 
@@ -36,9 +36,9 @@ constexpr int kAttnThreads = 512;
 __global__ void __launch_bounds__(kAttnThreads)
 attention_step_kernel(const AttnArgs a) {
   extern __shared__ float sm[];
-  const int b = blockIdx.x, split = blockIdx.y, nsplit = gridDim.y;
+  const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = kAttnThreads / 32;
-  const int T = a.T, A = a.A, E = a.E;
+  const int T = a.T, A = a.A;
   const int len = min(a.enc_len[b], T);
   float* s_e = sm;                       // [T] energies -> weights
   float* s_q = s_e + T;                  // [A]
@@ -129,33 +129,50 @@ attention_step_kernel(const AttnArgs a) {
   const float inv = 1.f / sum;
   for (int t = tid; t < T; t += kAttnThreads) {
     const float w = s_e[t] * inv;
-    s_e[t] = w;
-    if (split == 0) a.alpha[(size_t)b * T + t] = w;
+    a.alpha[(size_t)b * T + t] = w;
   }
-  __syncthreads();
-  // context slice: this CTA owns E/nsplit features, 4 per thread (float4), weights are exactly
-  // 0 past `len` so padded frames are never read
-  const int e_per = (E / 4 + nsplit - 1) / nsplit;           // float4 columns per split
-  const int c0 = split * e_per, c1 = min(E / 4, c0 + e_per);
-  const float4* encb = (const float4*)(a.enc + (size_t)b * T * E);
-  for (int c = c0 + tid; c < c1; c += kAttnThreads) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int t = 0;
-    for (; t + 4 <= len; t += 4) {
-      const float4 h0 = encb[(size_t)(t + 0) * (E / 4) + c], h1 = encb[(size_t)(t + 1) * (E / 4) + c];
-      const float4 h2 = encb[(size_t)(t + 2) * (E / 4) + c], h3 = encb[(size_t)(t + 3) * (E / 4) + c];
-      const float w0 = s_e[t], w1 = s_e[t + 1], w2 = s_e[t + 2], w3 = s_e[t + 3];
+}
+
+// context[b, e] = sum_{t < len} alpha[b,t] * enc[b,t,e].  CTA = 64 float4 columns (256
+// features) x 8 time groups; weights past `len` are exactly 0 so padded frames are never read.
+__global__ void __launch_bounds__(512)
+attention_context_kernel(const float* __restrict__ enc, const float* __restrict__ alpha,
+                         const int* __restrict__ enc_len, int T, int E, float* __restrict__ context) {
+  __shared__ float4 red[8][64];
+  const int b = blockIdx.x;
+  const int col = blockIdx.y * 64 + (threadIdx.x & 63);      // float4 column
+  const int tg = threadIdx.x >> 6;
+  const int len = min(enc_len[b], T);
+  const int E4 = E / 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < E4) {
+    const float4* encb = (const float4*)(enc + (size_t)b * T * E) + col;
+    const float* al = alpha + (size_t)b * T;
+    int t = tg;
+    for (; t + 24 < len; t += 32) {
+      const float4 h0 = __ldg(encb + (size_t)t * E4), h1 = __ldg(encb + (size_t)(t + 8) * E4);
+      const float4 h2 = __ldg(encb + (size_t)(t + 16) * E4), h3 = __ldg(encb + (size_t)(t + 24) * E4);
+      const float w0 = al[t], w1 = al[t + 8], w2 = al[t + 16], w3 = al[t + 24];
       acc.x += w0 * h0.x + w1 * h1.x + w2 * h2.x + w3 * h3.x;
       acc.y += w0 * h0.y + w1 * h1.y + w2 * h2.y + w3 * h3.y;
       acc.z += w0 * h0.z + w1 * h1.z + w2 * h2.z + w3 * h3.z;
       acc.w += w0 * h0.w + w1 * h1.w + w2 * h2.w + w3 * h3.w;
     }
-    for (; t < len; ++t) {
-      const float4 h = encb[(size_t)t * (E / 4) + c];
-      const float w = s_e[t];
+    for (; t < len; t += 8) {
+      const float4 h = __ldg(encb + (size_t)t * E4);
+      const float w = al[t];
       acc.x += w * h.x; acc.y += w * h.y; acc.z += w * h.z; acc.w += w * h.w;
     }
-    ((float4*)(a.context + (size_t)b * E))[c] = acc;
+  }
+  red[tg][threadIdx.x & 63] = acc;
+  __syncthreads();
+  if (tg == 0 && col < E4) {
+#pragma unroll
+    for (int g = 1; g < 8; ++g) {
+      const float4 o = red[g][threadIdx.x & 63];
+      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
+    ((float4*)(context + (size_t)b * E))[col] = acc;
   }
 }
 
@@ -187,10 +204,10 @@ extern "C" int b2_attention_step_forward(int mode, const float* enc, const float
   if (conv_filter) smem += ((size_t)T + filter_width + (size_t)T * 10 + (size_t)filter_width * 10) * 4;
   B2_CHECK_ARG(smem <= 200 * 1024, "b2_attention_step_forward: T=%d too long for shared memory", T);
   B2_CUDA(cudaFuncSetAttribute(attention_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int nsplit = 1;
-  while (B * nsplit < 296 && nsplit < 8 && (E / 4) / (nsplit * 2) >= 32) nsplit *= 2;
-  dim3 grid(B, nsplit);
-  attention_step_kernel<<<grid, kAttnThreads, smem, stream>>>(a);
+  attention_step_kernel<<<B, kAttnThreads, smem, stream>>>(a);
+  B2_LAUNCH_CHECK();
+  dim3 cgrid(B, cdiv(E / 4, 64));
+  attention_context_kernel<<<cgrid, 512, 0, stream>>>(enc, alpha, enc_len, T, E, context);
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
