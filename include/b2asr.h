@@ -190,6 +190,11 @@ int b2_blstm_layer_backward(const b2_lstm_desc* d, const float* x, const void* x
                             void* workspace, size_t workspace_bytes,
                             b2_stream_t stream);
 
+/* In the bf16 path the weight-gradient GEMMs of a layer run on an internal low-priority
+ * side stream (they overlap the next layer's BPTT recurrence).  Call this once after the
+ * last b2_blstm_layer_backward of a step: it makes `stream` wait for them (no host sync). */
+int b2_blstm_backward_join(b2_stream_t stream);
+
 /* ------------------------------------------------------------------------ *
  * Attention step (energy + masked softmax + context)   replaces
  *   AttentionLayer.__call__, models/attention/decoders/attention_layer.py:45-347

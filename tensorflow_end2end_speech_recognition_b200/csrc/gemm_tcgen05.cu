@@ -302,6 +302,11 @@ int make_tmap_generic(CUtensorMap* tm, int dtype_is_f32, const void* base, int r
   return B2_OK;
 }
 
+// cap on persistent GEMM CTAs (0 = all SMs): lets a GEMM on a side stream run next to a
+// recurrence kernel that owns a fixed set of SMs instead of queueing behind it
+static thread_local int g_cta_limit = 0;
+void gemm_set_cta_limit(int n) { g_cta_limit = n; }
+
 static int g_num_sms = 0;
 int num_sms() {
   if (!g_num_sms) {
@@ -324,7 +329,9 @@ static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     attr_done = true;
   }
   const int total = a.m_tiles * a.n_tiles * a.k_splits;
-  const int grid = total < num_sms() ? total : num_sms();
+  int cap = num_sms();
+  if (g_cta_limit > 0 && g_cta_limit < cap) cap = g_cta_limit;
+  const int grid = total < cap ? total : cap;
   gemm_tc_kernel<BN, A_MN, B_MN><<<grid, kGemmThreads, Cfg::kSmem, stream>>>(tmA, tmB, a);
   B2_LAUNCH_CHECK();
   return B2_OK;

@@ -53,6 +53,7 @@ int make_tmap_generic(CUtensorMap* tm, int dtype_is_f32, const void* base, int r
                       const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
                       int swizzle128);
 int num_sms();
+void gemm_set_cta_limit(int n);
 
 // bf16 / tcgen05 layer (lstm_tc.cu)
 size_t tc_layer_workspace_bytes(const b2_lstm_desc* d);
@@ -65,6 +66,8 @@ int tc_layer_backward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16
                       const float* dy, const void* reserve, float* dx, const b2_lstm_grads* g_fw,
                       const b2_lstm_grads* g_bw, void* workspace, size_t workspace_bytes,
                       cudaStream_t stream);
+
+int tc_backward_join(cudaStream_t stream);
 
 inline int env_int(const char* name, int dflt) {
   const char* v = getenv(name);

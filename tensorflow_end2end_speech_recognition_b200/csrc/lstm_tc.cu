@@ -17,7 +17,8 @@ static size_t pad8(size_t x) { return (x + 7) / 8 * 8; }
 
 struct TcWork {
   float* G;                  // [TB, 8H] fp32 gate pre-activations (forward)
-  __nv_bfloat16* dG;         // [TB, 8H] bf16 gate gradients (backward)
+  __nv_bfloat16* dG;         // [TB, 8H] bf16 gate gradients (backward), set 0 / set 1 below
+  __nv_bfloat16* dG2[2]; float* dwx2[2]; float* dwh2[2]; float* dbias2[2];
   __nv_bfloat16* xb;         // [TB, pad8(D)] bf16 copy of x when the caller has none
   __nv_bfloat16* wx;         // [D, 8H] packed input weights
   float* bias;               // [8H] packed bias
@@ -42,12 +43,21 @@ static size_t tc_work_layout(const b2_lstm_desc* d, void* base, TcWork* w) {
   const size_t odwx = take(D * 8 * H * 4);
   const size_t odwh = take(2 * H * 4 * H * 4);
   const size_t odb = take(8 * H * 4);
+  // second set of backward buffers: the weight-gradient GEMMs of layer l run on a side stream
+  // while layer l-1's recurrence already fills the other set
+  const size_t oG1 = take(TB * 8 * H * 2);
+  const size_t odwx1 = take(D * 8 * H * 4);
+  const size_t odwh1 = take(2 * H * 4 * H * 4);
+  const size_t odb1 = take(8 * H * 4);
   if (w) {
     char* p = (char*)base;
     w->G = (float*)(p + oG); w->dG = (__nv_bfloat16*)(p + oG); w->xb = (__nv_bfloat16*)(p + oxb);
     w->wx = (__nv_bfloat16*)(p + owx); w->bias = (float*)(p + ob); w->wh = (uint16_t*)(p + owh);
     w->whT = (uint16_t*)(p + owt); w->dwx = (float*)(p + odwx); w->dwh = (float*)(p + odwh);
     w->dbias = (float*)(p + odb);
+    w->dG2[0] = w->dG; w->dwx2[0] = w->dwx; w->dwh2[0] = w->dwh; w->dbias2[0] = w->dbias;
+    w->dG2[1] = (__nv_bfloat16*)(p + oG1); w->dwx2[1] = (float*)(p + odwx1);
+    w->dwh2[1] = (float*)(p + odwh1); w->dbias2[1] = (float*)(p + odb1);
   }
   return off;
 }
@@ -177,6 +187,42 @@ tc_small_grads_kernel(const __nv_bfloat16* __restrict__ dG, const float* __restr
   }
 }
 
+// ------------------------------------------------------------------ side stream
+// Weight-gradient GEMMs are off the BPTT critical path: they run on a low-priority side
+// stream, capped to the SMs the recurrence clusters leave free, while the next layer's
+// recurrence proceeds on the caller's stream.
+struct SideCtx {
+  cudaStream_t s = nullptr;
+  cudaEvent_t ev_main = nullptr, ev_done[2] = {nullptr, nullptr};
+  bool pending[2] = {false, false};
+  int toggle = 0;
+};
+static SideCtx g_side[16];
+static SideCtx* side_ctx() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  SideCtx* c = &g_side[dev & 15];
+  if (!c->s) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    cudaStreamCreateWithPriority(&c->s, cudaStreamNonBlocking, lo);
+    cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_done[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_done[1], cudaEventDisableTiming);
+  }
+  return c;
+}
+// make `stream` wait for every outstanding side-stream gradient GEMM
+int tc_backward_join(cudaStream_t stream) {
+  SideCtx* c = side_ctx();
+  for (int k = 0; k < 2; ++k)
+    if (c->pending[k]) {
+      B2_CUDA(cudaStreamWaitEvent(stream, c->ev_done[k], 0));
+      c->pending[k] = false;
+    }
+  return B2_OK;
+}
+
 // ------------------------------------------------------------------ layer entry points
 bool tc_layer_supported(const b2_lstm_desc* d) {
   static int sm100 = -1;
@@ -207,7 +253,9 @@ int tc_layer_forward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16*
   Reserve r;
   reserve_layout(d, reserve, &r);
   const int T = d->T, B = d->B, D = d->D_in, H = d->H, TB = T * B;
-  int rc = pack_weights(d, fw, bw, w, false, stream);
+  int rc = tc_backward_join(stream);
+  if (rc) return rc;
+  rc = pack_weights(d, fw, bw, w, false, stream);
   if (rc) return rc;
   const __nv_bfloat16* xa = x_lp;
   int ldx = D;
@@ -260,30 +308,39 @@ int tc_layer_backward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16
   Reserve r;
   reserve_layout(d, (void*)reserve, &r);
   const int T = d->T, B = d->B, D = d->D_in, H = d->H, TB = T * B;
+  const bool use_side = env_int("B2_SIDE_STREAM", 1) != 0;
+  SideCtx* sc = side_ctx();
+  const int k = use_side ? sc->toggle : 0;
+  if (sc->pending[k]) {            // the side work that last used buffer set k must be done
+    B2_CUDA(cudaStreamWaitEvent(stream, sc->ev_done[k], 0));
+    sc->pending[k] = false;
+  }
+  __nv_bfloat16* dG = w.dG2[k];
+  float* dwx = w.dwx2[k]; float* dwh = w.dwh2[k]; float* dbias = w.dbias2[k];
   int rc = pack_weights(d, fw, bw, w, true, stream);
   if (rc) return rc;
-  // 1. BPTT recurrence -> dG (bf16, packed order)
+  // 1. BPTT recurrence -> dG (bf16, packed order); bias / peephole gradients accumulate in
+  //    registers inside the kernel and are flushed with atomics
   RecBwdArgs ba;
   ba.T = T; ba.B = B; ba.H = H; ba.NG = 0; ba.seq_len = seq_len; ba.wpackT = w.whT;
   const b2_lstm_params* P[2] = {fw, bw};
-  for (int dir = 0; dir < 2; ++dir) {
-    ba.wi[dir] = P[dir]->w_i_diag; ba.wf[dir] = P[dir]->w_f_diag; ba.wo[dir] = P[dir]->w_o_diag;
-  }
-  ba.use_peephole = d->use_peephole; ba.cell_clip = d->cell_clip; ba.keep_prob = d->keep_prob;
-  ba.seed = d->dropout_seed; ba.gates = r.gates; ba.cs = r.cs; ba.dG = w.dG; ba.dfinal = nullptr;
-  B2_CUDA(cudaMemsetAsync(w.dbias, 0, (size_t)8 * H * 4, stream));
-  ba.dbias = w.dbias;
   const b2_lstm_grads* GR[2] = {g_fw, g_bw};
   for (int dir = 0; dir < 2; ++dir) {
+    ba.wi[dir] = P[dir]->w_i_diag; ba.wf[dir] = P[dir]->w_f_diag; ba.wo[dir] = P[dir]->w_o_diag;
     ba.dwi[dir] = GR[dir]->w_i_diag; ba.dwf[dir] = GR[dir]->w_f_diag; ba.dwo[dir] = GR[dir]->w_o_diag;
   }
+  ba.use_peephole = d->use_peephole; ba.cell_clip = d->cell_clip; ba.keep_prob = d->keep_prob;
+  ba.seed = d->dropout_seed; ba.gates = r.gates; ba.cs = r.cs; ba.dG = dG; ba.dfinal = nullptr;
+  B2_CUDA(cudaMemsetAsync(dbias, 0, (size_t)8 * H * 4, stream));
+  ba.dbias = dbias;
   ba.dbg = nullptr;
+  const int nchain = env_int("B2_REC_NCHAIN", 0);
   if (env_int("B2_REC_DBG", 0)) {
     static long long* dbg_buf = nullptr;
     if (!dbg_buf) cudaMalloc(&dbg_buf, 64 * sizeof(long long));
     cudaMemsetAsync(dbg_buf, 0, 64 * sizeof(long long), stream);
     ba.dbg = dbg_buf;
-    rc = rec_tc_backward(ba, dy, env_int("B2_REC_NCHAIN", 0), stream);
+    rc = rec_tc_backward(ba, dy, nchain, stream);
     long long hb[8];
     cudaMemcpyAsync(hb, dbg_buf, sizeof(hb), cudaMemcpyDeviceToHost, stream);
     cudaStreamSynchronize(stream);
@@ -291,11 +348,10 @@ int tc_layer_backward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16
             "bar1=%lld wait_mma=%lld ld+convert=%lld bar2+send=%lld\n",
             hb[0] / T, hb[1] / T, hb[2] / T, hb[3] / T, hb[4] / T, hb[5] / T, hb[6] / T);
   } else {
-    rc = rec_tc_backward(ba, dy, env_int("B2_REC_NCHAIN", 0), stream);
+    rc = rec_tc_backward(ba, dy, nchain, stream);
   }
   if (rc) return rc;
-  // 2. bias + peephole gradients: accumulated inside the recurrence kernel (registers -> atomics)
-  // 3. time-batched GEMMs on packed operands
+  // 2. critical path: dX[TB, D] = dG[TB, 8H] . Wx_packed^T  (sums both directions)
   const __nv_bfloat16* xa = x_lp;
   int ldx = D;
   if (!xa || (D % 8)) {
@@ -304,31 +360,51 @@ int tc_layer_backward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16
     if (rc) return rc;
     xa = w.xb;
   }
-  if (dx) {   // dX[TB, D] = dG[TB, 8H] . Wx_packed^T  (sums both directions)
-    rc = gemm_bf16_tc(0, 0, TB, D, 8 * H, 1.f, w.dG, 8 * H, w.wx, 8 * H, dx, D, nullptr,
+  if (dx) {
+    rc = gemm_bf16_tc(0, 0, TB, D, 8 * H, 1.f, dG, 8 * H, w.wx, 8 * H, dx, D, nullptr,
                       EPI_STORE_F32, 0, stream);
     if (rc) return rc;
   }
+  // 3. off the critical path: weight gradients on packed operands
+  cudaStream_t gs = stream;
+  if (use_side) {
+    B2_CUDA(cudaEventRecord(sc->ev_main, stream));
+    B2_CUDA(cudaStreamWaitEvent(sc->s, sc->ev_main, 0));
+    gs = sc->s;
+    // leave the SMs of the next layer's recurrence clusters alone
+    const int ng = cdiv(B, RN);
+    const int nch = nchain > 0 ? (nchain > 2 ? 2 : nchain) : (ng >= 2 ? 2 : 1);
+    const int rec_ctas = 2 * cdiv(ng, nch) * (H / RU);
+    int free_sms = num_sms() - rec_ctas;
+    if (free_sms < 16) free_sms = 16;
+    gemm_set_cta_limit(free_sms);
+  }
   // dWx_packed[D, 8H] = X^T . dG
-  B2_CUDA(cudaMemsetAsync(w.dwx, 0, (size_t)D * 8 * H * 4, stream));
-  rc = gemm_bf16_tc(1, 1, D, 8 * H, TB, 1.f, xa, ldx, w.dG, 8 * H, w.dwx, 8 * H, nullptr,
-                    EPI_ATOMIC_F32, 0, stream);
-  if (rc) return rc;
+  B2_CUDA(cudaMemsetAsync(dwx, 0, (size_t)D * 8 * H * 4, gs));
+  rc = gemm_bf16_tc(1, 1, D, 8 * H, TB, 1.f, xa, ldx, dG, 8 * H, dwx, 8 * H, nullptr,
+                    EPI_ATOMIC_F32, 0, gs);
   // dWh_packed[dir][H, 4H] = Hprev_dir^T . dG_dir   (hs shifted by one step)
-  B2_CUDA(cudaMemsetAsync(w.dwh, 0, (size_t)2 * H * 4 * H * 4, stream));
-  if (T > 1) {
-    for (int dir = 0; dir < 2; ++dir) {
+  if (!rc) rc = (cudaMemsetAsync(dwh, 0, (size_t)2 * H * 4 * H * 4, gs) == cudaSuccess) ? B2_OK : B2_ERR_CUDA;
+  if (!rc && T > 1) {
+    for (int dir = 0; dir < 2 && !rc; ++dir) {
       const __nv_bfloat16* ha = r.hs_lp + (size_t)dir * H + (dir == 0 ? 0 : (size_t)B * 2 * H);
-      const __nv_bfloat16* gb = w.dG + (size_t)dir * 4 * H + (dir == 0 ? (size_t)B * 8 * H : 0);
+      const __nv_bfloat16* gb = dG + (size_t)dir * 4 * H + (dir == 0 ? (size_t)B * 8 * H : 0);
       rc = gemm_bf16_tc(1, 1, H, 4 * H, (T - 1) * B, 1.f, ha, 2 * H, gb, 8 * H,
-                        w.dwh + (size_t)dir * H * 4 * H, 4 * H, nullptr, EPI_ATOMIC_F32, 0, stream);
-      if (rc) return rc;
+                        dwh + (size_t)dir * H * 4 * H, 4 * H, nullptr, EPI_ATOMIC_F32, 0, gs);
     }
   }
-  unpack_lstm_grads_kernel<<<num_sms() * 8, 256, 0, stream>>>(w.dwx, w.dwh, w.dbias, D, H,
-                                                            g_fw->kernel, g_bw->kernel, g_fw->bias,
-                                                            g_bw->bias);
+  gemm_set_cta_limit(0);
+  if (rc) return rc;
+  unpack_lstm_grads_kernel<<<num_sms() * 4, 256, 0, gs>>>(dwx, dwh, dbias, D, H, g_fw->kernel,
+                                                        g_bw->kernel, g_fw->bias, g_bw->bias);
   B2_LAUNCH_CHECK();
+  if (use_side) {
+    B2_CUDA(cudaEventRecord(sc->ev_done[k], sc->s));
+    sc->pending[k] = true;
+    sc->toggle ^= 1;
+    // the first layer is the last one of a backward pass: hand the gradients back
+    if (!dx) return tc_backward_join(stream);
+  }
   return B2_OK;
 }
 

@@ -121,5 +121,6 @@ class BLSTMEncoder(object):
                                           need_dx=(i_layer > 1 or need_dx), x_lp=x_lp)
             if on_layer_done is not None:
                 on_layer_done(i_layer)
+        ops.blstm_backward_join()      # side-stream weight-gradient GEMMs -> gradients final
         self._saved = None
         return dy

@@ -193,6 +193,11 @@ def blstm_layer_forward(desc, x, seq_len, p_fw, p_bw, want_final_state=False, x_
     return y, fs, reserve
 
 
+def blstm_backward_join():
+    """current stream waits for the side-stream weight-gradient GEMMs of the bf16 path."""
+    _lib.check(_lib.load().b2_blstm_backward_join(_stream()), "b2_blstm_backward_join")
+
+
 def reserve_y_lp(desc, reserve):
     """raw device pointer (int) of the bf16 layer output kept in `reserve`, or 0."""
     if reserve is None:

@@ -46,6 +46,7 @@ def run_layer(dev, T, B, D, H, seq, precision, peephole=True, cell_clip=None, se
     G = {d: {k: torch.zeros_like(v) for k, v in P[d].items()} for d in P}
     dx = ops.blstm_layer_backward(desc, xd, seq_t, P["fw"], P["bw"], torch.tensor(dy, device=dev),
                                   reserve, G["fw"], G["bw"])
+    ops.blstm_backward_join()
     torch.cuda.synchronize()
     masks = None
     if keep_prob < 1.0:
