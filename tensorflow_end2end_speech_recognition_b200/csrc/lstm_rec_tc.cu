@@ -299,6 +299,10 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
       }
       float pwi = 0.f, pwf = 0.f, pwo = 0.f;
       if (a.use_peephole) { pwi = a.wi[dir][u]; pwf = a.wf[dir][u]; pwo = a.wo[dir][u]; }
+      size_t cell0[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cell0[j] = ((size_t)bidx[j] * 2 + dir) * H + u;
+      const size_t cell_step = (size_t)B * 2 * H;
       int stage = 0; uint32_t gph = 0;
       for (int t = 0; t < T; ++t) {
         const int td = dir ? T - 1 - t : t;
@@ -387,7 +391,7 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             if (bidx[j] < B) {
-              const size_t cell = (((size_t)td * B + bidx[j]) * 2 + dir) * H + u;
+              const size_t cell = cell0[j] + (size_t)td * cell_step;
               *(float4*)(a.gates + cell * 4) = gsv[j];
               a.cs[cell] = cst[j];
             }
@@ -642,6 +646,11 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
       float pwi = 0.f, pwf = 0.f, pwo = 0.f;
       if (a.use_peephole) { pwi = a.wi[dir][u]; pwf = a.wf[dir][u]; pwo = a.wo[dir][u]; }
       uint8_t* bop = smem + L::kBopOff + c * 4096;
+      __nv_bfloat16* dgp[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        dgp[j] = a.dG + (size_t)bidx[j] * 8 * H + (size_t)dir * 4 * H + u * 4;
+      const size_t dg_step = (size_t)B * 8 * H;
       int stage = 0; uint32_t gph = 0;
       uint32_t rph = 0;                          // bit p: parity of rfull[c][p]
       for (int s = 0; s < T; ++s) {
@@ -681,17 +690,21 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
           cpv[j] = tp_ok ? Rs[2048 + 512 + bl * 32 + ul] : 0.f;
           dyq[j] = Rs[2048 + 1024 + bl * 32 + ul];
         }
+        if (a.keep_prob < 1.f) {       // DropoutWrapper mask, outside the cell loop (keeps it branch-free)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const size_t oidx = ((size_t)td * B + bidx[j]) * 2 * H + (size_t)dir * H + u;
+            dyq[j] = dropout_keep(a.seed, oidx, a.keep_prob) ? dyq[j] / a.keep_prob : 0.f;
+          }
+        }
+        const long long bL = clock64();
         uint2 pkv[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float cc = ccv[j], c_prev = cpv[j];
-          float dyv = dyq[j];
+          const float dyv = dyq[j];
           const bool active = td < len[j];
           const bool nb_active = s > 0 && tn >= 0 && tn < T && tn < len[j];
-          if (a.keep_prob < 1.f) {
-            const size_t oidx = ((size_t)td * B + bidx[j]) * 2 * H + (size_t)dir * H + u;
-            dyv = dropout_keep(a.seed, oidx, a.keep_prob) ? dyv / a.keep_prob : 0.f;
-          }
           const float dh = dyv + (nb_active ? dh_rec[j] : 0.f);
           const float dc_in = nb_active ? dcs[j] : 0.f;
           const float gi = g4[j].x, gg = g4[j].y, gf = g4[j].z, go = g4[j].w;
@@ -715,12 +728,12 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
           __nv_bfloat162 lo = __floats2bfloat162_rn(dzi, dzg), hi = __floats2bfloat162_rn(dzf2, dzo2);
           pkv[j].x = *(uint32_t*)&lo; pkv[j].y = *(uint32_t*)&hi;
         }
+        const long long bM = clock64();
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int bl = gq * 4 + j;
           *(uint2*)(bop + (ul >> 1) * 256 + (bl >> 3) * 128 + (bl & 7) * 16 + (ul & 1) * 8) = pkv[j];
-          if (bidx[j] < B)
-            *(uint2*)(a.dG + ((size_t)td * B + bidx[j]) * 8 * H + (size_t)dir * 4 * H + u * 4) = pkv[j];
+          if (bidx[j] < B) *(uint2*)(dgp[j] + (size_t)td * dg_step) = pkv[j];
         }
         const long long b3 = clock64();
         fence_proxy_async_smem();
@@ -776,6 +789,9 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
           a.dbg[0] += b1 - b0;   // wait partials + sum
           a.dbg[1] += b2 - b1;   // wait ring
           a.dbg[2] += b3 - b2;   // math + stores
+          a.dbg[8] += bL - b2;   //   smem loads
+          a.dbg[9] += bM - bL;   //   math
+          a.dbg[10] += b3 - bM;  //   stores
           a.dbg[3] += b4 - b3;   // fence + bar + arrive
           a.dbg[4] += b5 - b4;   // wait MMA
           a.dbg[5] += b6 - b5;   // tmem ld + convert + stage

@@ -343,9 +343,10 @@ int tc_layer_backward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16
     cudaMemsetAsync(dbg_buf, 0, 64 * sizeof(long long), stream);
     ba.dbg = dbg_buf;
     rc = rec_tc_backward(ba, dy, nchain, stream);
-    long long hb[8];
+    long long hb[12];
     cudaMemcpyAsync(hb, dbg_buf, sizeof(hb), cudaMemcpyDeviceToHost, stream);
     cudaStreamSynchronize(stream);
+    fprintf(stderr, "[rec bwd dbg2] loads=%lld math=%lld stores=%lld\n", hb[8] / T, hb[9] / T, hb[10] / T);
     fprintf(stderr, "[rec bwd dbg] cycles/step: wait_partials+sum=%lld wait_ring=%lld math+stores=%lld "
             "bar1=%lld wait_mma=%lld ld+convert=%lld bar2+send=%lld\n",
             hb[0] / T, hb[1] / T, hb[2] / T, hb[3] / T, hb[4] / T, hb[5] / T, hb[6] / T);
