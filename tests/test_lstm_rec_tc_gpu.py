@@ -48,3 +48,29 @@ def test_rec_tc_matches_fp32_step_kernels_long(cuda):
     err = np.abs(ys["fp32"][0] - ys["bf16"][0]).max()
     assert err < 2e-2, err
     assert np.abs(ys["fp32"][1] - ys["bf16"][1]).max() < 3e-2
+
+
+def test_rec_tc_dropout_matches_oracle_mask(cuda):
+    """DropoutWrapper(output_keep_prob) in the bf16 path: same counter-hash mask as the oracle,
+    applied to the emitted output only (the bf16 shadow fed to the next layer included)."""
+    from tensorflow_end2end_speech_recognition_b200 import ops
+    T, B, D, H = 14, 16, 32, 64
+    seq = [T] + list(np.random.RandomState(3).randint(T // 2, T + 1, size=B - 1))
+    got, ref = run_layer(cuda, T, B, D, H, seq, ops.PREC_BF16, seed=21, keep_prob=0.75)
+    compare(got, ref, 3e-2, 6e-2)
+
+
+def test_hybrid_fallback_path_when_units_not_multiple_of_32(cuda):
+    """H=48 cannot use the cluster/TMEM recurrence -> tcgen05 GEMMs + fp32 step kernels."""
+    from tensorflow_end2end_speech_recognition_b200 import ops
+    T, B, D, H = 10, 4, 16, 48
+    got, ref = run_layer(cuda, T, B, D, H, [10, 7, 10, 3], ops.PREC_BF16, seed=23)
+    compare(got, ref, 3e-2, 6e-2)
+
+
+def test_single_step_and_tiny_batch(cuda):
+    from tensorflow_end2end_speech_recognition_b200 import ops
+    got, ref = run_layer(cuda, 1, 1, 32, 32, [1], ops.PREC_BF16, seed=25)
+    compare(got, ref, 3e-2, 6e-2)
+    got, ref = run_layer(cuda, 2, 3, 32, 32, [2, 1, 2], ops.PREC_BF16, seed=26)
+    compare(got, ref, 3e-2, 6e-2)

@@ -98,3 +98,38 @@ def test_overfit_one_utterance(cuda):
             if ler < 0.1:
                 break
     assert ler < 0.1, "did not overfit: LER %.3f loss %.3f" % (ler, float(loss))
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 3e-4), ("bf16", 3e-2)])
+def test_timit_shape_plumbing_config1(cuda, precision, tol):
+    """BASELINE configs[0]: TIMIT 61-phone CTC, 2x256 BLSTM, 120-d input, T~300, batch 8:
+    the same batch through the GPU model and the CPU oracle (the reference's own CPU-runnable case)."""
+    rng = np.random.RandomState(5)
+    B, T, D, H, L, C = 8, 300, 120, 256, 2, 61
+    model = build(cuda, precision, D, H, L, C, clip=5.0, strict_input_size=True)
+    x, seq, labels = make_batch(rng, B, T, D, C, 25, 55)
+    loss, logits = model.compute_loss(x, labels, seq, keep_prob=1.0)
+    torch.cuda.synchronize()
+    vs = {v.name: v.tensor.cpu().numpy() for v in model.trainable_variables()}
+    tr = omodel.OracleTrainer(vs, L, clip_grad_norm=None, dtype=torch.float32)
+    l_ref, logits_ref, _ = tr.loss_and_grads(x, seq, labels)
+    assert abs(float(loss) - l_ref) <= tol * abs(l_ref), (float(loss), l_ref)
+    np.testing.assert_allclose(logits.cpu().numpy(), logits_ref, rtol=10 * tol, atol=10 * tol)
+
+
+def test_mid_size_bf16_loss_parity(cuda):
+    """3x256 BLSTM, T=200, B=16: CTC loss of the tcgen05 path vs the fp32 CUDA-core path and the
+    CPU oracle (north star: CTC loss within 1e-3 rtol -- asserted for fp32, reported for bf16)."""
+    rng = np.random.RandomState(6)
+    B, T, D, H, L, C = 16, 200, 80, 256, 3, 28
+    x, seq, labels = make_batch(rng, B, T, D, C, 20, 40)
+    losses = {}
+    for prec in ("fp32", "bf16"):
+        model = build(cuda, prec, D, H, L, C)
+        loss, _ = model.compute_loss(x, labels, seq, keep_prob=1.0, is_training=False)
+        losses[prec] = float(loss)
+        vs = {v.name: v.tensor.cpu().numpy() for v in model.trainable_variables()}
+    tr = omodel.OracleTrainer(vs, L, clip_grad_norm=None, dtype=torch.float32)
+    l_ref, _, _ = tr.loss_and_grads(x, seq, labels)
+    assert abs(losses["fp32"] - l_ref) <= 1e-3 * abs(l_ref)
+    assert abs(losses["bf16"] - l_ref) <= 1e-2 * abs(l_ref), (losses, l_ref)
