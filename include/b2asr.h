@@ -244,6 +244,9 @@ enum {
 int b2_clip_by_norm_multi(float* const* grads, const int64_t* sizes, int n,
                           float clip_norm, float post_scale, float* norms,
                           b2_stream_t stream);
+/* y_k += alpha * x_k over n tensors (weight-decay gradient wd*w, ctc.py:280-286) */
+int b2_axpy_multi(float* const* xs, float* const* ys, const int64_t* sizes, int n,
+                  float alpha, b2_stream_t stream);
 /* TF-1.x update rules; state0/state1 per tensor (may be NULL
  * where the rule needs none); step = 1-based global step (Adam). */
 int b2_optimizer_step_multi(int kind, float* const* params,

@@ -60,6 +60,7 @@ PROTOTYPES = {
     "b2_transpose_01": (_i, [_p, _p, _i, _i, _i, _p]),
     "b2_colsum": (_i, [_p, _i64, _i, _i, _p, _i, _p]),
     "b2_clip_by_norm_multi": (_i, [_p, _p, _i, _f, _f, _p, _p]),
+    "b2_axpy_multi": (_i, [_p, _p, _p, _i, _f, _p]),
     "b2_optimizer_step_multi": (_i, [_i, _p, _p, _p, _p, _p, _i, _f, _i64, _p]),
 }
 

@@ -33,6 +33,7 @@ using namespace sm100;
 constexpr int RGS = 3;        // TMA ring stages
 constexpr int RPITCH = 20;    // transpose scratch pitch (floats)
 constexpr int NISSW = 4;      // MMA issuer warps
+constexpr int ACC_STRIDE = 32; // TMEM columns between accumulators (16 used)
 
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
                                             int c0, int c1, int c2) {
@@ -185,7 +186,7 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
           tc_fence_after();
           // one descriptor per buffer; the k-th step only moves the start address by 512 B
           const uint64_t bd0 = bdesc0 + (uint64_t)((c * 2 + p) * (L::kHbufBytes >> 4));
-          const uint32_t acc = tAcc + (c * NISS + warp) * RN;
+          const uint32_t acc = tAcc + (c * NISS + warp) * ACC_STRIDE;
 #pragma unroll
           for (int kk = 0; kk < KPER; ++kk) {
             const int k = warp * KPER + kk;
@@ -304,6 +305,7 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
       for (int j = 0; j < 4; ++j) cell0[j] = ((size_t)bidx[j] * 2 + dir) * H + u;
       const size_t cell_step = (size_t)B * 2 * H;
       int stage = 0; uint32_t gph = 0;
+      const long long loop_t0 = clock64();
       for (int t = 0; t < T; ++t) {
         const int td = dir ? T - 1 - t : t;
         const bool dbg = a.dbg && blockIdx.x == 0 && ctid == 0 && c == 0;
@@ -326,7 +328,7 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
           uint32_t w[NISS][16];
 #pragma unroll
           for (int s2 = 0; s2 < NISS; ++s2)
-            tmem_ld_32x32b_x16(tAcc + (c * NISS + s2) * RN + ((uint32_t)(q * 32) << 16), w[s2]);
+            tmem_ld_32x32b_x16(tAcc + (c * NISS + s2) * ACC_STRIDE + ((uint32_t)(q * 32) << 16), w[s2]);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -422,6 +424,7 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
         }
         if (++stage == RGS) { stage = 0; gph ^= 1; }
       }
+      if (a.dbg && ctid == 0 && cta == 0) a.dbg[16 + cluster_id * 2 + c] = clock64() - loop_t0;
       if (a.final_state) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -590,7 +593,7 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
           if (!mbar_try_wait(&bready[c], s & 1)) continue;
           tc_fence_after();
           const uint64_t bd0 = make_smem_desc(smem_u32(smem + L::kBopOff + c * 4096), 256, 128, 0);
-          const uint32_t acc = tAcc + (c * 4 + warp) * RN;
+          const uint32_t acc = tAcc + (c * 4 + warp) * ACC_STRIDE;
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
             mma_ts(acc, tA + warp * 64 + kk * 8, bd0 + (uint64_t)(kk * 32), idesc, kk > 0 ? 1u : 0u);
@@ -754,7 +757,7 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
           uint32_t v[4][16];
 #pragma unroll
           for (int m = 0; m < 4; ++m)
-            if (m < MT) tmem_ld_32x32b_x16(tAcc + (c * 4 + m) * RN + ((uint32_t)(q * 32) << 16), v[m]);
+            if (m < MT) tmem_ld_32x32b_x16(tAcc + (c * 4 + m) * ACC_STRIDE + ((uint32_t)(q * 32) << 16), v[m]);
           tmem_ld_wait();
 #pragma unroll
           for (int m = 0; m < 4; ++m) {

@@ -286,9 +286,11 @@ int tc_layer_forward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16*
     cudaMemsetAsync(dbg_buf, 0, 64 * sizeof(long long), stream);
     ra.dbg = dbg_buf;
     rc = rec_tc_forward(ra, w.G, env_int("B2_REC_NCHAIN", 0), stream);
-    long long hb[8];
+    long long hb[32];
     cudaMemcpyAsync(hb, dbg_buf, sizeof(hb), cudaMemcpyDeviceToHost, stream);
     cudaStreamSynchronize(stream);
+    fprintf(stderr, "[rec fwd dbg3] loop cycles per (cluster,chain): %lld %lld | %lld %lld | %lld %lld | %lld %lld\n",
+            hb[16], hb[17], hb[18], hb[19], hb[20], hb[21], hb[22], hb[23]);
     fprintf(stderr, "[rec fwd dbg] cycles/step: mma_wait_h=%lld mma_issue=%lld | epi wait_acc=%lld "
             "ld+transpose=%lld wait_G=%lld math+saves=%lld fence+bar=%lld send+store=%lld\n",
             hb[0] / T, hb[1] / T, hb[2] / T, hb[3] / T, hb[4] / T, hb[5] / T, hb[6] / T, hb[7] / T);

@@ -89,6 +89,19 @@ optimizer_multi_kernel(int kind, float* const* __restrict__ params, float* const
   }
 }
 
+// y_k += alpha * x_k for a list of tensors (weight-decay gradient, models/ctc/ctc.py:280-286)
+__global__ void __launch_bounds__(256)
+axpy_multi_kernel(float* const* __restrict__ xs, float* const* __restrict__ ys,
+                  const int64_t* __restrict__ sizes, float alpha) {
+  const int k = blockIdx.y;
+  const float* x = xs[k];
+  float* y = ys[k];
+  const int64_t n = sizes[k];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = fmaf(alpha, x[i], y[i]);
+}
+
 // [d0, d1, d2] -> [d1, d0, d2]
 __global__ void __launch_bounds__(256)
 transpose01_kernel(const float* __restrict__ x, float* __restrict__ y, int d0, int d1, int d2) {
@@ -145,6 +158,16 @@ extern "C" int b2_clip_by_norm_multi(float* const* grads, const int64_t* sizes, 
     B2_LAUNCH_CHECK();
   }
   clip_scale_multi_kernel<<<grid, 256, 0, stream>>>(grads, sizes, norms, clip_norm, post_scale);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_axpy_multi(float* const* xs, float* const* ys, const int64_t* sizes, int n,
+                            float alpha, b2_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B2_CHECK_ARG(xs && ys && sizes && n > 0, "b2_axpy_multi: bad argument");
+  dim3 grid(64, n);
+  axpy_multi_kernel<<<grid, 256, 0, stream>>>(xs, ys, sizes, alpha);
   B2_LAUNCH_CHECK();
   return B2_OK;
 }

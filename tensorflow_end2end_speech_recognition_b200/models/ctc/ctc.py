@@ -45,8 +45,6 @@ class CTC(ModelBase):
         if clip_grad_norm is not None:
             assert float(clip_grad_norm) > 0, "clip_grad_norm must be larger than 0."
         assert float(weight_decay) >= 0, "weight_decay must not be a negative value."
-        if float(weight_decay) > 0:
-            raise NotImplementedError("weight_decay > 0 is not built yet (reference configs use 0)")
         if bottleneck_dim not in (None, 0):
             raise NotImplementedError("bottleneck_dim is not built yet (reference configs use 0)")
 
@@ -91,6 +89,11 @@ class CTC(ModelBase):
         self._allocate_variables(named, self.device)
         self._step = 0
         self._ctx = None
+        # weight decay covers every variable whose name has no 'bias' (ctc.py:283-285): kernels,
+        # peepholes and the output weights
+        decay = [v for v in self._variables if "bias" not in v.name.lower()]
+        self._decay_params = ops.TensorList([v.tensor for v in decay])
+        self._decay_grads = ops.TensorList([v.grad for v in decay])
 
     # ----------------------------------------------------------------- feeds
     def create_placeholders(self):
@@ -152,6 +155,10 @@ class CTC(ModelBase):
                                             need_grad=is_training)
         self.ctc_losses = losses
         total_loss = losses.mean()
+        if self.weight_decay > 0:
+            # weight_decay * sum_{non-bias} l2_loss(w), l2_loss = sum(w^2)/2   (ctc.py:280-286)
+            sq = ops.clip_by_norm_multi(self._decay_params, 3.0e38)      # norms^2, no scaling
+            total_loss = total_loss + 0.5 * float(self.weight_decay) * sq.sum()
         self._ctx = (dlogits, inputs.shape) if is_training else None
         return total_loss, logits
 
@@ -167,6 +174,8 @@ class CTC(ModelBase):
         ops.colsum(dl2d, out=self.grads["output/biases"], accumulate=True)
         denc = ops.gemm(dl2d, self.variables["output/weights"], False, True, None, prec)
         self.encoder.backward(denc.view(T, B, -1), self.variables, self.grads)
+        if self.weight_decay > 0:
+            ops.axpy_multi(self._decay_params, self._decay_grads, float(self.weight_decay))
         self._ctx = None
 
     # ---------------------------------------------------------------- decode

@@ -246,6 +246,13 @@ def clip_by_norm_multi(grads, clip_norm, post_scale=1.0):
     return norms
 
 
+def axpy_multi(xs, ys, alpha):
+    """ys[k] += alpha * xs[k]  (TensorLists with equal sizes)."""
+    lib = _lib.load()
+    _lib.check(lib.b2_axpy_multi(_ptr(xs.ptrs), _ptr(ys.ptrs), _ptr(xs.sizes), xs.n, float(alpha), _stream()),
+               "b2_axpy_multi")
+
+
 def optimizer_step_multi(kind, params, grads, state0, state1, learning_rate, step):
     lib = _lib.load()
     rc = lib.b2_optimizer_step_multi(_lib.OPT_KINDS[kind], _ptr(params.ptrs), _ptr(grads.ptrs),

@@ -133,3 +133,27 @@ def test_mid_size_bf16_loss_parity(cuda):
     l_ref, _, _ = tr.loss_and_grads(x, seq, labels)
     assert abs(losses["fp32"] - l_ref) <= 1e-3 * abs(l_ref)
     assert abs(losses["bf16"] - l_ref) <= 1e-2 * abs(l_ref), (losses, l_ref)
+
+
+def test_weight_decay_loss_and_gradient(cuda):
+    """total_loss = ctc + wd * sum_{non-bias vars} l2_loss(w)  (ctc.py:280-286); grad += wd * w."""
+    rng = np.random.RandomState(7)
+    B, T, D, H, L, C = 4, 30, 12, 32, 1, 7
+    wd = 1e-2
+    model = build(cuda, "fp32", D, H, L, C, weight_decay=wd)
+    plain = build(cuda, "fp32", D, H, L, C)
+    x, seq, labels = make_batch(rng, B, T, D, C, 2, 8)
+    l0, _ = plain.compute_loss(x, labels, seq, keep_prob=1.0)
+    plain._backward()
+    l1, _ = model.compute_loss(x, labels, seq, keep_prob=1.0)
+    model._backward()
+    torch.cuda.synchronize()
+    reg = 0.0
+    for v0, v1 in zip(plain.trainable_variables(), model.trainable_variables()):
+        w = v0.tensor.cpu().numpy().astype(np.float64)
+        if "bias" in v0.name.lower():
+            np.testing.assert_allclose(v1.grad.cpu().numpy(), v0.grad.cpu().numpy(), atol=1e-6)
+        else:
+            reg += 0.5 * np.sum(w * w)
+            np.testing.assert_allclose(v1.grad.cpu().numpy(), v0.grad.cpu().numpy() + wd * w, rtol=1e-5, atol=1e-6)
+    assert abs(float(l1) - (float(l0) + wd * reg)) < 1e-4 * abs(float(l1))
