@@ -64,6 +64,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Polite wait for warps that are not on the critical path of the tensor pipe: back off between
+// polls so that the spinning does not steal issue slots / shared-memory bandwidth.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
 // Whole-warp wait where only lane 0 polls: 32 spinning lanes steal issue slots from the
 // MMA-issuer warp that shares the SM sub-partition.
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
