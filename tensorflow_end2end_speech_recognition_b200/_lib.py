@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb2asr.so")
+LIB_PATH = os.environ.get("B2ASR_LIB", os.path.join(_HERE, "libb2asr.so"))   # override: A/B builds
 
 PREC_FP32, PREC_BF16 = 0, 1
 OPT_KINDS = {"sgd": 0, "momentum": 1, "nestrov": 2, "adagrad": 3, "adadelta": 4, "adam": 5,
