@@ -285,6 +285,42 @@ def main():
                                   "frac": by / t_ctc / 1e6 / peaks["hbm_gbs"], "traffic": None, "ms": t_ctc,
                                   "note": "latency-bound at C=29 (T sequential lattice steps); bytes = "
                                           "8*T*B*C + 16*T*B*S spill", "peak_src": peaks["src"]}
+        # the persistent recurrence kernels (dominant share of the step), timed with CUDA events
+        # placed around their launches inside the library
+        from oracle import lstm as olstm
+        Hh = CFG["num_units"]
+        lay = olstm.init_blstm_params(2 * Hh, Hh, 1, parameter_init=0.1, seed=0)[0]
+        Pl = {d: {k: torch.tensor(v, device=dev) for k, v in lay[d].items()} for d in lay}
+        Gl = {d: {k: torch.zeros_like(v) for k, v in Pl[d].items()} for d in Pl}
+        xx = torch.randn(T, B, 2 * Hh, device=dev)
+        dyy = torch.randn(T, B, 2 * Hh, device=dev)
+        desc = ops.lstm_desc(T, B, 2 * Hh, Hh, precision=ops.PREC_BF16 if args.precision == "bf16" else ops.PREC_FP32)
+        lib.b2_blstm_profile_enable(1)
+        f_ms, b_ms = [], []
+        for it in range(4):
+            yy, _, res = ops.blstm_layer_forward(desc, xx, seq_dev, Pl["fw"], Pl["bw"])
+            ops.blstm_layer_backward(desc, xx, seq_dev, Pl["fw"], Pl["bw"], dyy, res, Gl["fw"], Gl["bw"])
+            ops.blstm_backward_join()
+            torch.cuda.synchronize()
+            fm, bm = C.c_float(0), C.c_float(0)
+            if lib.b2_blstm_profile_last_ms(C.byref(fm), C.byref(bm)) == 0 and it > 0:
+                f_ms.append(fm.value); b_ms.append(bm.value)
+        lib.b2_blstm_profile_enable(0)
+        del xx, dyy, yy, res
+        if f_ms and min(f_ms) > 0:
+            rec_fl = 2.0 * T * B * 2 * Hh * 4 * Hh            # h.Wh over T steps, both directions
+            tf_, tb_ = float(np.median(f_ms)), float(np.median(b_ms))
+            roof["blstm_recurrence_fwd"] = {
+                "kernel": "lstm_rec_fwd_kernel<2,32> (persistent cluster/TMEM recurrence, one layer, T=1000)",
+                "bound": "tensor", "achieved": rec_fl / tf_ / 1e9, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": rec_fl / tf_ / 1e9 / peaks["bf16_tflops"], "traffic": 2.71e9, "ms": tf_,
+                "note": "latency-bound: 1000 dependent steps (tensor-pipe issue + DSMEM all-gather + gate math); "
+                        "traffic = ncu dram bytes of profiles/prof_rec_fwd_r01", "peak_src": peaks["src"] + " burst"}
+            roof["blstm_recurrence_bwd"] = {
+                "kernel": "lstm_rec_bwd_kernel<2> (BPTT, one layer)", "bound": "tensor",
+                "achieved": rec_fl / tb_ / 1e9, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": rec_fl / tb_ / 1e9 / peaks["bf16_tflops"], "traffic": 2.08e9, "ms": tb_,
+                "note": "latency-bound; traffic from profiles/prof_rec_bwd_r01", "peak_src": peaks["src"] + " burst"}
         # whole step against the tensor roofline (algorithmic gate-GEMM FLOPs / step time)
         step_fl = 3.0 * FWD_FLOP_PER_FRAME * B * T
         roof["step_blended"] = {"kernel": "whole training step (algorithmic gate-GEMM FLOPs / step time)",
@@ -317,7 +353,8 @@ def main():
                        "d2h_bytes_per_step": 4, "loss": last.get("loss")},
                "gpu_launches": int(launches),
                "clocks": clocks,
-               "roofline": roof.get("blstm_gate_gemm"),
+               # dominant kernel by time share (profiles/README.md: recurrence 72 % of the step)
+               "roofline": roof.get("blstm_recurrence_bwd") or roof.get("blstm_gate_gemm"),
                "rooflines": roof,
                "cpu_baseline": cpu}
         print(json.dumps(out))

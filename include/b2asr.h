@@ -190,6 +190,11 @@ int b2_blstm_layer_backward(const b2_lstm_desc* d, const float* x, const void* x
                             void* workspace, size_t workspace_bytes,
                             b2_stream_t stream);
 
+/* Measurement aid: CUDA-event timers around the persistent recurrence kernels of the most
+ * recent bf16 layer forward / backward (caller synchronises before reading). */
+void b2_blstm_profile_enable(int on);
+int b2_blstm_profile_last_ms(float* fwd_ms, float* bwd_ms);
+
 /* In the bf16 path the weight-gradient GEMMs of a layer run on an internal low-priority
  * side stream (they overlap the next layer's BPTT recurrence).  Call this once after the
  * last b2_blstm_layer_backward of a step: it makes `stream` wait for them (no host sync). */

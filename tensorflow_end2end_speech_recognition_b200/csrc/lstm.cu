@@ -296,6 +296,11 @@ extern "C" size_t b2_blstm_workspace_bytes(const b2_lstm_desc* d) {
   return work_layout(d, nullptr, nullptr);
 }
 
+extern "C" void b2_blstm_profile_enable(int on) { tc_profile_enable(on); }
+extern "C" int b2_blstm_profile_last_ms(float* fwd_ms, float* bwd_ms) {
+  return tc_profile_last_ms(fwd_ms, bwd_ms);
+}
+
 extern "C" int b2_blstm_backward_join(b2_stream_t stream_) {
   return tc_backward_join((cudaStream_t)stream_);
 }

@@ -68,6 +68,8 @@ int tc_layer_backward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16
                       cudaStream_t stream);
 
 int tc_backward_join(cudaStream_t stream);
+void tc_profile_enable(int on);
+int tc_profile_last_ms(float* fwd_ms, float* bwd_ms);
 
 inline int env_int(const char* name, int dflt) {
   const char* v = getenv(name);

@@ -187,6 +187,23 @@ tc_small_grads_kernel(const __nv_bfloat16* __restrict__ dG, const float* __restr
   }
 }
 
+// ------------------------------------------------------------------ kernel timers
+// Optional CUDA-event timers around the recurrence launches (bench.py's live roofline).
+static bool g_prof_on = false;
+static cudaEvent_t g_prof_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // fwd0 fwd1 bwd0 bwd1
+static void prof_record(int idx, cudaStream_t stream) {
+  if (!g_prof_on) return;
+  if (!g_prof_ev[0]) for (int i = 0; i < 4; ++i) cudaEventCreate(&g_prof_ev[i]);
+  cudaEventRecord(g_prof_ev[idx], stream);
+}
+void tc_profile_enable(int on) { g_prof_on = on != 0; }
+int tc_profile_last_ms(float* fwd_ms, float* bwd_ms) {
+  if (!g_prof_ev[0]) return B2_ERR_INVALID;
+  if (fwd_ms && cudaEventElapsedTime(fwd_ms, g_prof_ev[0], g_prof_ev[1]) != cudaSuccess) *fwd_ms = -1.f;
+  if (bwd_ms && cudaEventElapsedTime(bwd_ms, g_prof_ev[2], g_prof_ev[3]) != cudaSuccess) *bwd_ms = -1.f;
+  return B2_OK;
+}
+
 // ------------------------------------------------------------------ side stream
 // Weight-gradient GEMMs are off the BPTT critical path: they run on a low-priority side
 // stream, capped to the SMs the recurrence clusters leave free, while the next layer's
@@ -296,7 +313,10 @@ int tc_layer_forward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16*
             hb[0] / T, hb[1] / T, hb[2] / T, hb[3] / T, hb[4] / T, hb[5] / T, hb[6] / T, hb[7] / T);
     return rc;
   }
-  return rec_tc_forward(ra, w.G, env_int("B2_REC_NCHAIN", 0), stream);
+  prof_record(0, stream);
+  rc = rec_tc_forward(ra, w.G, env_int("B2_REC_NCHAIN", 0), stream);
+  prof_record(1, stream);
+  return rc;
 }
 
 int tc_layer_backward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16* x_lp,
@@ -353,7 +373,9 @@ int tc_layer_backward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16
             "bar1=%lld wait_mma=%lld ld+convert=%lld bar2+send=%lld\n",
             hb[0] / T, hb[1] / T, hb[2] / T, hb[3] / T, hb[4] / T, hb[5] / T, hb[6] / T);
   } else {
+    prof_record(2, stream);
     rc = rec_tc_backward(ba, dy, nchain, stream);
+    prof_record(3, stream);
   }
   if (rc) return rc;
   // 2. critical path: dX[TB, D] = dG[TB, 8H] . Wx_packed^T  (sums both directions)
