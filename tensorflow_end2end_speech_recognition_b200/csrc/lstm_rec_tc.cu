@@ -34,17 +34,7 @@ using namespace sm100;
 
 constexpr int RGS = 3;        // TMA ring stages
 constexpr int RPITCH = 20;    // transpose scratch pitch (floats)
-#ifndef B2_VARIANT
-#define B2_VARIANT 0
-#endif
-// experiment switch (A/B builds): 1 = cluster-scope acquire on the gate warps' accumulator waits
-#if B2_VARIANT == 1
-#define ACC_WAIT mbar_wait_cluster
-#else
-#define ACC_WAIT mbar_wait
-#endif
 constexpr int NISSW = 4;      // MMA issuer warps
-constexpr unsigned kBackoffNs = 20;   // poll back-off of the gate-math warps
 constexpr int ACC_STRIDE = 32; // TMEM columns between accumulators (16 used)
 
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
@@ -104,7 +94,6 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
   const int dir = cluster_id & 1;
   const int gbase = (cluster_id >> 1) * NCHAIN;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t hall = (uint32_t)CS * 1024u;  // bytes of one h buffer (16 batch x H bf16)
 
   uint64_t* bars = (uint64_t*)(smem + L::kBarOff);
   uint64_t* hfull = bars;                      // [NCHAIN][2][16]: one per (buffer, source CTA slice)
@@ -332,7 +321,7 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
         for (int j = 0; j < 4; ++j) G4[j] = *(const float4*)(Gs + (gq * 4 + j) * 128 + ul * 4);   // [b][u][gate]
         if (t >= 2) mbar_wait(&stfree[c * 2 + p], ((t >> 1) - 1) & 1);
         const long long e1 = clock64();
-        ACC_WAIT(&accfull[c], t & 1);
+        mbar_wait(&accfull[c], t & 1);
         tc_fence_after();
         const long long e2 = clock64();
         float v[16];
@@ -761,7 +750,7 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
         if (s + 1 >= T) break;
         // ---- C) partial dh of this step -> bf16 slices for the peers
         const long long b4 = clock64();
-        ACC_WAIT(&accfull[c], s & 1);
+        mbar_wait(&accfull[c], s & 1);
         tc_fence_after();
         const long long b5 = clock64();
         uint8_t* sst = smem + L::kSendOff + (c * 2 + (p ^ 1)) * 16384;
