@@ -52,6 +52,11 @@ __device__ __forceinline__ float lse3(float a, float b, float c) {
   if (m == -INFINITY) return -INFINITY;
   return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
 }
+// branch-free form (-inf safe): lets the compiler interleave many independent chains
+__device__ __forceinline__ float lse3_nb(float a, float b, float c) {
+  const float m = fmaxf(fmaxf(a, fmaxf(b, c)), -1e30f);
+  return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
+}
 __device__ __forceinline__ float lse2(float a, float b) {
   float m = fmaxf(a, b);
   if (m == -INFINITY) return -INFINITY;

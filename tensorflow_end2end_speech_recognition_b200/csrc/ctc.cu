@@ -14,6 +14,7 @@
 //
 // Algorithmic HBM bytes: 8*T*B*C (read logits, write grad) + 16*T*B*S spill.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace b2 {
 
@@ -123,19 +124,24 @@ ctc_alpha_beta_kernel(const float* __restrict__ logits, const float* __restrict_
   __shared__ float s_shift;
   double offset_sum = 0.0;           // meaningful in thread 0 only
 
-  constexpr int PF = 4;              // prefetch distance (steps) for the emission gather
+  // prefetch ring for the emission gather: RAW loads only -- subtracting lse at refill time would
+  // make the thread wait for the loads right there (45 % of the kernel in the first profile)
+  constexpr int PF = 4;
   float xq[PF][SPT];
+  float lq[PF];
   const int nsteps = Tb - 1;
 #pragma unroll
   for (int j = 0; j < PF; ++j) {
     const int i = j;
     const int t = t0 + dt * (i + 1);
 #pragma unroll
+    lq[j] = 0.f;
+    if (i < nsteps) lq[j] = __ldg(&lse[(int64_t)t * B + b]);
     for (int k = 0; k < SPT; ++k) {
       xq[j][k] = 0.f;
       if (i < nsteps && valid[k]) {
         const int64_t row = (int64_t)t * B + b;
-        xq[j][k] = __ldg(&logits[row * C + cls[k]]) - __ldg(&lse[row]);
+        xq[j][k] = __ldg(&logits[row * C + cls[k]]);
       }
     }
   }
@@ -154,7 +160,7 @@ ctc_alpha_beta_kernel(const float* __restrict__ logits, const float* __restrict_
             const float a0 = prev[s + 2];
             const float a1 = is_beta ? prev[s + 3] : prev[s + 1];
             const float a2 = skip[k] ? (is_beta ? prev[s + 4] : prev[s]) : -INFINITY;
-            const float v = lse3(a0, a1, a2) + xq[j][k];
+            const float v = lse3_nb(a0, a1, a2) + (xq[j][k] - lq[j]);
             cur[s + 2] = v;
             out[(int64_t)t * S_pad + s] = v;
           }
@@ -164,10 +170,10 @@ ctc_alpha_beta_kernel(const float* __restrict__ logits, const float* __restrict_
         if (ip < nsteps) {
           const int tp = t0 + dt * (ip + 1);
           const int64_t row = (int64_t)tp * B + b;
-          const float l = __ldg(&lse[row]);
+          lq[j] = __ldg(&lse[row]);
 #pragma unroll
           for (int k = 0; k < SPT; ++k)
-            if (valid[k]) xq[j][k] = __ldg(&logits[row * C + cls[k]]) - l;
+            if (valid[k]) xq[j][k] = __ldg(&logits[row * C + cls[k]]);
         }
         __syncthreads();
         float* tmp = prev; prev = cur; cur = tmp;
@@ -274,19 +280,20 @@ ctc_alpha_beta_warp_kernel(const float* __restrict__ logits, const float* __rest
     }
   }
   const int nsteps = Tb - 1;
-  float x0[SPT], x1[SPT];          // emissions of the next two steps (prefetch distance 2)
-  auto fetch = [&](int i, float (&x)[SPT]) {
+  float x0[SPT], x1[SPT];          // raw emissions of the next two steps (prefetch distance 2)
+  float l0 = 0.f, l1 = 0.f;
+  auto fetch = [&](int i, float (&x)[SPT], float& l) {
     if (i < nsteps) {
       const int64_t row = (int64_t)(t0 + dt * (i + 1)) * B + b;
-      const float l = __ldg(&lse[row]);
+      l = __ldg(&lse[row]);
 #pragma unroll
-      for (int k = 0; k < SPT; ++k) x[k] = valid[k] ? __ldg(&logits[row * C + cls[k]]) - l : 0.f;
+      for (int k = 0; k < SPT; ++k) x[k] = valid[k] ? __ldg(&logits[row * C + cls[k]]) : 0.f;
     }
   };
-  fetch(0, x0);
-  fetch(1, x1);
+  fetch(0, x0, l0);
+  fetch(1, x1, l1);
   double offset_sum = 0.0;
-  auto step = [&](int i, float (&x)[SPT]) {
+  auto step = [&](int i, float (&x)[SPT], float l) {
     const int t = t0 + dt * (i + 1);
     // neighbours across the lane boundary
     float n1, n2;
@@ -316,7 +323,7 @@ ctc_alpha_beta_warp_kernel(const float* __restrict__ logits, const float* __rest
         p2 = (k + 2 < SPT) ? a[k + 2 < SPT ? k + 2 : 0] : (k + 1 < SPT ? n1 : n2);
         if (SPT >= 2 && k == SPT - 1) { p1 = n1; p2 = n2; }
       }
-      const float v = lse3(a[k], p1, skip[k] ? p2 : -INFINITY) + x[k];
+      const float v = lse3_nb(a[k], p1, skip[k] ? p2 : -INFINITY) + (x[k] - l);
       nw[k] = valid[k] ? v : -INFINITY;
     }
 #pragma unroll
@@ -337,11 +344,11 @@ ctc_alpha_beta_warp_kernel(const float* __restrict__ logits, const float* __rest
     }
   };
   for (int i = 0; i < nsteps; i += 2) {
-    step(i, x0);
-    fetch(i + 2, x0);
+    step(i, x0, l0);
+    fetch(i + 2, x0, l0);
     if (i + 1 < nsteps) {
-      step(i + 1, x1);
-      fetch(i + 3, x1);
+      step(i + 1, x1, l1);
+      fetch(i + 3, x1, l1);
     }
   }
   if (!is_beta) {
@@ -488,7 +495,8 @@ extern "C" int b2_ctc_loss_grad(const float* logits, const int32_t* labels_flat,
 
   const int S_max = 2 * max_label_len + 1;
   int grad_spt = 0;
-  if (S_max <= 512) {
+  static const int use_warp = getenv("B2_CTC_WARP") ? atoi(getenv("B2_CTC_WARP")) : 0;
+  if (S_max <= 512 && use_warp) {
     // register-resident warp kernel: S_pad = 32*SPT <= workspace S_pad (both are multiples of 32)
     int spt = 1;
     while (32 * spt < S_max) spt *= 2;
