@@ -226,6 +226,40 @@ int b2_attention_step_forward(int mode, const float* enc, const float* keys,
                               float* context, b2_stream_t stream);
 
 /* ------------------------------------------------------------------------ *
+ * Attention decoder step, forward (greedy inference path)
+ *   reference: models/attention/decoders/attention_decoder.py:256-295 (step),
+ *   :170-211 (_compute_output), attention_seq2seq.py:352-363 (LSTMBlockCell),
+ *   :490-494 (GreedyEmbeddingHelper)
+ * ------------------------------------------------------------------------ */
+/* gate math of one LSTMBlockCell step on z[B,4H] = [x,h].W (gate blocks i,g,f,o); bias and
+ * peepholes may be NULL; cell_clip <= 0: none */
+int b2_lstm_cell_pointwise(const float* z, const float* bias, const float* w_i_diag,
+                           const float* w_f_diag, const float* w_o_diag,
+                           const float* c_prev, int B, int H, float forget_bias,
+                           float cell_clip, float* c_out, float* h_out,
+                           b2_stream_t stream);
+int b2_tanh_inplace(float* x, int64_t n, b2_stream_t stream);
+/* Tail of one dynamic_decode iteration (dynamic_decoder.py:148-196 with impute_finished, the
+ * input-feeding next_inputs of attention_decoder.py:221-238 and the helper's finished rule):
+ * writes the step's outputs into slot t of the batch-major [B,L,*] output arrays (zeros for
+ * finished rows), copies the state through for finished rows, builds the next cell input
+ * xh[B, emb+E+Hd] = [embedding(next id) ; ctx ; h_state] and updates finished[B] in place.
+ * labels == NULL: greedy helper (next id = ids[b], finished when it equals eos);
+ * labels [B,labels_ld] + dec_len[B]: training helper on labels[:, :-1] (finished when
+ * t + 1 >= dec_len[b]).  max_iter > 0: everything is finished once t + 1 >= max_iter. */
+int b2_decoder_step_emit(int B, int C, int Hd, int E, int T, int emb_dim, int t, int L,
+                         const float* logits, const int32_t* ids, const float* av,
+                         const float* alpha, const float* ctx, const float* c_new,
+                         const float* h_new, float* c_state, float* h_state,
+                         int32_t* finished, const float* embedding,
+                         const int32_t* labels, int labels_ld, const int32_t* dec_len,
+                         int eos, int max_iter, float* xh, float* out_logits,
+                         int32_t* out_ids, float* out_av, float* out_alpha,
+                         float* out_ctx, b2_stream_t stream);
+/* out[r] = argmax_c x[r, c], first index on ties */
+int b2_argmax_rows(const float* x, int64_t rows, int C, int32_t* out, b2_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
  * Small data-movement helpers of the step
  * ------------------------------------------------------------------------ */
 /* [B,T,D] -> [T,B,D]  (tf.transpose at blstm.py:279) */

@@ -59,6 +59,10 @@ PROTOTYPES = {
                                      C.POINTER(LstmGrads), _p, _sz, _p]),
     "b2_attention_step_forward": (_i, [_i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _f,
                                        _i, _p, _p, _p]),
+    "b2_lstm_cell_pointwise": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _f, _f, _p, _p, _p]),
+    "b2_tanh_inplace": (_i, [_p, _i64, _p]),
+    "b2_decoder_step_emit": (_i, [_i] * 8 + [_p] * 12 + [_i, _p, _i, _i] + [_p] * 6 + [_p]),
+    "b2_argmax_rows": (_i, [_p, _i64, _i, _p, _p]),
     "b2_transpose_01": (_i, [_p, _p, _i, _i, _i, _p]),
     "b2_colsum": (_i, [_p, _i64, _i, _i, _p, _i, _p]),
     "b2_clip_by_norm_multi": (_i, [_p, _p, _i, _f, _f, _p, _p]),

@@ -135,6 +135,40 @@ def gemm(A, B, transa=False, transb=False, bias=None, precision=PREC_FP32, out=N
     return out
 
 
+def lstm_cell_pointwise(z, bias, peep, c_prev, forget_bias=1.0, cell_clip=None):
+    """z [B,4H] pre-activations -> (c [B,H], h [B,H]); peep = (w_i, w_f, w_o) or None."""
+    lib = _lib.load()
+    _require_cuda(z, c_prev)
+    B, H4 = z.shape
+    H = H4 // 4
+    c = torch.empty((B, H), dtype=torch.float32, device=z.device)
+    h = torch.empty_like(c)
+    wi, wf, wo = peep if peep is not None else (None, None, None)
+    rc = lib.b2_lstm_cell_pointwise(_ptr(z.contiguous()), _ptr(bias), _ptr(wi), _ptr(wf), _ptr(wo),
+                                    _ptr(c_prev.contiguous()), B, H, float(forget_bias),
+                                    float(cell_clip) if cell_clip else 0.0, _ptr(c), _ptr(h), _stream())
+    _lib.check(rc, "b2_lstm_cell_pointwise")
+    return c, h
+
+
+def tanh_(x):
+    lib = _lib.load()
+    _require_cuda(x)
+    assert x.is_contiguous()
+    _lib.check(lib.b2_tanh_inplace(_ptr(x), x.numel(), _stream()), "b2_tanh_inplace")
+    return x
+
+
+def argmax_rows(x):
+    lib = _lib.load()
+    _require_cuda(x)
+    x = x.contiguous()
+    rows, Cc = x.shape
+    out = torch.empty(rows, dtype=torch.int32, device=x.device)
+    _lib.check(lib.b2_argmax_rows(_ptr(x), rows, Cc, _ptr(out), _stream()), "b2_argmax_rows")
+    return out
+
+
 def transpose_01(x):
     lib = _lib.load()
     _require_cuda(x)
