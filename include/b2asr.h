@@ -190,6 +190,17 @@ int b2_blstm_layer_backward(const b2_lstm_desc* d, const float* x, const void* x
                             void* workspace, size_t workspace_bytes,
                             b2_stream_t stream);
 
+/* Same, with the gradient of the layer's final state d_final_state [4,B,H] =
+ * d(c_fw, h_fw, c_bw, h_bw) (NULL: none) -- the path by which the attention model's bridge
+ * (models/attention/bridge.py:128-151) back-propagates into the encoder. */
+int b2_blstm_layer_backward_ex(const b2_lstm_desc* d, const float* x, const void* x_lp,
+                               const int32_t* seq_len, const b2_lstm_params* fw,
+                               const b2_lstm_params* bw, const float* dy,
+                               const float* d_final_state, const void* reserve, float* dx,
+                               const b2_lstm_grads* g_fw, const b2_lstm_grads* g_bw,
+                               void* workspace, size_t workspace_bytes,
+                               b2_stream_t stream);
+
 /* Measurement aid: CUDA-event timers around the persistent recurrence kernels of the most
  * recent bf16 layer forward / backward (caller synchronises before reading). */
 void b2_blstm_profile_enable(int on);
@@ -215,6 +226,8 @@ int b2_blstm_backward_join(b2_stream_t stream);
  * enc [B,T,E], keys [B,T,A], q [B,A], prev_alpha [B,T], enc_len [B];
  * energies of t >= enc_len are float32.min, then *sharpening_factor, then
  * softmax (or sigmoid / sum when sigmoid_smoothing).  alpha [B,T], context [B,E].
+ * energy_out (may be NULL): the sharpened energies [B,T] of the valid frames, kept for
+ * the backward pass of the sigmoid-smoothing form.
  * ------------------------------------------------------------------------ */
 int b2_attention_step_forward(int mode, const float* enc, const float* keys,
                               const float* q, const float* prev_alpha,
@@ -223,7 +236,56 @@ int b2_attention_step_forward(int mode, const float* enc, const float* keys,
                               const float* b_filter, const float* v_a, int B,
                               int T, int E, int A, float sharpening_factor,
                               int sigmoid_smoothing, float* alpha,
-                              float* context, b2_stream_t stream);
+                              float* context, float* energy_out,
+                              b2_stream_t stream);
+
+/* Backward of one attention step given d(context) [B,E] of that decoder step
+ * (attention_layer.py:45-113 differentiated).  Writes dq [B,A] (adds to it when
+ * dq_accumulate != 0); accumulates (+=) into
+ * d_keys [B,T,A] (NULL: no key term), dv [A] (NULL for multiplicative scores) and
+ * db_filter [A] (NULL: no location term).  The location term is the constant b_filter
+ * (the reference's decoder always feeds zero previous weights), so conv filter and W_filter
+ * receive no gradient.  d(enc) through the context, alpha_t (x) dctx_t, is NOT added here:
+ * it is a rank-(number of steps) update per utterance done by one b2_gemm after the loop.
+ * alpha/energy: the forward outputs of this step.  workspace from
+ * b2_attention_step_backward_workspace_bytes(B, T). */
+size_t b2_attention_step_backward_workspace_bytes(int B, int T);
+int b2_attention_step_backward(int mode, const float* enc, const float* keys, const float* q,
+                               const float* alpha, const float* energy,
+                               const int32_t* enc_len, const float* b_filter,
+                               const float* v_a, int B, int T, int E, int A,
+                               float sharpening_factor, int sigmoid_smoothing,
+                               const float* dctx, float* d_keys, float* dq,
+                               int dq_accumulate, float* dv, float* db_filter, void* workspace, size_t workspace_bytes,
+                               b2_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * Attention decoder, training side
+ *   reference: attention_seq2seq.py:579-664 (compute_loss), :413-459 (_decode_train)
+ * ------------------------------------------------------------------------ */
+/* tf.contrib.seq2seq.sequence_loss(average_across_timesteps=True, average_across_batch=True)
+ * with weights = sequence_mask(lengths, L) on logits/temperature [B,L,C] and targets
+ * [B, >=L] (row stride targets_ld):  rowloss[b*L+t] = w*xent (the caller divides their sum by
+ * sum(w) + 1e-12);  dlogits (may be NULL) = grad_scale * d(loss)/d(logits). */
+int b2_sequence_loss(const float* logits, const int32_t* targets, int targets_ld,
+                     const int32_t* lengths, int B, int L, int C, float temperature,
+                     float grad_scale, float* rowloss, float* dlogits,
+                     b2_stream_t stream);
+int b2_tanh_backward(const float* dy, const float* y, float* dx, int64_t n, b2_stream_t stream);
+/* backward of b2_lstm_cell_pointwise: dz [B,4H] (gate blocks i,g,f,o), dc_prev [B,H];
+ * dc_in may be NULL (no gradient from the next step) */
+int b2_lstm_cell_pointwise_backward(const float* z, const float* bias, const float* w_i_diag,
+                                    const float* w_f_diag, const float* w_o_diag,
+                                    const float* c_prev, const float* dh, const float* dc_in,
+                                    int B, int H, float forget_bias, float cell_clip,
+                                    float* dz, float* dc_prev, b2_stream_t stream);
+/* peephole gradients over all decoder steps: dz [steps*B,4H]; c_all [(steps+1)*B,H] where
+ * block s is the cell state before step s (block 0 = initial state).  Accumulates. */
+int b2_decoder_peephole_grad(const float* dz, const float* c_all, int steps, int B, int H,
+                             float* dw_i, float* dw_f, float* dw_o, b2_stream_t stream);
+/* dW[ids[r], :D] += dx[r, :D] for r < rows (dx row stride ldx); ids outside [0,V) skipped */
+int b2_embedding_grad(const float* dx, int ldx, const int32_t* ids, int64_t rows, int D, int V,
+                      float* dW, b2_stream_t stream);
 
 /* ------------------------------------------------------------------------ *
  * Attention decoder step, forward (greedy inference path)

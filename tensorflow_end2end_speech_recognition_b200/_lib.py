@@ -57,8 +57,19 @@ PROTOTYPES = {
     "b2_blstm_layer_backward": (_i, [C.POINTER(LstmDesc), _p, _p, _p, C.POINTER(LstmParams),
                                      C.POINTER(LstmParams), _p, _p, _p, C.POINTER(LstmGrads),
                                      C.POINTER(LstmGrads), _p, _sz, _p]),
+    "b2_blstm_layer_backward_ex": (_i, [C.POINTER(LstmDesc), _p, _p, _p, C.POINTER(LstmParams),
+                                        C.POINTER(LstmParams), _p, _p, _p, _p, C.POINTER(LstmGrads),
+                                        C.POINTER(LstmGrads), _p, _sz, _p]),
     "b2_attention_step_forward": (_i, [_i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _f,
-                                       _i, _p, _p, _p]),
+                                       _i, _p, _p, _p, _p]),
+    "b2_attention_step_backward_workspace_bytes": (_sz, [_i, _i]),
+    "b2_attention_step_backward": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i,
+                                        _p, _p, _p, _i, _p, _p, _p, _sz, _p]),
+    "b2_sequence_loss": (_i, [_p, _p, _i, _p, _i, _i, _i, _f, _f, _p, _p, _p]),
+    "b2_tanh_backward": (_i, [_p, _p, _p, _i64, _p]),
+    "b2_lstm_cell_pointwise_backward": (_i, [_p] * 8 + [_i, _i, _f, _f, _p, _p, _p]),
+    "b2_decoder_peephole_grad": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),
+    "b2_embedding_grad": (_i, [_p, _i, _p, _i64, _i, _i, _p, _p]),
     "b2_lstm_cell_pointwise": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _f, _f, _p, _p, _p]),
     "b2_tanh_inplace": (_i, [_p, _i64, _p]),
     "b2_decoder_step_emit": (_i, [_i] * 8 + [_p] * 12 + [_i, _p, _i, _i] + [_p] * 6 + [_p]),

@@ -28,7 +28,7 @@ struct AttnArgs {
   const float* filt; const float* w_f; const float* b_f; const float* v_a;
   int B, T, E, A, Kw;
   float sharpening; int sigmoid_smoothing;
-  float* alpha; float* context;
+  float* alpha; float* context; float* energy;
 };
 
 constexpr int kAttnThreads = 512;
@@ -98,7 +98,10 @@ attention_step_kernel(const AttnArgs a) {
     } else {
       e = -FLT_MAX;                                   // tf.float32.min (attention_layer.py:84-85)
     }
-    if (lane == 0) s_e[t] = e * a.sharpening;
+    if (lane == 0) {
+      s_e[t] = e * a.sharpening;
+      if (a.energy) a.energy[(size_t)b * T + t] = e * a.sharpening;
+    }
   }
   __syncthreads();
   // normalise over T
@@ -176,6 +179,120 @@ attention_context_kernel(const float* __restrict__ enc, const float* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Backward of one attention step (training).  Given d(context) of this decoder step:
+//   K1  dalpha[b,t] = enc[b,t,:] . dctx[b,:]   and the row reductions sum_t alpha*dalpha
+//       (softmax / sigmoid-normalisation backward) and, for sigmoid smoothing, S = sum_t sig(e)
+//   K2  de[t] -> energy backward: d_keys += ..., dq, dv, db_filter
+// d(enc) through the context (alpha_t (x) dctx_t) is a rank-L update per utterance and is left
+// to one GEMM per utterance after the decoder loop; here only the per-step sequential part.
+// The location term is the constant b_filter (the reference feeds zero previous weights,
+// SURVEY A.7.1), so the filter and W_filter get zero gradient.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+attention_bwd_dalpha_kernel(const float* __restrict__ enc, const float* __restrict__ dctx,
+                            const float* __restrict__ alpha, const float* __restrict__ energy,
+                            const int* __restrict__ enc_len, int T, int E, int sigmoid_smoothing,
+                            float* __restrict__ dalpha, float* __restrict__ red) {
+  extern __shared__ float s_d[];                    // [E]
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int len = min(enc_len[b], T);
+  for (int i = threadIdx.x; i < E; i += 256) s_d[i] = dctx[(size_t)b * E + i];
+  __syncthreads();
+  float dot = 0.f, ssum = 0.f;
+  const int t0 = blockIdx.y * 64;
+  for (int t = t0 + warp; t < min(t0 + 64, T); t += 8) {
+    float acc = 0.f;
+    if (t < len) {
+      const float4* er = (const float4*)(enc + ((size_t)b * T + t) * E);
+      for (int i = lane; i < E / 4; i += 32) {
+        const float4 h = __ldg(er + i);
+        const float4 d = ((const float4*)s_d)[i];
+        acc += h.x * d.x + h.y * d.y + h.z * d.z + h.w * d.w;
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        dot += alpha[(size_t)b * T + t] * acc;
+        if (sigmoid_smoothing) ssum += 1.f / (1.f + __expf(-energy[(size_t)b * T + t]));
+      }
+    }
+    if (lane == 0) dalpha[(size_t)b * T + t] = acc;
+  }
+  if (lane == 0) {
+    if (dot != 0.f) atomicAdd(&red[b * 2], dot);
+    if (ssum != 0.f) atomicAdd(&red[b * 2 + 1], ssum);
+  }
+}
+
+struct AttnBwdArgs {
+  int mode;
+  const float* keys; const float* q; const float* alpha; const float* energy; const float* dalpha;
+  const float* red; const int* enc_len; const float* b_f; const float* v_a;
+  int T, A; float sharpening; int sigmoid_smoothing;
+  float* d_keys; float* dq; float* dv; float* db_f;
+};
+
+// grid (B, ceil(T/32)); 8 warps, warp w takes rows t0+w, t0+w+8, ...
+__global__ void __launch_bounds__(256) attention_bwd_energy_kernel(const AttnBwdArgs a) {
+  extern __shared__ float sm[];
+  const int A = a.A, T = a.T;
+  float* s_q = sm;                 // [A]
+  float* s_v = s_q + A;            // [A]
+  float* s_b = s_v + A;            // [A]
+  float* s_dq = s_b + A;           // [8][A]
+  float* s_dv = s_dq + 8 * A;      // [8][A]
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int len = min(a.enc_len[b], T);
+  for (int i = threadIdx.x; i < A; i += 256) {
+    s_q[i] = a.q ? a.q[(size_t)b * A + i] : 0.f;
+    s_v[i] = a.v_a ? a.v_a[i] : 1.f;
+    s_b[i] = a.b_f ? a.b_f[i] : 0.f;
+  }
+  for (int i = threadIdx.x; i < 16 * A; i += 256) s_dq[i] = 0.f;
+  __syncthreads();
+  const float dot = a.red[b * 2];
+  const float S = a.sigmoid_smoothing ? a.red[b * 2 + 1] : 1.f;
+  const int t0 = blockIdx.y * 32;
+  float* my_dq = s_dq + warp * A;
+  float* my_dv = s_dv + warp * A;
+  for (int t = t0 + warp; t < min(t0 + 32, len); t += 8) {
+    const size_t bt = (size_t)b * T + t;
+    float de;
+    if (a.sigmoid_smoothing) {
+      const float s = 1.f / (1.f + __expf(-a.energy[bt]));
+      de = (a.dalpha[bt] - dot) / S * s * (1.f - s) * a.sharpening;
+    } else {
+      de = a.alpha[bt] * (a.dalpha[bt] - dot) * a.sharpening;
+    }
+    const float* kr = a.keys ? a.keys + bt * A : nullptr;
+    float* dk = a.d_keys ? a.d_keys + bt * A : nullptr;
+    for (int i = lane; i < A; i += 32) {
+      const float kv = kr ? kr[i] : 0.f;
+      if (a.mode == 1) {
+        if (dk) dk[i] += de * s_q[i];
+        my_dq[i] += de * kv;
+      } else {
+        const float u = tanhf_(kv + s_q[i] + s_b[i]);
+        const float g = de * s_v[i] * (1.f - u * u);
+        if (dk) dk[i] += g;
+        my_dq[i] += g;
+        my_dv[i] += de * u;
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < A; i += 256) {
+    float sq = 0.f, sv = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { sq += s_dq[w * A + i]; sv += s_dv[w * A + i]; }
+    if (sq != 0.f) {
+      atomicAdd(&a.dq[(size_t)b * A + i], sq);
+      if (a.db_f) atomicAdd(&a.db_f[i], sq);
+    }
+    if (a.dv && sv != 0.f) atomicAdd(&a.dv[i], sv);
+  }
+}
+
 }  // namespace b2
 
 using namespace b2;
@@ -186,7 +303,8 @@ extern "C" int b2_attention_step_forward(int mode, const float* enc, const float
                                          const float* w_filter, const float* b_filter,
                                          const float* v_a, int B, int T, int E, int A,
                                          float sharpening_factor, int sigmoid_smoothing,
-                                         float* alpha, float* context, b2_stream_t stream_) {
+                                         float* alpha, float* context, float* energy_out,
+                                         b2_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B2_CHECK_ARG(enc && enc_len && alpha && context, "b2_attention_step_forward: null pointer");
   B2_CHECK_ARG(mode == 0 || mode == 1, "b2_attention_step_forward: mode %d", mode);
@@ -199,7 +317,7 @@ extern "C" int b2_attention_step_forward(int mode, const float* enc, const float
   a.filt = conv_filter; a.w_f = w_filter; a.b_f = b_filter; a.v_a = v_a;
   a.B = B; a.T = T; a.E = E; a.A = A; a.Kw = conv_filter ? filter_width : 0;
   a.sharpening = sharpening_factor; a.sigmoid_smoothing = sigmoid_smoothing;
-  a.alpha = alpha; a.context = context;
+  a.alpha = alpha; a.context = context; a.energy = energy_out;
   size_t smem = ((size_t)T + 3 * A + 10 * A) * 4;
   if (conv_filter) smem += ((size_t)T + filter_width + (size_t)T * 10 + (size_t)filter_width * 10) * 4;
   B2_CHECK_ARG(smem <= 200 * 1024, "b2_attention_step_forward: T=%d too long for shared memory", T);
@@ -208,6 +326,48 @@ extern "C" int b2_attention_step_forward(int mode, const float* enc, const float
   B2_LAUNCH_CHECK();
   dim3 cgrid(B, cdiv(E / 4, 64));
   attention_context_kernel<<<cgrid, 512, 0, stream>>>(enc, alpha, enc_len, T, E, context);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" size_t b2_attention_step_backward_workspace_bytes(int B, int T) {
+  return align_up((size_t)B * T * 4, 256) + align_up((size_t)B * 2 * 4, 256);
+}
+
+extern "C" int b2_attention_step_backward(int mode, const float* enc, const float* keys, const float* q,
+                                          const float* alpha, const float* energy,
+                                          const int32_t* enc_len, const float* b_filter,
+                                          const float* v_a, int B, int T, int E, int A,
+                                          float sharpening_factor, int sigmoid_smoothing,
+                                          const float* dctx, float* d_keys, float* dq,
+                                          int dq_accumulate, float* dv,
+                                          float* db_filter, void* workspace, size_t workspace_bytes,
+                                          b2_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B2_CHECK_ARG(enc && alpha && enc_len && dctx && dq && workspace, "b2_attention_step_backward: null pointer");
+  B2_CHECK_ARG(mode == 0 || mode == 1, "b2_attention_step_backward: mode %d", mode);
+  B2_CHECK_ARG(B > 0 && T > 0 && E > 0 && A > 0 && E % 4 == 0, "b2_attention_step_backward: bad shape");
+  B2_CHECK_ARG(!sigmoid_smoothing || energy, "b2_attention_step_backward: sigmoid smoothing needs the saved energies");
+  B2_CHECK_ARG(mode == 0 || keys, "b2_attention_step_backward: multiplicative mode needs keys");
+  const size_t need = b2_attention_step_backward_workspace_bytes(B, T);
+  if (workspace_bytes < need) { set_error("b2_attention_step_backward: workspace %zu < %zu", workspace_bytes, need); return B2_ERR_WORKSPACE; }
+  float* dalpha = (float*)workspace;
+  float* red = (float*)((char*)workspace + align_up((size_t)B * T * 4, 256));
+  B2_CUDA(cudaMemsetAsync(red, 0, (size_t)B * 2 * 4, stream));
+  if (!dq_accumulate) B2_CUDA(cudaMemsetAsync(dq, 0, (size_t)B * A * 4, stream));
+  dim3 g1(B, cdiv(T, 64));
+  attention_bwd_dalpha_kernel<<<g1, 256, (size_t)E * 4, stream>>>(enc, dctx, alpha, energy, enc_len, T, E,
+                                                                 sigmoid_smoothing, dalpha, red);
+  B2_LAUNCH_CHECK();
+  AttnBwdArgs a;
+  a.mode = mode; a.keys = keys; a.q = q; a.alpha = alpha; a.energy = energy; a.dalpha = dalpha; a.red = red;
+  a.enc_len = enc_len; a.b_f = b_filter; a.v_a = v_a; a.T = T; a.A = A; a.sharpening = sharpening_factor;
+  a.sigmoid_smoothing = sigmoid_smoothing; a.d_keys = d_keys; a.dq = dq; a.dv = dv; a.db_f = db_filter;
+  const size_t smem = (size_t)19 * A * 4;
+  B2_CHECK_ARG(smem <= 200 * 1024, "b2_attention_step_backward: A=%d too wide for shared memory", A);
+  B2_CUDA(cudaFuncSetAttribute(attention_bwd_energy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 g2(B, cdiv(T, 32));
+  attention_bwd_energy_kernel<<<g2, 256, smem, stream>>>(a);
   B2_LAUNCH_CHECK();
   return B2_OK;
 }

@@ -395,13 +395,24 @@ extern "C" int b2_blstm_layer_backward(const b2_lstm_desc* d, const float* x, co
                                        const void* reserve, float* dx, const b2_lstm_grads* g_fw,
                                        const b2_lstm_grads* g_bw, void* workspace,
                                        size_t workspace_bytes, b2_stream_t stream_) {
+  return b2_blstm_layer_backward_ex(d, x, x_lp, seq_len, fw, bw, dy, nullptr, reserve, dx, g_fw, g_bw,
+                                    workspace, workspace_bytes, stream_);
+}
+
+extern "C" int b2_blstm_layer_backward_ex(const b2_lstm_desc* d, const float* x, const void* x_lp,
+                                          const int32_t* seq_len, const b2_lstm_params* fw,
+                                          const b2_lstm_params* bw, const float* dy,
+                                          const float* d_final_state, const void* reserve,
+                                          float* dx, const b2_lstm_grads* g_fw,
+                                          const b2_lstm_grads* g_bw, void* workspace,
+                                          size_t workspace_bytes, b2_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   int rc = check_desc(d);
   if (rc) return rc;
   if (tc_layer_supported(d)) {
     B2_CHECK_ARG(x && seq_len && fw && bw && dy && reserve && g_fw && g_bw && workspace,
                  "blstm_backward: null pointer");
-    return tc_layer_backward(d, x, (const __nv_bfloat16*)x_lp, seq_len, fw, bw, dy, reserve, dx,
+    return tc_layer_backward(d, x, (const __nv_bfloat16*)x_lp, seq_len, fw, bw, dy, d_final_state, reserve, dx,
                              g_fw, g_bw, workspace, workspace_bytes, stream);
   }
   B2_CHECK_ARG(x && seq_len && fw && bw && dy && reserve && g_fw && g_bw && workspace,
@@ -427,7 +438,7 @@ extern "C" int b2_blstm_layer_backward(const b2_lstm_desc* d, const float* x, co
     a.wo[dir] = P[dir]->w_o_diag;
   }
   a.seq_len = seq_len; a.dy = dy; a.gates = r.gates; a.cs = r.cs; a.dG = w.G; a.dcstate = w.cstate;
-  a.dfinal = nullptr;
+  a.dfinal = d_final_state;
   dim3 grid(cdiv(H, RU), cdiv(B, RB), 2);
   for (int i = 0; i < T; ++i) {
     a.step = i;

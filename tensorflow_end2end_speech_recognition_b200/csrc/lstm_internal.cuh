@@ -63,7 +63,8 @@ int tc_layer_forward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16*
                      size_t workspace_bytes, cudaStream_t stream);
 int tc_layer_backward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16* x_lp,
                       const int32_t* seq_len, const b2_lstm_params* fw, const b2_lstm_params* bw,
-                      const float* dy, const void* reserve, float* dx, const b2_lstm_grads* g_fw,
+                      const float* dy, const float* d_final_state, const void* reserve, float* dx,
+                      const b2_lstm_grads* g_fw,
                       const b2_lstm_grads* g_bw, void* workspace, size_t workspace_bytes,
                       cudaStream_t stream);
 

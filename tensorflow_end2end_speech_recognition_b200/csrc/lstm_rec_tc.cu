@@ -647,6 +647,18 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
         len[j] = bidx[j] < B ? a.seq_len[bidx[j]] : 0;
         dcs[j] = 0.f;
       }
+      // gradient of the layer's final state (encoder -> decoder bridge): enters at the first
+      // active BPTT step of each utterance
+      // (dcs is only rewritten by active steps, so d(c_final) simply is its initial value)
+      float dfh[4] = {0.f, 0.f, 0.f, 0.f};
+      if (a.dfinal) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (bidx[j] < B) {
+            dcs[j] = a.dfinal[((size_t)(dir * 2 + 0) * B + bidx[j]) * H + u];
+            dfh[j] = a.dfinal[((size_t)(dir * 2 + 1) * B + bidx[j]) * H + u];
+          }
+      }
       float pwi = 0.f, pwf = 0.f, pwo = 0.f;
       if (a.use_peephole) { pwi = a.wi[dir][u]; pwf = a.wf[dir][u]; pwo = a.wo[dir][u]; }
       uint8_t* bop = smem + L::kBopOff + c * 4096;
@@ -709,8 +721,8 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
           const float dyv = dyq[j];
           const bool active = td < len[j];
           const bool nb_active = s > 0 && tn >= 0 && tn < T && tn < len[j];
-          const float dh = dyv + (nb_active ? dh_rec[j] : 0.f);
-          const float dc_in = nb_active ? dcs[j] : 0.f;
+          const float dh = dyv + (nb_active ? dh_rec[j] : dfh[j]);
+          const float dc_in = dcs[j];
           const float gi = g4[j].x, gg = g4[j].y, gf = g4[j].z, go = g4[j].w;
           const float Ec = __expf(fminf(-2.f * cc, 25.f));
           const float tc = (1.f - Ec) * fast_rcp(1.f + Ec);

@@ -321,7 +321,8 @@ int tc_layer_forward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16*
 
 int tc_layer_backward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16* x_lp,
                       const int32_t* seq_len, const b2_lstm_params* fw, const b2_lstm_params* bw,
-                      const float* dy, const void* reserve, float* dx, const b2_lstm_grads* g_fw,
+                      const float* dy, const float* d_final_state, const void* reserve, float* dx,
+                      const b2_lstm_grads* g_fw,
                       const b2_lstm_grads* g_bw, void* workspace, size_t workspace_bytes,
                       cudaStream_t stream) {
   TcWork w;
@@ -354,7 +355,7 @@ int tc_layer_backward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16
     ba.dwi[dir] = GR[dir]->w_i_diag; ba.dwf[dir] = GR[dir]->w_f_diag; ba.dwo[dir] = GR[dir]->w_o_diag;
   }
   ba.use_peephole = d->use_peephole; ba.cell_clip = d->cell_clip; ba.keep_prob = d->keep_prob;
-  ba.seed = d->dropout_seed; ba.gates = r.gates; ba.cs = r.cs; ba.dG = dG; ba.dfinal = nullptr;
+  ba.seed = d->dropout_seed; ba.gates = r.gates; ba.cs = r.cs; ba.dG = dG; ba.dfinal = d_final_state;
   B2_CUDA(cudaMemsetAsync(dbias, 0, (size_t)8 * H * 4, stream));
   ba.dbias = dbias;
   ba.dbg = nullptr;

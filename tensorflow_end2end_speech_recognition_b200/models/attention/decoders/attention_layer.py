@@ -95,8 +95,12 @@ class AttentionLayer(object):
         return self._keys
 
     # ------------------------------------------------------------------ step
-    def __call__(self, encoder_outputs, decoder_output, encoder_outputs_length, attention_weights):
+    def __call__(self, encoder_outputs, decoder_output, encoder_outputs_length, attention_weights,
+                 out=None):
+        """out: optional dict of preallocated cuda tensors {'alpha','context','energy','q'} the
+        step writes into (the training decoder keeps them for the backward pass)."""
         lib = _lib.load()
+        out = out or {}
         t = self.attention_type
         v = self.variables
         B, T, E = encoder_outputs.shape
@@ -105,16 +109,21 @@ class AttentionLayer(object):
         if t == "luong_dot" and E != decoder_output.shape[-1]:
             raise ValueError("encoder_num_units and decoder_num_units must be the same size.")
         if t in ("bahdanau_content", "location", "hybrid", "dot_product"):
-            q = ops.gemm(decoder_output, v["W_query/weights"])
+            q = ops.gemm(decoder_output, v["W_query/weights"], out=out.get("q"))
         elif t == "luong_concat":
-            q = ops.gemm(decoder_output, v["W_concat/weights"][E:])
+            q = ops.gemm(decoder_output, v["W_concat/weights"][E:], out=out.get("q"))
         else:
             q = decoder_output.contiguous()
         mode = 1 if t in ("dot_product", "luong_dot", "luong_general") else 0
         A = q.shape[-1]
         loc = t in ("hybrid", "location")
-        alpha = torch.empty((B, T), dtype=torch.float32, device=encoder_outputs.device)
-        ctx = torch.empty((B, E), dtype=torch.float32, device=encoder_outputs.device)
+        alpha = out.get("alpha")
+        if alpha is None:
+            alpha = torch.empty((B, T), dtype=torch.float32, device=encoder_outputs.device)
+        ctx = out.get("context")
+        if ctx is None:
+            ctx = torch.empty((B, E), dtype=torch.float32, device=encoder_outputs.device)
+        energy = out.get("energy")
         p = lambda x: C.c_void_p(x.data_ptr()) if x is not None else C.c_void_p(0)
         filt = v["filter"].reshape(-1, 10).contiguous() if loc else None
         rc = lib.b2_attention_step_forward(
@@ -124,6 +133,48 @@ class AttentionLayer(object):
             p(v["W_filter/weights"]) if loc else C.c_void_p(0),
             p(v["W_filter/biases"]) if loc else C.c_void_p(0),
             p(v.get("v_a")), B, T, E, A, float(self.sharpening_factor), int(bool(self.sigmoid_smoothing)),
-            p(alpha), p(ctx), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            p(alpha), p(ctx), p(energy), C.c_void_p(torch.cuda.current_stream().cuda_stream))
         _lib.check(rc, "b2_attention_step_forward")
         return alpha, ctx
+
+    # -------------------------------------------------------------- backward
+    def query_is_projected(self):
+        return self.attention_type in ("bahdanau_content", "location", "hybrid", "dot_product", "luong_concat")
+
+    def backward_step(self, encoder_outputs, q, alpha, energy, encoder_outputs_length, dctx, d_keys, dq,
+                      grads, dq_accumulate=False):
+        """Sequential part of the step's backward: dq [B,A] is written, d_keys / v_a / W_filter
+        bias gradients accumulate.  ``grads``: dict with the same keys as ``variables``."""
+        lib = _lib.load()
+        t, v = self.attention_type, self.variables
+        B, T, E = encoder_outputs.shape
+        mode = 1 if t in ("dot_product", "luong_dot", "luong_general") else 0
+        loc = t in ("hybrid", "location")
+        A = q.shape[-1]
+        nbytes = lib.b2_attention_step_backward_workspace_bytes(B, T)
+        ws = ops.workspace("attn_bwd", nbytes, encoder_outputs.device)
+        p = ops._ptr
+        rc = lib.b2_attention_step_backward(
+            mode, p(encoder_outputs), p(self._keys), p(q), p(alpha), p(energy), p(encoder_outputs_length),
+            p(v["W_filter/biases"]) if loc else p(None), p(v.get("v_a")), B, T, E, A,
+            float(self.sharpening_factor), int(bool(self.sigmoid_smoothing)), p(dctx), p(d_keys), p(dq),
+            int(dq_accumulate), p(grads.get("v_a")), p(grads["W_filter/biases"]) if loc else p(None), p(ws), nbytes, ops._stream())
+        _lib.check(rc, "b2_attention_step_backward")
+
+    def backward_keys(self, encoder_outputs, d_keys, d_enc, grads):
+        """After the loop: push the accumulated d_keys [B,T,A] through the hoisted key projection.
+        d_enc [B,T,E] accumulates."""
+        t, v = self.attention_type, self.variables
+        B, T, E = encoder_outputs.shape
+        if t in ("location", "luong_dot") or d_keys is None:
+            return                                      # no projection (luong_dot: d_keys aliases d_enc)
+        prec = ops.PREC_BF16 if self.precision == "bf16" else ops.PREC_FP32
+        enc2d, dk2d = encoder_outputs.reshape(B * T, E), d_keys.reshape(B * T, -1)
+        if t == "luong_concat":
+            w, gw = v["W_concat/weights"][:E], grads["W_concat/weights"][:E]
+        else:
+            w, gw = v["W_keys/weights"], grads["W_keys/weights"]
+        ops.gemm(enc2d, dk2d, True, False, None, prec, out=gw, beta=1.0)
+        if "W_keys/biases" in v and t != "luong_concat":
+            ops.colsum(dk2d, out=grads["W_keys/biases"], accumulate=True)
+        ops.gemm(dk2d, w, False, True, None, prec, out=d_enc.reshape(B * T, E), beta=1.0)

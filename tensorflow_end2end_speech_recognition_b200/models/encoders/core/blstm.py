@@ -107,9 +107,11 @@ class BLSTMEncoder(object):
         return outputs, final_state
 
     # ------------------------------------------------------------- backward
-    def backward(self, d_outputs, variables, grads, need_dx=False, on_layer_done=None):
+    def backward(self, d_outputs, variables, grads, need_dx=False, on_layer_done=None,
+                 d_final_state=None):
         """d_outputs [T,B,2H] (time-major).  Accumulates into ``grads`` (same keys as
-        ``variables``); calls ``on_layer_done(i_layer)`` when a layer's gradients are final."""
+        ``variables``); calls ``on_layer_done(i_layer)`` when a layer's gradients are final.
+        d_final_state [4,B,H]: gradient of the returned (fw(c,h), bw(c,h)) of the last layer."""
         saved, seq_len = self._saved
         dy = d_outputs
         for desc, x, reserve, i_layer, x_lp in reversed(saved):
@@ -118,7 +120,8 @@ class BLSTMEncoder(object):
             gf = self._layer_params(grads, i_layer, "fw")
             gb = self._layer_params(grads, i_layer, "bw")
             dy = ops.blstm_layer_backward(desc, x, seq_len, pf, pb, dy, reserve, gf, gb,
-                                          need_dx=(i_layer > 1 or need_dx), x_lp=x_lp)
+                                          need_dx=(i_layer > 1 or need_dx), x_lp=x_lp,
+                                          d_final_state=d_final_state if i_layer == self.num_layers else None)
             if on_layer_done is not None:
                 on_layer_done(i_layer)
         ops.blstm_backward_join()      # side-stream weight-gradient GEMMs -> gradients final

@@ -135,20 +135,76 @@ def gemm(A, B, transa=False, transb=False, bias=None, precision=PREC_FP32, out=N
     return out
 
 
-def lstm_cell_pointwise(z, bias, peep, c_prev, forget_bias=1.0, cell_clip=None):
+def lstm_cell_pointwise(z, bias, peep, c_prev, forget_bias=1.0, cell_clip=None, out_c=None, out_h=None):
     """z [B,4H] pre-activations -> (c [B,H], h [B,H]); peep = (w_i, w_f, w_o) or None."""
     lib = _lib.load()
     _require_cuda(z, c_prev)
     B, H4 = z.shape
     H = H4 // 4
-    c = torch.empty((B, H), dtype=torch.float32, device=z.device)
-    h = torch.empty_like(c)
+    c = out_c if out_c is not None else torch.empty((B, H), dtype=torch.float32, device=z.device)
+    h = out_h if out_h is not None else torch.empty((B, H), dtype=torch.float32, device=z.device)
     wi, wf, wo = peep if peep is not None else (None, None, None)
     rc = lib.b2_lstm_cell_pointwise(_ptr(z.contiguous()), _ptr(bias), _ptr(wi), _ptr(wf), _ptr(wo),
                                     _ptr(c_prev.contiguous()), B, H, float(forget_bias),
                                     float(cell_clip) if cell_clip else 0.0, _ptr(c), _ptr(h), _stream())
     _lib.check(rc, "b2_lstm_cell_pointwise")
     return c, h
+
+
+def lstm_cell_pointwise_backward(z, bias, peep, c_prev, dh, dc_in, forget_bias=1.0, cell_clip=None,
+                                 out_dz=None):
+    """-> (dz [B,4H], dc_prev [B,H])"""
+    lib = _lib.load()
+    _require_cuda(z, c_prev, dh)
+    B, H4 = z.shape
+    H = H4 // 4
+    dz = out_dz if out_dz is not None else torch.empty((B, H4), dtype=torch.float32, device=z.device)
+    dc_prev = torch.empty((B, H), dtype=torch.float32, device=z.device)
+    wi, wf, wo = peep if peep is not None else (None, None, None)
+    rc = lib.b2_lstm_cell_pointwise_backward(_ptr(z), _ptr(bias), _ptr(wi), _ptr(wf), _ptr(wo), _ptr(c_prev),
+                                             _ptr(dh), _ptr(dc_in), B, H, float(forget_bias),
+                                             float(cell_clip) if cell_clip else 0.0, _ptr(dz), _ptr(dc_prev),
+                                             _stream())
+    _lib.check(rc, "b2_lstm_cell_pointwise_backward")
+    return dz, dc_prev
+
+
+def sequence_loss(logits, targets, lengths, temperature=1.0, grad_scale=1.0, need_grad=True):
+    """logits [B,L,C] f32, targets [B,>=L] int32 view (row stride = its stride(0)), lengths [B]
+    -> (loss 0-d tensor, dlogits [B,L,C] or None)."""
+    lib = _lib.load()
+    _require_cuda(logits, targets, lengths)
+    B, L, Cc = logits.shape
+    assert logits.is_contiguous() and targets.stride(1) == 1 and targets.dtype == torch.int32
+    rowloss = torch.empty((B, L), dtype=torch.float32, device=logits.device)
+    dlogits = torch.empty_like(logits) if need_grad else None
+    rc = lib.b2_sequence_loss(_ptr(logits), _ptr(targets), targets.stride(0), _ptr(lengths), B, L, Cc,
+                              float(temperature), float(grad_scale), _ptr(rowloss), _ptr(dlogits), _stream())
+    _lib.check(rc, "b2_sequence_loss")
+    wsum = torch.clamp(lengths, 0, L).sum().to(torch.float32)
+    return rowloss.sum() / (wsum + 1e-12), dlogits
+
+
+def tanh_backward(dy, y, out=None):
+    lib = _lib.load()
+    _require_cuda(dy, y)
+    assert dy.is_contiguous() and y.is_contiguous()
+    dx = out if out is not None else torch.empty_like(dy)
+    _lib.check(lib.b2_tanh_backward(_ptr(dy), _ptr(y), _ptr(dx), dy.numel(), _stream()), "b2_tanh_backward")
+    return dx
+
+
+def decoder_peephole_grad(dz_all, c_all, steps, B, H, dwi, dwf, dwo):
+    lib = _lib.load()
+    rc = lib.b2_decoder_peephole_grad(_ptr(dz_all), _ptr(c_all), steps, B, H, _ptr(dwi), _ptr(dwf), _ptr(dwo),
+                                      _stream())
+    _lib.check(rc, "b2_decoder_peephole_grad")
+
+
+def embedding_grad(dx, ldx, ids, rows, D, dW):
+    lib = _lib.load()
+    rc = lib.b2_embedding_grad(_ptr(dx), ldx, _ptr(ids), rows, D, dW.shape[0], _ptr(dW), _stream())
+    _lib.check(rc, "b2_embedding_grad")
 
 
 def tanh_(x):
@@ -239,8 +295,10 @@ def reserve_y_lp(desc, reserve):
     return _lib.load().b2_blstm_reserve_y_lp(C.byref(desc), _ptr(reserve)) or 0
 
 
-def blstm_layer_backward(desc, x, seq_len, p_fw, p_bw, dy, reserve, g_fw, g_bw, need_dx=True, x_lp=0):
-    """Accumulates into the gradient dicts g_fw / g_bw; returns dx [T,B,D] or None."""
+def blstm_layer_backward(desc, x, seq_len, p_fw, p_bw, dy, reserve, g_fw, g_bw, need_dx=True, x_lp=0,
+                         d_final_state=None):
+    """Accumulates into the gradient dicts g_fw / g_bw; returns dx [T,B,D] or None.
+    d_final_state: [4,B,H] gradient of (c_fw, h_fw, c_bw, h_bw) or None."""
     lib = _lib.load()
     _require_cuda(x, dy)
     dev = x.device
@@ -249,10 +307,14 @@ def blstm_layer_backward(desc, x, seq_len, p_fw, p_bw, dy, reserve, g_fw, g_bw, 
     ws = workspace("lstm", nbytes, dev)
     fw, bw = _params_struct(p_fw), _params_struct(p_bw)
     gf, gb = _params_struct(g_fw), _params_struct(g_bw)
-    rc = lib.b2_blstm_layer_backward(C.byref(desc), _ptr(x.contiguous()), C.c_void_p(x_lp or 0),
-                                     _ptr(seq_len), C.byref(fw),
-                                     C.byref(bw), _ptr(dy.contiguous()), _ptr(reserve), _ptr(dx),
-                                     C.byref(gf), C.byref(gb), _ptr(ws), nbytes, _stream())
+    if d_final_state is not None:
+        _require_cuda(d_final_state)
+        assert d_final_state.is_contiguous() and tuple(d_final_state.shape) == (4, desc.B, desc.H)
+    rc = lib.b2_blstm_layer_backward_ex(C.byref(desc), _ptr(x.contiguous()), C.c_void_p(x_lp or 0),
+                                        _ptr(seq_len), C.byref(fw),
+                                        C.byref(bw), _ptr(dy.contiguous()), _ptr(d_final_state),
+                                        _ptr(reserve), _ptr(dx),
+                                        C.byref(gf), C.byref(gb), _ptr(ws), nbytes, _stream())
     _lib.check(rc, "b2_blstm_layer_backward")
     return dx
 

@@ -115,3 +115,76 @@ def test_clip_and_average():
     avg = oopt.average_gradients([[np.ones(3), None], [3 * np.ones(3), np.ones(2)]])
     np.testing.assert_allclose(avg[0], 2 * np.ones(3))
     np.testing.assert_allclose(avg[1], np.ones(2))
+
+
+def test_attention_torch_twin_matches_numpy_oracle():
+    """oracle/seq2seq.py (torch, autograd) restates oracle/attention.py and
+    oracle/attention_decoder.py; the two forms must agree."""
+    import torch
+    from oracle import attention as oatt, attention_decoder as odec, seq2seq as os2s
+    rng = np.random.RandomState(0)
+    B, T, E, Dq, A = 3, 9, 8, 6, 5
+    for t in oatt.ATTENTION_TYPE:
+        p = {"W_query/weights": rng.randn(Dq, A), "W_keys/weights": rng.randn(E, A if t != "luong_general" else Dq),
+             "W_keys/biases": rng.randn(A), "filter": rng.randn(5, 1, 10), "W_filter/weights": rng.randn(10, A),
+             "W_filter/biases": rng.randn(A), "v_a": rng.randn(A), "W_concat/weights": rng.randn(E + Dq, A)}
+        enc = rng.randn(B, T, E)
+        q = rng.randn(B, E if t == "luong_dot" else Dq)
+        lens = np.array([9, 4, 6])
+        pa = np.abs(rng.rand(B, T))
+        for sig in (False, True):
+            a, c = oatt.attention_step(t, enc, q, lens, pa, p, 1.5, sig)
+            pt = {k: torch.tensor(v) for k, v in p.items()}
+            a2, c2 = os2s.attention_step_t(t, torch.tensor(enc), torch.tensor(q), lens, torch.tensor(pa), pt, 1.5, sig)
+            np.testing.assert_allclose(a, a2.numpy(), atol=1e-12)
+            np.testing.assert_allclose(c, c2.numpy(), atol=1e-12)
+    # teacher-forced decoder loop, both forms
+    Hd, emb, C = 6, 4, 7
+    p = {"W_embedding": rng.randn(C, emb), "attentional_vector/weights": rng.randn(Hd + E, Hd) * .3,
+         "output_layer/weights": rng.randn(Hd, C), "output_layer/biases": rng.randn(C) * .1,
+         "cell": {"kernel": rng.randn(emb + E + Hd, 4 * Hd) * .3, "bias": rng.randn(4 * Hd) * .1,
+                  "w_i_diag": rng.randn(Hd) * .1, "w_f_diag": rng.randn(Hd) * .1, "w_o_diag": rng.randn(Hd) * .1},
+         "attention": {"W_keys/weights": rng.randn(E, Hd) * .3}}
+    enc = rng.randn(B, T, E)
+    lens = np.array([9, 3, 5])
+    labels = np.array([[5, 1, 2, 3, 6], [5, 0, 6, 6, 6], [5, 1, 1, 6, 6]])
+    lab_len = np.array([5, 3, 4])
+    st = (rng.randn(B, Hd) * .1, rng.randn(B, Hd) * .1)
+    r = odec.decode(p, "luong_general", enc, lens, st, labels=labels, labels_seq_len=lab_len)
+    tt = lambda x: {k: tt(v) for k, v in x.items()} if isinstance(x, dict) else torch.tensor(x)
+    r2 = os2s.decode_train_t(tt(p), "luong_general", torch.tensor(enc), lens, (torch.tensor(st[0]), torch.tensor(st[1])),
+                             labels, lab_len)
+    np.testing.assert_allclose(r["logits"], r2["logits"].numpy(), atol=1e-12)
+    assert np.array_equal(r["predicted_ids"], r2["predicted_ids"].numpy())
+    # sequence loss: hand-computed masked mean
+    logits = rng.randn(2, 3, 4)
+    tg = np.array([[1, 2, 0], [3, 0, 0]])
+    ln = np.array([3, 1])
+    lp = logits - np.log(np.exp(logits).sum(-1, keepdims=True))
+    want = -(lp[0, 0, 1] + lp[0, 1, 2] + lp[0, 2, 0] + lp[1, 0, 3]) / 4.0
+    assert abs(float(os2s.sequence_loss_t(torch.tensor(logits), tg, ln)) - want) < 1e-12
+
+
+def test_greedy_decoder_oracle_semantics():
+    """dynamic_decode rules: stop when every row emitted <EOS> (or at max length), finished rows
+    emit zeros and keep their state."""
+    from oracle import attention_decoder as odec
+    rng = np.random.RandomState(1)
+    B, T, E, Hd, emb, C = 3, 7, 8, 6, 4, 5
+    p = {"W_embedding": rng.randn(C, emb), "attentional_vector/weights": rng.randn(Hd + E, Hd) * .3,
+         "output_layer/weights": rng.randn(Hd, C), "output_layer/biases": np.zeros(C),
+         "cell": {"kernel": rng.randn(emb + E + Hd, 4 * Hd) * .3, "bias": np.zeros(4 * Hd)},
+         "attention": {"W_keys/weights": rng.randn(E, Hd) * .3}}
+    enc = rng.randn(B, T, E)
+    lens = np.array([7, 3, 5])
+    st = (np.zeros((B, Hd)), np.zeros((B, Hd)))
+    r = odec.decode(p, "luong_general", enc, lens, st, sos=3, eos=4, max_decode_length=6)
+    ids = r["predicted_ids"]
+    assert ids.shape[1] <= 6
+    for b in range(B):
+        hit = np.where(ids[b] == 4)[0]
+        if len(hit):
+            assert np.all(r["logits"][b, hit[0] + 1:] == 0) and np.all(ids[b, hit[0] + 1:] == 0)
+    p["output_layer/biases"] = np.array([0, 0, 0, 0, 50.0])
+    r = odec.decode(p, "luong_general", enc, lens, st, sos=3, eos=4, max_decode_length=6)
+    assert r["logits"].shape[1] == 1
