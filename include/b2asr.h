@@ -212,6 +212,45 @@ int b2_blstm_profile_last_ms(float* fwd_ms, float* bwd_ms);
 int b2_blstm_backward_join(b2_stream_t stream);
 
 /* ------------------------------------------------------------------------ *
+ * VGG front-end of the VGG-BLSTM encoder
+ *   reference: models/encoders/core/vgg_blstm.py:93-177 (VGGBLSTMEncoder.__call__ up to the
+ *   BLSTM), models/encoders/core/cnn_util.py:52-84 (conv_layer), :13-29 (max_pool)
+ * x [N=B*T, H=num_channels, W=splice*num_stack, 3] (the reference's reshape of [B,T,D]) ->
+ * conv3x3(3->64) ReLU, dropout, conv(64->64) ReLU, max_pool 2x2/2 SAME, dropout,
+ * conv(64->128) ReLU, dropout, conv(128->128) ReLU, max_pool, dropout, flatten (h,w,c),
+ * fully connected 256 + ReLU, dropout -> out [N,256].
+ * Filters are TF layout [3,3,C_in,C_out]; fc_w [b2_vgg_output_size(d), 256].
+ * ------------------------------------------------------------------------ */
+typedef struct {
+  int32_t N, H, W;            /* frames, num_channels, splice*num_stack      */
+  float keep_prob;            /* tf.nn.dropout keep probability; 1 = off      */
+  uint64_t dropout_seed;      /* counter-hash seed (sites use seed+1..seed+5) */
+  int32_t precision;          /* B2_PREC_FP32 (the only one built so far)     */
+} b2_vgg_desc;
+typedef struct {
+  const float* conv_w[4];     /* VGG1/conv1, VGG1/conv2, VGG2/conv1, VGG2/conv2 */
+  const float* conv_b[4];
+  const float* fc_w;          /* bridge/weights */
+  const float* fc_b;          /* bridge/biases  */
+} b2_vgg_params;
+typedef struct {
+  float* conv_w[4];
+  float* conv_b[4];
+  float* fc_w;
+  float* fc_b;
+} b2_vgg_grads;
+size_t b2_vgg_reserve_bytes(const b2_vgg_desc* d);
+size_t b2_vgg_workspace_bytes(const b2_vgg_desc* d);
+int b2_vgg_output_size(const b2_vgg_desc* d);   /* flattened width feeding the FC */
+int b2_vgg_frontend_forward(const b2_vgg_desc* d, const float* x, const b2_vgg_params* p,
+                            float* out, void* reserve, void* workspace,
+                            size_t workspace_bytes, b2_stream_t stream);
+/* gradients are ACCUMULATED into g; there is no input gradient (x is the feature matrix) */
+int b2_vgg_frontend_backward(const b2_vgg_desc* d, const b2_vgg_params* p, const float* d_out,
+                             const void* reserve, const b2_vgg_grads* g, void* workspace,
+                             size_t workspace_bytes, b2_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
  * Attention step (energy + masked softmax + context)   replaces
  *   AttentionLayer.__call__, models/attention/decoders/attention_layer.py:45-347
  * One decoder step over all T encoder states; the key projection is hoisted

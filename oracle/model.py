@@ -30,9 +30,14 @@ def layers_from_variables(variables, num_layers, use_peephole=True):
 
 
 def ctc_model_forward(variables, inputs_btd, seq_len, labels, num_layers, use_peephole=True,
-                      cell_clip=None, keep_prob=1.0, dropout_masks=None):
-    """variables: dict name -> torch tensor.  Returns (mean loss, logits [T,B,C], per-utt losses)."""
+                      cell_clip=None, keep_prob=1.0, dropout_masks=None, vgg=None):
+    """variables: dict name -> torch tensor.  Returns (mean loss, logits [T,B,C], per-utt losses).
+    vgg = (num_channels, width): run the VGG front-end (oracle/vgg.py) before the BLSTM stack
+    (encoder_type 'vgg_blstm', ctc.py:135-147)."""
     layers = layers_from_variables(variables, num_layers, use_peephole)
+    if vgg is not None:
+        from . import vgg as ovgg
+        inputs_btd = ovgg.vgg_frontend(inputs_btd, variables, vgg[0], vgg[1])
     enc, _ = olstm.blstm_forward(inputs_btd, seq_len, layers, keep_prob=keep_prob,
                                  dropout_masks=dropout_masks, cell_clip=cell_clip)
     T, B, E = enc.shape

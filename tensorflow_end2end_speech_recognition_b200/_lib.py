@@ -29,6 +29,19 @@ class LstmParams(C.Structure):
 
 LstmGrads = LstmParams  # same layout (non-const pointers)
 
+
+class VggDesc(C.Structure):
+    _fields_ = [("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("keep_prob", C.c_float),
+                ("dropout_seed", C.c_uint64), ("precision", C.c_int32)]
+
+
+class VggParams(C.Structure):
+    _fields_ = [("conv_w", C.c_void_p * 4), ("conv_b", C.c_void_p * 4), ("fc_w", C.c_void_p),
+                ("fc_b", C.c_void_p)]
+
+
+VggGrads = VggParams
+
 _p, _i, _f, _sz, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_int64
 
 # name -> (restype, argtypes); mirrors include/b2asr.h one to one
@@ -60,6 +73,12 @@ PROTOTYPES = {
     "b2_blstm_layer_backward_ex": (_i, [C.POINTER(LstmDesc), _p, _p, _p, C.POINTER(LstmParams),
                                         C.POINTER(LstmParams), _p, _p, _p, _p, C.POINTER(LstmGrads),
                                         C.POINTER(LstmGrads), _p, _sz, _p]),
+    "b2_vgg_reserve_bytes": (_sz, [C.POINTER(VggDesc)]),
+    "b2_vgg_workspace_bytes": (_sz, [C.POINTER(VggDesc)]),
+    "b2_vgg_output_size": (_i, [C.POINTER(VggDesc)]),
+    "b2_vgg_frontend_forward": (_i, [C.POINTER(VggDesc), _p, C.POINTER(VggParams), _p, _p, _p, _sz, _p]),
+    "b2_vgg_frontend_backward": (_i, [C.POINTER(VggDesc), C.POINTER(VggParams), _p, _p, C.POINTER(VggGrads),
+                                      _p, _sz, _p]),
     "b2_attention_step_forward": (_i, [_i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _f,
                                        _i, _p, _p, _p, _p]),
     "b2_attention_step_backward_workspace_bytes": (_sz, [_i, _i]),

@@ -13,7 +13,7 @@ template <bool TA, bool TB>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int lda,
                  const float* __restrict__ Bm, int ldb, float beta, float* __restrict__ C,
-                 int ldc, const float* __restrict__ bias) {
+                 int ldc, const float* __restrict__ bias, int k_chunk) {
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
   const int tid = threadIdx.x;
@@ -25,7 +25,12 @@ gemm_simt_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, 
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < K; k0 += BK) {
+  // split-K: slice blockIdx.z covers [kb, ke); partial sums are added atomically (C was
+  // pre-scaled by beta on the host side of the launch)
+  const bool split = gridDim.z > 1;
+  const int kb = split ? blockIdx.z * k_chunk : 0;
+  const int ke = split ? min(K, kb + k_chunk) : K;
+  for (int k0 = kb; k0 < ke; k0 += BK) {
     // A tile: BM x BK  (2048 elements, 8 per thread)
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
@@ -34,7 +39,7 @@ gemm_simt_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, 
       if (TA) { m = e % BM; k = e / BM; } else { k = e % BK; m = e / BK; }
       const int gm = m0 + m, gk = k0 + k;
       float v = 0.f;
-      if (gm < M && gk < K) v = TA ? A[(int64_t)gk * lda + gm] : A[(int64_t)gm * lda + gk];
+      if (gm < M && gk < ke) v = TA ? A[(int64_t)gk * lda + gm] : A[(int64_t)gm * lda + gk];
       As[k][m] = v;
     }
     // B tile: BK x BN  (1024 elements, 4 per thread)
@@ -45,7 +50,7 @@ gemm_simt_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, 
       if (TB) { k = e % BK; n = e / BK; } else { n = e % BN; k = e / BN; }
       const int gn = n0 + n, gk = k0 + k;
       float v = 0.f;
-      if (gn < N && gk < K) v = TB ? Bm[(int64_t)gn * ldb + gk] : Bm[(int64_t)gk * ldb + gn];
+      if (gn < N && gk < ke) v = TB ? Bm[(int64_t)gn * ldb + gk] : Bm[(int64_t)gk * ldb + gn];
       Bs[k][n] = v;
     }
     __syncthreads();
@@ -72,26 +77,58 @@ gemm_simt_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, 
       const int gn = n0 + tx * 4 + j;
       if (gn >= N) continue;
       float v = alpha * acc[i][j];
-      if (bias) v += bias[gn];
       float* c = C + (int64_t)gm * ldc + gn;
-      if (beta != 0.f) v += beta * (*c);
-      *c = v;
+      if (split) {
+        if (bias && blockIdx.z == 0) v += bias[gn];
+        atomicAdd(c, v);
+      } else {
+        if (bias) v += bias[gn];
+        if (beta != 0.f) v += beta * (*c);
+        *c = v;
+      }
     }
   }
 }
+
+__global__ void __launch_bounds__(256)
+scale_matrix_kernel(float* __restrict__ C, int M, int N, int ldc, float beta) {
+  const int64_t n = (int64_t)M * N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float* c = C + (i / N) * ldc + (i % N);
+    *c = beta == 0.f ? 0.f : beta * (*c);
+  }
+}
+
+int num_sms();
 
 int gemm_simt(int transa, int transb, int M, int N, int K, float alpha, const float* A, int lda,
               const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
               cudaStream_t stream) {
   dim3 grid(cdiv(N, BN), cdiv(M, BM));
+  // few output tiles and a long reduction (weight gradients over millions of rows): split K
+  int k_chunk = K;
+  const int tiles = grid.x * grid.y;
+  if (tiles * 2 <= num_sms() && K >= 8192) {
+    int splits = cdiv(2 * num_sms(), tiles);
+    if (splits > cdiv(K, 2048)) splits = cdiv(K, 2048);
+    if (splits > 1) {
+      k_chunk = cdiv(cdiv(K, splits), BK) * BK;
+      grid.z = cdiv(K, k_chunk);
+      if (grid.z > 1 && beta != 1.f) {
+        int blocks = cdiv((int64_t)M * N, 256); if (blocks > 1184) blocks = 1184;
+        scale_matrix_kernel<<<blocks, 256, 0, stream>>>(C, M, N, ldc, beta);
+        B2_LAUNCH_CHECK();
+      }
+    }
+  }
   if (!transa && !transb)
-    gemm_simt_kernel<false, false><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias);
+    gemm_simt_kernel<false, false><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, k_chunk);
   else if (!transa && transb)
-    gemm_simt_kernel<false, true><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias);
+    gemm_simt_kernel<false, true><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, k_chunk);
   else if (transa && !transb)
-    gemm_simt_kernel<true, false><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias);
+    gemm_simt_kernel<true, false><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, k_chunk);
   else
-    gemm_simt_kernel<true, true><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias);
+    gemm_simt_kernel<true, true><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, k_chunk);
   B2_LAUNCH_CHECK();
   return B2_OK;
 }

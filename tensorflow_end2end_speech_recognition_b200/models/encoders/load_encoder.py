@@ -1,7 +1,8 @@
 """Encoder registry, same entry point as ``models/encoders/load_encoder.py:26-57``."""
 from .core.blstm import BLSTMEncoder
+from .core.vgg_blstm import VGGBLSTMEncoder
 
-ENCODERS = {"blstm": BLSTMEncoder}
+ENCODERS = {"blstm": BLSTMEncoder, "vgg_blstm": VGGBLSTMEncoder}
 
 
 def load(encoder_type):

@@ -319,6 +319,51 @@ def blstm_layer_backward(desc, x, seq_len, p_fw, p_bw, dy, reserve, g_fw, g_bw, 
     return dx
 
 
+# ------------------------------------------------------------------ VGG front-end
+VGG_CONVS = ("VGG1/conv1", "VGG1/conv2", "VGG2/conv1", "VGG2/conv2")
+
+
+def vgg_desc(N, H, W, keep_prob=1.0, dropout_seed=0, precision=PREC_FP32):
+    return _lib.VggDesc(int(N), int(H), int(W), float(keep_prob), int(dropout_seed), int(precision))
+
+
+def _vgg_struct(p):
+    s = _lib.VggParams()
+    for i, c in enumerate(VGG_CONVS):
+        s.conv_w[i] = p[c + "/weight"].data_ptr()
+        s.conv_b[i] = p[c + "/bias"].data_ptr()
+    s.fc_w = p["bridge/weights"].data_ptr()
+    s.fc_b = p["bridge/biases"].data_ptr()
+    return s
+
+
+def vgg_frontend_forward(desc, x, params):
+    """x [N,H,W,3] (any view of that many contiguous floats) -> (out [N,256], reserve)"""
+    lib = _lib.load()
+    _require_cuda(x)
+    dev = x.device
+    out = torch.empty((desc.N, 256), dtype=torch.float32, device=dev)
+    reserve = torch.empty(lib.b2_vgg_reserve_bytes(C.byref(desc)), dtype=torch.uint8, device=dev)
+    nbytes = lib.b2_vgg_workspace_bytes(C.byref(desc))
+    ws = workspace("vgg", nbytes, dev)
+    ps = _vgg_struct(params)
+    rc = lib.b2_vgg_frontend_forward(C.byref(desc), _ptr(x.contiguous()), C.byref(ps), _ptr(out), _ptr(reserve),
+                                     _ptr(ws), nbytes, _stream())
+    _lib.check(rc, "b2_vgg_frontend_forward")
+    return out, reserve
+
+
+def vgg_frontend_backward(desc, params, d_out, reserve, grads):
+    lib = _lib.load()
+    _require_cuda(d_out)
+    nbytes = lib.b2_vgg_workspace_bytes(C.byref(desc))
+    ws = workspace("vgg", nbytes, d_out.device)
+    ps, gs = _vgg_struct(params), _vgg_struct(grads)
+    rc = lib.b2_vgg_frontend_backward(C.byref(desc), C.byref(ps), _ptr(d_out.contiguous()), _ptr(reserve),
+                                      C.byref(gs), _ptr(ws), nbytes, _stream())
+    _lib.check(rc, "b2_vgg_frontend_backward")
+
+
 # ------------------------------------------------------------------ clip + optimizer
 class TensorList(object):
     """Device-side arrays of pointers / sizes for the multi-tensor kernels."""

@@ -1,0 +1,115 @@
+"""VGG front-end (b2_vgg_frontend_forward/backward behind VGGBLSTMEncoder) vs oracle/vgg.py
+(torch float64, autograd): output, every filter / bias gradient, with and without dropout, for
+1-wide (splice*num_stack = 1) and wider images, odd and even sizes (SAME pooling tails), and the
+CTC model with encoder_type='vgg_blstm'.  fp32 tolerance 2e-4."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import model as omodel
+from oracle import vgg as ovgg
+from tests.util_dropout import dropout_mask
+
+pytestmark = pytest.mark.gpu
+
+
+def make_params(rng, H, W, scale=0.15):
+    chans = (3, 64, 64, 128, 128)
+    p = {}
+    for i, n in enumerate(ovgg.CONVS):
+        p[n + "/weight"] = (rng.randn(3, 3, chans[i], chans[i + 1]) * scale / np.sqrt(chans[i])).astype(np.float32)
+        p[n + "/bias"] = (rng.randn(chans[i + 1]) * 0.05).astype(np.float32)
+    h4, w4 = ovgg.output_geometry(H, W)
+    p["bridge/weights"] = (rng.randn(h4 * w4 * 128, 256) * 0.05).astype(np.float32)
+    p["bridge/biases"] = (rng.randn(256) * 0.05).astype(np.float32)
+    return p
+
+
+def run_gpu(cuda, x, p, H, W, keep, seed, d_out):
+    from tensorflow_end2end_speech_recognition_b200 import ops
+    N = x.shape[0] * x.shape[1]
+    pc = {k: torch.tensor(v, device=cuda) for k, v in p.items()}
+    gc = {k: torch.zeros_like(v) for k, v in pc.items()}
+    desc = ops.vgg_desc(N, H, W, keep_prob=keep, dropout_seed=seed)
+    out, reserve = ops.vgg_frontend_forward(desc, torch.tensor(x, device=cuda), pc)
+    ops.vgg_frontend_backward(desc, pc, torch.tensor(d_out, device=cuda).view(N, 256), reserve, gc)
+    torch.cuda.synchronize()
+    return out.cpu().numpy(), {k: v.cpu().numpy() for k, v in gc.items()}
+
+
+def run_oracle(x, p, H, W, keep, masks, d_out):
+    pt = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in p.items()}
+    out = ovgg.vgg_frontend(torch.tensor(x, dtype=torch.float64), pt, H, W, keep, masks)
+    (out * torch.tensor(d_out, dtype=torch.float64)).sum().backward()
+    return out.detach().numpy(), {k: v.grad.numpy() for k, v in pt.items()}
+
+
+@pytest.mark.parametrize("H,W", [(8, 1), (13, 1), (7, 3), (10, 2), (5, 5)])
+def test_frontend_forward_backward(cuda, H, W):
+    rng = np.random.RandomState(H * 10 + W)
+    B, T = 2, 5
+    x = rng.randn(B, T, H * W * 3).astype(np.float32)
+    p = make_params(rng, H, W)
+    d_out = rng.randn(B, T, 256).astype(np.float32)
+    out, g = run_gpu(cuda, x, p, H, W, 1.0, 0, d_out)
+    out_ref, g_ref = run_oracle(x, p, H, W, 1.0, None, d_out)
+    np.testing.assert_allclose(out.reshape(B, T, 256), out_ref, rtol=2e-4, atol=2e-5)
+    for k in p:
+        s = max(1e-4, np.abs(g_ref[k]).max())
+        np.testing.assert_allclose(g[k], g_ref[k], rtol=0, atol=5e-4 * s, err_msg=k)
+    if W == 1:      # the side columns of a 1-wide image only ever see padding
+        for n in ovgg.CONVS:
+            assert np.all(g[n + "/weight"][:, 0] == 0) and np.all(g[n + "/weight"][:, 2] == 0)
+
+
+@pytest.mark.parametrize("H,W", [(9, 1), (6, 3)])
+def test_frontend_dropout(cuda, H, W):
+    rng = np.random.RandomState(3)
+    B, T, keep, seed = 2, 4, 0.7, 4242
+    N = B * T
+    x = rng.randn(B, T, H * W * 3).astype(np.float32)
+    p = make_params(rng, H, W)
+    d_out = rng.randn(B, T, 256).astype(np.float32)
+    H2, W2 = (H + 1) // 2, (W + 1) // 2
+    H4, W4 = ovgg.output_geometry(H, W)
+    shapes = [(N, H, W, 64), (N, H2, W2, 64), (N, H2, W2, 128), (N, H4, W4, 128), (N, 256)]
+    masks = [dropout_mask(seed + 1 + i, int(np.prod(s)), keep).reshape(s) for i, s in enumerate(shapes)]
+    out, g = run_gpu(cuda, x, p, H, W, keep, seed, d_out)
+    out_ref, g_ref = run_oracle(x, p, H, W, keep, masks, d_out)
+    np.testing.assert_allclose(out.reshape(B, T, 256), out_ref, rtol=2e-4, atol=2e-5)
+    for k in p:
+        s = max(1e-4, np.abs(g_ref[k]).max())
+        np.testing.assert_allclose(g[k], g_ref[k], rtol=0, atol=5e-4 * s, err_msg=k)
+
+
+def test_vgg_blstm_ctc_model(cuda):
+    from tensorflow_end2end_speech_recognition_b200.models.ctc.ctc import CTC
+    rng = np.random.RandomState(5)
+    B, T, nch, C, H, L = 3, 16, 8, 9, 16, 2
+    D = nch * 3
+    model = CTC(encoder_type="vgg_blstm", input_size=D, num_units=H, num_layers=L, num_classes=C,
+                parameter_init=0.1, clip_grad_norm=5.0, device=cuda, seed=2)
+    x = rng.randn(B, T, D).astype(np.float32)
+    seq = np.array([T, 11, 14], np.int32)
+    for b in range(B):
+        x[b, seq[b]:] = 0
+    labels = [list(rng.randint(0, C, size=int(rng.randint(2, 5)))) for _ in range(B)]
+    loss, logits = model.compute_loss(x, labels, seq, keep_prob=1.0)
+    model._backward()
+    torch.cuda.synchronize()
+    vs = {v.name: torch.tensor(v.tensor.cpu().numpy(), dtype=torch.float64, requires_grad=True)
+          for v in model.trainable_variables()}
+    l_ref, logits_ref, _ = omodel.ctc_model_forward(vs, torch.tensor(x, dtype=torch.float64), seq, labels, L,
+                                                    vgg=(nch, 1))
+    l_ref.backward()
+    assert abs(float(loss) - float(l_ref.detach())) <= 2e-4 * abs(float(l_ref.detach()))
+    np.testing.assert_allclose(logits.cpu().numpy(), logits_ref.detach().numpy(), rtol=2e-4, atol=2e-5)
+    for v in model.trainable_variables():
+        g = vs[v.name].grad.numpy()
+        s = max(1e-4, np.abs(g).max())
+        np.testing.assert_allclose(v.grad.cpu().numpy(), g, rtol=0, atol=1e-3 * s, err_msg=v.name)
+    # one optimizer step runs and lowers the loss on the same batch
+    loss, _ = model.compute_loss(x, labels, seq, keep_prob=1.0)
+    model.train(loss, "adam", 1e-2)
+    loss2, _ = model.compute_loss(x, labels, seq, keep_prob=1.0, is_training=False)
+    assert float(loss2) < float(loss)
