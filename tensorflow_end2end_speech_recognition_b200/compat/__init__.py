@@ -1,0 +1,53 @@
+"""Drop-in glue for the reference's driver scripts.
+
+``install()`` makes ``import tensorflow`` resolve to ``compat.tf`` and aliases the reference's
+package paths (``models.ctc.ctc``, ``models.attention.*``, ``models.encoders.*``,
+``utils.io.labels.sparsetensor``, ``utils.training.multi_gpu``) to this package, so a script
+written against the reference imports the B200 implementation without edits.
+"""
+import importlib
+import sys
+
+_ALIASES = {
+    "models": "models",
+    "models.model_base": "models.model_base",
+    "models.ctc": "models.ctc",
+    "models.ctc.ctc": "models.ctc.ctc",
+    "models.encoders": "models.encoders",
+    "models.encoders.load_encoder": "models.encoders.load_encoder",
+    "models.encoders.core": "models.encoders.core",
+    "models.encoders.core.blstm": "models.encoders.core.blstm",
+    "models.encoders.core.vgg_blstm": "models.encoders.core.vgg_blstm",
+    "models.attention": "models.attention",
+    "models.attention.attention_seq2seq": "models.attention.attention_seq2seq",
+    "models.attention.joint_ctc_attention": "models.attention.joint_ctc_attention",
+    "models.attention.bridge": "models.attention.bridge",
+    "models.attention.decoders": "models.attention.decoders",
+    "models.attention.decoders.attention_layer": "models.attention.decoders.attention_layer",
+    "models.attention.decoders.attention_decoder": "models.attention.decoders.attention_decoder",
+    "utils": "utils",
+    "utils.io": "utils.io",
+    "utils.io.labels": "utils.io.labels",
+    "utils.io.labels.sparsetensor": "utils.io.labels.sparsetensor",
+    "utils.training": "utils.training",
+    "utils.training.multi_gpu": "utils.training.multi_gpu",
+}
+
+
+def install(alias_reference_packages=True):
+    from . import tf
+    sys.modules["tensorflow"] = tf
+    if alias_reference_packages:
+        pkg = __name__.rsplit(".", 1)[0]
+        for ref, mine in _ALIASES.items():
+            sys.modules.setdefault(ref, importlib.import_module(pkg + "." + mine))
+    return tf
+
+
+def uninstall():
+    sys.modules.pop("tensorflow", None)
+    pkg = __name__.rsplit(".", 1)[0]
+    for ref in _ALIASES:
+        m = sys.modules.get(ref)
+        if m is not None and getattr(m, "__name__", "").startswith(pkg):
+            sys.modules.pop(ref, None)

@@ -1,0 +1,248 @@
+"""The slice of the ``tensorflow`` 1.x module the reference's training / evaluation scripts and
+``models/test`` touch, re-expressed over ``compat.graph``: enough for
+
+    with tf.Graph().as_default():
+        model.create_placeholders(); lr = tf.placeholder(tf.float32, name='learning_rate')
+        loss_op, logits = model.compute_loss(model.inputs_pl_list[0], ...)
+        train_op = model.train(loss_op, optimizer='adam', learning_rate=lr)
+        ...
+        with tf.Session() as sess:
+            sess.run(tf.global_variables_initializer())
+            _, loss = sess.run([train_op, loss_op], feed_dict={...})
+
+to run unchanged on the B200 models.  ``compat.install()`` registers this module as
+``tensorflow`` so that ``import tensorflow as tf`` in a driver script resolves here.
+Nothing here computes: ops evaluate through the models' CUDA paths.
+"""
+import contextlib
+import os
+import unittest
+
+import numpy as np
+
+from . import graph as _g
+from ..utils.io.labels.sparsetensor import SparseTensorValue  # noqa: F401  (tf.SparseTensorValue)
+
+float32, float64, int32, int64, bool = "float32", "float64", "int32", "int64", "bool"   # noqa: A001
+__version__ = "1.2.0"        # the pinned version of the reference (requirements.txt:11)
+
+SparseTensor = _g.SparseTensor
+_default_graph = None
+
+
+class Graph(object):
+    def __init__(self):
+        self.models = []
+
+    @contextlib.contextmanager
+    def as_default(self):
+        global _default_graph
+        prev, _default_graph = _default_graph, self
+        try:
+            yield self
+        finally:
+            _default_graph = prev
+
+
+def get_default_graph():
+    global _default_graph
+    if _default_graph is None:
+        _default_graph = Graph()
+    return _default_graph
+
+
+def reset_default_graph():
+    global _default_graph
+    _default_graph = Graph()
+
+
+def register_model(model):
+    """Models announce themselves so tf.trainable_variables() / Saver can find their variables."""
+    g = get_default_graph()
+    if model not in g.models:
+        g.models.append(model)
+
+
+def placeholder(dtype, shape=None, name=None):
+    return _g.Placeholder(dtype, shape, name)
+
+
+@contextlib.contextmanager
+def _noop_scope(*args, **kwargs):
+    yield None
+
+
+device = name_scope = _noop_scope
+
+
+class _VarScope(object):
+    def reuse_variables(self):
+        pass
+
+
+@contextlib.contextmanager
+def variable_scope(*args, **kwargs):
+    yield _VarScope()
+
+
+def get_variable_scope():
+    return _VarScope()
+
+
+class _Dim(object):
+    def __init__(self, v):
+        self.value = int(v)
+
+
+class _VarView(object):
+    """What utils/parameter.py::count_total_parameters needs (:14-20): .name, .get_shape() -> dims with .value"""
+
+    def __init__(self, v):
+        self._v, self.name = v, v.name
+
+    def get_shape(self):
+        return [_Dim(d) for d in self._v.tensor.shape]
+
+
+def trainable_variables():
+    return [_VarView(v) for m in get_default_graph().models for v in m.trainable_variables()]
+
+
+def Variable(initial_value, name=None, trainable=True):   # noqa: N802  (global_step only)
+    return _g.Constant(initial_value)
+
+
+def global_variables_initializer():
+    return _g.Op(lambda: None, (), {}, name="init")       # variables are initialised at construction
+
+
+def _host(v):
+    return _g.to_host(v)
+
+
+def expand_dims(x, axis=0):
+    return _g.Op(lambda v: np.expand_dims(np.asarray(_host(v)), axis), (x,), {}, name="expand_dims")
+
+
+def concat(values, axis=0):
+    return _g.Op(lambda vs: np.concatenate([np.asarray(_host(v)) for v in vs], axis), (list(values),), {},
+                 name="concat")
+
+
+def reduce_mean(x, axis=None, name=None):
+    return _g.Op(lambda v: np.mean(np.asarray(_host(v)), axis=axis), (x,), {}, name=name or "reduce_mean")
+
+
+def edit_distance(hypothesis, truth, normalize=True):
+    from ..models.ctc.ctc import _edit_distance
+    from ..utils.io.labels.sparsetensor import sparse_to_label_lists
+
+    def fn(h, t):
+        B = int(np.asarray(t[2])[0])
+        hl, tl = sparse_to_label_lists(h, B), sparse_to_label_lists(t, B)
+        d = [float(_edit_distance(a, b)) / (len(b) if normalize else 1.0) for a, b in zip(hl, tl)]
+        return np.asarray(d, np.float32)
+    return _g.Op(fn, (hypothesis, truth), {}, name="edit_distance")
+
+
+class ConfigProto(object):
+    def __init__(self, **kwargs):
+        self.__dict__.update(kwargs)
+
+
+class Session(object):
+    def __init__(self, target="", graph=None, config=None):
+        self.graph = graph or get_default_graph()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+    def close(self):
+        pass
+
+    def run(self, fetches, feed_dict=None):
+        run = _g._Run(feed_dict)
+        single = not isinstance(fetches, (list, tuple))
+        out = [_host(run.resolve(f)) for f in ([fetches] if single else fetches)]
+        return out[0] if single else out
+
+
+class _Summary(object):
+    @staticmethod
+    def scalar(name, tensor):
+        return _g.Op(lambda v: (name, float(np.asarray(_host(v)))), (tensor,), {}, name="summary/" + name)
+
+    @staticmethod
+    def merge(inputs):
+        return _g.Op(lambda vs: list(vs), (list(inputs),), {}, name="summary/merge")
+
+    class FileWriter(object):
+        def __init__(self, logdir, graph=None):
+            self.logdir, self.events = logdir, []
+
+        def add_summary(self, summary, global_step=None):
+            self.events.append((global_step, summary))
+
+        def flush(self):
+            pass
+
+        def close(self):
+            pass
+
+
+summary = _Summary
+
+
+class _CheckpointState(object):
+    def __init__(self, path):
+        self.model_checkpoint_path = path
+
+
+class _Train(object):
+    class Saver(object):
+        """Checkpoints = {TF variable name: array} in one .npz (+ a 'checkpoint' index file)."""
+
+        def __init__(self, max_to_keep=None, var_list=None):
+            pass
+
+        def save(self, sess, save_path, global_step=None):
+            path = save_path if global_step is None else "%s-%d" % (save_path, global_step)
+            arrays = {v.name: v.tensor.detach().cpu().numpy() for m in sess.graph.models
+                      for v in m.trainable_variables()}
+            np.savez(path + ".npz", **arrays)
+            with open(os.path.join(os.path.dirname(path) or ".", "checkpoint"), "w") as f:
+                f.write('model_checkpoint_path: "%s"\n' % path)
+            return path
+
+        def restore(self, sess, save_path):
+            import torch
+            data = np.load(save_path + ".npz")
+            for m in sess.graph.models:
+                for v in m.trainable_variables():
+                    v.tensor.copy_(torch.as_tensor(data[v.name]).to(v.tensor.device))
+
+    @staticmethod
+    def get_checkpoint_state(checkpoint_dir):
+        idx = os.path.join(checkpoint_dir, "checkpoint")
+        if not os.path.isfile(idx):
+            return None
+        with open(idx) as f:
+            line = f.readline()
+        return _CheckpointState(line.split('"')[1])
+
+
+train = _Train
+
+
+class _Test(object):
+    TestCase = unittest.TestCase
+
+    @staticmethod
+    def main():
+        unittest.main()
+
+
+test = _Test

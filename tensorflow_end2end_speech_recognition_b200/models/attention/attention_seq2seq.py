@@ -21,6 +21,8 @@ import numpy as np
 import torch
 
 from ... import ops
+from ...compat import graph as _graph
+from ...compat.graph import graph_op
 from ..encoders.load_encoder import load
 from ..model_base import ModelBase
 from .bridge import InitialStateBridge, LSTMStateTuple
@@ -163,9 +165,20 @@ class AttentionSeq2Seq(ModelBase):
     # ----------------------------------------------------------------- feeds
     def create_placeholders(self):
         """Graph-mode relic (attention_seq2seq.py:511-548); feeds go straight to compute_loss."""
-        for k in ("inputs", "labels", "inputs_seq_len", "labels_seq_len", "keep_prob_encoder",
-                  "keep_prob_decoder", "keep_prob_embedding", "labels_st_true", "labels_st_pred"):
-            getattr(self, k + "_pl_list").append(None)
+        from ...compat import tf as _tf
+        _tf.register_model(self)
+        P, S = _graph.Placeholder, _graph.SparseTensor
+        self.inputs_pl_list.append(P("float32", [None, None, self.input_size], "input"))
+        self.labels_pl_list.append(P("int32", [None, None], "labels"))
+        self.inputs_seq_len_pl_list.append(P("int32", [None], "inputs_seq_len"))
+        self.labels_seq_len_pl_list.append(P("int32", [None], "labels_seq_len"))
+        self.keep_prob_encoder_pl_list.append(P("float32", name="keep_prob_encoder"))
+        self.keep_prob_decoder_pl_list.append(P("float32", name="keep_prob_decoder"))
+        self.keep_prob_embedding_pl_list.append(P("float32", name="keep_prob_embedding"))
+        self.labels_st_true_pl = S(P("int64"), P("int32"), P("int64"))
+        self.labels_st_pred_pl = S(P("int64"), P("int32"), P("int64"))
+        self.labels_st_true_pl_list.append(S(P("int64"), P("int32"), P("int64")))
+        self.labels_st_pred_pl_list.append(S(P("int64"), P("int32"), P("int64")))
 
     def _dev(self, x, dtype):
         if not torch.is_tensor(x):
@@ -204,6 +217,7 @@ class AttentionSeq2Seq(ModelBase):
         self._enc_out, self._init_state = enc, init
         return out_train.logits, out_train, _LazyDecoderOutput(infer), enc.outputs
 
+    @graph_op(n_out=4, name="compute_loss")
     def compute_loss(self, inputs, labels, inputs_seq_len, labels_seq_len, keep_prob_encoder,
                      keep_prob_decoder, keep_prob_embedding, scope=None, is_training=True):
         """-> (total_loss, logits [B,T_out-1,V], decoder_outputs_train, decoder_outputs_infer)
@@ -265,18 +279,22 @@ class AttentionSeq2Seq(ModelBase):
         return d_enc_tm
 
     # ---------------------------------------------------------------- decode
+    @graph_op(n_out=2, name="decode")
     def decode(self, decoder_outputs_train, decoder_outputs_infer):
         """-> (decoded_train [B,T_out-1], decoded_infer [B,<=max_decode_length])  (:666-699)"""
         return decoder_outputs_train.predicted_ids, decoder_outputs_infer.predicted_ids
 
+    @graph_op(name="compute_ler")
     def compute_ler(self, labels_true, labels_pred):
         """mean_b edit_distance(pred_b, true_b) / len(true_b)  (:701-724); sparse triples or lists"""
         from ..ctc.ctc import _edit_distance
         from ...utils.io.labels.sparsetensor import sparse_to_label_lists
 
         def lists(x):
-            if isinstance(x, list) and (not x or isinstance(x[0], (list, tuple, np.ndarray))):
-                return [list(r) for r in x]
-            return sparse_to_label_lists(x, int(x[2][0]) if isinstance(x, (tuple, list)) else int(x.dense_shape[0]))
+            if hasattr(x, "dense_shape"):
+                return sparse_to_label_lists(x, int(x.dense_shape[0]))
+            if isinstance(x, (list, tuple)) and len(x) == 3 and getattr(x[0], "ndim", 0) == 2:
+                return sparse_to_label_lists(x, int(np.asarray(x[2])[0]))
+            return [list(r) for r in x]
         t, p = lists(labels_true), lists(labels_pred)
         return float(np.mean([_edit_distance(h, r) / float(len(r)) for h, r in zip(p, t)]))

@@ -18,6 +18,8 @@ import numpy as np
 import torch
 
 from ... import ops
+from ...compat import graph as _graph
+from ...compat.graph import graph_op
 from ..ctc.ctc import _truncated_normal
 from ...utils.io.labels.sparsetensor import SparseTensorValue, sparse_to_label_lists
 from .attention_seq2seq import AttentionSeq2Seq
@@ -59,7 +61,8 @@ class JointCTCAttention(AttentionSeq2Seq):
 
     def create_placeholders(self):
         super(JointCTCAttention, self).create_placeholders()
-        self.ctc_labels_pl_list.append(None)
+        P = _graph.Placeholder
+        self.ctc_labels_pl_list.append(_graph.SparseTensor(P("int64"), P("int32"), P("int64")))
 
     def ctc_logits(self, encoder_outputs):
         """encoder_outputs [B,T,2H] batch-major -> logits [T,B,ctc_num_classes]  (:182-235)"""
@@ -73,6 +76,7 @@ class JointCTCAttention(AttentionSeq2Seq):
         self._ctc_rows = rows
         return ops.gemm(rows, w, False, False, b, prec).view(T, B, self.ctc_num_classes)
 
+    @graph_op(n_out=5, name="compute_loss")
     def compute_loss(self, inputs, labels, ctc_labels, inputs_seq_len, labels_seq_len,
                      keep_prob_encoder, keep_prob_decoder, keep_prob_embedding, scope=None,
                      is_training=True):

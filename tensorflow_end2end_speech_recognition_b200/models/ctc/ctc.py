@@ -14,6 +14,8 @@ import numpy as np
 import torch
 
 from ... import ops
+from ...compat import graph as _graph
+from ...compat.graph import graph_op
 from ...utils.io.labels.sparsetensor import SparseTensorValue, sparse_to_label_lists
 from ..encoders.load_encoder import load
 from ..model_base import ModelBase
@@ -103,12 +105,16 @@ class CTC(ModelBase):
 
     # ----------------------------------------------------------------- feeds
     def create_placeholders(self):
-        """Graph-mode relic (ctc.py:240-254): kept so driver scripts can call it; feeds are
-        passed directly to compute_loss."""
-        self.inputs_pl_list.append(None)
-        self.labels_pl_list.append(None)
-        self.inputs_seq_len_pl_list.append(None)
-        self.keep_prob_pl_list.append(None)
+        """One placeholder set per tower (ctc.py:240-254).  Passing these handles to compute_loss /
+        decoder / ... yields lazy ops for ``compat.tf.Session.run``; passing arrays evaluates eagerly."""
+        from ...compat import tf as _tf
+        _tf.register_model(self)
+        self.inputs_pl_list.append(_graph.Placeholder("float32", [None, None, self.input_size], "input"))
+        self.labels_pl_list.append(_graph.SparseTensor(_graph.Placeholder("int64", name="indices"),
+                                                       _graph.Placeholder("int32", name="values"),
+                                                       _graph.Placeholder("int64", name="shape")))
+        self.inputs_seq_len_pl_list.append(_graph.Placeholder("int32", [None], "inputs_seq_len"))
+        self.keep_prob_pl_list.append(_graph.Placeholder("float32", name="keep_prob"))
 
     def _to_device(self, inputs, inputs_seq_len):
         if not torch.is_tensor(inputs):
@@ -134,6 +140,7 @@ class CTC(ModelBase):
                             self.variables["output/biases"], prec)
         return logits2d.view(T, B, self.num_classes)
 
+    @graph_op(n_out=2, name="compute_loss")
     def compute_loss(self, inputs, labels, inputs_seq_len, keep_prob, scope=None,
                      softmax_temperature=1, is_training=True):
         """-> (total_loss 0-d cuda tensor, logits [T,B,C])   (ctc.py:256-323).
@@ -185,6 +192,7 @@ class CTC(ModelBase):
         self._ctx = None
 
     # ---------------------------------------------------------------- decode
+    @graph_op(name="decoder")
     def decoder(self, logits, inputs_seq_len, beam_width=1):
         """-> SparseTensorValue(indices int64 [N,2], values int32 [N], dense_shape)  (ctc.py:325-352)"""
         assert isinstance(beam_width, int), "beam_width must be integer."
@@ -206,11 +214,13 @@ class CTC(ModelBase):
         return SparseTensorValue(np.asarray(idx, np.int64).reshape(-1, 2), np.asarray(val, np.int32),
                                  np.asarray([B, maxlen], np.int64))
 
+    @graph_op(name="posteriors")
     def posteriors(self, logits, blank_prior=1):
         """softmax over classes, batch-major [B*T, num_classes]  (ctc.py:354-380)"""
         lb = ops.transpose_01(logits)
         return ops.softmax_rows(lb.view(-1, self.num_classes))
 
+    @graph_op(name="compute_ler")
     def compute_ler(self, decode_op, labels):
         """mean_b edit_distance(hyp_b, ref_b)/len(ref_b)  (ctc.py:382-398)"""
         B = int(decode_op.dense_shape[0])

@@ -11,6 +11,7 @@ import numpy as np
 import torch
 
 from .. import ops
+from ..compat.graph import graph_op
 
 OPTIMIZER_CLS_NAMES = {          # name -> (kernel kind, number of state slots, slot-0 init)
     "adagrad": ("adagrad", 1, 0.1),
@@ -112,6 +113,7 @@ class ModelBase(object):
         ops.clip_by_norm_multi(self._grad_list, self.clip_grad_norm, post_scale=1.0 / self.world_size)
         return [(g, v) for g, v in grads_and_vars if g is not None]
 
+    @graph_op(name="train")
     def train(self, loss, optimizer, learning_rate):
         """One optimisation step on the loss of the last ``compute_loss``
         (reference: model_base.py:97-133).  ``optimizer`` is a name from
