@@ -212,6 +212,21 @@ int b2_blstm_profile_last_ms(float* fwd_ms, float* bwd_ms);
 int b2_blstm_backward_join(b2_stream_t stream);
 
 /* ------------------------------------------------------------------------ *
+ * Input pipeline on the device: frame stacking / skipping + splicing + zero padding
+ *   reference: utils/io/inputs/frame_stacking.py:14-85 (stack_frame),
+ *   utils/io/inputs/splicing.py:9-73 (do_splice), applied per utterance before padding by
+ *   utils/dataset/ctc.py:120-160.  Bit-exact gather (golden vectors from the reference's own
+ *   numpy functions: tests/golden/input_pipeline.npz).
+ * raw [B,Traw,D] zero-padded features, raw_len [B] -> out [B,Tout,Dout] (zero past each
+ * utterance's new length), out_len [B] = raw_len (num_stack == 1) or ceil(raw_len/num_skip).
+ * Dout = b2_stack_splice_out_dim(D, num_stack, splice).
+ * ------------------------------------------------------------------------ */
+int b2_stack_splice_out_dim(int D, int num_stack, int splice);
+int b2_stack_splice(const float* raw, const int32_t* raw_len, int B, int Traw, int D,
+                    int num_stack, int num_skip, int splice, int Tout, float* out,
+                    int32_t* out_len, b2_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
  * VGG front-end of the VGG-BLSTM encoder
  *   reference: models/encoders/core/vgg_blstm.py:93-177 (VGGBLSTMEncoder.__call__ up to the
  *   BLSTM), models/encoders/core/cnn_util.py:52-84 (conv_layer), :13-29 (max_pool)

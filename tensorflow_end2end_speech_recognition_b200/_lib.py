@@ -73,6 +73,8 @@ PROTOTYPES = {
     "b2_blstm_layer_backward_ex": (_i, [C.POINTER(LstmDesc), _p, _p, _p, C.POINTER(LstmParams),
                                         C.POINTER(LstmParams), _p, _p, _p, _p, C.POINTER(LstmGrads),
                                         C.POINTER(LstmGrads), _p, _sz, _p]),
+    "b2_stack_splice_out_dim": (_i, [_i, _i, _i]),
+    "b2_stack_splice": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "b2_vgg_reserve_bytes": (_sz, [C.POINTER(VggDesc)]),
     "b2_vgg_workspace_bytes": (_sz, [C.POINTER(VggDesc)]),
     "b2_vgg_output_size": (_i, [C.POINTER(VggDesc)]),

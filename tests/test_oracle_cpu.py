@@ -4,6 +4,7 @@ enumeration, torch's independent CTC, and a second literal LSTM form."""
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import ctc as octc
@@ -188,3 +189,21 @@ def test_greedy_decoder_oracle_semantics():
     p["output_layer/biases"] = np.array([0, 0, 0, 0, 50.0])
     r = odec.decode(p, "luong_general", enc, lens, st, sos=3, eos=4, max_decode_length=6)
     assert r["logits"].shape[1] == 1
+
+
+def test_input_pipeline_oracle_against_reference_golden():
+    """oracle/inputs.py vs the outputs of the reference's own stack_frame / do_splice."""
+    import os
+    from oracle import inputs as oin
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "input_pipeline.npz"))
+    for i in range(int(g["n_cases"])):
+        T, nch, S, K, P = [int(v) for v in g["cfg_%d" % i]]
+        st = oin.stack_frame(g["x_%d" % i], S, K)
+        assert np.array_equal(st, g["stacked_%d" % i])
+        assert np.array_equal(oin.do_splice(st, P, S), g["spliced_%d" % i])
+    with pytest.raises(ValueError):
+        oin.stack_frame(np.zeros((4, 3), np.float32), 2, 3)
+    ins, labs, lens = oin.make_batch([np.ones((5, 3), np.float32), np.ones((2, 3), np.float32), np.ones((4, 3), np.float32)],
+                                     [[1, 2], [3], [4, 5, 6]], num_gpu=2)
+    assert [a.shape for a in ins] == [(2, 5, 3), (1, 5, 3)] and labs[0].tolist() == [[1, 2, -1], [3, -1, -1]]
+    assert lens[1].tolist() == [4]
