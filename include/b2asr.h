@@ -266,6 +266,84 @@ int b2_vgg_frontend_backward(const b2_vgg_desc* d, const b2_vgg_params* p, const
                              size_t workspace_bytes, b2_stream_t stream);
 
 /* ------------------------------------------------------------------------ *
+ * The whole attention decoder loop behind one call per direction
+ *   reference: tf.while_loop over AttentionDecoder.step -- dynamic_decoder.py:148-212,
+ *   attention_decoder.py:142-295; helpers attention_seq2seq.py:440-446 (TrainingHelper),
+ *   :486-494 (GreedyEmbeddingHelper)
+ * ------------------------------------------------------------------------ */
+typedef struct {
+  int32_t B, T, E, Hd, A, emb, C;   /* batch, encoder frames, encoder width, decoder units, query
+                                       width, embedding dim, classes (incl. <SOS>, <EOS>)     */
+  int32_t attention_mode;           /* 0 additive, 1 multiplicative (b2_attention_step_forward) */
+  int32_t query_projected;          /* 1: q = h . w_query [Hd,A]; 0: q = h (A == Hd)          */
+  int32_t filter_width;             /* location term: conv filter taps, 0 = none              */
+  float sharpening;
+  int32_t sigmoid_smoothing;
+  float forget_bias, cell_clip;     /* LSTMBlockCell; cell_clip <= 0: none                     */
+  int32_t feed_previous_attention;  /* 0 = the reference's behaviour (zeros), inference only   */
+} b2_decoder_desc;
+typedef struct {
+  const float* cell_kernel;         /* [emb+E+Hd, 4Hd], gate blocks i,g,f,o                     */
+  const float* cell_bias;           /* [4Hd]                                                   */
+  const float* w_i_diag; const float* w_f_diag; const float* w_o_diag;   /* [Hd] or all NULL   */
+  const float* w_query;             /* [Hd,A] or NULL                                          */
+  const float* conv_filter;         /* [filter_width,10] or NULL                               */
+  const float* w_filter;            /* [10,A]                                                  */
+  const float* b_filter;            /* [A]                                                     */
+  const float* v_a;                 /* [A] or NULL                                             */
+  const float* w_av;                /* attentional_vector/weights [Hd+E, Hd]                   */
+  const float* w_out;               /* output_layer/weights [Hd, C]                            */
+  const float* b_out;               /* [C]                                                     */
+  const float* embedding;           /* W_embedding [C, emb]                                    */
+} b2_decoder_params;
+typedef struct {                    /* same fields, gradients are ACCUMULATED                  */
+  float* cell_kernel; float* cell_bias; float* w_i_diag; float* w_f_diag; float* w_o_diag;
+  float* w_query; float* conv_filter; float* w_filter; float* b_filter; float* v_a;
+  float* w_av; float* w_out; float* b_out; float* embedding;
+} b2_decoder_grads;
+size_t b2_attention_decoder_reserve_bytes(const b2_decoder_desc* d, int max_steps);
+size_t b2_attention_decoder_workspace_bytes(const b2_decoder_desc* d, int max_steps);
+/* labels == NULL: greedy decoding from <SOS> until every row emitted <EOS> or max_steps (the
+ * finished flags are polled on the host every poll_every steps, 0 = never); labels [B,labels_ld]
+ * + dec_len [B]: teacher forcing on labels[:, :-1].  reserve != NULL (teacher forcing only): keep
+ * what b2_attention_decoder_backward needs.  keys: the hoisted key projection [B,T,A] (NULL for
+ * `location`).  Outputs are batch-major [B,max_steps,*] with zeros past each row's finish;
+ * c_state/h_state [B,Hd] = final state; *steps_run = iterations executed. */
+int b2_attention_decoder_forward(const b2_decoder_desc* d, const b2_decoder_params* p,
+                                 const float* enc, const float* keys, const int32_t* enc_len,
+                                 const float* c0, const float* h0, const int32_t* labels,
+                                 int labels_ld, const int32_t* dec_len, int sos, int eos,
+                                 int max_steps, int poll_every, void* reserve,
+                                 float* out_logits, int32_t* out_ids, float* out_av,
+                                 float* out_alpha, float* out_ctx, float* c_state,
+                                 float* h_state, int32_t* finished, int32_t* steps_run,
+                                 void* workspace, size_t workspace_bytes, b2_stream_t stream);
+/* dlogits_tm [steps,B,C] time-major.  Accumulates parameter gradients into g, d_keys [B,T,A]
+ * (NULL for `location`; for luong_dot pass d_enc) and d_enc [B,T,E] (through the context only --
+ * the key projection's share is the caller's GEMM); writes dc0, dh0 [B,Hd]. */
+int b2_attention_decoder_backward(const b2_decoder_desc* d, const b2_decoder_params* p,
+                                  const float* enc, const float* keys, const int32_t* enc_len,
+                                  const int32_t* labels, int labels_ld, int steps,
+                                  const void* reserve, const float* dlogits_tm,
+                                  const b2_decoder_grads* g, float* d_keys, float* d_enc,
+                                  float* dc0, float* dh0, void* workspace,
+                                  size_t workspace_bytes, b2_stream_t stream);
+
+/* Levenshtein distance of B (hypothesis, reference) label-sequence pairs (tf.edit_distance as
+ * compute_ler uses it, models/ctc/ctc.py:382-398): flat label arrays + [B+1] offsets, dist [B].
+ * The caller divides by the reference length (normalize=True) and averages. */
+int b2_edit_distance(const int32_t* hyp, const int32_t* hyp_offsets, const int32_t* ref,
+                     const int32_t* ref_offsets, int B, int max_ref_len, int32_t* dist,
+                     b2_stream_t stream);
+
+/* x = dropout(relu(x)) in place (element i keeps with the counter hash of (seed, i)) and its
+ * backward d_in = d_out * (out > 0 ? 1/keep_prob : 0): the activation of the VGG bridge layer and
+ * of the CTC bottleneck layer (models/ctc/ctc.py:200-213). */
+int b2_relu_dropout_forward(float* x, int64_t n, float keep_prob, uint64_t seed, b2_stream_t stream);
+int b2_relu_dropout_backward(const float* d_out, const float* out, int64_t n, float keep_prob,
+                             float* d_in, b2_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
  * Attention step (energy + masked softmax + context)   replaces
  *   AttentionLayer.__call__, models/attention/decoders/attention_layer.py:45-347
  * One decoder step over all T encoder states; the key projection is hoisted
@@ -276,7 +354,8 @@ int b2_vgg_frontend_backward(const b2_vgg_desc* d, const b2_vgg_params* p, const
  *                          (dot_product, luong_dot, luong_general)
  *   loc = conv1d_SAME(prev_alpha, conv_filter[filter_width,10]) . w_filter[10,A]
  *         + b_filter (NULL conv_filter = no location term; keys may be NULL
- *         for pure `location`)
+ *         for pure `location`; prev_alpha NULL with a location term = all-zero
+ *         previous weights, the convolution is skipped)
  * enc [B,T,E], keys [B,T,A], q [B,A], prev_alpha [B,T], enc_len [B];
  * energies of t >= enc_len are float32.min, then *sharpening_factor, then
  * softmax (or sigmoid / sum when sigmoid_smoothing).  alpha [B,T], context [B,E].

@@ -41,7 +41,10 @@ def ctc_model_forward(variables, inputs_btd, seq_len, labels, num_layers, use_pe
     enc, _ = olstm.blstm_forward(inputs_btd, seq_len, layers, keep_prob=keep_prob,
                                  dropout_masks=dropout_masks, cell_clip=cell_clip)
     T, B, E = enc.shape
-    logits = (enc.reshape(T * B, E) @ variables["output/weights"] + variables["output/biases"])
+    feat = enc.reshape(T * B, E)
+    if "bottleneck/weights" in variables:                               # ctc.py:200-213 (keep_prob 1)
+        feat = torch.relu(feat @ variables["bottleneck/weights"] + variables["bottleneck/biases"])
+    logits = (feat @ variables["output/weights"] + variables["output/biases"])
     logits = logits.reshape(T, B, -1)
     C = logits.shape[-1]
     lens = torch.tensor([len(l) for l in labels], dtype=torch.long)

@@ -42,6 +42,25 @@ class VggParams(C.Structure):
 
 VggGrads = VggParams
 
+
+class DecoderDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("E", C.c_int32), ("Hd", C.c_int32), ("A", C.c_int32),
+                ("emb", C.c_int32), ("C", C.c_int32), ("attention_mode", C.c_int32),
+                ("query_projected", C.c_int32), ("filter_width", C.c_int32), ("sharpening", C.c_float),
+                ("sigmoid_smoothing", C.c_int32), ("forget_bias", C.c_float), ("cell_clip", C.c_float),
+                ("feed_previous_attention", C.c_int32)]
+
+
+_DEC_FIELDS = ("cell_kernel", "cell_bias", "w_i_diag", "w_f_diag", "w_o_diag", "w_query", "conv_filter",
+               "w_filter", "b_filter", "v_a", "w_av", "w_out", "b_out", "embedding")
+
+
+class DecoderParams(C.Structure):
+    _fields_ = [(f, C.c_void_p) for f in _DEC_FIELDS]
+
+
+DecoderGrads = DecoderParams
+
 _p, _i, _f, _sz, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_int64
 
 # name -> (restype, argtypes); mirrors include/b2asr.h one to one
@@ -73,6 +92,16 @@ PROTOTYPES = {
     "b2_blstm_layer_backward_ex": (_i, [C.POINTER(LstmDesc), _p, _p, _p, C.POINTER(LstmParams),
                                         C.POINTER(LstmParams), _p, _p, _p, _p, C.POINTER(LstmGrads),
                                         C.POINTER(LstmGrads), _p, _sz, _p]),
+    "b2_attention_decoder_reserve_bytes": (_sz, [C.POINTER(DecoderDesc), _i]),
+    "b2_attention_decoder_workspace_bytes": (_sz, [C.POINTER(DecoderDesc), _i]),
+    "b2_attention_decoder_forward": (_i, [C.POINTER(DecoderDesc), C.POINTER(DecoderParams), _p, _p, _p, _p, _p, _p,
+                                          _i, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p,
+                                          C.POINTER(C.c_int32), _p, _sz, _p]),
+    "b2_attention_decoder_backward": (_i, [C.POINTER(DecoderDesc), C.POINTER(DecoderParams), _p, _p, _p, _p, _i, _i,
+                                           _p, _p, C.POINTER(DecoderGrads), _p, _p, _p, _p, _p, _sz, _p]),
+    "b2_edit_distance": (_i, [_p, _p, _p, _p, _i, _i, _p, _p]),
+    "b2_relu_dropout_forward": (_i, [_p, _i64, _f, C.c_uint64, _p]),
+    "b2_relu_dropout_backward": (_i, [_p, _p, _i64, _f, _p, _p]),
     "b2_stack_splice_out_dim": (_i, [_i, _i, _i]),
     "b2_stack_splice": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "b2_vgg_reserve_bytes": (_sz, [C.POINTER(VggDesc)]),

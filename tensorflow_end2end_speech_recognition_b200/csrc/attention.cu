@@ -56,7 +56,10 @@ attention_step_kernel(const AttnArgs a) {
     s_bf[i] = a.b_f ? a.b_f[i] : 0.f;
   }
   const bool loc = a.filt != nullptr;
-  if (loc) {
+  // prev_alpha == NULL with a location term: the previous weights are known to be all zero (what the
+  // reference's decoder always feeds) -> conv features are 0, the term is b_filter
+  const bool loc_conv = loc && a.prev_alpha != nullptr;
+  if (loc_conv) {
     const int pl = (a.Kw - 1) / 2;
     for (int i = tid; i < 10 * A; i += kAttnThreads) s_wf[i] = a.w_f[i];
     for (int i = tid; i < a.Kw * 10; i += kAttnThreads) s_filt[i] = a.filt[i];
@@ -85,11 +88,13 @@ attention_step_kernel(const AttnArgs a) {
         if (a.mode == 1) acc = fmaf(kv, s_q[i], acc);
         else {
           float x = kv + s_q[i];
-          if (loc) {
+          if (loc_conv) {
             float l = s_bf[i];
 #pragma unroll
             for (int k = 0; k < 10; ++k) l = fmaf(s_f[t * 10 + k], s_wf[k * A + i], l);
             x += l;
+          } else if (loc) {
+            x += s_bf[i];
           }
           acc = fmaf(s_v[i], tanhf_(x), acc);
         }
@@ -310,8 +315,8 @@ extern "C" int b2_attention_step_forward(int mode, const float* enc, const float
   B2_CHECK_ARG(mode == 0 || mode == 1, "b2_attention_step_forward: mode %d", mode);
   B2_CHECK_ARG(B > 0 && T > 0 && E > 0 && A > 0 && E % 4 == 0, "b2_attention_step_forward: bad shape");
   B2_CHECK_ARG(keys || (mode == 0 && conv_filter), "b2_attention_step_forward: keys missing");
-  B2_CHECK_ARG(!conv_filter || (prev_alpha && w_filter && filter_width > 0),
-               "b2_attention_step_forward: location term needs prev_alpha / W_filter");
+  B2_CHECK_ARG(!conv_filter || (w_filter && filter_width > 0),
+               "b2_attention_step_forward: location term needs W_filter");
   AttnArgs a;
   a.mode = mode; a.enc = enc; a.keys = keys; a.q = q; a.prev_alpha = prev_alpha; a.enc_len = enc_len;
   a.filt = conv_filter; a.w_f = w_filter; a.b_f = b_filter; a.v_a = v_a;

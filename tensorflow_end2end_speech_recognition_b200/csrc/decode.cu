@@ -116,3 +116,71 @@ extern "C" int b2_softmax_rows(const float* x, float* y, int64_t rows, int C,
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// Label error rate: Levenshtein distance of B (hypothesis, reference) pairs, one warp per pair.
+// Replaces tf.edit_distance(hyp, truth, normalize=True) as used by compute_ler
+// (models/ctc/ctc.py:382-398, attention_seq2seq.py:701-724).  Integer work, bit-exact.
+// Row DP over the hypothesis; the reference row lives in shared memory (two int rows), lanes
+// sweep the row in chunks of 32 with the left-neighbour dependency resolved by a warp scan:
+//   d[j] = min(up[j] + 1, diag[j] + cost, d[j-1] + 1)  ->  e[j] = min(up+1, diag+cost) then
+//   d[j] = min_k<=j (e[k] + (j - k))  (prefix-min of e[k]-k, plus j).
+// ---------------------------------------------------------------------------------------
+namespace b2 {
+
+__global__ void __launch_bounds__(128)
+edit_distance_kernel(const int* __restrict__ hyp, const int* __restrict__ hyp_off,
+                     const int* __restrict__ ref, const int* __restrict__ ref_off, int B, int max_ref,
+                     int* __restrict__ dist) {
+  extern __shared__ int sm_ed[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = blockIdx.x * 4 + warp;
+  if (p >= B) return;
+  int* row0 = sm_ed + (size_t)warp * 2 * (max_ref + 1);
+  int* row1 = row0 + (max_ref + 1);
+  const int* h = hyp + hyp_off[p];
+  const int* r = ref + ref_off[p];
+  const int n = hyp_off[p + 1] - hyp_off[p], m = ref_off[p + 1] - ref_off[p];
+  for (int j = lane; j <= m; j += 32) row0[j] = j;
+  __syncwarp();
+  int* up = row0; int* cur = row1;
+  for (int i = 1; i <= n; ++i) {
+    const int hc = h[i - 1];
+    int carry = i;                                   // d[i][0]
+    if (lane == 0) cur[0] = i;
+    for (int j0 = 1; j0 <= m; j0 += 32) {
+      const int j = j0 + lane;
+      int e = 0x3fffffff;
+      if (j <= m) e = min(up[j] + 1, up[j - 1] + (hc != r[j - 1] ? 1 : 0));
+      // prefix-min of (e[k] - k) over the chunk, seeded with the carry from the previous chunk
+      int v = e - j;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v = min(v, t);
+      }
+      int d = min(v + j, carry + (j - (j0 - 1)));
+      if (j <= m) cur[j] = d;
+      carry = __shfl_sync(0xffffffffu, d, 31);
+    }
+    __syncwarp();
+    int* t = up; up = cur; cur = t;
+  }
+  if (lane == 0) dist[p] = up[m];
+}
+
+}  // namespace b2
+
+extern "C" int b2_edit_distance(const int32_t* hyp, const int32_t* hyp_offsets, const int32_t* ref,
+                                const int32_t* ref_offsets, int B, int max_ref_len, int32_t* dist,
+                                b2_stream_t stream_) {
+  using namespace b2;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B2_CHECK_ARG(hyp_offsets && ref_offsets && dist && B > 0 && max_ref_len >= 0, "b2_edit_distance: bad argument");
+  const size_t smem = (size_t)4 * 2 * (max_ref_len + 1) * sizeof(int);
+  B2_CHECK_ARG(smem <= 200 * 1024, "b2_edit_distance: reference of %d labels too long", max_ref_len);
+  B2_CUDA(cudaFuncSetAttribute(edit_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  edit_distance_kernel<<<cdiv(B, 4), 128, smem, stream>>>(hyp, hyp_offsets, ref, ref_offsets, B, max_ref_len, dist);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}

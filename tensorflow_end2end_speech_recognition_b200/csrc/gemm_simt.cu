@@ -101,9 +101,109 @@ scale_matrix_kernel(float* __restrict__ C, int M, int N, int ldc, float beta) {
 
 int num_sms();
 
+// ---------------------------------------------------------------------------------------
+// Skinny GEMM: M <= 32 rows (one decoder step's batch).  The 128x64 tile kernel above runs such a
+// product on a handful of CTAs with a serial K loop (measured 80 us for [8x1344].[1344x1024]);
+// here the work is split over N tiles x K slices so that ~2 waves of CTAs stream B once
+// (L2/HBM-bound, a few microseconds).  Tile: 64 columns x 64 k per iteration, B tile staged in
+// shared memory as Bs[k][n] whatever its storage order, thread = (column, quarter of the rows).
+// Partial sums of the K slices are added atomically (C pre-scaled by beta and seeded with the bias).
+// ---------------------------------------------------------------------------------------
+constexpr int SN = 64, SK = 64, SM_MAX = 32;
+
+template <bool TB>
+__global__ void __launch_bounds__(256)
+gemm_skinny_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int lda,
+                   const float* __restrict__ Bm, int ldb, float beta, float* __restrict__ C, int ldc,
+                   const float* __restrict__ bias, int k_chunk) {
+  __shared__ float As[SM_MAX][SK + 1];
+  __shared__ float Bs[SK][SN + 1];
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.x * SN;
+  const int kb = blockIdx.y * k_chunk, ke = min(K, kb + k_chunk);
+  const int nl = tid & 63, mg = tid >> 6;              // column within the tile, row group (rows mg, mg+4, ...)
+  float acc[SM_MAX / 4];
+#pragma unroll
+  for (int i = 0; i < SM_MAX / 4; ++i) acc[i] = 0.f;
+  for (int k0 = kb; k0 < ke; k0 += SK) {
+    // A chunk: M x SK
+    for (int e = tid; e < M * SK; e += 256) {
+      const int m = e / SK, k = e % SK;
+      As[m][k] = (k0 + k < ke) ? A[(int64_t)m * lda + k0 + k] : 0.f;
+    }
+    // B tile: SK x SN
+#pragma unroll
+    for (int r = 0; r < (SK * SN) / 256; ++r) {
+      const int e = tid + r * 256;
+      int k, n;
+      if (TB) { k = e % SK; n = e / SK; } else { n = e % SN; k = e / SN; }
+      float v = 0.f;
+      if (n0 + n < N && k0 + k < ke) v = TB ? Bm[(int64_t)(n0 + n) * ldb + k0 + k] : Bm[(int64_t)(k0 + k) * ldb + n0 + n];
+      Bs[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < SK; ++k) {
+      const float b = Bs[k][nl];
+#pragma unroll
+      for (int i = 0; i < SM_MAX / 4; ++i) acc[i] = fmaf(As[mg + 4 * i][k], b, acc[i]);
+    }
+    __syncthreads();
+  }
+  const int gn = n0 + nl;
+  if (gn >= N) return;
+#pragma unroll
+  for (int i = 0; i < SM_MAX / 4; ++i) {
+    const int m = mg + 4 * i;
+    if (m >= M) continue;
+    float v = alpha * acc[i];
+    float* c = C + (int64_t)m * ldc + gn;
+    if (gridDim.y > 1) atomicAdd(c, v);
+    else {
+      if (bias) v += bias[gn];
+      if (beta != 0.f) v += beta * (*c);
+      *c = v;
+    }
+  }
+}
+
+// C = beta*C + bias (the seed the split-K partial sums are added to)
+__global__ void __launch_bounds__(256)
+seed_matrix_kernel(float* __restrict__ C, int M, int N, int ldc, float beta, const float* __restrict__ bias) {
+  const int64_t n = (int64_t)M * N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int col = (int)(i % N);
+    float* c = C + (i / N) * ldc + col;
+    float v = beta == 0.f ? 0.f : beta * (*c);
+    if (bias) v += bias[col];
+    *c = v;
+  }
+}
+
+static int gemm_skinny(int transb, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
+                       int ldb, float beta, float* C, int ldc, const float* bias, cudaStream_t stream) {
+  const int ntiles = cdiv(N, SN);
+  int splits = cdiv(2 * num_sms(), ntiles);
+  if (splits > cdiv(K, SK)) splits = cdiv(K, SK);
+  if (splits < 1) splits = 1;
+  const int k_chunk = cdiv(cdiv(K, splits), SK) * SK;
+  dim3 grid(ntiles, cdiv(K, k_chunk));
+  if (grid.y > 1) {
+    int blocks = cdiv((int64_t)M * N, 256); if (blocks > 1184) blocks = 1184;
+    seed_matrix_kernel<<<blocks, 256, 0, stream>>>(C, M, N, ldc, beta, bias);
+    B2_LAUNCH_CHECK();
+  }
+  if (transb) gemm_skinny_kernel<true><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, k_chunk);
+  else gemm_skinny_kernel<false><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, k_chunk);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
 int gemm_simt(int transa, int transb, int M, int N, int K, float alpha, const float* A, int lda,
               const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
               cudaStream_t stream) {
+  if (!transa && M <= SM_MAX)
+    return gemm_skinny(transb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, stream);
   dim3 grid(cdiv(N, BN), cdiv(M, BM));
   // few output tiles and a long reduction (weight gradients over millions of rows): split K
   int k_chunk = K;

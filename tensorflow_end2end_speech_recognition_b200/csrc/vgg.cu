@@ -393,3 +393,21 @@ extern "C" int b2_vgg_frontend_backward(const b2_vgg_desc* d, const b2_vgg_param
   if ((rc = conv_wgrad(b.P[0], g0, 3, 64, w.Da, gr->conv_w[0], stream))) return rc;
   return B2_OK;
 }
+
+// ReLU + tf.nn.dropout as one in-place pass / its backward; also the epilogue of the CTC model's
+// bottleneck layer (models/ctc/ctc.py:200-213).
+extern "C" int b2_relu_dropout_forward(float* x, int64_t n, float keep_prob, uint64_t seed, b2_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B2_CHECK_ARG(x && n > 0 && keep_prob > 0.f && keep_prob <= 1.f, "b2_relu_dropout_forward: bad argument");
+  vgg_fc_epi_kernel<<<ew_blocks(n), 256, 0, stream>>>(x, n, keep_prob, seed);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+extern "C" int b2_relu_dropout_backward(const float* d_out, const float* out, int64_t n, float keep_prob,
+                                        float* d_in, b2_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B2_CHECK_ARG(d_out && out && d_in && n > 0 && keep_prob > 0.f && keep_prob <= 1.f, "b2_relu_dropout_backward: bad argument");
+  vgg_fc_epi_bwd_kernel<<<ew_blocks(n), 256, 0, stream>>>(d_out, out, n, keep_prob, d_in);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}

@@ -287,7 +287,7 @@ class AttentionSeq2Seq(ModelBase):
     @graph_op(name="compute_ler")
     def compute_ler(self, labels_true, labels_pred):
         """mean_b edit_distance(pred_b, true_b) / len(true_b)  (:701-724); sparse triples or lists"""
-        from ..ctc.ctc import _edit_distance
+        from ..ctc.ctc import ler_from_lists
         from ...utils.io.labels.sparsetensor import sparse_to_label_lists
 
         def lists(x):
@@ -297,4 +297,4 @@ class AttentionSeq2Seq(ModelBase):
                 return sparse_to_label_lists(x, int(np.asarray(x[2])[0]))
             return [list(r) for r in x]
         t, p = lists(labels_true), lists(labels_pred)
-        return float(np.mean([_edit_distance(h, r) / float(len(r)) for h, r in zip(p, t)]))
+        return ler_from_lists(p, t, self.device)

@@ -47,8 +47,6 @@ class CTC(ModelBase):
         if clip_grad_norm is not None:
             assert float(clip_grad_norm) > 0, "clip_grad_norm must be larger than 0."
         assert float(weight_decay) >= 0, "weight_decay must not be a negative value."
-        if bottleneck_dim not in (None, 0):
-            raise NotImplementedError("bottleneck_dim is not built yet (reference configs use 0)")
 
         self.encoder_type = encoder_type
         self.input_size = input_size
@@ -91,8 +89,13 @@ class CTC(ModelBase):
 
         rng = np.random.RandomState(seed)
         named = self.encoder.create_variables(input_size * num_stack * splice, rng)
-        named.append(("output/weights", _truncated_normal(rng, (2 * num_units, self.num_classes),
-                                                          parameter_init)))
+        out_in = 2 * num_units
+        if self.bottleneck_dim not in (None, 0):                       # ctc.py:200-209
+            named.append(("bottleneck/weights", _truncated_normal(rng, (out_in, int(self.bottleneck_dim)),
+                                                                  parameter_init)))
+            named.append(("bottleneck/biases", np.zeros(int(self.bottleneck_dim), np.float32)))
+            out_in = int(self.bottleneck_dim)
+        named.append(("output/weights", _truncated_normal(rng, (out_in, self.num_classes), parameter_init)))
         named.append(("output/biases", np.zeros(self.num_classes, np.float32)))
         self._allocate_variables(named, self.device)
         self._step = 0
@@ -136,7 +139,16 @@ class CTC(ModelBase):
                                         variables=self.variables, dropout_seed=self._step)
         self.encoder_outputs = enc
         prec = ops.PREC_BF16 if self.precision == "bf16" else ops.PREC_FP32
-        logits2d = ops.gemm(enc.view(T * B, -1), self.variables["output/weights"], False, False,
+        feat = enc.view(T * B, -1)
+        self._bneck = None
+        if self.bottleneck_dim not in (None, 0):
+            # fully connected + ReLU, then dropout on the hidden-output connection (ctc.py:200-213)
+            feat = ops.gemm(feat, self.variables["bottleneck/weights"], False, False,
+                            self.variables["bottleneck/biases"], prec)
+            ops.relu_dropout_(feat, float(keep_prob), self._step * 7919 + 5)
+            self._bneck = (feat, float(keep_prob))
+        self._head_in = feat
+        logits2d = ops.gemm(feat, self.variables["output/weights"], False, False,
                             self.variables["output/biases"], prec)
         return logits2d.view(T, B, self.num_classes)
 
@@ -183,9 +195,15 @@ class CTC(ModelBase):
         prec = ops.PREC_BF16 if self.precision == "bf16" else ops.PREC_FP32
         enc2d = self.encoder_outputs.view(T * B, -1)
         dl2d = dlogits.view(T * B, self.num_classes)
-        ops.gemm(enc2d, dl2d, True, False, None, prec, out=self.grads["output/weights"], beta=1.0)
+        ops.gemm(self._head_in, dl2d, True, False, None, prec, out=self.grads["output/weights"], beta=1.0)
         ops.colsum(dl2d, out=self.grads["output/biases"], accumulate=True)
         denc = ops.gemm(dl2d, self.variables["output/weights"], False, True, None, prec)
+        if self._bneck is not None:
+            feat, kp = self._bneck
+            dz = ops.relu_dropout_backward(denc, feat, kp)
+            ops.gemm(enc2d, dz, True, False, None, prec, out=self.grads["bottleneck/weights"], beta=1.0)
+            ops.colsum(dz, out=self.grads["bottleneck/biases"], accumulate=True)
+            denc = ops.gemm(dz, self.variables["bottleneck/weights"], False, True, None, prec)
         self.encoder.backward(denc.view(T, B, -1), self.variables, self.grads)
         if self.weight_decay > 0:
             ops.axpy_multi(self._decay_params, self._decay_grads, float(self.weight_decay))
@@ -227,10 +245,19 @@ class CTC(ModelBase):
         hyp = sparse_to_label_lists(decode_op, B)
         ref = sparse_to_label_lists(labels, B) if not isinstance(labels, list) or (
             len(labels) == 3 and hasattr(labels[0], "ndim")) else labels
-        return float(np.mean([_edit_distance(h, r) / float(len(r)) for h, r in zip(hyp, ref)]))
+        return ler_from_lists(hyp, ref, self.device)
+
+
+def ler_from_lists(hyp, ref, device):
+    """mean_b edit_distance / len(ref_b), distances from b2_edit_distance (tf.edit_distance, normalize=True)"""
+    d = ops.edit_distance(hyp, ref, device).astype(np.float64)
+    n = np.asarray([len(r) for r in ref], np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return float(np.mean(d / n))
 
 
 def _edit_distance(hyp, ref):
+    """host form, kept for the CPU-side tests of the wire formats"""
     n, m = len(hyp), len(ref)
     d = list(range(m + 1))
     for i in range(1, n + 1):

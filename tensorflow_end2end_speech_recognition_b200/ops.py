@@ -319,6 +319,39 @@ def blstm_layer_backward(desc, x, seq_len, p_fw, p_bw, dy, reserve, g_fw, g_bw, 
     return dx
 
 
+def edit_distance(hyp_lists, ref_lists, device):
+    """Levenshtein distances of paired label lists -> int32 numpy [B] (computed on the device)."""
+    lib = _lib.load()
+    B = len(hyp_lists)
+    hf, ho, _ = pack_labels(hyp_lists)
+    rf, ro, rmax = pack_labels(ref_lists)
+    dev = torch.device(device)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
+    hf_d, ho_d, rf_d, ro_d = t(hf if len(hf) else [0]), t(ho), t(rf if len(rf) else [0]), t(ro)
+    dist = torch.empty(B, dtype=torch.int32, device=dev)
+    rc = lib.b2_edit_distance(_ptr(hf_d), _ptr(ho_d), _ptr(rf_d), _ptr(ro_d), B, int(rmax), _ptr(dist), _stream())
+    _lib.check(rc, "b2_edit_distance")
+    return dist.cpu().numpy()
+
+
+def relu_dropout_(x, keep_prob=1.0, seed=0):
+    lib = _lib.load()
+    _require_cuda(x)
+    assert x.is_contiguous()
+    _lib.check(lib.b2_relu_dropout_forward(_ptr(x), x.numel(), float(keep_prob), int(seed), _stream()),
+               "b2_relu_dropout_forward")
+    return x
+
+
+def relu_dropout_backward(d_out, out, keep_prob=1.0):
+    lib = _lib.load()
+    _require_cuda(d_out, out)
+    d_in = torch.empty_like(out)
+    _lib.check(lib.b2_relu_dropout_backward(_ptr(d_out.contiguous()), _ptr(out), out.numel(), float(keep_prob),
+                                            _ptr(d_in), _stream()), "b2_relu_dropout_backward")
+    return d_in
+
+
 # ------------------------------------------------------------------ VGG front-end
 VGG_CONVS = ("VGG1/conv1", "VGG1/conv2", "VGG2/conv1", "VGG2/conv2")
 

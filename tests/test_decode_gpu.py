@@ -85,3 +85,30 @@ def test_beam_search_random_vs_oracle(cuda, T, B, C, beam, peaky):
     ref, rsc = odec.beam_search_decode(p, seq, C - 1, beam)
     assert labs == ref
     np.testing.assert_allclose(sc, np.asarray(rsc), rtol=1e-5, atol=1e-4)
+
+
+def test_edit_distance_kernel_bit_exact(cuda):
+    """b2_edit_distance vs the textbook DP on random pairs, incl. empty / long / identical rows."""
+    from tensorflow_end2end_speech_recognition_b200 import ops
+
+    def lev(a, b):
+        d = list(range(len(b) + 1))
+        for i in range(1, len(a) + 1):
+            prev, d[0] = d[0], i
+            for j in range(1, len(b) + 1):
+                cur = d[j]
+                d[j] = min(d[j] + 1, d[j - 1] + 1, prev + (a[i - 1] != b[j - 1]))
+                prev = cur
+        return d[len(b)]
+    rng = np.random.RandomState(0)
+    hyp, ref = [], []
+    for n, m in [(0, 5), (5, 0), (1, 1), (7, 7), (33, 31), (64, 65), (100, 250), (250, 100), (3, 40), (32, 32)]:
+        hyp.append(list(rng.randint(0, 4, n)))
+        ref.append(list(rng.randint(0, 4, m)))
+    hyp.append(list(range(50))); ref.append(list(range(50)))
+    for _ in range(20):
+        hyp.append(list(rng.randint(0, 28, int(rng.randint(0, 120)))))
+        ref.append(list(rng.randint(0, 28, int(rng.randint(1, 120)))))
+    got = ops.edit_distance(hyp, ref, cuda)
+    want = np.array([lev(a, b) for a, b in zip(hyp, ref)])
+    assert np.array_equal(got, want)

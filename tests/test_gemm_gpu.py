@@ -80,3 +80,25 @@ def test_bf16_linearity_large(cuda):
     # spot-check rows against fp64
     ref = x1[:4].double().cpu() @ W.double().cpu().T
     np.testing.assert_allclose(y1[:4].cpu().double().numpy(), ref.numpy(), rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("M", [1, 8, 13, 32])
+@pytest.mark.parametrize("transb", [False, True])
+def test_skinny_fp32_gemm(cuda, M, transb):
+    """M <= 32 takes the split-K skinny kernel (decoder-step products); any N/K, bias, beta, strides."""
+    from tensorflow_end2end_speech_recognition_b200 import ops
+    rng = np.random.RandomState(M + 7 * transb)
+    for N, K in [(1024, 1344), (30, 256), (77, 100), (1344, 1024), (64, 64)]:
+        A = rng.randn(M, K + 3).astype(np.float32)[:, :K]
+        Bm = rng.randn(N, K).astype(np.float32) if transb else rng.randn(K, N).astype(np.float32)
+        bias = rng.randn(N).astype(np.float32)
+        C0 = rng.randn(M, N).astype(np.float32)
+        At = torch.tensor(np.ascontiguousarray(rng.randn(M, K + 3).astype(np.float32)), device=cuda)
+        At[:, :K] = torch.tensor(A, device=cuda)
+        Av = At[:, :K]                                      # strided rows
+        out = torch.tensor(C0, device=cuda)
+        ops.gemm(Av, torch.tensor(Bm, device=cuda), False, transb, torch.tensor(bias, device=cuda), out=out, beta=1.0)
+        ref = A.astype(np.float64) @ (Bm.T if transb else Bm).astype(np.float64) + bias + C0
+        np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-4, atol=1e-4 * np.sqrt(K))
+        out2 = ops.gemm(Av, torch.tensor(Bm, device=cuda), False, transb)
+        np.testing.assert_allclose(out2.cpu().numpy(), ref - bias - C0, rtol=1e-4, atol=1e-4 * np.sqrt(K))

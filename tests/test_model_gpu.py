@@ -157,3 +157,27 @@ def test_weight_decay_loss_and_gradient(cuda):
             reg += 0.5 * np.sum(w * w)
             np.testing.assert_allclose(v1.grad.cpu().numpy(), v0.grad.cpu().numpy() + wd * w, rtol=1e-5, atol=1e-6)
     assert abs(float(l1) - (float(l0) + wd * reg)) < 1e-4 * abs(float(l1))
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 3e-2)])
+def test_bottleneck_layer(cuda, precision, tol):
+    """bottleneck FC + ReLU (+ dropout) between encoder and output layer (ctc.py:200-213)"""
+    rng = np.random.RandomState(11)
+    B, T, D, H, L, C = 5, 32, 24, 32, 2, 9
+    model = build(cuda, precision, D, H, L, C, bottleneck_dim=16)
+    assert model.variables["bottleneck/weights"].shape == (2 * H, 16)
+    assert model.variables["output/weights"].shape == (16, C + 1)
+    x, seq, labels = make_batch(rng, B, T, D, C, 3, 9)
+    loss, logits = model.compute_loss(x, labels, seq, keep_prob=1.0)
+    model._backward()
+    torch.cuda.synchronize()
+    vs = {v.name: v.tensor.cpu().numpy() for v in model.trainable_variables()}
+    tr = omodel.OracleTrainer(vs, L, clip_grad_norm=None)
+    l_ref, logits_ref, g_ref = tr.loss_and_grads(x, seq, labels)
+    assert abs(float(loss) - l_ref) <= tol * abs(l_ref)
+    for v, g in zip(model.trainable_variables(), g_ref):
+        s = max(1e-3, np.abs(g).max())
+        np.testing.assert_allclose(v.grad.cpu().numpy(), g, rtol=0, atol=5 * tol * s, err_msg=v.name)
+    # dropout on the bottleneck output changes the loss but keeps it finite
+    l2, _ = model.compute_loss(x, labels, seq, keep_prob=0.5)
+    assert np.isfinite(float(l2)) and abs(float(l2) - float(loss)) > 1e-6
