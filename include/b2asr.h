@@ -329,6 +329,24 @@ int b2_attention_decoder_backward(const b2_decoder_desc* d, const b2_decoder_par
                                   float* dc0, float* dh0, void* workspace,
                                   size_t workspace_bytes, b2_stream_t stream);
 
+/* Beam search over the attention decoder (models/attention/decoders/beam_search/
+ * beam_search_decoder.py:234-332 beam_search_step; util.py:38-95 mask_probs / normalize_score /
+ * choose_top_k; :14-26 gather_tree).  d->B utterances, each with its own beam of beam_width
+ * hypotheses (batch rows u*W + w share utterance u's enc / keys / enc_len); c0, h0 [B,Hd].
+ * Finished beams may only continue with <EOS>; scores = log_prob / ((5+len)^w / 6^w) unless the
+ * weight is 0 or 1 (the reference disables the penalty for 1); at step 0 only beam 0 is expanded.
+ * Stops when every beam of every utterance is finished (polled every poll_every steps, 0 = never)
+ * or after max_steps.  out_ids [B,W,max_steps] (<EOS> past the end), out_len / out_log_probs /
+ * out_scores [B,W]; beam 0 is the best hypothesis. */
+size_t b2_attention_decoder_beam_workspace_bytes(const b2_decoder_desc* d, int beam_width, int max_steps);
+int b2_attention_decoder_beam_search(const b2_decoder_desc* d, const b2_decoder_params* p,
+                                     const float* enc, const float* keys, const int32_t* enc_len,
+                                     const float* c0, const float* h0, int sos, int eos,
+                                     int beam_width, float length_penalty_weight, int max_steps,
+                                     int poll_every, int32_t* out_ids, int32_t* out_len,
+                                     float* out_log_probs, float* out_scores, int32_t* steps_run,
+                                     void* workspace, size_t workspace_bytes, b2_stream_t stream);
+
 /* Levenshtein distance of B (hypothesis, reference) label-sequence pairs (tf.edit_distance as
  * compute_ler uses it, models/ctc/ctc.py:382-398): flat label arrays + [B+1] offsets, dist [B].
  * The caller divides by the reference length (normalize=True) and averages. */

@@ -139,3 +139,83 @@ def decode(p, attention_type, enc, enc_len, initial_state, sos=None, eos=None, m
     res = {k: (np.stack(v, axis=1) if v else np.zeros((B, 0))) for k, v in outs.items()}
     res["final_state"] = (c, h)
     return res
+
+
+def beam_search_decode(p, attention_type, enc, enc_len, initial_state, sos, eos, beam_width,
+                       length_penalty_weight=0.6, max_decode_length=100, sharpening_factor=1.0,
+                       sigmoid_smoothing=False, feed_previous_attention=False, cell_clip=None):
+    """Beam search for ONE utterance (enc [T,E], initial_state (c0,h0) [Hd]) following
+    ``beam_search/beam_search_decoder.py:234-332`` (beam_search_step), ``util.py:38-95``
+    (mask_probs with float32.min, normalize_score -- disabled for weight None / 1 --, top-k with the
+    lower flat index first among equals) and ``util.py:14-26`` (gather_tree).  At time 0 only beam 0 is
+    expanded.  The loop ends when every beam is finished or at ``max_decode_length``.
+    Returns dict(ids [W,L], lengths [W], log_probs [W], scores [W], min_margin): ``min_margin`` is the
+    smallest score gap between the last kept and the first rejected candidate over all steps (how
+    close the search came to a tie)."""
+    from .attention import FLOAT32_MIN
+    W = beam_width
+    enc = np.asarray(enc, np.float64)[None].repeat(W, axis=0)            # the beam is the batch
+    T, E = enc.shape[1], enc.shape[2]
+    lens = np.full(W, int(enc_len))
+    emb = np.asarray(p["W_embedding"], np.float64)
+    w_av = np.asarray(p["attentional_vector/weights"], np.float64)
+    w_o = np.asarray(p["output_layer/weights"], np.float64)
+    b_o = np.asarray(p["output_layer/biases"], np.float64)
+    C = w_o.shape[1]
+    c = np.tile(np.asarray(initial_state[0], np.float64)[None], (W, 1))
+    h = np.tile(np.asarray(initial_state[1], np.float64)[None], (W, 1))
+    x_emb = emb[np.full(W, sos)]
+    ctx = np.zeros((W, E))
+    alpha_prev = np.zeros((W, T))
+    log_probs, finished, lengths = np.zeros(W), np.zeros(W, bool), np.zeros(W, int)
+    hist_w, hist_p = [], []
+    min_margin = np.inf
+    scores_sel = np.zeros(W)
+    for time in range(max_decode_length):
+        x = np.concatenate([x_emb, ctx], axis=1)
+        c_new, h_new = cell_step(x, c, h, p["cell"], 1.0, cell_clip)
+        alpha, ctx_new = attention_step(attention_type, enc, h_new, lens,
+                                        alpha_prev if feed_previous_attention else np.zeros((W, T)),
+                                        p["attention"], sharpening_factor, sigmoid_smoothing)
+        av = np.tanh(np.concatenate([h_new, ctx_new], axis=1) @ w_av)
+        logits = av @ w_o + b_o
+        m = logits.max(1, keepdims=True)
+        probs = logits - (m + np.log(np.exp(logits - m).sum(1, keepdims=True)))
+        fin_row = np.full(C, FLOAT32_MIN)
+        fin_row[eos] = 0.0
+        probs = np.where(finished[:, None], fin_row[None], probs)
+        total = log_probs[:, None] + probs
+        add = np.ones((W, C), int)
+        add[:, eos] = 0
+        new_len = lengths[:, None] + (~finished)[:, None].astype(int) * add
+        if length_penalty_weight is None or length_penalty_weight == 1:
+            scores = total
+        else:
+            scores = total / ((5.0 + new_len) ** length_penalty_weight / 6.0 ** length_penalty_weight)
+        flat = scores.reshape(-1) if time > 0 else scores[0]
+        order = np.argsort(-flat, kind="stable")                          # ties: lower index first
+        idx = order[:W]
+        if len(order) > W:
+            min_margin = min(min_margin, float(flat[order[W - 1]] - flat[order[W]]))
+        min_margin = min(min_margin, float(np.min(-np.diff(flat[idx]))) if W > 1 else np.inf)
+        scores_sel = flat[idx]
+        log_probs = total.reshape(-1)[idx]
+        words, parents = idx % C, idx // C
+        nf = finished[parents] | (words == eos)
+        lengths = lengths[parents] + (~nf).astype(int) * (words != eos).astype(int)
+        finished = nf
+        hist_w.append(words)
+        hist_p.append(parents)
+        c, h, ctx, alpha_prev = c_new[parents], h_new[parents], ctx_new[parents], alpha[parents]
+        x_emb = emb[words]
+        if finished.all():
+            break
+    L = len(hist_w)
+    ids = np.zeros((W, L), int)
+    for w in range(W):
+        cur = w
+        for t in range(L - 1, -1, -1):
+            ids[w, t] = hist_w[t][cur]
+            cur = hist_p[t][cur]
+    return {"ids": ids, "lengths": lengths, "log_probs": log_probs, "scores": scores_sel,
+            "min_margin": min_margin}

@@ -99,6 +99,10 @@ PROTOTYPES = {
                                           C.POINTER(C.c_int32), _p, _sz, _p]),
     "b2_attention_decoder_backward": (_i, [C.POINTER(DecoderDesc), C.POINTER(DecoderParams), _p, _p, _p, _p, _i, _i,
                                            _p, _p, C.POINTER(DecoderGrads), _p, _p, _p, _p, _p, _sz, _p]),
+    "b2_attention_decoder_beam_workspace_bytes": (_sz, [C.POINTER(DecoderDesc), _i, _i]),
+    "b2_attention_decoder_beam_search": (_i, [C.POINTER(DecoderDesc), C.POINTER(DecoderParams), _p, _p, _p, _p, _p,
+                                              _i, _i, _i, _f, _i, _i, _p, _p, _p, _p, C.POINTER(C.c_int32),
+                                              _p, _sz, _p]),
     "b2_edit_distance": (_i, [_p, _p, _p, _p, _i, _i, _p, _p]),
     "b2_relu_dropout_forward": (_i, [_p, _i64, _f, C.c_uint64, _p]),
     "b2_relu_dropout_backward": (_i, [_p, _p, _i64, _f, _p, _p]),

@@ -29,6 +29,7 @@ struct AttnArgs {
   int B, T, E, A, Kw;
   float sharpening; int sigmoid_smoothing;
   float* alpha; float* context; float* energy;
+  int rpu;                       // batch rows per utterance (beam search: beam_width rows share one enc/keys)
 };
 
 constexpr int kAttnThreads = 512;
@@ -37,9 +38,10 @@ __global__ void __launch_bounds__(kAttnThreads)
 attention_step_kernel(const AttnArgs a) {
   extern __shared__ float sm[];
   const int b = blockIdx.x;
+  const int ub = b / a.rpu;             // utterance whose encoder states this row attends to
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = kAttnThreads / 32;
   const int T = a.T, A = a.A;
-  const int len = min(a.enc_len[b], T);
+  const int len = min(a.enc_len[ub], T);
   float* s_e = sm;                       // [T] energies -> weights
   float* s_q = s_e + T;                  // [A]
   float* s_v = s_q + A;                  // [A]
@@ -81,7 +83,7 @@ attention_step_kernel(const AttnArgs a) {
   for (int t = warp; t < T; t += nwarp) {
     float e;
     if (t < len) {
-      const float* kr = a.keys ? a.keys + ((size_t)b * T + t) * A : nullptr;
+      const float* kr = a.keys ? a.keys + ((size_t)ub * T + t) * A : nullptr;
       float acc = 0.f;
       for (int i = lane; i < A; i += 32) {
         const float kv = kr ? kr[i] : 0.f;
@@ -145,16 +147,17 @@ attention_step_kernel(const AttnArgs a) {
 // features) x 8 time groups; weights past `len` are exactly 0 so padded frames are never read.
 __global__ void __launch_bounds__(512)
 attention_context_kernel(const float* __restrict__ enc, const float* __restrict__ alpha,
-                         const int* __restrict__ enc_len, int T, int E, float* __restrict__ context) {
+                         const int* __restrict__ enc_len, int T, int E, int rpu, float* __restrict__ context) {
   __shared__ float4 red[8][64];
   const int b = blockIdx.x;
+  const int ub = b / rpu;
   const int col = blockIdx.y * 64 + (threadIdx.x & 63);      // float4 column
   const int tg = threadIdx.x >> 6;
-  const int len = min(enc_len[b], T);
+  const int len = min(enc_len[ub], T);
   const int E4 = E / 4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (col < E4) {
-    const float4* encb = (const float4*)(enc + (size_t)b * T * E) + col;
+    const float4* encb = (const float4*)(enc + (size_t)ub * T * E) + col;
     const float* al = alpha + (size_t)b * T;
     int t = tg;
     for (; t + 24 < len; t += 32) {
@@ -302,6 +305,17 @@ __global__ void __launch_bounds__(256) attention_bwd_energy_kernel(const AttnBwd
 
 using namespace b2;
 
+namespace b2 {
+int attention_step_forward_rows(int mode, const float* enc, const float* keys, const float* q,
+                                const float* prev_alpha, const int32_t* enc_len,
+                                const float* conv_filter, int filter_width,
+                                const float* w_filter, const float* b_filter,
+                                const float* v_a, int B, int T, int E, int A,
+                                float sharpening_factor, int sigmoid_smoothing,
+                                float* alpha, float* context, float* energy_out, int rows_per_utt,
+                                b2_stream_t stream_);
+}
+
 extern "C" int b2_attention_step_forward(int mode, const float* enc, const float* keys, const float* q,
                                          const float* prev_alpha, const int32_t* enc_len,
                                          const float* conv_filter, int filter_width,
@@ -310,6 +324,20 @@ extern "C" int b2_attention_step_forward(int mode, const float* enc, const float
                                          float sharpening_factor, int sigmoid_smoothing,
                                          float* alpha, float* context, float* energy_out,
                                          b2_stream_t stream_) {
+  return attention_step_forward_rows(mode, enc, keys, q, prev_alpha, enc_len, conv_filter, filter_width, w_filter,
+                                     b_filter, v_a, B, T, E, A, sharpening_factor, sigmoid_smoothing, alpha,
+                                     context, energy_out, 1, stream_);
+}
+
+// B batch rows; rows_per_utt consecutive rows share one utterance's enc / keys / enc_len
+int b2::attention_step_forward_rows(int mode, const float* enc, const float* keys, const float* q,
+                                    const float* prev_alpha, const int32_t* enc_len,
+                                    const float* conv_filter, int filter_width,
+                                    const float* w_filter, const float* b_filter,
+                                    const float* v_a, int B, int T, int E, int A,
+                                    float sharpening_factor, int sigmoid_smoothing,
+                                    float* alpha, float* context, float* energy_out, int rows_per_utt,
+                                    b2_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B2_CHECK_ARG(enc && enc_len && alpha && context, "b2_attention_step_forward: null pointer");
   B2_CHECK_ARG(mode == 0 || mode == 1, "b2_attention_step_forward: mode %d", mode);
@@ -322,7 +350,7 @@ extern "C" int b2_attention_step_forward(int mode, const float* enc, const float
   a.filt = conv_filter; a.w_f = w_filter; a.b_f = b_filter; a.v_a = v_a;
   a.B = B; a.T = T; a.E = E; a.A = A; a.Kw = conv_filter ? filter_width : 0;
   a.sharpening = sharpening_factor; a.sigmoid_smoothing = sigmoid_smoothing;
-  a.alpha = alpha; a.context = context; a.energy = energy_out;
+  a.alpha = alpha; a.context = context; a.energy = energy_out; a.rpu = rows_per_utt > 0 ? rows_per_utt : 1;
   size_t smem = ((size_t)T + 3 * A + 10 * A) * 4;
   if (conv_filter) smem += ((size_t)T + filter_width + (size_t)T * 10 + (size_t)filter_width * 10) * 4;
   B2_CHECK_ARG(smem <= 200 * 1024, "b2_attention_step_forward: T=%d too long for shared memory", T);
@@ -330,7 +358,7 @@ extern "C" int b2_attention_step_forward(int mode, const float* enc, const float
   attention_step_kernel<<<B, kAttnThreads, smem, stream>>>(a);
   B2_LAUNCH_CHECK();
   dim3 cgrid(B, cdiv(E / 4, 64));
-  attention_context_kernel<<<cgrid, 512, 0, stream>>>(enc, alpha, enc_len, T, E, context);
+  attention_context_kernel<<<cgrid, 512, 0, stream>>>(enc, alpha, enc_len, T, E, a.rpu, context);
   B2_LAUNCH_CHECK();
   return B2_OK;
 }

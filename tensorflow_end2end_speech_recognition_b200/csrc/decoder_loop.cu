@@ -303,3 +303,298 @@ extern "C" int b2_attention_decoder_backward(const b2_decoder_desc* d, const b2_
                         d_enc + (size_t)b * T * E, E, nullptr, stream))) return rc;
   return B2_OK;
 }
+
+// =======================================================================================
+// Beam search over the attention decoder
+//   reference: models/attention/decoders/beam_search/beam_search_decoder.py:234-332
+//   (beam_search_step), util.py:38-95 (mask_probs, normalize_score, choose_top_k), :14-26
+//   (gather_tree_py).  The reference's wrapper (:25-232) is dead code limited to one utterance
+//   (batch = beam); here every utterance of the batch carries its own beam: batch rows
+//   r = u*W + w, the W rows of utterance u share its encoder states.
+// Per step: the greedy iteration up to the logits, then beam_step_kernel (log-softmax, finished
+// beams may only continue with <EOS>, length-normalised scores, top-W over W*C candidates -- only
+// beam 0 at time 0 --, new log-probs / lengths / finished flags, parents + words appended to the
+// history) and beam_gather_kernel (cell state, context, previous attention weights re-ordered by
+// parent; next input = [embedding(word); context; h]).  At the end the histories are walked back
+// (gather_tree).  Beam 0 is the best hypothesis (top-k output is sorted).
+// =======================================================================================
+namespace b2 {
+
+int attention_step_forward_rows(int mode, const float* enc, const float* keys, const float* q,
+                                const float* prev_alpha, const int32_t* enc_len,
+                                const float* conv_filter, int filter_width,
+                                const float* w_filter, const float* b_filter,
+                                const float* v_a, int B, int T, int E, int A,
+                                float sharpening_factor, int sigmoid_smoothing,
+                                float* alpha, float* context, float* energy_out, int rows_per_utt,
+                                b2_stream_t stream_);
+
+constexpr int kBeamMaxW = 64;
+
+struct BCand { float s; int idx; };
+__device__ __forceinline__ bool bcand_better(const BCand& a, const BCand& b) {
+  if (a.idx < 0) return false;
+  if (b.idx < 0) return true;
+  if (a.s > b.s) return true;
+  if (a.s < b.s) return false;
+  return a.idx < b.idx;                 // tf.nn.top_k: lower index first among equals
+}
+
+__global__ void __launch_bounds__(256)
+beam_step_kernel(const float* __restrict__ logits, int W, int C, int t, int eos, float lpw, int use_penalty,
+                 const float* __restrict__ lp_in, const int* __restrict__ fin_in, const int* __restrict__ len_in,
+                 float* __restrict__ lp_out, int* __restrict__ fin_out, int* __restrict__ len_out,
+                 float* __restrict__ score_out, int* __restrict__ parents, int* __restrict__ words,
+                 float* __restrict__ S_tot, float* __restrict__ S_sc, int* __restrict__ done) {
+  __shared__ BCand wbest[8];
+  __shared__ int sel[kBeamMaxW];
+  const int u = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* lg = logits + (size_t)u * W * C;
+  float* tot = S_tot + (size_t)u * W * C;
+  float* sc = S_sc + (size_t)u * W * C;
+  const float FMIN = -3.402823466e38f;
+  for (int w = warp; w < W; w += 8) {
+    const float* row = lg + (size_t)w * C;
+    float m = -INFINITY;
+    for (int c = lane; c < C; c += 32) m = fmaxf(m, row[c]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += __expf(row[c] - m);
+    s = warp_sum(s);
+    const float lse = m + __logf(s);
+    const int fin = fin_in[u * W + w];
+    const float base = lp_in[u * W + w];
+    const int len = len_in[u * W + w];
+    for (int c = lane; c < C; c += 32) {
+      float pr = row[c] - lse;
+      if (fin) pr = (c == eos) ? 0.f : FMIN;                       // mask_probs (util.py:38-68)
+      const float tp = base + pr;
+      const int nl = len + ((!fin && c != eos) ? 1 : 0);
+      float score = tp;
+      if (use_penalty) score = tp / (powf(5.f + (float)nl, lpw) / powf(6.f, lpw));   // util.py:71-95
+      tot[w * C + c] = tp;
+      sc[w * C + c] = (t == 0 && w > 0) ? __int_as_float(0x7fc00000) : score;             // time 0: beam 0 only
+    }
+  }
+  __syncthreads();
+  const int N = W * C;
+  for (int r = 0; r < W; ++r) {
+    BCand best; best.idx = -1; best.s = 0.f;
+    for (int n = tid; n < N; n += 256) {
+      const float v = sc[n];
+      if (v != v) continue;
+      BCand c; c.s = v; c.idx = n;
+      if (bcand_better(c, best)) best = c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      BCand other;
+      other.s = __shfl_xor_sync(0xffffffffu, best.s, o);
+      other.idx = __shfl_xor_sync(0xffffffffu, best.idx, o);
+      if (bcand_better(other, best)) best = other;
+    }
+    if (lane == 0) wbest[warp] = best;
+    __syncthreads();
+    if (tid == 0) {
+      BCand bb = wbest[0];
+      for (int k = 1; k < 8; ++k) if (bcand_better(wbest[k], bb)) bb = wbest[k];
+      sel[r] = bb.idx;
+      if (bb.idx >= 0) { score_out[u * W + r] = bb.s; sc[bb.idx] = __int_as_float(0x7fc00000); }
+    }
+    __syncthreads();
+  }
+  if (tid < W) {
+    const int idx = sel[tid];
+    int parent = 0, word = eos, nf = 1, nl = 0;
+    float nlp = FMIN;
+    if (idx >= 0) {
+      parent = idx / C; word = idx % C;
+      nlp = tot[idx];
+      nf = fin_in[u * W + parent] | (word == eos);
+      nl = len_in[u * W + parent] + (nf ? 0 : 1);
+    }
+    lp_out[u * W + tid] = nlp; fin_out[u * W + tid] = nf; len_out[u * W + tid] = nl;
+    parents[u * W + tid] = parent; words[u * W + tid] = word;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int all = 1;
+    for (int w = 0; w < W; ++w) all &= fin_out[u * W + w];
+    done[u] = all;
+  }
+}
+
+// row r = (u, w): state and next input re-ordered by the chosen parent
+__global__ void __launch_bounds__(256)
+beam_gather_kernel(const int* __restrict__ parents, const int* __restrict__ words, int W, int Hd, int E, int T,
+                   int emb, int C, const float* __restrict__ c_new, const float* __restrict__ h_new,
+                   const float* __restrict__ ctx, const float* __restrict__ alpha,
+                   const float* __restrict__ embedding, float* __restrict__ c_next, float* __restrict__ xh_next,
+                   float* __restrict__ alpha_next) {
+  const int r = blockIdx.x;
+  const int u = r / W;
+  const int src = u * W + parents[r];
+  const int word = words[r];
+  const int X = emb + E + Hd;
+  float* xr = xh_next + (size_t)r * X;
+  for (int i = threadIdx.x; i < Hd; i += 256) {
+    c_next[(size_t)r * Hd + i] = c_new[(size_t)src * Hd + i];
+    xr[emb + E + i] = h_new[(size_t)src * Hd + i];
+  }
+  for (int i = threadIdx.x; i < E; i += 256) xr[emb + i] = ctx[(size_t)src * E + i];
+  for (int i = threadIdx.x; i < emb; i += 256)
+    xr[i] = (word >= 0 && word < C) ? embedding[(size_t)word * emb + i] : 0.f;
+  if (alpha_next)
+    for (int i = threadIdx.x; i < T; i += 256) alpha_next[(size_t)r * T + i] = alpha[(size_t)src * T + i];
+}
+
+// xh0 / state of every beam row from the utterance's initial state
+__global__ void __launch_bounds__(256)
+beam_init_kernel(const float* __restrict__ embedding, int sos, const float* __restrict__ c0,
+                 const float* __restrict__ h0, int W, int emb, int E, int Hd, int C, float* __restrict__ xh,
+                 float* __restrict__ c_state, float* __restrict__ lp, int* __restrict__ fin, int* __restrict__ len) {
+  const int r = blockIdx.x, u = r / W;
+  const int X = emb + E + Hd;
+  float* xr = xh + (size_t)r * X;
+  for (int i = threadIdx.x; i < X; i += 256) {
+    float v = 0.f;
+    if (i < emb) v = (sos >= 0 && sos < C) ? embedding[(size_t)sos * emb + i] : 0.f;
+    else if (i >= emb + E) v = h0[(size_t)u * Hd + (i - emb - E)];
+    xr[i] = v;
+  }
+  for (int i = threadIdx.x; i < Hd; i += 256) c_state[(size_t)r * Hd + i] = c0[(size_t)u * Hd + i];
+  if (threadIdx.x == 0) { lp[r] = 0.f; fin[r] = 0; len[r] = 0; }
+}
+
+// gather_tree (util.py:14-26): walk the parent pointers back from the last step
+__global__ void beam_backtrack_kernel(const int* __restrict__ hist_words, const int* __restrict__ hist_parents,
+                                      int steps, int R, int W, int L, int eos, int* __restrict__ out_ids) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const int u = r / W;
+  int cur = r % W;
+  int* out = out_ids + (size_t)r * L;
+  for (int t = steps - 1; t >= 0; --t) {
+    out[t] = hist_words[(size_t)t * R + u * W + cur];
+    cur = hist_parents[(size_t)t * R + u * W + cur];
+  }
+  for (int t = steps; t < L; ++t) out[t] = eos;
+}
+
+struct BeamWs {
+  DecScratch s; float* xh2; float* c_state; float* c_next; float* alpha_prev;
+  float* lp[2]; int* fin[2]; int* len[2]; int* parents; int* words; int* hist_w; int* hist_p;
+  float* S_tot; float* S_sc; int* done;
+};
+static size_t beam_ws_layout(const b2_decoder_desc* d, int W, int L, void* base, BeamWs* w) {
+  b2_decoder_desc dr = *d;
+  dr.B = d->B * W;
+  const size_t R = dr.B, X = (size_t)d->emb + d->E + d->Hd;
+  size_t off = align_up(dec_scratch_layout(&dr, nullptr, nullptr), 256);
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+  const size_t o_c = take(R * d->Hd * 4), o_cn = take(R * d->Hd * 4), o_ap = take(R * d->T * 4);
+  const size_t o_lp0 = take(R * 4), o_lp1 = take(R * 4), o_f0 = take(R * 4), o_f1 = take(R * 4);
+  const size_t o_l0 = take(R * 4), o_l1 = take(R * 4), o_pa = take(R * 4), o_wd = take(R * 4);
+  const size_t o_hw = take((size_t)L * R * 4), o_hp = take((size_t)L * R * 4);
+  const size_t o_st = take(R * d->C * 4), o_ss = take(R * d->C * 4), o_dn = take((size_t)d->B * 4);
+  (void)X;
+  if (w) {
+    char* p = (char*)base;
+    dec_scratch_layout(&dr, base, &w->s);
+    w->c_state = (float*)(p + o_c); w->c_next = (float*)(p + o_cn); w->alpha_prev = (float*)(p + o_ap);
+    w->lp[0] = (float*)(p + o_lp0); w->lp[1] = (float*)(p + o_lp1);
+    w->fin[0] = (int*)(p + o_f0); w->fin[1] = (int*)(p + o_f1);
+    w->len[0] = (int*)(p + o_l0); w->len[1] = (int*)(p + o_l1);
+    w->parents = (int*)(p + o_pa); w->words = (int*)(p + o_wd);
+    w->hist_w = (int*)(p + o_hw); w->hist_p = (int*)(p + o_hp);
+    w->S_tot = (float*)(p + o_st); w->S_sc = (float*)(p + o_ss); w->done = (int*)(p + o_dn);
+  }
+  return off;
+}
+
+}  // namespace b2
+
+extern "C" size_t b2_attention_decoder_beam_workspace_bytes(const b2_decoder_desc* d, int beam_width, int max_steps) {
+  if (!d || beam_width < 1 || max_steps < 1) return 0;
+  return beam_ws_layout(d, beam_width, max_steps, nullptr, nullptr);
+}
+
+extern "C" int b2_attention_decoder_beam_search(const b2_decoder_desc* d, const b2_decoder_params* p,
+                                                const float* enc, const float* keys, const int32_t* enc_len,
+                                                const float* c0, const float* h0, int sos, int eos,
+                                                int beam_width, float length_penalty_weight, int max_steps,
+                                                int poll_every, int32_t* out_ids, int32_t* out_len,
+                                                float* out_log_probs, float* out_scores, int32_t* steps_run,
+                                                void* workspace, size_t workspace_bytes, b2_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = dec_check(d);
+  if (rc) return rc;
+  B2_CHECK_ARG(p && enc && enc_len && c0 && h0 && out_ids && out_len && out_log_probs && out_scores && workspace,
+               "b2_attention_decoder_beam_search: null pointer");
+  B2_CHECK_ARG(beam_width >= 1 && beam_width <= kBeamMaxW, "b2_attention_decoder_beam_search: beam width %d not in [1,%d]",
+               beam_width, kBeamMaxW);
+  B2_CHECK_ARG(d->C >= beam_width, "b2_attention_decoder_beam_search: beam width %d exceeds the %d classes", beam_width, d->C);
+  B2_CHECK_ARG(max_steps > 0, "b2_attention_decoder_beam_search: max_steps");
+  const int W = beam_width, Bu = d->B, R = Bu * W, L = max_steps;
+  const int T = d->T, E = d->E, Hd = d->Hd, A = d->A, emb = d->emb, C = d->C, X = emb + E + Hd;
+  BeamWs w;
+  if (workspace_bytes < beam_ws_layout(d, W, L, workspace, &w)) { set_error("b2_attention_decoder_beam_search: workspace too small"); return B2_ERR_WORKSPACE; }
+  const bool loc = d->filter_width > 0;
+  // the reference disables the penalty for weight None or 1 (util.py:88-91); 0 gives penalty 1
+  const int use_penalty = (length_penalty_weight != 1.f && length_penalty_weight != 0.f) ? 1 : 0;
+  float* xh = w.s.xh;
+  beam_init_kernel<<<R, 256, 0, stream>>>(p->embedding, sos, c0, h0, W, emb, E, Hd, C, xh, w.c_state, w.lp[0],
+                                          w.fin[0], w.len[0]);
+  B2_LAUNCH_CHECK();
+  const float* prev_alpha = nullptr;
+  int* h_done = nullptr;
+  if (poll_every > 0) B2_CUDA(cudaMallocHost(&h_done, (size_t)Bu * sizeof(int)));
+  float* c_state = w.c_state; float* c_next = w.c_next;
+  int t = 0, cur = 0;
+  for (; t < L; ++t) {
+    float* q = d->query_projected ? w.s.q : w.s.h_new;
+    float* xh_next = w.s.xh + (size_t)((t + 1) & 1) * R * X;
+    if ((rc = gemm_simt(0, 0, R, 4 * Hd, X, 1.f, xh, X, p->cell_kernel, 4 * Hd, 0.f, w.s.z, 4 * Hd, nullptr, stream))) break;
+    if ((rc = b2_lstm_cell_pointwise(w.s.z, p->cell_bias, p->w_i_diag, p->w_f_diag, p->w_o_diag, c_state, R, Hd,
+                                     d->forget_bias, d->cell_clip, w.s.c_new, w.s.h_new, stream_))) break;
+    if (d->query_projected)
+      if ((rc = gemm_simt(0, 0, R, A, Hd, 1.f, w.s.h_new, Hd, p->w_query, A, 0.f, q, A, nullptr, stream))) break;
+    if ((rc = attention_step_forward_rows(d->attention_mode, enc, keys, q, prev_alpha, enc_len,
+                                          loc ? p->conv_filter : nullptr, d->filter_width, p->w_filter, p->b_filter,
+                                          p->v_a, R, T, E, A, d->sharpening, d->sigmoid_smoothing, w.s.alpha, w.s.ctx,
+                                          nullptr, W, stream_))) break;
+    if ((rc = gemm_simt(0, 0, R, Hd, Hd, 1.f, w.s.h_new, Hd, p->w_av, Hd, 0.f, w.s.av, Hd, nullptr, stream))) break;
+    if ((rc = gemm_simt(0, 0, R, Hd, E, 1.f, w.s.ctx, E, p->w_av + (size_t)Hd * Hd, Hd, 1.f, w.s.av, Hd, nullptr, stream))) break;
+    if ((rc = b2_tanh_inplace(w.s.av, (int64_t)R * Hd, stream_))) break;
+    if ((rc = gemm_simt(0, 0, R, C, Hd, 1.f, w.s.av, Hd, p->w_out, C, 0.f, w.s.logits, C, p->b_out, stream))) break;
+    int* pa = w.hist_p + (size_t)t * R; int* wd = w.hist_w + (size_t)t * R;
+    beam_step_kernel<<<Bu, 256, 0, stream>>>(w.s.logits, W, C, t, eos, length_penalty_weight, use_penalty,
+                                             w.lp[cur], w.fin[cur], w.len[cur], w.lp[cur ^ 1], w.fin[cur ^ 1],
+                                             w.len[cur ^ 1], out_scores, pa, wd, w.S_tot, w.S_sc, w.done);
+    B2_LAUNCH_CHECK();
+    beam_gather_kernel<<<R, 256, 0, stream>>>(pa, wd, W, Hd, E, T, emb, C, w.s.c_new, w.s.h_new, w.s.ctx, w.s.alpha,
+                                              p->embedding, c_next, xh_next,
+                                              d->feed_previous_attention ? w.alpha_prev : nullptr);
+    B2_LAUNCH_CHECK();
+    { float* tmp = c_state; c_state = c_next; c_next = tmp; }
+    xh = xh_next;
+    cur ^= 1;
+    if (d->feed_previous_attention) prev_alpha = w.alpha_prev;
+    if (h_done && (t + 1) % poll_every == 0 && t + 1 < L) {
+      cudaMemcpyAsync(h_done, w.done, (size_t)Bu * sizeof(int), cudaMemcpyDeviceToHost, stream);
+      cudaStreamSynchronize(stream);
+      bool all = true;
+      for (int b = 0; b < Bu; ++b) all = all && h_done[b];
+      if (all) { ++t; break; }
+    }
+  }
+  if (h_done) cudaFreeHost(h_done);
+  if (rc) return rc;
+  const int steps = t < L ? t : L;
+  beam_backtrack_kernel<<<cdiv(R, 128), 128, 0, stream>>>(w.hist_w, w.hist_p, steps, R, W, L, eos, out_ids);
+  B2_LAUNCH_CHECK();
+  B2_CUDA(cudaMemcpyAsync(out_len, w.len[cur], (size_t)R * 4, cudaMemcpyDeviceToDevice, stream));
+  B2_CUDA(cudaMemcpyAsync(out_log_probs, w.lp[cur], (size_t)R * 4, cudaMemcpyDeviceToDevice, stream));
+  if (steps_run) *steps_run = steps;
+  return B2_OK;
+}

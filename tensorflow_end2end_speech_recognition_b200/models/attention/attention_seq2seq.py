@@ -251,6 +251,19 @@ class AttentionSeq2Seq(ModelBase):
             total_loss = total_loss + 0.5 * float(self.weight_decay) * sq.sum()
         return total_loss
 
+    def decode_beam(self, inputs, inputs_seq_len, beam_width=20, length_penalty_weight=0.6):
+        """Beam-search inference (the reference's ``_beam_search_decoder_wrapper``, :550-577, is dead
+        code limited to one utterance; here every utterance carries its own beam).
+        -> (ids [B,W,L'], lengths [B,W], log_probs [B,W], scores [B,W]); beam 0 is the best."""
+        assert isinstance(beam_width, int) and beam_width >= 1
+        inputs = self._dev(inputs, torch.float32)
+        inputs_seq_len = self._dev(inputs_seq_len, torch.int32)
+        enc = self._encode(inputs, inputs_seq_len, 1.0, is_training=False)
+        self.decoder.encoder_outputs, self.decoder.encoder_outputs_seq_len = enc.outputs, enc.seq_len
+        init = self.bridge(enc)
+        return self.decoder.beam_search(init, self.variables[_EMB], self.sos_index, self.eos_index, beam_width,
+                                        length_penalty_weight)
+
     # -------------------------------------------------------------- backward
     def _backward(self):
         assert self._ctx is not None, "train() needs a preceding compute_loss(is_training=True)"

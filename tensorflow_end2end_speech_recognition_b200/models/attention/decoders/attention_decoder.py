@@ -208,6 +208,35 @@ class AttentionDecoder(object):
                            "emb_table": emb_table, "keys": keys}
         return outs, LSTMStateTuple(c_state, h_state)
 
+    def beam_search(self, initial_state, embedding, sos_index, eos_index, beam_width, length_penalty_weight=0.6):
+        """Beam search for every utterance of the batch (reference semantics:
+        beam_search/beam_search_decoder.py:234-332, one beam per utterance instead of batch size 1).
+        -> (predicted_ids [B,W,L'] int32, lengths [B,W], log_probs [B,W], scores [B,W]); beam 0 is best."""
+        lib = _lib.load()
+        enc = self.encoder_outputs.contiguous()
+        B, T, E = enc.shape
+        dev = enc.device
+        W, L = int(beam_width), int(self.max_decode_length)
+        emb_table = embedding.contiguous()
+        keys = self.attention_layer.precompute_keys(enc)
+        desc = self._desc(B, T, E, emb_table.shape[1])
+        ps = self._param_struct(self.cell_variables, self.attention_layer.variables, self.variables, emb_table, E)
+        out_ids = torch.empty((B, W, L), dtype=torch.int32, device=dev)
+        out_len = torch.empty((B, W), dtype=torch.int32, device=dev)
+        out_lp = torch.empty((B, W), dtype=torch.float32, device=dev)
+        out_sc = torch.empty((B, W), dtype=torch.float32, device=dev)
+        nbytes = lib.b2_attention_decoder_beam_workspace_bytes(C_.byref(desc), W, L)
+        ws = ops.workspace("decoder_beam", nbytes, dev)
+        steps = C_.c_int32(0)
+        p = ops._ptr
+        rc = lib.b2_attention_decoder_beam_search(
+            C_.byref(desc), C_.byref(ps), p(enc), p(keys), p(self.encoder_outputs_seq_len),
+            p(initial_state.c.contiguous()), p(initial_state.h.contiguous()), int(sos_index), int(eos_index), W,
+            float(length_penalty_weight), L, self.poll_every, p(out_ids), p(out_len), p(out_lp), p(out_sc),
+            C_.byref(steps), p(ws), nbytes, ops._stream())
+        _lib.check(rc, "b2_attention_decoder_beam_search")
+        return out_ids[:, :, :int(steps.value)], out_len, out_lp, out_sc
+
     def _query_width(self, Hd, E):
         al = self.attention_layer
         if al.attention_type in ("bahdanau_content", "location", "hybrid", "dot_product", "luong_concat"):

@@ -149,3 +149,56 @@ def test_teacher_forced(cuda, feed_prev):
     for b in range(B):                                            # imputed past each length
         assert float(out_bm.logits[b, lab_len[b] - 1:].abs().sum()) == 0.0
     np.testing.assert_allclose(final.h.cpu().numpy(), ref["final_state"][1], rtol=2e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("atype,feed_prev,lpw", [("bahdanau_content", False, 0.6), ("location", True, 0.6),
+                                                 ("hybrid", True, 0.0), ("luong_general", False, 1.0)])
+def test_beam_search_vs_oracle(cuda, atype, feed_prev, lpw):
+    """b2_attention_decoder_beam_search (every utterance its own beam) vs the numpy restatement of
+    the reference's beam_search_step, one utterance at a time.  Utterances whose search came within
+    1e-3 of a score tie (fp32 vs fp64 could order candidates differently) are skipped; the others
+    must give identical hypotheses, lengths and (to 1e-4) log-probs / scores for every beam."""
+    B, T, H_enc, Hd, A, emb, C, W, L = 6, 30, 16, 32, 24, 12, 9, 4, 14
+    sos, eos = C - 2, C - 1
+    dec, bridge, embedding, enc_out, p, (enc, lens, fs) = build(cuda, atype, B, T, H_enc, Hd, A, emb, C, True, 21,
+                                                                 max_len=L, feed_prev=feed_prev)
+    dec.variables["output_layer/biases"][eos] += 1.0          # make <EOS> reasonably likely
+    p["output_layer/biases"] = dec.variables["output_layer/biases"].cpu().numpy()
+    st = bridge()
+    ids, lengths, log_probs, scores = dec.beam_search(st, embedding, sos, eos, W, lpw)
+    torch.cuda.synchronize()
+    ids, lengths = ids.cpu().numpy(), lengths.cpu().numpy()
+    log_probs, scores = log_probs.cpu().numpy(), scores.cpu().numpy()
+    c0, h0 = st.c.cpu().numpy(), st.h.cpu().numpy()
+    compared = 0
+    for b in range(B):
+        ref = odec.beam_search_decode(p, atype, enc[b], lens[b], (c0[b], h0[b]), sos, eos, W, lpw, L,
+                                      feed_previous_attention=feed_prev)
+        if ref["min_margin"] < 1e-3:
+            continue
+        compared += 1
+        Lr = ref["ids"].shape[1]
+        assert ids.shape[2] >= Lr
+        assert np.array_equal(ids[b, :, :Lr], ref["ids"]), (b, ids[b], ref["ids"])
+        assert np.all(ids[b, :, Lr:] == eos)
+        assert np.array_equal(lengths[b], ref["lengths"])
+        np.testing.assert_allclose(log_probs[b], ref["log_probs"], rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(scores[b], ref["scores"], rtol=1e-4, atol=1e-4)
+    assert compared >= 3
+
+
+def test_beam_width_one_equals_greedy(cuda):
+    from tensorflow_end2end_speech_recognition_b200.models.attention.decoders.helpers import GreedyEmbeddingHelper
+    B, C = 5, 9
+    sos, eos = C - 2, C - 1
+    dec, bridge, embedding, enc_out, p, _ = build(cuda, "bahdanau_content", B, 25, 16, 32, 24, 12, C, False, 31, max_len=12)
+    st = bridge()
+    helper = GreedyEmbeddingHelper(embedding, torch.full((B,), sos, dtype=torch.int32, device=cuda), eos)
+    out, _ = dec(st, helper)
+    ids, lengths, _, _ = dec.beam_search(st, embedding, sos, eos, 1, 0.0)
+    g = out.predicted_ids.cpu().numpy()
+    bm = ids[:, 0].cpu().numpy()
+    for b in range(B):
+        hit = np.where(g[b] == eos)[0]
+        n = hit[0] + 1 if len(hit) else g.shape[1]
+        assert np.array_equal(bm[b, :n], g[b, :n])
