@@ -20,6 +20,11 @@
 #include <float.h>
 
 namespace b2 {
+int gemm_skinny_batched(int M, int N, int K, const float* A, int lda, int64_t strideA, const float* B, int ldb,
+                        int64_t strideB, float* C, int ldc, int64_t strideC, int batch, cudaStream_t stream);
+}
+
+namespace b2 {
 
 struct AttnArgs {
   int mode;                      // 0 additive, 1 multiplicative
@@ -70,12 +75,20 @@ attention_step_kernel(const AttnArgs a) {
       s_pa[i] = (t >= 0 && t < T) ? a.prev_alpha[(size_t)b * T + t] : 0.f;
     }
     __syncthreads();
-    // conv features f[t][k] = sum_j pa[t + j - pl] * F[j][k]
-    for (int i = tid; i < len * 10; i += kAttnThreads) {
-      const int t = i / 10, k = i % 10;
-      float acc = 0.f;
-      for (int j = 0; j < a.Kw; ++j) acc = fmaf(s_pa[t + j], s_filt[j * 10 + k], acc);
-      s_f[i] = acc;
+    // conv features f[t][k] = sum_j pa[t + j - pl] * F[j][k]; thread = one frame, 10 accumulators
+    // (s_pa reads are stride-1 across the warp, the filter row is a broadcast)
+    for (int t = tid; t < len; t += kAttnThreads) {
+      float acc[10];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) acc[k] = 0.f;
+      for (int j = 0; j < a.Kw; ++j) {
+        const float pv = s_pa[t + j];
+        const float* fr = s_filt + j * 10;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) acc[k] = fmaf(pv, fr[k], acc[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 10; ++k) s_f[t * 10 + k] = acc[k];
     }
   }
   __syncthreads();
@@ -301,6 +314,53 @@ __global__ void __launch_bounds__(256) attention_bwd_energy_kernel(const AttnBwd
   }
 }
 
+// Beam rows of one utterance share its encoder states: stream enc[u] ONCE per group of RW rows
+// instead of once per row (20 rows x 4 MB per utterance and step otherwise).
+// grid (utterances, column tiles, row groups); thread = (float4 column, time group)
+template <int RW>
+__global__ void __launch_bounds__(512)
+attention_context_shared_kernel(const float* __restrict__ enc, const float* __restrict__ alpha,
+                                const int* __restrict__ enc_len, int T, int E, int rpu,
+                                float* __restrict__ context) {
+  __shared__ float4 red[8][64];
+  const int u = blockIdx.x;
+  const int col = blockIdx.y * 64 + (threadIdx.x & 63);
+  const int tg = threadIdx.x >> 6;
+  const int w0 = blockIdx.z * RW;
+  const int len = min(enc_len[u], T);
+  const int E4 = E / 4;
+  float4 acc[RW];
+#pragma unroll
+  for (int r = 0; r < RW; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < E4) {
+    const float4* encb = (const float4*)(enc + (size_t)u * T * E) + col;
+    const float* al = alpha + ((size_t)u * rpu + w0) * T;
+    for (int t = tg; t < len; t += 8) {
+      const float4 h = __ldg(encb + (size_t)t * E4);
+#pragma unroll
+      for (int r = 0; r < RW; ++r) {
+        const float w = (w0 + r < rpu) ? al[(size_t)r * T + t] : 0.f;
+        acc[r].x += w * h.x; acc[r].y += w * h.y; acc[r].z += w * h.z; acc[r].w += w * h.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RW; ++r) {
+    red[tg][threadIdx.x & 63] = acc[r];
+    __syncthreads();
+    if (tg == 0 && col < E4 && w0 + r < rpu) {
+      float4 s = acc[r];
+#pragma unroll
+      for (int g = 1; g < 8; ++g) {
+        const float4 o = red[g][threadIdx.x & 63];
+        s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+      }
+      ((float4*)(context + ((size_t)u * rpu + w0 + r) * E))[col] = s;
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace b2
 
 using namespace b2;
@@ -358,7 +418,19 @@ int b2::attention_step_forward_rows(int mode, const float* enc, const float* key
   attention_step_kernel<<<B, kAttnThreads, smem, stream>>>(a);
   B2_LAUNCH_CHECK();
   dim3 cgrid(B, cdiv(E / 4, 64));
-  attention_context_kernel<<<cgrid, 512, 0, stream>>>(enc, alpha, enc_len, T, E, a.rpu, context);
+  if (a.rpu > 1 && a.rpu <= 32) {
+    // beam rows of one utterance share its encoder states: context[u] = Alpha[u] [W,T] . enc[u] [T,E], one
+    // skinny product per utterance, enc streamed once (weights past enc_len are exactly 0)
+    int rc = gemm_skinny_batched(a.rpu, E, T, alpha, T, (int64_t)a.rpu * T, enc, E, (int64_t)T * E, context, E,
+                                 (int64_t)a.rpu * E, B / a.rpu, stream);
+    if (rc) return rc;
+  } else if (a.rpu > 1) {
+    constexpr int RW = 10;
+    dim3 sgrid(B / a.rpu, cdiv(E / 4, 64), cdiv(a.rpu, RW));
+    attention_context_shared_kernel<RW><<<sgrid, 512, 0, stream>>>(enc, alpha, enc_len, T, E, a.rpu, context);
+  } else {
+    attention_context_kernel<<<cgrid, 512, 0, stream>>>(enc, alpha, enc_len, T, E, a.rpu, context);
+  }
   B2_LAUNCH_CHECK();
   return B2_OK;
 }

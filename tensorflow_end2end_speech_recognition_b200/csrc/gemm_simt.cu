@@ -115,7 +115,9 @@ template <bool TB>
 __global__ void __launch_bounds__(256)
 gemm_skinny_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int lda,
                    const float* __restrict__ Bm, int ldb, float beta, float* __restrict__ C, int ldc,
-                   const float* __restrict__ bias, int k_chunk) {
+                   const float* __restrict__ bias, int k_chunk, int64_t strideA, int64_t strideB,
+                   int64_t strideC) {
+  A += blockIdx.z * strideA; Bm += blockIdx.z * strideB; C += blockIdx.z * strideC;   // batched form
   __shared__ float As[SM_MAX][SK + 1];
   __shared__ float Bs[SK][SN + 1];
   const int tid = threadIdx.x;
@@ -193,8 +195,19 @@ static int gemm_skinny(int transb, int M, int N, int K, float alpha, const float
     seed_matrix_kernel<<<blocks, 256, 0, stream>>>(C, M, N, ldc, beta, bias);
     B2_LAUNCH_CHECK();
   }
-  if (transb) gemm_skinny_kernel<true><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, k_chunk);
-  else gemm_skinny_kernel<false><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, k_chunk);
+  if (transb) gemm_skinny_kernel<true><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, k_chunk, 0, 0, 0);
+  else gemm_skinny_kernel<false><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, k_chunk, 0, 0, 0);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+// batch of independent skinny products C_i = A_i . B_i (M <= 32), one K sweep per CTA (no split-K)
+int gemm_skinny_batched(int M, int N, int K, const float* A, int lda, int64_t strideA, const float* B, int ldb,
+                        int64_t strideB, float* C, int ldc, int64_t strideC, int batch, cudaStream_t stream) {
+  if (M > SM_MAX) { set_error("gemm_skinny_batched: M=%d > %d", M, SM_MAX); return B2_ERR_INVALID; }
+  dim3 grid(cdiv(N, SN), 1, batch);
+  gemm_skinny_kernel<false><<<grid, 256, 0, stream>>>(M, N, K, 1.f, A, lda, B, ldb, 0.f, C, ldc, nullptr,
+                                                     cdiv(K, SK) * SK, strideA, strideB, strideC);
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
