@@ -14,8 +14,9 @@
 //                         luong_dot, luong_general)
 // loc[t,:] = conv1d_SAME(alpha_prev, F[k,10])[t,:] . W_filter + b_filter  (location / hybrid).
 // HBM-bound: per step it must read keys (4*B*T*A) and the encoder states (4*B*T*E) once.
-// Two launches: attention_step_kernel (one CTA per utterance: energies, mask, normalise) and
-// attention_context_kernel (B x E/256 CTAs streaming the encoder states once).
+// Three launches: attention_energy_kernel (B x T/64 CTAs: energies + mask), attention_normalise_kernel
+// (one CTA per row, in place) and attention_context_kernel (B x E/256 CTAs streaming the encoder
+// states once; one skinny GEMM per utterance when beam rows share them).
 #include "common.cuh"
 #include <float.h>
 
@@ -37,26 +38,28 @@ struct AttnArgs {
   int rpu;                       // batch rows per utterance (beam search: beam_width rows share one enc/keys)
 };
 
-constexpr int kAttnThreads = 512;
+constexpr int kAttnThreads = 256;
+constexpr int kEnergyChunk = 64;        // frames per CTA of the energy kernel
 
+// energies of kEnergyChunk frames of one batch row: grid (rows, ceil(T / chunk)).  Written (sharpened,
+// padded frames = float32.min * sharpening) into the `alpha` buffer, normalised in place afterwards.
 __global__ void __launch_bounds__(kAttnThreads)
-attention_step_kernel(const AttnArgs a) {
+attention_energy_kernel(const AttnArgs a) {
   extern __shared__ float sm[];
   const int b = blockIdx.x;
   const int ub = b / a.rpu;             // utterance whose encoder states this row attends to
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = kAttnThreads / 32;
   const int T = a.T, A = a.A;
   const int len = min(a.enc_len[ub], T);
-  float* s_e = sm;                       // [T] energies -> weights
-  float* s_q = s_e + T;                  // [A]
+  const int t0 = blockIdx.y * kEnergyChunk;
+  const int tn = min(kEnergyChunk, T - t0);
+  float* s_q = sm;                       // [A]
   float* s_v = s_q + A;                  // [A]
   float* s_bf = s_v + A;                 // [A]
-  float* s_wf = s_bf + A;                // [10*A]
-  float* s_pa = s_wf + 10 * A;           // [T + Kw] zero-padded previous weights
-  float* s_f = s_pa + (a.filt ? T + a.Kw : 0);    // [T*10] conv features
-  float* s_filt = s_f + (a.filt ? T * 10 : 0);    // [Kw*10]
-  __shared__ float s_red[32];
-
+  float* s_wf = s_bf + A;                // [10*A]            (location term with real previous weights)
+  float* s_pa = s_wf + 10 * A;           // [chunk + Kw]      zero-padded previous weights
+  float* s_f = s_pa + kEnergyChunk + a.Kw;        // [chunk*10] conv features
+  float* s_filt = s_f + kEnergyChunk * 10;        // [Kw*10]
   for (int i = tid; i < A; i += kAttnThreads) {
     s_q[i] = a.q ? a.q[(size_t)b * A + i] : 0.f;
     s_v[i] = a.v_a ? a.v_a[i] : 1.f;
@@ -66,34 +69,33 @@ attention_step_kernel(const AttnArgs a) {
   // prev_alpha == NULL with a location term: the previous weights are known to be all zero (what the
   // reference's decoder always feeds) -> conv features are 0, the term is b_filter
   const bool loc_conv = loc && a.prev_alpha != nullptr;
-  if (loc_conv) {
+  if (loc_conv && t0 < len) {
     const int pl = (a.Kw - 1) / 2;
     for (int i = tid; i < 10 * A; i += kAttnThreads) s_wf[i] = a.w_f[i];
     for (int i = tid; i < a.Kw * 10; i += kAttnThreads) s_filt[i] = a.filt[i];
-    for (int i = tid; i < T + a.Kw; i += kAttnThreads) {
-      const int t = i - pl;
+    for (int i = tid; i < kEnergyChunk + a.Kw; i += kAttnThreads) {
+      const int t = t0 + i - pl;
       s_pa[i] = (t >= 0 && t < T) ? a.prev_alpha[(size_t)b * T + t] : 0.f;
     }
     __syncthreads();
     // conv features f[t][k] = sum_j pa[t + j - pl] * F[j][k]; thread = one frame, 10 accumulators
-    // (s_pa reads are stride-1 across the warp, the filter row is a broadcast)
-    for (int t = tid; t < len; t += kAttnThreads) {
+    for (int tl = tid; tl < tn; tl += kAttnThreads) {
       float acc[10];
 #pragma unroll
       for (int k = 0; k < 10; ++k) acc[k] = 0.f;
       for (int j = 0; j < a.Kw; ++j) {
-        const float pv = s_pa[t + j];
+        const float pv = s_pa[tl + j];
         const float* fr = s_filt + j * 10;
 #pragma unroll
         for (int k = 0; k < 10; ++k) acc[k] = fmaf(pv, fr[k], acc[k]);
       }
 #pragma unroll
-      for (int k = 0; k < 10; ++k) s_f[t * 10 + k] = acc[k];
+      for (int k = 0; k < 10; ++k) s_f[tl * 10 + k] = acc[k];
     }
   }
   __syncthreads();
-  // energies: one warp per t, lanes over a
-  for (int t = warp; t < T; t += nwarp) {
+  for (int tl = warp; tl < tn; tl += nwarp) {
+    const int t = t0 + tl;
     float e;
     if (t < len) {
       const float* kr = a.keys ? a.keys + ((size_t)ub * T + t) * A : nullptr;
@@ -106,7 +108,7 @@ attention_step_kernel(const AttnArgs a) {
           if (loc_conv) {
             float l = s_bf[i];
 #pragma unroll
-            for (int k = 0; k < 10; ++k) l = fmaf(s_f[t * 10 + k], s_wf[k * A + i], l);
+            for (int k = 0; k < 10; ++k) l = fmaf(s_f[tl * 10 + k], s_wf[k * A + i], l);
             x += l;
           } else if (loc) {
             x += s_bf[i];
@@ -118,16 +120,29 @@ attention_step_kernel(const AttnArgs a) {
     } else {
       e = -FLT_MAX;                                   // tf.float32.min (attention_layer.py:84-85)
     }
-    if (lane == 0) {
-      s_e[t] = e * a.sharpening;
-      if (a.energy) a.energy[(size_t)b * T + t] = e * a.sharpening;
-    }
+    if (lane == 0) a.alpha[(size_t)b * T + t] = e * a.sharpening;
+  }
+}
+
+// one CTA per batch row: energies (in `alpha`) -> softmax or sigmoid / sum, in place
+__global__ void __launch_bounds__(512)
+attention_normalise_kernel(const AttnArgs a) {
+  extern __shared__ float s_e[];         // [T]
+  __shared__ float s_red[32];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = 16;
+  const int T = a.T;
+  const int len = min(a.enc_len[b / a.rpu], T);
+  float* al = a.alpha + (size_t)b * T;
+  for (int t = tid; t < T; t += 512) {
+    const float e = al[t];
+    s_e[t] = e;
+    if (a.energy && t < len) a.energy[(size_t)b * T + t] = e;
   }
   __syncthreads();
-  // normalise over T
   float m = -INFINITY;
   if (!a.sigmoid_smoothing) {
-    for (int t = tid; t < T; t += kAttnThreads) m = fmaxf(m, s_e[t]);
+    for (int t = tid; t < T; t += 512) m = fmaxf(m, s_e[t]);
     m = warp_max(m);
     if (lane == 0) s_red[warp] = m;
     __syncthreads();
@@ -136,7 +151,7 @@ attention_step_kernel(const AttnArgs a) {
     __syncthreads();
   }
   float sum = 0.f;
-  for (int t = tid; t < T; t += kAttnThreads) {
+  for (int t = tid; t < T; t += 512) {
     const float e = s_e[t];
     float w;
     if (a.sigmoid_smoothing) w = (t < len) ? 1.f / (1.f + __expf(-e)) : 0.f;
@@ -150,10 +165,7 @@ attention_step_kernel(const AttnArgs a) {
   sum = (lane < nwarp) ? s_red[lane] : 0.f;
   sum = warp_sum(sum);
   const float inv = 1.f / sum;
-  for (int t = tid; t < T; t += kAttnThreads) {
-    const float w = s_e[t] * inv;
-    a.alpha[(size_t)b * T + t] = w;
-  }
+  for (int t = tid; t < T; t += 512) al[t] = s_e[t] * inv;
 }
 
 // context[b, e] = sum_{t < len} alpha[b,t] * enc[b,t,e].  CTA = 64 float4 columns (256
@@ -411,14 +423,18 @@ int b2::attention_step_forward_rows(int mode, const float* enc, const float* key
   a.B = B; a.T = T; a.E = E; a.A = A; a.Kw = conv_filter ? filter_width : 0;
   a.sharpening = sharpening_factor; a.sigmoid_smoothing = sigmoid_smoothing;
   a.alpha = alpha; a.context = context; a.energy = energy_out; a.rpu = rows_per_utt > 0 ? rows_per_utt : 1;
-  size_t smem = ((size_t)T + 3 * A + 10 * A) * 4;
-  if (conv_filter) smem += ((size_t)T + filter_width + (size_t)T * 10 + (size_t)filter_width * 10) * 4;
-  B2_CHECK_ARG(smem <= 200 * 1024, "b2_attention_step_forward: T=%d too long for shared memory", T);
-  B2_CUDA(cudaFuncSetAttribute(attention_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attention_step_kernel<<<B, kAttnThreads, smem, stream>>>(a);
+  size_t smem = ((size_t)13 * A + kEnergyChunk + a.Kw + kEnergyChunk * 10 + (size_t)a.Kw * 10) * 4;
+  B2_CHECK_ARG(smem <= 200 * 1024 && (size_t)T * 4 <= 200 * 1024,
+               "b2_attention_step_forward: A=%d / T=%d too large for shared memory", A, T);
+  B2_CUDA(cudaFuncSetAttribute(attention_energy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2_CUDA(cudaFuncSetAttribute(attention_normalise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T * 4));
+  dim3 egrid(B, cdiv(T, kEnergyChunk));
+  attention_energy_kernel<<<egrid, kAttnThreads, smem, stream>>>(a);
+  B2_LAUNCH_CHECK();
+  attention_normalise_kernel<<<B, 512, (size_t)T * 4, stream>>>(a);
   B2_LAUNCH_CHECK();
   dim3 cgrid(B, cdiv(E / 4, 64));
-  if (a.rpu > 1 && a.rpu <= 32) {
+  if (a.rpu > 1 && a.rpu <= 64) {
     // beam rows of one utterance share its encoder states: context[u] = Alpha[u] [W,T] . enc[u] [T,E], one
     // skinny product per utterance, enc streamed once (weights past enc_len are exactly 0)
     int rc = gemm_skinny_batched(a.rpu, E, T, alpha, T, (int64_t)a.rpu * T, enc, E, (int64_t)T * E, context, E,

@@ -102,16 +102,16 @@ scale_matrix_kernel(float* __restrict__ C, int M, int N, int ldc, float beta) {
 int num_sms();
 
 // ---------------------------------------------------------------------------------------
-// Skinny GEMM: M <= 32 rows (one decoder step's batch).  The 128x64 tile kernel above runs such a
+// Skinny GEMM: M <= 64 rows (one decoder step's batch).  The 128x64 tile kernel above runs such a
 // product on a handful of CTAs with a serial K loop (measured 80 us for [8x1344].[1344x1024]);
 // here the work is split over N tiles x K slices so that ~2 waves of CTAs stream B once
 // (L2/HBM-bound, a few microseconds).  Tile: 64 columns x 64 k per iteration, B tile staged in
 // shared memory as Bs[k][n] whatever its storage order, thread = (column, quarter of the rows).
 // Partial sums of the K slices are added atomically (C pre-scaled by beta and seeded with the bias).
 // ---------------------------------------------------------------------------------------
-constexpr int SN = 64, SK = 64, SM_MAX = 32;
+constexpr int SN = 64, SK = 64, SM_MAX = 64;
 
-template <bool TB>
+template <bool TB, int RPT>      // RPT rows per thread: the kernel covers M <= 4*RPT
 __global__ void __launch_bounds__(256)
 gemm_skinny_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int lda,
                    const float* __restrict__ Bm, int ldb, float beta, float* __restrict__ C, int ldc,
@@ -124,9 +124,9 @@ gemm_skinny_kernel(int M, int N, int K, float alpha, const float* __restrict__ A
   const int n0 = blockIdx.x * SN;
   const int kb = blockIdx.y * k_chunk, ke = min(K, kb + k_chunk);
   const int nl = tid & 63, mg = tid >> 6;              // column within the tile, row group (rows mg, mg+4, ...)
-  float acc[SM_MAX / 4];
+  float acc[RPT];
 #pragma unroll
-  for (int i = 0; i < SM_MAX / 4; ++i) acc[i] = 0.f;
+  for (int i = 0; i < RPT; ++i) acc[i] = 0.f;
   for (int k0 = kb; k0 < ke; k0 += SK) {
     // A chunk: M x SK
     for (int e = tid; e < M * SK; e += 256) {
@@ -148,14 +148,14 @@ gemm_skinny_kernel(int M, int N, int K, float alpha, const float* __restrict__ A
     for (int k = 0; k < SK; ++k) {
       const float b = Bs[k][nl];
 #pragma unroll
-      for (int i = 0; i < SM_MAX / 4; ++i) acc[i] = fmaf(As[mg + 4 * i][k], b, acc[i]);
+      for (int i = 0; i < RPT; ++i) acc[i] = fmaf(As[mg + 4 * i][k], b, acc[i]);
     }
     __syncthreads();
   }
   const int gn = n0 + nl;
   if (gn >= N) return;
 #pragma unroll
-  for (int i = 0; i < SM_MAX / 4; ++i) {
+  for (int i = 0; i < RPT; ++i) {
     const int m = mg + 4 * i;
     if (m >= M) continue;
     float v = alpha * acc[i];
@@ -195,8 +195,10 @@ static int gemm_skinny(int transb, int M, int N, int K, float alpha, const float
     seed_matrix_kernel<<<blocks, 256, 0, stream>>>(C, M, N, ldc, beta, bias);
     B2_LAUNCH_CHECK();
   }
-  if (transb) gemm_skinny_kernel<true><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, k_chunk, 0, 0, 0);
-  else gemm_skinny_kernel<false><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, k_chunk, 0, 0, 0);
+#define B2_SKINNY(TBv, RPTv) gemm_skinny_kernel<TBv, RPTv><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, k_chunk, 0, 0, 0)
+  if (transb) { if (M <= 16) B2_SKINNY(true, 4); else if (M <= 32) B2_SKINNY(true, 8); else B2_SKINNY(true, 16); }
+  else { if (M <= 16) B2_SKINNY(false, 4); else if (M <= 32) B2_SKINNY(false, 8); else B2_SKINNY(false, 16); }
+#undef B2_SKINNY
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
@@ -206,8 +208,15 @@ int gemm_skinny_batched(int M, int N, int K, const float* A, int lda, int64_t st
                         int64_t strideB, float* C, int ldc, int64_t strideC, int batch, cudaStream_t stream) {
   if (M > SM_MAX) { set_error("gemm_skinny_batched: M=%d > %d", M, SM_MAX); return B2_ERR_INVALID; }
   dim3 grid(cdiv(N, SN), 1, batch);
-  gemm_skinny_kernel<false><<<grid, 256, 0, stream>>>(M, N, K, 1.f, A, lda, B, ldb, 0.f, C, ldc, nullptr,
-                                                     cdiv(K, SK) * SK, strideA, strideB, strideC);
+  if (M <= 16)
+    gemm_skinny_kernel<false, 4><<<grid, 256, 0, stream>>>(M, N, K, 1.f, A, lda, B, ldb, 0.f, C, ldc, nullptr,
+                                                          cdiv(K, SK) * SK, strideA, strideB, strideC);
+  else if (M <= 32)
+    gemm_skinny_kernel<false, 8><<<grid, 256, 0, stream>>>(M, N, K, 1.f, A, lda, B, ldb, 0.f, C, ldc, nullptr,
+                                                          cdiv(K, SK) * SK, strideA, strideB, strideC);
+  else
+    gemm_skinny_kernel<false, 16><<<grid, 256, 0, stream>>>(M, N, K, 1.f, A, lda, B, ldb, 0.f, C, ldc, nullptr,
+                                                           cdiv(K, SK) * SK, strideA, strideB, strideC);
   B2_LAUNCH_CHECK();
   return B2_OK;
 }

@@ -14,37 +14,57 @@
 
 namespace b2 {
 
+// The map output element o -> (frame delta, stack slot, raw feature) is the same for every output
+// frame, so each CTA builds it once in shared memory (no per-element divisions afterwards) and then
+// copies ROWS_PER_CTA output frames with it.  grid = ceil(B*Tout / ROWS_PER_CTA).
+constexpr int kRowsPerCta = 16;
+
 __global__ void __launch_bounds__(256)
 stack_splice_kernel(const float* __restrict__ raw, const int* __restrict__ raw_len, int B, int Traw, int D,
                     int S, int K, int P, int Tout, int Dout, float* __restrict__ out,
                     int* __restrict__ out_len) {
-  const int64_t total = (int64_t)B * Tout * Dout;
+  extern __shared__ int s_map[];        // [Dout] packed: bits 0..19 raw feature d, 20..25 stack slot, 26..30 delta+1.., 31 valid
+  int* s_dj = s_map + Dout;             // [Dout] frame delta (<= 0) in stacked-frame units
   const int R = P * S;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int o = (int)(idx % Dout);
-    const int j = (int)((idx / Dout) % Tout);
-    const int b = (int)(idx / ((int64_t)Dout * Tout));
+  for (int o = threadIdx.x; o < Dout; o += 256) {
+    int dj = 0, e = o, ok = 1;
+    if (P > 1) {
+      const int c = o / (R * 3), r = (o / 3) % R, k = o % 3;
+      if (r <= P - 1) { dj = r - P; e = (c * 3 + k) * S; }
+      else if (r <= P - 2 + S) { dj = -1; e = (c * 3 + k) * S + (r - P + 1); }
+      else ok = 0;
+    }
+    const int istack = (S > 1) ? e / D : 0;
+    const int d = (S > 1) ? e % D : e;
+    s_map[o] = ok ? ((istack << 20) | d) : -1;
+    s_dj[o] = dj;
+  }
+  __syncthreads();
+  const int64_t rows = (int64_t)B * Tout;
+  const int64_t row0 = (int64_t)blockIdx.x * kRowsPerCta;
+  for (int rr = 0; rr < kRowsPerCta; ++rr) {
+    const int64_t row = row0 + rr;
+    if (row >= rows) break;
+    const int b = (int)(row / Tout), j = (int)(row % Tout);
     const int len = min(raw_len[b], Traw);
     const int olen = (S == 1) ? len : (len + K - 1) / K;
-    if (o == 0 && j == 0) out_len[b] = min(olen, Tout);
-    float v = 0.f;
-    if (j < olen) {
-      int js = j, e = o;
-      bool ok = true;
-      if (P > 1) {
-        const int c = o / (R * 3), r = (o / 3) % R, k = o % 3;
-        if (r <= P - 1) { js = max(0, j + r - P); e = (c * 3 + k) * S; }
-        else if (r <= P - 2 + S) { js = max(0, j - 1); e = (c * 3 + k) * S + (r - P + 1); }
-        else ok = false;
-      }
-      if (ok) {
-        int t = js, d = e;
-        if (S > 1) { t = js * K + e / D; d = e % D; }
-        if (t < len) v = raw[((size_t)b * Traw + t) * D + d];
-      }
+    if (j == 0 && threadIdx.x == 0) out_len[b] = min(olen, Tout);
+    float* orow = out + row * Dout;
+    const float* rb = raw + (size_t)b * Traw * D;
+    if (j >= olen) {
+      for (int o = threadIdx.x; o < Dout; o += 256) orow[o] = 0.f;
+      continue;
     }
-    out[idx] = v;
+    for (int o = threadIdx.x; o < Dout; o += 256) {
+      const int m = s_map[o];
+      float v = 0.f;
+      if (m >= 0) {
+        const int js = (P > 1) ? max(0, j + s_dj[o]) : j;
+        const int t = (S > 1) ? js * K + (m >> 20) : js;
+        if (t < len) v = rb[(size_t)t * D + (m & 0xfffff)];
+      }
+      orow[o] = v;
+    }
   }
 }
 
@@ -67,11 +87,13 @@ extern "C" int b2_stack_splice(const float* raw, const int32_t* raw_len, int B, 
   B2_CHECK_ARG(num_stack == 1 || num_stack >= num_skip, "num_skip must be less than num_stack.");
   B2_CHECK_ARG(splice == 1 || D % 3 == 0, "b2_stack_splice: splicing needs a feature width divisible by 3");
   const int Dout = b2_stack_splice_out_dim(D, num_stack, splice);
-  const int64_t total = (int64_t)B * Tout * Dout;
-  int64_t blocks = (total + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  stack_splice_kernel<<<(int)blocks, 256, 0, stream>>>(raw, raw_len, B, Traw, D, num_stack, num_skip, splice,
-                                                      Tout, Dout, out, out_len);
+  B2_CHECK_ARG(D < (1 << 20) && num_stack < 2048, "b2_stack_splice: feature width / stack too large");
+  const size_t smem = (size_t)2 * Dout * sizeof(int);
+  B2_CHECK_ARG(smem <= 200 * 1024, "b2_stack_splice: output frame of %d features too wide", Dout);
+  B2_CUDA(cudaFuncSetAttribute(stack_splice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t blocks = ((int64_t)B * Tout + kRowsPerCta - 1) / kRowsPerCta;
+  stack_splice_kernel<<<(int)blocks, 256, smem, stream>>>(raw, raw_len, B, Traw, D, num_stack, num_skip, splice,
+                                                         Tout, Dout, out, out_len);
   B2_LAUNCH_CHECK();
   return B2_OK;
 }

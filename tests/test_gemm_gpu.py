@@ -82,10 +82,10 @@ def test_bf16_linearity_large(cuda):
     np.testing.assert_allclose(y1[:4].cpu().double().numpy(), ref.numpy(), rtol=1e-5, atol=1e-4)
 
 
-@pytest.mark.parametrize("M", [1, 8, 13, 32])
+@pytest.mark.parametrize("M", [1, 8, 13, 32, 50, 64])
 @pytest.mark.parametrize("transb", [False, True])
 def test_skinny_fp32_gemm(cuda, M, transb):
-    """M <= 32 takes the split-K skinny kernel (decoder-step products); any N/K, bias, beta, strides."""
+    """M <= 64 takes the split-K skinny kernel (decoder-step products); any N/K, bias, beta, strides."""
     from tensorflow_end2end_speech_recognition_b200 import ops
     rng = np.random.RandomState(M + 7 * transb)
     for N, K in [(1024, 1344), (30, 256), (77, 100), (1344, 1024), (64, 64)]:
