@@ -20,6 +20,14 @@ namespace b2 {
 
 constexpr int kWarpsPerBlock = 8;
 
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 ctc_lse_kernel(const float* __restrict__ logits, const int* __restrict__ seq_len,
                int T, int B, int C, float* __restrict__ lse) {
@@ -124,27 +132,42 @@ ctc_alpha_beta_kernel(const float* __restrict__ logits, const float* __restrict_
   __shared__ float s_shift;
   double offset_sum = 0.0;           // meaningful in thread 0 only
 
-  // prefetch ring for the emission gather: RAW loads only -- subtracting lse at refill time would
-  // make the thread wait for the loads right there (45 % of the kernel in the first profile)
+  // prefetch ring for the emission gather.  A register ring fed by ld.global does not work: the
+  // compiler tracks loads with 6 scoreboards, the refill issued at step i shares one with the slot
+  // consumed at step i+1, so every step waited a full memory latency (ncu: 28 % long-scoreboard on
+  // the FADD that consumes the slot, ~1000 cycles per lattice step).  cp.async groups are counted,
+  // not scoreboarded: the ring lives in shared memory, every thread copies and later reads only
+  // its own cells, `cp.async.wait_group PF-1` releases exactly the oldest slot.
   constexpr int PF = 4;
-  float xq[PF][SPT];
-  float lq[PF];
+  float* ring = smem + 2 * W;                       // [PF][SPT*NT + 32]  (+32: the row's lse, one copy per warp)
+  const int ring_stride = SPT * NT + 32;
   const int nsteps = Tb - 1;
+  // running pointers (one 64-bit add per step instead of re-deriving row*C + class every time)
+  const int64_t row_step = (int64_t)dt * B;
+  const float* lg_next[SPT];
 #pragma unroll
-  for (int j = 0; j < PF; ++j) {
-    const int i = j;
-    const int t = t0 + dt * (i + 1);
+  for (int k = 0; k < SPT; ++k) lg_next[k] = logits + ((int64_t)(t0 + dt) * B + b) * C + cls[k];
+  const float* lse_next = lse + (int64_t)(t0 + dt) * B + b;
+  const int64_t lg_stride = row_step * C;
+  int issued = 0;
+  auto issue = [&](int j) {                         // emissions of the next not-yet-issued lattice step -> slot j
+    if (issued < nsteps) {
+      float* slot = ring + (size_t)j * ring_stride;
 #pragma unroll
-    lq[j] = 0.f;
-    if (i < nsteps) lq[j] = __ldg(&lse[(int64_t)t * B + b]);
-    for (int k = 0; k < SPT; ++k) {
-      xq[j][k] = 0.f;
-      if (i < nsteps && valid[k]) {
-        const int64_t row = (int64_t)t * B + b;
-        xq[j][k] = __ldg(&logits[row * C + cls[k]]);
+      for (int k = 0; k < SPT; ++k) {
+        cp_async4(slot + k * NT + tid, lg_next[k]);
+        lg_next[k] += lg_stride;
       }
+      if ((tid & 31) == 0) cp_async4(slot + SPT * NT + (tid >> 5), lse_next);
+      lse_next += row_step;
     }
-  }
+    ++issued;
+    cp_async_commit();                              // empty groups keep the count uniform
+  };
+#pragma unroll
+  for (int j = 0; j < PF; ++j) issue(j);
+  float* out_next = out + (int64_t)(t0 + dt) * S_pad + tid;
+  const int64_t out_stride = (int64_t)dt * S_pad;
   float* prev = buf0;
   float* cur = buf1;
   for (int i0 = 0; i0 < nsteps; i0 += PF) {
@@ -152,7 +175,14 @@ ctc_alpha_beta_kernel(const float* __restrict__ logits, const float* __restrict_
     for (int j = 0; j < PF; ++j) {
       const int i = i0 + j;
       if (i < nsteps) {               // uniform across the CTA
-        const int t = t0 + dt * (i + 1);
+        cp_async_wait<PF - 1>();      // slot j has landed (this thread's own copies)
+        __syncwarp();                 // ... and lane 0's copy of the row's lse is visible to its warp
+        const float* slot = ring + (size_t)j * ring_stride;
+        const float lq = slot[SPT * NT + (tid >> 5)];     // copied by lane 0 of this warp
+        float xv[SPT];
+#pragma unroll
+        for (int k = 0; k < SPT; ++k) xv[k] = slot[k * NT + tid];
+        __syncwarp();
 #pragma unroll
         for (int k = 0; k < SPT; ++k) {
           const int s = tid + k * NT;
@@ -160,21 +190,14 @@ ctc_alpha_beta_kernel(const float* __restrict__ logits, const float* __restrict_
             const float a0 = prev[s + 2];
             const float a1 = is_beta ? prev[s + 3] : prev[s + 1];
             const float a2 = skip[k] ? (is_beta ? prev[s + 4] : prev[s]) : -INFINITY;
-            const float v = lse3_nb(a0, a1, a2) + (xq[j][k] - lq[j]);
+            const float v = lse3_nb(a0, a1, a2) + (xv[k] - lq);
             cur[s + 2] = v;
-            out[(int64_t)t * S_pad + s] = v;
+            out_next[k * NT] = v;
           }
         }
+        out_next += out_stride;
         // refill this ring slot with the emission PF steps ahead
-        const int ip = i + PF;
-        if (ip < nsteps) {
-          const int tp = t0 + dt * (ip + 1);
-          const int64_t row = (int64_t)tp * B + b;
-          lq[j] = __ldg(&lse[row]);
-#pragma unroll
-          for (int k = 0; k < SPT; ++k)
-            if (valid[k]) xq[j][k] = __ldg(&logits[row * C + cls[k]]);
-        }
+        issue(j);
         __syncthreads();
         float* tmp = prev; prev = cur; cur = tmp;
         if ((i % kNorm) == kNorm - 1) {     // uniform: renormalise the column just written
@@ -516,7 +539,7 @@ extern "C" int b2_ctc_loss_grad(const float* logits, const int32_t* labels_flat,
     int spt = 1;
     while (NT > 1024) { spt *= 2; NT = (int)align_up((size_t)cdiv(S_max, spt), 32); }
     B2_CHECK_ARG(spt <= 8, "b2_ctc_loss_grad: label length %d too long (max 4095)", max_label_len);
-    const size_t smem = (size_t)2 * (w.S_pad + 4) * sizeof(float);
+    const size_t smem = ((size_t)2 * (w.S_pad + 4) + (size_t)4 * ((size_t)spt * NT + 32)) * sizeof(float);
     dim3 grid(B, 2);
 #define LAUNCH_AB(SPT)                                                                      \
     do {                                                                                    \
