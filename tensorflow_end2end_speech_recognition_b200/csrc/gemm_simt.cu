@@ -221,6 +221,28 @@ int gemm_skinny_batched(int M, int N, int K, const float* A, int lda, int64_t st
   return B2_OK;
 }
 
+// two independent skinny products of the same shape in ONE launch (forward / backward direction of a
+// recurrence step): C_i = A_i . op(B_i), i = 0,1; C_1 must follow C_0 (C_1 == C_0 + M*ldc).  Split-K as above.
+int gemm_skinny_pair(int transb, int M, int N, int K, const float* A0, const float* A1, int lda,
+                     const float* B0, const float* B1, int ldb, float* C0, float* C1, int ldc,
+                     cudaStream_t stream) {
+  if (M > SM_MAX || C1 != C0 + (int64_t)M * ldc) { set_error("gemm_skinny_pair: bad arguments"); return B2_ERR_INVALID; }
+  const int ntiles = cdiv(N, SN);
+  int splits = cdiv(num_sms(), ntiles);            // two problems share the machine
+  if (splits > cdiv(K, SK)) splits = cdiv(K, SK);
+  if (splits < 1) splits = 1;
+  const int k_chunk = cdiv(cdiv(K, splits), SK) * SK;
+  dim3 grid(ntiles, cdiv(K, k_chunk), 2);
+  if (grid.y > 1) B2_CUDA(cudaMemsetAsync(C0, 0, (size_t)2 * M * ldc * sizeof(float), stream));
+  const int64_t sA = A1 - A0, sB = B1 - B0, sC = C1 - C0;
+#define B2_SKINNY2(TBv, RPTv) gemm_skinny_kernel<TBv, RPTv><<<grid, 256, 0, stream>>>(M, N, K, 1.f, A0, lda, B0, ldb, 0.f, C0, ldc, nullptr, k_chunk, sA, sB, sC)
+  if (transb) { if (M <= 16) B2_SKINNY2(true, 4); else if (M <= 32) B2_SKINNY2(true, 8); else B2_SKINNY2(true, 16); }
+  else { if (M <= 16) B2_SKINNY2(false, 4); else if (M <= 32) B2_SKINNY2(false, 8); else B2_SKINNY2(false, 16); }
+#undef B2_SKINNY2
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
 int gemm_simt(int transa, int transb, int M, int N, int K, float alpha, const float* A, int lda,
               const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
               cudaStream_t stream) {

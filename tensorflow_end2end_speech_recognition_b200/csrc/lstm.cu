@@ -25,6 +25,7 @@ struct Work {
   float* G;        // [T*B, 8H] gate pre-activations (fwd) / dG (bwd)
   float* hstate;   // [2 parity][2 dir][B][H]
   float* cstate;   // [2 dir][B][H]   (fwd: c ; bwd: dc)
+  float* zrec;     // [2 dir][B][4H]  recurrent pre-activations / dh of one step (wide-H path)
   __nv_bfloat16* xb;   // bf16 operand copies for the tcgen05 GEMMs
   __nv_bfloat16* wb;
   __nv_bfloat16* gb;
@@ -37,6 +38,7 @@ static size_t work_layout(const b2_lstm_desc* d, void* base, Work* w) {
   const size_t oG = take(TB * 8 * d->H * sizeof(float));
   const size_t oh = take((size_t)2 * 2 * d->B * d->H * sizeof(float));
   const size_t oc = take((size_t)2 * d->B * d->H * sizeof(float));
+  const size_t oz = take((size_t)2 * d->B * 4 * d->H * sizeof(float));
   size_t oxb = 0, owb = 0, ogb = 0;
   if (d->precision == B2_PREC_BF16) {
     const size_t din = pad8z((size_t)(d->D_in > 2 * d->H ? d->D_in : 2 * d->H));
@@ -47,6 +49,7 @@ static size_t work_layout(const b2_lstm_desc* d, void* base, Work* w) {
   if (w) {
     char* p = (char*)base;
     w->G = (float*)(p + oG); w->hstate = (float*)(p + oh); w->cstate = (float*)(p + oc);
+    w->zrec = (float*)(p + oz);
     w->xb = (__nv_bfloat16*)(p + oxb); w->wb = (__nv_bfloat16*)(p + owb);
     w->gb = (__nv_bfloat16*)(p + ogb);
   }
@@ -68,6 +71,7 @@ struct StepArgs {
   float* hstate; float* cstate;
   float* y;                         // [T,B,2H]
   float* gates; float* cs; float* hs;   // reserve (may be null when !need_backward)
+  const float* zrec;                // [2,B,4H] h_prev . Wh computed by the caller (wide-H path) or null
 };
 
 __global__ void __launch_bounds__(256)
@@ -85,6 +89,13 @@ lstm_fwd_step_kernel(const StepArgs a) {
   float* hnext = a.hstate + ((size_t)((par ^ 1) * 2 + dir) * B) * H;
   const float* Wh = a.kernel[dir] + (size_t)a.D_in * 4 * H;     // rows D_in.. are the h rows
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (a.zrec) {                      // recurrent product done by a split-K GEMM launch (H too wide for this loop)
+    if (u < H && b < B) {
+      const float* zr = a.zrec + ((size_t)dir * B + b) * 4 * H;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) acc[g] = zr[g * H + u];
+    }
+  } else
   for (int k0 = 0; k0 < H; k0 += RK) {
     // Ws[k][g*RU + uu] = Wh[k0+k][g*H + u0+uu]   (RK x 64 = 2048 elems, 8 per thread)
 #pragma unroll
@@ -159,6 +170,7 @@ struct BwdStepArgs {
   float* dG;                        // [T,B,8H]
   float* dcstate;                   // [2][B][H]
   const float* dfinal;              // [4,B,H] d(c_fw,h_fw,c_bw,h_bw) or null
+  const float* dhrec;               // [2,B,H] dz_next . Wh^T computed by the caller (wide-H path) or null
 };
 
 __global__ void __launch_bounds__(256)
@@ -174,7 +186,9 @@ lstm_bwd_step_kernel(const BwdStepArgs a) {
   const int tn = dir == 0 ? t + 1 : t - 1;          // the step processed just before (in BPTT order)
   const float* Wh = a.kernel[dir] + (size_t)a.D_in * 4 * H;
   float acc = 0.f;
-  if (tn >= 0 && tn < T) {
+  if (a.dhrec) {
+    if (u < H && b < B) acc = a.dhrec[((size_t)dir * B + b) * H + u];
+  } else if (tn >= 0 && tn < T) {
     const float* dzn = a.dG + (size_t)tn * B * 8 * H + (size_t)dir * 4 * H;   // row b: + b*8H
     for (int k0 = 0; k0 < 4 * H; k0 += RK) {
 #pragma unroll
@@ -370,9 +384,20 @@ extern "C" int b2_blstm_layer_forward(const b2_lstm_desc* d, const float* x, con
   }
   a.seq_len = seq_len; a.G = w.G; a.hstate = w.hstate; a.cstate = w.cstate; a.y = y;
   a.gates = r.gates; a.cs = r.cs; a.hs = r.hs;
+  // Wide layers (H > 512: the cluster-resident tcgen05 recurrence does not hold them and the serial-K
+  // loop of the step kernel takes 80 us per frame at H=1024): the recurrent product h_prev . Wh becomes
+  // one split-K skinny GEMM per direction and frame, the step kernel only does the gate math.
+  const bool wide = H > 512 && B <= 64;
+  a.zrec = wide ? w.zrec : nullptr;
   dim3 grid(cdiv(H, RU), cdiv(B, RB), 2);
   for (int i = 0; i < T; ++i) {
     a.step = i;
+    if (wide) {
+      const float* hprev = w.hstate + ((size_t)((i & 1) * 2) * B) * H;          // [dir][B][H], this parity
+      rc = gemm_skinny_pair(0, B, 4 * H, H, hprev, hprev + (size_t)B * H, H, P[0]->kernel + (size_t)D * 4 * H,
+                            P[1]->kernel + (size_t)D * 4 * H, 4 * H, w.zrec, w.zrec + (size_t)B * 4 * H, 4 * H, stream);
+      if (rc) return rc;
+    }
     lstm_fwd_step_kernel<<<grid, 256, 0, stream>>>(a);
   }
   count_launches(T - 1);
@@ -439,9 +464,22 @@ extern "C" int b2_blstm_layer_backward_ex(const b2_lstm_desc* d, const float* x,
   }
   a.seq_len = seq_len; a.dy = dy; a.gates = r.gates; a.cs = r.cs; a.dG = w.G; a.dcstate = w.cstate;
   a.dfinal = d_final_state;
+  const bool wide = H > 512 && B <= 64;            // see the forward pass
+  a.dhrec = wide ? w.zrec : nullptr;
   dim3 grid(cdiv(H, RU), cdiv(B, RB), 2);
   for (int i = 0; i < T; ++i) {
     a.step = i;
+    if (wide) {
+      if (i == 0) B2_CUDA(cudaMemsetAsync(w.zrec, 0, (size_t)2 * B * H * sizeof(float), stream));
+      else {
+        // the frame processed one BPTT step earlier: fw t+1 = T-i, bw t-1 = i-1
+        const float* dz_fw = w.G + (size_t)(T - i) * B * 8 * H;
+        const float* dz_bw = w.G + (size_t)(i - 1) * B * 8 * H + (size_t)4 * H;
+        rc = gemm_skinny_pair(1, B, H, 4 * H, dz_fw, dz_bw, 8 * H, P[0]->kernel + (size_t)D * 4 * H,
+                              P[1]->kernel + (size_t)D * 4 * H, 4 * H, w.zrec, w.zrec + (size_t)B * H, H, stream);
+        if (rc) return rc;
+      }
+    }
     lstm_bwd_step_kernel<<<grid, 256, 0, stream>>>(a);
   }
   count_launches(T - 1);

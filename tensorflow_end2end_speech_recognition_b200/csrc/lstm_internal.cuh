@@ -44,6 +44,9 @@ inline size_t reserve_layout(const b2_lstm_desc* d, void* base, Reserve* r) {
 int gemm_simt(int transa, int transb, int M, int N, int K, float alpha, const float* A, int lda,
               const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
               cudaStream_t stream);
+int gemm_skinny_pair(int transb, int M, int N, int K, const float* A0, const float* A1, int lda,
+                     const float* B0, const float* B1, int ldb, float* C0, float* C1, int ldc,
+                     cudaStream_t stream);
 int gemm_bf16_tc(int a_mn, int b_mn, int M, int N, int K, float alpha, const __nv_bfloat16* A,
                  int lda, const __nv_bfloat16* B, int ldb, void* C, int ldc, const float* bias,
                  int epi, int k_splits_hint, cudaStream_t stream);

@@ -74,3 +74,14 @@ def test_single_step_and_tiny_batch(cuda):
     compare(got, ref, 3e-2, 6e-2)
     got, ref = run_layer(cuda, 2, 3, 32, 32, [2, 1, 2], ops.PREC_BF16, seed=26)
     compare(got, ref, 3e-2, 6e-2)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 3e-2)])
+def test_wide_layer_per_step_gemm_path(cuda, precision, tol):
+    """H > 512 (config 4 uses 1024): recurrent product as one split-K skinny GEMM per direction and frame
+    in front of the gate-math step kernel, forward and BPTT."""
+    from tensorflow_end2end_speech_recognition_b200 import ops
+    T, B, D, H = 7, 5, 24, 576
+    prec = ops.PREC_FP32 if precision == "fp32" else ops.PREC_BF16
+    got, ref = run_layer(cuda, T, B, D, H, [7, 4, 7, 2, 6], prec, seed=29, parameter_init=0.05)
+    compare(got, ref, tol, 2 * tol)
