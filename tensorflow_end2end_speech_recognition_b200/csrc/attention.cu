@@ -21,6 +21,7 @@
 #include <float.h>
 
 namespace b2 {
+int num_sms();
 int gemm_skinny_batched(int M, int N, int K, const float* A, int lda, int64_t strideA, const float* B, int ldb,
                         int64_t strideB, float* C, int ldc, int64_t strideC, int batch, cudaStream_t stream);
 }
@@ -178,13 +179,18 @@ attention_context_kernel(const float* __restrict__ enc, const float* __restrict_
   const int ub = b / rpu;
   const int col = blockIdx.y * 64 + (threadIdx.x & 63);      // float4 column
   const int tg = threadIdx.x >> 6;
-  const int len = min(enc_len[ub], T);
+  // blockIdx.z: slice of the time axis (few rows -> more CTAs; partial sums are added atomically into
+  // a zeroed context)
+  const int nz = gridDim.z;
+  const int tchunk = ((T + nz - 1) / nz + 7) / 8 * 8;
+  const int tbeg = blockIdx.z * tchunk;
+  const int len = min(min(enc_len[ub], T), tbeg + tchunk);
   const int E4 = E / 4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (col < E4) {
     const float4* encb = (const float4*)(enc + (size_t)ub * T * E) + col;
     const float* al = alpha + (size_t)b * T;
-    int t = tg;
+    int t = tbeg + tg;
     for (; t + 24 < len; t += 32) {
       const float4 h0 = __ldg(encb + (size_t)t * E4), h1 = __ldg(encb + (size_t)(t + 8) * E4);
       const float4 h2 = __ldg(encb + (size_t)(t + 16) * E4), h3 = __ldg(encb + (size_t)(t + 24) * E4);
@@ -208,7 +214,9 @@ attention_context_kernel(const float* __restrict__ enc, const float* __restrict_
       const float4 o = red[g][threadIdx.x & 63];
       acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
     }
-    ((float4*)(context + (size_t)b * E))[col] = acc;
+    float* cp = context + (size_t)b * E + col * 4;
+    if (nz == 1) *(float4*)cp = acc;
+    else if (tbeg < len) { atomicAdd(cp, acc.x); atomicAdd(cp + 1, acc.y); atomicAdd(cp + 2, acc.z); atomicAdd(cp + 3, acc.w); }
   }
 }
 
@@ -445,6 +453,11 @@ int b2::attention_step_forward_rows(int mode, const float* enc, const float* key
     dim3 sgrid(B / a.rpu, cdiv(E / 4, 64), cdiv(a.rpu, RW));
     attention_context_shared_kernel<RW><<<sgrid, 512, 0, stream>>>(enc, alpha, enc_len, T, E, a.rpu, context);
   } else {
+    // enough CTAs to fill the machine: split the time axis when the batch is small
+    int nz = 1;
+    while ((int64_t)cgrid.x * cgrid.y * nz < 2 * num_sms() && nz < 16 && T / (nz * 2) >= 64) nz *= 2;
+    cgrid.z = nz;
+    if (nz > 1) B2_CUDA(cudaMemsetAsync(context, 0, (size_t)B * E * sizeof(float), stream));
     attention_context_kernel<<<cgrid, 512, 0, stream>>>(enc, alpha, enc_len, T, E, a.rpu, context);
   }
   B2_LAUNCH_CHECK();
