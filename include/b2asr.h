@@ -144,6 +144,10 @@ typedef struct {
   uint64_t dropout_seed;      /* counter-hash seed for the mask              */
   int32_t precision;          /* B2_PREC_*                                   */
   int32_t need_backward;      /* 1: fill `reserve` for b2_blstm_layer_backward */
+  int32_t num_proj;           /* LSTMCell num_proj (blstm.py:215-228): 0 = none; P > 0: the emitted and
+                                 recurrent h is (o*tanh(c)) . projection [H,P]; kernel is [(D_in+P),4H],
+                                 y [T,B,2P], final_state = c_fw [B,H], h_fw [B,P], c_bw [B,H], h_bw [B,P];
+                                 fp32 CUDA-core path whatever `precision` says */
 } b2_lstm_desc;
 
 /* parameters of one direction, TF LSTMBlockCell layout:
@@ -154,6 +158,7 @@ typedef struct {
   const float* w_i_diag;    /* [H] or NULL */
   const float* w_f_diag;
   const float* w_o_diag;
+  const float* projection;  /* [H, num_proj] or NULL */
 } b2_lstm_params;
 
 typedef struct {
@@ -162,6 +167,7 @@ typedef struct {
   float* w_i_diag;
   float* w_f_diag;
   float* w_o_diag;
+  float* projection;
 } b2_lstm_grads;
 
 size_t b2_blstm_reserve_bytes(const b2_lstm_desc* d);

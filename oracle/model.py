@@ -24,6 +24,8 @@ def layers_from_variables(variables, num_layers, use_peephole=True):
             if use_peephole:
                 for k in ("w_i_diag", "w_f_diag", "w_o_diag"):
                     p[k] = variables[scope + k]
+            if scope + "projection/kernel" in variables:                 # LSTMCell(num_proj), blstm.py:215-228
+                p["projection"] = variables[scope + "projection/kernel"]
             layer[d] = p
         layers.append(layer)
     return layers

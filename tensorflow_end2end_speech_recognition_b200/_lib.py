@@ -19,12 +19,12 @@ class LstmDesc(C.Structure):
     _fields_ = [("T", C.c_int32), ("B", C.c_int32), ("D_in", C.c_int32), ("H", C.c_int32),
                 ("use_peephole", C.c_int32), ("forget_bias", C.c_float), ("cell_clip", C.c_float),
                 ("keep_prob", C.c_float), ("dropout_seed", C.c_uint64), ("precision", C.c_int32),
-                ("need_backward", C.c_int32)]
+                ("need_backward", C.c_int32), ("num_proj", C.c_int32)]
 
 
 class LstmParams(C.Structure):
     _fields_ = [("kernel", C.c_void_p), ("bias", C.c_void_p), ("w_i_diag", C.c_void_p),
-                ("w_f_diag", C.c_void_p), ("w_o_diag", C.c_void_p)]
+                ("w_f_diag", C.c_void_p), ("w_o_diag", C.c_void_p), ("projection", C.c_void_p)]
 
 
 LstmGrads = LstmParams  # same layout (non-const pointers)

@@ -26,6 +26,9 @@ struct Work {
   float* hstate;   // [2 parity][2 dir][B][H]
   float* cstate;   // [2 dir][B][H]   (fwd: c ; bwd: dc)
   float* zrec;     // [2 dir][B][4H]  recurrent pre-activations / dh of one step (wide-H path)
+  float* mcur;     // [2 dir][B][H]   projection mode: o*tanh(c) of the frame (fwd) / d(o*tanh(c)) (bwd)
+  float* hpnew;    // [2 dir][B][P]   projection mode: projected h of the frame (fwd) / its gradient (bwd)
+  float* dhp_all;  // [T*B][2P]       projection mode, backward: d(projected h) of every frame
   __nv_bfloat16* xb;   // bf16 operand copies for the tcgen05 GEMMs
   __nv_bfloat16* wb;
   __nv_bfloat16* gb;
@@ -36,9 +39,13 @@ static size_t work_layout(const b2_lstm_desc* d, void* base, Work* w) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
   const size_t oG = take(TB * 8 * d->H * sizeof(float));
-  const size_t oh = take((size_t)2 * 2 * d->B * d->H * sizeof(float));
+  const size_t Pw = d->num_proj > 0 ? (size_t)d->num_proj : 0;
+  const size_t oh = take((size_t)2 * 2 * d->B * (d->H > (int)Pw ? d->H : Pw) * sizeof(float));
   const size_t oc = take((size_t)2 * d->B * d->H * sizeof(float));
   const size_t oz = take((size_t)2 * d->B * 4 * d->H * sizeof(float));
+  const size_t om = Pw ? take((size_t)2 * d->B * d->H * sizeof(float)) : 0;
+  const size_t ohn = Pw ? take((size_t)2 * d->B * Pw * sizeof(float)) : 0;
+  const size_t oda = Pw ? take(TB * 2 * Pw * sizeof(float)) : 0;
   size_t oxb = 0, owb = 0, ogb = 0;
   if (d->precision == B2_PREC_BF16) {
     const size_t din = pad8z((size_t)(d->D_in > 2 * d->H ? d->D_in : 2 * d->H));
@@ -50,6 +57,8 @@ static size_t work_layout(const b2_lstm_desc* d, void* base, Work* w) {
     char* p = (char*)base;
     w->G = (float*)(p + oG); w->hstate = (float*)(p + oh); w->cstate = (float*)(p + oc);
     w->zrec = (float*)(p + oz);
+    w->mcur = Pw ? (float*)(p + om) : nullptr; w->hpnew = Pw ? (float*)(p + ohn) : nullptr;
+    w->dhp_all = Pw ? (float*)(p + oda) : nullptr;
     w->xb = (__nv_bfloat16*)(p + oxb); w->wb = (__nv_bfloat16*)(p + owb);
     w->gb = (__nv_bfloat16*)(p + ogb);
   }
@@ -72,6 +81,8 @@ struct StepArgs {
   float* y;                         // [T,B,2H]
   float* gates; float* cs; float* hs;   // reserve (may be null when !need_backward)
   const float* zrec;                // [2,B,4H] h_prev . Wh computed by the caller (wide-H path) or null
+  float* mout;                      // [2,B,H] projection mode: o*tanh(c) of this frame (y / h state are written
+                                    // by proj_finalize_kernel after the projection GEMM); null otherwise
 };
 
 __global__ void __launch_bounds__(256)
@@ -129,7 +140,7 @@ lstm_fwd_step_kernel(const StepArgs a) {
   const size_t cidx = ((size_t)dir * B + b) * H + u;
   const bool active = t < a.seq_len[b];
   const float c_prev = a.cstate[cidx];
-  const float h_prev = hprev[(size_t)b * H + u];
+  const float h_prev = a.mout ? 0.f : hprev[(size_t)b * H + u];
   const size_t row = (size_t)t * B + b;
   float h_out = 0.f, c_new = c_prev, h_state = h_prev;
   float gi = 0.f, gg = 0.f, gf = 0.f, go = 0.f;
@@ -147,12 +158,16 @@ lstm_fwd_step_kernel(const StepArgs a) {
     h_state = h_out;
   }
   a.cstate[cidx] = c_new;
-  hnext[(size_t)b * H + u] = h_state;
-  const size_t oidx = row * 2 * H + (size_t)dir * H + u;
-  float yv = h_out;
-  if (a.keep_prob < 1.f && active)
-    yv = dropout_keep(a.seed, oidx, a.keep_prob) ? h_out / a.keep_prob : 0.f;
-  a.y[oidx] = yv;
+  if (a.mout) {
+    a.mout[cidx] = h_out;
+  } else {
+    hnext[(size_t)b * H + u] = h_state;
+    const size_t oidx = row * 2 * H + (size_t)dir * H + u;
+    float yv = h_out;
+    if (a.keep_prob < 1.f && active)
+      yv = dropout_keep(a.seed, oidx, a.keep_prob) ? h_out / a.keep_prob : 0.f;
+    a.y[oidx] = yv;
+  }
   if (a.gates) {
     *(float4*)(a.gates + ((row * 2 + dir) * H + u) * 4) = make_float4(gi, gg, gf, go);
     a.cs[(row * 2 + dir) * H + u] = c_new;
@@ -171,6 +186,8 @@ struct BwdStepArgs {
   float* dcstate;                   // [2][B][H]
   const float* dfinal;              // [4,B,H] d(c_fw,h_fw,c_bw,h_bw) or null
   const float* dhrec;               // [2,B,H] dz_next . Wh^T computed by the caller (wide-H path) or null
+  int proj;                         // projection mode: dhrec is the TOTAL dh of this frame (dy and the recurrent
+                                    // part went through the projection in the caller)
 };
 
 __global__ void __launch_bounds__(256)
@@ -224,10 +241,15 @@ lstm_bwd_step_kernel(const BwdStepArgs a) {
     dh_in = a.dfinal ? a.dfinal[((size_t)(dir * 2 + 1) * B + b) * H + u] : 0.f;
     dc_in = a.dfinal ? a.dfinal[((size_t)(dir * 2 + 0) * B + b) * H + u] : 0.f;
   }
-  const size_t oidx = row * 2 * H + (size_t)dir * H + u;
-  float dyv = a.dy[oidx];
-  if (a.keep_prob < 1.f) dyv = dropout_keep(a.seed, oidx, a.keep_prob) ? dyv / a.keep_prob : 0.f;
-  const float dh = dyv + dh_in;
+  float dh;
+  if (a.proj) {
+    dh = acc;
+  } else {
+    const size_t oidx = row * 2 * H + (size_t)dir * H + u;
+    float dyv = a.dy[oidx];
+    if (a.keep_prob < 1.f) dyv = dropout_keep(a.seed, oidx, a.keep_prob) ? dyv / a.keep_prob : 0.f;
+    dh = dyv + dh_in;
+  }
   const float4 g4 = *(const float4*)(a.gates + ((row * 2 + dir) * H + u) * 4);
   const float gi = g4.x, gg = g4.y, gf = g4.z, go = g4.w;
   const float c = a.cs[(row * 2 + dir) * H + u];
@@ -246,6 +268,61 @@ lstm_bwd_step_kernel(const BwdStepArgs a) {
   if (a.use_peephole) dc_prev += dzi * a.wi[dir][u] + dzf * a.wf[dir][u];
   a.dcstate[cidx] = dc_prev;
   dz[u] = dzi; dz[H + u] = dzg; dz[2 * H + u] = dzf; dz[3 * H + u] = dzo;
+}
+
+// ---- LSTMCell projection (num_proj): per-frame epilogue of the forward pass and prologue of BPTT
+// hp_new [2,B,P] = m . Wp (this frame).  Active rows take it, the others keep their state; y gets the
+// (dropout-scaled) emitted value, hps the emitted value before dropout.  grid over 2*B*P elements.
+__global__ void __launch_bounds__(256)
+proj_finalize_kernel(const float* __restrict__ hp_new, const float* __restrict__ hp_prev,
+                     float* __restrict__ hp_next, const int* __restrict__ seq_len, int T, int B, int P, int step,
+                     float keep_prob, unsigned long long seed, float* __restrict__ y, float* __restrict__ hps) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 2 * B * P) return;
+  const int p = idx % P, b = (idx / P) % B, dir = idx / (P * B);
+  const int t = dir == 0 ? step : T - 1 - step;
+  const bool active = t < seq_len[b];
+  const float v = hp_new[idx];
+  hp_next[idx] = active ? v : hp_prev[idx];
+  const size_t oidx = ((size_t)t * B + b) * 2 * P + (size_t)dir * P + p;
+  float yv = active ? v : 0.f;
+  if (keep_prob < 1.f && active) yv = dropout_keep(seed, oidx, keep_prob) ? v / keep_prob : 0.f;
+  y[oidx] = yv;
+  if (hps) hps[oidx] = active ? v : 0.f;
+}
+
+// d(projected h) of this BPTT frame = dropout'(dy) + recurrent part (or the final-state gradient at the
+// first active frame); written for the projection GEMM of this frame and kept for d(projection).
+__global__ void __launch_bounds__(256)
+proj_bwd_combine_kernel(const float* __restrict__ dy, const float* __restrict__ dhp_rec,
+                        const int* __restrict__ seq_len, int T, int B, int P, int step, float keep_prob,
+                        unsigned long long seed, float* __restrict__ dhp, float* __restrict__ dhp_all) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 2 * B * P) return;
+  const int p = idx % P, b = (idx / P) % B, dir = idx / (P * B);
+  const int t = dir == 0 ? T - 1 - step : step;
+  const int tn = dir == 0 ? t + 1 : t - 1;
+  const int len = seq_len[b];
+  const size_t oidx = ((size_t)t * B + b) * 2 * P + (size_t)dir * P + p;
+  float v = 0.f;
+  if (t < len) {
+    float dyv = dy[oidx];
+    if (keep_prob < 1.f) dyv = dropout_keep(seed, oidx, keep_prob) ? dyv / keep_prob : 0.f;
+    const bool nb_active = step > 0 && tn >= 0 && tn < T && tn < len;
+    v = dyv + (nb_active ? dhp_rec[idx] : 0.f);
+  }
+  dhp[idx] = v;
+  dhp_all[oidx] = v;
+}
+
+// two products of one shape (forward / backward direction): skinny pair when the batch allows
+static int pair_gemm(int transb, int M, int N, int K, const float* A0, const float* A1, int lda, const float* B0,
+                     const float* B1, int ldb, float* C0, float* C1, int ldc, cudaStream_t stream) {
+  if (M <= 64 && C1 == C0 + (size_t)M * ldc)
+    return gemm_skinny_pair(transb, M, N, K, A0, A1, lda, B0, B1, ldb, C0, C1, ldc, stream);
+  int rc = gemm_simt(0, transb, M, N, K, 1.f, A0, lda, B0, ldb, 0.f, C0, ldc, nullptr, stream);
+  if (rc) return rc;
+  return gemm_simt(0, transb, M, N, K, 1.f, A1, lda, B1, ldb, 0.f, C1, ldc, nullptr, stream);
 }
 
 // peephole gradients: dwi[u] += sum_{t,b} dz_i * c_prev ; dwf likewise ; dwo += dz_o * c
@@ -286,6 +363,142 @@ peephole_grad_kernel(const float* __restrict__ dG, const float* __restrict__ cs,
   }
 }
 
+// ---------------------------------------------------------------------------
+// LSTMCell with num_proj (models/encoders/core/blstm.py:187-255, cell equations
+// models/recurrent/layers/lstm.py:166-176): h_t = (o * tanh(c_t)) . W_proj, and it is this projected
+// h that recurs and is emitted.  fp32 CUDA-core path: per frame one skinny GEMM pair for the recurrent
+// product, the gate-math kernel, one skinny GEMM pair for the projection, one finalize kernel.
+// ---------------------------------------------------------------------------
+static int proj_forward(const b2_lstm_desc* d, const float* x, const int32_t* seq_len, const b2_lstm_params* fw,
+                        const b2_lstm_params* bw, float* y, float* final_state, void* reserve, const Work& w,
+                        cudaStream_t stream) {
+  const int T = d->T, B = d->B, D = d->D_in, H = d->H, P = d->num_proj, TB = T * B;
+  const b2_lstm_params* Pm[2] = {fw, bw};
+  B2_CHECK_ARG(fw->projection && bw->projection, "blstm_forward: num_proj without projection weights");
+  Reserve r = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (d->need_backward) reserve_layout(d, reserve, &r);
+  int rc;
+  for (int dir = 0; dir < 2; ++dir) {
+    rc = gemm_simt(0, 0, TB, 4 * H, D, 1.f, x, D, Pm[dir]->kernel, 4 * H, 0.f, w.G + (size_t)dir * 4 * H, 8 * H,
+                   Pm[dir]->bias, stream);
+    if (rc) return rc;
+  }
+  B2_CUDA(cudaMemsetAsync(w.hstate, 0, (size_t)2 * 2 * B * P * sizeof(float), stream));
+  B2_CUDA(cudaMemsetAsync(w.cstate, 0, (size_t)2 * B * H * sizeof(float), stream));
+  StepArgs a;
+  a.T = T; a.B = B; a.D_in = D; a.H = H;
+  a.use_peephole = d->use_peephole; a.forget_bias = d->forget_bias; a.cell_clip = d->cell_clip;
+  a.keep_prob = 1.f; a.seed = d->dropout_seed;            // dropout is applied after the projection
+  for (int dir = 0; dir < 2; ++dir) {
+    a.kernel[dir] = Pm[dir]->kernel; a.wi[dir] = Pm[dir]->w_i_diag; a.wf[dir] = Pm[dir]->w_f_diag;
+    a.wo[dir] = Pm[dir]->w_o_diag;
+  }
+  a.seq_len = seq_len; a.G = w.G; a.hstate = w.hstate; a.cstate = w.cstate; a.y = y;
+  a.gates = r.gates; a.cs = r.cs; a.hs = r.hs; a.zrec = w.zrec; a.mout = w.mcur;
+  dim3 grid(cdiv(H, RU), cdiv(B, RB), 2);
+  for (int i = 0; i < T; ++i) {
+    a.step = i;
+    float* hp_prev = w.hstate + (size_t)((i & 1) * 2) * B * P;          // [dir][B][P]
+    float* hp_next = w.hstate + (size_t)(((i & 1) ^ 1) * 2) * B * P;
+    rc = pair_gemm(0, B, 4 * H, P, hp_prev, hp_prev + (size_t)B * P, P, fw->kernel + (size_t)D * 4 * H,
+                   bw->kernel + (size_t)D * 4 * H, 4 * H, w.zrec, w.zrec + (size_t)B * 4 * H, 4 * H, stream);
+    if (rc) return rc;
+    lstm_fwd_step_kernel<<<grid, 256, 0, stream>>>(a);
+    rc = pair_gemm(0, B, P, H, w.mcur, w.mcur + (size_t)B * H, H, fw->projection, bw->projection, P, w.hpnew,
+                   w.hpnew + (size_t)B * P, P, stream);
+    if (rc) return rc;
+    proj_finalize_kernel<<<cdiv((int64_t)2 * B * P, 256), 256, 0, stream>>>(w.hpnew, hp_prev, hp_next, seq_len, T, B, P, i,
+                                                                           d->keep_prob, d->dropout_seed, y, r.hps);
+  }
+  count_launches(2 * T - 1);
+  B2_LAUNCH_CHECK();
+  if (final_state) {      // c_fw [B,H], h_fw [B,P], c_bw [B,H], h_bw [B,P]
+    const float* hfin = w.hstate + (size_t)((T & 1) * 2) * B * P;
+    float* o = final_state;
+    B2_CUDA(cudaMemcpyAsync(o, w.cstate, (size_t)B * H * 4, cudaMemcpyDeviceToDevice, stream)); o += (size_t)B * H;
+    B2_CUDA(cudaMemcpyAsync(o, hfin, (size_t)B * P * 4, cudaMemcpyDeviceToDevice, stream)); o += (size_t)B * P;
+    B2_CUDA(cudaMemcpyAsync(o, w.cstate + (size_t)B * H, (size_t)B * H * 4, cudaMemcpyDeviceToDevice, stream)); o += (size_t)B * H;
+    B2_CUDA(cudaMemcpyAsync(o, hfin + (size_t)B * P, (size_t)B * P * 4, cudaMemcpyDeviceToDevice, stream));
+  }
+  return B2_OK;
+}
+
+static int proj_backward(const b2_lstm_desc* d, const float* x, const int32_t* seq_len, const b2_lstm_params* fw,
+                         const b2_lstm_params* bw, const float* dy, const void* reserve, float* dx,
+                         const b2_lstm_grads* g_fw, const b2_lstm_grads* g_bw, const Work& w, cudaStream_t stream) {
+  const int T = d->T, B = d->B, D = d->D_in, H = d->H, P = d->num_proj, TB = T * B;
+  const b2_lstm_params* Pm[2] = {fw, bw};
+  const b2_lstm_grads* Gr[2] = {g_fw, g_bw};
+  B2_CHECK_ARG(fw->projection && bw->projection && g_fw->projection && g_bw->projection,
+               "blstm_backward: num_proj without projection weights / gradients");
+  Reserve r;
+  reserve_layout(d, (void*)reserve, &r);
+  int rc;
+  B2_CUDA(cudaMemsetAsync(w.cstate, 0, (size_t)2 * B * H * sizeof(float), stream));
+  BwdStepArgs a;
+  a.T = T; a.B = B; a.D_in = D; a.H = H;
+  a.use_peephole = d->use_peephole; a.cell_clip = d->cell_clip; a.keep_prob = 1.f; a.seed = d->dropout_seed;
+  for (int dir = 0; dir < 2; ++dir) {
+    a.kernel[dir] = Pm[dir]->kernel; a.wi[dir] = Pm[dir]->w_i_diag; a.wf[dir] = Pm[dir]->w_f_diag;
+    a.wo[dir] = Pm[dir]->w_o_diag;
+  }
+  a.seq_len = seq_len; a.dy = dy; a.gates = r.gates; a.cs = r.cs; a.dG = w.G; a.dcstate = w.cstate;
+  a.dfinal = nullptr; a.dhrec = w.mcur; a.proj = 1;
+  float* dhp_rec = w.zrec;                 // [2,B,P]
+  float* dhp = w.hpnew;                    // [2,B,P]
+  dim3 grid(cdiv(H, RU), cdiv(B, RB), 2);
+  for (int i = 0; i < T; ++i) {
+    a.step = i;
+    if (i > 0) {
+      const float* dz_fw = w.G + (size_t)(T - i) * B * 8 * H;
+      const float* dz_bw = w.G + (size_t)(i - 1) * B * 8 * H + (size_t)4 * H;
+      rc = pair_gemm(1, B, P, 4 * H, dz_fw, dz_bw, 8 * H, fw->kernel + (size_t)D * 4 * H,
+                     bw->kernel + (size_t)D * 4 * H, 4 * H, dhp_rec, dhp_rec + (size_t)B * P, P, stream);
+      if (rc) return rc;
+    }
+    proj_bwd_combine_kernel<<<cdiv((int64_t)2 * B * P, 256), 256, 0, stream>>>(dy, dhp_rec, seq_len, T, B, P, i, d->keep_prob,
+                                                                              d->dropout_seed, dhp, w.dhp_all);
+    rc = pair_gemm(1, B, H, P, dhp, dhp + (size_t)B * P, P, fw->projection, bw->projection, P, w.mcur,
+                   w.mcur + (size_t)B * H, H, stream);
+    if (rc) return rc;
+    lstm_bwd_step_kernel<<<grid, 256, 0, stream>>>(a);
+  }
+  count_launches(2 * T - 1);
+  B2_LAUNCH_CHECK();
+  for (int dir = 0; dir < 2; ++dir) {
+    rc = b2_colsum(w.G + (size_t)dir * 4 * H, TB, 4 * H, 8 * H, Gr[dir]->bias, 1, (b2_stream_t)stream);
+    if (rc) return rc;
+  }
+  if (d->use_peephole) {
+    int slabs = cdiv(TB, 64); if (slabs > 128) slabs = 128;
+    dim3 pg(cdiv(H, 32), slabs, 2);
+    peephole_grad_kernel<<<pg, 256, 0, stream>>>(w.G, r.cs, seq_len, T, B, H, g_fw->w_i_diag, g_fw->w_f_diag,
+                                                g_fw->w_o_diag, g_bw->w_i_diag, g_bw->w_f_diag, g_bw->w_o_diag);
+    B2_LAUNCH_CHECK();
+  }
+  for (int dir = 0; dir < 2; ++dir) {
+    const float* dGd = w.G + (size_t)dir * 4 * H;
+    if (dx) {
+      rc = gemm_simt(0, 1, TB, D, 4 * H, 1.f, dGd, 8 * H, Pm[dir]->kernel, 4 * H, dir == 0 ? 0.f : 1.f, dx, D, nullptr, stream);
+      if (rc) return rc;
+    }
+    rc = gemm_simt(1, 0, D, 4 * H, TB, 1.f, x, D, dGd, 8 * H, 1.f, Gr[dir]->kernel, 4 * H, nullptr, stream);
+    if (rc) return rc;
+    if (T > 1) {        // d(Wh) [P,4H] += Hp_prev^T . dG  (projected h of the neighbouring frame)
+      const float* hp_a = r.hps + (dir == 0 ? 0 : (size_t)B * 2 * P) + (size_t)dir * P;
+      const float* dG_h = dGd + (dir == 0 ? (size_t)B * 8 * H : 0);
+      rc = gemm_simt(1, 0, P, 4 * H, (T - 1) * B, 1.f, hp_a, 2 * P, dG_h, 8 * H, 1.f,
+                     Gr[dir]->kernel + (size_t)D * 4 * H, 4 * H, nullptr, stream);
+      if (rc) return rc;
+    }
+    // d(W_proj) [H,P] += M^T . d(projected h)
+    rc = gemm_simt(1, 0, H, P, TB, 1.f, r.hs + (size_t)dir * H, 2 * H, w.dhp_all + (size_t)dir * P, 2 * P, 1.f,
+                   Gr[dir]->projection, P, nullptr, stream);
+    if (rc) return rc;
+  }
+  return B2_OK;
+}
+
 }  // namespace b2
 
 using namespace b2;
@@ -298,6 +511,7 @@ static int check_desc(const b2_lstm_desc* d) {
                d->keep_prob);
   B2_CHECK_ARG(d->precision == B2_PREC_FP32 || d->precision == B2_PREC_BF16,
                "lstm: unknown precision %d", d->precision);
+  B2_CHECK_ARG(d->num_proj >= 0 && d->num_proj <= 4 * d->H, "lstm: num_proj %d out of range", d->num_proj);
   return B2_OK;
 }
 
@@ -348,7 +562,8 @@ extern "C" int b2_blstm_layer_forward(const b2_lstm_desc* d, const float* x, con
   Work w;
   const size_t need = work_layout(d, workspace, &w);
   if (workspace_bytes < need) { set_error("blstm_forward: workspace %zu < %zu", workspace_bytes, need); return B2_ERR_WORKSPACE; }
-  Reserve r = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (d->num_proj > 0) return proj_forward(d, x, seq_len, fw, bw, y, final_state, reserve, w, stream);
+  Reserve r = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   if (d->need_backward) reserve_layout(d, reserve, &r);
   const int T = d->T, B = d->B, D = d->D_in, H = d->H;
   const int TB = T * B;
@@ -383,7 +598,7 @@ extern "C" int b2_blstm_layer_forward(const b2_lstm_desc* d, const float* x, con
     a.wo[dir] = P[dir]->w_o_diag;
   }
   a.seq_len = seq_len; a.G = w.G; a.hstate = w.hstate; a.cstate = w.cstate; a.y = y;
-  a.gates = r.gates; a.cs = r.cs; a.hs = r.hs;
+  a.gates = r.gates; a.cs = r.cs; a.hs = r.hs; a.mout = nullptr;
   // Wide layers (H > 512: the cluster-resident tcgen05 recurrence does not hold them and the serial-K
   // loop of the step kernel takes 80 us per frame at H=1024): the recurrent product h_prev . Wh becomes
   // one split-K skinny GEMM per direction and frame, the step kernel only does the gate math.
@@ -445,6 +660,10 @@ extern "C" int b2_blstm_layer_backward_ex(const b2_lstm_desc* d, const float* x,
   Work w;
   const size_t need = work_layout(d, workspace, &w);
   if (workspace_bytes < need) { set_error("blstm_backward: workspace %zu < %zu", workspace_bytes, need); return B2_ERR_WORKSPACE; }
+  if (d->num_proj > 0) {
+    B2_CHECK_ARG(!d_final_state, "blstm_backward: d_final_state with num_proj is not built");
+    return proj_backward(d, x, seq_len, fw, bw, dy, reserve, dx, g_fw, g_bw, w, stream);
+  }
   Reserve r;
   reserve_layout(d, (void*)reserve, &r);
   const int T = d->T, B = d->B, D = d->D_in, H = d->H;
@@ -463,7 +682,7 @@ extern "C" int b2_blstm_layer_backward_ex(const b2_lstm_desc* d, const float* x,
     a.wo[dir] = P[dir]->w_o_diag;
   }
   a.seq_len = seq_len; a.dy = dy; a.gates = r.gates; a.cs = r.cs; a.dG = w.G; a.dcstate = w.cstate;
-  a.dfinal = d_final_state;
+  a.dfinal = d_final_state; a.proj = 0;
   const bool wide = H > 512 && B <= 64;            // see the forward pass
   a.dhrec = wide ? w.zrec : nullptr;
   dim3 grid(cdiv(H, RU), cdiv(B, RB), 2);

@@ -19,6 +19,7 @@ bool tc_layer_supported(const b2_lstm_desc* d);
 struct Reserve {
   float* gates; float* cs; float* hs;
   __nv_bfloat16* hs_lp; __nv_bfloat16* y_lp;
+  float* hps;      // [T][B][2][P] projected h before dropout (num_proj > 0; `hs` then holds o*tanh(c))
 };
 
 inline size_t reserve_layout(const b2_lstm_desc* d, void* base, Reserve* r) {
@@ -31,12 +32,14 @@ inline size_t reserve_layout(const b2_lstm_desc* d, void* base, Reserve* r) {
   const size_t oh = lp ? 0 : take(n * sizeof(float));
   const size_t ohl = lp ? take(n * 2) : 0;
   const size_t oyl = lp ? (d->keep_prob < 1.f ? take(n * 2) : ohl) : 0;
+  const size_t ohp = d->num_proj > 0 ? take((size_t)d->T * d->B * 2 * d->num_proj * sizeof(float)) : 0;
   if (r) {
     char* p = (char*)base;
     r->gates = (float*)(p + og); r->cs = (float*)(p + oc);
     r->hs = lp ? nullptr : (float*)(p + oh);
     r->hs_lp = lp ? (__nv_bfloat16*)(p + ohl) : nullptr;
     r->y_lp = lp ? (__nv_bfloat16*)(p + oyl) : nullptr;
+    r->hps = d->num_proj > 0 ? (float*)(p + ohp) : nullptr;
   }
   return off;
 }

@@ -243,7 +243,7 @@ int tc_backward_join(cudaStream_t stream) {
 // ------------------------------------------------------------------ layer entry points
 bool tc_layer_supported(const b2_lstm_desc* d) {
   static int sm100 = -1;
-  if (d->precision != B2_PREC_BF16 || !rec_tc_supported(d->H)) return false;
+  if (d->precision != B2_PREC_BF16 || !rec_tc_supported(d->H) || d->num_proj > 0) return false;
   if (!env_int("B2_REC_TC", 1)) return false;
   if (sm100 < 0) sm100 = b2_device_is_sm100();
   return sm100 == 1;

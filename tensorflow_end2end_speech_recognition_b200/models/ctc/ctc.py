@@ -89,7 +89,7 @@ class CTC(ModelBase):
 
         rng = np.random.RandomState(seed)
         named = self.encoder.create_variables(input_size * num_stack * splice, rng)
-        out_in = 2 * num_units
+        out_in = self.encoder.output_size if hasattr(self.encoder, "output_size") else 2 * num_units
         if self.bottleneck_dim not in (None, 0):                       # ctc.py:200-209
             named.append(("bottleneck/weights", _truncated_normal(rng, (out_in, int(self.bottleneck_dim)),
                                                                   parameter_init)))

@@ -35,8 +35,6 @@ class BLSTMEncoder(object):
         if lstm_impl not in LSTM_IMPLS:
             raise IndexError('lstm_impl is "BasicLSTMCell" or "LSTMCell" or ' +
                              '"LSTMBlockCell" or "LSTMBlockFusedCell" or ' + '"CudnnLSTM".')
-        if self.num_proj:
-            raise NotImplementedError("num_proj (LSTMCell projection) is a 'next' row (SURVEY 8f.3)")
         # BasicLSTMCell has no peephole / clip (blstm.py:148-157); the block cell only
         # receives clip_cell when tf.__version__ == '1.3.0' (blstm.py:286-305)
         if lstm_impl == "BasicLSTMCell":
@@ -55,17 +53,25 @@ class BLSTMEncoder(object):
         out = []
         d_in = input_size
         H = self.num_units
+        Hout = self.num_proj or H                       # LSTMCell(num_proj): the recurrent / emitted width
         for i_layer in range(1, self.num_layers + 1):
             for d in ("fw", "bw"):
                 scope = "blstm_hidden%d/%s/lstm_cell/" % (i_layer, d)
                 a = self.parameter_init
-                out.append((scope + "kernel", rng.uniform(-a, a, (d_in + H, 4 * H)).astype(np.float32)))
+                out.append((scope + "kernel", rng.uniform(-a, a, (d_in + Hout, 4 * H)).astype(np.float32)))
                 out.append((scope + "bias", np.zeros(4 * H, np.float32)))
                 if self._peephole:
                     for k in ("w_i_diag", "w_f_diag", "w_o_diag"):
                         out.append((scope + k, rng.uniform(-a, a, H).astype(np.float32)))
-            d_in = 2 * H
+                if self.num_proj:
+                    out.append((scope + "projection/kernel",
+                                rng.uniform(-a, a, (H, self.num_proj)).astype(np.float32)))
+            d_in = 2 * Hout
         return out
+
+    @property
+    def output_size(self):
+        return 2 * (self.num_proj or self.num_units)
 
     def _layer_params(self, variables, i_layer, d):
         scope = "blstm_hidden%d/%s/lstm_cell/" % (i_layer, d)
@@ -73,6 +79,8 @@ class BLSTMEncoder(object):
         if self._peephole:
             for k in ("w_i_diag", "w_f_diag", "w_o_diag"):
                 p[k] = variables[scope + k]
+        if self.num_proj:
+            p["projection"] = variables[scope + "projection/kernel"]
         return p
 
     # -------------------------------------------------------------- forward
@@ -90,7 +98,7 @@ class BLSTMEncoder(object):
             desc = ops.lstm_desc(T, B, x.shape[2], self.num_units, use_peephole=self._peephole,
                                  forget_bias=1.0, cell_clip=self._clip, keep_prob=float(keep_prob),
                                  dropout_seed=dropout_seed * 131 + i_layer, precision=prec,
-                                 need_backward=is_training)
+                                 need_backward=is_training, num_proj=self.num_proj)
             pf = self._layer_params(variables, i_layer, "fw")
             pb = self._layer_params(variables, i_layer, "bw")
             y, fs, reserve = ops.blstm_layer_forward(desc, x, inputs_seq_len, pf, pb,

@@ -43,6 +43,10 @@ class VGGBLSTMEncoder(object):
         self.num_proj = self.blstm.num_proj
         self._saved = None
 
+    @property
+    def output_size(self):
+        return self.blstm.output_size
+
     # ------------------------------------------------------------ variables
     def create_variables(self, input_size, rng):
         """-> ordered [(tf_name, numpy)]: conv filters/biases (cnn_util.py:67-70: truncated normal,

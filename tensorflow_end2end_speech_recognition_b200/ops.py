@@ -252,24 +252,30 @@ def _params_struct(p):
     return LstmParams(p["kernel"].data_ptr(), p["bias"].data_ptr(),
                       p["w_i_diag"].data_ptr() if "w_i_diag" in p else 0,
                       p["w_f_diag"].data_ptr() if "w_f_diag" in p else 0,
-                      p["w_o_diag"].data_ptr() if "w_o_diag" in p else 0)
+                      p["w_o_diag"].data_ptr() if "w_o_diag" in p else 0,
+                      p["projection"].data_ptr() if "projection" in p else 0)
 
 
 def lstm_desc(T, B, D_in, H, use_peephole=True, forget_bias=1.0, cell_clip=None, keep_prob=1.0,
-              dropout_seed=0, precision=PREC_FP32, need_backward=True):
+              dropout_seed=0, precision=PREC_FP32, need_backward=True, num_proj=None):
     return LstmDesc(T, B, D_in, H, int(bool(use_peephole)), float(forget_bias),
                     float(cell_clip) if cell_clip else 0.0, float(keep_prob), int(dropout_seed),
-                    int(precision), int(bool(need_backward)))
+                    int(precision), int(bool(need_backward)), int(num_proj or 0))
 
 
 def blstm_layer_forward(desc, x, seq_len, p_fw, p_bw, want_final_state=False, x_lp=0):
     """x [T,B,D] -> (y [T,B,2H], final_state [4,B,H] or None, reserve buffer).
-    x_lp: raw device pointer of a bf16 shadow of x (from reserve_y_lp of the layer below) or 0."""
+    x_lp: raw device pointer of a bf16 shadow of x (from reserve_y_lp of the layer below) or 0.
+    With desc.num_proj = P: y [T,B,2P]; final_state is the tuple (c_fw [B,H], h_fw [B,P], c_bw, h_bw)."""
     lib = _lib.load()
     _require_cuda(x, seq_len)
     dev = x.device
-    y = torch.empty((desc.T, desc.B, 2 * desc.H), dtype=torch.float32, device=dev)
-    fs = torch.empty((4, desc.B, desc.H), dtype=torch.float32, device=dev) if want_final_state else None
+    Hout = desc.num_proj if desc.num_proj > 0 else desc.H
+    y = torch.empty((desc.T, desc.B, 2 * Hout), dtype=torch.float32, device=dev)
+    fs = None
+    if want_final_state:
+        fs = torch.empty((4, desc.B, desc.H), dtype=torch.float32, device=dev) if desc.num_proj <= 0 else \
+            torch.empty(2 * desc.B * (desc.H + Hout), dtype=torch.float32, device=dev)
     # the bf16 path keeps its bf16 output shadow in `reserve` even for inference
     reserve = torch.empty(lib.b2_blstm_reserve_bytes(C.byref(desc)), dtype=torch.uint8, device=dev)
     nbytes = lib.b2_blstm_workspace_bytes(C.byref(desc))
@@ -280,6 +286,10 @@ def blstm_layer_forward(desc, x, seq_len, p_fw, p_bw, want_final_state=False, x_
                                     C.byref(bw), _ptr(y), _ptr(fs), _ptr(reserve), _ptr(ws), nbytes,
                                     _stream())
     _lib.check(rc, "b2_blstm_layer_forward")
+    if fs is not None and desc.num_proj > 0:
+        B, H, P = desc.B, desc.H, Hout
+        o = [0, B * H, B * H + B * P, 2 * B * H + B * P]
+        fs = (fs[o[0]:o[1]].view(B, H), fs[o[1]:o[2]].view(B, P), fs[o[2]:o[3]].view(B, H), fs[o[3]:].view(B, P))
     return y, fs, reserve
 
 

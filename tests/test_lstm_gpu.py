@@ -105,3 +105,48 @@ def test_layer_bf16(cuda, T, B, D, H):
     seq = [T] + list(np.random.RandomState(2).randint(T // 2, T + 1, size=B - 1))
     got, ref = run_layer(cuda, T, B, D, H, seq, ops.PREC_BF16, seed=7)
     compare(got, ref, 3e-2, 5e-2)
+
+
+@pytest.mark.parametrize("T,B,D,H,P,seq", [
+    (6, 3, 5, 8, 4, [6, 3, 5]),
+    (15, 7, 20, 32, 12, None),
+    (9, 70, 16, 24, 24, None),          # batch > 64: the projection products fall back to the tile GEMM
+])
+@pytest.mark.parametrize("keep_prob", [1.0, 0.7])
+def test_layer_num_proj(cuda, T, B, D, H, P, seq, keep_prob):
+    """LSTMCell(num_proj) (blstm.py:215-228, lstm.py:171-176): projected recurrent / emitted state,
+    forward + BPTT incl. d(projection), dropout applied after the projection."""
+    from tensorflow_end2end_speech_recognition_b200 import ops
+    rng = np.random.RandomState(T * 100 + B)
+    if seq is None:
+        seq = [T] + list(rng.randint(1, T + 1, size=B - 1))
+    layer = olstm.init_blstm_params(D, H, 1, parameter_init=0.3, use_peephole=True, num_proj=P, seed=3)[0]
+    for d in layer:
+        layer[d]["bias"] = (rng.randn(4 * H) * 0.1).astype(np.float32)
+    x = rng.randn(T, B, D).astype(np.float32)
+    dy = rng.randn(T, B, 2 * P).astype(np.float32)
+    Pd = to_dev(layer, cuda)
+    desc = ops.lstm_desc(T, B, D, H, use_peephole=True, cell_clip=3.0, precision=ops.PREC_FP32, keep_prob=keep_prob,
+                         dropout_seed=77, num_proj=P)
+    seq_t = torch.tensor(np.asarray(seq, np.int32), device=cuda)
+    xd = torch.tensor(x, device=cuda)
+    y, fs, reserve = ops.blstm_layer_forward(desc, xd, seq_t, Pd["fw"], Pd["bw"], want_final_state=True)
+    G = {d: {k: torch.zeros_like(v) for k, v in Pd[d].items()} for d in Pd}
+    dx = ops.blstm_layer_backward(desc, xd, seq_t, Pd["fw"], Pd["bw"], torch.tensor(dy, device=cuda), reserve,
+                                  G["fw"], G["bw"])
+    torch.cuda.synchronize()
+    masks = None
+    if keep_prob < 1.0:
+        from tests.util_dropout import dropout_mask
+        masks = [torch.tensor(dropout_mask(77, T * B * 2 * P, keep_prob).reshape(T, B, 2 * P))]
+    yr, fsr, dxr, gr = oracle_layer(x, seq, layer, dy, 3.0, masks, keep_prob)
+    assert y.shape == (T, B, 2 * P)
+    np.testing.assert_allclose(y.cpu().numpy(), yr, rtol=1e-4, atol=1e-4)
+    for got, ref in zip(fs, (fsr[0][0], fsr[0][1], fsr[1][0], fsr[1][1])):
+        np.testing.assert_allclose(got.cpu().numpy(), ref.detach().numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(dx.cpu().numpy(), dxr, rtol=1e-3, atol=1e-3 * max(1.0, np.abs(dxr).max()))
+    for d in G:
+        assert set(G[d]) == set(gr[d])
+        for k in G[d]:
+            s = max(1.0, np.abs(gr[d][k]).max())
+            np.testing.assert_allclose(G[d][k].cpu().numpy(), gr[d][k], rtol=1e-3, atol=1e-3 * s, err_msg="%s/%s" % (d, k))

@@ -181,3 +181,28 @@ def test_bottleneck_layer(cuda, precision, tol):
     # dropout on the bottleneck output changes the loss but keeps it finite
     l2, _ = model.compute_loss(x, labels, seq, keep_prob=0.5)
     assert np.isfinite(float(l2)) and abs(float(l2) - float(loss)) > 1e-6
+
+
+def test_lstmcell_num_proj_model(cuda):
+    """CTC(lstm_impl='LSTMCell', num_proj=P): the reference's models/test/test_ctc.py configuration
+    (num_proj with LSTMCell, clip_activation) -- loss, logits, every gradient vs the oracle."""
+    rng = np.random.RandomState(13)
+    B, T, D, H, L, C, P = 4, 28, 24, 32, 2, 9, 12
+    model = build(cuda, "fp32", D, H, L, C, lstm_impl="LSTMCell", num_proj=P, clip_activation=5.0)
+    assert model.variables["blstm_hidden2/fw/lstm_cell/kernel"].shape == (2 * P + P, 4 * H)
+    assert model.variables["output/weights"].shape == (2 * P, C + 1)
+    x, seq, labels = make_batch(rng, B, T, D, C, 3, 9)
+    loss, logits = model.compute_loss(x, labels, seq, keep_prob=1.0)
+    model._backward()
+    torch.cuda.synchronize()
+    vs = {v.name: v.tensor.cpu().numpy() for v in model.trainable_variables()}
+    tr = omodel.OracleTrainer(vs, L, clip_grad_norm=None, cell_clip=5.0)
+    l_ref, logits_ref, g_ref = tr.loss_and_grads(x, seq, labels)
+    assert abs(float(loss) - l_ref) <= 2e-4 * abs(l_ref)
+    np.testing.assert_allclose(logits.cpu().numpy(), logits_ref, rtol=2e-4, atol=2e-4)
+    for v, g in zip(model.trainable_variables(), g_ref):
+        s = max(1e-3, np.abs(g).max())
+        np.testing.assert_allclose(v.grad.cpu().numpy(), g, rtol=0, atol=1e-3 * s, err_msg=v.name)
+    # the projection is ignored for the other cell types, as in the reference (blstm.py:49-52)
+    m2 = build(cuda, "fp32", D, H, 1, C, lstm_impl="LSTMBlockCell", num_proj=P)
+    assert m2.variables["output/weights"].shape == (2 * H, C + 1)
