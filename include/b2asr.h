@@ -287,6 +287,10 @@ typedef struct {
   int32_t sigmoid_smoothing;
   float forget_bias, cell_clip;     /* LSTMBlockCell; cell_clip <= 0: none                     */
   int32_t feed_previous_attention;  /* 0 = the reference's behaviour (zeros), inference only   */
+  float keep_prob_decoder;          /* DropoutWrapper(output_keep_prob) on the decoder cell output; training only */
+  float keep_prob_embedding;        /* tf.nn.dropout on the embedded labels (attention_seq2seq.py:438-439)        */
+  uint64_t dropout_seed;            /* cell output mask index (t*B+b)*Hd+i at seed; embedding mask index
+                                       (b*labels_ld+pos)*emb+i at seed+1                                           */
 } b2_decoder_desc;
 typedef struct {
   const float* cell_kernel;         /* [emb+E+Hd, 4Hd], gate blocks i,g,f,o                     */
@@ -440,6 +444,11 @@ int b2_lstm_cell_pointwise_backward(const float* z, const float* bias, const flo
  * block s is the cell state before step s (block 0 = initial state).  Accumulates. */
 int b2_decoder_peephole_grad(const float* dz, const float* c_all, int steps, int B, int H,
                              float* dw_i, float* dw_f, float* dw_o, b2_stream_t stream);
+/* tf.nn.dropout on a row-strided matrix with explicit element numbering: (r, c) is kept iff the counter
+ * hash of (seed, idx_base + r*idx_row_stride + c) says so; y = mask*x/keep_prob, or y += ... when add != 0
+ * (x == y allowed).  Used for the decoder-cell output and the label embedding of the attention model. */
+int b2_dropout_rows(const float* x, int ldx, float* y, int ldy, int64_t rows, int cols, float keep_prob,
+                    uint64_t seed, uint64_t idx_base, uint64_t idx_row_stride, int add, b2_stream_t stream);
 /* dW[ids[r], :D] += dx[r, :D] for r < rows (dx row stride ldx); ids outside [0,V) skipped */
 int b2_embedding_grad(const float* dx, int ldx, const int32_t* ids, int64_t rows, int D, int V,
                       float* dW, b2_stream_t stream);

@@ -84,12 +84,18 @@ def bridge_t(final_state, p):
 
 def decode_train_t(p, attention_type, enc, enc_len, initial_state, labels, labels_seq_len,
                    sharpening_factor=1.0, sigmoid_smoothing=False, feed_previous_attention=False,
-                   cell_clip=None):
-    """Teacher-forced decoder -> dict(logits [B,L,C], predicted_ids, attention_weights)."""
+                   cell_clip=None, emb_mask=None, keep_prob_embedding=1.0, dec_mask=None, keep_prob_decoder=1.0):
+    """Teacher-forced decoder -> dict(logits [B,L,C], predicted_ids, attention_weights).
+    emb_mask [B,T_out,emb] / dec_mask [L,B,Hd]: {0,1} dropout masks of the embedded labels
+    (attention_seq2seq.py:438-439) and of the decoder cell OUTPUT (DropoutWrapper, :367-369: the state that
+    recurs is not dropped)."""
     B, T, E = enc.shape
     labels = np.asarray(labels)
     emb = p["W_embedding"]
-    dec_in = emb[torch.as_tensor(labels[:, :-1], dtype=torch.long)]         # [B, L, emb]
+    embedded = emb[torch.as_tensor(labels, dtype=torch.long)]               # [B, T_out, emb]
+    if emb_mask is not None and keep_prob_embedding < 1.0:
+        embedded = embedded * torch.as_tensor(emb_mask, dtype=embedded.dtype) / keep_prob_embedding
+    dec_in = embedded[:, :-1]                                               # [B, L, emb]
     L = dec_in.shape[1]
     seq = np.asarray(labels_seq_len) - 1
     c, h = initial_state
@@ -101,10 +107,13 @@ def decode_train_t(p, attention_type, enc, enc_len, initial_state, labels, label
     while not finished.all():
         x = torch.cat([dec_in[:, time], ctx], dim=1)
         h_new, c_new = olstm.lstm_cell_step(x, h, c, p["cell"], 1.0, cell_clip)
-        alpha, ctx = attention_step_t(attention_type, enc, h_new, enc_len,
+        h_out = h_new
+        if dec_mask is not None and keep_prob_decoder < 1.0:
+            h_out = h_new * torch.as_tensor(dec_mask[time], dtype=h_new.dtype) / keep_prob_decoder
+        alpha, ctx = attention_step_t(attention_type, enc, h_out, enc_len,
                                       alpha_state if feed_previous_attention else enc.new_zeros((B, T)),
                                       p["attention"], sharpening_factor, sigmoid_smoothing)
-        av = torch.tanh(torch.cat([h_new, ctx], dim=1) @ p["attentional_vector/weights"])
+        av = torch.tanh(torch.cat([h_out, ctx], dim=1) @ p["attentional_vector/weights"])
         logits = av @ p["output_layer/weights"] + p["output_layer/biases"]
         keep = torch.as_tensor(~finished)
         m = keep[:, None].to(enc.dtype)
@@ -161,7 +170,8 @@ def seq2seq_loss(variables, cfg, inputs_btd, inputs_seq_len, labels, labels_seq_
     init = bridge_t(final, p)
     dec = decode_train_t(p, cfg["attention_type"], enc, inputs_seq_len, init, labels, labels_seq_len,
                          cfg.get("sharpening_factor", 1.0), cfg.get("sigmoid_smoothing", False),
-                         cfg.get("feed_previous_attention", False))
+                         cfg.get("feed_previous_attention", False), None, cfg.get("emb_mask"),
+                         cfg.get("keep_prob_embedding", 1.0), cfg.get("dec_mask"), cfg.get("keep_prob_decoder", 1.0))
     logits = dec["logits"] / cfg.get("logits_temperature", 1.0) + 1e-10
     labels = np.asarray(labels)
     L = logits.shape[1]

@@ -48,7 +48,8 @@ class DecoderDesc(C.Structure):
                 ("emb", C.c_int32), ("C", C.c_int32), ("attention_mode", C.c_int32),
                 ("query_projected", C.c_int32), ("filter_width", C.c_int32), ("sharpening", C.c_float),
                 ("sigmoid_smoothing", C.c_int32), ("forget_bias", C.c_float), ("cell_clip", C.c_float),
-                ("feed_previous_attention", C.c_int32)]
+                ("feed_previous_attention", C.c_int32), ("keep_prob_decoder", C.c_float),
+                ("keep_prob_embedding", C.c_float), ("dropout_seed", C.c_uint64)]
 
 
 _DEC_FIELDS = ("cell_kernel", "cell_bias", "w_i_diag", "w_f_diag", "w_o_diag", "w_query", "conv_filter",
@@ -123,6 +124,7 @@ PROTOTYPES = {
     "b2_tanh_backward": (_i, [_p, _p, _p, _i64, _p]),
     "b2_lstm_cell_pointwise_backward": (_i, [_p] * 8 + [_i, _i, _f, _f, _p, _p, _p]),
     "b2_decoder_peephole_grad": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),
+    "b2_dropout_rows": (_i, [_p, _i, _p, _i, _i64, _i, _f, C.c_uint64, C.c_uint64, C.c_uint64, _i, _p]),
     "b2_embedding_grad": (_i, [_p, _i, _p, _i64, _i, _i, _p, _p]),
     "b2_lstm_cell_pointwise": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _f, _f, _p, _p, _p]),
     "b2_tanh_inplace": (_i, [_p, _i64, _p]),

@@ -100,6 +100,8 @@ static int dec_check(const b2_decoder_desc* d) {
                "decoder: bad shape");
   B2_CHECK_ARG(d->E % 4 == 0, "decoder: encoder width must be a multiple of 4");
   B2_CHECK_ARG(d->query_projected || d->A == d->Hd, "decoder: unprojected query needs A == Hd");
+  B2_CHECK_ARG(d->keep_prob_decoder > 0.f && d->keep_prob_decoder <= 1.f && d->keep_prob_embedding > 0.f &&
+               d->keep_prob_embedding <= 1.f, "decoder: keep_prob out of (0,1]");
   return B2_OK;
 }
 
@@ -113,7 +115,7 @@ extern "C" size_t b2_attention_decoder_workspace_bytes(const b2_decoder_desc* d,
   size_t bwd = 0;
   auto add = [&](size_t n) { bwd += align_up(n * 4, 256); };
   add(L * B * d->Hd); add(L * B * d->Hd); add(L * B * d->E); add(L * B * d->A);
-  add(L * B * 4 * d->Hd); add(L * B * d->emb); add(L * B); add(B * d->Hd);
+  add(L * B * 4 * d->Hd); add(L * B * d->emb); add(L * B); add(B * d->Hd); add(B * d->Hd);
   bwd += b2_attention_step_backward_workspace_bytes(d->B, d->T) + 256;
   const size_t fwd = dec_scratch_layout(d, nullptr, nullptr);
   return fwd > bwd ? fwd : bwd;
@@ -157,6 +159,10 @@ extern "C" int b2_attention_decoder_forward(const b2_decoder_desc* d, const b2_d
   decoder_init_finished_kernel<<<cdiv(B, 128), 128, 0, stream>>>(dec_len, B, teacher ? 1 : L, finished);
   B2_LAUNCH_CHECK();
   if (reserve) B2_CUDA(cudaMemcpyAsync(sv.c, c0, (size_t)B * Hd * 4, cudaMemcpyDeviceToDevice, stream));
+  // dropout only in the training pass (teacher forcing with a reserve)
+  const float kd = reserve ? d->keep_prob_decoder : 1.f, ke = reserve ? d->keep_prob_embedding : 1.f;
+  if (ke < 1.f)
+    if ((rc = b2_dropout_rows(xh, X, xh, X, B, emb, ke, d->dropout_seed + 1, 0, (uint64_t)labels_ld * emb, 0, stream_))) return rc;
   const float* prev_alpha = nullptr;                 // NULL = all zero (b2_attention_step_forward)
   int* h_fin = nullptr;
   if (!teacher && poll_every > 0) B2_CUDA(cudaMallocHost(&h_fin, (size_t)B * sizeof(int)));
@@ -164,23 +170,28 @@ extern "C" int b2_attention_decoder_forward(const b2_decoder_desc* d, const b2_d
   for (; t < L; ++t) {
     float* z = reserve ? sv.z + (size_t)t * B * 4 * Hd : w.z;
     float* c_new = reserve ? sv.c + (size_t)(t + 1) * B * Hd : w.c_new;
-    float* h_new = reserve ? sv.h + (size_t)t * B * Hd : w.h_new;
+    float* h_new = (reserve && kd >= 1.f) ? sv.h + (size_t)t * B * Hd : w.h_new;   // cell state h (never dropped)
     float* alpha = reserve ? sv.alpha + (size_t)t * B * T : ((t & 1) ? w.alpha2 : w.alpha);
     float* ctx = reserve ? sv.ctx + (size_t)t * B * E : w.ctx;
     float* av = reserve ? sv.av + (size_t)t * B * Hd : w.av;
-    float* q = d->query_projected ? (reserve ? sv.q + (size_t)t * B * A : w.q) : h_new;
+    // cell OUTPUT = DropoutWrapper(h): what the attention and the attentional vector see
+    float* h_use = h_new;
+    if (kd < 1.f) h_use = sv.h + (size_t)t * B * Hd;
+    float* q = d->query_projected ? (reserve ? sv.q + (size_t)t * B * A : w.q) : h_use;
     float* energy = (reserve && sv.energy) ? sv.energy + (size_t)t * B * T : nullptr;
     float* xh_next = reserve ? sv.xh + (size_t)(t + 1) * B * X : (w.xh + (size_t)((t + 1) & 1) * B * X);
     if ((rc = gemm_simt(0, 0, B, 4 * Hd, X, 1.f, xh, X, p->cell_kernel, 4 * Hd, 0.f, z, 4 * Hd, nullptr, stream))) break;
     if ((rc = b2_lstm_cell_pointwise(z, p->cell_bias, p->w_i_diag, p->w_f_diag, p->w_o_diag, c_state, B, Hd,
                                      d->forget_bias, d->cell_clip, c_new, h_new, stream_))) break;
+    if (kd < 1.f)
+      if ((rc = b2_dropout_rows(h_new, Hd, h_use, Hd, B, Hd, kd, d->dropout_seed, (uint64_t)t * B * Hd, Hd, 0, stream_))) break;
     if (d->query_projected)
-      if ((rc = gemm_simt(0, 0, B, A, Hd, 1.f, h_new, Hd, p->w_query, A, 0.f, q, A, nullptr, stream))) break;
+      if ((rc = gemm_simt(0, 0, B, A, Hd, 1.f, h_use, Hd, p->w_query, A, 0.f, q, A, nullptr, stream))) break;
     if ((rc = b2_attention_step_forward(d->attention_mode, enc, keys, q, prev_alpha, enc_len,
                                         loc ? p->conv_filter : nullptr, d->filter_width, p->w_filter, p->b_filter,
                                         p->v_a, B, T, E, A, d->sharpening, d->sigmoid_smoothing, alpha, ctx, energy,
                                         stream_))) break;
-    if ((rc = gemm_simt(0, 0, B, Hd, Hd, 1.f, h_new, Hd, p->w_av, Hd, 0.f, av, Hd, nullptr, stream))) break;
+    if ((rc = gemm_simt(0, 0, B, Hd, Hd, 1.f, h_use, Hd, p->w_av, Hd, 0.f, av, Hd, nullptr, stream))) break;
     if ((rc = gemm_simt(0, 0, B, Hd, E, 1.f, ctx, E, p->w_av + (size_t)Hd * Hd, Hd, 1.f, av, Hd, nullptr, stream))) break;
     if ((rc = b2_tanh_inplace(av, (int64_t)B * Hd, stream_))) break;
     if ((rc = gemm_simt(0, 0, B, C, Hd, 1.f, av, Hd, p->w_out, C, 0.f, w.logits, C, p->b_out, stream))) break;
@@ -189,6 +200,9 @@ extern "C" int b2_attention_decoder_forward(const b2_decoder_desc* d, const b2_d
                                    c_state, h_state, finished, p->embedding, labels, labels_ld, dec_len,
                                    teacher ? -1 : eos, teacher ? 0 : L, xh_next, out_logits, out_ids, out_av,
                                    out_alpha, out_ctx, stream_))) break;
+    if (ke < 1.f && t + 1 < L)        // the next input's embedding is labels_embedded[:, t+1] with ITS dropout mask
+      if ((rc = b2_dropout_rows(xh_next, X, xh_next, X, B, emb, ke, d->dropout_seed + 1, (uint64_t)(t + 1) * emb,
+                                (uint64_t)labels_ld * emb, 0, stream_))) break;
     xh = xh_next;
     if (d->feed_previous_attention) prev_alpha = alpha;
     if (h_fin && (t + 1) % poll_every == 0 && t + 1 < L) {
@@ -235,6 +249,7 @@ extern "C" int b2_attention_decoder_backward(const b2_decoder_desc* d, const b2_
   float* demb_all = take((size_t)LB * emb);
   int* ids_tm = (int*)take((size_t)LB);
   float* dc_buf = take((size_t)B * Hd);
+  float* dc_tmp = take((size_t)B * Hd);
   void* att_ws = (void*)wp;
   const size_t att_ws_bytes = b2_attention_step_backward_workspace_bytes(B, T);
   const float* dl = dlogits_tm;
@@ -247,6 +262,12 @@ extern "C" int b2_attention_decoder_backward(const b2_decoder_desc* d, const b2_
   if ((rc = gemm_simt(1, 0, E, Hd, (int)LB, 1.f, sv.ctx, E, d_av, Hd, 1.f, g->w_av + (size_t)Hd * Hd, Hd, nullptr, stream))) return rc;
   if ((rc = gemm_simt(0, 1, (int)LB, Hd, Hd, 1.f, d_av, Hd, p->w_av, Hd, 0.f, dh_av, Hd, nullptr, stream))) return rc;
   if ((rc = gemm_simt(0, 1, (int)LB, E, Hd, 1.f, d_av, Hd, p->w_av + (size_t)Hd * Hd, Hd, 0.f, dctx_all, E, nullptr, stream))) return rc;
+  const float kd = d->keep_prob_decoder, ke = d->keep_prob_embedding;
+  // DropoutWrapper on the cell output: sv.h holds the DROPPED output (operand of the query / attentional-vector
+  // products); its gradient passes the same mask.  Masking is linear, so the attentional-vector share is masked
+  // here, the attention share per step below; the recurrent share (cell state h, never dropped) is not masked.
+  if (kd < 1.f)
+    if ((rc = b2_dropout_rows(dh_av, Hd, dh_av, Hd, LB, Hd, kd, d->dropout_seed, 0, Hd, 0, stream_))) return rc;
   // ---- sequential part
   const float* k_emb = p->cell_kernel;
   const float* k_ctx = p->cell_kernel + (size_t)emb * 4 * Hd;
@@ -265,12 +286,20 @@ extern "C" int b2_attention_decoder_backward(const b2_decoder_desc* d, const b2_
                                            loc ? p->b_filter : nullptr, p->v_a, B, T, E, A, d->sharpening,
                                            d->sigmoid_smoothing, dctx_t, d_keys, dq, 0, g->v_a,
                                            loc ? g->b_filter : nullptr, att_ws, att_ws_bytes, stream_))) return rc;
-      if ((rc = gemm_simt(0, 1, B, Hd, A, 1.f, dq, A, p->w_query, A, 1.f, dh_t, Hd, nullptr, stream))) return rc;
+      if (kd < 1.f) {
+        if ((rc = gemm_simt(0, 1, B, Hd, A, 1.f, dq, A, p->w_query, A, 0.f, dc_tmp, Hd, nullptr, stream))) return rc;
+        if ((rc = b2_dropout_rows(dc_tmp, Hd, dh_t, Hd, B, Hd, kd, d->dropout_seed, (uint64_t)t * B * Hd, Hd, 1, stream_))) return rc;
+      } else {
+        if ((rc = gemm_simt(0, 1, B, Hd, A, 1.f, dq, A, p->w_query, A, 1.f, dh_t, Hd, nullptr, stream))) return rc;
+      }
     } else {
+      float* dq_dst = kd < 1.f ? dc_tmp : dh_t;
       if ((rc = b2_attention_step_backward(d->attention_mode, enc, keys, sv.h + (size_t)t * B * Hd, alpha, energy, enc_len,
                                            loc ? p->b_filter : nullptr, p->v_a, B, T, E, A, d->sharpening,
-                                           d->sigmoid_smoothing, dctx_t, d_keys, dh_t, 1, g->v_a,
+                                           d->sigmoid_smoothing, dctx_t, d_keys, dq_dst, kd < 1.f ? 0 : 1, g->v_a,
                                            loc ? g->b_filter : nullptr, att_ws, att_ws_bytes, stream_))) return rc;
+      if (kd < 1.f)
+        if ((rc = b2_dropout_rows(dc_tmp, Hd, dh_t, Hd, B, Hd, kd, d->dropout_seed, (uint64_t)t * B * Hd, Hd, 1, stream_))) return rc;
     }
     float* dz = dz_all + (size_t)t * B * 4 * Hd;
     float* dc_out = (t & 1) ? dc_a : dc_b;
@@ -279,6 +308,9 @@ extern "C" int b2_attention_decoder_backward(const b2_decoder_desc* d, const b2_
                                               d->forget_bias, d->cell_clip, dz, dc_out, stream_))) return rc;
     dc_in = dc_out;
     if ((rc = gemm_simt(0, 1, B, emb, 4 * Hd, 1.f, dz, 4 * Hd, k_emb, 4 * Hd, 0.f, demb_all + (size_t)t * B * emb, emb, nullptr, stream))) return rc;
+    if (ke < 1.f)
+      if ((rc = b2_dropout_rows(demb_all + (size_t)t * B * emb, emb, demb_all + (size_t)t * B * emb, emb, B, emb, ke,
+                                d->dropout_seed + 1, (uint64_t)t * emb, (uint64_t)labels_ld * emb, 0, stream_))) return rc;
     if (t > 0) {
       if ((rc = gemm_simt(0, 1, B, E, 4 * Hd, 1.f, dz, 4 * Hd, k_ctx, 4 * Hd, 1.f, dctx_all + (size_t)(t - 1) * B * E, E, nullptr, stream))) return rc;
       if ((rc = gemm_simt(0, 1, B, Hd, 4 * Hd, 1.f, dz, 4 * Hd, k_h, 4 * Hd, 1.f, dh_av + (size_t)(t - 1) * B * Hd, Hd, nullptr, stream))) return rc;

@@ -139,9 +139,41 @@ embedding_grad_kernel(const float* __restrict__ dx, int ldx, const int* __restri
   }
 }
 
+// tf.nn.dropout on a row-strided matrix with an explicit element numbering: element (r, c) is kept iff the
+// counter hash of (seed, idx_base + r*idx_row_stride + c) says so.  add != 0: y += mask*x/keep (backward of a
+// dropped operand whose gradient accumulates), else y = mask*x/keep (x == y allowed).
+__global__ void __launch_bounds__(256)
+dropout_rows_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int64_t rows, int cols,
+                    float keep, unsigned long long seed, unsigned long long idx_base,
+                    unsigned long long idx_row_stride, int add) {
+  const int64_t n = rows * cols;
+  const float sc = 1.f / keep;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols; const int c = (int)(i % cols);
+    const float v = dropout_keep(seed, idx_base + (unsigned long long)r * idx_row_stride + c, keep) ? x[r * ldx + c] * sc : 0.f;
+    float* o = y + r * ldy + c;
+    *o = add ? *o + v : v;
+  }
+}
+
 }  // namespace b2
 
 using namespace b2;
+
+extern "C" int b2_dropout_rows(const float* x, int ldx, float* y, int ldy, int64_t rows, int cols, float keep_prob,
+                               uint64_t seed, uint64_t idx_base, uint64_t idx_row_stride, int add,
+                               b2_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B2_CHECK_ARG(x && y && rows > 0 && cols > 0 && ldx >= cols && ldy >= cols && keep_prob > 0.f && keep_prob <= 1.f,
+               "b2_dropout_rows: bad argument");
+  int64_t blocks = (rows * cols + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  dropout_rows_kernel<<<(int)blocks, 256, 0, stream>>>(x, ldx, y, ldy, rows, cols, keep_prob, seed, idx_base,
+                                                      idx_row_stride, add);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
 
 extern "C" int b2_sequence_loss(const float* logits, const int32_t* targets, int targets_ld,
                                 const int32_t* lengths, int B, int L, int C, float temperature,

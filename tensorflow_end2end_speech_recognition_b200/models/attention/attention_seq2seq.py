@@ -11,9 +11,8 @@ Same constructor keywords and method names as the reference; handles are evaluat
 
 ``_build`` (:196-283): encoder -> bridge -> teacher-forced decoder (+ greedy inference
 decoder, evaluated lazily: the reference only runs it when ``decoded_infer`` is fetched).
-Deviations, all documented in DESIGN.md: dropout inside the decoder / on the embedding is not
-built (keep_prob_decoder / keep_prob_embedding must be 1); GRU decoder not built (the
-reference's GRU branch references an undefined attribute).
+Deviation documented in DESIGN.md: GRU decoder not built (the reference's GRU branch references an
+undefined attribute).
 """
 from collections import namedtuple
 
@@ -196,15 +195,14 @@ class AttentionSeq2Seq(ModelBase):
 
     def _build(self, inputs, labels, inputs_seq_len, labels_seq_len, keep_prob_encoder,
                keep_prob_decoder, keep_prob_embedding, is_training=True):
-        if keep_prob_decoder != 1.0 or keep_prob_embedding != 1.0:
-            raise NotImplementedError("decoder / embedding dropout is not built: keep_prob must be 1")
         enc = self._encode(inputs, inputs_seq_len, keep_prob_encoder, is_training)
         self.decoder.encoder_outputs = enc.outputs
         self.decoder.encoder_outputs_seq_len = enc.seq_len
         embedding = self.variables[_EMB]
         init = self.bridge(enc)
         helper = TrainingHelper(embedding, labels, labels_seq_len - 1)
-        out_train, _ = self.decoder(init, helper, is_training=is_training)
+        out_train, _ = self.decoder(init, helper, keep_prob=float(keep_prob_decoder), is_training=is_training,
+                                    keep_prob_embedding=float(keep_prob_embedding), dropout_seed=self._step * 7 + 3)
         B = inputs.shape[0]
 
         def infer():

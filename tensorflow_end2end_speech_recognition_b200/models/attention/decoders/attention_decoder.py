@@ -13,11 +13,12 @@ condition (:143-146) is polled every ``poll_every`` iterations and the outputs a
 first all-finished step, which is what the reference returns because finished rows only emit
 zeros.
 
-``backward(dlogits)`` is the teacher-forced loop differentiated: everything that is not
+Decoder-cell output dropout and label-embedding dropout act in the training pass (counter-hash
+masks, same convention as the encoder's).  ``backward(dlogits)`` is the teacher-forced loop differentiated: everything that is not
 sequential is time-batched (output layer, attentional vector, cell-kernel / embedding /
 W_query / W_keys gradients, d(enc) through the context as one GEMM per utterance); the
 per-step remainder is attention backward -> query GEMM -> cell gate math backward -> cell
-kernel GEMM.  Dropout inside the decoder is not built -- ``keep_prob`` other than 1 raises.
+kernel GEMM.
 """
 from collections import namedtuple
 
@@ -102,7 +103,7 @@ class AttentionDecoder(object):
         return self.variables
 
     # ----------------------------------------------------------------- loop
-    def _desc(self, B, T, E, emb):
+    def _desc(self, B, T, E, emb, keep_prob_decoder=1.0, keep_prob_embedding=1.0, dropout_seed=0):
         al = self.attention_layer
         t = al.attention_type
         Hd = self.rnn_cell.num_units
@@ -114,7 +115,8 @@ class AttentionDecoder(object):
             int(al.variables["filter"].shape[0]) if loc else 0,
             float(al.sharpening_factor), int(bool(al.sigmoid_smoothing)),
             float(self.rnn_cell.forget_bias), float(self.rnn_cell.clip_cell or 0.0),
-            int(bool(self.feed_previous_attention)))
+            int(bool(self.feed_previous_attention)), float(keep_prob_decoder), float(keep_prob_embedding),
+            int(dropout_seed))
 
     def _param_struct(self, cell, att, dec, embedding, E):
         """b2_decoder_params / b2_decoder_grads from the variable (or gradient) dicts"""
@@ -133,9 +135,10 @@ class AttentionDecoder(object):
         s.b_out, s.embedding = ptr(dec["output_layer/biases"]), ptr(embedding)
         return s
 
-    def __call__(self, initial_state, helper, keep_prob=1.0, is_training=False):
-        if keep_prob != 1.0:
-            raise NotImplementedError("decoder dropout: keep_prob must be 1")
+    def __call__(self, initial_state, helper, keep_prob=1.0, is_training=False, keep_prob_embedding=1.0,
+                 dropout_seed=0):
+        """keep_prob: DropoutWrapper(output_keep_prob) of the decoder cell (attention_seq2seq.py:367-369);
+        keep_prob_embedding: dropout on the embedded labels (:438-439).  Both act in the training pass only."""
         lib = _lib.load()
         enc = self.encoder_outputs.contiguous()
         B, T, E = enc.shape
@@ -170,7 +173,8 @@ class AttentionDecoder(object):
         c_state, h_state = torch.empty((B, Hd), **f32), torch.empty((B, Hd), **f32)
         finished = torch.empty(B, dtype=torch.int32, device=dev)
         keys = self.attention_layer.precompute_keys(enc)
-        desc = self._desc(B, T, E, emb)
+        desc = self._desc(B, T, E, emb, keep_prob if is_training else 1.0,
+                          keep_prob_embedding if is_training else 1.0, dropout_seed)
         ps = self._param_struct(self.cell_variables, self.attention_layer.variables, self.variables, emb_table, E)
         reserve = None
         if is_training:

@@ -176,3 +176,31 @@ def test_bf16_encoder_final_state_gradient(cuda):
     ref, g_ref = oracle_loss_and_grads(model, cfg, x, seq, labels, lab_len)
     assert abs(float(loss) - float(ref["total_loss"])) <= 3e-2 * abs(float(ref["total_loss"]))
     check_grads(model, g_ref, 0.1)
+
+
+@pytest.mark.parametrize("attention_type", ["bahdanau_content", "luong_general"])
+def test_decoder_and_embedding_dropout(cuda, attention_type):
+    """keep_prob_decoder (DropoutWrapper on the cell output) and keep_prob_embedding (dropout on the embedded
+    labels): same counter-hash masks applied in the oracle; loss and every gradient."""
+    from tests.util_dropout import dropout_mask
+    rng = np.random.RandomState(8)
+    B, T, D, V, Lmax, Hd, emb = 4, 20, 12, 7, 8, 20, 8
+    kd, ke = 0.8, 0.6
+    model = build(cuda, attention_type)
+    x, seq, labels, lab_len, _ = make_batch(rng, B, T, D, V, Lmax)
+    loss, logits, _, _ = model.compute_loss(x, labels, seq, lab_len, 1.0, kd, ke)
+    seed = model._step * 7 + 3
+    model._backward()
+    L = Lmax - 1
+    dec_mask = dropout_mask(seed, L * B * Hd, kd).reshape(L, B, Hd)
+    emb_mask = dropout_mask(seed + 1, B * Lmax * emb, ke).reshape(B, Lmax, emb)
+    cfg = dict(num_layers=2, attention_type=attention_type, dec_mask=dec_mask, keep_prob_decoder=kd,
+               emb_mask=emb_mask, keep_prob_embedding=ke)
+    ref, g_ref = oracle_loss_and_grads(model, cfg, x, seq, labels, lab_len)
+    assert abs(float(loss) - float(ref["total_loss"].detach())) <= 2e-4 * abs(float(ref["total_loss"].detach()))
+    np.testing.assert_allclose(logits.cpu().numpy(), ref["decoder"]["logits"].detach().numpy(), rtol=2e-4, atol=2e-5)
+    check_grads(model, g_ref, 1e-3)
+    # evaluation mode ignores the dropout rates
+    l_eval, _, _, _ = model.compute_loss(x, labels, seq, lab_len, 1.0, kd, ke, is_training=False)
+    l_ref, _, _, _ = model.compute_loss(x, labels, seq, lab_len, 1.0, 1.0, 1.0, is_training=False)
+    assert abs(float(l_eval) - float(l_ref)) < 1e-6
