@@ -86,3 +86,52 @@ class DeviceInputPipeline(object):
                                  self.splice, Tout, ops._ptr(out), ops._ptr(out_len), ops._stream())
         _lib.check(rc, "b2_stack_splice")
         return out, out_len
+
+
+class PinnedPrefetcher(object):
+    """Double-buffered host -> device staging on a side stream.
+
+    ``put(arrays...)`` starts the asynchronous copy of the NEXT batch (pinned host tensors) while the
+    current step computes; ``get()`` makes the compute stream wait for that copy and hands out the
+    device tensors.  Two device buffer sets alternate, so a batch is never overwritten while the step
+    that consumes it may still be running (the event recorded by ``get`` guards the reuse)."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._slots = [None, None]
+        self._ready = [None, None]       # copy finished
+        self._free = [None, None]        # last consumer finished
+        self._turn = 0
+        self._pending = None
+
+    def put(self, *host_tensors):
+        k = self._turn
+        self._turn ^= 1
+        if self._free[k] is not None:
+            self.stream.wait_event(self._free[k])
+        with torch.cuda.stream(self.stream):
+            if self._slots[k] is None or any(d.shape != h.shape or d.dtype != h.dtype
+                                             for d, h in zip(self._slots[k], host_tensors)):
+                self._slots[k] = [torch.empty(h.shape, dtype=h.dtype, device=self.device) for h in host_tensors]
+            for d, h in zip(self._slots[k], host_tensors):
+                d.copy_(h, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self._ready[k] = ev
+        self._pending = k
+
+    def get(self):
+        k = self._pending
+        assert k is not None, "PinnedPrefetcher.get() without a preceding put()"
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self._ready[k])
+        self._pending = None
+        self._last = k
+        return self._slots[k]
+
+    def release(self):
+        """call after the step that consumed the last ``get()`` has been enqueued"""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._free[self._last] = ev
