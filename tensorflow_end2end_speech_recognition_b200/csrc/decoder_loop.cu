@@ -19,6 +19,19 @@
 
 namespace b2 {
 
+// pinned host words for the finished-flag polls of the greedy / beam loops (grown on demand, per thread)
+static int* poll_buffer(int n) {
+  static thread_local int* buf = nullptr;
+  static thread_local int cap = 0;
+  if (n > cap) {
+    if (buf) cudaFreeHost(buf);
+    buf = nullptr; cap = 0;
+    if (cudaMallocHost(&buf, (size_t)n * sizeof(int)) != cudaSuccess) { buf = nullptr; return nullptr; }
+    cap = n;
+  }
+  return buf;
+}
+
 struct DecSaved {
   float* xh; float* z; float* c; float* h; float* alpha; float* ctx; float* av; float* q; float* energy;
 };
@@ -164,8 +177,7 @@ extern "C" int b2_attention_decoder_forward(const b2_decoder_desc* d, const b2_d
   if (ke < 1.f)
     if ((rc = b2_dropout_rows(xh, X, xh, X, B, emb, ke, d->dropout_seed + 1, 0, (uint64_t)labels_ld * emb, 0, stream_))) return rc;
   const float* prev_alpha = nullptr;                 // NULL = all zero (b2_attention_step_forward)
-  int* h_fin = nullptr;
-  if (!teacher && poll_every > 0) B2_CUDA(cudaMallocHost(&h_fin, (size_t)B * sizeof(int)));
+  int* h_fin = (!teacher && poll_every > 0) ? poll_buffer(B) : nullptr;
   int t = 0;
   for (; t < L; ++t) {
     float* z = reserve ? sv.z + (size_t)t * B * 4 * Hd : w.z;
@@ -213,7 +225,6 @@ extern "C" int b2_attention_decoder_forward(const b2_decoder_desc* d, const b2_d
       if (all) { ++t; break; }
     }
   }
-  if (h_fin) cudaFreeHost(h_fin);
   if (steps_run) *steps_run = t < L ? t : L;
   return rc;
 }
@@ -579,8 +590,7 @@ extern "C" int b2_attention_decoder_beam_search(const b2_decoder_desc* d, const 
                                           w.fin[0], w.len[0]);
   B2_LAUNCH_CHECK();
   const float* prev_alpha = nullptr;
-  int* h_done = nullptr;
-  if (poll_every > 0) B2_CUDA(cudaMallocHost(&h_done, (size_t)Bu * sizeof(int)));
+  int* h_done = poll_every > 0 ? poll_buffer(Bu) : nullptr;
   float* c_state = w.c_state; float* c_next = w.c_next;
   int t = 0, cur = 0;
   for (; t < L; ++t) {
@@ -620,7 +630,6 @@ extern "C" int b2_attention_decoder_beam_search(const b2_decoder_desc* d, const 
       if (all) { ++t; break; }
     }
   }
-  if (h_done) cudaFreeHost(h_done);
   if (rc) return rc;
   const int steps = t < L ? t : L;
   beam_backtrack_kernel<<<cdiv(R, 128), 128, 0, stream>>>(w.hist_w, w.hist_p, steps, R, W, L, eos, out_ids);

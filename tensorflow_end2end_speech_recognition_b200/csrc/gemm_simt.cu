@@ -118,7 +118,7 @@ gemm_skinny_kernel(int M, int N, int K, float alpha, const float* __restrict__ A
                    const float* __restrict__ bias, int k_chunk, int64_t strideA, int64_t strideB,
                    int64_t strideC) {
   A += blockIdx.z * strideA; Bm += blockIdx.z * strideB; C += blockIdx.z * strideC;   // batched form
-  __shared__ float As[SM_MAX][SK + 1];
+  __shared__ __align__(16) float As[SM_MAX][SK + 4];   // row stride 68 floats: float4 reads along k
   __shared__ float Bs[SK][SN + 1];
   const int tid = threadIdx.x;
   const int n0 = blockIdx.x * SN;
@@ -144,11 +144,17 @@ gemm_skinny_kernel(int M, int N, int K, float alpha, const float* __restrict__ A
       Bs[k][n] = v;
     }
     __syncthreads();
-#pragma unroll 8
-    for (int k = 0; k < SK; ++k) {
-      const float b = Bs[k][nl];
+    // four k per pass: one 16-byte broadcast read of A per row instead of four scalar ones (the loop was
+    // bound by shared-memory issue: 17 loads per 16 FMAs at M = 64)
+#pragma unroll 4
+    for (int k = 0; k < SK; k += 4) {
+      const float b0 = Bs[k][nl], b1 = Bs[k + 1][nl], b2 = Bs[k + 2][nl], b3 = Bs[k + 3][nl];
 #pragma unroll
-      for (int i = 0; i < RPT; ++i) acc[i] = fmaf(As[mg + 4 * i][k], b, acc[i]);
+      for (int i = 0; i < RPT; ++i) {
+        const float4 a4 = *(const float4*)&As[mg + 4 * i][k];
+        acc[i] = fmaf(a4.x, b0, acc[i]); acc[i] = fmaf(a4.y, b1, acc[i]);
+        acc[i] = fmaf(a4.z, b2, acc[i]); acc[i] = fmaf(a4.w, b3, acc[i]);
+      }
     }
     __syncthreads();
   }

@@ -66,3 +66,16 @@ def test_sparsetensor_round_trip():
     back = sparsetensor2list(st, 3)
     assert [list(b) for b in back] == [[1, 2, 3], [4], [5, 6, 7, 8]]
     assert sparse_to_label_lists(st, 3) == [[1, 2, 3], [4], [5, 6, 7, 8]]
+
+
+def test_shard_bounds_match_array_split():
+    """rank shards of the per-GPU split = np.array_split (utils/dataset/ctc.py:171-177)"""
+    import numpy as np
+    from tensorflow_end2end_speech_recognition_b200.utils.io.inputs.pipeline import pad_labels, shard_bounds
+    for B in (1, 7, 8, 64, 65):
+        for n in (1, 2, 3, 8):
+            want = [len(a) for a in np.array_split(np.arange(B), n)]
+            got = shard_bounds(B, n)
+            assert [e - s for s, e in got] == want and got[0][0] == 0 and got[-1][1] == B
+    lab = pad_labels([[1, 2, 3], [4]], padded_value=-1)
+    assert lab.tolist() == [[1, 2, 3], [4, -1, -1]]
