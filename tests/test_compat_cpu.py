@@ -94,3 +94,18 @@ def test_summary_scope_and_misc_symbols():
             w.flush()
             assert w.events[0][1] == [("loss", 0.0)]
             assert sess.run(tf.reduce_mean(tf.concat([tf.expand_dims(c, 0), tf.expand_dims(c, 0)], 0))) == 0
+
+
+def test_tf_surface_listed_in_integration_md_exists():
+    """every tf.* symbol INTEGRATION.md promises resolves on the shim"""
+    names = ["Graph", "reset_default_graph", "device", "name_scope", "variable_scope", "get_variable_scope",
+             "placeholder", "float32", "int32", "int64", "SparseTensor", "SparseTensorValue", "Variable",
+             "expand_dims", "concat", "reduce_mean", "edit_distance", "global_variables_initializer",
+             "trainable_variables", "Session", "ConfigProto"]
+    for n in names:
+        assert hasattr(tf, n), n
+    for n in ("scalar", "merge", "FileWriter"):
+        assert hasattr(tf.summary, n)
+    for n in ("Saver", "get_checkpoint_state"):
+        assert hasattr(tf.train, n)
+    assert hasattr(tf.test, "TestCase") and hasattr(tf.test, "main")
