@@ -420,6 +420,24 @@ int b2_attention_step_backward(int mode, const float* enc, const float* keys, co
                                int dq_accumulate, float* dv, float* db_filter, void* workspace, size_t workspace_bytes,
                                b2_stream_t stream);
 
+/* Same with the location term fed by REAL previous weights (feed_previous_attention; the intended
+ * behaviour the reference's while_loop never reaches): prev_alpha [B,T] != NULL makes the
+ * kernel recompute conv1d(prev_alpha, conv_filter) . w_filter, accumulate d_conv_filter [filter_width,10]
+ * and d_w_filter [10,A], and write d_prev_alpha [B,T] (gradient wrt the previous step's weights);
+ * dalpha_ext [B,T] (may be NULL) is the gradient wrt THIS step's weights that arrives from the next
+ * step's location term. */
+int b2_attention_step_backward_loc(int mode, const float* enc, const float* keys, const float* q,
+                                   const float* alpha, const float* energy,
+                                   const int32_t* enc_len, const float* b_filter,
+                                   const float* v_a, int B, int T, int E, int A,
+                                   float sharpening_factor, int sigmoid_smoothing,
+                                   const float* dctx, float* d_keys, float* dq,
+                                   int dq_accumulate, float* dv, float* db_filter,
+                                   const float* prev_alpha, const float* conv_filter, int filter_width,
+                                   const float* w_filter, const float* dalpha_ext,
+                                   float* d_prev_alpha, float* d_conv_filter, float* d_w_filter,
+                                   void* workspace, size_t workspace_bytes, b2_stream_t stream);
+
 /* ------------------------------------------------------------------------ *
  * Attention decoder, training side
  *   reference: attention_seq2seq.py:579-664 (compute_loss), :413-459 (_decode_train)

@@ -120,6 +120,8 @@ PROTOTYPES = {
     "b2_attention_step_backward_workspace_bytes": (_sz, [_i, _i]),
     "b2_attention_step_backward": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i,
                                         _p, _p, _p, _i, _p, _p, _p, _sz, _p]),
+    "b2_attention_step_backward_loc": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i,
+                                            _p, _p, _p, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "b2_sequence_loss": (_i, [_p, _p, _i, _p, _i, _i, _i, _f, _f, _p, _p, _p]),
     "b2_tanh_backward": (_i, [_p, _p, _p, _i64, _p]),
     "b2_lstm_cell_pointwise_backward": (_i, [_p] * 8 + [_i, _i, _f, _f, _p, _p, _p]),

@@ -234,7 +234,8 @@ __global__ void __launch_bounds__(256)
 attention_bwd_dalpha_kernel(const float* __restrict__ enc, const float* __restrict__ dctx,
                             const float* __restrict__ alpha, const float* __restrict__ energy,
                             const int* __restrict__ enc_len, int T, int E, int sigmoid_smoothing,
-                            float* __restrict__ dalpha, float* __restrict__ red) {
+                            const float* __restrict__ dalpha_ext, float* __restrict__ dalpha,
+                            float* __restrict__ red) {
   extern __shared__ float s_d[];                    // [E]
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int len = min(enc_len[b], T);
@@ -252,6 +253,7 @@ attention_bwd_dalpha_kernel(const float* __restrict__ enc, const float* __restri
         acc += h.x * d.x + h.y * d.y + h.z * d.z + h.w * d.w;
       }
       acc = warp_sum(acc);
+      if (dalpha_ext) acc += dalpha_ext[(size_t)b * T + t];   // gradient through the next step's location term
       if (lane == 0) {
         dot += alpha[(size_t)b * T + t] * acc;
         if (sigmoid_smoothing) ssum += 1.f / (1.f + __expf(-energy[(size_t)b * T + t]));
@@ -271,6 +273,10 @@ struct AttnBwdArgs {
   const float* red; const int* enc_len; const float* b_f; const float* v_a;
   int T, A; float sharpening; int sigmoid_smoothing;
   float* d_keys; float* dq; float* dv; float* db_f;
+  // location term with REAL previous weights (feed_previous_attention): recompute f = conv(prev_alpha, F),
+  // accumulate d(W_filter), emit df [B,T,10] for attention_bwd_location_kernel
+  const float* prev_alpha; const float* filt; const float* w_f; int Kw;
+  float* d_w_f; float* df;
 };
 
 // grid (B, ceil(T/32)); 8 warps, warp w takes rows t0+w, t0+w+8, ...
@@ -282,18 +288,41 @@ __global__ void __launch_bounds__(256) attention_bwd_energy_kernel(const AttnBwd
   float* s_b = s_v + A;            // [A]
   float* s_dq = s_b + A;           // [8][A]
   float* s_dv = s_dq + 8 * A;      // [8][A]
+  // the next five only with prev_alpha:
+  float* s_wf = s_dv + 8 * A;      // [10][A]
+  float* s_dwf = s_wf + 10 * A;    // [10][A]
+  float* s_pa = s_dwf + 10 * A;    // [32 + Kw]
+  float* s_f = s_pa + 32 + a.Kw;   // [32][10]
+  float* s_filt = s_f + 320;       // [Kw][10]
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int len = min(a.enc_len[b], T);
+  const bool conv = a.prev_alpha != nullptr;
   for (int i = threadIdx.x; i < A; i += 256) {
     s_q[i] = a.q ? a.q[(size_t)b * A + i] : 0.f;
     s_v[i] = a.v_a ? a.v_a[i] : 1.f;
     s_b[i] = a.b_f ? a.b_f[i] : 0.f;
   }
   for (int i = threadIdx.x; i < 16 * A; i += 256) s_dq[i] = 0.f;
+  const int t0 = blockIdx.y * 32;
+  if (conv) {
+    const int pl = (a.Kw - 1) / 2;
+    for (int i = threadIdx.x; i < 10 * A; i += 256) { s_wf[i] = a.w_f[i]; s_dwf[i] = 0.f; }
+    for (int i = threadIdx.x; i < a.Kw * 10; i += 256) s_filt[i] = a.filt[i];
+    for (int i = threadIdx.x; i < 32 + a.Kw; i += 256) {
+      const int t = t0 + i - pl;
+      s_pa[i] = (t >= 0 && t < T) ? a.prev_alpha[(size_t)b * T + t] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 320; i += 256) {
+      const int tl = i / 10, k = i % 10;
+      float acc = 0.f;
+      for (int j = 0; j < a.Kw; ++j) acc = fmaf(s_pa[tl + j], s_filt[j * 10 + k], acc);
+      s_f[i] = acc;
+    }
+  }
   __syncthreads();
   const float dot = a.red[b * 2];
   const float S = a.sigmoid_smoothing ? a.red[b * 2 + 1] : 1.f;
-  const int t0 = blockIdx.y * 32;
   float* my_dq = s_dq + warp * A;
   float* my_dv = s_dv + warp * A;
   for (int t = t0 + warp; t < min(t0 + 32, len); t += 8) {
@@ -307,18 +336,50 @@ __global__ void __launch_bounds__(256) attention_bwd_energy_kernel(const AttnBwd
     }
     const float* kr = a.keys ? a.keys + bt * A : nullptr;
     float* dk = a.d_keys ? a.d_keys + bt * A : nullptr;
+    const float* fr = s_f + (t - t0) * 10;
+    float dfk[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) dfk[k] = 0.f;
     for (int i = lane; i < A; i += 32) {
       const float kv = kr ? kr[i] : 0.f;
       if (a.mode == 1) {
         if (dk) dk[i] += de * s_q[i];
         my_dq[i] += de * kv;
       } else {
-        const float u = tanhf_(kv + s_q[i] + s_b[i]);
+        float l = s_b[i];
+        if (conv) {
+#pragma unroll
+          for (int k = 0; k < 10; ++k) l = fmaf(fr[k], s_wf[k * A + i], l);
+        }
+        const float u = tanhf_(kv + s_q[i] + l);
         const float g = de * s_v[i] * (1.f - u * u);
         if (dk) dk[i] += g;
         my_dq[i] += g;
         my_dv[i] += de * u;
+        if (conv) {
+#pragma unroll
+          for (int k = 0; k < 10; ++k) {
+            dfk[k] = fmaf(g, s_wf[k * A + i], dfk[k]);
+            atomicAdd(&s_dwf[k * A + i], fr[k] * g);       // d(W_filter)[k,a] += f[t,k] * g[t,a]
+          }
+        }
       }
+    }
+    if (conv) {
+#pragma unroll
+      for (int k = 0; k < 10; ++k) dfk[k] = warp_sum(dfk[k]);
+      if (lane < 10) {
+        float v = dfk[0];
+#pragma unroll
+        for (int k = 1; k < 10; ++k) v = (lane == k) ? dfk[k] : v;
+        a.df[bt * 10 + lane] = v;
+      }
+    }
+  }
+  if (conv) {      // frames of this chunk past the utterance's end (or never visited) carry no gradient
+    for (int i = threadIdx.x; i < 320; i += 256) {
+      const int t = t0 + i / 10;
+      if (t < T && t >= len) a.df[((size_t)b * T + t) * 10 + i % 10] = 0.f;
     }
   }
   __syncthreads();
@@ -331,6 +392,58 @@ __global__ void __launch_bounds__(256) attention_bwd_energy_kernel(const AttnBwd
       if (a.db_f) atomicAdd(&a.db_f[i], sq);
     }
     if (a.dv && sv != 0.f) atomicAdd(&a.dv[i], sv);
+  }
+  if (conv)
+    for (int i = threadIdx.x; i < 10 * A; i += 256)
+      if (s_dwf[i] != 0.f) atomicAdd(&a.d_w_f[i], s_dwf[i]);
+}
+
+// location term, second half: from df [B,T,10] (gradient wrt the conv features)
+//   d_prev_alpha[b,s] = sum_{j,k} F[j,k] * df[b, s - j + pl, k]
+//   dF[j,k]          += sum_{b,t} prev_alpha[b, t + j - pl] * df[b,t,k]
+// grid (B, ceil(T/64)), 256 threads
+__global__ void __launch_bounds__(256)
+attention_bwd_location_kernel(const float* __restrict__ df, const float* __restrict__ prev_alpha,
+                              const float* __restrict__ filt, int T, int Kw, float* __restrict__ d_prev_alpha,
+                              float* __restrict__ d_filt) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x, t0 = blockIdx.y * 64, pl = (Kw - 1) / 2;
+  float* s_filt = sm;                       // [Kw][10]
+  float* s_df = s_filt + Kw * 10;           // [64 + Kw][10]: frames t0 - (Kw-1-pl) .. t0 + 63 + pl
+  float* s_pa = s_df + (64 + Kw) * 10;      // [64 + Kw]:     frames t0 - pl .. t0 + 63 + (Kw-1-pl)
+  const int lo = t0 - (Kw - 1 - pl);
+  for (int i = threadIdx.x; i < Kw * 10; i += 256) s_filt[i] = filt[i];
+  for (int i = threadIdx.x; i < (64 + Kw) * 10; i += 256) {
+    const int t = lo + i / 10;
+    s_df[i] = (t >= 0 && t < T) ? df[((size_t)b * T + t) * 10 + i % 10] : 0.f;
+  }
+  for (int i = threadIdx.x; i < 64 + Kw; i += 256) {
+    const int t = t0 - pl + i;
+    s_pa[i] = (t >= 0 && t < T) ? prev_alpha[(size_t)b * T + t] : 0.f;
+  }
+  __syncthreads();
+  // d_prev_alpha for s = t0 .. t0+63: frame index s - j + pl -> local (s - j + pl) - lo
+  for (int sl = threadIdx.x; sl < 64; sl += 256) {
+    const int s = t0 + sl;
+    if (s >= T) continue;
+    float acc = 0.f;
+    for (int j = 0; j < Kw; ++j) {
+      const float* dr = s_df + (s - j + pl - lo) * 10;
+      const float* fr = s_filt + j * 10;
+#pragma unroll
+      for (int k = 0; k < 10; ++k) acc = fmaf(fr[k], dr[k], acc);
+    }
+    d_prev_alpha[(size_t)b * T + s] = acc;
+  }
+  // dF[j,k] += sum_{t in chunk} pa[t + j - pl] * df[t,k]
+  for (int i = threadIdx.x; i < Kw * 10; i += 256) {
+    const int j = i / 10, k = i % 10;
+    float acc = 0.f;
+    for (int tl = 0; tl < 64; ++tl) {
+      if (t0 + tl >= T) break;
+      acc = fmaf(s_pa[tl + j], s_df[(t0 + tl - lo) * 10 + k], acc);
+    }
+    if (acc != 0.f) atomicAdd(&d_filt[i], acc);
   }
 }
 
@@ -465,7 +578,7 @@ int b2::attention_step_forward_rows(int mode, const float* enc, const float* key
 }
 
 extern "C" size_t b2_attention_step_backward_workspace_bytes(int B, int T) {
-  return align_up((size_t)B * T * 4, 256) + align_up((size_t)B * 2 * 4, 256);
+  return align_up((size_t)B * T * 4, 256) + align_up((size_t)B * 2 * 4, 256) + align_up((size_t)B * T * 10 * 4, 256);
 }
 
 extern "C" int b2_attention_step_backward(int mode, const float* enc, const float* keys, const float* q,
@@ -477,31 +590,64 @@ extern "C" int b2_attention_step_backward(int mode, const float* enc, const floa
                                           int dq_accumulate, float* dv,
                                           float* db_filter, void* workspace, size_t workspace_bytes,
                                           b2_stream_t stream_) {
+  return b2_attention_step_backward_loc(mode, enc, keys, q, alpha, energy, enc_len, b_filter, v_a, B, T, E, A,
+                                        sharpening_factor, sigmoid_smoothing, dctx, d_keys, dq, dq_accumulate, dv,
+                                        db_filter, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                        workspace, workspace_bytes, stream_);
+}
+
+extern "C" int b2_attention_step_backward_loc(int mode, const float* enc, const float* keys, const float* q,
+                                              const float* alpha, const float* energy,
+                                              const int32_t* enc_len, const float* b_filter,
+                                              const float* v_a, int B, int T, int E, int A,
+                                              float sharpening_factor, int sigmoid_smoothing,
+                                              const float* dctx, float* d_keys, float* dq,
+                                              int dq_accumulate, float* dv, float* db_filter,
+                                              const float* prev_alpha, const float* conv_filter, int filter_width,
+                                              const float* w_filter, const float* dalpha_ext,
+                                              float* d_prev_alpha, float* d_conv_filter, float* d_w_filter,
+                                              void* workspace, size_t workspace_bytes, b2_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B2_CHECK_ARG(enc && alpha && enc_len && dctx && dq && workspace, "b2_attention_step_backward: null pointer");
   B2_CHECK_ARG(mode == 0 || mode == 1, "b2_attention_step_backward: mode %d", mode);
   B2_CHECK_ARG(B > 0 && T > 0 && E > 0 && A > 0 && E % 4 == 0, "b2_attention_step_backward: bad shape");
   B2_CHECK_ARG(!sigmoid_smoothing || energy, "b2_attention_step_backward: sigmoid smoothing needs the saved energies");
   B2_CHECK_ARG(mode == 0 || keys, "b2_attention_step_backward: multiplicative mode needs keys");
+  const bool conv = prev_alpha != nullptr;
+  B2_CHECK_ARG(!conv || (mode == 0 && conv_filter && w_filter && filter_width > 0 && d_prev_alpha && d_conv_filter &&
+                         d_w_filter && b_filter),
+               "b2_attention_step_backward: location term with previous weights needs filter / W_filter and their gradients");
   const size_t need = b2_attention_step_backward_workspace_bytes(B, T);
   if (workspace_bytes < need) { set_error("b2_attention_step_backward: workspace %zu < %zu", workspace_bytes, need); return B2_ERR_WORKSPACE; }
   float* dalpha = (float*)workspace;
   float* red = (float*)((char*)workspace + align_up((size_t)B * T * 4, 256));
+  float* df = (float*)((char*)red + align_up((size_t)B * 2 * 4, 256));
   B2_CUDA(cudaMemsetAsync(red, 0, (size_t)B * 2 * 4, stream));
   if (!dq_accumulate) B2_CUDA(cudaMemsetAsync(dq, 0, (size_t)B * A * 4, stream));
   dim3 g1(B, cdiv(T, 64));
   attention_bwd_dalpha_kernel<<<g1, 256, (size_t)E * 4, stream>>>(enc, dctx, alpha, energy, enc_len, T, E,
-                                                                 sigmoid_smoothing, dalpha, red);
+                                                                 sigmoid_smoothing, dalpha_ext, dalpha, red);
   B2_LAUNCH_CHECK();
   AttnBwdArgs a;
   a.mode = mode; a.keys = keys; a.q = q; a.alpha = alpha; a.energy = energy; a.dalpha = dalpha; a.red = red;
   a.enc_len = enc_len; a.b_f = b_filter; a.v_a = v_a; a.T = T; a.A = A; a.sharpening = sharpening_factor;
   a.sigmoid_smoothing = sigmoid_smoothing; a.d_keys = d_keys; a.dq = dq; a.dv = dv; a.db_f = db_filter;
-  const size_t smem = (size_t)19 * A * 4;
+  a.prev_alpha = prev_alpha; a.filt = conv_filter; a.w_f = w_filter; a.Kw = conv ? filter_width : 0;
+  a.d_w_f = d_w_filter; a.df = df;
+  size_t smem = (size_t)19 * A * 4;
+  if (conv) smem += ((size_t)20 * A + 32 + filter_width + 320 + (size_t)filter_width * 10) * 4;
   B2_CHECK_ARG(smem <= 200 * 1024, "b2_attention_step_backward: A=%d too wide for shared memory", A);
   B2_CUDA(cudaFuncSetAttribute(attention_bwd_energy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 g2(B, cdiv(T, 32));
   attention_bwd_energy_kernel<<<g2, 256, smem, stream>>>(a);
   B2_LAUNCH_CHECK();
+  if (conv) {
+    const size_t smem3 = ((size_t)filter_width * 10 + (size_t)(64 + filter_width) * 11) * 4;
+    B2_CUDA(cudaFuncSetAttribute(attention_bwd_location_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+    dim3 g3(B, cdiv(T, 64));
+    attention_bwd_location_kernel<<<g3, 256, smem3, stream>>>(df, prev_alpha, conv_filter, T, filter_width,
+                                                             d_prev_alpha, d_conv_filter);
+    B2_LAUNCH_CHECK();
+  }
   return B2_OK;
 }

@@ -128,7 +128,7 @@ extern "C" size_t b2_attention_decoder_workspace_bytes(const b2_decoder_desc* d,
   size_t bwd = 0;
   auto add = [&](size_t n) { bwd += align_up(n * 4, 256); };
   add(L * B * d->Hd); add(L * B * d->Hd); add(L * B * d->E); add(L * B * d->A);
-  add(L * B * 4 * d->Hd); add(L * B * d->emb); add(L * B); add(B * d->Hd); add(B * d->Hd);
+  add(L * B * 4 * d->Hd); add(L * B * d->emb); add(L * B); add(B * d->Hd); add(B * d->Hd); add(2 * B * d->T);
   bwd += b2_attention_step_backward_workspace_bytes(d->B, d->T) + 256;
   const size_t fwd = dec_scratch_layout(d, nullptr, nullptr);
   return fwd > bwd ? fwd : bwd;
@@ -150,8 +150,6 @@ extern "C" int b2_attention_decoder_forward(const b2_decoder_desc* d, const b2_d
                c_state && h_state && finished && workspace, "b2_attention_decoder_forward: null pointer");
   B2_CHECK_ARG(!labels || (dec_len && labels_ld > 1), "b2_attention_decoder_forward: teacher forcing needs dec_len");
   B2_CHECK_ARG(!reserve || labels, "b2_attention_decoder_forward: saving for backward needs teacher forcing");
-  B2_CHECK_ARG(!reserve || !d->feed_previous_attention,
-               "b2_attention_decoder_forward: training with feed_previous_attention is not built");
   const int B = d->B, T = d->T, E = d->E, Hd = d->Hd, A = d->A, emb = d->emb, C = d->C;
   const int X = emb + E + Hd;
   const int L = max_steps;
@@ -242,7 +240,6 @@ extern "C" int b2_attention_decoder_backward(const b2_decoder_desc* d, const b2_
   B2_CHECK_ARG(p && enc && enc_len && labels && reserve && dlogits_tm && g && d_enc && dc0 && dh0 && workspace,
                "b2_attention_decoder_backward: null pointer");
   B2_CHECK_ARG(steps > 0, "b2_attention_decoder_backward: no steps");
-  B2_CHECK_ARG(!d->feed_previous_attention, "b2_attention_decoder_backward: feed_previous_attention not built");
   if (workspace_bytes < b2_attention_decoder_workspace_bytes(d, steps)) { set_error("b2_attention_decoder_backward: workspace too small"); return B2_ERR_WORKSPACE; }
   const int B = d->B, T = d->T, E = d->E, Hd = d->Hd, A = d->A, emb = d->emb, C = d->C, L = steps;
   const int X = emb + E + Hd;
@@ -261,6 +258,7 @@ extern "C" int b2_attention_decoder_backward(const b2_decoder_desc* d, const b2_
   int* ids_tm = (int*)take((size_t)LB);
   float* dc_buf = take((size_t)B * Hd);
   float* dc_tmp = take((size_t)B * Hd);
+  float* dal = take((size_t)2 * B * T);          // d(alpha) exchanged between steps (location term, real previous weights)
   void* att_ws = (void*)wp;
   const size_t att_ws_bytes = b2_attention_step_backward_workspace_bytes(B, T);
   const float* dl = dlogits_tm;
@@ -291,12 +289,20 @@ extern "C" int b2_attention_decoder_backward(const b2_decoder_desc* d, const b2_
     float* dctx_t = dctx_all + (size_t)t * B * E;
     const float* alpha = sv.alpha + (size_t)t * B * T;
     const float* energy = sv.energy ? sv.energy + (size_t)t * B * T : nullptr;
+    // location term fed by the previous step's weights: its gradient reaches alpha_{t-1} (handed to step t-1
+    // through dal) as well as the conv filter and W_filter.  Step 0 saw zeros (no conv, nothing to hand on).
+    const bool fp = loc && d->feed_previous_attention;
+    const float* prev_al = (fp && t > 0) ? sv.alpha + (size_t)(t - 1) * B * T : nullptr;
+    const float* dal_in = (fp && t < L - 1) ? dal + (size_t)((t + 1) & 1) * B * T : nullptr;
+    float* dal_out = prev_al ? dal + (size_t)(t & 1) * B * T : nullptr;
     if (d->query_projected) {
       float* dq = dq_all + (size_t)t * B * A;
-      if ((rc = b2_attention_step_backward(d->attention_mode, enc, keys, sv.q + (size_t)t * B * A, alpha, energy, enc_len,
-                                           loc ? p->b_filter : nullptr, p->v_a, B, T, E, A, d->sharpening,
-                                           d->sigmoid_smoothing, dctx_t, d_keys, dq, 0, g->v_a,
-                                           loc ? g->b_filter : nullptr, att_ws, att_ws_bytes, stream_))) return rc;
+      if ((rc = b2_attention_step_backward_loc(d->attention_mode, enc, keys, sv.q + (size_t)t * B * A, alpha, energy, enc_len,
+                                               loc ? p->b_filter : nullptr, p->v_a, B, T, E, A, d->sharpening,
+                                               d->sigmoid_smoothing, dctx_t, d_keys, dq, 0, g->v_a,
+                                               loc ? g->b_filter : nullptr, prev_al, p->conv_filter, d->filter_width,
+                                               p->w_filter, dal_in, dal_out, g->conv_filter, g->w_filter,
+                                               att_ws, att_ws_bytes, stream_))) return rc;
       if (kd < 1.f) {
         if ((rc = gemm_simt(0, 1, B, Hd, A, 1.f, dq, A, p->w_query, A, 0.f, dc_tmp, Hd, nullptr, stream))) return rc;
         if ((rc = b2_dropout_rows(dc_tmp, Hd, dh_t, Hd, B, Hd, kd, d->dropout_seed, (uint64_t)t * B * Hd, Hd, 1, stream_))) return rc;
@@ -305,10 +311,12 @@ extern "C" int b2_attention_decoder_backward(const b2_decoder_desc* d, const b2_
       }
     } else {
       float* dq_dst = kd < 1.f ? dc_tmp : dh_t;
-      if ((rc = b2_attention_step_backward(d->attention_mode, enc, keys, sv.h + (size_t)t * B * Hd, alpha, energy, enc_len,
-                                           loc ? p->b_filter : nullptr, p->v_a, B, T, E, A, d->sharpening,
-                                           d->sigmoid_smoothing, dctx_t, d_keys, dq_dst, kd < 1.f ? 0 : 1, g->v_a,
-                                           loc ? g->b_filter : nullptr, att_ws, att_ws_bytes, stream_))) return rc;
+      if ((rc = b2_attention_step_backward_loc(d->attention_mode, enc, keys, sv.h + (size_t)t * B * Hd, alpha, energy, enc_len,
+                                               loc ? p->b_filter : nullptr, p->v_a, B, T, E, A, d->sharpening,
+                                               d->sigmoid_smoothing, dctx_t, d_keys, dq_dst, kd < 1.f ? 0 : 1, g->v_a,
+                                               loc ? g->b_filter : nullptr, prev_al, p->conv_filter, d->filter_width,
+                                               p->w_filter, dal_in, dal_out, g->conv_filter, g->w_filter,
+                                               att_ws, att_ws_bytes, stream_))) return rc;
       if (kd < 1.f)
         if ((rc = b2_dropout_rows(dc_tmp, Hd, dh_t, Hd, B, Hd, kd, d->dropout_seed, (uint64_t)t * B * Hd, Hd, 1, stream_))) return rc;
     }

@@ -160,9 +160,6 @@ class AttentionDecoder(object):
             labels = dec_len = None
             L = int(self.max_decode_length)
             sos, eos = int(helper.start_tokens[0].item()), helper.end_token
-        if is_training and self.feed_previous_attention:
-            raise NotImplementedError("training with feed_previous_attention=True is not built "
-                                      "(the reference never feeds previous weights, SURVEY A.7.1)")
         Ls = max(L, 1)
         f32 = dict(dtype=torch.float32, device=dev)
         out_logits = torch.zeros((B, Ls, C), **f32)

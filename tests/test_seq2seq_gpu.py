@@ -91,7 +91,7 @@ def test_seq2seq_loss_and_grads(cuda, attention_type):
     torch.cuda.synchronize()
     cfg = dict(num_layers=2, attention_type=attention_type)
     ref, g_ref = oracle_loss_and_grads(model, cfg, x, seq, labels, lab_len)
-    assert abs(float(loss) - float(ref["total_loss"])) <= 2e-4 * abs(float(ref["total_loss"]))
+    assert abs(float(loss) - float(ref["total_loss"].detach())) <= 2e-4 * abs(float(ref["total_loss"].detach()))
     np.testing.assert_allclose(logits.cpu().numpy(), ref["decoder"]["logits"].detach().numpy(), rtol=2e-4, atol=2e-5)
     check_grads(model, g_ref, 1e-3)
     # the lazily evaluated inference decoder
@@ -111,7 +111,7 @@ def test_seq2seq_options(cuda):
     cfg = dict(num_layers=2, attention_type="hybrid", use_peephole=False, sharpening_factor=2.0,
                sigmoid_smoothing=True, logits_temperature=2.0, weight_decay=1e-3)
     ref, g_ref = oracle_loss_and_grads(model, cfg, x, seq, labels, lab_len)
-    assert abs(float(loss) - float(ref["total_loss"])) <= 2e-4 * abs(float(ref["total_loss"]))
+    assert abs(float(loss) - float(ref["total_loss"].detach())) <= 2e-4 * abs(float(ref["total_loss"].detach()))
     check_grads(model, g_ref, 1e-3)
 
 
@@ -125,7 +125,7 @@ def test_joint_ctc_attention(cuda, faithful):
     model._backward()
     cfg = dict(num_layers=2, attention_type="bahdanau_content", lambda_weight=0.4, ctc_faithful_reshape=faithful)
     ref, g_ref = oracle_loss_and_grads(model, cfg, x, seq, labels, lab_len, ctc_labels)
-    assert abs(float(loss) - float(ref["total_loss"])) <= 2e-4 * abs(float(ref["total_loss"]))
+    assert abs(float(loss) - float(ref["total_loss"].detach())) <= 2e-4 * abs(float(ref["total_loss"].detach()))
     np.testing.assert_allclose(ctc_logits.cpu().numpy(), ref["ctc_logits"].detach().numpy(), rtol=2e-4, atol=2e-5)
     check_grads(model, g_ref, 1e-3)
 
@@ -204,3 +204,25 @@ def test_decoder_and_embedding_dropout(cuda, attention_type):
     l_eval, _, _, _ = model.compute_loss(x, labels, seq, lab_len, 1.0, kd, ke, is_training=False)
     l_ref, _, _, _ = model.compute_loss(x, labels, seq, lab_len, 1.0, 1.0, 1.0, is_training=False)
     assert abs(float(l_eval) - float(l_ref)) < 1e-6
+
+
+@pytest.mark.parametrize("attention_type", ["hybrid", "location"])
+def test_training_with_previous_attention_weights(cuda, attention_type):
+    """feed_previous_attention=True: the location term sees the previous step's weights (the behaviour the
+    reference intends but never reaches).  The gradient then also flows alpha_t -> conv ->
+    alpha_{t-1} across decoder steps and into the conv filter and W_filter."""
+    rng = np.random.RandomState(9)
+    B, T, D, V, Lmax = 4, 22, 12, 7, 8
+    model = build(cuda, attention_type, feed_previous_attention=True)
+    # a wider filter init than truncated_normal(0.2)/0.1 so that its gradient is not negligible
+    x, seq, labels, lab_len, _ = make_batch(rng, B, T, D, V, Lmax)
+    loss, logits, _, _ = model.compute_loss(x, labels, seq, lab_len, 1.0, 1.0, 1.0)
+    model._backward()
+    torch.cuda.synchronize()
+    cfg = dict(num_layers=2, attention_type=attention_type, feed_previous_attention=True)
+    ref, g_ref = oracle_loss_and_grads(model, cfg, x, seq, labels, lab_len)
+    assert abs(float(loss) - float(ref["total_loss"].detach())) <= 2e-4 * abs(float(ref["total_loss"].detach()))
+    np.testing.assert_allclose(logits.cpu().numpy(), ref["decoder"]["logits"].detach().numpy(), rtol=2e-4, atol=2e-5)
+    check_grads(model, g_ref, 1e-3)
+    att = "decoder/attention_decoder/attention_layer/"
+    assert np.abs(g_ref[att + "filter"]).max() > 0 and np.abs(g_ref[att + "W_filter/weights"]).max() > 0
