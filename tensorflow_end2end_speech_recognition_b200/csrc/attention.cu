@@ -447,53 +447,6 @@ attention_bwd_location_kernel(const float* __restrict__ df, const float* __restr
   }
 }
 
-// Beam rows of one utterance share its encoder states: stream enc[u] ONCE per group of RW rows
-// instead of once per row (20 rows x 4 MB per utterance and step otherwise).
-// grid (utterances, column tiles, row groups); thread = (float4 column, time group)
-template <int RW>
-__global__ void __launch_bounds__(512)
-attention_context_shared_kernel(const float* __restrict__ enc, const float* __restrict__ alpha,
-                                const int* __restrict__ enc_len, int T, int E, int rpu,
-                                float* __restrict__ context) {
-  __shared__ float4 red[8][64];
-  const int u = blockIdx.x;
-  const int col = blockIdx.y * 64 + (threadIdx.x & 63);
-  const int tg = threadIdx.x >> 6;
-  const int w0 = blockIdx.z * RW;
-  const int len = min(enc_len[u], T);
-  const int E4 = E / 4;
-  float4 acc[RW];
-#pragma unroll
-  for (int r = 0; r < RW; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (col < E4) {
-    const float4* encb = (const float4*)(enc + (size_t)u * T * E) + col;
-    const float* al = alpha + ((size_t)u * rpu + w0) * T;
-    for (int t = tg; t < len; t += 8) {
-      const float4 h = __ldg(encb + (size_t)t * E4);
-#pragma unroll
-      for (int r = 0; r < RW; ++r) {
-        const float w = (w0 + r < rpu) ? al[(size_t)r * T + t] : 0.f;
-        acc[r].x += w * h.x; acc[r].y += w * h.y; acc[r].z += w * h.z; acc[r].w += w * h.w;
-      }
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < RW; ++r) {
-    red[tg][threadIdx.x & 63] = acc[r];
-    __syncthreads();
-    if (tg == 0 && col < E4 && w0 + r < rpu) {
-      float4 s = acc[r];
-#pragma unroll
-      for (int g = 1; g < 8; ++g) {
-        const float4 o = red[g][threadIdx.x & 63];
-        s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
-      }
-      ((float4*)(context + ((size_t)u * rpu + w0 + r) * E))[col] = s;
-    }
-    __syncthreads();
-  }
-}
-
 }  // namespace b2
 
 using namespace b2;
@@ -555,16 +508,13 @@ int b2::attention_step_forward_rows(int mode, const float* enc, const float* key
   attention_normalise_kernel<<<B, 512, (size_t)T * 4, stream>>>(a);
   B2_LAUNCH_CHECK();
   dim3 cgrid(B, cdiv(E / 4, 64));
-  if (a.rpu > 1 && a.rpu <= 64) {
+  B2_CHECK_ARG(a.rpu <= 64, "attention_step_forward_rows: at most 64 rows per utterance");
+  if (a.rpu > 1) {
     // beam rows of one utterance share its encoder states: context[u] = Alpha[u] [W,T] . enc[u] [T,E], one
     // skinny product per utterance, enc streamed once (weights past enc_len are exactly 0)
     int rc = gemm_skinny_batched(a.rpu, E, T, alpha, T, (int64_t)a.rpu * T, enc, E, (int64_t)T * E, context, E,
                                  (int64_t)a.rpu * E, B / a.rpu, stream);
     if (rc) return rc;
-  } else if (a.rpu > 1) {
-    constexpr int RW = 10;
-    dim3 sgrid(B / a.rpu, cdiv(E / 4, 64), cdiv(a.rpu, RW));
-    attention_context_shared_kernel<RW><<<sgrid, 512, 0, stream>>>(enc, alpha, enc_len, T, E, a.rpu, context);
   } else {
     // enough CTAs to fill the machine: split the time axis when the batch is small
     int nz = 1;

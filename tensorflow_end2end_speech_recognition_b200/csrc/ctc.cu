@@ -235,164 +235,6 @@ ctc_alpha_beta_kernel(const float* __restrict__ logits, const float* __restrict_
   }
 }
 
-// Register-resident variant for S <= 512: ONE WARP per (utterance, direction); lane l owns the
-// SPT consecutive lattice positions s = l*SPT + k, the column lives in registers, the two
-// neighbours that cross a lane boundary come from warp shuffles -- no block barrier in the
-// T-step loop, SPT independent log-sum-exp chains per thread (ILP).  Rows are spilled in the
-// lane-interleaved order index(s) = (s % SPT)*32 + s/SPT so that every store is coalesced;
-// ctc_grad_kernel reads them back through the same map.
-template <int SPT>
-__global__ void __launch_bounds__(128)
-ctc_alpha_beta_warp_kernel(const float* __restrict__ logits, const float* __restrict__ lse,
-                           const int* __restrict__ labels_flat, const int* __restrict__ label_offsets,
-                           const int* __restrict__ seq_len, int T, int B, int C, int blank,
-                           int ignore_longer, float* __restrict__ alpha, float* __restrict__ beta,
-                           float* __restrict__ logp_out, int* __restrict__ skip_out,
-                           float* __restrict__ loss) {
-  constexpr int S_pad = 32 * SPT;
-  const int lane = threadIdx.x & 31;
-  const int job = blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (job >= 2 * B) return;
-  const int b = job >> 1;
-  const bool is_beta = job & 1;
-  const int Tb = min(seq_len[b], T);
-  const int off = label_offsets[b];
-  const int L = label_offsets[b + 1] - off;
-  const int S = 2 * L + 1;
-  const int* lab = labels_flat + off;
-  if (L > Tb && ignore_longer) {
-    if (lane == 0 && !is_beta) { loss[b] = 0.f; logp_out[b] = 0.f; skip_out[b] = 1; }
-    return;
-  }
-  if (Tb <= 0) {
-    if (lane == 0 && !is_beta) {
-      loss[b] = (L == 0) ? 0.f : INFINITY;
-      logp_out[b] = (L == 0) ? 0.f : -INFINITY;
-      skip_out[b] = 1;
-    }
-    return;
-  }
-  if (lane == 0 && !is_beta) skip_out[b] = 0;
-
-  int cls[SPT];
-  bool skip[SPT], valid[SPT];
-#pragma unroll
-  for (int k = 0; k < SPT; ++k) {
-    const int s = lane * SPT + k;
-    valid[k] = s < S;
-    cls[k] = (valid[k] && (s & 1)) ? lab[s >> 1] : blank;
-    skip[k] = false;
-    if (valid[k] && (s & 1)) {
-      if (!is_beta) skip[k] = (s >= 3) && (lab[s >> 1] != lab[(s >> 1) - 1]);
-      else          skip[k] = (s + 2 < S) && (lab[(s >> 1) + 1] != lab[s >> 1]);
-    }
-  }
-  float* out = (is_beta ? beta : alpha) + (int64_t)b * T * S_pad;
-  const int t0 = is_beta ? Tb - 1 : 0;
-  const int dt = is_beta ? -1 : 1;
-  float a[SPT];
-  {
-    const int64_t row = (int64_t)t0 * B + b;
-    const float l = lse[row];
-#pragma unroll
-    for (int k = 0; k < SPT; ++k) {
-      const int s = lane * SPT + k;
-      const bool init = valid[k] && (is_beta ? (s >= S - 2) : (s <= 1));
-      a[k] = init ? logits[row * C + cls[k]] - l : -INFINITY;
-      out[(int64_t)t0 * S_pad + k * 32 + lane] = a[k];
-    }
-  }
-  const int nsteps = Tb - 1;
-  float x0[SPT], x1[SPT];          // raw emissions of the next two steps (prefetch distance 2)
-  float l0 = 0.f, l1 = 0.f;
-  auto fetch = [&](int i, float (&x)[SPT], float& l) {
-    if (i < nsteps) {
-      const int64_t row = (int64_t)(t0 + dt * (i + 1)) * B + b;
-      l = __ldg(&lse[row]);
-#pragma unroll
-      for (int k = 0; k < SPT; ++k) x[k] = valid[k] ? __ldg(&logits[row * C + cls[k]]) : 0.f;
-    }
-  };
-  fetch(0, x0, l0);
-  fetch(1, x1, l1);
-  double offset_sum = 0.0;
-  auto step = [&](int i, float (&x)[SPT], float l) {
-    const int t = t0 + dt * (i + 1);
-    // neighbours across the lane boundary
-    float n1, n2;
-    if (!is_beta) {
-      n1 = __shfl_up_sync(0xffffffffu, a[SPT - 1], 1);
-      n2 = __shfl_up_sync(0xffffffffu, SPT >= 2 ? a[SPT >= 2 ? SPT - 2 : 0] : 0.f, 1);
-      if (SPT == 1) n2 = __shfl_up_sync(0xffffffffu, a[0], 2);
-      if (lane == 0) { n1 = -INFINITY; n2 = -INFINITY; }
-      if (SPT == 1 && lane == 1) n2 = -INFINITY;
-    } else {
-      n1 = __shfl_down_sync(0xffffffffu, a[0], 1);
-      n2 = __shfl_down_sync(0xffffffffu, SPT >= 2 ? a[SPT >= 2 ? 1 : 0] : 0.f, 1);
-      if (SPT == 1) n2 = __shfl_down_sync(0xffffffffu, a[0], 2);
-      if (lane == 31) { n1 = -INFINITY; n2 = -INFINITY; }
-      if (SPT == 1 && lane == 30) n2 = -INFINITY;
-    }
-    float nw[SPT];
-#pragma unroll
-    for (int k = 0; k < SPT; ++k) {
-      float p1, p2;
-      if (!is_beta) {
-        p1 = (k >= 1) ? a[k >= 1 ? k - 1 : 0] : n1;
-        p2 = (k >= 2) ? a[k >= 2 ? k - 2 : 0] : (k == 1 ? n1 : n2);
-        if (SPT >= 2 && k == 0) { p1 = n1; p2 = n2; }
-      } else {
-        p1 = (k + 1 < SPT) ? a[k + 1 < SPT ? k + 1 : 0] : n1;
-        p2 = (k + 2 < SPT) ? a[k + 2 < SPT ? k + 2 : 0] : (k + 1 < SPT ? n1 : n2);
-        if (SPT >= 2 && k == SPT - 1) { p1 = n1; p2 = n2; }
-      }
-      const float v = lse3_nb(a[k], p1, skip[k] ? p2 : -INFINITY) + (x[k] - l);
-      nw[k] = valid[k] ? v : -INFINITY;
-    }
-#pragma unroll
-    for (int k = 0; k < SPT; ++k) {
-      a[k] = nw[k];
-      out[(int64_t)t * S_pad + k * 32 + lane] = nw[k];
-    }
-    if ((i & 15) == 15) {             // renormalise (rows carry arbitrary offsets, see above)
-      float m = -INFINITY;
-#pragma unroll
-      for (int k = 0; k < SPT; ++k) m = fmaxf(m, a[k]);
-      m = warp_max(m);
-      if (m != -INFINITY) {
-#pragma unroll
-        for (int k = 0; k < SPT; ++k) a[k] -= m;
-        offset_sum += (double)m;
-      }
-    }
-  };
-  for (int i = 0; i < nsteps; i += 2) {
-    step(i, x0, l0);
-    fetch(i + 2, x0, l0);
-    if (i + 1 < nsteps) {
-      step(i + 1, x1, l1);
-      fetch(i + 3, x1, l1);
-    }
-  }
-  if (!is_beta) {
-    // alpha(S-1) and alpha(S-2) live in (lane, k) = ((S-1)/SPT, (S-1)%SPT) etc.
-    float fin1 = -INFINITY, fin2 = -INFINITY;
-#pragma unroll
-    for (int k = 0; k < SPT; ++k) {
-      const int s = lane * SPT + k;
-      if (s == S - 1) fin1 = a[k];
-      if (s == S - 2) fin2 = a[k];
-    }
-    fin1 = warp_max(fin1);
-    fin2 = warp_max(fin2);
-    if (lane == 0) {
-      const float lp = (float)((double)lse2(fin1, fin2) + offset_sum);
-      logp_out[b] = lp;
-      loss[b] = -lp;
-    }
-  }
-}
-
 // One warp per (t,b) row.  g[c] = softmax_c - sum_{s: l'(s)=c} alpha*beta/(y*Z_t) with the
 // row-local normaliser Z_t = sum_s alpha*beta/y (= p, independent of per-row lattice shifts).
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
@@ -400,7 +242,7 @@ ctc_grad_kernel(const float* __restrict__ logits, const float* __restrict__ lse,
                 const int* __restrict__ labels_flat, const int* __restrict__ label_offsets,
                 const int* __restrict__ seq_len, const float* __restrict__ alpha,
                 const float* __restrict__ beta, const float* __restrict__ logp_in,
-                const int* __restrict__ skip_in, int T, int B, int C, int blank, int S_pad, int spt,
+                const int* __restrict__ skip_in, int T, int B, int C, int blank, int S_pad,
                 float grad_scale, int warps_per_block, float* __restrict__ grad) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -424,8 +266,7 @@ ctc_grad_kernel(const float* __restrict__ logits, const float* __restrict__ lse,
     const int S = 2 * L + 1;
     const float* ar = alpha + ((int64_t)b * T + t) * S_pad;
     const float* br = beta + ((int64_t)b * T + t) * S_pad;
-    // row layout: identity (block kernel) or lane-interleaved (warp kernel): (s % spt)*32 + s/spt
-    auto ix = [&](int s) { return spt > 0 ? (s % spt) * 32 + s / spt : s; };
+    auto ix = [&](int s) { return s; };
     const float xb = x[blank] - l;
     // pass 1: Z = logsumexp_s (alpha + beta - lp): equals log p up to the per-row shifts
     float m = -INFINITY;
@@ -464,12 +305,7 @@ struct CtcWs {
 };
 
 static size_t ctc_ws_layout(int T, int B, int max_label_len, void* base, CtcWs* w) {
-  int S_pad = (int)align_up(2 * (size_t)max_label_len + 1, 32);
-  if (2 * max_label_len + 1 <= 512) {          // warp kernel rows are 32*SPT wide (SPT power of two)
-    int spt = 1;
-    while (32 * spt < 2 * max_label_len + 1) spt *= 2;
-    S_pad = 32 * spt;
-  }
+  const int S_pad = (int)align_up(2 * (size_t)max_label_len + 1, 32);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
   size_t o_lse = take((size_t)T * B * 4);
@@ -517,24 +353,7 @@ extern "C" int b2_ctc_loss_grad(const float* logits, const int32_t* labels_flat,
   B2_LAUNCH_CHECK();
 
   const int S_max = 2 * max_label_len + 1;
-  int grad_spt = 0;
-  static const int use_warp = getenv("B2_CTC_WARP") ? atoi(getenv("B2_CTC_WARP")) : 0;
-  if (S_max <= 512 && use_warp) {
-    // register-resident warp kernel: S_pad = 32*SPT <= workspace S_pad (both are multiples of 32)
-    int spt = 1;
-    while (32 * spt < S_max) spt *= 2;
-    grad_spt = spt;
-    const int blocks = cdiv(2 * B, 4);
-#define LAUNCH_W(SPT)                                                                        \
-    ctc_alpha_beta_warp_kernel<SPT><<<blocks, 128, 0, stream>>>(                             \
-        logits, w.lse, labels_flat, label_offsets, seq_len, T, B, C, blank, ignore_longer,   \
-        w.alpha, w.beta, w.logp, w.skip, loss)
-    if (spt == 1) LAUNCH_W(1); else if (spt == 2) LAUNCH_W(2); else if (spt == 4) LAUNCH_W(4);
-    else if (spt == 8) LAUNCH_W(8); else LAUNCH_W(16);
-#undef LAUNCH_W
-    B2_LAUNCH_CHECK();
-    w.S_pad = 32 * spt;
-  } else {
+  {
     int NT = (int)align_up((size_t)S_max, 32);
     int spt = 1;
     while (NT > 1024) { spt *= 2; NT = (int)align_up((size_t)cdiv(S_max, spt), 32); }
@@ -564,7 +383,7 @@ extern "C" int b2_ctc_loss_grad(const float* logits, const int32_t* labels_flat,
                                  (int)gsmem));
     ctc_grad_kernel<<<cdiv(rows, wpb), wpb * 32, gsmem, stream>>>(
         logits, w.lse, labels_flat, label_offsets, seq_len, w.alpha, w.beta, w.logp, w.skip, T,
-        B, C, blank, w.S_pad, grad_spt, grad_scale, wpb, grad);
+        B, C, blank, w.S_pad, grad_scale, wpb, grad);
     B2_LAUNCH_CHECK();
   }
   return B2_OK;

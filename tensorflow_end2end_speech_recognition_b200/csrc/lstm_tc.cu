@@ -139,54 +139,6 @@ __global__ void unpack_lstm_grads_kernel(const float* __restrict__ dwx, const fl
   }
 }
 
-// bias + peephole gradients from the packed bf16 dG and the saved cell states
-// grid = (ceil(H/32), slabs, 2 dirs); block 256 = 8 row-lanes x 32 units
-__global__ void __launch_bounds__(256)
-tc_small_grads_kernel(const __nv_bfloat16* __restrict__ dG, const float* __restrict__ cs,
-                      const int* __restrict__ seq_len, int T, int B, int H, int use_peephole,
-                      float* __restrict__ dbias, float* dwi0, float* dwf0, float* dwo0,
-                      float* dwi1, float* dwf1, float* dwo1) {
-  __shared__ float sh[7][8][33];
-  const int dir = blockIdx.z;
-  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
-  const int u = blockIdx.x * 32 + lane;
-  float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // db_i, db_g, db_f, db_o, dwi, dwf, dwo
-  if (u < H) {
-    const int64_t rows = (int64_t)T * B;
-    for (int64_t r = (int64_t)blockIdx.y * 8 + wy; r < rows; r += (int64_t)gridDim.y * 8) {
-      const int t = (int)(r / B), b = (int)(r % B);
-      const int len = seq_len[b];
-      if (t >= len) continue;
-      const uint2 raw = *(const uint2*)(dG + r * 8 * H + (size_t)dir * 4 * H + u * 4);
-      const float dzi = __uint_as_float(raw.x << 16), dzg = __uint_as_float(raw.x & 0xffff0000u);
-      const float dzf = __uint_as_float(raw.y << 16), dzo = __uint_as_float(raw.y & 0xffff0000u);
-      acc[0] += dzi; acc[1] += dzg; acc[2] += dzf; acc[3] += dzo;
-      if (use_peephole) {
-        const float c = cs[(r * 2 + dir) * H + u];
-        const int tp = dir == 0 ? t - 1 : t + 1;
-        float cp = 0.f;
-        if (tp >= 0 && tp < T && tp < len) cp = cs[(((int64_t)tp * B + b) * 2 + dir) * H + u];
-        acc[4] = fmaf(dzi, cp, acc[4]); acc[5] = fmaf(dzf, cp, acc[5]); acc[6] = fmaf(dzo, c, acc[6]);
-      }
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 7; ++k) sh[k][wy][lane] = acc[k];
-  __syncthreads();
-  if (wy == 0 && u < H) {
-#pragma unroll
-    for (int k = 0; k < 7; ++k)
-      for (int j = 1; j < 8; ++j) acc[k] += sh[k][j][lane];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) atomicAdd(&dbias[(size_t)dir * 4 * H + u * 4 + g], acc[g]);
-    if (use_peephole) {
-      atomicAdd((dir ? dwi1 : dwi0) + u, acc[4]);
-      atomicAdd((dir ? dwf1 : dwf0) + u, acc[5]);
-      atomicAdd((dir ? dwo1 : dwo0) + u, acc[6]);
-    }
-  }
-}
-
 // ------------------------------------------------------------------ kernel timers
 // Optional CUDA-event timers around the recurrence launches (bench.py's live roofline).
 static bool g_prof_on = false;

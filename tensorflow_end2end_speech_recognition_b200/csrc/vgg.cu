@@ -206,7 +206,6 @@ static int ew_blocks(int64_t n) {
   return (int)(b < 1 ? 1 : b);
 }
 
-constexpr int kCh[5] = {3, 64, 64, 128, 128};
 
 struct VggBuf {
   Geo g0, g2, g4;
