@@ -679,7 +679,7 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
         // ---- A) dh_rec = sum of the peers' partial slices
         float dh_rec[4] = {0.f, 0.f, 0.f, 0.f};
         if (s > 0) {
-          mbar_wait_cluster(&rfull[c * 2 + p], (rph >> p) & 1u);   // measured: 7.16 vs 7.6 ms/layer with CTA scope
+          mbar_wait_cluster(&rfull[c * 2 + p], (rph >> p) & 1u);   // measured (twice): 7.15 vs 7.9 ms/layer with a CTA-scope wait
           rph ^= 1u << p;
           const uint8_t* rb = smem + L::kRecvOff + (c * 2 + p) * 16384 + (ul * 16 + gq * 4) * 2;
           for (int src = 0; src < CS; ++src) {
