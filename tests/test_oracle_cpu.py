@@ -207,3 +207,24 @@ def test_input_pipeline_oracle_against_reference_golden():
                                      [[1, 2], [3], [4, 5, 6]], num_gpu=2)
     assert [a.shape for a in ins] == [(2, 5, 3), (1, 5, 3)] and labs[0].tolist() == [[1, 2, -1], [3, -1, -1]]
     assert lens[1].tolist() == [4]
+
+
+def test_beam_search_oracle_width_one_is_greedy():
+    """oracle beam search with one beam and no length penalty follows the arg-max path of the greedy oracle."""
+    from oracle import attention_decoder as odec
+    rng = np.random.RandomState(2)
+    T, E, Hd, emb, C = 9, 8, 6, 4, 7
+    p = {"W_embedding": rng.randn(C, emb), "attentional_vector/weights": rng.randn(Hd + E, Hd) * .3,
+         "output_layer/weights": rng.randn(Hd, C), "output_layer/biases": rng.randn(C) * .1,
+         "cell": {"kernel": rng.randn(emb + E + Hd, 4 * Hd) * .3, "bias": np.zeros(4 * Hd)},
+         "attention": {"W_keys/weights": rng.randn(E, Hd) * .3}}
+    enc = rng.randn(1, T, E)
+    st = (rng.randn(1, Hd) * .1, rng.randn(1, Hd) * .1)
+    g = odec.decode(p, "luong_general", enc, np.array([T]), st, sos=5, eos=6, max_decode_length=8)
+    b = odec.beam_search_decode(p, "luong_general", enc[0], T, (st[0][0], st[1][0]), 5, 6, 1, 0.0, 8)
+    gi = g["predicted_ids"][0]
+    n = min(len(gi), b["ids"].shape[1])
+    assert np.array_equal(b["ids"][0, :n], gi[:n])
+    # wider beams never score worse than the greedy path
+    b4 = odec.beam_search_decode(p, "luong_general", enc[0], T, (st[0][0], st[1][0]), 5, 6, 4, 0.0, 8)
+    assert b4["log_probs"].max() >= b["log_probs"][0] - 1e-9
