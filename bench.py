@@ -29,7 +29,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 CFG = dict(input_size=80, num_units=512, num_layers=5, num_classes=28, T=1000, B=64,
-           label_min=150, label_max=250, optimizer="rmsprop", lr=1e-3, clip=5.0)
+           label_min=150, label_max=250, optimizer="rmsprop", lr=1e-3, clip=5.0,
+           keep_prob=float(os.environ.get("B2_BENCH_KEEP_PROB", "0.8")))   # dropout 0.2: blstm_ctc_960h_char.yml:34
 # forward MAC count of the gate GEMMs, x3 for training
 FWD_FLOP_PER_FRAME = 2 * 2 * (80 + 512) * 2048 + 4 * 2 * 2 * (1024 + 512) * 2048   # 55.18 M
 
@@ -186,7 +187,7 @@ def main():
     x_dev, seq_dev = x_host.to(dev), seq_host.to(dev)
 
     def step(xin, sin):
-        loss, _ = model.compute_loss(xin, labels, sin, keep_prob=1.0)
+        loss, _ = model.compute_loss(xin, labels, sin, keep_prob=CFG["keep_prob"])
         model.train(loss, CFG["optimizer"], CFG["lr"])
         return loss
 
@@ -376,7 +377,8 @@ def main():
                "data": "synthetic",
                "config": {"workload": "BASELINE configs[1]: LibriSpeech-shape char CTC, 5x512 BLSTM "
                                       "(LSTMBlockCell, peephole), 80-d input, T=1000, B=64 per GPU, "
-                                      "28 chars + blank, labels 150-250, rmsprop lr 1e-3, clip_by_norm 5",
+                                      "28 chars + blank, labels 150-250, rmsprop lr 1e-3, clip_by_norm 5, "
+                                      "dropout keep_prob %.2f" % CFG["keep_prob"],
                           "global_batch": B * world, "parallelism": "dp%d" % world,
                           "l2": "per-step working set (reserve + gate buffers, >8 GB) >> 126 MB L2, "
                                 "no explicit flush"},
