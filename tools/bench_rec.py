@@ -13,14 +13,14 @@ from tensorflow_end2end_speech_recognition_b200 import ops  # noqa: E402
 dev = torch.device("cuda:0")
 
 
-def bench(T, B, D, H, prec, backward, iters=5, label=""):
+def bench(T, B, D, H, prec, backward, iters=5, label="", keep_prob=1.0):
     layer = olstm.init_blstm_params(D, H, 1, parameter_init=0.1, seed=0)[0]
     P = {d: {k: torch.tensor(v, device=dev) for k, v in layer[d].items()} for d in layer}
     G = {d: {k: torch.zeros_like(v) for k, v in P[d].items()} for d in P}
     x = torch.randn(T, B, D, device=dev)
     dy = torch.randn(T, B, 2 * H, device=dev)
     seq = torch.full((B,), T, dtype=torch.int32, device=dev)
-    desc = ops.lstm_desc(T, B, D, H, precision=prec, need_backward=backward)
+    desc = ops.lstm_desc(T, B, D, H, precision=prec, need_backward=backward, keep_prob=keep_prob, dropout_seed=7)
 
     def run():
         y, fs, res = ops.blstm_layer_forward(desc, x, seq, P["fw"], P["bw"])
@@ -46,6 +46,9 @@ if __name__ == "__main__":
         os.environ["B2_REC_NCHAIN"] = str(nch)
         bench(1000, 64, 1024, 512, ops.PREC_BF16, bwd, label="bf16 tc nchain=%d %s" % (nch, "fwd+bwd" if bwd else "fwd"))
     os.environ.pop("B2_REC_NCHAIN")
+    bench(1000, 64, 1024, 512, ops.PREC_BF16, bwd, label="bf16 tc keep_prob=0.8", keep_prob=0.8)
+    bench(1000, 64, 1024, 512, ops.PREC_BF16, False, label="bf16 tc keep_prob=0.8 fwd only", keep_prob=0.8)
+    bench(1000, 64, 1024, 512, ops.PREC_BF16, False, label="bf16 tc keep_prob=1.0 fwd only")
     bench(1000, 16, 1024, 512, ops.PREC_BF16, bwd, label="bf16 tc B=16")
     bench(1000, 32, 1024, 512, ops.PREC_BF16, bwd, label="bf16 tc B=32")
     bench(300, 8, 120, 256, ops.PREC_BF16, bwd, label="bf16 tc cfg1")
