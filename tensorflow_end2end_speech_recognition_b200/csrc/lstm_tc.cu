@@ -27,6 +27,7 @@ struct TcWork {
   float* dwx;                // [D, 8H] fp32 packed weight gradient (scratch)
   float* dwh;                // [2][H, 4H] fp32 packed recurrent weight gradient (scratch)
   float* dbias;              // [8H]
+  float* dym;                // [TB, 2H] dropout-masked dy (backward, keep_prob < 1 only)
 };
 
 static size_t tc_work_layout(const b2_lstm_desc* d, void* base, TcWork* w) {
@@ -49,6 +50,7 @@ static size_t tc_work_layout(const b2_lstm_desc* d, void* base, TcWork* w) {
   const size_t odwx1 = take(D * 8 * H * 4);
   const size_t odwh1 = take(2 * H * 4 * H * 4);
   const size_t odb1 = take(8 * H * 4);
+  const size_t odym = d->keep_prob < 1.f ? take(TB * 2 * H * 4) : 0;
   if (w) {
     char* p = (char*)base;
     w->G = (float*)(p + oG); w->dG = (__nv_bfloat16*)(p + oG); w->xb = (__nv_bfloat16*)(p + oxb);
@@ -58,8 +60,27 @@ static size_t tc_work_layout(const b2_lstm_desc* d, void* base, TcWork* w) {
     w->dG2[0] = w->dG; w->dwx2[0] = w->dwx; w->dwh2[0] = w->dwh; w->dbias2[0] = w->dbias;
     w->dG2[1] = (__nv_bfloat16*)(p + oG1); w->dwx2[1] = (float*)(p + odwx1);
     w->dwh2[1] = (float*)(p + odwh1); w->dbias2[1] = (float*)(p + odb1);
+    w->dym = d->keep_prob < 1.f ? (float*)(p + odym) : nullptr;
   }
   return off;
+}
+
+// DropoutWrapper backward, hoisted out of the BPTT kernel: dy_masked[i] = keep(seed, i) ? dy[i]/keep : 0 over the
+// [T,B,2H] layout (the element index IS the mask counter).  Inside the kernel the hash sat on the dependent chain of the
+// gate-math warps (+0.29 ms per layer at config 2); as a streaming pass it costs the HBM time of 2 x 262 MB.
+__global__ void __launch_bounds__(256)
+dropout_mask_dy_kernel(const float* __restrict__ dy, float* __restrict__ out, int64_t n4, float keep,
+                       unsigned long long seed) {
+  const float sc = 1.f / keep;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = ((const float4*)dy)[i];
+    const uint64_t e = (uint64_t)i * 4;
+    v.x = dropout_keep(seed, e, keep) ? v.x * sc : 0.f;
+    v.y = dropout_keep(seed, e + 1, keep) ? v.y * sc : 0.f;
+    v.z = dropout_keep(seed, e + 2, keep) ? v.z * sc : 0.f;
+    v.w = dropout_keep(seed, e + 3, keep) ? v.w * sc : 0.f;
+    ((float4*)out)[i] = v;
+  }
 }
 
 // ---------------------------------------------------------------- packing kernels
@@ -308,6 +329,15 @@ int tc_layer_backward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16
   }
   ba.use_peephole = d->use_peephole; ba.cell_clip = d->cell_clip; ba.keep_prob = d->keep_prob;
   ba.seed = d->dropout_seed; ba.gates = r.gates; ba.cs = r.cs; ba.dG = dG; ba.dfinal = d_final_state;
+  if (d->keep_prob < 1.f && (((size_t)TB * 2 * H) % 4 == 0)) {     // mask dy once, outside the recurrence
+    const int64_t n4 = (int64_t)TB * 2 * H / 4;
+    int64_t blocks = (n4 + 255) / 256;
+    if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+    dropout_mask_dy_kernel<<<(int)blocks, 256, 0, stream>>>(dy, w.dym, n4, d->keep_prob, d->dropout_seed);
+    B2_LAUNCH_CHECK();
+    dy = w.dym;
+    ba.keep_prob = 1.f;
+  }
   B2_CUDA(cudaMemsetAsync(dbias, 0, (size_t)8 * H * 4, stream));
   ba.dbias = dbias;
   ba.dbg = nullptr;
