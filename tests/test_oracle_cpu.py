@@ -228,3 +228,85 @@ def test_beam_search_oracle_width_one_is_greedy():
     # wider beams never score worse than the greedy path
     b4 = odec.beam_search_decode(p, "luong_general", enc[0], T, (st[0][0], st[1][0]), 5, 6, 4, 0.0, 8)
     assert b4["log_probs"].max() >= b["log_probs"][0] - 1e-9
+
+
+def test_vgg_oracle_two_forms_and_geometry():
+    """oracle/vgg.py: the torch conv / pool form against literal numpy loops (SAME padding, pooling tails)."""
+    import torch
+    from oracle import vgg as ovgg
+    rng = np.random.RandomState(0)
+    for (H, W) in ((7, 1), (6, 3), (5, 4), (1, 1)):
+        x = rng.randn(2, H, W, 3)
+        w = rng.randn(3, 3, 3, 5)
+        b = rng.randn(5)
+        a = ovgg._conv_relu(torch.tensor(x), torch.tensor(w), torch.tensor(b)).numpy()
+        np.testing.assert_allclose(a, ovgg.conv_relu_numpy(x, w, b), atol=1e-12)
+        np.testing.assert_allclose(ovgg._pool(torch.tensor(a)).numpy(), ovgg.max_pool_numpy(a), atol=0)
+    assert ovgg.output_geometry(80, 1) == (20, 1) and ovgg.output_geometry(7, 3) == (2, 1)
+    # whole front-end: shapes and a 1-wide image never touches the side columns of the filters
+    nch, Wd = 6, 1
+    p = {}
+    chans = (3, 64, 64, 128, 128)
+    for i, n in enumerate(ovgg.CONVS):
+        p[n + "/weight"] = torch.tensor(rng.randn(3, 3, chans[i], chans[i + 1]) * 0.05, requires_grad=True)
+        p[n + "/bias"] = torch.zeros(chans[i + 1], dtype=torch.float64)
+    h4, w4 = ovgg.output_geometry(nch, Wd)
+    p["bridge/weights"] = torch.tensor(rng.randn(h4 * w4 * 128, 256) * 0.05)
+    p["bridge/biases"] = torch.zeros(256, dtype=torch.float64)
+    out = ovgg.vgg_frontend(torch.tensor(rng.randn(2, 3, nch * Wd * 3)), p, nch, Wd)
+    assert out.shape == (2, 3, 256)
+    out.sum().backward()
+    g = p["VGG1/conv2/weight"].grad.numpy()
+    assert np.all(g[:, 0] == 0) and np.all(g[:, 2] == 0) and np.abs(g[:, 1]).max() > 0
+
+
+def test_seq2seq_oracle_loss_gradient_matches_finite_differences():
+    """oracle/seq2seq.py end to end on CPU (encoder -> bridge -> teacher-forced decoder -> sequence loss, and the
+    joint CTC-attention total): autograd gradient of a few parameters vs central differences."""
+    import torch
+    from oracle import lstm as olstm, seq2seq as os2s
+    rng = np.random.RandomState(3)
+    B, T, D, H, Hd, A, emb, V = 2, 6, 4, 3, 5, 4, 3, 4
+    C = V + 2
+    layers = olstm.init_blstm_params(D, H, 1, parameter_init=0.3, seed=1, dtype=np.float64)
+    vs = {}
+    for d in ("fw", "bw"):
+        for k, v in layers[0][d].items():
+            vs["encoder/blstm_hidden1/%s/lstm_cell/%s" % (d, k)] = v
+    r = lambda *s: rng.randn(*s) * 0.3
+    vs.update({"decoder/bridge/weights": r(4 * H, 2 * Hd), "decoder/bridge/biases": r(2 * Hd),
+               "decoder/output_embedding/W_embedding": r(C, emb),
+               "decoder/decoder_rnn_cell/lstm_cell/kernel": r(emb + 2 * H + Hd, 4 * Hd),
+               "decoder/decoder_rnn_cell/lstm_cell/bias": r(4 * Hd),
+               "decoder/attention_decoder/attention_layer/W_query/weights": r(Hd, A),
+               "decoder/attention_decoder/attention_layer/W_keys/weights": r(2 * H, A),
+               "decoder/attention_decoder/attention_layer/W_keys/biases": r(A),
+               "decoder/attention_decoder/attention_layer/v_a": r(A),
+               "decoder/attention_decoder/attentional_vector/weights": r(Hd + 2 * H, Hd),
+               "decoder/attention_decoder/output_layer/weights": r(Hd, C),
+               "decoder/attention_decoder/output_layer/biases": r(C),
+               "ctc_output/weights": r(2 * H, V + 1), "ctc_output/biases": r(V + 1)})
+    x = rng.randn(B, T, D)
+    seq = np.array([6, 4])
+    labels = np.array([[V, 1, 2, V + 1], [V, 3, V + 1, V + 1]])
+    lab_len = np.array([4, 3])
+    ctc_labels = [[1, 2], [3]]
+    cfg = dict(num_layers=1, attention_type="bahdanau_content", lambda_weight=0.3, weight_decay=1e-2)
+
+    def loss_of(values):
+        t = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in values.items()}
+        out = os2s.seq2seq_loss(t, cfg, torch.tensor(x), seq, labels, lab_len, ctc_labels)
+        return out["total_loss"], t
+    loss, t = loss_of(vs)
+    loss.backward()
+    for name, idx in (("decoder/attention_decoder/attention_layer/v_a", (1,)),
+                      ("encoder/blstm_hidden1/bw/lstm_cell/kernel", (2, 5)),
+                      ("decoder/bridge/weights", (3, 4)), ("ctc_output/weights", (1, 2)),
+                      ("decoder/output_embedding/W_embedding", (1, 0))):
+        eps = 1e-6
+        vp = {k: v.copy() for k, v in vs.items()}
+        vm = {k: v.copy() for k, v in vs.items()}
+        vp[name][idx] += eps
+        vm[name][idx] -= eps
+        fd = (float(loss_of(vp)[0].detach()) - float(loss_of(vm)[0].detach())) / (2 * eps)
+        assert abs(fd - float(t[name].grad[idx])) <= 1e-6 + 1e-5 * abs(fd), (name, fd, float(t[name].grad[idx]))
