@@ -532,6 +532,11 @@ int b2_clip_by_norm_multi(float* const* grads, const int64_t* sizes, int n,
 /* y_k += alpha * x_k over n tensors (weight-decay gradient wd*w, ctc.py:280-286) */
 int b2_axpy_multi(float* const* xs, float* const* ys, const int64_t* sizes, int n,
                   float alpha, b2_stream_t stream);
+/* Tower mean   replaces average_gradients, utils/training/multi_gpu.py:13-48 (tf.concat + reduce_mean
+ * per variable on /cpu:0): dst[i] = mean_k srcs[k][i] over n_src <= 16 device buffers of n floats.
+ * srcs is a HOST array of device pointers; dst may alias srcs[0]. */
+int b2_tower_mean(const float* const* srcs, int n_src, float* dst, int64_t n,
+                  b2_stream_t stream);
 /* TF-1.x update rules; state0/state1 per tensor (may be NULL
  * where the rule needs none); step = 1-based global step (Adam). */
 int b2_optimizer_step_multi(int kind, float* const* params,
@@ -539,6 +544,34 @@ int b2_optimizer_step_multi(int kind, float* const* params,
                             float* const* state1, const int64_t* sizes, int n,
                             float learning_rate, int64_t step,
                             b2_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * Gradient exchange of the data-parallel step   replaces average_gradients,
+ *   utils/training/multi_gpu.py:13-48, as called at
+ *   examples/librispeech/training/train_ctc.py:143 (the synchronisation point
+ *   of the towers).  One communicator rank per GPU; NCCL (>= 2.10) is bound at
+ *   run time, b2_comm_available() returns its version or 0.
+ *   Bootstrap: rank 0 calls b2_comm_get_unique_id (128 bytes), the caller ships
+ *   the id to the other ranks (any side channel), every rank calls
+ *   b2_comm_init_rank with its own device current.
+ * ------------------------------------------------------------------------ */
+typedef void* b2_comm_t;
+#define B2_COMM_ID_BYTES 128
+int b2_comm_available(void);
+int b2_comm_get_unique_id(void* id_out);
+int b2_comm_init_rank(b2_comm_t* comm_out, int nranks, const void* id, int rank);
+/* one communicator per local device of a single process (in-graph towers) */
+int b2_comm_init_all(b2_comm_t* comms_out, int ndev, const int* devices);
+int b2_comm_size(b2_comm_t comm);
+int b2_comm_destroy(b2_comm_t comm);
+/* in-place mean over ranks of n_buckets device buffers (HOST arrays of pointers
+ * and element counts), one NCCL group call on `stream` */
+int b2_allreduce_mean(b2_comm_t comm, float* const* buckets, const int64_t* sizes,
+                      int n_buckets, b2_stream_t stream);
+/* single-process form: buffer k (n floats) lives on the device of comms[k] and
+ * is reduced on streams[k]; all ndev calls inside one group */
+int b2_allreduce_mean_local(const b2_comm_t* comms, float* const* buffers, int64_t n,
+                            int ndev, const b2_stream_t* streams);
 
 #ifdef __cplusplus
 }

@@ -136,7 +136,16 @@ PROTOTYPES = {
     "b2_colsum": (_i, [_p, _i64, _i, _i, _p, _i, _p]),
     "b2_clip_by_norm_multi": (_i, [_p, _p, _i, _f, _f, _p, _p]),
     "b2_axpy_multi": (_i, [_p, _p, _p, _i, _f, _p]),
+    "b2_tower_mean": (_i, [_p, _i, _p, _i64, _p]),
     "b2_optimizer_step_multi": (_i, [_i, _p, _p, _p, _p, _p, _i, _f, _i64, _p]),
+    "b2_comm_available": (_i, []),
+    "b2_comm_get_unique_id": (_i, [_p]),
+    "b2_comm_init_rank": (_i, [C.POINTER(C.c_void_p), _i, _p, _i]),
+    "b2_comm_init_all": (_i, [C.POINTER(C.c_void_p), _i, C.POINTER(C.c_int)]),
+    "b2_comm_size": (_i, [_p]),
+    "b2_comm_destroy": (_i, [_p]),
+    "b2_allreduce_mean": (_i, [_p, _p, _p, _i, _p]),
+    "b2_allreduce_mean_local": (_i, [_p, _p, _i64, _i, _p]),
 }
 
 _lib = None

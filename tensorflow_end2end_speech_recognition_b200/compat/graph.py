@@ -56,6 +56,16 @@ class OpOutput(Tensor):
         self.name = "%s:%d" % (op.name, index)
 
 
+class LazyGradsAndVars(Tensor):
+    """What ``optimizer.compute_gradients(tower_loss)`` / ``model._clip_gradients(...)`` /
+    ``average_gradients(...)`` hand around in graph mode (examples/librispeech/training/train_ctc.py:112-143):
+    a handle on the op that, when run, yields the tower's ``[(grad, var)]`` list."""
+
+    def __init__(self, op):
+        self.op = op
+        self.name = op.name
+
+
 class Constant(Tensor):
     def __init__(self, value):
         self.value = value
@@ -103,6 +113,8 @@ class _Run(object):
             return x.value
         if isinstance(x, OpOutput):
             return self.resolve(x.op)[x.index]
+        if isinstance(x, LazyGradsAndVars):
+            return self.resolve(x.op)
         if isinstance(x, Op):
             if id(x) in self.feed:                       # TF allows feeding any tensor
                 return self.feed[id(x)]

@@ -216,9 +216,24 @@ class _Train(object):
             pass
 
         def save(self, sess, save_path, global_step=None):
+            """A TF Saver stores every global variable: the trainable ones, the optimizer slots and the step
+            counters.  Same here (slot-style names under ``<model index>/optimizer/``); the container is an
+            .npz keyed by TF variable names, NOT the TF checkpoint format."""
             path = save_path if global_step is None else "%s-%d" % (save_path, global_step)
-            arrays = {v.name: v.tensor.detach().cpu().numpy() for m in sess.graph.models
-                      for v in m.trainable_variables()}
+            arrays = {}
+            for i, m in enumerate(sess.graph.models):
+                for v in m.trainable_variables():
+                    arrays[v.name] = v.tensor.detach().cpu().numpy()
+                arrays["%d/model_step" % i] = np.asarray(getattr(m, "_step", 0), np.int64)
+                opt = getattr(m, "optimizer", None)
+                if opt is not None:
+                    pre = "%d/optimizer/" % i
+                    arrays[pre + "name"] = np.asarray(opt.name)
+                    arrays[pre + "global_step"] = np.asarray(opt.global_step, np.int64)
+                    for k in ("state0", "state1"):
+                        st = getattr(opt, k, None)
+                        if st is not None:
+                            arrays[pre + k] = st.detach().cpu().numpy()
             np.savez(path + ".npz", **arrays)
             with open(os.path.join(os.path.dirname(path) or ".", "checkpoint"), "w") as f:
                 f.write('model_checkpoint_path: "%s"\n' % path)
@@ -227,9 +242,20 @@ class _Train(object):
         def restore(self, sess, save_path):
             import torch
             data = np.load(save_path + ".npz")
-            for m in sess.graph.models:
+            for i, m in enumerate(sess.graph.models):
                 for v in m.trainable_variables():
                     v.tensor.copy_(torch.as_tensor(data[v.name]).to(v.tensor.device))
+                if "%d/model_step" % i in data:
+                    m._step = int(data["%d/model_step" % i])
+                pre = "%d/optimizer/" % i
+                if pre + "name" in data:
+                    state = {k: data[pre + k] for k in ("state0", "state1", "global_step") if pre + k in data}
+                    state["name"] = str(data[pre + "name"])
+                    opt = getattr(m, "optimizer", None)
+                    if opt is not None and opt.name == state["name"]:
+                        opt.load_state(state)
+                    else:                       # the optimizer is created by the first train(): hand it over then
+                        m._restored_optimizer_state = state
 
     @staticmethod
     def get_checkpoint_state(checkpoint_dir):

@@ -101,10 +101,22 @@ ctc_alpha_beta_kernel(const float* __restrict__ logits, const float* __restrict_
       else          skip[k] = (s + 2 < S) && (lab[(s >> 1) + 1] != lab[s >> 1]);
     }
   }
+  // label values index logits rows and shared gradient bins: reject anything outside [0, C) or equal to
+  // the blank (tf.nn.ctc_loss raises InvalidArgument; here the utterance gets loss NaN and a zero gradient,
+  // the host wrapper raises before launching)
+  {
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < SPT; ++k)
+      if (valid[k] && ((tid + k * NT) & 1)) bad |= (cls[k] < 0) | (cls[k] >= C) | (cls[k] == blank);
+    if (__syncthreads_or(bad)) {
+      if (tid == 0 && !is_beta) { loss[b] = __int_as_float(0x7fc00000); logp_out[b] = 0.f; skip_out[b] = 1; }
+      return;
+    }
+  }
   float* out = (is_beta ? beta : alpha) + (int64_t)b * T * S_pad;
   const int t0 = is_beta ? Tb - 1 : 0;
   const int dt = is_beta ? -1 : 1;
-  __syncthreads();
 
   // t = t0 (initial column)
   {

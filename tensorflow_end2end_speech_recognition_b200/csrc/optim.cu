@@ -142,9 +142,64 @@ static int grid_for(int64_t n) {
   return (int)b;
 }
 
+// Tower mean (utils/training/multi_gpu.py:13-48): dst[i] = (1/n_src) * sum_k srcs[k][i].  dst may alias
+// srcs[0].  One streaming pass: n_src reads + 1 write per element, float4 when everything is 16-byte aligned.
+constexpr int kMaxTowers = 16;
+struct TowerPtrs { const float* p[kMaxTowers]; };
+
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+tower_mean_kernel(TowerPtrs srcs, int n_src, float* __restrict__ dst, int64_t n, float inv) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (VEC) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      float4 a = ((const float4*)srcs.p[0])[i];
+      for (int k = 1; k < n_src; ++k) {
+        const float4 b = ((const float4*)srcs.p[k])[i];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
+      ((float4*)dst)[i] = a;
+    }
+    for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      float a = srcs.p[0][i];
+      for (int k = 1; k < n_src; ++k) a += srcs.p[k][i];
+      dst[i] = a * inv;
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      float a = srcs.p[0][i];
+      for (int k = 1; k < n_src; ++k) a += srcs.p[k][i];
+      dst[i] = a * inv;
+    }
+  }
+}
+
 }  // namespace b2
 
 using namespace b2;
+
+extern "C" int b2_tower_mean(const float* const* srcs_host, int n_src, float* dst, int64_t n,
+                             b2_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B2_CHECK_ARG(srcs_host && dst && n > 0, "b2_tower_mean: bad argument");
+  B2_CHECK_ARG(n_src >= 1 && n_src <= kMaxTowers, "b2_tower_mean: 1..%d towers, got %d", kMaxTowers, n_src);
+  TowerPtrs tp;
+  bool vec = ((uintptr_t)dst & 15) == 0;
+  for (int k = 0; k < n_src; ++k) {
+    B2_CHECK_ARG(srcs_host[k] != nullptr, "b2_tower_mean: tower %d is null", k);
+    tp.p[k] = srcs_host[k];
+    vec = vec && (((uintptr_t)srcs_host[k] & 15) == 0);
+  }
+  int64_t blocks = (n / 4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  if (vec) tower_mean_kernel<true><<<(int)blocks, 256, 0, stream>>>(tp, n_src, dst, n, 1.f / n_src);
+  else tower_mean_kernel<false><<<(int)blocks, 256, 0, stream>>>(tp, n_src, dst, n, 1.f / n_src);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
 
 extern "C" int b2_clip_by_norm_multi(float* const* grads, const int64_t* sizes, int n,
                                      float clip_norm, float post_scale, float* norms,

@@ -91,6 +91,7 @@ class JointCTCAttention(AttentionSeq2Seq):
             ctc_lists = sparse_to_label_lists(ctc_labels, B)
         else:
             ctc_lists = [list(l) for l in ctc_labels]
+        ops.check_labels(ctc_lists, self.ctc_num_classes, self.ctc_num_classes - 1, what="ctc_labels")
         logits, out_train, out_infer, enc_bm = self._build(
             inputs, labels, inputs_seq_len, labels_seq_len, keep_prob_encoder, keep_prob_decoder,
             keep_prob_embedding, is_training)

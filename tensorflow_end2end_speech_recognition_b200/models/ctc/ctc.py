@@ -152,23 +152,35 @@ class CTC(ModelBase):
                             self.variables["output/biases"], prec)
         return logits2d.view(T, B, self.num_classes)
 
-    @graph_op(n_out=2, name="compute_loss")
     def compute_loss(self, inputs, labels, inputs_seq_len, keep_prob, scope=None,
                      softmax_temperature=1, is_training=True):
         """-> (total_loss 0-d cuda tensor, logits [T,B,C])   (ctc.py:256-323).
 
         labels: the SparseTensor triple (indices, values, dense_shape) of
-        ``list2sparsetensor`` or a list of label sequences."""
+        ``list2sparsetensor`` or a list of label sequences.
+
+        Graph mode (any argument a placeholder): two ops, as in the reference's graph -- ``logits`` depends
+        only on (inputs, inputs_seq_len, keep_prob), the loss on (logits, labels, inputs_seq_len) -- so that
+        ``sess.run(decode_op)`` / ``sess.run(posteriors_op)`` need no labels in the feed
+        (examples/timit/metrics/ctc.py:72-81) and do not run the CTC loss."""
+        if any(_graph.is_handle(a) for a in (inputs, labels, inputs_seq_len, keep_prob)):
+            logits_op = _graph.Op(self._eval_logits, (inputs, inputs_seq_len, keep_prob, is_training), {},
+                                  name="logits")
+            loss_op = _graph.Op(self._eval_loss, (logits_op, labels, inputs_seq_len, softmax_temperature,
+                                                  is_training), {}, name="compute_loss")
+            return loss_op, logits_op
+        logits = self._eval_logits(inputs, inputs_seq_len, keep_prob, is_training)
+        return self._eval_loss(logits, labels, inputs_seq_len, softmax_temperature, is_training), logits
+
+    def _eval_logits(self, inputs, inputs_seq_len, keep_prob, is_training=True):
         inputs, inputs_seq_len = self._to_device(inputs, inputs_seq_len)
-        B = inputs.shape[0]
-        if isinstance(labels, (list, tuple)) and len(labels) == 3 and hasattr(labels[0], "ndim") \
-                and getattr(labels[0], "ndim", 0) == 2:
-            label_lists = sparse_to_label_lists(labels, B)
-        elif isinstance(labels, SparseTensorValue):
-            label_lists = sparse_to_label_lists(labels, B)
-        else:
-            label_lists = [list(l) for l in labels]
-        logits = self._build(inputs, inputs_seq_len, keep_prob, is_training)
+        return self._build(inputs, inputs_seq_len, keep_prob, is_training)
+
+    def _eval_loss(self, logits, labels, inputs_seq_len, softmax_temperature=1, is_training=True):
+        _, inputs_seq_len = self._to_device(logits, inputs_seq_len)
+        T, B, _ = logits.shape
+        label_lists = label_lists_from(labels, B)
+        ops.check_labels(label_lists, self.num_classes, self.num_classes - 1)
         flat, offs, lmax = ops.pack_labels(label_lists)
         d_flat = torch.as_tensor(flat).to(self.device, non_blocking=True)
         d_offs = torch.as_tensor(offs).to(self.device, non_blocking=True)
@@ -184,8 +196,8 @@ class CTC(ModelBase):
             # weight_decay * sum_{non-bias} l2_loss(w), l2_loss = sum(w^2)/2   (ctc.py:280-286)
             sq = ops.clip_by_norm_multi(self._decay_params, 3.0e38)      # norms^2, no scaling
             total_loss = total_loss + 0.5 * float(self.weight_decay) * sq.sum()
-        self._ctx = (dlogits, inputs.shape) if is_training else None
-        return total_loss, logits
+        self._ctx = (dlogits, (B, T, None)) if is_training else None
+        return total_loss
 
     def _backward(self):
         """Gradients of the last compute_loss into self.flat_grads."""
@@ -243,9 +255,20 @@ class CTC(ModelBase):
         """mean_b edit_distance(hyp_b, ref_b)/len(ref_b)  (ctc.py:382-398)"""
         B = int(decode_op.dense_shape[0])
         hyp = sparse_to_label_lists(decode_op, B)
-        ref = sparse_to_label_lists(labels, B) if not isinstance(labels, list) or (
-            len(labels) == 3 and hasattr(labels[0], "ndim")) else labels
+        ref = label_lists_from(labels, B)
         return ler_from_lists(hyp, ref, self.device)
+
+
+def label_lists_from(labels, B):
+    """the three label formats every entry point accepts -> list of B python lists:
+    the ``list2sparsetensor`` triple (indices [N,2], values [N], dense_shape [2]) -- recognised by
+    ``indices.ndim == 2`` so that a batch of exactly three 1-D label arrays is not mistaken for it --,
+    a SparseTensorValue, or a list of label sequences."""
+    if isinstance(labels, SparseTensorValue):
+        return sparse_to_label_lists(labels, B)
+    if isinstance(labels, (list, tuple)) and len(labels) == 3 and getattr(labels[0], "ndim", 0) == 2:
+        return sparse_to_label_lists(labels, B)
+    return [list(l) for l in labels]
 
 
 def ler_from_lists(hyp, ref, device):

@@ -50,6 +50,14 @@ class Optimizer(object):
         self._s1 = ops.TensorList([self.state1]) if self.state1 is not None else None
         self.global_step = 0
 
+    def load_state(self, state):
+        """slots + step counter from a checkpoint (compat.tf.train.Saver.restore)"""
+        for k in ("state0", "state1"):
+            st = getattr(self, k)
+            if st is not None and k in state:
+                st.copy_(torch.as_tensor(state[k]).to(st.device))
+        self.global_step = int(state.get("global_step", self.global_step))
+
     def compute_gradients(self, loss):
         """Runs the backward pass of the last compute_loss -> [(grad, var)]."""
         self.model._backward()
@@ -120,6 +128,10 @@ class ModelBase(object):
         OPTIMIZER_CLS_NAMES (kept across calls) ; returns the optimizer object."""
         if getattr(self, "optimizer", None) is None or self.optimizer.name != optimizer.lower():
             self.optimizer = self._set_optimizer(optimizer, learning_rate)
+            restored = getattr(self, "_restored_optimizer_state", None)
+            if restored is not None and restored.get("name") == self.optimizer.name:
+                self.optimizer.load_state(restored)
+            self._restored_optimizer_state = None
         grads_and_vars = self.optimizer.compute_gradients(loss)
         if self.clip_grad_norm is not None or self.world_size > 1:
             grads_and_vars = self._clip_gradients(grads_and_vars)

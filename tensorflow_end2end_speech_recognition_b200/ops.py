@@ -46,6 +46,22 @@ def pack_labels(labels):
     return flat, offs, (max(lens) if lens else 0)
 
 
+def check_labels(labels, num_classes, blank=None, what="labels"):
+    """tf.nn.ctc_loss rejects label values outside [0, num_classes) or equal to the blank with
+    InvalidArgument (its kernel indexes the softmax row by label); same contract here, raised on the host
+    before anything is launched.  A dense -1-padded row (utils/dataset/ctc.py pads with -1) must be
+    stripped by the caller -- ``list2sparsetensor(..., padded_value=-1)`` does."""
+    if blank is None:
+        blank = num_classes - 1
+    for b, l in enumerate(labels):
+        if len(l) == 0:
+            continue
+        a = np.asarray(l)
+        if a.min() < 0 or a.max() >= num_classes or (a == blank).any():
+            raise ValueError("%s[%d]: label values must be in [0, %d) and differ from the blank index %d, got "
+                             "min %d max %d" % (what, b, num_classes, blank, int(a.min()), int(a.max())))
+
+
 def ctc_loss_grad(logits, labels_flat, label_offsets, seq_len, max_label_len, blank=None,
                   ignore_longer=True, grad_scale=1.0, need_grad=True):
     """logits [T,B,C] f32 cuda; labels_flat/label_offsets/seq_len int32 cuda.
@@ -435,6 +451,17 @@ def axpy_multi(xs, ys, alpha):
     lib = _lib.load()
     _lib.check(lib.b2_axpy_multi(_ptr(xs.ptrs), _ptr(ys.ptrs), _ptr(xs.sizes), xs.n, float(alpha), _stream()),
                "b2_axpy_multi")
+
+
+def tower_mean(srcs, dst):
+    """dst = mean of the equally-shaped fp32 cuda tensors in ``srcs`` (dst may be srcs[0])."""
+    lib = _lib.load()
+    _require_cuda(dst, *srcs)
+    n = dst.numel()
+    assert all(t.numel() == n and t.dtype == torch.float32 and t.is_contiguous() for t in srcs)
+    arr = (C.c_void_p * len(srcs))(*[t.data_ptr() for t in srcs])
+    _lib.check(lib.b2_tower_mean(arr, len(srcs), _ptr(dst), n, _stream()), "b2_tower_mean")
+    return dst
 
 
 def optimizer_step_multi(kind, params, grads, state0, state1, learning_rate, step):

@@ -57,7 +57,14 @@ def test_ctc_graph_style_training(cuda, tmp_path):
                 labels_pred_st = sess.run(decode_op, feed_dict=feed_dict)
                 pred = sparsetensor2list(labels_pred_st, batch_size=B)
                 assert list(pred[0]) == list(labels[0, :8]) and list(pred[1]) == list(labels[1, :5])
-                post = sess.run(posteriors_op, feed_dict=feed_dict)
+                # evaluation feeds carry no labels (examples/timit/metrics/ctc.py:72-81): decode / posteriors
+                # depend on (inputs, inputs_seq_len, keep_prob) only
+                feed_eval = {k: v for k, v in feed_dict.items() if k is not model.labels_pl_list[0]}
+                pred2 = sparsetensor2list(sess.run(decode_op, feed_dict=feed_eval), batch_size=B)
+                assert [list(p) for p in pred2] == [list(p) for p in pred]
+                with pytest.raises(ValueError):
+                    sess.run(loss_op, feed_dict=feed_eval)
+                post = sess.run(posteriors_op, feed_dict=feed_eval)
                 assert post.shape == (B * T, C + 1) and np.allclose(post.sum(-1), 1, atol=1e-5)
                 # checkpoint round trip
                 path = saver.save(sess, os.path.join(str(tmp_path), "model.ckpt"), global_step=2)
