@@ -33,6 +33,12 @@ CFG = dict(input_size=80, num_units=512, num_layers=5, num_classes=28, T=1000, B
            keep_prob=float(os.environ.get("B2_BENCH_KEEP_PROB", "0.8")))   # dropout 0.2: blstm_ctc_960h_char.yml:34
 # forward MAC count of the gate GEMMs, x3 for training
 FWD_FLOP_PER_FRAME = 2 * 2 * (80 + 512) * 2048 + 4 * 2 * 2 * (1024 + 512) * 2048   # 55.18 M
+# weak: 64 utterances per GPU (default, the driver's convention); strong: the reference's own semantics --
+# ONE global batch of 64 np.array_split over the ranks (utils/dataset/ctc.py:171-177)
+SCALING = os.environ.get("B2_BENCH_SCALING", "weak")
+# CPU arm: one step = full model on CPU_B utterances x CPU_T frames, fixed thread count
+CPU_B, CPU_T = int(os.environ.get("B2_BENCH_CPU_B", "8")), int(os.environ.get("B2_BENCH_CPU_T", "1000"))
+CPU_THREADS = int(os.environ.get("B2_BENCH_CPU_THREADS", "32"))
 
 
 def make_batch(seed, B, T, D, C, lmin, lmax):
@@ -85,6 +91,16 @@ class ClockSampler(object):
                 "samples": len(sm)}
 
 
+def cpu_model_name():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
 def cpu_baseline(B_s, T_s, threads=None, steps=1):
     """CPU restatement of the same train step on a bounded sample (B_s utterances x T_s frames,
     full 5x512 model).  Returns frames/s."""
@@ -115,33 +131,40 @@ def cpu_baseline(B_s, T_s, threads=None, steps=1):
     return B_s * T_s / dt, dt
 
 
+def cpu_arm_record(v, dt, threads, nsteps):
+    sample = ("one full train step (fwd + CTC + bwd + clip + rmsprop) of the config-2 model (5x512 BLSTM, 80-d, "
+              "C=29) on B=%d utterances x T=%d frames = %d frames, %.1f s; frames/s is per frame, so the B=64 "
+              "figure is this value (per-step work is linear in B)" % (CPU_B, CPU_T, CPU_B * CPU_T, dt))
+    return {"value": v, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample,
+            "cpu_model": cpu_model_name(), "host_cpus": os.cpu_count(), "timed_steps": nsteps,
+            "note": "torch-CPU restatement of the TF-1.x step (oracle/model.py, fp32, %d intra-op threads); "
+                    "TensorFlow itself is not installable here" % threads}
+
+
 def run_reference(args):
-    """--impl reference: CPU port of the reference step, rank 0 only."""
+    """--impl reference: CPU port of the reference step, rank 0 only.  One step = the bounded sample
+    CPU_B x CPU_T (T stays 1000); at ~1 minute per step the arm times min(K, 2) steps after min(W, 1)
+    warm-up so that the whole run ends within a few minutes, and says so in "steps"/"warmup"."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-    cores = os.cpu_count() or 1
-    threads = min(cores, 64)
-    B_s, T_s = 64, 64
+    threads = min(os.cpu_count() or 1, CPU_THREADS)
+    k_eff, w_eff = max(1, min(args.steps, 2)), min(args.warmup, 1)
     vals = []
-    for i in range(args.warmup + args.steps):
-        v, dt = cpu_baseline(B_s, T_s, threads=threads, steps=1)
-        if i >= args.warmup:
+    for i in range(w_eff + k_eff):
+        v, dt = cpu_baseline(CPU_B, CPU_T, threads=threads, steps=1)
+        if i >= w_eff:
             vals.append((v, dt))
     v = float(np.mean([a for a, _ in vals]))
-    ms = float(np.mean([b for _, b in vals])) * 1e3
-    sample = "B=%d x T=%d frames of the config-2 model (5x512 BLSTM, 80-d, CTC), full train step" % (B_s, T_s)
+    dt = float(np.mean([b for _, b in vals]))
     out = {"impl": "reference", "metric": "frames/sec BLSTM-CTC train", "value": v, "unit": "frames/s",
-           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "n_gpus": args.gpus, "steps": k_eff, "warmup": w_eff, "ms_per_step": dt * 1e3,
+           "higher_is_better": True, "scaling": SCALING, "vs_baseline": None, "dtype": "f32",
            "data": "synthetic",
            "config": {"workload": "BASELINE configs[1]: LibriSpeech-shape char CTC, 5x512 BLSTM, 80-d, "
-                                  "T=1000, B=64 (CPU arm: bounded sample, see cpu_baseline.sample)"},
-           "cpu_baseline": {"value": v, "unit": "frames/s", "cores": threads, "kind": "port",
-                            "sample": sample,
-                            "note": "torch-CPU restatement of the TF-1.x step (oracle/model.py); "
-                                    "TensorFlow itself is not installable here"},
+                                  "T=1000, B=64 (CPU arm: bounded sample B=%d x T=%d, see cpu_baseline.sample)"
+                                  % (CPU_B, CPU_T)},
+           "cpu_baseline": cpu_arm_record(v, dt, threads, k_eff),
            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
@@ -174,13 +197,18 @@ def main():
     lib = _lib.load()
 
     B, T, D = CFG["B"], CFG["T"], CFG["input_size"]
+    if SCALING == "strong":
+        # the reference's semantics: one global batch of 64, np.array_split over the towers
+        from tensorflow_end2end_speech_recognition_b200.utils.io.inputs.pipeline import shard_bounds
+        lo, hi = shard_bounds(CFG["B"], world)[rank]
+        B = hi - lo
     model = CTC(encoder_type="blstm", input_size=D, num_units=CFG["num_units"],
                 num_layers=CFG["num_layers"], num_classes=CFG["num_classes"],
                 lstm_impl="LSTMBlockCell", use_peephole=True, parameter_init=0.1,
                 clip_grad_norm=CFG["clip"], precision=args.precision, device=dev, seed=1)
     model.set_data_parallel(world)
     # weak scaling: every rank gets its own 64-utterance shard (np.array_split of a 64*N batch,
-    # utils/dataset/ctc.py:171-177)
+    # utils/dataset/ctc.py:171-177); strong scaling: its slice of the one 64-utterance batch
     x, seq, labels = make_batch(1234 + rank, B, T, D, CFG["num_classes"], CFG["label_min"], CFG["label_max"])
     x_host = torch.from_numpy(x).pin_memory()
     seq_host = torch.from_numpy(seq).pin_memory()
@@ -263,7 +291,7 @@ def main():
     e2e_flush()
     clocks = sampler.stop() if rank == 0 else None
 
-    frames = B * T * world
+    frames = (CFG["B"] if SCALING == "strong" else B * world) * T
     value = frames * args.steps / (ms_dev / 1e3)
     e2e = frames * args.steps / (ms_e2e / 1e3)
     ms_step = ms_dev / args.steps
@@ -311,19 +339,26 @@ def main():
         flat, offs, lmax = ops.pack_labels(labels)
         dflat, doffs = torch.tensor(flat, device=dev), torch.tensor(offs, device=dev)
         t_ctc = time_ms(lambda: ops.ctc_loss_grad(lg, dflat, doffs, seq_dev, lmax))
-        s_pad = (2 * lmax + 1 + 31) // 32 * 32
-        by = 8.0 * T * B * Cc + 16.0 * T * B * s_pad
+        # algorithmic bytes = 8*T*B*C (read logits, write grad) + 8*T*B*S alpha spill, S = 2*mean(L)+1
+        s_mean = 2.0 * float(np.mean([len(l) for l in labels])) + 1.0
+        by = 8.0 * T * B * Cc + 8.0 * T * B * s_mean
         roof["ctc_alpha_beta"] = {"kernel": "ctc_lse + ctc_alpha_beta + ctc_grad", "bound": "hbm",
                                   "achieved": by / t_ctc / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                   "frac": by / t_ctc / 1e6 / peaks["hbm_gbs"], "traffic": None, "ms": t_ctc,
-                                  "note": "latency-bound at C=29 (T sequential lattice steps); bytes = "
-                                          "8*T*B*C + 16*T*B*S spill", "peak_src": peaks["src"]}
+                                  "achieved_logits_only": 8.0 * T * B * Cc / t_ctc / 1e6,
+                                  "note": "latency-bound at C=29 (T sequential lattice steps); algorithmic bytes = "
+                                          "8*T*B*C + 8*T*B*S (S = 2*mean label length + 1, unpadded)",
+                                  "peak_src": peaks["src"]}
         # the persistent recurrence kernels (dominant share of the step), timed with CUDA events
         # placed around their launches inside the library
-        from oracle import lstm as olstm
         Hh = CFG["num_units"]
-        lay = olstm.init_blstm_params(2 * Hh, Hh, 1, parameter_init=0.1, seed=0)[0]
-        Pl = {d: {k: torch.tensor(v, device=dev) for k, v in lay[d].items()} for d in lay}
+        prng = np.random.RandomState(0)
+        Pl = {}
+        for d in ("fw", "bw"):        # U(-0.1, 0.1) kernels / peepholes, zero bias (blstm.py:79-80)
+            Pl[d] = {"kernel": torch.tensor(prng.uniform(-0.1, 0.1, (3 * Hh, 4 * Hh)).astype(np.float32), device=dev),
+                     "bias": torch.zeros(4 * Hh, device=dev)}
+            for k in ("w_i_diag", "w_f_diag", "w_o_diag"):
+                Pl[d][k] = torch.tensor(prng.uniform(-0.1, 0.1, Hh).astype(np.float32), device=dev)
         Gl = {d: {k: torch.zeros_like(v) for k, v in Pl[d].items()} for d in Pl}
         xx = torch.randn(T, B, 2 * Hh, device=dev)
         dyy = torch.randn(T, B, 2 * Hh, device=dev)
@@ -346,14 +381,17 @@ def main():
             roof["blstm_recurrence_fwd"] = {
                 "kernel": "lstm_rec_fwd_kernel<2,32> (persistent cluster/TMEM recurrence, one layer, T=1000)",
                 "bound": "tensor", "achieved": rec_fl / tf_ / 1e9, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": rec_fl / tf_ / 1e9 / peaks["bf16_tflops"], "traffic": 2.71e9, "ms": tf_,
-                "note": "latency-bound: 1000 dependent steps (tensor-pipe issue + DSMEM all-gather + gate math); "
-                        "traffic = ncu dram bytes of profiles/prof_rec_fwd_r01", "peak_src": peaks["src"] + " burst"}
+                "frac": rec_fl / tf_ / 1e9 / peaks["bf16_tflops"], "traffic": 2.71e9, "traffic_src": "static: ncu dram bytes "
+                "read+write of one launch, profiles/prof_rec_fwd_r01_metrics.csv (not re-measured in this run)", "ms": tf_,
+                "note": "latency-bound: 1000 dependent steps (tensor-pipe issue + DSMEM all-gather + gate math)",
+                "peak_src": peaks["src"] + " burst"}
             roof["blstm_recurrence_bwd"] = {
                 "kernel": "lstm_rec_bwd_kernel<2> (BPTT, one layer)", "bound": "tensor",
                 "achieved": rec_fl / tb_ / 1e9, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": rec_fl / tb_ / 1e9 / peaks["bf16_tflops"], "traffic": 2.08e9, "ms": tb_,
-                "note": "latency-bound; traffic from profiles/prof_rec_bwd_r01", "peak_src": peaks["src"] + " burst"}
+                "frac": rec_fl / tb_ / 1e9 / peaks["bf16_tflops"], "traffic": 2.08e9, "traffic_src": "static: ncu dram bytes "
+                "read+write of one launch, profiles/prof_rec_bwd_r01_metrics.csv (not re-measured in this run)", "ms": tb_,
+                "note": "latency-bound (DSMEM reduce-scatter + gate math + tensor-pipe issue per step)",
+                "peak_src": peaks["src"] + " burst"}
         # whole step against the tensor roofline (algorithmic gate-GEMM FLOPs / step time)
         step_fl = 3.0 * FWD_FLOP_PER_FRAME * B * T
         roof["step_blended"] = {"kernel": "whole training step (algorithmic gate-GEMM FLOPs / step time)",
@@ -364,22 +402,25 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = min(os.cpu_count() or 1, 64)
-        v, dt = cpu_baseline(64, 64, threads=cores, steps=1)
-        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
-               "sample": "one train step on B=64 x T=64 frames of the same 5x512 model (%.1f s)" % dt,
-               "note": "torch-CPU restatement of the TF-1.x step; TensorFlow itself cannot be installed here"}
+        threads = min(os.cpu_count() or 1, CPU_THREADS)
+        # bounded: one step of the T=1000 sample at a quarter of the reference arm's batch
+        v, dt = cpu_baseline(max(1, CPU_B // 4), CPU_T, threads=threads, steps=1)
+        cpu = cpu_arm_record(v, dt, threads, 1)
+        cpu["sample"] = cpu["sample"].replace("B=%d utterances" % CPU_B, "B=%d utterances" % max(1, CPU_B // 4)) \
+            .replace("= %d frames" % (CPU_B * CPU_T), "= %d frames" % (max(1, CPU_B // 4) * CPU_T))
 
     if rank == 0:
         out = {"metric": "frames/sec BLSTM-CTC train", "value": value, "unit": "frames/s", "n_gpus": world,
                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
-               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision,
+               "higher_is_better": True, "scaling": SCALING, "vs_baseline": None, "dtype": args.precision,
                "data": "synthetic",
                "config": {"workload": "BASELINE configs[1]: LibriSpeech-shape char CTC, 5x512 BLSTM "
-                                      "(LSTMBlockCell, peephole), 80-d input, T=1000, B=64 per GPU, "
+                                      "(LSTMBlockCell, peephole), 80-d input, T=1000, %s, "
                                       "28 chars + blank, labels 150-250, rmsprop lr 1e-3, clip_by_norm 5, "
-                                      "dropout keep_prob %.2f" % CFG["keep_prob"],
-                          "global_batch": B * world, "parallelism": "dp%d" % world,
+                                      "dropout keep_prob %.2f" % (
+                                          "B=64 per GPU" if SCALING != "strong" else
+                                          "global B=64 array_split over the GPUs", CFG["keep_prob"]),
+                          "global_batch": (CFG["B"] if SCALING == "strong" else B * world), "per_gpu_batch": B, "parallelism": "dp%d" % world,
                           "l2": "per-step working set (reserve + gate buffers, >8 GB) >> 126 MB L2, "
                                 "no explicit flush"},
                "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,

@@ -117,6 +117,14 @@ int b2_gemm(int transa, int transb, int M, int N, int K, float alpha,
             float* C, int ldc, const float* bias, int precision,
             void* workspace, size_t workspace_bytes, b2_stream_t stream);
 
+/* b2_gemm with a caller-kept bf16 shadow of A (same logical layout as A, row stride lda_lp elements,
+ * 16-byte aligned, lda_lp % 8 == 0): the bf16 path then skips its fp32->bf16 pass over A -- e.g. the
+ * encoder output [T*B, 2H] feeding the output layer (models/ctc/ctc.py:215-226), whose bf16 copy the
+ * BLSTM layer already wrote (b2_blstm_reserve_y_lp).  A_lp == NULL or precision fp32: identical to b2_gemm. */
+int b2_gemm_lp(int transa, int transb, int M, int N, int K, float alpha,
+               const float* A, int lda, const void* A_lp, int lda_lp, const float* B, int ldb,
+               float beta, float* C, int ldc, const float* bias, int precision,
+               void* workspace, size_t workspace_bytes, b2_stream_t stream);
 /* Same GEMM on operands that are already bf16 (uint16_t storage), no casts:
  *   a_mn = 0: A is [M rows][K contiguous] (pitch lda)   1: A is [K rows][M contiguous]
  *   b_mn = 0: B is [N rows][K contiguous] (pitch ldb)   1: B is [K rows][N contiguous]

@@ -78,6 +78,7 @@ PROTOTYPES = {
     "b2_softmax_rows": (_i, [_p, _p, _i64, _i, _p]),
     "b2_gemm_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "b2_gemm": (_i, [_i, _i, _i, _i, _i, _f, _p, _i, _p, _i, _f, _p, _i, _p, _i, _p, _sz, _p]),
+    "b2_gemm_lp": (_i, [_i, _i, _i, _i, _i, _f, _p, _i, _p, _i, _p, _i, _f, _p, _i, _p, _i, _p, _sz, _p]),
     "b2_gemm_bf16": (_i, [_i, _i, _i, _i, _i, _f, _p, _i, _p, _i, _p, _i, _p, _i, _i, _p]),
     "b2_blstm_reserve_bytes": (_sz, [C.POINTER(LstmDesc)]),
     "b2_blstm_workspace_bytes": (_sz, [C.POINTER(LstmDesc)]),

@@ -13,11 +13,14 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libb2asr.so")
-OBJ = os.path.join(HERE, "build")
+# B2_BUILD_VARIANT=timing builds libb2asr_timing.so with -DB2_REC_TIMING=1 (phase timers inside the recurrence
+# kernels, tools/bench_rec.py + B2_REC_DBG=1); the default library carries no timer code
+VARIANT = os.environ.get("B2_BUILD_VARIANT", "")
+OUT = os.path.join(HERE, "libb2asr%s.so" % ("_" + VARIANT if VARIANT else ""))
+OBJ = os.path.join(HERE, "build" + ("_" + VARIANT if VARIANT else ""))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--use_fast_math" if False else "-DB2_BUILD"]
+         "-Xcompiler", "-fPIC", "-DB2_BUILD"] + (["-DB2_REC_TIMING=1"] if VARIANT == "timing" else [])
 
 
 def _sources():

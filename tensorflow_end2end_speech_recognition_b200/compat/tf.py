@@ -121,7 +121,20 @@ def _host(v):
 
 
 def expand_dims(x, axis=0):
-    return _g.Op(lambda v: np.expand_dims(np.asarray(_host(v)), axis), (x,), {}, name="expand_dims")
+    def fn(v):
+        try:
+            import torch
+        except ImportError:                               # pragma: no cover
+            torch = None
+        if torch is not None and torch.is_tensor(v):
+            # stays a device tensor and keeps the backward context of the loss it wraps:
+            # ``optimizer.compute_gradients(tf.expand_dims(tower_loss, axis=0))``, train_ctc.py:104-112
+            r = v.unsqueeze(axis)
+            if hasattr(v, "_b2_ctx"):
+                r._b2_ctx = v._b2_ctx
+            return r
+        return np.expand_dims(np.asarray(_host(v)), axis)
+    return _g.Op(fn, (x,), {}, name="expand_dims")
 
 
 def concat(values, axis=0):

@@ -424,11 +424,10 @@ extern "C" size_t b2_gemm_workspace_bytes(int M, int N, int K, int precision) {
   return align_up(a, 256) + align_up(b, 256) + 1024;
 }
 
-extern "C" int b2_gemm(int transa, int transb, int M, int N, int K, float alpha, const float* A,
-                       int lda, const float* B, int ldb, float beta, float* C, int ldc,
-                       const float* bias, int precision, void* workspace, size_t workspace_bytes,
-                       b2_stream_t stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+static int gemm_f32_api(int transa, int transb, int M, int N, int K, float alpha, const float* A,
+                        int lda, const void* A_lp, int lda_lp, const float* B, int ldb, float beta, float* C,
+                        int ldc, const float* bias, int precision, void* workspace, size_t workspace_bytes,
+                        cudaStream_t stream) {
   B2_CHECK_ARG(A && B && C, "b2_gemm: null pointer");
   B2_CHECK_ARG(M > 0 && N > 0 && K > 0, "b2_gemm: bad shape %dx%dx%d", M, N, K);
   if (precision == B2_PREC_FP32)
@@ -439,24 +438,45 @@ extern "C" int b2_gemm(int transa, int transb, int M, int N, int K, float alpha,
   // operand copies: A as stored ([M,K] or [K,M]); B as stored ([K,N] -> MN-major, [N,K] -> K-major)
   const int a_rows = transa ? K : M, a_cols = transa ? M : K;
   const int b_rows = transb ? N : K, b_cols = transb ? K : N;
-  const int a_ld = pad8(a_cols);
+  const bool a_given = A_lp != nullptr && (lda_lp % 8) == 0 && (((uintptr_t)A_lp) & 15) == 0;
+  const int a_ld = a_given ? lda_lp : pad8(a_cols);
   int b_ld = pad8(b_cols);
   if (!transb && b_ld < 64) b_ld = 64;        // MN-major B needs a full 64-wide box
-  const size_t a_bytes = align_up((size_t)a_rows * a_ld * 2, 256);
+  const size_t a_bytes = a_given ? 0 : align_up((size_t)a_rows * a_ld * 2, 256);
   const size_t b_bytes = align_up((size_t)b_rows * b_ld * 2, 256);
   if (workspace_bytes < a_bytes + b_bytes) {
     set_error("b2_gemm: workspace %zu < %zu", workspace_bytes, a_bytes + b_bytes);
     return B2_ERR_WORKSPACE;
   }
-  __nv_bfloat16* Ab = (__nv_bfloat16*)workspace;
+  const __nv_bfloat16* Ab = (const __nv_bfloat16*)A_lp;
   __nv_bfloat16* Bb = (__nv_bfloat16*)((char*)workspace + a_bytes);
-  int rc = cast_f32_bf16(A, a_rows, a_cols, lda, Ab, a_ld, stream);
-  if (rc) return rc;
+  int rc = B2_OK;
+  if (!a_given) {                              // the caller has no bf16 shadow of A: make one
+    rc = cast_f32_bf16(A, a_rows, a_cols, lda, (__nv_bfloat16*)workspace, a_ld, stream);
+    if (rc) return rc;
+    Ab = (const __nv_bfloat16*)workspace;
+  }
   rc = cast_f32_bf16(B, b_rows, b_cols, ldb, Bb, b_ld, stream);
   if (rc) return rc;
   const int epi = (beta == 1.f) ? EPI_ATOMIC_F32 : EPI_STORE_F32;
   return gemm_bf16_tc(transa ? 1 : 0, transb ? 0 : 1, M, N, K, alpha, Ab, a_ld, Bb, b_ld, C, ldc,
                       bias, epi, 0, stream);
+}
+
+extern "C" int b2_gemm(int transa, int transb, int M, int N, int K, float alpha, const float* A,
+                       int lda, const float* B, int ldb, float beta, float* C, int ldc,
+                       const float* bias, int precision, void* workspace, size_t workspace_bytes,
+                       b2_stream_t stream_) {
+  return gemm_f32_api(transa, transb, M, N, K, alpha, A, lda, nullptr, 0, B, ldb, beta, C, ldc, bias, precision,
+                      workspace, workspace_bytes, (cudaStream_t)stream_);
+}
+
+extern "C" int b2_gemm_lp(int transa, int transb, int M, int N, int K, float alpha, const float* A,
+                          int lda, const void* A_lp, int lda_lp, const float* B, int ldb, float beta, float* C,
+                          int ldc, const float* bias, int precision, void* workspace, size_t workspace_bytes,
+                          b2_stream_t stream_) {
+  return gemm_f32_api(transa, transb, M, N, K, alpha, A, lda, A_lp, lda_lp, B, ldb, beta, C, ldc, bias, precision,
+                      workspace, workspace_bytes, (cudaStream_t)stream_);
 }
 
 extern "C" int b2_gemm_bf16(int a_mn, int b_mn, int M, int N, int K, float alpha, const uint16_t* A,

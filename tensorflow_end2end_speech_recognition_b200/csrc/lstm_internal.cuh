@@ -20,7 +20,25 @@ struct Reserve {
   float* gates; float* cs; float* hs;
   __nv_bfloat16* hs_lp; __nv_bfloat16* y_lp;
   float* hps;      // [T][B][2][P] projected h before dropout (num_proj > 0; `hs` then holds o*tanh(c))
+  void* wpack;     // bf16 path: the layer's packed weights (wx | bias | wh | whT), written by forward and
+                   // read back by backward, so the pack kernel runs once per layer and step
+  // bf16 path, backward scratch that must outlive the layer's own call: the weight-gradient GEMMs of layer l
+  // run on a side stream next to layer l-1's BPTT, so their operands cannot sit in the workspace all layers share
+  __nv_bfloat16* dG;   // [T*B, 8H] gate gradients (packed order)
+  float* dwx;          // [D, 8H]   packed input-weight gradient
+  float* dwh;          // [2][H,4H] packed recurrent-weight gradient
+  float* dbias;        // [8H]
 };
+
+// bytes of the packed-weight block kept in the reserve (bf16 path, need_backward)
+inline size_t tc_pack_bytes(int D, int H) {
+  size_t n = 0;
+  n += align_up((size_t)D * 8 * H * 2, 1024);                              // wx   [D, 8H] bf16
+  n += align_up((size_t)8 * H * 4, 1024);                                  // bias [8H] fp32
+  n += align_up((size_t)2 * 4 * H * H * 2, 1024);                          // wh   [2][CS][128][H] bf16
+  n += align_up((size_t)2 * (H / 32) * 4 * 128 * 128 * 2, 1024);           // whT  [2][CS][4][128][128] bf16
+  return n;
+}
 
 inline size_t reserve_layout(const b2_lstm_desc* d, void* base, Reserve* r) {
   const size_t n = (size_t)d->T * d->B * 2 * d->H;
@@ -33,6 +51,12 @@ inline size_t reserve_layout(const b2_lstm_desc* d, void* base, Reserve* r) {
   const size_t ohl = lp ? take(n * 2) : 0;
   const size_t oyl = lp ? (d->keep_prob < 1.f ? take(n * 2) : ohl) : 0;
   const size_t ohp = d->num_proj > 0 ? take((size_t)d->T * d->B * 2 * d->num_proj * sizeof(float)) : 0;
+  const bool lpb = lp && d->need_backward;
+  const size_t owp = lpb ? take(tc_pack_bytes(d->D_in, d->H)) : 0;
+  const size_t odg = lpb ? take((size_t)d->T * d->B * 8 * d->H * 2) : 0;
+  const size_t odwx = lpb ? take((size_t)d->D_in * 8 * d->H * 4) : 0;
+  const size_t odwh = lpb ? take((size_t)2 * d->H * 4 * d->H * 4) : 0;
+  const size_t odb = lpb ? take((size_t)8 * d->H * 4) : 0;
   if (r) {
     char* p = (char*)base;
     r->gates = (float*)(p + og); r->cs = (float*)(p + oc);
@@ -40,6 +64,11 @@ inline size_t reserve_layout(const b2_lstm_desc* d, void* base, Reserve* r) {
     r->hs_lp = lp ? (__nv_bfloat16*)(p + ohl) : nullptr;
     r->y_lp = lp ? (__nv_bfloat16*)(p + oyl) : nullptr;
     r->hps = d->num_proj > 0 ? (float*)(p + ohp) : nullptr;
+    r->wpack = lpb ? (void*)(p + owp) : nullptr;
+    r->dG = lpb ? (__nv_bfloat16*)(p + odg) : nullptr;
+    r->dwx = lpb ? (float*)(p + odwx) : nullptr;
+    r->dwh = lpb ? (float*)(p + odwh) : nullptr;
+    r->dbias = lpb ? (float*)(p + odb) : nullptr;
   }
   return off;
 }

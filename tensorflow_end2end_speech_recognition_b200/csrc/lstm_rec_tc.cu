@@ -33,9 +33,32 @@ namespace b2 {
 using namespace sm100;
 
 constexpr int RGS = 3;        // TMA ring stages
-constexpr int RPITCH = 20;    // transpose scratch pitch (floats)
 constexpr int NISSW = 4;      // MMA issuer warps
 constexpr int ACC_STRIDE = 32; // TMEM columns between accumulators (16 used)
+
+// Gate-math team of a chain: GW warps.  A warp can only read the TMEM lane quarter 32*(warp_id % 4), so
+// with GW = 8 the two warps that share a quarter split the 16 batch columns of the accumulator:
+// NBW = 16 / (GW/4) columns per warp, CPT = NBW / 4 cells per thread.  GW = 8 halves the dependent
+// chain of the cell math per step (2 cells per thread instead of 4) and the per-warp share of the
+// DSMEM copy issue (2 copies instead of 4).
+template <int GW> struct GateTeam {
+  static_assert(GW == 4 || GW == 8, "gate team = 4 or 8 warps");
+  static constexpr int HF = GW / 4;
+  static constexpr int NBW = 16 / HF;
+  static constexpr int CPT = NBW / 4;
+  static constexpr int PITCH = NBW + 4;      // transpose scratch pitch (floats)
+  static constexpr int SENDS = 16 / GW;      // bulk copies issued per warp and step
+};
+
+// phase timers of the gate-math warps: compiled out unless -DB2_REC_TIMING=1
+#ifndef B2_REC_TIMING
+#define B2_REC_TIMING 0
+#endif
+#if B2_REC_TIMING
+#define REC_CLK(name) const long long name = clock64()
+#else
+#define REC_CLK(name) do {} while (0)
+#endif
 
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
                                             int c0, int c1, int c2) {
@@ -60,6 +83,17 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// warp-specialised register budget (whole warpgroups): the issuer / producer warps keep 24 registers,
+// what they give up lets the gate-math warps run without spills
+template <int N> __device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N> __device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+__device__ __forceinline__ void fence_acq_rel_cluster() {
+  asm volatile("fence.acq_rel.cluster;" ::: "memory");
+}
 __device__ __forceinline__ float fast_rcp(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -67,25 +101,33 @@ __device__ __forceinline__ float fast_rcp(float x) {
 }
 
 // ======================================================================== forward
-template <int NCHAIN>
+template <int NCHAIN, int GW>
 struct RecSmem {
   static constexpr int kHbufOff = 0;                                   // [NCHAIN][2][32*H]  (H<=512 -> 16 KB)
   static constexpr int kHbufBytes = 32 * 512;
   static constexpr int kStageOff = kHbufOff + NCHAIN * 2 * kHbufBytes; // [NCHAIN][2][1 KB]
   static constexpr int kGOff = kStageOff + NCHAIN * 2 * 1024;          // [NCHAIN][RGS][8 KB]
-  static constexpr int kScrOff = kGOff + NCHAIN * RGS * 8192;          // [NCHAIN*4][32*RPITCH*4]
-  static constexpr int kBarOff = kScrOff + NCHAIN * 4 * 32 * RPITCH * 4;
+  static constexpr int kScrOff = kGOff + NCHAIN * RGS * 8192;          // [NCHAIN*GW][32*PITCH*4]
+  static constexpr int kBarOff = kScrOff + NCHAIN * GW * 32 * GateTeam<GW>::PITCH * 4;
   static constexpr int kBytes = kBarOff + 1024;
 };
 
-// warp roles: 0..3 = MMA issuers, 4 = G producer, 5.. = gate math (4 warps per chain),
+template <int N>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[N]) {
+  if constexpr (N == 16) tmem_ld_32x32b_x16(taddr, r); else tmem_ld_32x32b_x8(taddr, r);
+}
+
+// warp roles: 0..3 = MMA issuers, 4 = G producer, 5.. = gate math (GW warps per chain),
 // then one output-store warp per chain
-template <int NCHAIN, int KS>     // KS = H/16 MMA k-steps per time step
-__global__ void __launch_bounds__(160 + 160 * NCHAIN, 1)
+template <int NCHAIN, int KS, int GW>     // KS = H/16 MMA k-steps per time step
+__global__ void __launch_bounds__(160 + (GW * 32 + 32) * NCHAIN, 1)
 lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a) {
-  using L = RecSmem<NCHAIN>;
+  using L = RecSmem<NCHAIN, GW>;
+  using GT = GateTeam<GW>;
+  constexpr int NBW = GT::NBW, CPT = GT::CPT, PITCH = GT::PITCH;
   constexpr int NISS = KS < NISSW ? KS : NISSW;      // issuer warps actually used
   constexpr int KPER = KS / NISS;                    // k-steps per issuer
+  constexpr int GTHREADS = GW * 32;                  // gate-math threads per chain
   extern __shared__ __align__(1024) uint8_t smem[];
   const int H = a.H, T = a.T, B = a.B;
   const int CS = H / RU;
@@ -123,7 +165,7 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
   const uint32_t tA = tmem;                    // columns [0, H/2): the weight slice
   const uint32_t tAcc = tmem + 256;            // [NCHAIN][NISS] accumulators of 16 columns
 
-  // ---- load this CTA's 128 x H bf16 weight slice into TMEM (chain-0 gate-math warps)
+  // ---- load this CTA's 128 x H bf16 weight slice into TMEM (first four gate-math warps: one per lane quarter)
   if (warp >= 5 && warp < 9) {
     const int q = warp & 3;
     const int r = q * 32 + lane;
@@ -150,7 +192,7 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
     // ------------------------------------------------------------- MMA issuers
     if (lane == 0 && warp < NISS) {
       const uint32_t idesc = make_idesc_bf16(128, RN, 0, 0);
-      uint32_t hphase = 0;                       // bit (c*2+p): parity of hfull[c][p]
+      uint32_t hphase = 0;                       // bit (c*2+p)*4 + local slice: parity of hfull[c][p][slice]
       const uint64_t bdesc0 = make_smem_desc(smem_u32(smem + L::kHbufOff), 256, 128, 0);
       // the chains drift against each other: poll both and serve whichever has its h ready
       int tc[NCHAIN];
@@ -169,21 +211,11 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
           // h arrives slice by slice (one 32-unit slice per source CTA, own mbarrier each):
           // the two MMAs of a slice are issued as soon as that slice has landed, so the
           // tensor pipe works underneath the DSMEM all-gather instead of after it
-          constexpr int SL0 = (0 * KPER) >> 1;
           const int sl_first = (warp * KPER) >> 1;
           if (t > 0) {
-            uint32_t ok;
-            asm volatile(
-                "{\n\t.reg .pred P;\n\t"
-                "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-                "selp.u32 %0, 1, 0, P;\n\t}"
-                : "=r"(ok)
-                : "r"(smem_u32(&hfull[(c * 2 + p) * 16 + sl_first])), "r"((hphase >> ((c * 2 + p) * 4)) & 1u)
-                : "memory");
-            if (!ok) continue;
+            if (!mbar_try_wait(&hfull[(c * 2 + p) * 16 + sl_first], (hphase >> ((c * 2 + p) * 4)) & 1u)) continue;
             hphase ^= 1u << ((c * 2 + p) * 4);
           }
-          (void)SL0;
           tc_fence_after();
           // one descriptor per buffer; the k-th step only moves the start address by 512 B
           const uint64_t bd0 = bdesc0 + (uint64_t)((c * 2 + p) * (L::kHbufBytes >> 4));
@@ -222,9 +254,9 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
         if (++stage == RGS) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp >= 5 + 4 * NCHAIN) {
+  } else if (warp >= 5 + GW * NCHAIN) {
     // ------------------------------------------------------------- output store warp
-    const int c = warp - 5 - 4 * NCHAIN;
+    const int c = warp - 5 - GW * NCHAIN;
     const int grp = gbase + c;
     if (grp < a.NG) {
       uint8_t* stage_base = smem + L::kStageOff + c * 2 * 1024;
@@ -281,86 +313,96 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
     }
   } else {
     // ------------------------------------------------------------- gate math
-    const int c = (warp - 5) >> 2;              // chain of this warp
+    const int c = (warp - 5) / GW;              // chain of this warp
     const int grp = gbase + c;
     if (grp < a.NG) {
-      const int q = warp & 3;                   // TMEM lane quarter
+      const int gw = (warp - 5) - c * GW;       // warp inside the chain's team
+      const int q = warp & 3;                   // TMEM lane quarter (hardware: warp_id % 4)
+      const int col0 = (gw >> 2) * NBW;         // first batch column of this warp's accumulator slice
       const int ug = lane >> 2, gq = lane & 3;
       const int ul = q * 8 + ug;                // unit inside the CTA
       const int u = cta * RU + ul;              // unit inside the layer
-      const int ctid = threadIdx.x - 160 - c * 128;   // 0..127 inside the chain
-      float* scr = (float*)(smem + L::kScrOff) + (size_t)(warp - 5) * 32 * RPITCH;
+      const int ctid = threadIdx.x - 160 - c * GTHREADS;   // 0..GTHREADS-1 inside the chain
+      float* scr = (float*)(smem + L::kScrOff) + (size_t)(warp - 5) * 32 * PITCH;
       uint8_t* stage_base = smem + L::kStageOff + c * 2 * 1024;
-      int bidx[4], len[4];
-      float cst[4], hst[4];
+      int bl[CPT], bidx[CPT], len[CPT];
+      float cst[CPT], hst[CPT];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        bidx[j] = grp * RN + gq * 4 + j;
+      for (int j = 0; j < CPT; ++j) {
+        bl[j] = col0 + gq * CPT + j;            // batch column inside the chain's group of 16
+        bidx[j] = grp * RN + bl[j];
         len[j] = bidx[j] < B ? a.seq_len[bidx[j]] : 0;
         cst[j] = 0.f; hst[j] = 0.f;
       }
       float pwi = 0.f, pwf = 0.f, pwo = 0.f;
       if (a.use_peephole) { pwi = a.wi[dir][u]; pwf = a.wf[dir][u]; pwo = a.wo[dir][u]; }
-      size_t cell0[4];
+      size_t cell0[CPT];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) cell0[j] = ((size_t)bidx[j] * 2 + dir) * H + u;
+      for (int j = 0; j < CPT; ++j) cell0[j] = ((size_t)bidx[j] * 2 + dir) * H + u;
       const size_t cell_step = (size_t)B * 2 * H;
       int stage = 0; uint32_t gph = 0;
+#if B2_REC_TIMING
       const long long loop_t0 = clock64();
+#endif
       for (int t = 0; t < T; ++t) {
         const int td = dir ? T - 1 - t : t;
-        const bool dbg = a.dbg && blockIdx.x == 0 && ctid == 0 && c == 0;
-        const long long e0 = clock64();
+        REC_CLK(e0);
         const int p = t & 1;
         // off the critical path (the MMAs of this step are still running): G_t into registers,
         // and make sure the store warp is done with the staging buffer we are about to reuse
         mbar_wait(&gfull[c * RGS + stage], gph);
         const float* Gs = (const float*)(smem + L::kGOff + (c * RGS + stage) * 8192);
-        float4 G4[4];
+        float4 G4[CPT];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) G4[j] = *(const float4*)(Gs + (gq * 4 + j) * 128 + ul * 4);   // [b][u][gate]
+        for (int j = 0; j < CPT; ++j) G4[j] = *(const float4*)(Gs + bl[j] * 128 + ul * 4);   // [b][u][gate]
         if (t >= 2) mbar_wait(&stfree[c * 2 + p], ((t >> 1) - 1) & 1);
-        const long long e1 = clock64();
+        REC_CLK(e1);
         mbar_wait(&accfull[c], t & 1);
         tc_fence_after();
-        const long long e2 = clock64();
-        float v[16];
+        REC_CLK(e2);
+        float v[NBW];
         {
-          uint32_t w[NISS][16];
+          uint32_t w[NISS][NBW];
 #pragma unroll
           for (int s2 = 0; s2 < NISS; ++s2)
-            tmem_ld_32x32b_x16(tAcc + (c * NISS + s2) * ACC_STRIDE + ((uint32_t)(q * 32) << 16), w[s2]);
+            tmem_ld_cols<NBW>(tAcc + (c * NISS + s2) * ACC_STRIDE + ((uint32_t)(q * 32) << 16) + col0, w[s2]);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
+          for (int i = 0; i < NBW; ++i) {
             float acc = __uint_as_float(w[0][i]);
 #pragma unroll
             for (int s2 = 1; s2 < NISS; ++s2) acc += __uint_as_float(w[s2][i]);
             v[i] = acc;
           }
         }
-        // 4x4 transpose inside each 4-lane group through shared memory
+        // (4 gates) x (NBW batches) transpose inside each 4-lane group through shared memory:
+        // lane = gate row, afterwards thread (unit, batch quad) holds all four gates of its CPT cells
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *(float4*)&scr[lane * RPITCH + 4 * j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        for (int j = 0; j < NBW / 4; ++j)
+          *(float4*)&scr[lane * PITCH + 4 * j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         __syncwarp();
-        float z[4][4];                           // [gate][batch j]
+        float z[4][CPT];                         // [gate][cell j]
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const float4 f = *(const float4*)&scr[(ug * 4 + g) * RPITCH + gq * 4];
-          z[g][0] = f.x; z[g][1] = f.y; z[g][2] = f.z; z[g][3] = f.w;
+          if constexpr (CPT == 4) {
+            const float4 f = *(const float4*)&scr[(ug * 4 + g) * PITCH + gq * 4];
+            z[g][0] = f.x; z[g][1] = f.y; z[g][2] = f.z; z[g][3] = f.w;
+          } else {
+            const float2 f = *(const float2*)&scr[(ug * 4 + g) * PITCH + gq * 2];
+            z[g][0] = f.x; z[g][1] = f.y;
+          }
         }
         __syncwarp();
-        const long long e3 = clock64();
+        REC_CLK(e3);
         uint8_t* stg = stage_base + p * 1024;
         // loads first, stores last: a shared-memory store between two cells would serialise
         // them (the compiler must assume it aliases the next cell's loads)
-        float4 gsv[4];
+        float4 gsv[CPT];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < CPT; ++j) {
           const bool active = td < len[j];
           const float c_prev = cst[j];
-          // branch-free so that the four cells of a thread interleave (ILP); inactive steps
+          // branch-free so that the cells of a thread interleave (ILP); inactive steps
           // (t >= seq_len) discard the result below
           float zi = z[0][j] + G4[j].x, zg = z[1][j] + G4[j].y;
           float zf = z[2][j] + G4[j].z + a.forget_bias, zo = z[3][j] + G4[j].w;
@@ -384,51 +426,58 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
           gsv[j] = make_float4(gi, gg, gf, go);
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int bl = gq * 4 + j;
+        for (int j = 0; j < CPT; ++j) {
           // state h (carried through inactive steps) feeds the next step's GEMM
-          const int off = (ul >> 3) * 256 + (bl >> 3) * 128 + (bl & 7) * 16 + (ul & 7) * 2;
+          const int off = (ul >> 3) * 256 + (bl[j] >> 3) * 128 + (bl[j] & 7) * 16 + (ul & 7) * 2;
           *(__nv_bfloat16*)(stg + off) = __float2bfloat16(hst[j]);
         }
+        REC_CLK(e4);
+        fence_proxy_async_smem();                 // staged h visible to the bulk-copy engine
+        named_bar_sync(1 + c, GTHREADS);
+        REC_CLK(e5);
+        if (ctid == 0) { mbar_arrive(&gempty[c * RGS + stage]); mbar_arrive(&stfull[c * 2 + p]); }
+        if (t + 1 < T && ctid < CS) mbar_expect_tx(&hfull[(c * 2 + (p ^ 1)) * 16 + ctid], 1024);
+        // GT::SENDS lanes in each of the chain's GW warps issue the CS bulk copies (one per peer): a warp
+        // issues one async-proxy operation per ~53 cycles, so the issue is spread over all warps of the team
+        {
+          const int dstcta = gw * GT::SENDS + lane;
+          if (t + 1 < T && lane < GT::SENDS && dstcta < CS) {
+            uint8_t* dst = smem + L::kHbufOff + (c * 2 + (p ^ 1)) * L::kHbufBytes + cta * 1024;
+            bulk_s2cluster(dst, stg, 1024, &hfull[(c * 2 + (p ^ 1)) * 16 + cta], (uint32_t)dstcta);
+          }
+        }
+        REC_CLK(e6);
+        // reserve for BPTT: after the hand-off, so that these global stores overlap the DSMEM flight and
+        // the next step's MMAs instead of delaying them
         if (a.gates) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
+          for (int j = 0; j < CPT; ++j)
             if (bidx[j] < B) {
               const size_t cell = cell0[j] + (size_t)td * cell_step;
               *(float4*)(a.gates + cell * 4) = gsv[j];
               a.cs[cell] = cst[j];
             }
         }
-        const long long e4 = clock64();
-        fence_proxy_async_smem();                 // staged h visible to the bulk-copy engine
-        named_bar_sync(1 + c, 128);
-        const long long e5 = clock64();
-        if (ctid == 0) { mbar_arrive(&gempty[c * RGS + stage]); mbar_arrive(&stfull[c * 2 + p]); }
-        if (t + 1 < T && ctid < CS) mbar_expect_tx(&hfull[(c * 2 + (p ^ 1)) * 16 + ctid], 1024);
-        // 4 lanes in each of the chain's 4 warps issue the CS bulk copies (one per peer):
-        // spreading the issue over warps costs ~250 cycles instead of ~850 from one warp
-        {
-          const int dstcta = q * 4 + lane;
-          if (t + 1 < T && lane < 4 && dstcta < CS) {
-            uint8_t* dst = smem + L::kHbufOff + (c * 2 + (p ^ 1)) * L::kHbufBytes + cta * 1024;
-            bulk_s2cluster(dst, stg, 1024, &hfull[(c * 2 + (p ^ 1)) * 16 + cta], (uint32_t)dstcta);
-          }
-        }
-        if (dbg) {
-          const long long e6 = clock64();
+#if B2_REC_TIMING
+        if (a.dbg && blockIdx.x == 0 && ctid == 0 && c == 0) {
+          const long long e7 = clock64();
           a.dbg[2] += e2 - e1;   // wait accumulator
           a.dbg[3] += e3 - e2;   // tmem ld + transpose
           a.dbg[4] += e1 - e0;   // G prefetch + staging-free wait (overlaps the MMAs)
-          a.dbg[5] += e4 - e3;   // gate math + saves
+          a.dbg[5] += e4 - e3;   // gate math + staging
           a.dbg[6] += e5 - e4;   // fence + named barrier
-          a.dbg[7] += e6 - e5;   // sends + output store
+          a.dbg[7] += e6 - e5;   // arrives + sends
+          a.dbg[1] += e7 - e6;   // reserve stores
         }
+#endif
         if (++stage == RGS) { stage = 0; gph ^= 1; }
       }
+#if B2_REC_TIMING
       if (a.dbg && ctid == 0 && cta == 0) a.dbg[16 + cluster_id * 2 + c] = clock64() - loop_t0;
+#endif
       if (a.final_state) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < CPT; ++j)
           if (bidx[j] < B) {
             a.final_state[((size_t)(dir * 2 + 0) * B + bidx[j]) * H + u] = cst[j];
             a.final_state[((size_t)(dir * 2 + 1) * B + bidx[j]) * H + u] = hst[j];
@@ -448,16 +497,16 @@ bool rec_tc_supported(int H) {
   return cs == 1 || cs == 2 || cs == 4 || cs == 8 || cs == 16;
 }
 
-template <int NCHAIN, int KS>
+template <int NCHAIN, int KS, int GW>
 static int launch_rec_fwd(const CUtensorMap& tmG, const RecFwdArgs& a, int nclusters, int CS,
                           cudaStream_t stream) {
-  using L = RecSmem<NCHAIN>;
-  auto kern = lstm_rec_fwd_kernel<NCHAIN, KS>;
+  using L = RecSmem<NCHAIN, GW>;
+  auto kern = lstm_rec_fwd_kernel<NCHAIN, KS, GW>;
   B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes));
   if (CS > 8) B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(nclusters * CS);
-  cfg.blockDim = dim3(160 + 160 * NCHAIN);
+  cfg.blockDim = dim3(160 + (GW * 32 + 32) * NCHAIN);
   cfg.dynamicSmemBytes = L::kBytes;
   cfg.stream = stream;
   cudaLaunchAttribute at[1];
@@ -470,11 +519,13 @@ static int launch_rec_fwd(const CUtensorMap& tmG, const RecFwdArgs& a, int nclus
 }
 
 // G: [T*B, 8H] fp32 gate pre-activations, column = dir*4H + u*4 + gate (packed order)
-int rec_tc_forward(RecFwdArgs a, const float* G, int nchain, cudaStream_t stream) {
+// gate_warps: 4 or 8 warps per chain in the gate-math team (0 = default)
+int rec_tc_forward(RecFwdArgs a, const float* G, int nchain, int gate_warps, cudaStream_t stream) {
   const int H = a.H, CS = H / RU;
   a.NG = cdiv(a.B, RN);
   if (nchain < 1) nchain = (a.NG >= 2) ? 2 : 1;
   if (nchain > 2) nchain = 2;
+  if (gate_warps != 4 && gate_warps != 8) gate_warps = kDefaultGateWarps;
   const int nclusters = 2 * cdiv(a.NG, nchain);
   CUtensorMap tmG;
   const uint64_t dims[3] = {(uint64_t)4 * H, 2, (uint64_t)a.T * a.B};
@@ -482,10 +533,14 @@ int rec_tc_forward(RecFwdArgs a, const float* G, int nchain, cudaStream_t stream
   const uint32_t box[3] = {128, 1, RN};
   int rc = make_tmap_generic(&tmG, 1, G, 3, dims, strides, box, 0);
   if (rc) return rc;
-#define B2_REC_DISPATCH(KS_)                                                          \
-  if (H / 16 == KS_) {                                                               \
-    if (nchain == 2) return launch_rec_fwd<2, KS_>(tmG, a, nclusters, CS, stream);  \
-    return launch_rec_fwd<1, KS_>(tmG, a, nclusters, CS, stream);                   \
+#define B2_REC_DISPATCH(KS_)                                                                   \
+  if (H / 16 == KS_) {                                                                        \
+    if (gate_warps == 8) {                                                                    \
+      if (nchain == 2) return launch_rec_fwd<2, KS_, 8>(tmG, a, nclusters, CS, stream);      \
+      return launch_rec_fwd<1, KS_, 8>(tmG, a, nclusters, CS, stream);                       \
+    }                                                                                         \
+    if (nchain == 2) return launch_rec_fwd<2, KS_, 4>(tmG, a, nclusters, CS, stream);        \
+    return launch_rec_fwd<1, KS_, 4>(tmG, a, nclusters, CS, stream);                         \
   }
   B2_REC_DISPATCH(2) B2_REC_DISPATCH(4) B2_REC_DISPATCH(8) B2_REC_DISPATCH(16) B2_REC_DISPATCH(32)
 #undef B2_REC_DISPATCH
@@ -514,11 +569,22 @@ struct RecBwdSmem {
   static constexpr int kBytes = kBarOff + 512;
 };
 
-template <int NCHAIN>
-__global__ void __launch_bounds__(160 + 128 * NCHAIN, 1)
+template <int NCHAIN, int GW>
+__global__ void __launch_bounds__(256 + GW * 32 * NCHAIN, 1)
 lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_constant__ CUtensorMap tmCs,
                     const __grid_constant__ CUtensorMap tmDy, const RecBwdArgs a) {
   using L = RecBwdSmem<NCHAIN>;
+  using GT = GateTeam<GW>;
+  constexpr int NBW = GT::NBW, CPT = GT::CPT;
+  constexpr int GTHREADS = GW * 32;
+  // warp roles (warpgroup aligned, so that setmaxnreg can move registers from the issuer / producer
+  // warpgroups to the gate-math teams): 0..3 MMA issuers | 4 .. 4+GW*NCHAIN-1 gate math | then the TMA
+  // producer warpgroup (its first warp works, the other three only give up their registers)
+  constexpr int W_GATE0 = 4, W_PROD = 4 + GW * NCHAIN;
+  // launch allocation (from __launch_bounds__): 168 / 128 / 128 / 80 registers for (GW,NCHAIN) = (4,1) (4,2) (8,1) (8,2);
+  // gate threads + 56 per issuer thread + 24 per producer-warpgroup thread stay inside the CTA's pool and inside
+  // the 16 K registers of each SM sub-partition
+  constexpr int GATE_REGS = GW == 4 ? 208 : (NCHAIN == 1 ? 128 : 96);
   extern __shared__ __align__(1024) uint8_t smem[];
   const int H = a.H, T = a.T, B = a.B;
   const int CS = H / RU;
@@ -552,7 +618,7 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
   const uint32_t tA = tmem;                    // tile m at columns [64m, 64m+64)
   const uint32_t tAcc = tmem + 256;            // [NCHAIN][4] x 16 columns
 
-  if (warp >= 5 && warp < 9) {                 // transposed weight slice -> TMEM
+  if (warp >= W_GATE0 && warp < W_GATE0 + 4) {   // transposed weight slice -> TMEM (one warp per lane quarter)
     const int q = warp & 3;
     const int row = q * 32 + lane;
     for (int m = 0; m < MT; ++m) {
@@ -574,9 +640,12 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
   __syncthreads();
   tc_fence_after();
   cluster_sync();
+  // every CTA of this cluster is running: tell the host-side scheduler (side-stream GEMMs wait for all clusters)
+  if (a.resident && cta == 0 && threadIdx.x == 0) atomicAdd(a.resident, 1u);
 
   if (warp < NISSW) {
     // ------------------------------------------------------------- MMA issuers (one M tile each)
+    reg_dealloc<56>();
     if (lane == 0 && warp < MT) {
       const uint32_t idesc = make_idesc_bf16(128, RN, 0, 0);
       int sc[NCHAIN];
@@ -604,9 +673,10 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp >= W_PROD) {
     // ------------------------------------------------------------- TMA producer
-    if (lane == 0) {
+    reg_dealloc<24>();
+    if (warp == W_PROD && lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int s = 0; s < T; ++s) {
         const int td = dir ? s : T - 1 - s;
@@ -630,30 +700,36 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
     }
   } else {
     // ------------------------------------------------------------- gate math
-    const int c = (warp - 5) >> 2;
+    reg_alloc<GATE_REGS>();
+    const int c = (warp - W_GATE0) / GW;
     const int grp = gbase + c;
     if (grp < a.NG) {
-      const int q = warp & 3;
+      const int gw = (warp - W_GATE0) - c * GW;
+      const int q = warp & 3;                    // TMEM lane quarter (hardware: warp_id % 4)
+      const int col0 = (gw >> 2) * NBW;
       const int ug = lane >> 2, gq = lane & 3;
       const int ul = q * 8 + ug;
       const int u = cta * RU + ul;
-      const int ctid = threadIdx.x - 160 - c * 128;
-      int bidx[4], len[4];
-      float dcs[4];
+      const int ctid = threadIdx.x - W_GATE0 * 32 - c * GTHREADS;
+      int bl[CPT], bidx[CPT], len[CPT];
+      float dcs[CPT];
       float gacc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // db_i, db_g, db_f, db_o, dw_i, dw_f, dw_o
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        bidx[j] = grp * RN + gq * 4 + j;
+      for (int j = 0; j < CPT; ++j) {
+        bl[j] = col0 + gq * CPT + j;
+        bidx[j] = grp * RN + bl[j];
         len[j] = bidx[j] < B ? a.seq_len[bidx[j]] : 0;
         dcs[j] = 0.f;
       }
       // gradient of the layer's final state (encoder -> decoder bridge): enters at the first
       // active BPTT step of each utterance
       // (dcs is only rewritten by active steps, so d(c_final) simply is its initial value)
-      float dfh[4] = {0.f, 0.f, 0.f, 0.f};
+      float dfh[CPT];
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) dfh[j] = 0.f;
       if (a.dfinal) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < CPT; ++j)
           if (bidx[j] < B) {
             dcs[j] = a.dfinal[((size_t)(dir * 2 + 0) * B + bidx[j]) * H + u];
             dfh[j] = a.dfinal[((size_t)(dir * 2 + 1) * B + bidx[j]) * H + u];
@@ -662,9 +738,9 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
       float pwi = 0.f, pwf = 0.f, pwo = 0.f;
       if (a.use_peephole) { pwi = a.wi[dir][u]; pwf = a.wf[dir][u]; pwo = a.wo[dir][u]; }
       uint8_t* bop = smem + L::kBopOff + c * 4096;
-      __nv_bfloat16* dgp[4];
+      __nv_bfloat16* dgp[CPT];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < CPT; ++j)
         dgp[j] = a.dG + (size_t)bidx[j] * 8 * H + (size_t)dir * 4 * H + u * 4;
       const size_t dg_step = (size_t)B * 8 * H;
       int stage = 0; uint32_t gph = 0;
@@ -674,147 +750,182 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
         const int tn = dir ? td - 1 : td + 1;    // step processed just before (BPTT order)
         const int tp = dir ? td + 1 : td - 1;    // previous step in forward order
         const int p = s & 1;
-        const bool dbg = a.dbg && blockIdx.x == 0 && ctid == 0 && c == 0;
-        const long long b0 = clock64();
-        // ---- A) dh_rec = sum of the peers' partial slices
-        float dh_rec[4] = {0.f, 0.f, 0.f, 0.f};
-        if (s > 0) {
-          mbar_wait_cluster(&rfull[c * 2 + p], (rph >> p) & 1u);   // measured (twice): 7.15 vs 7.9 ms/layer with a CTA-scope wait
-          rph ^= 1u << p;
-          const uint8_t* rb = smem + L::kRecvOff + (c * 2 + p) * 16384 + (ul * 16 + gq * 4) * 2;
-          for (int src = 0; src < CS; ++src) {
-            const uint2 raw = *(const uint2*)(rb + src * 1024);
-            dh_rec[0] += __uint_as_float(raw.x << 16);
-            dh_rec[1] += __uint_as_float(raw.x & 0xffff0000u);
-            dh_rec[2] += __uint_as_float(raw.y << 16);
-            dh_rec[3] += __uint_as_float(raw.y & 0xffff0000u);
-          }
-        }
-        const long long b1 = clock64();
+        REC_CLK(b0);
+        // ---- everything that does not depend on dh first (the TMA ring runs ahead; the peers' partial sums
+        //      are still in flight): saved gates / cell states / dy from the ring, tanh(c), and the linear
+        //      coefficients of dh and dc in the gate derivatives
         mbar_wait(&gfull[c * BGS + stage], gph);
-        const long long b2 = clock64();
+        REC_CLK(b1);
         const float* Rs = (const float*)(smem + L::kRingOff + (c * BGS + stage) * BSTAGE);
         const bool tp_ok = tp >= 0 && tp < T;
-        // loads first, stores last (see the forward kernel)
-        float4 g4[4];
-        float ccv[4], cpv[4], dyq[4];
+        float dyq[CPT], kzo[CPT], kdc[CPT], kzi[CPT], kzg[CPT], kzf[CPT], kcp[CPT], ccv[CPT], cpv[CPT];
+        bool clipz[CPT];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int bl = gq * 4 + j;
-          g4[j] = *(const float4*)(Rs + bl * 128 + ul * 4);
-          ccv[j] = Rs[2048 + bl * 32 + ul];
-          cpv[j] = tp_ok ? Rs[2048 + 512 + bl * 32 + ul] : 0.f;
-          dyq[j] = Rs[2048 + 1024 + bl * 32 + ul];
+        for (int j = 0; j < CPT; ++j) {
+          const float4 g4 = *(const float4*)(Rs + bl[j] * 128 + ul * 4);
+          const float cc = Rs[2048 + bl[j] * 32 + ul];
+          const float c_prev = tp_ok ? Rs[2048 + 512 + bl[j] * 32 + ul] : 0.f;
+          dyq[j] = Rs[2048 + 1024 + bl[j] * 32 + ul];
+          const float gi = g4.x, gg = g4.y, gf = g4.z, go = g4.w;
+          const float Ec = __expf(fminf(-2.f * cc, 25.f));
+          const float tc = (1.f - Ec) * fast_rcp(1.f + Ec);
+          // dzo = dh * kzo ; dc = dc_in + dh * kdc  (kdc includes the peephole path through dzo)
+          kzo[j] = tc * go * (1.f - go);
+          kdc[j] = fmaf(kzo[j], pwo, go * (1.f - tc * tc));
+          // dzi = dc * kzi ; dzg = dc * kzg ; dzf = dc * kzf ; dc_prev = dc * kcp
+          kzi[j] = gg * gi * (1.f - gi);
+          kzg[j] = gi * (1.f - gg * gg);
+          kzf[j] = c_prev * gf * (1.f - gf);
+          kcp[j] = fmaf(kzf[j], pwf, fmaf(kzi[j], pwi, gf));
+          clipz[j] = a.cell_clip > 0.f && fabsf(cc) >= a.cell_clip;
+          ccv[j] = cc; cpv[j] = c_prev;
         }
-        if (a.keep_prob < 1.f) {       // DropoutWrapper mask, outside the cell loop (keeps it branch-free)
+        if (a.keep_prob < 1.f) {       // DropoutWrapper mask (only when the caller did not pre-mask dy)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < CPT; ++j) {
             const size_t oidx = ((size_t)td * B + bidx[j]) * 2 * H + (size_t)dir * H + u;
             dyq[j] = dropout_keep(a.seed, oidx, a.keep_prob) ? dyq[j] / a.keep_prob : 0.f;
           }
         }
-        const long long bL = clock64();
-        uint2 pkv[4];
+        REC_CLK(b2);
+        // ---- A) dh_rec = sum of the peers' partial slices
+        float dh_rec[CPT];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float cc = ccv[j], c_prev = cpv[j];
-          const float dyv = dyq[j];
+        for (int j = 0; j < CPT; ++j) dh_rec[j] = 0.f;
+        if (s > 0) {
+          // the partials are written by the peers' bulk copies (async proxy, complete_tx on this barrier).
+          // wait_mode 0: spin with a cluster-scope acquire (ptxas puts CCTL.IVALL into the spin loop);
+          // 1: spin at CTA scope, then ONE cluster-scope acquire; 2: CTA scope only (as TMA consumers do)
+          // -- measured equal for 0 and 2 (6.38 ms/layer fwd+bwd), 7.76 for 1
+          if (a.wait_mode == 0) {
+            mbar_wait_cluster(&rfull[c * 2 + p], (rph >> p) & 1u);
+          } else {
+            mbar_wait(&rfull[c * 2 + p], (rph >> p) & 1u);
+            if (a.wait_mode == 1) fence_acq_rel_cluster();
+          }
+          rph ^= 1u << p;
+          const uint8_t* rb = smem + L::kRecvOff + (c * 2 + p) * 16384 + (ul * 16 + col0 + gq * CPT) * 2;
+          for (int src = 0; src < CS; ++src) {
+            if constexpr (CPT == 4) {
+              const uint2 raw = *(const uint2*)(rb + src * 1024);
+              dh_rec[0] += __uint_as_float(raw.x << 16);
+              dh_rec[1] += __uint_as_float(raw.x & 0xffff0000u);
+              dh_rec[2] += __uint_as_float(raw.y << 16);
+              dh_rec[3] += __uint_as_float(raw.y & 0xffff0000u);
+            } else {
+              const uint32_t raw = *(const uint32_t*)(rb + src * 1024);
+              dh_rec[0] += __uint_as_float(raw << 16);
+              dh_rec[1] += __uint_as_float(raw & 0xffff0000u);
+            }
+          }
+        }
+        REC_CLK(bL);
+        uint2 pkv[CPT];
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
           const bool active = td < len[j];
           const bool nb_active = s > 0 && tn >= 0 && tn < T && tn < len[j];
-          const float dh = dyv + (nb_active ? dh_rec[j] : dfh[j]);
-          const float dc_in = dcs[j];
-          const float gi = g4[j].x, gg = g4[j].y, gf = g4[j].z, go = g4[j].w;
-          const float Ec = __expf(fminf(-2.f * cc, 25.f));
-          const float tc = (1.f - Ec) * fast_rcp(1.f + Ec);
-          const float dzo = dh * tc * go * (1.f - go);
-          float dc = dc_in + dh * go * (1.f - tc * tc);
-          dc = fmaf(dzo, pwo, dc);
-          if (a.cell_clip > 0.f && fabsf(cc) >= a.cell_clip) dc = 0.f;
-          float dzi = dc * gg * gi * (1.f - gi);
-          float dzg = dc * gi * (1.f - gg * gg);
-          float dzf = dc * c_prev * gf * (1.f - gf);
-          const float dc_prev = fmaf(dzf, pwf, fmaf(dzi, pwi, dc * gf));
-          dcs[j] = active ? dc_prev : dcs[j];
+          const float dh = dyq[j] + (nb_active ? dh_rec[j] : dfh[j]);
+          const float dzo = dh * kzo[j];
+          float dc = fmaf(dh, kdc[j], dcs[j]);
+          if (clipz[j]) dc = 0.f;
+          float dzi = dc * kzi[j], dzg = dc * kzg[j];
+          const float dzf = dc * kzf[j];
+          dcs[j] = active ? dc * kcp[j] : dcs[j];
           dzi = active ? dzi : 0.f; dzg = active ? dzg : 0.f;
           const float dzf2 = active ? dzf : 0.f, dzo2 = active ? dzo : 0.f;
           // bias and peephole gradients accumulate in registers over the whole sequence
           gacc[0] += dzi; gacc[1] += dzg; gacc[2] += dzf2; gacc[3] += dzo2;
-          gacc[4] = fmaf(dzi, c_prev, gacc[4]); gacc[5] = fmaf(dzf2, c_prev, gacc[5]);
-          gacc[6] = fmaf(dzo2, cc, gacc[6]);
+          gacc[4] = fmaf(dzi, cpv[j], gacc[4]); gacc[5] = fmaf(dzf2, cpv[j], gacc[5]);
+          gacc[6] = fmaf(dzo2, ccv[j], gacc[6]);
           __nv_bfloat162 lo = __floats2bfloat162_rn(dzi, dzg), hi = __floats2bfloat162_rn(dzf2, dzo2);
           pkv[j].x = *(uint32_t*)&lo; pkv[j].y = *(uint32_t*)&hi;
         }
-        const long long bM = clock64();
+        REC_CLK(bM);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int bl = gq * 4 + j;
-          *(uint2*)(bop + (ul >> 1) * 256 + (bl >> 3) * 128 + (bl & 7) * 16 + (ul & 1) * 8) = pkv[j];
-          if (bidx[j] < B) *(uint2*)(dgp[j] + (size_t)td * dg_step) = pkv[j];
-        }
-        const long long b3 = clock64();
+        for (int j = 0; j < CPT; ++j)
+          *(uint2*)(bop + (ul >> 1) * 256 + (bl[j] >> 3) * 128 + (bl[j] & 7) * 16 + (ul & 1) * 8) = pkv[j];
+        REC_CLK(b3);
         fence_proxy_async_smem();
-        named_bar_sync(1 + c, 128);
+        tc_fence_before();                         // this thread's accumulator reads of step s-1 are done
+        named_bar_sync(1 + c, GTHREADS);
         if (ctid == 0) {
           mbar_arrive(&gempty[c * BGS + stage]);
           if (s + 1 < T) mbar_arrive(&bready[c]);
         }
+        // dG (operand of the time-batched weight/input-gradient GEMMs) goes out after the hand-off to the
+        // issuers: the stores overlap the step's MMAs instead of delaying them
+#pragma unroll
+        for (int j = 0; j < CPT; ++j)
+          if (bidx[j] < B) *(uint2*)(dgp[j] + (size_t)td * dg_step) = pkv[j];
         if (++stage == BGS) { stage = 0; gph ^= 1; }
         if (s + 1 >= T) break;
         // ---- C) partial dh of this step -> bf16 slices for the peers
-        const long long b4 = clock64();
+        REC_CLK(b4);
         mbar_wait(&accfull[c], s & 1);
         tc_fence_after();
-        const long long b5 = clock64();
+        REC_CLK(b5);
         uint8_t* sst = smem + L::kSendOff + (c * 2 + (p ^ 1)) * 16384;
         {
-          uint32_t v[4][16];
+          uint32_t v[4][NBW];
 #pragma unroll
           for (int m = 0; m < 4; ++m)
-            if (m < MT) tmem_ld_32x32b_x16(tAcc + (c * 4 + m) * ACC_STRIDE + ((uint32_t)(q * 32) << 16), v[m]);
+            if (m < MT) tmem_ld_cols<NBW>(tAcc + (c * 4 + m) * ACC_STRIDE + ((uint32_t)(q * 32) << 16) + col0, v[m]);
           tmem_ld_wait();
 #pragma unroll
           for (int m = 0; m < 4; ++m) {
             const int dest = m * 4 + q;
             if (m < MT && dest < CS) {
-              uint32_t pk[8];
+              uint32_t pk[NBW / 2];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
+              for (int i = 0; i < NBW / 2; ++i) {
                 __nv_bfloat162 b2v = __floats2bfloat162_rn(__uint_as_float(v[m][2 * i]), __uint_as_float(v[m][2 * i + 1]));
                 pk[i] = *(uint32_t*)&b2v;
               }
-              uint4* d4 = (uint4*)(sst + dest * 1024 + lane * 32);
-              d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+              uint4* d4 = (uint4*)(sst + dest * 1024 + lane * 32 + col0 * 2);
+#pragma unroll
+              for (int i = 0; i < NBW / 8; ++i)
+                d4[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
             }
           }
         }
-        const long long b6 = clock64();
-        tc_fence_before();
+        REC_CLK(b6);
         fence_proxy_async_smem();
-        named_bar_sync(1 + c, 128);
         if (ctid == 0) mbar_expect_tx(&rfull[c * 2 + (p ^ 1)], rall);
-        {
-          const int dstcta = q * 4 + lane;
-          if (lane < 4 && dstcta < CS) {
+        if constexpr (GW == 4) {
+          // warp q staged the COMPLETE 1 KB slices of destinations q, 4+q, 8+q, 12+q (one per M tile): it sends
+          // them itself after a warp-level sync -- no CTA-wide barrier between the accumulator read and the send
+          __syncwarp();
+          const int dstcta = lane * 4 + q;
+          if (lane < 4 && lane < MT && dstcta < CS) {
+            uint8_t* dst = smem + L::kRecvOff + (c * 2 + (p ^ 1)) * 16384 + cta * 1024;
+            bulk_s2cluster(dst, sst + dstcta * 1024, 1024, &rfull[c * 2 + (p ^ 1)], (uint32_t)dstcta);
+          }
+        } else {
+          named_bar_sync(1 + c, GTHREADS);         // two warps share a slice: both halves must be staged
+          const int dstcta = gw * GT::SENDS + lane;
+          if (lane < GT::SENDS && dstcta < CS) {
             uint8_t* dst = smem + L::kRecvOff + (c * 2 + (p ^ 1)) * 16384 + cta * 1024;
             bulk_s2cluster(dst, sst + dstcta * 1024, 1024, &rfull[c * 2 + (p ^ 1)], (uint32_t)dstcta);
           }
         }
-        if (dbg) {
+#if B2_REC_TIMING
+        if (a.dbg && blockIdx.x == 0 && ctid == 0 && c == 0) {
           const long long b7 = clock64();
-          a.dbg[0] += b1 - b0;   // wait partials + sum
-          a.dbg[1] += b2 - b1;   // wait ring
-          a.dbg[2] += b3 - b2;   // math + stores
-          a.dbg[8] += bL - b2;   //   smem loads
-          a.dbg[9] += bM - bL;   //   math
-          a.dbg[10] += b3 - bM;  //   stores
-          a.dbg[3] += b4 - b3;   // fence + bar + arrive
+          a.dbg[1] += b1 - b0;   // wait ring
+          a.dbg[8] += b2 - b1;   // ring loads + dh-independent coefficients
+          a.dbg[0] += bL - b2;   // wait partials + sum
+          a.dbg[9] += bM - bL;   // dh-dependent math
+          a.dbg[10] += b3 - bM;  // staging stores
+          a.dbg[2] += b3 - b1;   // (everything between ring wait and barrier 1)
+          a.dbg[3] += b4 - b3;   // fence + bar + arrive + dG stores
           a.dbg[4] += b5 - b4;   // wait MMA
           a.dbg[5] += b6 - b5;   // tmem ld + convert + stage
           a.dbg[6] += b7 - b6;   // fence + bar + sends
         }
+#endif
       }
-      // flush the register-accumulated bias / peephole gradients (4 batch quads x chains x clusters)
+      // flush the register-accumulated bias / peephole gradients (batch quads x chains x clusters)
       if (a.dbias) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) atomicAdd(&a.dbias[(size_t)dir * 4 * H + u * 4 + g], gacc[g]);
@@ -832,16 +943,16 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-template <int NCHAIN>
+template <int NCHAIN, int GW>
 static int launch_rec_bwd(const CUtensorMap& tg, const CUtensorMap& tc, const CUtensorMap& td,
                           const RecBwdArgs& a, int nclusters, int CS, cudaStream_t stream) {
   using L = RecBwdSmem<NCHAIN>;
-  auto kern = lstm_rec_bwd_kernel<NCHAIN>;
+  auto kern = lstm_rec_bwd_kernel<NCHAIN, GW>;
   B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes));
   if (CS > 8) B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(nclusters * CS);
-  cfg.blockDim = dim3(160 + 128 * NCHAIN);
+  cfg.blockDim = dim3(256 + GW * 32 * NCHAIN);
   cfg.dynamicSmemBytes = L::kBytes;
   cfg.stream = stream;
   cudaLaunchAttribute at[1];
@@ -853,11 +964,12 @@ static int launch_rec_bwd(const CUtensorMap& tg, const CUtensorMap& tc, const CU
   return B2_OK;
 }
 
-int rec_tc_backward(RecBwdArgs a, const float* dy, int nchain, cudaStream_t stream) {
+int rec_tc_backward(RecBwdArgs a, const float* dy, int nchain, int gate_warps, cudaStream_t stream) {
   const int H = a.H, CS = H / RU;
   a.NG = cdiv(a.B, RN);
   if (nchain < 1) nchain = (a.NG >= 2) ? 2 : 1;
   if (nchain > 2) nchain = 2;
+  if (gate_warps != 4 && gate_warps != 8) gate_warps = kDefaultGateWarps;
   const int nclusters = 2 * cdiv(a.NG, nchain);
   const uint64_t TB = (uint64_t)a.T * a.B;
   CUtensorMap tg, tc, td;
@@ -877,8 +989,12 @@ int rec_tc_backward(RecBwdArgs a, const float* dy, int nchain, cudaStream_t stre
     rc = make_tmap_generic(&td, 1, dy, 3, dims, strides, box, 0);
     if (rc) return rc;
   }
-  if (nchain == 2) return launch_rec_bwd<2>(tg, tc, td, a, nclusters, CS, stream);
-  return launch_rec_bwd<1>(tg, tc, td, a, nclusters, CS, stream);
+  if (gate_warps == 8) {
+    if (nchain == 2) return launch_rec_bwd<2, 8>(tg, tc, td, a, nclusters, CS, stream);
+    return launch_rec_bwd<1, 8>(tg, tc, td, a, nclusters, CS, stream);
+  }
+  if (nchain == 2) return launch_rec_bwd<2, 4>(tg, tc, td, a, nclusters, CS, stream);
+  return launch_rec_bwd<1, 4>(tg, tc, td, a, nclusters, CS, stream);
 }
 
 }  // namespace b2

@@ -7,6 +7,7 @@ namespace b2 {
 
 constexpr int RU = 32;        // hidden units per CTA
 constexpr int RN = 16;        // batch columns per chain (MMA N)
+constexpr int kDefaultGateWarps = 4;   // gate-math warps per chain (4 or 8; B2_REC_GW overrides)
 
 struct RecFwdArgs {
   int T, B, H, NG;            // NG = number of 16-wide batch groups per direction (filled by launcher)
@@ -33,12 +34,14 @@ struct RecBwdArgs {
   const float* dfinal;        // [4,B,H] or null
   float* dbias;               // [8H] packed bias gradient (+=), or null
   float* dwi[2]; float* dwf[2]; float* dwo[2];   // peephole gradients (+=)
+  int wait_mode;              // how the gate warps wait for the peers' partials (see the kernel; B2_REC_WAIT)
+  unsigned* resident;         // optional device counter: +1 per cluster once all of its CTAs are running
   long long* dbg;
 };
 
 bool rec_tc_supported(int H);
-int rec_tc_forward(RecFwdArgs a, const float* G, int nchain, cudaStream_t stream);
+int rec_tc_forward(RecFwdArgs a, const float* G, int nchain, int gate_warps, cudaStream_t stream);
 // dy: [T,B,2H] fp32 gradient of the layer output (after dropout)
-int rec_tc_backward(RecBwdArgs a, const float* dy, int nchain, cudaStream_t stream);
+int rec_tc_backward(RecBwdArgs a, const float* dy, int nchain, int gate_warps, cudaStream_t stream);
 
 }  // namespace b2

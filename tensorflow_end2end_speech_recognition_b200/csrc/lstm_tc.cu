@@ -17,8 +17,7 @@ static size_t pad8(size_t x) { return (x + 7) / 8 * 8; }
 
 struct TcWork {
   float* G;                  // [TB, 8H] fp32 gate pre-activations (forward)
-  __nv_bfloat16* dG;         // [TB, 8H] bf16 gate gradients (backward), set 0 / set 1 below
-  __nv_bfloat16* dG2[2]; float* dwx2[2]; float* dwh2[2]; float* dbias2[2];
+  __nv_bfloat16* dG;         // [TB, 8H] bf16 gate gradients (backward; only when the reserve holds none)
   __nv_bfloat16* xb;         // [TB, pad8(D)] bf16 copy of x when the caller has none
   __nv_bfloat16* wx;         // [D, 8H] packed input weights
   float* bias;               // [8H] packed bias
@@ -44,12 +43,6 @@ static size_t tc_work_layout(const b2_lstm_desc* d, void* base, TcWork* w) {
   const size_t odwx = take(D * 8 * H * 4);
   const size_t odwh = take(2 * H * 4 * H * 4);
   const size_t odb = take(8 * H * 4);
-  // second set of backward buffers: the weight-gradient GEMMs of layer l run on a side stream
-  // while layer l-1's recurrence already fills the other set
-  const size_t oG1 = take(TB * 8 * H * 2);
-  const size_t odwx1 = take(D * 8 * H * 4);
-  const size_t odwh1 = take(2 * H * 4 * H * 4);
-  const size_t odb1 = take(8 * H * 4);
   const size_t odym = d->keep_prob < 1.f ? take(TB * 2 * H * 4) : 0;
   if (w) {
     char* p = (char*)base;
@@ -57,12 +50,19 @@ static size_t tc_work_layout(const b2_lstm_desc* d, void* base, TcWork* w) {
     w->wx = (__nv_bfloat16*)(p + owx); w->bias = (float*)(p + ob); w->wh = (uint16_t*)(p + owh);
     w->whT = (uint16_t*)(p + owt); w->dwx = (float*)(p + odwx); w->dwh = (float*)(p + odwh);
     w->dbias = (float*)(p + odb);
-    w->dG2[0] = w->dG; w->dwx2[0] = w->dwx; w->dwh2[0] = w->dwh; w->dbias2[0] = w->dbias;
-    w->dG2[1] = (__nv_bfloat16*)(p + oG1); w->dwx2[1] = (float*)(p + odwx1);
-    w->dwh2[1] = (float*)(p + odwh1); w->dbias2[1] = (float*)(p + odb1);
     w->dym = d->keep_prob < 1.f ? (float*)(p + odym) : nullptr;
   }
   return off;
+}
+
+// packed weights live in the layer's reserve when a backward pass will follow (one pack per layer and step)
+static void use_reserve_pack(const b2_lstm_desc* d, void* pack, TcWork* w) {
+  char* p = (char*)pack;
+  const size_t H = d->H, D = d->D_in;
+  w->wx = (__nv_bfloat16*)p;  p += align_up(D * 8 * H * 2, 1024);
+  w->bias = (float*)p;        p += align_up(8 * H * 4, 1024);
+  w->wh = (uint16_t*)p;       p += align_up(2 * 4 * H * H * 2, 1024);
+  w->whT = (uint16_t*)p;
 }
 
 // DropoutWrapper backward, hoisted out of the BPTT kernel: dy_masked[i] = keep(seed, i) ? dy[i]/keep : 0 over the
@@ -178,14 +178,29 @@ int tc_profile_last_ms(float* fwd_ms, float* bwd_ms) {
 }
 
 // ------------------------------------------------------------------ side stream
-// Weight-gradient GEMMs are off the BPTT critical path: they run on a low-priority side
-// stream, capped to the SMs the recurrence clusters leave free, while the next layer's
-// recurrence proceeds on the caller's stream.
+// Weight-gradient GEMMs are off the BPTT critical path.  With B2_SIDE_STREAM=1 (default) the GEMMs of layer l
+// run on a low-priority side stream NEXT TO layer l-1's BPTT recurrence, on the SMs its clusters leave free:
+//   * they are enqueued only after layer l-1's recurrence kernel has been launched, and the side stream
+//     first waits (cuStreamWaitValue32) until every cluster of that kernel has reported itself resident --
+//     otherwise the persistent GEMM CTAs spread over all GPCs and the 16-CTA clusters cannot be placed
+//     until the GEMM drains (measured in round 1: 41.7 vs 35.6 ms/step);
+//   * the GEMM grid is capped to the SMs the clusters do not use.
+// The last layer of a backward pass has no recurrence to hide behind: its GEMMs are flushed by
+// tc_backward_join.
+struct DeferredWgrad {
+  bool valid = false;
+  int T = 0, B = 0, D = 0, H = 0, ldx = 0;
+  const __nv_bfloat16* xa = nullptr; const __nv_bfloat16* dG = nullptr; const __nv_bfloat16* hs_lp = nullptr;
+  float* dwx = nullptr; float* dwh = nullptr; const float* dbias = nullptr;
+  float* gk0 = nullptr; float* gk1 = nullptr; float* gb0 = nullptr; float* gb1 = nullptr;
+};
 struct SideCtx {
   cudaStream_t s = nullptr;
-  cudaEvent_t ev_main = nullptr, ev_done[2] = {nullptr, nullptr};
-  bool pending[2] = {false, false};
-  int toggle = 0;
+  cudaEvent_t ev_rec = nullptr, ev_done = nullptr;
+  bool pending = false;             // side-stream work whose completion `ev_done` marks
+  DeferredWgrad def;
+  unsigned* resident = nullptr;     // device counter: clusters of the recurrence kernels that are running
+  unsigned expected = 0;            // its value once every cluster launched so far is resident
 };
 static SideCtx g_side[16];
 static SideCtx* side_ctx() {
@@ -196,20 +211,69 @@ static SideCtx* side_ctx() {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     cudaStreamCreateWithPriority(&c->s, cudaStreamNonBlocking, lo);
-    cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&c->ev_done[0], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&c->ev_done[1], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_rec, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming);
+    cudaMalloc(&c->resident, sizeof(unsigned));
+    cudaMemset(c->resident, 0, sizeof(unsigned));
   }
   return c;
 }
-// make `stream` wait for every outstanding side-stream gradient GEMM
+
+typedef int (*StreamWaitValue32Fn)(cudaStream_t, unsigned long long, unsigned, unsigned);
+static StreamWaitValue32Fn stream_wait_value_fn() {
+  static StreamWaitValue32Fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (StreamWaitValue32Fn)p;
+  }
+  return fn;
+}
+
+// dWx, dWh (packed order) and the scatter back into the TF layout, on stream gs
+static int run_wgrad(const DeferredWgrad& w, cudaStream_t gs, int cta_limit) {
+  const int TB = w.T * w.B, D = w.D, H = w.H;
+  gemm_set_cta_limit(cta_limit);
+  // dWx_packed[D, 8H] = X^T . dG
+  int rc = (cudaMemsetAsync(w.dwx, 0, (size_t)D * 8 * H * 4, gs) == cudaSuccess) ? B2_OK : B2_ERR_CUDA;
+  if (!rc) rc = gemm_bf16_tc(1, 1, D, 8 * H, TB, 1.f, w.xa, w.ldx, w.dG, 8 * H, w.dwx, 8 * H, nullptr,
+                             EPI_ATOMIC_F32, 0, gs);
+  // dWh_packed[dir][H, 4H] = Hprev_dir^T . dG_dir   (hs shifted by one step)
+  if (!rc) rc = (cudaMemsetAsync(w.dwh, 0, (size_t)2 * H * 4 * H * 4, gs) == cudaSuccess) ? B2_OK : B2_ERR_CUDA;
+  if (!rc && w.T > 1) {
+    for (int dir = 0; dir < 2 && !rc; ++dir) {
+      const __nv_bfloat16* ha = w.hs_lp + (size_t)dir * H + (dir == 0 ? 0 : (size_t)w.B * 2 * H);
+      const __nv_bfloat16* gb = w.dG + (size_t)dir * 4 * H + (dir == 0 ? (size_t)w.B * 8 * H : 0);
+      rc = gemm_bf16_tc(1, 1, H, 4 * H, (w.T - 1) * w.B, 1.f, ha, 2 * H, gb, 8 * H,
+                        w.dwh + (size_t)dir * H * 4 * H, 4 * H, nullptr, EPI_ATOMIC_F32, 0, gs);
+    }
+  }
+  gemm_set_cta_limit(0);
+  if (rc) return rc;
+  unpack_lstm_grads_kernel<<<num_sms() * 4, 256, 0, gs>>>(w.dwx, w.dwh, w.dbias, D, H, w.gk0, w.gk1, w.gb0, w.gb1);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+// make `stream` wait for every outstanding side-stream gradient GEMM (flushing the deferred ones first)
 int tc_backward_join(cudaStream_t stream) {
   SideCtx* c = side_ctx();
-  for (int k = 0; k < 2; ++k)
-    if (c->pending[k]) {
-      B2_CUDA(cudaStreamWaitEvent(stream, c->ev_done[k], 0));
-      c->pending[k] = false;
-    }
+  if (c->def.valid) {
+    B2_CUDA(cudaStreamWaitEvent(c->s, c->ev_rec, 0));        // dG of that layer is complete
+    int rc = run_wgrad(c->def, c->s, 0);
+    if (rc) return rc;
+    B2_CUDA(cudaEventRecord(c->ev_done, c->s));
+    c->pending = true;
+    c->def.valid = false;
+  }
+  if (c->pending) {
+    B2_CUDA(cudaStreamWaitEvent(stream, c->ev_done, 0));     // the side stream is in-order: covers all earlier work
+    c->pending = false;
+  }
   return B2_OK;
 }
 
@@ -245,7 +309,8 @@ int tc_layer_forward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16*
   const int T = d->T, B = d->B, D = d->D_in, H = d->H, TB = T * B;
   int rc = tc_backward_join(stream);
   if (rc) return rc;
-  rc = pack_weights(d, fw, bw, w, false, stream);
+  if (r.wpack) use_reserve_pack(d, r.wpack, &w);      // backward will reuse this pack (incl. the transposed slices)
+  rc = pack_weights(d, fw, bw, w, r.wpack != nullptr, stream);
   if (rc) return rc;
   const __nv_bfloat16* xa = x_lp;
   int ldx = D;
@@ -275,19 +340,19 @@ int tc_layer_forward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16*
     if (!dbg_buf) cudaMalloc(&dbg_buf, 64 * sizeof(long long));
     cudaMemsetAsync(dbg_buf, 0, 64 * sizeof(long long), stream);
     ra.dbg = dbg_buf;
-    rc = rec_tc_forward(ra, w.G, env_int("B2_REC_NCHAIN", 0), stream);
+    rc = rec_tc_forward(ra, w.G, env_int("B2_REC_NCHAIN", 0), env_int("B2_REC_GW", 0), stream);
     long long hb[32];
     cudaMemcpyAsync(hb, dbg_buf, sizeof(hb), cudaMemcpyDeviceToHost, stream);
     cudaStreamSynchronize(stream);
     fprintf(stderr, "[rec fwd dbg3] loop cycles per (cluster,chain): %lld %lld | %lld %lld | %lld %lld | %lld %lld\n",
             hb[16], hb[17], hb[18], hb[19], hb[20], hb[21], hb[22], hb[23]);
-    fprintf(stderr, "[rec fwd dbg] cycles/step: mma_wait_h=%lld mma_issue=%lld | epi wait_acc=%lld "
-            "ld+transpose=%lld wait_G=%lld math+saves=%lld fence+bar=%lld send+store=%lld\n",
-            hb[0] / T, hb[1] / T, hb[2] / T, hb[3] / T, hb[4] / T, hb[5] / T, hb[6] / T, hb[7] / T);
+    fprintf(stderr, "[rec fwd dbg] cycles/step (needs a -DB2_REC_TIMING=1 build): reserve_stores=%lld | wait_acc=%lld "
+            "ld+transpose=%lld wait_G=%lld math+stage=%lld fence+bar=%lld arrive+send=%lld\n",
+            hb[1] / T, hb[2] / T, hb[3] / T, hb[4] / T, hb[5] / T, hb[6] / T, hb[7] / T);
     return rc;
   }
   prof_record(0, stream);
-  rc = rec_tc_forward(ra, w.G, env_int("B2_REC_NCHAIN", 0), stream);
+  rc = rec_tc_forward(ra, w.G, env_int("B2_REC_NCHAIN", 0), env_int("B2_REC_GW", 0), stream);
   prof_record(1, stream);
   return rc;
 }
@@ -304,18 +369,15 @@ int tc_layer_backward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16
   Reserve r;
   reserve_layout(d, (void*)reserve, &r);
   const int T = d->T, B = d->B, D = d->D_in, H = d->H, TB = T * B;
-  // measured on B200: co-scheduling the GEMM CTAs delays the 16-CTA clusters of the next recurrence
-  // (41.7 vs 35.6 ms/step), so the overlap is opt-in
-  const bool use_side = env_int("B2_SIDE_STREAM", 0) != 0;
+  // side-stream overlap needs the per-layer scratch in the reserve (a forward call made with need_backward)
+  const bool use_side = env_int("B2_SIDE_STREAM", 1) != 0 && stream_wait_value_fn() != nullptr && r.dG != nullptr;
   SideCtx* sc = side_ctx();
-  const int k = use_side ? sc->toggle : 0;
-  if (sc->pending[k]) {            // the side work that last used buffer set k must be done
-    B2_CUDA(cudaStreamWaitEvent(stream, sc->ev_done[k], 0));
-    sc->pending[k] = false;
-  }
-  __nv_bfloat16* dG = w.dG2[k];
-  float* dwx = w.dwx2[k]; float* dwh = w.dwh2[k]; float* dbias = w.dbias2[k];
-  int rc = pack_weights(d, fw, bw, w, true, stream);
+  if (!use_side && (sc->def.valid || sc->pending)) { int rcj = tc_backward_join(stream); if (rcj) return rcj; }
+  __nv_bfloat16* dG = r.dG ? r.dG : w.dG;
+  float* dwx = r.dwx ? r.dwx : w.dwx; float* dwh = r.dwh ? r.dwh : w.dwh; float* dbias = r.dbias ? r.dbias : w.dbias;
+  int rc = B2_OK;
+  if (r.wpack) use_reserve_pack(d, r.wpack, &w);      // packed by this layer's forward call
+  else rc = pack_weights(d, fw, bw, w, true, stream);
   if (rc) return rc;
   // 1. BPTT recurrence -> dG (bf16, packed order); bias / peephole gradients accumulate in
   //    registers inside the kernel and are flushed with atomics
@@ -340,27 +402,48 @@ int tc_layer_backward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16
   }
   B2_CUDA(cudaMemsetAsync(dbias, 0, (size_t)8 * H * 4, stream));
   ba.dbias = dbias;
+  ba.wait_mode = env_int("B2_REC_WAIT", 0);
   ba.dbg = nullptr;
   const int nchain = env_int("B2_REC_NCHAIN", 0);
-  if (env_int("B2_REC_DBG", 0)) {
+  const int ng = cdiv(B, RN);
+  const int nch = nchain > 0 ? (nchain > 2 ? 2 : nchain) : (ng >= 2 ? 2 : 1);
+  const int nclusters = 2 * cdiv(ng, nch);
+  ba.resident = use_side ? sc->resident : nullptr;
+  if (env_int("B2_REC_DBG", 0)) {          // phase timers: needs the B2_BUILD_VARIANT=timing library
     static long long* dbg_buf = nullptr;
     if (!dbg_buf) cudaMalloc(&dbg_buf, 64 * sizeof(long long));
     cudaMemsetAsync(dbg_buf, 0, 64 * sizeof(long long), stream);
     ba.dbg = dbg_buf;
-    rc = rec_tc_backward(ba, dy, nchain, stream);
+    rc = rec_tc_backward(ba, dy, nchain, env_int("B2_REC_GW", 0), stream);
     long long hb[12];
     cudaMemcpyAsync(hb, dbg_buf, sizeof(hb), cudaMemcpyDeviceToHost, stream);
     cudaStreamSynchronize(stream);
-    fprintf(stderr, "[rec bwd dbg2] loads=%lld math=%lld stores=%lld\n", hb[8] / T, hb[9] / T, hb[10] / T);
-    fprintf(stderr, "[rec bwd dbg] cycles/step: wait_partials+sum=%lld wait_ring=%lld math+stores=%lld "
-            "bar1=%lld wait_mma=%lld ld+convert=%lld bar2+send=%lld\n",
-            hb[0] / T, hb[1] / T, hb[2] / T, hb[3] / T, hb[4] / T, hb[5] / T, hb[6] / T);
+    fprintf(stderr, "[rec bwd dbg] cycles/step: wait_ring=%lld coeffs=%lld wait_partials+sum=%lld dh_math=%lld stage=%lld "
+            "bar1+dG=%lld wait_mma=%lld ld+convert+stage=%lld send=%lld\n",
+            hb[1] / T, hb[8] / T, hb[0] / T, hb[9] / T, hb[10] / T, hb[3] / T, hb[4] / T, hb[5] / T, hb[6] / T);
   } else {
     prof_record(2, stream);
-    rc = rec_tc_backward(ba, dy, nchain, stream);
+    rc = rec_tc_backward(ba, dy, nchain, env_int("B2_REC_GW", 0), stream);
     prof_record(3, stream);
   }
   if (rc) return rc;
+  if (use_side) {
+    sc->expected += (unsigned)nclusters;
+    if (sc->def.valid) {
+      // the previous layer's weight gradients: start once every cluster of this recurrence is resident,
+      // on the SMs the clusters leave free
+      const int r = stream_wait_value_fn()(sc->s, (unsigned long long)(uintptr_t)sc->resident, sc->expected, 0u /* GEQ */);
+      if (r != 0) { set_error("cuStreamWaitValue32 failed (%d)", r); return B2_ERR_CUDA; }
+      int free_sms = num_sms() - nclusters * (H / RU);
+      if (free_sms < 16) free_sms = 16;
+      rc = run_wgrad(sc->def, sc->s, free_sms);
+      if (rc) return rc;
+      B2_CUDA(cudaEventRecord(sc->ev_done, sc->s));
+      sc->pending = true;
+      sc->def.valid = false;
+    }
+    B2_CUDA(cudaEventRecord(sc->ev_rec, stream));          // dG of this layer complete (for a join-time flush)
+  }
   // 2. critical path: dX[TB, D] = dG[TB, 8H] . Wx_packed^T  (sums both directions)
   const __nv_bfloat16* xa = x_lp;
   int ldx = D;
@@ -376,45 +459,19 @@ int tc_layer_backward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16
     if (rc) return rc;
   }
   // 3. off the critical path: weight gradients on packed operands
-  cudaStream_t gs = stream;
-  if (use_side) {
-    B2_CUDA(cudaEventRecord(sc->ev_main, stream));
-    B2_CUDA(cudaStreamWaitEvent(sc->s, sc->ev_main, 0));
-    gs = sc->s;
-    // leave the SMs of the next layer's recurrence clusters alone
-    const int ng = cdiv(B, RN);
-    const int nch = nchain > 0 ? (nchain > 2 ? 2 : nchain) : (ng >= 2 ? 2 : 1);
-    const int rec_ctas = 2 * cdiv(ng, nch) * (H / RU);
-    int free_sms = num_sms() - rec_ctas;
-    if (free_sms < 16) free_sms = 16;
-    gemm_set_cta_limit(free_sms);
+  DeferredWgrad wg;
+  wg.valid = true; wg.T = T; wg.B = B; wg.D = D; wg.H = H; wg.ldx = ldx;
+  wg.xa = xa; wg.dG = dG; wg.hs_lp = r.hs_lp; wg.dwx = dwx; wg.dwh = dwh; wg.dbias = dbias;
+  wg.gk0 = g_fw->kernel; wg.gk1 = g_bw->kernel; wg.gb0 = g_fw->bias; wg.gb1 = g_bw->bias;
+  // (a bf16 copy of x made in the shared workspace does not survive until a deferred launch)
+  if (!use_side || xa == w.xb) {
+    rc = run_wgrad(wg, stream, 0);
+    if (rc) return rc;
+    return dx ? B2_OK : tc_backward_join(stream);
   }
-  // dWx_packed[D, 8H] = X^T . dG
-  B2_CUDA(cudaMemsetAsync(dwx, 0, (size_t)D * 8 * H * 4, gs));
-  rc = gemm_bf16_tc(1, 1, D, 8 * H, TB, 1.f, xa, ldx, dG, 8 * H, dwx, 8 * H, nullptr,
-                    EPI_ATOMIC_F32, 0, gs);
-  // dWh_packed[dir][H, 4H] = Hprev_dir^T . dG_dir   (hs shifted by one step)
-  if (!rc) rc = (cudaMemsetAsync(dwh, 0, (size_t)2 * H * 4 * H * 4, gs) == cudaSuccess) ? B2_OK : B2_ERR_CUDA;
-  if (!rc && T > 1) {
-    for (int dir = 0; dir < 2 && !rc; ++dir) {
-      const __nv_bfloat16* ha = r.hs_lp + (size_t)dir * H + (dir == 0 ? 0 : (size_t)B * 2 * H);
-      const __nv_bfloat16* gb = dG + (size_t)dir * 4 * H + (dir == 0 ? (size_t)B * 8 * H : 0);
-      rc = gemm_bf16_tc(1, 1, H, 4 * H, (T - 1) * B, 1.f, ha, 2 * H, gb, 8 * H,
-                        dwh + (size_t)dir * H * 4 * H, 4 * H, nullptr, EPI_ATOMIC_F32, 0, gs);
-    }
-  }
-  gemm_set_cta_limit(0);
-  if (rc) return rc;
-  unpack_lstm_grads_kernel<<<num_sms() * 4, 256, 0, gs>>>(dwx, dwh, dbias, D, H, g_fw->kernel,
-                                                        g_bw->kernel, g_fw->bias, g_bw->bias);
-  B2_LAUNCH_CHECK();
-  if (use_side) {
-    B2_CUDA(cudaEventRecord(sc->ev_done[k], sc->s));
-    sc->pending[k] = true;
-    sc->toggle ^= 1;
-    // the first layer is the last one of a backward pass: hand the gradients back
-    if (!dx) return tc_backward_join(stream);
-  }
+  sc->def = wg;
+  // the first layer is the last one of a backward pass: hand the gradients back
+  if (!dx) return tc_backward_join(stream);
   return B2_OK;
 }
 

@@ -140,16 +140,22 @@ class CTC(ModelBase):
         self.encoder_outputs = enc
         prec = ops.PREC_BF16 if self.precision == "bf16" else ops.PREC_FP32
         feat = enc.view(T * B, -1)
+        # the last BLSTM layer already wrote a bf16 copy of its output: the output-layer GEMMs read that
+        # instead of re-casting 64000 x 1024 floats (twice per step)
+        feat_lp = getattr(self.encoder, "output_lp", None) if prec == ops.PREC_BF16 else None
+        self._enc_lp = feat_lp
         self._bneck = None
         if self.bottleneck_dim not in (None, 0):
             # fully connected + ReLU, then dropout on the hidden-output connection (ctc.py:200-213)
             feat = ops.gemm(feat, self.variables["bottleneck/weights"], False, False,
-                            self.variables["bottleneck/biases"], prec)
+                            self.variables["bottleneck/biases"], prec, a_lp=feat_lp)
             ops.relu_dropout_(feat, float(keep_prob), self._step * 7919 + 5)
             self._bneck = (feat, float(keep_prob))
+            feat_lp = None
         self._head_in = feat
+        self._head_lp = feat_lp
         logits2d = ops.gemm(feat, self.variables["output/weights"], False, False,
-                            self.variables["output/biases"], prec)
+                            self.variables["output/biases"], prec, a_lp=feat_lp)
         return logits2d.view(T, B, self.num_classes)
 
     def compute_loss(self, inputs, labels, inputs_seq_len, keep_prob, scope=None,
@@ -174,7 +180,13 @@ class CTC(ModelBase):
 
     def _eval_logits(self, inputs, inputs_seq_len, keep_prob, is_training=True):
         inputs, inputs_seq_len = self._to_device(inputs, inputs_seq_len)
-        return self._build(inputs, inputs_seq_len, keep_prob, is_training)
+        logits = self._build(inputs, inputs_seq_len, keep_prob, is_training)
+        # everything the backward pass of THIS forward needs travels with the logits, so that several towers
+        # (examples/librispeech/training/train_ctc.py:82-147) can be in flight on one model object
+        logits._b2_state = {"head_in": self._head_in, "bneck": self._bneck, "enc": self.encoder_outputs,
+                            "saved": getattr(self.encoder, "_saved", None),
+                            "head_lp": self._head_lp, "enc_lp": self._enc_lp}
+        return logits
 
     def _eval_loss(self, logits, labels, inputs_seq_len, softmax_temperature=1, is_training=True):
         _, inputs_seq_len = self._to_device(logits, inputs_seq_len)
@@ -196,30 +208,45 @@ class CTC(ModelBase):
             # weight_decay * sum_{non-bias} l2_loss(w), l2_loss = sum(w^2)/2   (ctc.py:280-286)
             sq = ops.clip_by_norm_multi(self._decay_params, 3.0e38)      # norms^2, no scaling
             total_loss = total_loss + 0.5 * float(self.weight_decay) * sq.sum()
-        self._ctx = (dlogits, (B, T, None)) if is_training else None
+        self._ctx = (dlogits, (B, T, None), getattr(logits, "_b2_state", None)) if is_training else None
+        total_loss._b2_ctx = self._ctx
         return total_loss
 
-    def _backward(self):
-        """Gradients of the last compute_loss into self.flat_grads."""
-        assert self._ctx is not None, "train() needs a preceding compute_loss(is_training=True)"
-        dlogits, (B, T, _) = self._ctx
-        self.flat_grads.zero_()
+    def _backward(self, ctx=None, flat=None, grads=None):
+        """Gradients of a compute_loss into ``flat`` / ``grads`` (default: the model's own flat_grads views).
+        ``ctx``: the context of the loss to differentiate (default: the last compute_loss)."""
+        ctx = ctx if ctx is not None else self._ctx
+        assert ctx is not None, "train() needs a preceding compute_loss(is_training=True)"
+        dlogits, (B, T, _), state = ctx
+        flat = self.flat_grads if flat is None else flat
+        grads = self.grads if grads is None else grads
+        head_in, bneck, enc_out = self._head_in, self._bneck, self.encoder_outputs
+        head_lp, enc_lp = getattr(self, "_head_lp", None), getattr(self, "_enc_lp", None)
+        saved = None
+        if state is not None:
+            head_in, bneck, enc_out, saved = state["head_in"], state["bneck"], state["enc"], state["saved"]
+            head_lp, enc_lp = state["head_lp"], state["enc_lp"]
+        flat.zero_()
         prec = ops.PREC_BF16 if self.precision == "bf16" else ops.PREC_FP32
-        enc2d = self.encoder_outputs.view(T * B, -1)
+        enc2d = enc_out.view(T * B, -1)
         dl2d = dlogits.view(T * B, self.num_classes)
-        ops.gemm(self._head_in, dl2d, True, False, None, prec, out=self.grads["output/weights"], beta=1.0)
-        ops.colsum(dl2d, out=self.grads["output/biases"], accumulate=True)
+        ops.gemm(head_in, dl2d, True, False, None, prec, out=grads["output/weights"], beta=1.0, a_lp=head_lp)
+        ops.colsum(dl2d, out=grads["output/biases"], accumulate=True)
         denc = ops.gemm(dl2d, self.variables["output/weights"], False, True, None, prec)
-        if self._bneck is not None:
-            feat, kp = self._bneck
+        if bneck is not None:
+            feat, kp = bneck
             dz = ops.relu_dropout_backward(denc, feat, kp)
-            ops.gemm(enc2d, dz, True, False, None, prec, out=self.grads["bottleneck/weights"], beta=1.0)
-            ops.colsum(dz, out=self.grads["bottleneck/biases"], accumulate=True)
+            ops.gemm(enc2d, dz, True, False, None, prec, out=grads["bottleneck/weights"], beta=1.0, a_lp=enc_lp)
+            ops.colsum(dz, out=grads["bottleneck/biases"], accumulate=True)
             denc = ops.gemm(dz, self.variables["bottleneck/weights"], False, True, None, prec)
-        self.encoder.backward(denc.view(T, B, -1), self.variables, self.grads)
+        self.encoder.backward(denc.view(T, B, -1), self.variables, grads, saved=saved,
+                              on_layer_done=self._on_layer_done)
         if self.weight_decay > 0:
-            ops.axpy_multi(self._decay_params, self._decay_grads, float(self.weight_decay))
-        self._ctx = None
+            decay_grads = self._decay_grads if grads is self.grads else \
+                ops.TensorList([grads[v.name] for v in self._variables if "bias" not in v.name.lower()])
+            ops.axpy_multi(self._decay_params, decay_grads, float(self.weight_decay))
+        if ctx is self._ctx:
+            self._ctx = None
 
     # ---------------------------------------------------------------- decode
     @graph_op(name="decoder")

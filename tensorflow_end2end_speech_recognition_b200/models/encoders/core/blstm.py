@@ -108,6 +108,9 @@ class BLSTMEncoder(object):
             x = y
             x_lp = ops.reserve_y_lp(desc, reserve)   # bf16 shadow feeds the next layer's GEMM
         self._saved = (saved, inputs_seq_len)
+        # (device pointer, row stride) of the bf16 copy of the time-major output the last layer wrote, or None
+        self.output_lp = (x_lp, x.shape[2]) if (x_lp and self.time_major) else None
+        self._keepalive = reserve          # the shadow lives in the last layer's reserve
         outputs = x if self.time_major else ops.transpose_01(x)
         final_state = None
         if fs is not None:
@@ -116,11 +119,12 @@ class BLSTMEncoder(object):
 
     # ------------------------------------------------------------- backward
     def backward(self, d_outputs, variables, grads, need_dx=False, on_layer_done=None,
-                 d_final_state=None):
+                 d_final_state=None, saved=None):
         """d_outputs [T,B,2H] (time-major).  Accumulates into ``grads`` (same keys as
         ``variables``); calls ``on_layer_done(i_layer)`` when a layer's gradients are final.
         d_final_state [4,B,H]: gradient of the returned (fw(c,h), bw(c,h)) of the last layer."""
-        saved, seq_len = self._saved
+        own = saved is None
+        saved, seq_len = self._saved if own else saved
         dy = d_outputs
         for desc, x, reserve, i_layer, x_lp in reversed(saved):
             pf = self._layer_params(variables, i_layer, "fw")
@@ -133,5 +137,6 @@ class BLSTMEncoder(object):
             if on_layer_done is not None:
                 on_layer_done(i_layer)
         ops.blstm_backward_join()      # side-stream weight-gradient GEMMs -> gradients final
-        self._saved = None
+        if own:
+            self._saved = None
         return dy

@@ -79,21 +79,28 @@ class VGGBLSTMEncoder(object):
                             dropout_seed=(dropout_seed * 977 + 13) * 8)
         # [B,T,D] -> [B*T, num_channels, W, 3] is a pure reshape (:108-110)
         feat, reserve = ops.vgg_frontend_forward(desc, inputs.contiguous(), self._vgg_params(variables))
-        self._saved = (desc, reserve) if is_training else None
         outputs, final_state = self.blstm(feat.view(B, T, 256), inputs_seq_len, keep_prob, is_training,
                                           variables=variables, dropout_seed=dropout_seed)
+        self.output_lp = getattr(self.blstm, "output_lp", None) if self.time_major else None
+        # (front-end state, BLSTM state): one bundle, so a tower's backward can be handed its own
+        self._saved = (desc, reserve, self.blstm._saved) if is_training else None
         if not self.time_major:
             outputs = ops.transpose_01(outputs)
         return outputs, final_state
 
     # ------------------------------------------------------------- backward
-    def backward(self, d_outputs, variables, grads, need_dx=False, on_layer_done=None, d_final_state=None):
+    def backward(self, d_outputs, variables, grads, need_dx=False, on_layer_done=None, d_final_state=None,
+                 saved=None):
         """d_outputs time-major [T,B,2H]."""
-        desc, reserve = self._saved
+        own = saved is None
+        desc, reserve, blstm_saved = self._saved if own else saved
         d_feat_tm = self.blstm.backward(d_outputs, variables, grads, need_dx=True, on_layer_done=on_layer_done,
-                                        d_final_state=d_final_state)             # [T,B,256]
+                                        d_final_state=d_final_state, saved=blstm_saved)   # [T,B,256]
+        if own:
+            self.blstm._saved = None
         d_feat = ops.transpose_01(d_feat_tm)                                     # [B,T,256]
         ops.vgg_frontend_backward(desc, self._vgg_params(variables), d_feat.view(-1, 256), reserve,
                                   self._vgg_params(grads))
-        self._saved = None
+        if own:
+            self._saved = None
         return None

@@ -11,6 +11,7 @@ import numpy as np
 import torch
 
 from .. import ops
+from ..compat import graph as _graph
 from ..compat.graph import graph_op
 
 OPTIMIZER_CLS_NAMES = {          # name -> (kernel kind, number of state slots, slot-0 init)
@@ -34,8 +35,16 @@ class Variable(object):
         return tuple(self.tensor.shape)
 
 
+class GradsAndVars(list):
+    """``[(grad, var)]`` as tf.train.Optimizer.compute_gradients returns it, plus the flat buffer the
+    gradients are views of (one tower = one flat fp32 buffer with the parameter layout)."""
+    flat = None
+    tensor_list = None
+
+
 class Optimizer(object):
-    """Eager stand-in for tf.train.*Optimizer: compute_gradients / apply_gradients."""
+    """Stand-in for tf.train.*Optimizer: ``compute_gradients`` / ``apply_gradients`` (the in-graph tower flow of
+    examples/librispeech/training/train_ctc.py:82-147) -- eager on tensors, lazy on graph handles."""
 
     def __init__(self, name, learning_rate, model):
         self.name, self.learning_rate, self.model = name, learning_rate, model
@@ -49,6 +58,7 @@ class Optimizer(object):
         self._s0 = ops.TensorList([self.state0]) if self.state0 is not None else None
         self._s1 = ops.TensorList([self.state1]) if self.state1 is not None else None
         self.global_step = 0
+        self._towers_out = 0         # compute_gradients calls since the last apply_gradients
 
     def load_state(self, state):
         """slots + step counter from a checkpoint (compat.tf.train.Saver.restore)"""
@@ -59,17 +69,54 @@ class Optimizer(object):
         self.global_step = int(state.get("global_step", self.global_step))
 
     def compute_gradients(self, loss):
-        """Runs the backward pass of the last compute_loss -> [(grad, var)]."""
-        self.model._backward()
-        return [(v.grad, v) for v in self.model.trainable_variables()]
+        """Backward pass of the ``compute_loss`` that produced ``loss`` -> [(grad, var)].
+        Tower k of a step (k-th call since the last ``apply_gradients``) writes its own flat buffer;
+        tower 0 is the model's ``flat_grads`` itself."""
+        if _graph.is_handle(loss):
+            return _graph.LazyGradsAndVars(_graph.Op(self._compute_gradients, (loss,), {}, name="gradients"))
+        return self._compute_gradients(loss)
+
+    def _compute_gradients(self, loss):
+        k = self._towers_out
+        self._towers_out += 1
+        flat, grads, tl = self.model._tower_buffers(k)
+        ctx = getattr(loss, "_b2_ctx", None)
+        if ctx is None and k > 0:
+            raise RuntimeError("compute_gradients: a second tower needs the loss tensor of its own compute_loss "
+                               "(this model type keeps one forward context)")
+        if ctx is not None or k > 0:
+            self.model._backward(ctx=ctx, flat=flat, grads=grads)
+        else:
+            self.model._backward()
+        gv = GradsAndVars((grads[v.name], v) for v in self.model.trainable_variables())
+        gv.flat, gv.tensor_list = flat, tl
+        return gv
 
     def apply_gradients(self, grads_and_vars, global_step=None, learning_rate=None):
-        lr = self.learning_rate if learning_rate is None else learning_rate
+        if _graph.is_handle(grads_and_vars) or _graph.is_handle(self.learning_rate if learning_rate is None
+                                                                else learning_rate):
+            lr = self.learning_rate if learning_rate is None else learning_rate
+            src = grads_and_vars.op if isinstance(grads_and_vars, _graph.LazyGradsAndVars) else grads_and_vars
+            return _graph.Op(lambda gv, lr_: self._apply_gradients(gv, lr_), (src, lr), {}, name="apply_gradients")
+        return self._apply_gradients(grads_and_vars, self.learning_rate if learning_rate is None else learning_rate)
+
+    def _apply_gradients(self, grads_and_vars, lr):
         self.global_step += 1
+        self._towers_out = 0
+        flat = getattr(grads_and_vars, "flat", None)
+        g = self._g
+        if flat is not None and flat.data_ptr() != self.model.flat_grads.data_ptr():
+            g = ops.TensorList([flat])
+        elif flat is None and grads_and_vars is not None:
+            # a plain [(grad, var)] list (e.g. the per-variable form of average_gradients)
+            for gr, v in grads_and_vars:
+                if gr is not None and gr.data_ptr() != v.grad.data_ptr():
+                    v.grad.copy_(gr)
         # parameters, gradients and optimizer state are flat buffers with one layout,
         # so the whole update is a single elementwise launch
-        ops.optimizer_step_multi(self.kind, self._p, self._g, self._s0, self._s1, float(lr),
-                                 self.global_step)
+        ops.optimizer_step_multi(self.kind, self._p, g, self._s0, self._s1, float(lr), self.global_step)
+        self.model._params_version += 1
+        return self
 
 
 class ModelBase(object):
@@ -80,6 +127,10 @@ class ModelBase(object):
         self.flat_grads = None
         self.world_size = 1
         self._pending = []
+        self._towers = {}
+        self._params_version = 0        # bumped by every optimizer step (packed-weight caches key on it)
+        self._on_layer_done = None
+        self._comm = None
 
     # ------------------------------------------------------------ variables
     def _allocate_variables(self, named_arrays, device):
@@ -106,6 +157,20 @@ class ModelBase(object):
     def trainable_variables(self):
         return list(self._variables)
 
+    def _tower_buffers(self, k):
+        """(flat gradient buffer, name -> view dict, TensorList) of tower k; tower 0 = flat_grads."""
+        if k == 0:
+            return self.flat_grads, self.grads, self._grad_list
+        if k not in self._towers:
+            flat = torch.zeros_like(self.flat_grads)
+            base = self.flat_grads.data_ptr()
+            views = {}
+            for v in self._variables:
+                o = (v.grad.data_ptr() - base) // 4
+                views[v.name] = flat[o:o + v.grad.numel()].view(v.grad.shape)
+            self._towers[k] = (flat, views, ops.TensorList([views[v.name] for v in self._variables]))
+        return self._towers[k]
+
     # ------------------------------------------------------------ optimizer
     def _set_optimizer(self, optimizer, learning_rate):
         """(reference: model_base.py:68-95)"""
@@ -117,8 +182,16 @@ class ModelBase(object):
 
     def _clip_gradients(self, grads_and_vars):
         """Per-tensor tf.clip_by_norm, in place (reference: model_base.py:135-166).  The
-        1/world_size of the tower mean is folded into the same launch."""
-        ops.clip_by_norm_multi(self._grad_list, self.clip_grad_norm, post_scale=1.0 / self.world_size)
+        1/world_size of the one-rank-per-GPU tower mean is folded into the same launch."""
+        if isinstance(grads_and_vars, _graph.LazyGradsAndVars):
+            return _graph.LazyGradsAndVars(_graph.Op(self._clip_gradients, (grads_and_vars.op,), {},
+                                                     name="clip_gradients"))
+        tl = getattr(grads_and_vars, "tensor_list", None) or self._grad_list
+        post = 1.0 / self.world_size if (self.world_size > 1 and self._comm is None) else 1.0
+        if self.clip_grad_norm is not None or post != 1.0:
+            ops.clip_by_norm_multi(tl, self.clip_grad_norm, post_scale=post)
+        if isinstance(grads_and_vars, GradsAndVars):
+            return grads_and_vars
         return [(g, v) for g, v in grads_and_vars if g is not None]
 
     @graph_op(name="train")
@@ -132,24 +205,30 @@ class ModelBase(object):
             if restored is not None and restored.get("name") == self.optimizer.name:
                 self.optimizer.load_state(restored)
             self._restored_optimizer_state = None
-        grads_and_vars = self.optimizer.compute_gradients(loss)
+        self.optimizer._towers_out = 0
+        grads_and_vars = self.optimizer._compute_gradients(loss)
         if self.clip_grad_norm is not None or self.world_size > 1:
             grads_and_vars = self._clip_gradients(grads_and_vars)
         self._allreduce_gradients()
-        self.optimizer.apply_gradients(grads_and_vars, learning_rate=learning_rate)
+        self.optimizer._apply_gradients(grads_and_vars, learning_rate)
         return self.optimizer
 
     # -------------------------------------------------------- data parallel
-    def set_data_parallel(self, world_size, group=None, broadcast=True):
+    def set_data_parallel(self, world_size, group=None, broadcast=True, comm=None):
         """One rank per GPU; replaces the in-graph towers of
-        examples/librispeech/training/train_ctc.py:82-147."""
+        examples/librispeech/training/train_ctc.py:82-147.  ``comm``: a
+        ``utils.training.multi_gpu.NcclComm`` -> the gradient mean goes through ``b2_allreduce_mean``
+        (NCCL bound from C); without it ``torch.distributed`` all-reduce (gloo on CPU boxes)."""
         import torch.distributed as dist
-        self.world_size, self._group = int(world_size), group
+        self.world_size, self._group, self._comm = int(world_size), group, comm
         if world_size > 1 and broadcast:
             dist.broadcast(self.flat_params, src=0, group=group)
 
     def _allreduce_gradients(self):
         if self.world_size <= 1:
+            return
+        if self._comm is not None:
+            self._comm.allreduce_mean_([self.flat_grads])
             return
         from ..utils.training.multi_gpu import allreduce_mean_
         allreduce_mean_(self.flat_grads, self.world_size, group=getattr(self, "_group", None))

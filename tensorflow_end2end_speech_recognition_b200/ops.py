@@ -129,8 +129,9 @@ def softmax_rows(x):
 
 
 def gemm(A, B, transa=False, transb=False, bias=None, precision=PREC_FP32, out=None, beta=0.0,
-         alpha=1.0):
-    """C = alpha*op(A).op(B) + beta*C + bias.  2-D f32 cuda tensors (row-major, may be strided rows)."""
+         alpha=1.0, a_lp=None):
+    """C = alpha*op(A).op(B) + beta*C + bias.  2-D f32 cuda tensors (row-major, may be strided rows).
+    a_lp = (device pointer, row stride) of a bf16 shadow of A the caller already holds (bf16 path only)."""
     lib = _lib.load()
     _require_cuda(A, B, bias, out)
     assert A.dtype == torch.float32 and B.dtype == torch.float32
@@ -144,9 +145,11 @@ def gemm(A, B, transa=False, transb=False, bias=None, precision=PREC_FP32, out=N
         assert beta == 0.0
     nbytes = lib.b2_gemm_workspace_bytes(M, N, K, precision)
     ws = workspace("gemm", nbytes, A.device) if nbytes else None
-    rc = lib.b2_gemm(int(transa), int(transb), M, N, K, float(alpha), _ptr(A), A.stride(0), _ptr(B),
-                     B.stride(0), float(beta), _ptr(out), out.stride(0), _ptr(bias), int(precision),
-                     _ptr(ws), nbytes, _stream())
+    lp_ptr, lp_ld = (a_lp if a_lp else (0, 0))
+    rc = lib.b2_gemm_lp(int(transa), int(transb), M, N, K, float(alpha), _ptr(A), A.stride(0),
+                        C.c_void_p(lp_ptr or 0), int(lp_ld), _ptr(B),
+                        B.stride(0), float(beta), _ptr(out), out.stride(0), _ptr(bias), int(precision),
+                        _ptr(ws), nbytes, _stream())
     _lib.check(rc, "b2_gemm")
     return out
 

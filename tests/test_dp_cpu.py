@@ -48,15 +48,6 @@ def test_allreduce_mean_matches_oracle_tower_average(tmp_path):
         np.testing.assert_allclose(f, ref, rtol=1e-6, atol=1e-7)
 
 
-def test_average_gradients_list_form():
-    from tensorflow_end2end_speech_recognition_b200.utils.training.multi_gpu import average_gradients
-    g0 = [(torch.ones(3), "v0"), (None, "v1")]
-    g1 = [(3 * torch.ones(3), "v0"), (torch.ones(2), "v1")]
-    out = average_gradients([g0, g1])
-    assert out[0][1] == "v0" and torch.allclose(out[0][0], 2 * torch.ones(3))
-    assert torch.allclose(out[1][0], torch.ones(2))      # towers with None grads are skipped
-
-
 def test_sparsetensor_round_trip():
     from tensorflow_end2end_speech_recognition_b200.utils.io.labels.sparsetensor import (
         list2sparsetensor, sparse_to_label_lists, sparsetensor2list)

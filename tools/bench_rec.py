@@ -42,6 +42,11 @@ def bench(T, B, D, H, prec, backward, iters=5, label="", keep_prob=1.0):
 
 if __name__ == "__main__":
     bwd = "--bwd" in sys.argv
+    if "--quick" in sys.argv:
+        tag = " ".join("%s=%s" % (k, os.environ[k]) for k in sorted(os.environ) if k.startswith("B2_REC"))
+        bench(1000, 64, 1024, 512, ops.PREC_BF16, True, label="fwd+bwd " + tag)
+        bench(1000, 64, 1024, 512, ops.PREC_BF16, False, label="fwd only " + tag)
+        sys.exit(0)
     for nch in (1, 2):
         os.environ["B2_REC_NCHAIN"] = str(nch)
         bench(1000, 64, 1024, 512, ops.PREC_BF16, bwd, label="bf16 tc nchain=%d %s" % (nch, "fwd+bwd" if bwd else "fwd"))
