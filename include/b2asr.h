@@ -97,6 +97,17 @@ int b2_ctc_beam_decode(const float* log_probs, const int32_t* seq_len, int T,
                        void* workspace, size_t workspace_bytes,
                        b2_stream_t stream);
 
+/* TF-semantics CTC beam search      replaces tf.nn.ctc_beam_search_decoder as called at
+ *   models/ctc/ctc.py:344-346 (beam_width, top_paths=1, merge_repeated=True).
+ * logits [T,B,C] fp32 TIME-major raw scores (the op's own input), blank = C-1.
+ * out_labels [B,T] padded -1, out_len [B], out_score [B] = log P_total of the best leaf
+ * (logits minus the per-frame maximum, as TF 1.x accumulates it).  merge_repeated != 0 drops
+ * a label that repeats its successor in the emitted path (TF's default). */
+size_t b2_ctc_beam_tf_workspace_bytes(int T, int B, int C, int beam_width);
+int b2_ctc_beam_decode_tf(const float* logits, const int32_t* seq_len, int T, int B, int C,
+                          int blank, int beam_width, int merge_repeated,
+                          int32_t* out_labels, int32_t* out_len, float* out_score,
+                          void* workspace, size_t workspace_bytes, b2_stream_t stream);
 /* softmax over the last axis of [rows, C]   (CTC.posteriors, ctc.py:354-380) */
 int b2_softmax_rows(const float* x, float* y, int64_t rows, int C,
                     b2_stream_t stream);

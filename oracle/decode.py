@@ -122,3 +122,114 @@ def edit_distance(hyp, ref):
 def label_error_rate(hyps, refs):
     """mean_b(edit_distance/len(ref))  (``compute_ler``, ctc.py:382-398)."""
     return float(np.mean([edit_distance(h, r) / len(r) for h, r in zip(hyps, refs)]))
+
+
+# --------------------------------------------------------------------------- TF-semantics beam search
+class _TfBeamEntry(object):
+    __slots__ = ("parent", "label", "children", "old", "new")
+
+    def __init__(self, parent, label):
+        self.parent, self.label, self.children = parent, label, None
+        self.old = [NEG_INF, NEG_INF, NEG_INF]      # total, blank, label   (log domain)
+        self.new = [NEG_INF, NEG_INF, NEG_INF]
+
+    def active(self):
+        return self.new[0] != NEG_INF
+
+
+def tf_ctc_beam_search_single(logits_tc, blank, beam_width, merge_repeated=True, top_paths=1,
+                              normalize=False):
+    """``tf.nn.ctc_beam_search_decoder`` for one utterance, as the reference calls it at ``models/ctc/ctc.py:344-346``
+    (``beam_width`` from the config, ``top_paths=1``, ``merge_repeated=True`` by default).
+
+    TensorFlow is not vendored in the reference and cannot be installed here: this restates the algorithm of
+    TF 1.x ``tensorflow/core/util/ctc/ctc_beam_search.h`` (``CTCBeamSearchDecoder::Step`` / ``TopPaths``,
+    ``ctc_beam_entry.h::LabelSeq``) from its published source -- PARITY UNPINNED against TensorFlow itself:
+      * per frame the input is the logit row minus its maximum (TF <= 1.8; ``normalize=True`` gives the
+        log-softmax of later versions -- a per-frame constant, rankings are identical);
+      * the beam is a prefix tree; every leaf keeps (P_total, P_blank, P_label) at t-1 and t;
+      * existing leaves are updated first (label part from the parent only while the parent is still in the beam),
+        then every leaf whose OLD total still beats the current bottom of the beam proposes its children, in
+        descending old-probability order, labels ascending; a child enters iff its total beats the bottom;
+      * ``blank`` must be the last class (children are labels 0..C-2);
+      * the returned path walks leaf -> root and, with ``merge_repeated``, drops a label equal to the one emitted
+        right after it (so "a a b" comes out as "a b" -- TF's documented quirk).
+    Ties between equal totals are broken by the position in the candidate list (TF leaves them to its heap).
+    Returns ([label lists, best first], [log scores])."""
+    T, C = logits_tc.shape
+    assert blank == C - 1, "TF's decoder assumes the blank is the last class"
+    root = _TfBeamEntry(None, -1)
+    root.new = [0.0, 0.0, NEG_INF]
+    leaves = [root]
+    for t in range(T):
+        row = np.asarray(logits_tc[t], np.float64)
+        x = row - row.max()
+        if normalize:
+            x = x - math.log(np.exp(x).sum())
+        branches = sorted(leaves, key=lambda e: -e.new[0])          # Extract(): descending new probability
+        leaves = []
+        for b in branches:
+            b.old = list(b.new)
+        for b in branches:
+            if b.parent is not None:
+                if b.parent.active():
+                    prev = b.parent.old[1] if b.label == b.parent.label else b.parent.old[0]
+                    b.new[2] = _lse2(b.new[2], prev)
+                b.new[2] += x[b.label]
+            b.new[1] = b.old[0] + x[blank]
+            b.new[0] = _lse2(b.new[1], b.new[2])
+            leaves.append(b)
+
+        def bottom():
+            return min(leaves, key=lambda e: e.new[0])
+
+        def is_candidate(total):
+            return total > NEG_INF and (len(leaves) < beam_width or total > bottom().new[0])
+
+        def push(e):
+            if len(leaves) < beam_width:
+                leaves.append(e)
+            else:
+                bt = bottom()
+                if e.new[0] > bt.new[0]:
+                    bt.new = [NEG_INF, NEG_INF, NEG_INF]
+                    leaves.remove(bt)
+                    leaves.append(e)
+        # (existing leaves beyond the width cannot happen: |branches| <= beam_width)
+        for b in branches:
+            if not is_candidate(b.old[0]):
+                continue
+            if b.children is None:
+                b.children = [_TfBeamEntry(b, c) for c in range(C - 1)]
+            for c in b.children:
+                if c.active():
+                    continue
+                prev = b.old[1] if c.label == b.label else b.old[0]
+                c.new = [x[c.label] + prev, NEG_INF, x[c.label] + prev]
+                if is_candidate(c.new[0]):
+                    push(c)
+                else:
+                    c.old = [NEG_INF, NEG_INF, NEG_INF]
+                    c.new = [NEG_INF, NEG_INF, NEG_INF]
+    best = sorted(leaves, key=lambda e: -e.new[0])[:top_paths]
+    paths, scores = [], []
+    for e in best:
+        labels, prev_label, c = [], -1, e
+        while c.parent is not None:
+            if not merge_repeated or c.label != prev_label:
+                labels.append(c.label)
+            prev_label = c.label
+            c = c.parent
+        paths.append(labels[::-1])
+        scores.append(e.new[0])
+    return paths, scores
+
+
+def tf_ctc_beam_search(logits_tbc, seq_len, blank, beam_width, merge_repeated=True):
+    """batched form over time-major logits [T,B,C] -> list of best label lists"""
+    out = []
+    for b in range(logits_tbc.shape[1]):
+        paths, _ = tf_ctc_beam_search_single(np.asarray(logits_tbc[:int(seq_len[b]), b]), blank, beam_width,
+                                             merge_repeated)
+        out.append(paths[0])
+    return out

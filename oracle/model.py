@@ -89,3 +89,33 @@ class OracleTrainer(object):
             grads = [oopt.clip_by_norm(g, self.clip) if g is not None else None for g in grads]
         self.opt.step(self.params, grads)
         return loss, logits, grads
+
+
+def multitask_ctc_forward(variables, inputs_btd, seq_len, labels_main, labels_sub, num_layers_main,
+                          num_layers_sub, main_task_weight, use_peephole=True):
+    """Hierarchical CTC (models/ctc/multitask_ctc.py:109-191,225-296): main head on the top BLSTM layer, sub head on
+    layer ``num_layers_sub`` (blstm.py:325-331); total = w * mean(ctc_main) + (1 - w) * mean(ctc_sub).
+    variables: dict name -> torch tensor.  Returns (total, logits_main [T,B,Cm], logits_sub [T,B,Cs])."""
+    layers = layers_from_variables(variables, num_layers_main, use_peephole)
+    x = inputs_btd
+    enc_sub = None
+    for i, layer in enumerate(layers, 1):
+        y, _ = olstm.blstm_forward(x, seq_len, [layer])
+        if i == num_layers_sub:
+            enc_sub = y
+        x = y.transpose(0, 1)
+    enc = y
+    T, B, E = enc.shape
+    lens_t = torch.as_tensor(np.asarray(seq_len), dtype=torch.long)
+
+    def head(feat, w, b, labels):
+        logits = (feat.reshape(T * B, E) @ variables[w] + variables[b]).reshape(T, B, -1)
+        C = logits.shape[-1]
+        lens = torch.tensor([len(l) for l in labels], dtype=torch.long)
+        flat = torch.tensor([v for l in labels for v in l], dtype=torch.long)
+        losses = torch.nn.functional.ctc_loss(torch.log_softmax(logits, -1), flat, lens_t, lens, blank=C - 1,
+                                              reduction="none", zero_infinity=False)
+        return losses.mean(), logits
+    l_main, logits_main = head(enc, "output_main/weights", "output_main/biases", labels_main)
+    l_sub, logits_sub = head(enc_sub, "output_sub/weights", "output_sub/biases", labels_sub)
+    return main_task_weight * l_main + (1.0 - main_task_weight) * l_sub, logits_main, logits_sub

@@ -75,6 +75,8 @@ PROTOTYPES = {
     "b2_ctc_greedy_decode": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "b2_ctc_beam_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "b2_ctc_beam_decode": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
+    "b2_ctc_beam_tf_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "b2_ctc_beam_decode_tf": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
     "b2_softmax_rows": (_i, [_p, _p, _i64, _i, _p]),
     "b2_gemm_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "b2_gemm": (_i, [_i, _i, _i, _i, _i, _f, _p, _i, _p, _i, _f, _p, _i, _p, _i, _p, _sz, _p]),

@@ -13,6 +13,8 @@ _ALIASES = {
     "models.model_base": "models.model_base",
     "models.ctc": "models.ctc",
     "models.ctc.ctc": "models.ctc.ctc",
+    "models.ctc.multitask_ctc": "models.ctc.multitask_ctc",
+    "models.encoders.core.multitask_blstm": "models.encoders.core.multitask_blstm",
     "models.encoders": "models.encoders",
     "models.encoders.load_encoder": "models.encoders.load_encoder",
     "models.encoders.core": "models.encoders.core",
@@ -29,6 +31,8 @@ _ALIASES = {
     "utils.io": "utils.io",
     "utils.io.labels": "utils.io.labels",
     "utils.io.labels.sparsetensor": "utils.io.labels.sparsetensor",
+    "utils.evaluation": "utils.evaluation",
+    "utils.evaluation.edit_distance": "utils.evaluation.edit_distance",
     "utils.training": "utils.training",
     "utils.training.multi_gpu": "utils.training.multi_gpu",
 }

@@ -250,17 +250,25 @@ class CTC(ModelBase):
 
     # ---------------------------------------------------------------- decode
     @graph_op(name="decoder")
-    def decoder(self, logits, inputs_seq_len, beam_width=1):
-        """-> SparseTensorValue(indices int64 [N,2], values int32 [N], dense_shape)  (ctc.py:325-352)"""
+    def decoder(self, logits, inputs_seq_len, beam_width=1, merge_repeated=True, impl="tf"):
+        """-> SparseTensorValue(indices int64 [N,2], values int32 [N], dense_shape)  (ctc.py:325-352)
+
+        beam_width == 1: ``tf.nn.ctc_greedy_decoder``; > 1: ``tf.nn.ctc_beam_search_decoder(beam_width,
+        top_paths=1, merge_repeated=True)`` semantics (``b2_ctc_beam_decode_tf``) -- the op the reference model
+        calls.  ``impl="numpy"`` selects the reference's OTHER decoder, the numpy prefix beam search of
+        ``models/ctc/decoders/beam_search_decoder.py`` (no output merge, ``b2_ctc_beam_decode``)."""
         assert isinstance(beam_width, int), "beam_width must be integer."
         assert beam_width >= 1, "beam_width must be >= 1"
         _, inputs_seq_len = self._to_device(logits, inputs_seq_len)
         T, B, C = logits.shape
         if beam_width == 1:
             lab, n = ops.ctc_greedy_decode(logits, inputs_seq_len, blank=C - 1)
-        else:
+        elif impl == "numpy":
             lp = torch.log(ops.softmax_rows(ops.transpose_01(logits)))
             lab, n, _ = ops.ctc_beam_decode(lp, inputs_seq_len, beam_width, blank=C - 1)
+        else:
+            lab, n, _ = ops.ctc_beam_decode_tf(logits, inputs_seq_len, beam_width, blank=C - 1,
+                                               merge_repeated=merge_repeated)
         lab, n = lab.cpu().numpy(), n.cpu().numpy()
         idx, val = [], []
         for b in range(B):

@@ -45,6 +45,7 @@ class BLSTMEncoder(object):
         else:
             self._peephole, self._clip = bool(use_peephole), clip_activation
         self._saved = None
+        self.num_layers_sub = None       # MultitaskBLSTMEncoder: the layer whose output feeds the sub task
 
     # ------------------------------------------------------------ variables
     def create_variables(self, input_size, rng):
@@ -94,6 +95,7 @@ class BLSTMEncoder(object):
         saved = []
         fs = None
         x_lp = 0
+        self.sub_outputs = self.sub_final_state = self.sub_output_lp = None
         for i_layer in range(1, self.num_layers + 1):
             desc = ops.lstm_desc(T, B, x.shape[2], self.num_units, use_peephole=self._peephole,
                                  forget_bias=1.0, cell_clip=self._clip, keep_prob=float(keep_prob),
@@ -101,12 +103,17 @@ class BLSTMEncoder(object):
                                  need_backward=is_training, num_proj=self.num_proj)
             pf = self._layer_params(variables, i_layer, "fw")
             pb = self._layer_params(variables, i_layer, "bw")
+            is_sub = self.num_layers_sub is not None and i_layer == self.num_layers_sub
             y, fs, reserve = ops.blstm_layer_forward(desc, x, inputs_seq_len, pf, pb,
-                                                     want_final_state=(i_layer == self.num_layers),
+                                                     want_final_state=(i_layer == self.num_layers or is_sub),
                                                      x_lp=x_lp)
             saved.append((desc, x, reserve, i_layer, x_lp))
             x = y
             x_lp = ops.reserve_y_lp(desc, reserve)   # bf16 shadow feeds the next layer's GEMM
+            if is_sub:                               # blstm.py:325-327: outputs_sub / final_state_sub of that layer
+                self.sub_outputs = y
+                self.sub_final_state = ((fs[0], fs[1]), (fs[2], fs[3])) if fs is not None else None
+                self.sub_output_lp = (x_lp, y.shape[2]) if x_lp else None
         self._saved = (saved, inputs_seq_len)
         # (device pointer, row stride) of the bf16 copy of the time-major output the last layer wrote, or None
         self.output_lp = (x_lp, x.shape[2]) if (x_lp and self.time_major) else None
@@ -119,14 +126,17 @@ class BLSTMEncoder(object):
 
     # ------------------------------------------------------------- backward
     def backward(self, d_outputs, variables, grads, need_dx=False, on_layer_done=None,
-                 d_final_state=None, saved=None):
+                 d_final_state=None, saved=None, d_inject=None):
         """d_outputs [T,B,2H] (time-major).  Accumulates into ``grads`` (same keys as
         ``variables``); calls ``on_layer_done(i_layer)`` when a layer's gradients are final.
-        d_final_state [4,B,H]: gradient of the returned (fw(c,h), bw(c,h)) of the last layer."""
+        d_final_state [4,B,H]: gradient of the returned (fw(c,h), bw(c,h)) of the last layer.
+        d_inject {layer: [T,B,2H]}: extra gradient of that layer's OUTPUT (heads tapped below the top)."""
         own = saved is None
         saved, seq_len = self._saved if own else saved
         dy = d_outputs
         for desc, x, reserve, i_layer, x_lp in reversed(saved):
+            if d_inject and i_layer in d_inject:      # gradient of a head tapped at this layer's output (sub task)
+                dy = ops.add_(dy.contiguous(), d_inject[i_layer])
             pf = self._layer_params(variables, i_layer, "fw")
             pb = self._layer_params(variables, i_layer, "bw")
             gf = self._layer_params(grads, i_layer, "fw")

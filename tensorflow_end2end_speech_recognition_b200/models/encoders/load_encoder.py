@@ -1,8 +1,11 @@
 """Encoder registry, same entry point as ``models/encoders/load_encoder.py:26-57``."""
 from .core.blstm import BLSTMEncoder
+from .core.multitask_blstm import MultitaskBLSTMEncoder
 from .core.vgg_blstm import VGGBLSTMEncoder
 
-ENCODERS = {"blstm": BLSTMEncoder, "vgg_blstm": VGGBLSTMEncoder}
+# the encoders on the B200 hot path; the reference's other entries (uni-directional lstm, gru/bgru, vgg_lstm,
+# cnn_zhang, vgg_wang, pyramid_blstm, cldnn_wang, student_*; load_encoder.py:26-44) are not built
+ENCODERS = {"blstm": BLSTMEncoder, "vgg_blstm": VGGBLSTMEncoder, "multitask_blstm": MultitaskBLSTMEncoder}
 
 
 def load(encoder_type):

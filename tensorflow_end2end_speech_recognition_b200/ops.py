@@ -117,6 +117,26 @@ def ctc_beam_decode(log_probs, seq_len, beam_width, blank=None):
     return out, n, score
 
 
+def ctc_beam_decode_tf(logits, seq_len, beam_width, blank=None, merge_repeated=True):
+    """tf.nn.ctc_beam_search_decoder semantics.  logits [T,B,C] raw scores -> (labels [B,T] -1 padded, lengths [B],
+    score [B])."""
+    lib = _lib.load()
+    _require_cuda(logits, seq_len)
+    T, B, Cc = logits.shape
+    if blank is None:
+        blank = Cc - 1
+    out = torch.empty((B, T), dtype=torch.int32, device=logits.device)
+    n = torch.empty(B, dtype=torch.int32, device=logits.device)
+    score = torch.empty(B, dtype=torch.float32, device=logits.device)
+    nbytes = lib.b2_ctc_beam_tf_workspace_bytes(T, B, Cc, int(beam_width))
+    ws = workspace("beam_tf", nbytes, logits.device)
+    rc = lib.b2_ctc_beam_decode_tf(_ptr(logits.contiguous()), _ptr(seq_len), T, B, Cc, int(blank), int(beam_width),
+                                   int(bool(merge_repeated)), _ptr(out), _ptr(n), _ptr(score), _ptr(ws), nbytes,
+                                   _stream())
+    _lib.check(rc, "b2_ctc_beam_decode_tf")
+    return out, n, score
+
+
 def softmax_rows(x):
     lib = _lib.load()
     _require_cuda(x)
@@ -454,6 +474,14 @@ def axpy_multi(xs, ys, alpha):
     lib = _lib.load()
     _lib.check(lib.b2_axpy_multi(_ptr(xs.ptrs), _ptr(ys.ptrs), _ptr(xs.sizes), xs.n, float(alpha), _stream()),
                "b2_axpy_multi")
+
+
+def add_(y, x, alpha=1.0):
+    """y += alpha * x  (same-shape contiguous fp32 cuda tensors), in place; returns y"""
+    _require_cuda(y, x)
+    assert y.is_contiguous() and x.is_contiguous() and y.numel() == x.numel()
+    axpy_multi(TensorList([x]), TensorList([y]), alpha)
+    return y
 
 
 def tower_mean(srcs, dst):

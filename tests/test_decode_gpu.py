@@ -112,3 +112,71 @@ def test_edit_distance_kernel_bit_exact(cuda):
     got = ops.edit_distance(hyp, ref, cuda)
     want = np.array([lev(a, b) for a, b in zip(hyp, ref)])
     assert np.array_equal(got, want)
+
+
+def test_per_cer_wer_wrappers(cuda):
+    """utils/evaluation/edit_distance.py:35-109 call shapes over the device Levenshtein kernel"""
+    from tensorflow_end2end_speech_recognition_b200.utils.evaluation import edit_distance as ed
+
+    def lev(a, b):
+        d = list(range(len(b) + 1))
+        for i in range(1, len(a) + 1):
+            prev, d[0] = d[0], i
+            for j in range(1, len(b) + 1):
+                cur = d[j]
+                d[j] = min(d[j] + 1, d[j - 1] + 1, prev + (a[i - 1] != b[j - 1]))
+                prev = cur
+        return d[len(b)]
+    ref = "she had your dark suit in greasy wash water all year".split()
+    hyp = "she had dark suite in greasy wash water water all year".split()
+    assert ed.compute_wer(ref, hyp, normalize=False) == lev(ref, hyp)
+    assert abs(ed.compute_wer(ref, hyp) - lev(ref, hyp) / len(ref)) < 1e-12
+    s, i, d = ed.wer_align(ref, hyp)
+    assert s + i + d == lev(ref, hyp)
+    a, b = "shehadyourdarksuit", "shehadyrdarksuite"
+    assert abs(ed.compute_cer(b, a) - lev(list(b), list(a)) / len(a)) < 1e-12
+    pr, ph = ["sh", "iy", "hv", "ae", "d"], ["sh", "ih", "hv", "d"]
+    assert abs(ed.compute_per(pr, ph) - lev(pr, ph) / len(pr)) < 1e-12
+    # batched form + the sparse-triple form (normalised by the prediction length, as the reference's swapped call does)
+    from tensorflow_end2end_speech_recognition_b200.utils.io.labels.sparsetensor import list2sparsetensor
+    import numpy as np
+    true = np.array([[1, 2, 3, 4], [5, 6, -1, -1]]); pred = np.array([[1, 3, 4, -1], [5, 6, 7, -1]])
+    out = ed.compute_edit_distance(None, list2sparsetensor(true, -1), list2sparsetensor(pred, -1))
+    np.testing.assert_allclose(out, [1 / 3, 1 / 3], rtol=1e-6)
+
+
+@pytest.mark.parametrize("T,B,C,W", [(30, 4, 6, 3), (60, 5, 29, 20), (40, 3, 29, 100), (25, 2, 301, 16),
+                                     (12, 2, 3001, 100), (1, 2, 5, 4)])
+@pytest.mark.parametrize("merge", [True, False])
+def test_tf_semantics_beam_search(cuda, T, B, C, W, merge):
+    """b2_ctc_beam_decode_tf vs the restatement of tf.nn.ctc_beam_search_decoder (oracle/decode.py): label sequences
+    identical, scores equal to fp32 rounding; peaky and flat posteriors, ragged lengths, merge_repeated on/off"""
+    import torch
+    from tensorflow_end2end_speech_recognition_b200 import ops
+    rng = np.random.RandomState(T * 131 + C + W)
+    logits = (rng.randn(T, B, C) * (3.0 if C < 100 else 1.5)).astype(np.float32)
+    logits[:, :, C - 1] += 1.0                       # blanks a little more likely, as in a trained model
+    seq = np.array([T] + [int(rng.randint(max(1, T // 2), T + 1)) for _ in range(B - 1)], np.int32)
+    lab, n, score = ops.ctc_beam_decode_tf(torch.tensor(logits, device=cuda), torch.tensor(seq, device=cuda), W,
+                                           blank=C - 1, merge_repeated=merge)
+    lab, n, score = lab.cpu().numpy(), n.cpu().numpy(), score.cpu().numpy()
+    for b in range(B):
+        paths, scores = odec.tf_ctc_beam_search_single(logits[:seq[b], b], C - 1, W, merge_repeated=merge)
+        assert list(lab[b, :n[b]]) == paths[0], (b, list(lab[b, :n[b]]), paths[0])
+        assert (lab[b, n[b]:] == -1).all()
+        assert abs(score[b] - scores[0]) <= 1e-4 * max(1.0, abs(scores[0]))
+
+
+def test_tf_beam_width_one_is_not_greedy_but_close(cuda):
+    """model-level: CTC.decoder(beam_width>1) takes the TF-semantics path and merges repeats in the output"""
+    import torch
+    from tensorflow_end2end_speech_recognition_b200 import ops
+    T, C = 6, 4
+    logits = np.full((T, 1, C), -5.0, np.float32)
+    for t, c in enumerate([0, 3, 0, 1, 3, 1]):        # a - a b - b  -> "a a b b"
+        logits[t, 0, c] = 5.0
+    seq = np.array([T], np.int32)
+    for merge, want in ((True, [0, 1]), (False, [0, 0, 1, 1])):
+        lab, n, _ = ops.ctc_beam_decode_tf(torch.tensor(logits, device=cuda), torch.tensor(seq, device=cuda), 8,
+                                           blank=C - 1, merge_repeated=merge)
+        assert list(lab.cpu().numpy()[0, :int(n[0])]) == want

@@ -1,0 +1,72 @@
+"""MultitaskCTC (models/ctc/multitask_ctc.py) with the multitask BLSTM encoder: loss, both logits and every gradient
+vs the torch-fp64 oracle; bf16 path loss check; decode / LER plumbing; a few adam steps reduce the loss."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import model as omodel
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(rng, B, T, D, Cm, Cs):
+    x = rng.randn(B, T, D).astype(np.float32)
+    seq = np.array([T] + [int(rng.randint(T // 2 + 4, T + 1)) for _ in range(B - 1)], np.int32)
+    for b in range(B):
+        x[b, seq[b]:] = 0
+    lm = [list(rng.randint(0, Cm, size=int(rng.randint(2, 7)))) for _ in range(B)]
+    ls = [list(rng.randint(0, Cs, size=int(rng.randint(3, 10)))) for _ in range(B)]
+    return x, seq, lm, ls
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 3e-2)])
+@pytest.mark.parametrize("lsub", [1, 2, 3])
+def test_multitask_loss_and_grads(cuda, precision, tol, lsub):
+    from tensorflow_end2end_speech_recognition_b200.models.ctc.multitask_ctc import MultitaskCTC
+    rng = np.random.RandomState(7 + lsub)
+    B, T, D, H, L, Cm, Cs, w = 5, 36, 20, 32, 3, 9, 13, 0.7
+    model = MultitaskCTC(encoder_type="multitask_blstm", input_size=D, num_units=H, num_layers_main=L,
+                         num_layers_sub=lsub, num_classes_main=Cm, num_classes_sub=Cs, main_task_weight=w,
+                         parameter_init=0.1, clip_grad_norm=5.0, precision=precision, device=cuda, seed=5)
+    x, seq, lm, ls = _batch(rng, B, T, D, Cm, Cs)
+    loss, logits_main, logits_sub = model.compute_loss(x, lm, ls, seq, keep_prob=1.0)
+    model._backward()
+    torch.cuda.synchronize()
+    vs = {v.name: torch.tensor(v.tensor.cpu().numpy(), dtype=torch.float64, requires_grad=True)
+          for v in model.trainable_variables()}
+    total, lgm, lgs = omodel.multitask_ctc_forward(vs, torch.tensor(x, dtype=torch.float64), seq, lm, ls, L, lsub, w)
+    total.backward()
+    assert abs(float(loss) - float(total)) <= tol * abs(float(total))
+    np.testing.assert_allclose(logits_main.cpu().numpy(), lgm.detach().numpy(), rtol=tol, atol=tol)
+    np.testing.assert_allclose(logits_sub.cpu().numpy(), lgs.detach().numpy(), rtol=tol, atol=tol)
+    for v in model.trainable_variables():
+        g = vs[v.name].grad
+        g = np.zeros(v.tensor.shape) if g is None else g.numpy()
+        s = max(1e-3, np.abs(g).max())
+        np.testing.assert_allclose(v.grad.cpu().numpy(), g, rtol=0, atol=5 * tol * s, err_msg=v.name)
+
+
+def test_multitask_train_decode_ler(cuda):
+    from tensorflow_end2end_speech_recognition_b200.models.ctc.multitask_ctc import MultitaskCTC
+    rng = np.random.RandomState(3)
+    B, T, D, H, Cm, Cs = 4, 40, 16, 48, 8, 11
+    model = MultitaskCTC(encoder_type="multitask_blstm", input_size=D, num_units=H, num_layers_main=2,
+                         num_layers_sub=1, num_classes_main=Cm, num_classes_sub=Cs, main_task_weight=0.5,
+                         clip_grad_norm=5.0, precision="fp32", device=cuda, seed=6)
+    x, seq, lm, ls = _batch(rng, B, T, D, Cm, Cs)
+    first = None
+    for _ in range(60):
+        loss, logits_main, logits_sub = model.compute_loss(x, lm, ls, seq, keep_prob=1.0)
+        model.train(loss, "adam", 5e-3)
+        first = float(loss) if first is None else first
+    assert float(loss) < 0.5 * first
+    dm, ds = model.decoder(logits_main, logits_sub, seq, beam_width=1)
+    ler_m, ler_s = model.compute_ler(dm, ds, lm, ls)
+    assert 0 <= ler_m <= 2 and 0 <= ler_s <= 2
+    pm, ps = model.posteriors(logits_main, logits_sub)
+    assert pm.shape == (B * T, Cm + 1) and ps.shape == (B * T, Cs + 1)
+    with pytest.raises(ValueError):
+        MultitaskCTC(encoder_type="multitask_blstm", input_size=D, num_units=H, num_layers_main=2, num_layers_sub=1,
+                     num_classes_main=Cm, num_classes_sub=Cs, main_task_weight=1.5, device=cuda)
+    with pytest.raises(RuntimeError):       # ignore_longer_outputs_than_inputs=False
+        model.compute_loss(x[:, :5], lm, [list(range(8))] * B, np.full(B, 5, np.int32), keep_prob=1.0)
