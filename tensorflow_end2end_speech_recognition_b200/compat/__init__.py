@@ -38,18 +38,44 @@ _ALIASES = {
 }
 
 
-def install(alias_reference_packages=True):
+def install(alias_reference_packages=True, reference_root=None):
+    """``reference_root``: checkout of the reference repository.  The aliased packages (``models``, ``utils``, ...)
+    then also search the reference's own directories, so that modules this package does not replace --
+    ``utils.training.learning_rate_controller``, ``utils.directory``, ``utils.parameter``,
+    ``examples.*.metrics`` ... -- keep importing from the reference next to the B200 models."""
     from . import tf
     sys.modules["tensorflow"] = tf
     if alias_reference_packages:
         pkg = __name__.rsplit(".", 1)[0]
         for ref, mine in _ALIASES.items():
-            sys.modules.setdefault(ref, importlib.import_module(pkg + "." + mine))
+            m = importlib.import_module(pkg + "." + mine)
+            sys.modules.setdefault(ref, m)
+            if reference_root and hasattr(m, "__path__"):
+                import os
+                extra = os.path.join(reference_root, *ref.split("."))
+                if os.path.isdir(extra) and extra not in list(m.__path__):
+                    m.__path__.append(extra)
+                    _EXTENDED.append((m, extra))
+        if reference_root and reference_root not in sys.path:
+            sys.path.append(reference_root)
+            _EXTENDED.append((None, reference_root))
     return tf
+
+
+_EXTENDED = []
 
 
 def uninstall():
     sys.modules.pop("tensorflow", None)
+    while _EXTENDED:
+        m, extra = _EXTENDED.pop()
+        if m is None:
+            if extra in sys.path:
+                sys.path.remove(extra)
+        elif extra in list(m.__path__):
+            m.__path__.remove(extra)
+    for name in [n for n in sys.modules if n == "examples" or n.startswith("examples.")]:
+        sys.modules.pop(name, None)
     pkg = __name__.rsplit(".", 1)[0]
     for ref in _ALIASES:
         m = sys.modules.get(ref)

@@ -10,12 +10,16 @@
 // child not yet in the beam is a candidate, and the beam keeps the `beam_width` best totals of leaves + candidates;
 // the emitted path optionally drops a label that repeats its successor (merge_repeated).
 //
-// One CTA per utterance.  The sequential insert-if-better-than-the-bottom loop of TF equals an exact top-W
-// selection (a candidate's total never exceeds its parent's old total, so TF's early-outs prune nothing that could
-// enter), which is what this kernel computes: per frame
-//   1. x = logits row - max (shared memory), the W+1 labels with the largest x (a candidate outside them has at
-//      least W better siblings), 2. leaf update in fp64, 3. candidate totals, fp64, [leaf][top label | own label],
-//   4. W rounds of block-wide arg-max over leaves + candidates (ties: lowest index), 5. new leaves get tree nodes.
+// One CTA per utterance.  TF's Step() is a SEQUENTIAL procedure whose outcome depends on its order: leaves grow in
+// descending old-probability order, children in ascending label order, each accepted child evicts the current bottom
+// of the beam, and a child that is REJECTED has both its old and new probabilities reset -- when that child is itself
+// a leaf evicted earlier in the same frame, it thereby loses its own turn to grow (ctc_beam_search.h, "Deactivate
+// child").  An exact top-W selection is therefore NOT equivalent; this kernel reproduces the procedure:
+//   1. x = logits row - max (shared memory);
+//   2. every leaf is updated in parallel (fp64), and the growth order (descending old total) is ranked in parallel;
+//   3. per growing leaf b: all threads compute the candidate totals of its children, then ONE thread replays TF's
+//      insert / evict / reset sequence over them (rejections are a compare against the cached bottom);
+//   4. the surviving members become the next frame's leaves; new children get tree nodes.
 // Integer / ordering work, latency-bound; label sequences are bit-exact against the oracle.
 #include "common.cuh"
 #include <math_constants.h>
@@ -31,63 +35,30 @@ __device__ __forceinline__ double tf_lse2(double a, double b) {
   return m + log(exp(a - m) + exp(b - m));
 }
 
-struct TfBest { double s; int idx; };     // idx < 0: none
-__device__ __forceinline__ bool tf_better(const TfBest& a, const TfBest& b) {
-  if (a.idx < 0) return false;
-  if (b.idx < 0) return true;
-  if (a.s > b.s) return true;
-  if (a.s < b.s) return false;
-  return a.idx < b.idx;
-}
-// block-wide arg-max over vals[0..n) (entries equal to -inf are not candidates); every thread gets the result
-__device__ TfBest tf_block_argmax(const double* vals, int n, TfBest* wbest) {
-  TfBest b; b.s = -CUDART_INF; b.idx = -1;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const double v = vals[i];
-    if (v == -CUDART_INF) continue;
-    TfBest c; c.s = v; c.idx = i;
-    if (tf_better(c, b)) b = c;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    TfBest c;
-    c.s = __shfl_xor_sync(0xffffffffu, b.s, o);
-    c.idx = __shfl_xor_sync(0xffffffffu, b.idx, o);
-    if (tf_better(c, b)) b = c;
-  }
-  if ((threadIdx.x & 31) == 0) wbest[threadIdx.x >> 5] = b;
-  __syncthreads();
-  b = wbest[0];
-  for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
-    if (tf_better(wbest[w], b)) b = wbest[w];
-  __syncthreads();
-  return b;
-}
-
-// dynamic shared memory: [cand: W*(W+2) doubles][xs: C doubles][xsel: C doubles][rank: C ints]
+// dynamic shared memory: [xs: C doubles][score: C doubles][child_slot: C ints]
 __global__ void __launch_bounds__(kTfBeamThreads)
 ctc_beam_tf_kernel(const float* __restrict__ logits, const int* __restrict__ seq_len, int T, int B, int C,
                    int blank, int W, int merge_repeated, int* __restrict__ node_parent_all,
                    int* __restrict__ node_label_all, int* __restrict__ out_labels, int* __restrict__ out_len,
                    float* __restrict__ out_score) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int WL = min(W + 1, C - 1);              // labels considered per leaf (+ the leaf's own label)
-  const int CS = WL + 1;                         // candidate slots per leaf
-  double* cand = (double*)smem_raw;              // [W][CS]
-  double* xs = cand + (size_t)W * CS;            // [C] row - max
-  double* xsel = xs + C;                         // [C] scratch for the label selection
-  int* rank = (int*)(xsel + C);                  // [C] position in topl, or -1
+  double* xs = (double*)smem_raw;                // [C] row - max
+  double* score = xs + C;                        // [C] candidate totals of the growing leaf's children
+  int* child_slot = (int*)(score + C);           // [C] existing leaf that IS child (b, c), or -1
+  // leaves of the previous frame ("branches")
   __shared__ double tot[kTfMaxBeam], pbl[kTfMaxBeam], plb[kTfMaxBeam];      // new (t)
   __shared__ double otot[kTfMaxBeam], opbl[kTfMaxBeam];                      // old (t-1)
-  __shared__ double ntot[kTfMaxBeam], npbl[kTfMaxBeam], nplb[kTfMaxBeam];
-  __shared__ int node[kTfMaxBeam], label[kTfMaxBeam], pslot[kTfMaxBeam];
+  __shared__ int node[kTfMaxBeam], label[kTfMaxBeam], pslot[kTfMaxBeam], order[kTfMaxBeam];
+  __shared__ unsigned char alive[kTfMaxBeam], oreset[kTfMaxBeam];
+  // members of the beam while it grows: kind 0 = branch `idx` with its updated probabilities, 1 = branch `idx`
+  // re-entered as a fresh child (it keeps its node), 2 = new child (parent branch `par`, label `lab`)
+  __shared__ int m_kind[kTfMaxBeam], m_idx[kTfMaxBeam], m_par[kTfMaxBeam], m_lab[kTfMaxBeam];
+  __shared__ double m_tot[kTfMaxBeam];
+  __shared__ double nt[kTfMaxBeam], nb[kTfMaxBeam], nl[kTfMaxBeam];
   __shared__ int nnode[kTfMaxBeam], nlabel[kTfMaxBeam], npar[kTfMaxBeam];
-  __shared__ int topl[kTfMaxBeam + 1];
-  __shared__ unsigned int active_bits[kTfMaxBeam * 5];                        // [W][CS <= 130 bits -> 5 words]
-  __shared__ TfBest wbest[kTfBeamThreads / 32];
-  __shared__ double lvals[kTfMaxBeam];
-  __shared__ int s_n, s_nodes;
-  __shared__ double s_max;
+  __shared__ double red[kTfBeamThreads / 32];
+  __shared__ int s_n, s_nodes, s_members, s_bottom;
+  __shared__ double s_max, s_bottom_val;
 
   const int b = blockIdx.x, tid = threadIdx.x;
   const int Tb = min(seq_len[b], T);
@@ -95,7 +66,6 @@ ctc_beam_tf_kernel(const float* __restrict__ logits, const int* __restrict__ seq
   int* node_parent = node_parent_all + (size_t)b * node_cap;
   int* node_label = node_label_all + (size_t)b * node_cap;
 
-  for (int c = tid; c < C; c += blockDim.x) rank[c] = -1;
   if (tid == 0) {
     node[0] = 0; label[0] = -1; pslot[0] = -1;
     tot[0] = 0.0; pbl[0] = 0.0; plb[0] = -CUDART_INF;
@@ -111,137 +81,144 @@ ctc_beam_tf_kernel(const float* __restrict__ logits, const int* __restrict__ seq
     float m = -INFINITY;
     for (int c = tid; c < C; c += blockDim.x) m = fmaxf(m, row[c]);
     m = warp_max(m);
-    if ((tid & 31) == 0) lvals[tid >> 5] = (double)m;
+    if ((tid & 31) == 0) red[tid >> 5] = (double)m;
     __syncthreads();
     if (tid == 0) {
-      double mm = lvals[0];
-      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mm = fmax(mm, lvals[w]);
+      double mm = red[0];
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mm = fmax(mm, red[w]);
       s_max = mm;
     }
     __syncthreads();
     const double mx = s_max;
-    for (int c = tid; c < C; c += blockDim.x) {
-      const double v = (double)row[c] - mx;
-      xs[c] = v;
-      xsel[c] = (c == blank) ? -CUDART_INF : v;
-    }
-    __syncthreads();
-    // the WL labels with the largest x (all of them when the vocabulary is small)
-    if (C - 1 <= WL) {
-      for (int c = tid; c < C; c += blockDim.x)
-        if (c != blank) { const int j = c < blank ? c : c - 1; topl[j] = c; rank[c] = j; }
-      __syncthreads();
-    } else {
-      for (int j = 0; j < WL; ++j) {
-        const TfBest bst = tf_block_argmax(xsel, C, wbest);
-        if (tid == 0) { topl[j] = bst.idx; rank[bst.idx] = j; xsel[bst.idx] = -CUDART_INF; }
-        __syncthreads();
-      }
-    }
-    // ---- 2. existing leaves: old <- new, then the update of CTCBeamSearchDecoder::Step's first loop
+    for (int c = tid; c < C; c += blockDim.x) xs[c] = (double)row[c] - mx;
     if (tid < n) { otot[tid] = tot[tid]; opbl[tid] = pbl[tid]; }
-    for (int i = tid; i < W * 5; i += blockDim.x) active_bits[i] = 0u;
     __syncthreads();
+    // ---- 2. existing leaves (first loop of Step) + growth order = descending old total
     if (tid < n) {
       const int i = tid;
-      double nl = plb[i];
+      double l = plb[i];
       if (label[i] >= 0) {
         const int p = pslot[i];
-        if (p >= 0) {
-          const double prev = (label[i] == label[p]) ? opbl[p] : otot[p];
-          nl = tf_lse2(nl, prev);
-          // this leaf IS the child (p, label[i]): it is not a candidate again
-          const int j = (label[i] == label[p]) ? WL : rank[label[i]];
-          if (j >= 0) atomicOr(&active_bits[p * 5 + (j >> 5)], 1u << (j & 31));
-        }
-        nl += xs[label[i]];
+        if (p >= 0) l = tf_lse2(l, (label[i] == label[p]) ? opbl[p] : otot[p]);
+        l += xs[label[i]];
       }
-      const double nb = otot[i] + xs[blank];
-      plb[i] = nl; pbl[i] = nb; tot[i] = tf_lse2(nb, nl);
+      const double bk = otot[i] + xs[blank];
+      plb[i] = l; pbl[i] = bk; tot[i] = tf_lse2(bk, l);
+      int r = 0;
+      for (int j = 0; j < n; ++j) r += (otot[j] > otot[i]) || (otot[j] == otot[i] && j < i);
+      order[r] = i;
+      alive[i] = 1; oreset[i] = 0;
+      m_kind[i] = 0; m_idx[i] = i; m_tot[i] = tot[i];
     }
     __syncthreads();
-    // ---- 3. candidates [leaf i][slot j]: j < WL -> label topl[j] (skipped when it is the leaf's own label),
-    //         j == WL -> the leaf's own label, fed from P_blank only
-    for (int k = tid; k < n * CS; k += blockDim.x) {
-      const int i = k / CS, j = k - i * CS;
-      double v = -CUDART_INF;
-      if (otot[i] != -CUDART_INF && !((active_bits[i * 5 + (j >> 5)] >> (j & 31)) & 1u)) {
-        if (j < WL) {
-          const int c = topl[j];
-          if (c != label[i]) v = xs[c] + otot[i];
-        } else if (label[i] >= 0) {
-          v = xs[label[i]] + opbl[i];
-        }
-      }
-      cand[k] = v;
+    if (tid == 0) {
+      s_members = n;
+      int bi = -1; double bv = CUDART_INF;
+      if (n == W) for (int k = 0; k < n; ++k) if (m_tot[k] < bv) { bv = m_tot[k]; bi = k; }
+      s_bottom = bi; s_bottom_val = (n == W) ? bv : -CUDART_INF;
     }
-    if (tid < n) lvals[tid] = tot[tid];
     __syncthreads();
-    // ---- 4. W rounds: best of (leaves, candidates); a leaf wins ties (it was pushed first)
-    int nsel = 0;
-    for (int r = 0; r < W; ++r) {
-      const TfBest bl = tf_block_argmax(lvals, n, wbest);
-      const TfBest bc = tf_block_argmax(cand, n * CS, wbest);
-      if (bl.idx < 0 && bc.idx < 0) break;
-      const bool take_leaf = bl.idx >= 0 && (bc.idx < 0 || bl.s >= bc.s);
+    // ---- 3. growth, leaf by leaf in TF's order
+    for (int r = 0; r < n; ++r) {
+      const int g = order[r];
+      const bool full = s_members == W;
+      // is_candidate(b->oldp): total nonzero and (beam not full or better than the bottom); a leaf whose
+      // probabilities were reset as a rejected child earlier in this frame has lost its turn
+      const bool go = !oreset[g] && otot[g] != -CUDART_INF && (!full || otot[g] > s_bottom_val);
+      if (!go) continue;                                   // uniform: decided from shared state
+      for (int c = tid; c < C; c += blockDim.x) {
+        child_slot[c] = -1;
+        score[c] = (c == blank) ? -CUDART_INF : xs[c] + ((c == label[g]) ? opbl[g] : otot[g]);
+      }
+      __syncthreads();
+      if (tid < n && pslot[tid] == g) child_slot[label[tid]] = tid;
+      __syncthreads();
       if (tid == 0) {
-        if (take_leaf) {
-          const int i = bl.idx;
-          nnode[nsel] = node[i]; nlabel[nsel] = label[i]; npar[nsel] = node_parent[node[i]];
-          ntot[nsel] = tot[i]; npbl[nsel] = pbl[i]; nplb[nsel] = plb[i];
-          lvals[i] = -CUDART_INF;
-        } else {
-          const int i = bc.idx / CS, j = bc.idx - i * CS;
-          const int c = j < WL ? topl[j] : label[i];
-          const int id = s_nodes++;
-          node_parent[id] = node[i]; node_label[id] = c;
-          nnode[nsel] = id; nlabel[nsel] = c; npar[nsel] = node[i];
-          ntot[nsel] = bc.s; npbl[nsel] = -CUDART_INF; nplb[nsel] = bc.s;
-          cand[bc.idx] = -CUDART_INF;
+        int members = s_members, bi = s_bottom;
+        double bv = s_bottom_val;
+        for (int c = 0; c < C; ++c) {
+          if (c == blank) continue;
+          const int e = child_slot[c];
+          const double sc = score[c];
+          if (e >= 0 && alive[e]) continue;                // c.Active(): the child is in the beam already
+          const bool cand = sc != -CUDART_INF && (members < W || sc > bv);
+          if (!cand) {
+            if (e >= 0) oreset[e] = 1;                     // "Deactivate child": oldp and newp reset
+            continue;
+          }
+          int slot;
+          if (members == W) {                              // the bottom leaves the beam
+            slot = bi;
+            if (m_kind[slot] != 2) alive[m_idx[slot]] = 0;
+          } else {
+            slot = members++;
+          }
+          if (e >= 0) { m_kind[slot] = 1; m_idx[slot] = e; alive[e] = 1; }
+          else { m_kind[slot] = 2; m_idx[slot] = -1; }
+          m_par[slot] = g; m_lab[slot] = c; m_tot[slot] = sc;
+          if (members == W) {
+            bi = 0; bv = m_tot[0];
+            for (int k = 1; k < W; ++k) if (m_tot[k] < bv) { bv = m_tot[k]; bi = k; }
+          }
         }
+        s_members = members; s_bottom = bi; s_bottom_val = (members == W) ? bv : -CUDART_INF;
       }
-      ++nsel;
       __syncthreads();
     }
-    // ---- 5. the new beam; parent slot = position of the parent node in it (or -1: parent left the beam)
-    if (tid < nsel) {
-      node[tid] = nnode[tid]; label[tid] = nlabel[tid];
-      tot[tid] = ntot[tid]; pbl[tid] = npbl[tid]; plb[tid] = nplb[tid];
-      int ps = -1;
-      for (int k = 0; k < nsel; ++k)
-        if (nnode[k] == npar[tid]) { ps = k; break; }
-      pslot[tid] = npar[tid] >= 0 ? ps : -1;
+    // ---- 4. members -> leaves of the next frame
+    const int nm = s_members;
+    if (tid == 0) {
+      for (int k = 0; k < nm; ++k) {
+        if (m_kind[k] == 0) {
+          const int i = m_idx[k];
+          nnode[k] = node[i]; nlabel[k] = label[i]; npar[k] = node_parent[node[i]];
+          nt[k] = tot[i]; nb[k] = pbl[i]; nl[k] = plb[i];
+        } else {
+          int id;
+          if (m_kind[k] == 1) id = node[m_idx[k]];
+          else { id = s_nodes++; node_parent[id] = node[m_par[k]]; node_label[id] = m_lab[k]; }
+          nnode[k] = id; nlabel[k] = m_lab[k]; npar[k] = node[m_par[k]];
+          nt[k] = m_tot[k]; nb[k] = -CUDART_INF; nl[k] = m_tot[k];
+        }
+      }
     }
-    for (int j = tid; j < WL; j += blockDim.x) rank[topl[j]] = -1;
-    if (tid == 0) s_n = nsel;
+    __syncthreads();
+    if (tid < nm) {
+      int ps = -1;
+      if (npar[tid] >= 0)
+        for (int k = 0; k < nm; ++k)
+          if (nnode[k] == npar[tid]) { ps = k; break; }
+      m_par[tid] = ps;
+    }
+    __syncthreads();
+    if (tid < nm) {
+      node[tid] = nnode[tid]; label[tid] = nlabel[tid]; pslot[tid] = m_par[tid];
+      tot[tid] = nt[tid]; pbl[tid] = nb[tid]; plb[tid] = nl[tid];
+    }
+    if (tid == 0) s_n = nm;
     __syncthreads();
   }
 
   // ---- TopPaths(1): best total; LabelSeq(merge_repeated) walks leaf -> root
-  {
+  if (tid == 0) {
     const int n = s_n;
-    if (tid < n) lvals[tid] = tot[tid];
-    __syncthreads();
-    const TfBest best = tf_block_argmax(lvals, n, wbest);
-    if (tid == 0) {
-      int* out = out_labels + (size_t)b * T;
-      int len = 0;
-      if (best.idx >= 0) {
-        int cur = node[best.idx], prev_label = -1;
-        while (node_parent[cur] >= 0 || node_label[cur] >= 0) {
-          const int l = node_label[cur];
-          if (l < 0) break;
-          if (!merge_repeated || l != prev_label) out[len++] = l;
-          prev_label = l;
-          cur = node_parent[cur];
-          if (cur < 0) break;
-        }
-        for (int i = 0; i < len / 2; ++i) { const int tmp = out[i]; out[i] = out[len - 1 - i]; out[len - 1 - i] = tmp; }
+    int best = -1; double bv = -CUDART_INF;
+    for (int k = 0; k < n; ++k) if (best < 0 || tot[k] > bv) { bv = tot[k]; best = k; }
+    int* out = out_labels + (size_t)b * T;
+    int len = 0;
+    if (best >= 0) {
+      int cur = node[best], prev_label = -1;
+      while (cur >= 0 && node_label[cur] >= 0) {
+        const int l = node_label[cur];
+        if (!merge_repeated || l != prev_label) out[len++] = l;
+        prev_label = l;
+        cur = node_parent[cur];
       }
-      for (int i = len; i < T; ++i) out[i] = -1;
-      out_len[b] = len;
-      out_score[b] = best.idx >= 0 ? (float)best.s : -INFINITY;
+      for (int i = 0; i < len / 2; ++i) { const int tmp = out[i]; out[i] = out[len - 1 - i]; out[len - 1 - i] = tmp; }
     }
+    for (int i = len; i < T; ++i) out[i] = -1;
+    out_len[b] = len;
+    out_score[b] = best >= 0 ? (float)bv : -INFINITY;
   }
 }
 
@@ -276,8 +253,7 @@ extern "C" int b2_ctc_beam_decode_tf(const float* logits, const int32_t* seq_len
   int* parent = nullptr; int* lab = nullptr;
   const size_t need = tf_beam_ws_layout(T, B, beam_width, workspace, &parent, &lab);
   if (workspace_bytes < need) { set_error("b2_ctc_beam_decode_tf: workspace %zu < %zu", workspace_bytes, need); return B2_ERR_WORKSPACE; }
-  const int WL = (beam_width + 1 < C - 1) ? beam_width + 1 : C - 1;
-  const size_t smem = ((size_t)beam_width * (WL + 1) + 2 * (size_t)C) * sizeof(double) + (size_t)C * sizeof(int);
+  const size_t smem = 2 * (size_t)C * sizeof(double) + (size_t)C * sizeof(int);
   B2_CHECK_ARG(smem <= 200 * 1024, "b2_ctc_beam_decode_tf: beam %d x vocabulary %d needs %zu bytes of shared memory",
                beam_width, C, smem);
   B2_CUDA(cudaFuncSetAttribute(ctc_beam_tf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

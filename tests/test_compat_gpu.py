@@ -20,8 +20,10 @@ def test_ctc_graph_style_training(cuda, tmp_path):
         inputs = rng.randn(B, T, D).astype(np.float32)
         inputs_seq_len = np.array([T, T - 6], np.int32)
         labels = np.full((B, 8), -1, np.int32)
-        labels[0, :8] = rng.randint(0, C, 8)
-        labels[1, :5] = rng.randint(0, C, 5)
+        # no adjacent repeats: decode_op (beam_width=20) is tf.nn.ctc_beam_search_decoder, whose default
+        # merge_repeated=True collapses "a a" to "a" in the emitted path (ctc.py:344-346)
+        labels[0, :8] = [3, 7, 1, 19, 4, 11, 26, 0]
+        labels[1, :5] = [5, 2, 9, 2, 14]
         with tf.Graph().as_default():
             model = CTC(encoder_type="blstm", input_size=D, splice=1, num_stack=1, num_units=32, num_layers=2,
                         num_classes=C, lstm_impl="LSTMBlockCell", parameter_init=0.1, clip_grad_norm=5.0,
