@@ -206,7 +206,17 @@ def main():
                 num_layers=CFG["num_layers"], num_classes=CFG["num_classes"],
                 lstm_impl="LSTMBlockCell", use_peephole=True, parameter_init=0.1,
                 clip_grad_norm=CFG["clip"], precision=args.precision, device=dev, seed=1)
-    model.set_data_parallel(world)
+    comm, comm_kind = None, "none"
+    if world > 1:
+        comm_kind = "torch.distributed all_reduce (one call after BPTT)"
+        if os.environ.get("B2_BENCH_COMM", "c_abi") == "c_abi":
+            try:     # NCCL bound from the C ABI (b2_allreduce_mean), per-layer buckets overlapped with BPTT
+                from tensorflow_end2end_speech_recognition_b200.utils.training.multi_gpu import NcclComm
+                comm = NcclComm(rank, world, device=dev)
+                comm_kind = "b2_allreduce_mean (NCCL from the C ABI), per-layer buckets overlapped with BPTT"
+            except Exception as e:          # keep the run alive on the torch path, and say so
+                comm, comm_kind = None, "torch.distributed all_reduce (C-ABI communicator failed: %s)" % (e,)
+    model.set_data_parallel(world, comm=comm)
     # weak scaling: every rank gets its own 64-utterance shard (np.array_split of a 64*N batch,
     # utils/dataset/ctc.py:171-177); strong scaling: its slice of the one 64-utterance batch
     x, seq, labels = make_batch(1234 + rank, B, T, D, CFG["num_classes"], CFG["label_min"], CFG["label_max"])
@@ -421,6 +431,7 @@ def main():
                                           "B=64 per GPU" if SCALING != "strong" else
                                           "global B=64 array_split over the GPUs", CFG["keep_prob"]),
                           "global_batch": (CFG["B"] if SCALING == "strong" else B * world), "per_gpu_batch": B, "parallelism": "dp%d" % world,
+                          "gradient_exchange": comm_kind,
                           "l2": "per-step working set (reserve + gate buffers, >8 GB) >> 126 MB L2, "
                                 "no explicit flush"},
                "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,

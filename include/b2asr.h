@@ -235,6 +235,11 @@ int b2_blstm_profile_last_ms(float* fwd_ms, float* bwd_ms);
  * side stream (they overlap the next layer's BPTT recurrence).  Call this once after the
  * last b2_blstm_layer_backward of a step: it makes `stream` wait for them (no host sync). */
 int b2_blstm_backward_join(b2_stream_t stream);
+/* `stream` waits for the side-stream work ENQUEUED so far -- after the backward call of layer l that is the
+ * weight gradients of layer l+1 (those of layer l itself are launched next to layer l-1's recurrence, or by the
+ * join).  The data-parallel step reduces layer l+1's gradient bucket behind this wait while BPTT continues
+ * (replaces the single synchronisation point of utils/training/multi_gpu.py:13-48). */
+int b2_blstm_backward_side_wait(b2_stream_t stream);
 
 /* ------------------------------------------------------------------------ *
  * Input pipeline on the device: frame stacking / skipping + splicing + zero padding
@@ -265,7 +270,8 @@ typedef struct {
   int32_t N, H, W;            /* frames, num_channels, splice*num_stack      */
   float keep_prob;            /* tf.nn.dropout keep probability; 1 = off      */
   uint64_t dropout_seed;      /* counter-hash seed (sites use seed+1..seed+5) */
-  int32_t precision;          /* B2_PREC_FP32 (the only one built so far)     */
+  int32_t precision;          /* B2_PREC_FP32: CUDA-core fp32 GEMMs; B2_PREC_BF16: the 64/128-channel
+                                 convolutions and the bridge FC on tcgen05 (bf16 operands, fp32 accumulate) */
 } b2_vgg_desc;
 typedef struct {
   const float* conv_w[4];     /* VGG1/conv1, VGG1/conv2, VGG2/conv1, VGG2/conv2 */

@@ -87,6 +87,7 @@ PROTOTYPES = {
     "b2_blstm_layer_forward": (_i, [C.POINTER(LstmDesc), _p, _p, _p, C.POINTER(LstmParams),
                                     C.POINTER(LstmParams), _p, _p, _p, _p, _sz, _p]),
     "b2_blstm_backward_join": (_i, [_p]),
+    "b2_blstm_backward_side_wait": (_i, [_p]),
     "b2_blstm_profile_enable": (None, [_i]),
     "b2_blstm_profile_last_ms": (_i, [_p, _p]),
     "b2_blstm_reserve_y_lp": (_p, [C.POINTER(LstmDesc), _p]),

@@ -33,6 +33,9 @@ struct GemmArgs {
   float alpha;
   int m_tiles, n_tiles, k_splits, kb_per_split, kblocks;
   int epi;
+  // implicit convolution over a zero-bordered NHWC buffer (vgg.cu): K block kb belongs to kernel row
+  // kb / a_tap_kb; its A tile sits a_tap_rows rows further down and (kb % a_tap_kb) * 64 columns in.  0 = plain GEMM.
+  int a_tap_kb, a_tap_rows;
 };
 
 template <int BN> struct GemmCfg {
@@ -99,7 +102,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* a = sA + stage * Cfg::kStageA;
           uint8_t* b = sB + stage * Cfg::kStageB;
           if (!A_MN) {
-            tma_load_2d(a, &tmA, &full[stage], kb * GK, m0);
+            int acol = kb * GK, arow = m0;
+            if (args.a_tap_kb) {
+              const int tap = kb / args.a_tap_kb;
+              acol = (kb - tap * args.a_tap_kb) * GK;
+              arow = m0 + tap * args.a_tap_rows;
+            }
+            tma_load_2d(a, &tmA, &full[stage], acol, arow);
           } else {
 #pragma unroll
             for (int i = 0; i < GM / 64; ++i)
@@ -349,6 +358,7 @@ int gemm_bf16_tc(int a_mn, int b_mn, int M, int N, int K, float alpha, const __n
   if (b_mn && BN < 64) BN = 64;
   GemmArgs g;
   g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.C = C; g.bias = bias; g.alpha = alpha; g.epi = epi;
+  g.a_tap_kb = 0; g.a_tap_rows = 0;
   g.m_tiles = cdiv(M, GM); g.n_tiles = cdiv(N, BN);
   g.kblocks = cdiv(K, GK);
   int splits = 1;
@@ -381,6 +391,29 @@ int gemm_bf16_tc(int a_mn, int b_mn, int M, int N, int K, float alpha, const __n
 #undef DISPATCH
   set_error("gemm_bf16_tc: no kernel for BN=%d", BN);
   return B2_ERR_UNSUPPORTED;
+}
+
+// 3x3 convolution over a zero-bordered NHWC activation buffer as ONE tensor-core GEMM (vgg.cu):
+//   C[M, N] = sum_{dh < taps} A_dh[M, Ktap] . B[dh*Ktap .. , N],  A_dh row r = activation row r + dh*tap_rows,
+// where a row holds Ktap = kw*Cin contiguous bf16 (overlapping rows when kw = 3: row pitch Cin < Ktap -- the three
+// horizontal taps of a kernel row are adjacent in memory).  A: [a_rows, pitch lda], B: [taps*Ktap rows][N contiguous].
+int gemm_bf16_tc_conv(int M, int N, int Ktap, int taps, int tap_rows, const __nv_bfloat16* A, int64_t a_rows, int lda,
+                      const __nv_bfloat16* B, int ldb, float* C, int ldc, cudaStream_t stream) {
+  B2_CHECK_ARG(M > 0 && N >= 64 && Ktap % GK == 0 && taps >= 1, "gemm_bf16_tc_conv: bad shape M=%d N=%d Ktap=%d", M, N, Ktap);
+  const int BN = N > 128 ? 256 : N > 64 ? 128 : 64;
+  GemmArgs g;
+  g.M = M; g.N = N; g.K = Ktap * taps; g.ldc = ldc; g.C = C; g.bias = nullptr; g.alpha = 1.f; g.epi = EPI_STORE_F32;
+  g.a_tap_kb = Ktap / GK; g.a_tap_rows = tap_rows;
+  g.m_tiles = cdiv(M, GM); g.n_tiles = cdiv(N, BN);
+  g.kblocks = g.K / GK; g.kb_per_split = g.kblocks; g.k_splits = 1;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16(&tmA, A, (uint64_t)Ktap, (uint64_t)a_rows, (uint64_t)lda, GK, GM);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tmB, B, (uint64_t)N, (uint64_t)g.K, (uint64_t)ldb, 64, GK);
+  if (rc) return rc;
+  if (BN == 256) return launch_gemm_tc<256, false, true>(tmA, tmB, g, stream);
+  if (BN == 128) return launch_gemm_tc<128, false, true>(tmA, tmB, g, stream);
+  return launch_gemm_tc<64, false, true>(tmA, tmB, g, stream);
 }
 
 // fp32 [rows, cols] (pitch ldi) -> bf16 [rows, ldo] with zero padding of cols..ldo

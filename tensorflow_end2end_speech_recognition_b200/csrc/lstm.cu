@@ -533,6 +533,10 @@ extern "C" int b2_blstm_backward_join(b2_stream_t stream_) {
   return tc_backward_join((cudaStream_t)stream_);
 }
 
+extern "C" int b2_blstm_backward_side_wait(b2_stream_t stream_) {
+  return tc_backward_side_wait((cudaStream_t)stream_);
+}
+
 extern "C" const void* b2_blstm_reserve_y_lp(const b2_lstm_desc* d, const void* reserve) {
   if (!d || !reserve || !tc_layer_supported(d)) return nullptr;
   Reserve r;

@@ -82,6 +82,8 @@ int gemm_skinny_pair(int transb, int M, int N, int K, const float* A0, const flo
 int gemm_bf16_tc(int a_mn, int b_mn, int M, int N, int K, float alpha, const __nv_bfloat16* A,
                  int lda, const __nv_bfloat16* B, int ldb, void* C, int ldc, const float* bias,
                  int epi, int k_splits_hint, cudaStream_t stream);
+int gemm_bf16_tc_conv(int M, int N, int Ktap, int taps, int tap_rows, const __nv_bfloat16* A, int64_t a_rows, int lda,
+                      const __nv_bfloat16* B, int ldb, float* C, int ldc, cudaStream_t stream);
 int cast_f32_bf16(const float* in, int64_t rows, int cols, int ldi, __nv_bfloat16* out, int ldo,
                   cudaStream_t stream);
 int make_tmap_generic(CUtensorMap* tm, int dtype_is_f32, const void* base, int rank,
@@ -104,6 +106,7 @@ int tc_layer_backward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16
                       cudaStream_t stream);
 
 int tc_backward_join(cudaStream_t stream);
+int tc_backward_side_wait(cudaStream_t stream);
 void tc_profile_enable(int on);
 int tc_profile_last_ms(float* fwd_ms, float* bwd_ms);
 

@@ -259,6 +259,14 @@ static int run_wgrad(const DeferredWgrad& w, cudaStream_t gs, int cta_limit) {
   return B2_OK;
 }
 
+// make `stream` wait for the side-stream work enqueued so far (NOT for the still-deferred weight gradients of the
+// layer processed last): the per-layer gradient buckets of the data-parallel step are reduced behind this
+int tc_backward_side_wait(cudaStream_t stream) {
+  SideCtx* c = side_ctx();
+  if (c->pending) B2_CUDA(cudaStreamWaitEvent(stream, c->ev_done, 0));
+  return B2_OK;
+}
+
 // make `stream` wait for every outstanding side-stream gradient GEMM (flushing the deferred ones first)
 int tc_backward_join(cudaStream_t stream) {
   SideCtx* c = side_ctx();

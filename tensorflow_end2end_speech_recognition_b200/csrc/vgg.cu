@@ -207,8 +207,13 @@ static int ew_blocks(int64_t n) {
 }
 
 
+// bf16 tensor-core path (precision == B2_PREC_BF16): every activation / gradient buffer that feeds a GEMM also
+// exists as a bf16 shadow with the same row geometry; the 64- and 128-channel convolutions and the bridge FC run on
+// gemm_tc_kernel (tcgen05), conv1_1 (3 input channels = 6-byte rows, no TMA) stays on the fp32 CUDA-core GEMM.
 struct VggBuf {
   Geo g0, g2, g4;
+  __nv_bfloat16* Pb[4];   // shadows of P[1..3] (index 0 unused)
+  __nv_bfloat16* Fb;      // shadow of F
   float* P[4];     // P[0] = padded input (3 ch), P[1] = conv1_1 out (64, g0), P[2] = pooled conv1_2 (64, g2),
                    // P[3] = conv2_1 out (128, g2)
   float* Y2;       // conv1_2 GEMM output, frame of g0, 64 ch
@@ -227,16 +232,24 @@ static size_t vgg_reserve_layout(const b2_vgg_desc* d, void* base, VggBuf* b) {
   const size_t o2 = take((size_t)t.g2.rows * 64 * 4), o3 = take((size_t)t.g2.rows * 128 * 4);
   const size_t oy2 = take((size_t)t.g0.M * 64 * 4), oy4 = take((size_t)t.g2.M * 128 * 4);
   const size_t of = take((size_t)d->N * t.g4.H * t.g4.W * 128 * 4), oo = take((size_t)d->N * 256 * 4);
+  const bool lp = d->precision == B2_PREC_BF16;
+  const size_t ob1 = lp ? take((size_t)t.g0.rows * 64 * 2) : 0, ob2 = lp ? take((size_t)t.g2.rows * 64 * 2) : 0;
+  const size_t ob3 = lp ? take((size_t)t.g2.rows * 128 * 2) : 0;
+  const size_t obf = lp ? take((size_t)d->N * t.g4.H * t.g4.W * 128 * 2) : 0;
   if (b) {
     char* p = (char*)base;
     t.P[0] = (float*)(p + o0); t.P[1] = (float*)(p + o1); t.P[2] = (float*)(p + o2); t.P[3] = (float*)(p + o3);
     t.Y2 = (float*)(p + oy2); t.Y4 = (float*)(p + oy4); t.F = (float*)(p + of); t.fc_out = (float*)(p + oo);
+    t.Pb[0] = nullptr;
+    t.Pb[1] = lp ? (__nv_bfloat16*)(p + ob1) : nullptr; t.Pb[2] = lp ? (__nv_bfloat16*)(p + ob2) : nullptr;
+    t.Pb[3] = lp ? (__nv_bfloat16*)(p + ob3) : nullptr; t.Fb = lp ? (__nv_bfloat16*)(p + obf) : nullptr;
     *b = t;
   }
   return off;
 }
 // workspace: one frame-sized GEMM output / gradient pair at the largest geometry + flipped filter
-struct VggWs { float* Ya; float* Da; float* Ga; float* Wt; float* dz; };
+struct VggWs { float* Ya; float* Da; float* Ga; float* Wt; float* dz;
+               __nv_bfloat16* Dab; __nv_bfloat16* Wb; __nv_bfloat16* dzb; };
 static size_t vgg_ws_layout(const b2_vgg_desc* d, void* base, VggWs* w) {
   const Geo g0 = make_geo(d->N, d->H, d->W);
   const Geo g2 = make_geo(d->N, (d->H + 1) / 2, (d->W + 1) / 2);
@@ -246,10 +259,17 @@ static size_t vgg_ws_layout(const b2_vgg_desc* d, void* base, VggWs* w) {
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
   const size_t oa = take(big), od = take(big), og = take(big), ow = take((size_t)9 * 128 * 128 * 4);
   const size_t oz = take((size_t)d->N * 256 * 4);
+  const bool lp = d->precision == B2_PREC_BF16;
+  const Geo g4 = make_geo(d->N, (g2.H + 1) / 2, (g2.W + 1) / 2);
+  size_t wb = (size_t)9 * 128 * 128 * 2;                       // packed conv filter or the bridge weights
+  if ((size_t)g4.H * g4.W * 128 * 256 * 2 > wb) wb = (size_t)g4.H * g4.W * 128 * 256 * 2;
+  const size_t odb = lp ? take(big / 2) : 0, owb = lp ? take(wb) : 0, ozb = lp ? take((size_t)d->N * 256 * 2) : 0;
   if (w) {
     char* p = (char*)base;
     w->Ya = (float*)(p + oa); w->Da = (float*)(p + od); w->Ga = (float*)(p + og); w->Wt = (float*)(p + ow);
     w->dz = (float*)(p + oz);
+    w->Dab = lp ? (__nv_bfloat16*)(p + odb) : nullptr; w->Wb = lp ? (__nv_bfloat16*)(p + owb) : nullptr;
+    w->dzb = lp ? (__nv_bfloat16*)(p + ozb) : nullptr;
   }
   return off;
 }
@@ -278,6 +298,43 @@ static int conv_wgrad(const float* P, const Geo& g, int Cin, int Cout, const flo
     if (rc) return rc;
   }
   return B2_OK;
+}
+
+// filt [3][3][Cin][Cout] fp32 -> bf16 [3 kernel rows][kw*Cin][Cout] (only the centre column when the image is 1 wide)
+__global__ void __launch_bounds__(256)
+vgg_pack_filter_bf16_kernel(const float* __restrict__ filt, int Cin, int Cout, int kw, __nv_bfloat16* __restrict__ out) {
+  const int total = 3 * kw * Cin * Cout;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int co = i % Cout, r = i / Cout;                 // r = dh*(kw*Cin) + dw*Cin + ci
+    const int dh = r / (kw * Cin), q = r % (kw * Cin), dw = q / Cin, ci = q % Cin;
+    out[i] = __float2bfloat16(filt[(((size_t)dh * 3 + (kw == 3 ? dw : 1)) * Cin + ci) * Cout + co]);
+  }
+}
+
+// conv3x3 on tensor cores: ONE tcgen05 GEMM with K = 3*kw*Cin, A = the bf16 activation shadow read with the
+// per-kernel-row shift inside the TMA producer (gemm_bf16_tc_conv)
+static int conv_gemms_tc(const __nv_bfloat16* Pb, const Geo& g, int Cin, int Cout, const float* filt,
+                         __nv_bfloat16* Wb, float* Y, cudaStream_t stream) {
+  const int kw = g.pw ? 3 : 1;
+  vgg_pack_filter_bf16_kernel<<<ew_blocks((int64_t)3 * kw * Cin * Cout), 256, 0, stream>>>(filt, Cin, Cout, kw, Wb);
+  B2_LAUNCH_CHECK();
+  return gemm_bf16_tc_conv((int)g.M, Cout, kw * Cin, 3, g.Wp, Pb, g.rows, Cin, Wb, Cout, Y, Cout, stream);
+}
+// dfilt[dh] += A_dh^T . dYframe on tensor cores (split-K, fp32 atomics); Db = bf16 shadow of the gradient buffer
+static int conv_wgrad_tc(const __nv_bfloat16* Pb, const Geo& g, int Cin, int Cout, const __nv_bfloat16* Db,
+                         float* dfilt, cudaStream_t stream) {
+  const int kw = g.pw ? 3 : 1;
+  const __nv_bfloat16* dY = Db + (size_t)g.lead * Cout;
+  for (int dh = 0; dh < 3; ++dh) {
+    const __nv_bfloat16* A = Pb + (size_t)dh * g.Wp * Cin;
+    float* Cm = dfilt + (size_t)(dh * 3 + (g.pw ? 0 : 1)) * Cin * Cout;
+    int rc = gemm_bf16_tc(1, 1, kw * Cin, Cout, (int)g.M, 1.f, A, Cin, dY, Cout, Cm, Cout, nullptr, 1 /*atomic*/, 0, stream);
+    if (rc) return rc;
+  }
+  return B2_OK;
+}
+static int to_bf16(const float* src, int64_t n, __nv_bfloat16* dst, cudaStream_t stream) {
+  return cast_f32_bf16(src, 1, (int)n, (int)n, dst, (int)n, stream);
 }
 
 }  // namespace b2
@@ -320,19 +377,34 @@ extern "C" int b2_vgg_frontend_forward(const b2_vgg_desc* d, const float* x, con
   if ((rc = conv_gemms(b.P[0], g0, 3, 64, p->conv_w[0], w.Ya, stream))) return rc;
   vgg_epi_kernel<<<ew_blocks(g0.rows * 64), 256, 0, stream>>>(w.Ya, p->conv_b[0], g0, 64, keep, seed + 1, b.P[1]);
   B2_LAUNCH_CHECK();
-  if ((rc = conv_gemms(b.P[1], g0, 64, 64, p->conv_w[1], b.Y2, stream))) return rc;
+  const bool tc = d->precision == B2_PREC_BF16 && b2_device_is_sm100() == 1;
+  if (tc) {
+    if ((rc = to_bf16(b.P[1], g0.rows * 64, b.Pb[1], stream))) return rc;
+    if ((rc = conv_gemms_tc(b.Pb[1], g0, 64, 64, p->conv_w[1], w.Wb, b.Y2, stream))) return rc;
+  } else if ((rc = conv_gemms(b.P[1], g0, 64, 64, p->conv_w[1], b.Y2, stream))) return rc;
   vgg_epi_pool_kernel<<<ew_blocks(g2.rows * 64), 256, 0, stream>>>(b.Y2, p->conv_b[1], g0, g2, 64, keep, seed + 2, 0, b.P[2]);
   B2_LAUNCH_CHECK();
   // VGG2
-  if ((rc = conv_gemms(b.P[2], g2, 64, 128, p->conv_w[2], w.Ya, stream))) return rc;
+  if (tc) {
+    if ((rc = to_bf16(b.P[2], g2.rows * 64, b.Pb[2], stream))) return rc;
+    if ((rc = conv_gemms_tc(b.Pb[2], g2, 64, 128, p->conv_w[2], w.Wb, w.Ya, stream))) return rc;
+  } else if ((rc = conv_gemms(b.P[2], g2, 64, 128, p->conv_w[2], w.Ya, stream))) return rc;
   vgg_epi_kernel<<<ew_blocks(g2.rows * 128), 256, 0, stream>>>(w.Ya, p->conv_b[2], g2, 128, keep, seed + 3, b.P[3]);
   B2_LAUNCH_CHECK();
-  if ((rc = conv_gemms(b.P[3], g2, 128, 128, p->conv_w[3], b.Y4, stream))) return rc;
+  if (tc) {
+    if ((rc = to_bf16(b.P[3], g2.rows * 128, b.Pb[3], stream))) return rc;
+    if ((rc = conv_gemms_tc(b.Pb[3], g2, 128, 128, p->conv_w[3], w.Wb, b.Y4, stream))) return rc;
+  } else if ((rc = conv_gemms(b.P[3], g2, 128, 128, p->conv_w[3], b.Y4, stream))) return rc;
   const int64_t nf = (int64_t)d->N * g4.H * g4.W * 128;
   vgg_epi_pool_kernel<<<ew_blocks(nf), 256, 0, stream>>>(b.Y4, p->conv_b[3], g2, g4, 128, keep, seed + 4, 1, b.F);
   B2_LAUNCH_CHECK();
   // bridge FC 256 + ReLU + dropout
   const int Kf = g4.H * g4.W * 128;
+  if (tc && Kf % 8 == 0) {
+    if ((rc = to_bf16(b.F, nf, b.Fb, stream))) return rc;
+    if ((rc = to_bf16(p->fc_w, (int64_t)Kf * 256, w.Wb, stream))) return rc;
+    if ((rc = gemm_bf16_tc(0, 1, d->N, 256, Kf, 1.f, b.Fb, Kf, w.Wb, 256, b.fc_out, 256, p->fc_b, 0 /*store*/, 0, stream))) return rc;
+  } else
   if ((rc = gemm_simt(0, 0, d->N, 256, Kf, 1.f, b.F, Kf, p->fc_w, 256, 0.f, b.fc_out, 256, p->fc_b, stream))) return rc;
   vgg_fc_epi_kernel<<<ew_blocks((int64_t)d->N * 256), 256, 0, stream>>>(b.fc_out, (int64_t)d->N * 256, keep, seed + 5);
   B2_LAUNCH_CHECK();
@@ -357,34 +429,57 @@ extern "C" int b2_vgg_frontend_backward(const b2_vgg_desc* d, const b2_vgg_param
   // FC
   vgg_fc_epi_bwd_kernel<<<ew_blocks((int64_t)N * 256), 256, 0, stream>>>(d_out, b.fc_out, (int64_t)N * 256, keep, w.dz);
   B2_LAUNCH_CHECK();
-  if ((rc = gemm_simt(1, 0, Kf, 256, N, 1.f, b.F, Kf, w.dz, 256, 1.f, gr->fc_w, 256, nullptr, stream))) return rc;
-  if ((rc = b2_colsum(w.dz, N, 256, 256, gr->fc_b, 1, stream_))) return rc;
+  const bool tc = d->precision == B2_PREC_BF16 && b2_device_is_sm100() == 1;
   float* dF = w.Ga;                                           // dense [N, Kf]
-  if ((rc = gemm_simt(0, 1, N, Kf, 256, 1.f, w.dz, 256, p->fc_w, 256, 0.f, dF, Kf, nullptr, stream))) return rc;
+  if (tc && Kf % 8 == 0) {
+    if ((rc = to_bf16(w.dz, (int64_t)N * 256, w.dzb, stream))) return rc;
+    if ((rc = gemm_bf16_tc(1, 1, Kf, 256, N, 1.f, b.Fb, Kf, w.dzb, 256, gr->fc_w, 256, nullptr, 1 /*atomic*/, 0, stream))) return rc;
+    if ((rc = to_bf16(p->fc_w, (int64_t)Kf * 256, w.Wb, stream))) return rc;
+    if ((rc = gemm_bf16_tc(0, 0, N, Kf, 256, 1.f, w.dzb, 256, w.Wb, 256, dF, Kf, nullptr, 0 /*store*/, 0, stream))) return rc;
+  } else {
+    if ((rc = gemm_simt(1, 0, Kf, 256, N, 1.f, b.F, Kf, w.dz, 256, 1.f, gr->fc_w, 256, nullptr, stream))) return rc;
+    if ((rc = gemm_simt(0, 1, N, Kf, 256, 1.f, w.dz, 256, p->fc_w, 256, 0.f, dF, Kf, nullptr, stream))) return rc;
+  }
+  if ((rc = b2_colsum(w.dz, N, 256, 256, gr->fc_b, 1, stream_))) return rc;
   // conv2_2 (pooled, dense output)
   vgg_epi_pool_bwd_kernel<<<ew_blocks(g2.rows * 128), 256, 0, stream>>>(dF, b.F, b.Y4, p->conv_b[3], g2, g4, 128, keep, 1, w.Da);
   B2_LAUNCH_CHECK();
   if ((rc = b2_colsum(w.Da + (size_t)g2.lead * 128, g2.M, 128, 128, gr->conv_b[3], 1, stream_))) return rc;
-  if ((rc = conv_wgrad(b.P[3], g2, 128, 128, w.Da, gr->conv_w[3], stream))) return rc;
+  if (tc) { if ((rc = to_bf16(w.Da, g2.rows * 128, w.Dab, stream))) return rc; }
+  if (tc) rc = conv_wgrad_tc(b.Pb[3], g2, 128, 128, w.Dab, gr->conv_w[3], stream);
+  else rc = conv_wgrad(b.P[3], g2, 128, 128, w.Da, gr->conv_w[3], stream);
+  if (rc) return rc;
   vgg_flip_filter_kernel<<<ew_blocks(9 * 128 * 128), 256, 0, stream>>>(p->conv_w[3], 128, 128, w.Wt);
   B2_LAUNCH_CHECK();
-  if ((rc = conv_gemms(w.Da, g2, 128, 128, w.Wt, w.Ga, stream))) return rc;      // d(P3 valid), frame of g2
+  if (tc) rc = conv_gemms_tc(w.Dab, g2, 128, 128, w.Wt, w.Wb, w.Ga, stream);
+  else rc = conv_gemms(w.Da, g2, 128, 128, w.Wt, w.Ga, stream);                   // d(P3 valid), frame of g2
+  if (rc) return rc;
   // conv2_1
   vgg_epi_bwd_kernel<<<ew_blocks(g2.rows * 128), 256, 0, stream>>>(w.Ga, b.P[3], g2, 128, keep, w.Da);
   B2_LAUNCH_CHECK();
   if ((rc = b2_colsum(w.Da + (size_t)g2.lead * 128, g2.M, 128, 128, gr->conv_b[2], 1, stream_))) return rc;
-  if ((rc = conv_wgrad(b.P[2], g2, 64, 128, w.Da, gr->conv_w[2], stream))) return rc;
+  if (tc) { if ((rc = to_bf16(w.Da, g2.rows * 128, w.Dab, stream))) return rc; }
+  if (tc) rc = conv_wgrad_tc(b.Pb[2], g2, 64, 128, w.Dab, gr->conv_w[2], stream);
+  else rc = conv_wgrad(b.P[2], g2, 64, 128, w.Da, gr->conv_w[2], stream);
+  if (rc) return rc;
   vgg_flip_filter_kernel<<<ew_blocks(9 * 64 * 128), 256, 0, stream>>>(p->conv_w[2], 64, 128, w.Wt);
   B2_LAUNCH_CHECK();
-  if ((rc = conv_gemms(w.Da, g2, 128, 64, w.Wt, w.Ga, stream))) return rc;       // d(P2 valid), frame of g2
+  if (tc) rc = conv_gemms_tc(w.Dab, g2, 128, 64, w.Wt, w.Wb, w.Ga, stream);
+  else rc = conv_gemms(w.Da, g2, 128, 64, w.Wt, w.Ga, stream);                    // d(P2 valid), frame of g2
+  if (rc) return rc;
   // conv1_2 (pooled into g2)
   vgg_epi_pool_bwd_kernel<<<ew_blocks(g0.rows * 64), 256, 0, stream>>>(w.Ga, b.P[2], b.Y2, p->conv_b[1], g0, g2, 64, keep, 0, w.Da);
   B2_LAUNCH_CHECK();
   if ((rc = b2_colsum(w.Da + (size_t)g0.lead * 64, g0.M, 64, 64, gr->conv_b[1], 1, stream_))) return rc;
-  if ((rc = conv_wgrad(b.P[1], g0, 64, 64, w.Da, gr->conv_w[1], stream))) return rc;
+  if (tc) { if ((rc = to_bf16(w.Da, g0.rows * 64, w.Dab, stream))) return rc; }
+  if (tc) rc = conv_wgrad_tc(b.Pb[1], g0, 64, 64, w.Dab, gr->conv_w[1], stream);
+  else rc = conv_wgrad(b.P[1], g0, 64, 64, w.Da, gr->conv_w[1], stream);
+  if (rc) return rc;
   vgg_flip_filter_kernel<<<ew_blocks(9 * 64 * 64), 256, 0, stream>>>(p->conv_w[1], 64, 64, w.Wt);
   B2_LAUNCH_CHECK();
-  if ((rc = conv_gemms(w.Da, g0, 64, 64, w.Wt, w.Ga, stream))) return rc;        // d(P1 valid), frame of g0
+  if (tc) rc = conv_gemms_tc(w.Dab, g0, 64, 64, w.Wt, w.Wb, w.Ga, stream);
+  else rc = conv_gemms(w.Da, g0, 64, 64, w.Wt, w.Ga, stream);                     // d(P1 valid), frame of g0
+  if (rc) return rc;
   // conv1_1 (no data gradient: the input is the feature matrix)
   vgg_epi_bwd_kernel<<<ew_blocks(g0.rows * 64), 256, 0, stream>>>(w.Ga, b.P[1], g0, 64, keep, w.Da);
   B2_LAUNCH_CHECK();

@@ -76,7 +76,8 @@ class VGGBLSTMEncoder(object):
         W = self.splice * self.num_stack
         assert D == self.num_channels * W * 3                          # vgg_blstm.py:106
         desc = ops.vgg_desc(B * T, self.num_channels, W, keep_prob=float(keep_prob),
-                            dropout_seed=(dropout_seed * 977 + 13) * 8)
+                            dropout_seed=(dropout_seed * 977 + 13) * 8,
+                            precision=ops.PREC_BF16 if getattr(self, "precision", "fp32") == "bf16" else ops.PREC_FP32)
         # [B,T,D] -> [B*T, num_channels, W, 3] is a pure reshape (:108-110)
         feat, reserve = ops.vgg_frontend_forward(desc, inputs.contiguous(), self._vgg_params(variables))
         outputs, final_state = self.blstm(feat.view(B, T, 256), inputs_seq_len, keep_prob, is_training,

@@ -206,10 +206,21 @@ class ModelBase(object):
                 self.optimizer.load_state(restored)
             self._restored_optimizer_state = None
         self.optimizer._towers_out = 0
-        grads_and_vars = self.optimizer._compute_gradients(loss)
-        if self.clip_grad_norm is not None or self.world_size > 1:
-            grads_and_vars = self._clip_gradients(grads_and_vars)
-        self._allreduce_gradients()
+        # bucket mode needs every gradient outside the BLSTM layers final BEFORE the encoder's backward pass starts:
+        # the plain BLSTM-CTC model without a weight-decay term (added at the end of _backward) qualifies
+        bucketed = self.world_size > 1 and self._comm is not None and getattr(self, "bucketed_exchange", True) \
+            and type(self).__name__ == "CTC" and getattr(self, "encoder_type", "") == "blstm" \
+            and not getattr(self, "weight_decay", 0)
+        if bucketed:
+            # clip + mean per layer bucket, issued while BPTT of the layers below still runs
+            self._bucketed_exchange_begin()
+            grads_and_vars = self.optimizer._compute_gradients(loss)
+            self._bucketed_exchange_end()
+        else:
+            grads_and_vars = self.optimizer._compute_gradients(loss)
+            if self.clip_grad_norm is not None or self.world_size > 1:
+                grads_and_vars = self._clip_gradients(grads_and_vars)
+            self._allreduce_gradients()
         self.optimizer._apply_gradients(grads_and_vars, learning_rate)
         return self.optimizer
 
@@ -223,6 +234,67 @@ class ModelBase(object):
         self.world_size, self._group, self._comm = int(world_size), group, comm
         if world_size > 1 and broadcast:
             dist.broadcast(self.flat_params, src=0, group=group)
+
+    # ---- per-layer gradient buckets (clip per tensor locally, then mean over ranks), overlapped with BPTT
+    def _bucket_plan(self):
+        """[(first variable index, last+1)] per BLSTM layer (variables of a layer are contiguous in the flat buffer),
+        plus one bucket for everything else (heads)."""
+        if getattr(self, "_buckets", None) is None:
+            import re
+            groups, other = {}, []
+            for i, v in enumerate(self._variables):
+                m = re.match(r"blstm_hidden(\d+)/", v.name)
+                (groups.setdefault(int(m.group(1)), []) if m else other).append(i)
+            plan = {}
+            for key, idx in list(groups.items()) + [(0, other)]:
+                if not idx:
+                    continue
+                vs = [self._variables[i] for i in idx]
+                base = self.flat_grads.data_ptr()
+                lo = min((v.grad.data_ptr() - base) // 4 for v in vs)
+                hi = max((v.grad.data_ptr() - base) // 4 + (v.grad.numel() + 3) // 4 * 4 for v in vs)
+                plan[key] = (self.flat_grads[lo:hi], ops.TensorList([v.grad for v in vs]))
+            self._buckets = plan
+            self._comm_stream = torch.cuda.Stream(device=self.flat_grads.device)
+            self._comm_done = torch.cuda.Event()
+        return self._buckets
+
+    def _reduce_bucket(self, key, stream):
+        """per-tensor clip of bucket `key`, then its mean over the ranks, on `stream`"""
+        flat, tl = self._bucket_plan()[key]
+        with torch.cuda.stream(stream):
+            if self.clip_grad_norm is not None:
+                ops.clip_by_norm_multi(tl, self.clip_grad_norm, post_scale=1.0)
+            self._comm.allreduce_mean_([flat], stream=stream)
+        self._reduced.add(key)
+
+    def _bucketed_exchange_begin(self):
+        """call right before the encoder's backward pass: the head bucket is final already"""
+        self._bucket_plan()
+        self._reduced = set()
+        cur = torch.cuda.current_stream()
+        self._comm_stream.wait_stream(cur)
+        if 0 in self._buckets:
+            self._reduce_bucket(0, self._comm_stream)
+
+        def on_layer_done(i_layer):
+            # layer i_layer+1's weight gradients were enqueued on the library's side stream during this call
+            j = i_layer + 1
+            if j in self._buckets and j not in self._reduced:
+                ops.blstm_backward_side_wait(self._comm_stream)
+                self._comm_stream.wait_stream(torch.cuda.current_stream())    # bias / peephole sums of layer j
+                self._reduce_bucket(j, self._comm_stream)
+        self._on_layer_done = on_layer_done
+
+    def _bucketed_exchange_end(self):
+        """after the backward pass (side stream joined): the remaining buckets, then wait for all of them"""
+        cur = torch.cuda.current_stream()
+        for key in sorted(self._buckets, reverse=True):
+            if key not in self._reduced:
+                self._reduce_bucket(key, cur)
+        self._comm_done.record(self._comm_stream)
+        cur.wait_event(self._comm_done)
+        self._on_layer_done = None
 
     def _allreduce_gradients(self):
         if self.world_size <= 1:

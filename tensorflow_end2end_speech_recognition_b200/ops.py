@@ -337,6 +337,12 @@ def blstm_backward_join():
     _lib.check(_lib.load().b2_blstm_backward_join(_stream()), "b2_blstm_backward_join")
 
 
+def blstm_backward_side_wait(stream=None):
+    """`stream` (default: current) waits for the side-stream weight-gradient GEMMs enqueued so far."""
+    s = C.c_void_p(stream.cuda_stream) if stream is not None else _stream()
+    _lib.check(_lib.load().b2_blstm_backward_side_wait(s), "b2_blstm_backward_side_wait")
+
+
 def reserve_y_lp(desc, reserve):
     """raw device pointer (int) of the bf16 layer output kept in `reserve`, or 0."""
     if reserve is None:

@@ -25,12 +25,13 @@ def make_params(rng, H, W, scale=0.15):
     return p
 
 
-def run_gpu(cuda, x, p, H, W, keep, seed, d_out):
+def run_gpu(cuda, x, p, H, W, keep, seed, d_out, precision=None):
     from tensorflow_end2end_speech_recognition_b200 import ops
     N = x.shape[0] * x.shape[1]
     pc = {k: torch.tensor(v, device=cuda) for k, v in p.items()}
     gc = {k: torch.zeros_like(v) for k, v in pc.items()}
-    desc = ops.vgg_desc(N, H, W, keep_prob=keep, dropout_seed=seed)
+    desc = ops.vgg_desc(N, H, W, keep_prob=keep, dropout_seed=seed,
+                        precision=ops.PREC_FP32 if precision is None else precision)
     out, reserve = ops.vgg_frontend_forward(desc, torch.tensor(x, device=cuda), pc)
     ops.vgg_frontend_backward(desc, pc, torch.tensor(d_out, device=cuda).view(N, 256), reserve, gc)
     torch.cuda.synchronize()
@@ -113,3 +114,33 @@ def test_vgg_blstm_ctc_model(cuda):
     model.train(loss, "adam", 1e-2)
     loss2, _ = model.compute_loss(x, labels, seq, keep_prob=1.0, is_training=False)
     assert float(loss2) < float(loss)
+
+
+@pytest.mark.parametrize("H,W", [(8, 1), (13, 1), (20, 1), (7, 3), (10, 2)])
+def test_frontend_bf16_tensor_core_path(cuda, H, W):
+    """precision bf16: conv 64/128-channel layers and the bridge FC on tcgen05 (one GEMM per convolution, the
+    kernel-row shift applied inside the TMA producer), operands rounded to bf16 -> bf16 tolerance vs the fp64 oracle;
+    enough frames that the GEMM has several M tiles"""
+    from tensorflow_end2end_speech_recognition_b200 import ops
+    rng = np.random.RandomState(H * 10 + W + 100)
+    B, T = 4, 40
+    x = rng.randn(B, T, H * W * 3).astype(np.float32)
+    p = make_params(rng, H, W)
+    d_out = rng.randn(B, T, 256).astype(np.float32)
+    out, g = run_gpu(cuda, x, p, H, W, 1.0, 0, d_out, precision=ops.PREC_BF16)
+    out_ref, g_ref = run_oracle(x, p, H, W, 1.0, None, d_out)
+    err = np.linalg.norm(out.reshape(B, T, 256) - out_ref) / np.linalg.norm(out_ref)
+    assert err < 1.5e-2, err
+    # Gradients: bf16 rounding of the forward activations flips a small fraction of the ReLU / max-pool routing
+    # decisions against the exact forward pass, and each flip moves a whole gradient entry -- the relative L2 error of
+    # the early layers' gradients is therefore ~sqrt(fraction flipped), about 10 % for conv1 (measured 8-11 %), while
+    # the layers next to the output stay at the bf16 operand level.
+    errs = {}
+    for k in p:
+        e = np.linalg.norm(g[k] - g_ref[k]) / max(np.linalg.norm(g_ref[k]), 1e-30)
+        if W == 1 and k.endswith("/weight") and g_ref[k].ndim == 4:
+            e = np.linalg.norm(g[k][:, 1] - g_ref[k][:, 1]) / max(np.linalg.norm(g_ref[k][:, 1]), 1e-30)
+        errs[k] = float(e)
+    print("\n[vgg bf16 H=%d W=%d] output rel-L2 %.4f, gradient rel-L2 %s" % (H, W, err, {k: round(v, 4) for k, v in errs.items()}))
+    assert errs["bridge/weights"] < 3e-2 and errs["bridge/biases"] < 3e-2, errs
+    assert max(errs.values()) < 0.2, errs

@@ -21,16 +21,19 @@ def main():
     N = B * T
     x = torch.randn(N, H * W * 3, device=dev)
     d_out = torch.randn(N, 256, device=dev)
-    desc = ops.vgg_desc(N, H, W, keep_prob=0.8, dropout_seed=1)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    for it in range(4):
-        ev[0].record()
-        out, reserve = ops.vgg_frontend_forward(desc, x, p)
-        ev[1].record()
-        ops.vgg_frontend_backward(desc, p, d_out, reserve, g)
-        ev[2].record()
-        torch.cuda.synchronize()
-        print("N=%d fwd %.2f ms  bwd %.2f ms" % (N, ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])))
+    for name, prec in (("fp32 CUDA-core", ops.PREC_FP32), ("bf16 tcgen05", ops.PREC_BF16)):
+        desc = ops.vgg_desc(N, H, W, keep_prob=0.8, dropout_seed=1, precision=prec)
+        for it in range(4):
+            ev[0].record()
+            out, reserve = ops.vgg_frontend_forward(desc, x, p)
+            ev[1].record()
+            ops.vgg_frontend_backward(desc, p, d_out, reserve, g)
+            ev[2].record()
+            torch.cuda.synchronize()
+            print("%-15s N=%d fwd %.2f ms  bwd %.2f ms" % (name, N, ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])),
+                  flush=True)
+        del out, reserve
     flops_fwd = N * (80 * (3 * 3 * 64 + 3 * 64 * 64) + 40 * (3 * 64 * 128 + 3 * 128 * 128) + 2560 * 256) * 2
     print("algorithmic fwd GFLOP %.1f (non-padding taps)" % (flops_fwd / 1e9))
 
