@@ -26,6 +26,7 @@ struct Work {
   float* hstate;   // [2 parity][2 dir][B][H]
   float* cstate;   // [2 dir][B][H]   (fwd: c ; bwd: dc)
   float* zrec;     // [2 dir][B][4H]  recurrent pre-activations / dh of one step (wide-H path)
+  void* wide;      // exchange buffer + barrier counters of the grid-resident wide-layer recurrence (lstm_wide.cu)
   float* mcur;     // [2 dir][B][H]   projection mode: o*tanh(c) of the frame (fwd) / d(o*tanh(c)) (bwd)
   float* hpnew;    // [2 dir][B][P]   projection mode: projected h of the frame (fwd) / its gradient (bwd)
   float* dhp_all;  // [T*B][2P]       projection mode, backward: d(projected h) of every frame
@@ -46,6 +47,7 @@ static size_t work_layout(const b2_lstm_desc* d, void* base, Work* w) {
   const size_t om = Pw ? take((size_t)2 * d->B * d->H * sizeof(float)) : 0;
   const size_t ohn = Pw ? take((size_t)2 * d->B * Pw * sizeof(float)) : 0;
   const size_t oda = Pw ? take(TB * 2 * Pw * sizeof(float)) : 0;
+  const size_t owide = take(wide_rec_workspace_bytes(d));
   size_t oxb = 0, owb = 0, ogb = 0;
   if (d->precision == B2_PREC_BF16) {
     const size_t din = pad8z((size_t)(d->D_in > 2 * d->H ? d->D_in : 2 * d->H));
@@ -56,7 +58,7 @@ static size_t work_layout(const b2_lstm_desc* d, void* base, Work* w) {
   if (w) {
     char* p = (char*)base;
     w->G = (float*)(p + oG); w->hstate = (float*)(p + oh); w->cstate = (float*)(p + oc);
-    w->zrec = (float*)(p + oz);
+    w->zrec = (float*)(p + oz); w->wide = (void*)(p + owide);
     w->mcur = Pw ? (float*)(p + om) : nullptr; w->hpnew = Pw ? (float*)(p + ohn) : nullptr;
     w->dhp_all = Pw ? (float*)(p + oda) : nullptr;
     w->xb = (__nv_bfloat16*)(p + oxb); w->wb = (__nv_bfloat16*)(p + owb);
@@ -591,6 +593,8 @@ extern "C" int b2_blstm_layer_forward(const b2_lstm_desc* d, const float* x, con
     if (rc) return rc;
   }
   // 2. recurrence
+  if (wide_rec_supported(d))        // wide layer (config 4: H = 1024): ONE cooperative launch, weights register-resident
+    return wide_rec_forward(d, fw, bw, seq_len, w.G, y, r.gates, r.cs, r.hs, final_state, w.wide, stream);
   B2_CUDA(cudaMemsetAsync(w.hstate, 0, (size_t)2 * 2 * B * H * sizeof(float), stream));
   B2_CUDA(cudaMemsetAsync(w.cstate, 0, (size_t)2 * B * H * sizeof(float), stream));
   StepArgs a;

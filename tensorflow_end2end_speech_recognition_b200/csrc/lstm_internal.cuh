@@ -105,6 +105,13 @@ int tc_layer_backward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16
                       const b2_lstm_grads* g_bw, void* workspace, size_t workspace_bytes,
                       cudaStream_t stream);
 
+// grid-resident recurrence for wide layers (lstm_wide.cu)
+bool wide_rec_supported(const b2_lstm_desc* d);
+size_t wide_rec_workspace_bytes(const b2_lstm_desc* d);
+int wide_rec_forward(const b2_lstm_desc* d, const b2_lstm_params* fw, const b2_lstm_params* bw, const int32_t* seq_len,
+                     const float* G, float* y, float* gates, float* cs, float* hs, float* final_state, void* workspace,
+                     cudaStream_t stream);
+
 int tc_backward_join(cudaStream_t stream);
 int tc_backward_side_wait(cudaStream_t stream);
 void tc_profile_enable(int on);

@@ -1,0 +1,272 @@
+// Grid-resident BLSTM recurrence for wide layers (512 < H <= 1024, BASELINE config 4: 6 x 1024) on sm_100a.
+//
+// The cluster/TMEM recurrence of lstm_rec_tc.cu keeps one direction's recurrent weights inside a 16-CTA cluster; at
+// H = 1024 the bf16 matrix is 8 MB and does not fit, and the fallback (one split-K skinny GEMM + one gate kernel PER
+// FRAME, lstm.cu) costs ~45 us per frame, L2-bound on 32 MB of fp32 weights and launch-bound.  Here the whole layer
+// forward is ONE cooperative launch (same op as before: LSTMBlockCell under tf.nn.bidirectional_dynamic_rnn,
+// models/encoders/core/blstm.py:287-320):
+//
+//   * grid = 2 directions x H/16 CTAs, all co-resident (cooperative launch; <= 148 SMs);
+//   * CTA j of a direction owns 16 hidden units = 64 gate rows; its bf16 slice of Wh (64 x H = 128 KB at H = 1024)
+//     lives in REGISTERS for the whole sequence as mma.sync A fragments (8 warps = 4 gates x 2 K halves,
+//     H/8 = 128 registers per thread) -- the per-step GEMM [64 x H] . [H x B] streams only h_{t-1} (B <= 32 rows of
+//     bf16, 64 KB) from shared memory;
+//   * h_t travels through L2: every CTA writes its 16 columns of the [B, H] bf16 exchange buffer (double-buffered by
+//     step parity), then one grid barrier per direction and step (release: __threadfence + atomicAdd; acquire:
+//     ld.acquire spin) -- about 2 us, the cost this design accepts in exchange for having all SMs hold weights;
+//   * the two K-half partial sums meet in shared memory, then 256 threads do the gate math for 16 units x 32 batch rows
+//     (2 cells per thread, fp32, cell state in registers), emit y / the fp32 reserve the BPTT kernels read.
+//
+// tcgen05 is not used here on purpose: the step GEMM is M = 64 rows per SM with the weights stationary; with A in TMEM
+// the 64 x 1024 slice would take all 512 columns and leave no accumulator, and an SS-mode MMA would re-read 128 KB of
+// weights from shared memory every step.  mma.sync with register-resident A reads only h.
+#include "lstm_internal.cuh"
+#include <cooperative_groups.h>
+
+namespace b2 {
+
+constexpr int WU = 16;            // units per CTA
+constexpr int WB = 32;            // batch rows per launch (mma N = 4 tiles of 8)
+constexpr int WTHREADS = 256;
+constexpr int WPP = 34;           // pitch of the partial-sum tiles (floats)
+
+struct WideFwdArgs {
+  int T, B, D_in, H;
+  int use_peephole; float forget_bias, cell_clip, keep_prob; unsigned long long seed;
+  const float* kernel[2]; const float* wi[2]; const float* wf[2]; const float* wo[2];
+  const int* seq_len;
+  const float* G;                 // [T*B, 8H] fp32, column = dir*4H + gate*H + u (TF order), bias included
+  float* y;                       // [T,B,2H]
+  float* gates; float* cs; float* hs;   // fp32 reserve ([T,B,2,H,4], [T,B,2,H], [T,B,2,H]) or null
+  float* final_state;             // [4,B,H] (c_fw, h_fw, c_bw, h_bw) or null
+  __nv_bfloat16* hx;              // exchange buffer [2 dir][2 parity][WB][H]
+  unsigned* bar;                  // [2] grid-barrier counters (zeroed before the launch)
+};
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *(uint32_t*)&v;
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// KSH = k-steps (of 16) per K half = H / 32
+template <int KSH>
+__global__ void __launch_bounds__(WTHREADS, 1)
+lstm_wide_fwd_kernel(const WideFwdArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int H = a.H, B = a.B, T = a.T;
+  const int HP = H + 8;                                   // bf16 row pitch of the h tile: conflict-free fragment loads
+  __nv_bfloat16* hbuf = (__nv_bfloat16*)smem_raw;          // [WB][HP]
+  float* part = (float*)(smem_raw + (size_t)WB * HP * 2);  // [2 K halves][64 rows][WPP]
+  const int NS = H / WU;
+  const int dir = blockIdx.x / NS, slice = blockIdx.x % NS;
+  const int u0 = slice * WU;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mt = warp & 3, kh = warp >> 2;                 // m-tile = gate (16 unit rows), K half
+  const int fr = lane >> 2, fc = lane & 3;                 // fragment row / column-pair index
+
+  // ---- this warp's weight fragments: A[row = unit][k] = Wh[k][gate*H + u0 + unit], gate = mt, k in this K half
+  uint32_t afrag[KSH][4];
+  {
+    const float* col0 = a.kernel[dir] + (size_t)a.D_in * 4 * H + (size_t)mt * H + u0;       // + k*4H + unit
+#pragma unroll
+    for (int ks = 0; ks < KSH; ++ks) {
+      const int k0 = kh * (KSH * 16) + ks * 16 + 2 * fc;
+      afrag[ks][0] = pack_bf16(col0[(size_t)k0 * 4 * H + fr], col0[(size_t)(k0 + 1) * 4 * H + fr]);
+      afrag[ks][1] = pack_bf16(col0[(size_t)k0 * 4 * H + fr + 8], col0[(size_t)(k0 + 1) * 4 * H + fr + 8]);
+      afrag[ks][2] = pack_bf16(col0[(size_t)(k0 + 8) * 4 * H + fr], col0[(size_t)(k0 + 9) * 4 * H + fr]);
+      afrag[ks][3] = pack_bf16(col0[(size_t)(k0 + 8) * 4 * H + fr + 8], col0[(size_t)(k0 + 9) * 4 * H + fr + 8]);
+    }
+  }
+  // ---- gate-math ownership: unit ul = tid & 15, batch rows bq and bq + 16
+  const int ul = tid & 15, bq = tid >> 4;
+  const int u = u0 + ul;
+  int len[2]; float cst[2], hst[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int b = bq + 16 * j;
+    len[j] = b < B ? a.seq_len[b] : 0;
+    cst[j] = 0.f; hst[j] = 0.f;
+  }
+  float pwi = 0.f, pwf = 0.f, pwo = 0.f;
+  if (a.use_peephole) { pwi = a.wi[dir][u]; pwf = a.wf[dir][u]; pwo = a.wo[dir][u]; }
+  __nv_bfloat16* hx_dir = a.hx + (size_t)dir * 2 * WB * H;
+  unsigned* bar = a.bar + dir;
+
+  for (int s = 0; s < T; ++s) {
+    const int td = dir ? T - 1 - s : s;
+    // G_t for this thread's two cells (independent of h: in flight while the barrier is awaited)
+    float z[2][4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int b = bq + 16 * j;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        z[j][g] = b < B ? __ldg(a.G + ((size_t)td * B + b) * 8 * H + (size_t)dir * 4 * H + (size_t)g * H + u) : 0.f;
+    }
+
+    if (s > 0) {
+      // ---- every CTA of this direction has published h_{s-1}
+      if (tid == 0) {
+        const unsigned want = (unsigned)NS * (unsigned)s;
+        while (ld_acquire_u32(bar) < want) {}
+      }
+      __syncthreads();
+      // h_{s-1} [B, H] bf16 from L2 (cache-global loads: the lines were written by other SMs) into the padded tile
+      {
+        const uint4* src = (const uint4*)(hx_dir + (size_t)((s - 1) & 1) * WB * H);
+        const int vec_per_row = H / 8;
+        for (int i = tid; i < WB * vec_per_row; i += WTHREADS) {
+          const int r = i / vec_per_row, cvec = i - r * vec_per_row;
+          const uint4 v = __ldcg(src + (size_t)r * vec_per_row + cvec);
+          *(uint4*)(hbuf + (size_t)r * HP + cvec * 8) = v;
+        }
+      }
+      __syncthreads();
+      // ---- z_rec[64 x 32] = Wslice . h^T : this warp = the 16 rows of gate mt x K half kh x all 32 batch columns
+      float acc[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KSH; ++ks) {
+        const int k0 = kh * (KSH * 16) + ks * 16 + 2 * fc;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const __nv_bfloat16* hp = hbuf + (size_t)(nt * 8 + fr) * HP + k0;
+          mma_bf16_16816(acc[nt], afrag[ks], *(const uint32_t*)hp, *(const uint32_t*)(hp + 8));
+        }
+      }
+      // partial sums of this K half: part[kh][gate*16 + unit][batch]
+      {
+        float* pr = part + ((size_t)kh * 64 + mt * 16) * WPP;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          *(float2*)(pr + (size_t)fr * WPP + nt * 8 + 2 * fc) = make_float2(acc[nt][0], acc[nt][1]);
+          *(float2*)(pr + (size_t)(fr + 8) * WPP + nt * 8 + 2 * fc) = make_float2(acc[nt][2], acc[nt][3]);
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          z[j][g] += part[((size_t)g * 16 + ul) * WPP + bq + 16 * j] +
+                     part[((size_t)64 + g * 16 + ul) * WPP + bq + 16 * j];
+    }
+    // ---- gate math (models/recurrent/layers/lstm.py:142-183: i, g(ci), f, o; forget bias; peepholes; clip)
+    __nv_bfloat16* hx_out = hx_dir + (size_t)(s & 1) * WB * H;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int b = bq + 16 * j;
+      const bool active = td < len[j];
+      const float c_prev = cst[j];
+      float gi = 0.f, gg = 0.f, gf = 0.f, go = 0.f, h_out = 0.f, c_new = c_prev;
+      if (active) {
+        float zi = z[j][0], zg = z[j][1], zf = z[j][2] + a.forget_bias, zo = z[j][3];
+        zi = fmaf(pwi, c_prev, zi); zf = fmaf(pwf, c_prev, zf);
+        gi = sigmoidf_(zi); gg = tanhf_(zg); gf = sigmoidf_(zf);
+        c_new = fmaf(gf, c_prev, gi * gg);
+        if (a.cell_clip > 0.f) c_new = fminf(fmaxf(c_new, -a.cell_clip), a.cell_clip);
+        zo = fmaf(pwo, c_new, zo);
+        go = sigmoidf_(zo);
+        h_out = go * tanhf_(c_new);
+        cst[j] = c_new; hst[j] = h_out;
+      }
+      // the carried state h feeds the next step's product (inactive rows keep their last state)
+      hx_out[(size_t)b * H + u] = __float2bfloat16(hst[j]);
+      if (b < B) {
+        const size_t row = (size_t)td * B + b;
+        const size_t oidx = row * 2 * H + (size_t)dir * H + u;
+        float yv = h_out;
+        if (a.keep_prob < 1.f && active) yv = dropout_keep(a.seed, oidx, a.keep_prob) ? h_out / a.keep_prob : 0.f;
+        a.y[oidx] = yv;
+        if (a.gates) {
+          const size_t cell = (row * 2 + dir) * H + u;
+          *(float4*)(a.gates + cell * 4) = make_float4(gi, gg, gf, go);
+          a.cs[cell] = cst[j];
+          a.hs[cell] = h_out;
+        }
+      }
+    }
+    // ---- publish: every thread's stores are fenced, then one arrival per CTA
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) atomicAdd(bar, 1u);
+  }
+  if (a.final_state) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int b = bq + 16 * j;
+      if (b < B) {
+        a.final_state[((size_t)(dir * 2 + 0) * B + b) * H + u] = cst[j];
+        a.final_state[((size_t)(dir * 2 + 1) * B + b) * H + u] = hst[j];
+      }
+    }
+  }
+}
+
+bool wide_rec_supported(const b2_lstm_desc* d) {
+  if (d->precision != B2_PREC_BF16 || d->num_proj > 0) return false;
+  if (!env_int("B2_WIDE_REC", 1)) return false;
+  const int H = d->H;
+  if (H <= 512 || H > 1024 || (H % 128) != 0) return false;          // KSH = H/32 in {20,24,28,32}: 640 768 896 1024
+  if (d->B > WB) return false;
+  if (2 * (H / WU) > num_sms()) return false;
+  return b2_device_is_sm100() == 1;
+}
+
+size_t wide_rec_workspace_bytes(const b2_lstm_desc* d) {
+  return align_up((size_t)2 * 2 * WB * d->H * 2, 256) + 256;          // exchange buffer + barrier counters
+}
+
+template <int KSH>
+static int launch_wide_fwd(WideFwdArgs& a, cudaStream_t stream) {
+  const size_t smem = (size_t)WB * (a.H + 8) * 2 + (size_t)2 * 64 * WPP * 4;
+  auto kern = lstm_wide_fwd_kernel<KSH>;
+  B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void* params[] = {(void*)&a};
+  B2_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(2 * (a.H / WU)), dim3(WTHREADS), params, smem, stream));
+  count_launches(1);
+  return B2_OK;
+}
+
+// workspace: wide_rec_workspace_bytes(d) bytes (exchange buffer | counters)
+int wide_rec_forward(const b2_lstm_desc* d, const b2_lstm_params* fw, const b2_lstm_params* bw, const int32_t* seq_len,
+                     const float* G, float* y, float* gates, float* cs, float* hs, float* final_state, void* workspace,
+                     cudaStream_t stream) {
+  WideFwdArgs a;
+  a.T = d->T; a.B = d->B; a.D_in = d->D_in; a.H = d->H;
+  a.use_peephole = d->use_peephole; a.forget_bias = d->forget_bias; a.cell_clip = d->cell_clip;
+  a.keep_prob = d->keep_prob; a.seed = d->dropout_seed;
+  const b2_lstm_params* P[2] = {fw, bw};
+  for (int dir = 0; dir < 2; ++dir) {
+    a.kernel[dir] = P[dir]->kernel; a.wi[dir] = P[dir]->w_i_diag; a.wf[dir] = P[dir]->w_f_diag; a.wo[dir] = P[dir]->w_o_diag;
+  }
+  a.seq_len = seq_len; a.G = G; a.y = y; a.gates = gates; a.cs = cs; a.hs = hs; a.final_state = final_state;
+  a.hx = (__nv_bfloat16*)workspace;
+  const size_t hx_bytes = align_up((size_t)2 * 2 * WB * d->H * 2, 256);
+  a.bar = (unsigned*)((char*)workspace + hx_bytes);
+  B2_CUDA(cudaMemsetAsync(a.bar, 0, 2 * sizeof(unsigned), stream));
+  switch (d->H / 32) {
+    case 20: return launch_wide_fwd<20>(a, stream);
+    case 24: return launch_wide_fwd<24>(a, stream);
+    case 28: return launch_wide_fwd<28>(a, stream);
+    case 32: return launch_wide_fwd<32>(a, stream);
+  }
+  set_error("wide_rec_forward: unsupported H=%d", d->H);
+  return B2_ERR_UNSUPPORTED;
+}
+
+}  // namespace b2

@@ -85,3 +85,23 @@ def test_wide_layer_per_step_gemm_path(cuda, precision, tol):
     prec = ops.PREC_FP32 if precision == "fp32" else ops.PREC_BF16
     got, ref = run_layer(cuda, T, B, D, H, [7, 4, 7, 2, 6], prec, seed=29, parameter_init=0.05)
     compare(got, ref, tol, 2 * tol)
+
+
+@pytest.mark.parametrize("T,B,D,H", [(9, 5, 24, 640), (14, 32, 40, 1024), (6, 17, 16, 768), (1, 3, 16, 896)])
+def test_grid_resident_wide_layer(cuda, T, B, D, H):
+    """512 < H <= 1024 (config 4: 6 x 1024), precision bf16: the forward recurrence is ONE cooperative launch
+    (lstm_wide.cu: recurrent weights register-resident as mma.sync fragments, h exchanged through L2 behind a grid
+    barrier per step) feeding the fp32 reserve of the BPTT path; forward + gradients vs the fp64 oracle at the bf16
+    tolerance, ragged lengths, final state; and against the per-frame fallback (B2_WIDE_REC=0)."""
+    import torch
+    from tensorflow_end2end_speech_recognition_b200 import ops
+    seq = [T] + list(np.random.RandomState(T + B).randint(max(T // 2, 1), T + 1, size=B - 1))
+    got, ref = run_layer(cuda, T, B, D, H, seq, ops.PREC_BF16, seed=31, parameter_init=0.05)
+    compare(got, ref, 3e-2, 6e-2)
+    os.environ["B2_WIDE_REC"] = "0"
+    try:
+        old, _ = run_layer(cuda, T, B, D, H, seq, ops.PREC_BF16, seed=31, parameter_init=0.05)
+    finally:
+        os.environ.pop("B2_WIDE_REC", None)
+    # the fallback multiplies h by fp32 recurrent weights, the resident kernel by their bf16 rounding
+    assert np.abs(got[0] - old[0]).max() < 2e-2, np.abs(got[0] - old[0]).max()
