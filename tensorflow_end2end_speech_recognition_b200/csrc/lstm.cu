@@ -694,7 +694,12 @@ extern "C" int b2_blstm_layer_backward_ex(const b2_lstm_desc* d, const float* x,
   const bool wide = H > 512 && B <= 64;            // see the forward pass
   a.dhrec = wide ? w.zrec : nullptr;
   dim3 grid(cdiv(H, RU), cdiv(B, RB), 2);
-  for (int i = 0; i < T; ++i) {
+  const bool resident = wide_rec_supported(d);     // config 4: ONE cooperative launch for the whole BPTT recurrence
+  if (resident) {
+    rc = wide_rec_backward(d, fw, bw, seq_len, dy, r.gates, r.cs, d_final_state, w.G, w.wide, stream);
+    if (rc) return rc;
+  }
+  for (int i = 0; i < (resident ? 0 : T); ++i) {
     a.step = i;
     if (wide) {
       if (i == 0) B2_CUDA(cudaMemsetAsync(w.zrec, 0, (size_t)2 * B * H * sizeof(float), stream));
@@ -709,8 +714,7 @@ extern "C" int b2_blstm_layer_backward_ex(const b2_lstm_desc* d, const float* x,
     }
     lstm_bwd_step_kernel<<<grid, 256, 0, stream>>>(a);
   }
-  count_launches(T - 1);
-  B2_LAUNCH_CHECK();
+  if (!resident) { count_launches(T - 1); B2_LAUNCH_CHECK(); }
 
   // 2. bias + peephole reductions
   for (int dir = 0; dir < 2; ++dir) {

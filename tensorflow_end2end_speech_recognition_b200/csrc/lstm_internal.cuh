@@ -112,6 +112,9 @@ int wide_rec_forward(const b2_lstm_desc* d, const b2_lstm_params* fw, const b2_l
                      const float* G, float* y, float* gates, float* cs, float* hs, float* final_state, void* workspace,
                      cudaStream_t stream);
 
+int wide_rec_backward(const b2_lstm_desc* d, const b2_lstm_params* fw, const b2_lstm_params* bw, const int32_t* seq_len,
+                      const float* dy, const float* gates, const float* cs, const float* d_final_state, float* dG,
+                      void* workspace, cudaStream_t stream);
 int tc_backward_join(cudaStream_t stream);
 int tc_backward_side_wait(cudaStream_t stream);
 void tc_profile_enable(int on);

@@ -217,6 +217,185 @@ lstm_wide_fwd_kernel(const WideFwdArgs a) {
   }
 }
 
+// ======================================================================== BPTT
+// dh_t[b, u] = dy_t + sum_k dz_{t'}[b, k] . Wh[u, k]  (t' = the frame processed one BPTT step earlier, k over the 4H
+// gate columns).  CTA j of a direction owns 16 units: its 16 x 4H bf16 rows of Wh are register-resident (8 warps = 8
+// K eighths, H/8 registers per thread); the gate gradients dz_{t'} of ALL units ([B, 4H] bf16, 256 KB at H = 1024) are
+// all-gathered through L2 behind the same grid barrier and streamed through shared memory one gate (H columns) at a
+// time; the eight partial sums meet in shared memory; the gate-derivative math runs on 2 cells per thread and emits
+// dz_t to the exchange buffer (bf16) and to dG (fp32, TF column order) for the time-batched GEMMs of lstm.cu.
+struct WideBwdArgs {
+  int T, B, D_in, H;
+  int use_peephole; float cell_clip, keep_prob; unsigned long long seed;
+  const float* kernel[2]; const float* wi[2]; const float* wf[2]; const float* wo[2];
+  const int* seq_len;
+  const float* dy;                // [T,B,2H]
+  const float* gates; const float* cs;
+  const float* dfinal;            // [4,B,H] or null
+  float* dG;                      // [T*B, 8H] fp32, column = dir*4H + gate*H + u
+  __nv_bfloat16* dzx;             // exchange buffer [2 dir][2 parity][WB][4H]
+  unsigned* bar;                  // [2]
+};
+
+// KS8 = k-steps (of 16) per (gate, warp) = H / 128
+template <int KS8>
+__global__ void __launch_bounds__(WTHREADS, 1)
+lstm_wide_bwd_kernel(const WideBwdArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int H = a.H, B = a.B, T = a.T;
+  const int HP = H + 8;
+  __nv_bfloat16* zbuf = (__nv_bfloat16*)smem_raw;          // [WB][HP]: one gate's columns of dz_{t'}
+  float* part = (float*)(smem_raw + (size_t)WB * HP * 2);  // [8 warps][16 units][WPP]
+  const int NS = H / WU;
+  const int dir = blockIdx.x / NS, slice = blockIdx.x % NS;
+  const int u0 = slice * WU;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int fr = lane >> 2, fc = lane & 3;
+
+  // A[row = unit][k] = Wh[u0 + unit][k]: rows of the TF kernel are contiguous in k
+  uint32_t afrag[4][KS8][4];
+  {
+    const float* W0 = a.kernel[dir] + (size_t)(a.D_in + u0) * 4 * H;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+      for (int ks = 0; ks < KS8; ++ks) {
+        const int k0 = g * H + warp * (KS8 * 16) + ks * 16 + 2 * fc;
+        const float* r0 = W0 + (size_t)fr * 4 * H + k0;
+        const float* r1 = W0 + (size_t)(fr + 8) * 4 * H + k0;
+        afrag[g][ks][0] = pack_bf16(r0[0], r0[1]);
+        afrag[g][ks][1] = pack_bf16(r1[0], r1[1]);
+        afrag[g][ks][2] = pack_bf16(r0[8], r0[9]);
+        afrag[g][ks][3] = pack_bf16(r1[8], r1[9]);
+      }
+  }
+  const int ul = tid & 15, bq = tid >> 4;
+  const int u = u0 + ul;
+  int len[2]; float dcs[2], dfh[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int b = bq + 16 * j;
+    len[j] = b < B ? a.seq_len[b] : 0;
+    dcs[j] = 0.f; dfh[j] = 0.f;
+    if (a.dfinal && b < B) {
+      dcs[j] = a.dfinal[((size_t)(dir * 2 + 0) * B + b) * H + u];
+      dfh[j] = a.dfinal[((size_t)(dir * 2 + 1) * B + b) * H + u];
+    }
+  }
+  float pwi = 0.f, pwf = 0.f, pwo = 0.f;
+  if (a.use_peephole) { pwi = a.wi[dir][u]; pwf = a.wf[dir][u]; pwo = a.wo[dir][u]; }
+  __nv_bfloat16* zx_dir = a.dzx + (size_t)dir * 2 * WB * 4 * H;
+  unsigned* bar = a.bar + dir;
+
+  for (int s = 0; s < T; ++s) {
+    const int td = dir ? s : T - 1 - s;
+    const int tn = dir ? td - 1 : td + 1;      // frame processed one BPTT step earlier
+    const int tp = dir ? td + 1 : td - 1;      // previous frame in forward order
+    // ---- reserve + dy of this thread's two cells (independent of dh: in flight while the barrier is awaited)
+    float4 g4[2]; float cc[2], cp[2], dyv[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int b = bq + 16 * j;
+      g4[j] = make_float4(0.f, 0.f, 0.f, 0.f); cc[j] = 0.f; cp[j] = 0.f; dyv[j] = 0.f;
+      if (b < B) {
+        const size_t row = (size_t)td * B + b;
+        const size_t cell = (row * 2 + dir) * H + u;
+        g4[j] = __ldg((const float4*)(a.gates + cell * 4));
+        cc[j] = __ldg(a.cs + cell);
+        if (tp >= 0 && tp < T && tp < len[j]) cp[j] = __ldg(a.cs + (((size_t)tp * B + b) * 2 + dir) * H + u);
+        const size_t oidx = row * 2 * H + (size_t)dir * H + u;
+        dyv[j] = __ldg(a.dy + oidx);
+        if (a.keep_prob < 1.f) dyv[j] = dropout_keep(a.seed, oidx, a.keep_prob) ? dyv[j] / a.keep_prob : 0.f;
+      }
+    }
+    float dh_rec[2] = {0.f, 0.f};
+    if (s > 0) {
+      if (tid == 0) {
+        const unsigned want = (unsigned)NS * (unsigned)s;
+        while (ld_acquire_u32(bar) < want) {}
+      }
+      __syncthreads();
+      float acc[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+      const __nv_bfloat16* zsrc = zx_dir + (size_t)((s - 1) & 1) * WB * 4 * H;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        // gate g's H columns of dz_{t'} for all batch rows -> shared memory
+        {
+          const int vec_per_row = H / 8;
+          for (int i = tid; i < WB * vec_per_row; i += WTHREADS) {
+            const int r = i / vec_per_row, cvec = i - r * vec_per_row;
+            const uint4 v = __ldcg((const uint4*)(zsrc + (size_t)r * 4 * H + (size_t)g * H) + cvec);
+            *(uint4*)(zbuf + (size_t)r * HP + cvec * 8) = v;
+          }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < KS8; ++ks) {
+          const int k0 = warp * (KS8 * 16) + ks * 16 + 2 * fc;
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            const __nv_bfloat16* zp = zbuf + (size_t)(nt * 8 + fr) * HP + k0;
+            mma_bf16_16816(acc[nt], afrag[g][ks], *(const uint32_t*)zp, *(const uint32_t*)(zp + 8));
+          }
+        }
+        __syncthreads();
+      }
+      {
+        float* pr = part + (size_t)warp * 16 * WPP;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          *(float2*)(pr + (size_t)fr * WPP + nt * 8 + 2 * fc) = make_float2(acc[nt][0], acc[nt][1]);
+          *(float2*)(pr + (size_t)(fr + 8) * WPP + nt * 8 + 2 * fc) = make_float2(acc[nt][2], acc[nt][3]);
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += part[((size_t)w * 16 + ul) * WPP + bq + 16 * j];
+        dh_rec[j] = sum;
+      }
+    }
+    // ---- gate derivatives (the fp32 step kernel's math, lstm.cu::lstm_bwd_step_kernel)
+    __nv_bfloat16* zx_out = zx_dir + (size_t)(s & 1) * WB * 4 * H;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int b = bq + 16 * j;
+      const bool active = td < len[j];
+      float dzi = 0.f, dzg = 0.f, dzf = 0.f, dzo = 0.f;
+      if (active) {
+        const bool nb_active = s > 0 && tn >= 0 && tn < T && tn < len[j];
+        const float dh = dyv[j] + (nb_active ? dh_rec[j] : dfh[j]);
+        const float gi = g4[j].x, gg = g4[j].y, gf = g4[j].z, go = g4[j].w;
+        const float tc = tanhf_(cc[j]);
+        dzo = dh * tc * go * (1.f - go);
+        float dc = dcs[j] + dh * go * (1.f - tc * tc);
+        dc = fmaf(dzo, pwo, dc);
+        if (a.cell_clip > 0.f && fabsf(cc[j]) >= a.cell_clip) dc = 0.f;
+        dzi = dc * gg * gi * (1.f - gi);
+        dzg = dc * gi * (1.f - gg * gg);
+        dzf = dc * cp[j] * gf * (1.f - gf);
+        dcs[j] = fmaf(dzf, pwf, fmaf(dzi, pwi, dc * gf));
+      }
+      __nv_bfloat16* zr = zx_out + (size_t)b * 4 * H + u;
+      zr[0] = __float2bfloat16(dzi); zr[H] = __float2bfloat16(dzg);
+      zr[2 * H] = __float2bfloat16(dzf); zr[3 * H] = __float2bfloat16(dzo);
+      if (b < B) {
+        float* dz = a.dG + ((size_t)td * B + b) * 8 * H + (size_t)dir * 4 * H + u;
+        dz[0] = dzi; dz[H] = dzg; dz[2 * H] = dzf; dz[3 * H] = dzo;
+      }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) atomicAdd(bar, 1u);
+  }
+}
+
 bool wide_rec_supported(const b2_lstm_desc* d) {
   if (d->precision != B2_PREC_BF16 || d->num_proj > 0) return false;
   if (!env_int("B2_WIDE_REC", 1)) return false;
@@ -228,7 +407,8 @@ bool wide_rec_supported(const b2_lstm_desc* d) {
 }
 
 size_t wide_rec_workspace_bytes(const b2_lstm_desc* d) {
-  return align_up((size_t)2 * 2 * WB * d->H * 2, 256) + 256;          // exchange buffer + barrier counters
+  // exchange buffer (forward: h [2][2][WB][H]; BPTT: dz [2][2][WB][4H]) + barrier counters
+  return align_up((size_t)2 * 2 * WB * 4 * d->H * 2, 256) + 256;
 }
 
 template <int KSH>
@@ -256,7 +436,7 @@ int wide_rec_forward(const b2_lstm_desc* d, const b2_lstm_params* fw, const b2_l
   }
   a.seq_len = seq_len; a.G = G; a.y = y; a.gates = gates; a.cs = cs; a.hs = hs; a.final_state = final_state;
   a.hx = (__nv_bfloat16*)workspace;
-  const size_t hx_bytes = align_up((size_t)2 * 2 * WB * d->H * 2, 256);
+  const size_t hx_bytes = align_up((size_t)2 * 2 * WB * 4 * d->H * 2, 256);
   a.bar = (unsigned*)((char*)workspace + hx_bytes);
   B2_CUDA(cudaMemsetAsync(a.bar, 0, 2 * sizeof(unsigned), stream));
   switch (d->H / 32) {
@@ -266,6 +446,43 @@ int wide_rec_forward(const b2_lstm_desc* d, const b2_lstm_params* fw, const b2_l
     case 32: return launch_wide_fwd<32>(a, stream);
   }
   set_error("wide_rec_forward: unsupported H=%d", d->H);
+  return B2_ERR_UNSUPPORTED;
+}
+
+template <int KS8>
+static int launch_wide_bwd(WideBwdArgs& a, cudaStream_t stream) {
+  const size_t smem = (size_t)WB * (a.H + 8) * 2 + (size_t)8 * 16 * WPP * 4;
+  auto kern = lstm_wide_bwd_kernel<KS8>;
+  B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void* params[] = {(void*)&a};
+  B2_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(2 * (a.H / WU)), dim3(WTHREADS), params, smem, stream));
+  count_launches(1);
+  return B2_OK;
+}
+
+// BPTT recurrence of a wide layer -> dG [T*B, 8H] fp32 (TF column order); same workspace block as the forward pass
+int wide_rec_backward(const b2_lstm_desc* d, const b2_lstm_params* fw, const b2_lstm_params* bw, const int32_t* seq_len,
+                      const float* dy, const float* gates, const float* cs, const float* d_final_state, float* dG,
+                      void* workspace, cudaStream_t stream) {
+  WideBwdArgs a;
+  a.T = d->T; a.B = d->B; a.D_in = d->D_in; a.H = d->H;
+  a.use_peephole = d->use_peephole; a.cell_clip = d->cell_clip; a.keep_prob = d->keep_prob; a.seed = d->dropout_seed;
+  const b2_lstm_params* P[2] = {fw, bw};
+  for (int dir = 0; dir < 2; ++dir) {
+    a.kernel[dir] = P[dir]->kernel; a.wi[dir] = P[dir]->w_i_diag; a.wf[dir] = P[dir]->w_f_diag; a.wo[dir] = P[dir]->w_o_diag;
+  }
+  a.seq_len = seq_len; a.dy = dy; a.gates = gates; a.cs = cs; a.dfinal = d_final_state; a.dG = dG;
+  a.dzx = (__nv_bfloat16*)workspace;
+  const size_t zx_bytes = align_up((size_t)2 * 2 * WB * 4 * d->H * 2, 256);
+  a.bar = (unsigned*)((char*)workspace + zx_bytes);
+  B2_CUDA(cudaMemsetAsync(a.bar, 0, 2 * sizeof(unsigned), stream));
+  switch (d->H / 128) {
+    case 5: return launch_wide_bwd<5>(a, stream);
+    case 6: return launch_wide_bwd<6>(a, stream);
+    case 7: return launch_wide_bwd<7>(a, stream);
+    case 8: return launch_wide_bwd<8>(a, stream);
+  }
+  set_error("wide_rec_backward: unsupported H=%d", d->H);
   return B2_ERR_UNSUPPORTED;
 }
 
