@@ -239,6 +239,8 @@ class CTC(ModelBase):
             ops.gemm(enc2d, dz, True, False, None, prec, out=grads["bottleneck/weights"], beta=1.0, a_lp=enc_lp)
             ops.colsum(dz, out=grads["bottleneck/biases"], accumulate=True)
             denc = ops.gemm(dz, self.variables["bottleneck/weights"], False, True, None, prec)
+        if getattr(self, "_on_heads_done", None) is not None:
+            self._on_heads_done()
         self.encoder.backward(denc.view(T, B, -1), self.variables, grads, saved=saved,
                               on_layer_done=self._on_layer_done)
         if self.weight_decay > 0:

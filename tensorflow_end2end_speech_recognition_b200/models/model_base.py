@@ -130,6 +130,7 @@ class ModelBase(object):
         self._towers = {}
         self._params_version = 0        # bumped by every optimizer step (packed-weight caches key on it)
         self._on_layer_done = None
+        self._on_heads_done = None
         self._comm = None
 
     # ------------------------------------------------------------ variables
@@ -269,13 +270,16 @@ class ModelBase(object):
         self._reduced.add(key)
 
     def _bucketed_exchange_begin(self):
-        """call right before the encoder's backward pass: the head bucket is final already"""
+        """installs the hooks _backward calls: after the head GEMMs (head bucket final) and after every layer"""
         self._bucket_plan()
         self._reduced = set()
-        cur = torch.cuda.current_stream()
-        self._comm_stream.wait_stream(cur)
-        if 0 in self._buckets:
-            self._reduce_bucket(0, self._comm_stream)
+
+        def on_heads_done():
+            # called by _backward between the head GEMMs and the encoder's backward pass: head gradients are final
+            if 0 in self._buckets:
+                self._comm_stream.wait_stream(torch.cuda.current_stream())
+                self._reduce_bucket(0, self._comm_stream)
+        self._on_heads_done = on_heads_done
 
         def on_layer_done(i_layer):
             # layer i_layer+1's weight gradients were enqueued on the library's side stream during this call
@@ -295,6 +299,7 @@ class ModelBase(object):
         self._comm_done.record(self._comm_stream)
         cur.wait_event(self._comm_done)
         self._on_layer_done = None
+        self._on_heads_done = None
 
     def _allreduce_gradients(self):
         if self.world_size <= 1:

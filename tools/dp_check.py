@@ -55,6 +55,8 @@ def main():
         dist.broadcast(ref, src=0)
         same = bool((ref == p1).all())
         results[mode] = (float(ms), p1, same)
+        names = [(v.name, (v.tensor.data_ptr() - model.flat_params.data_ptr()) // 4, v.tensor.numel())
+                 for v in model.trainable_variables()]
         if rank == 0:
             print("%-14s %.3f ms/step  ranks identical after step: %s" % (mode, float(ms), same), flush=True)
     if rank == 0:
@@ -62,6 +64,9 @@ def main():
         d1 = float((a - b).abs().max() / a.abs().max())
         d2 = float((a - c).abs().max() / a.abs().max())
         print("max |param diff| / max|param| after one step: torch vs c_abi_single %.2e, torch vs buckets %.2e" % (d1, d2))
+        if d2 >= 1e-5:
+            for n, o, k in names:
+                print("   %-50s %.3e" % (n, float((a[o:o + k] - c[o:o + k]).abs().max())))
         assert d1 < 1e-5 and d2 < 1e-5, (d1, d2)
         print("dp_check ok")
     comm.close()
