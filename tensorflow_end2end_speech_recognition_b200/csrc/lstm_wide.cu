@@ -21,9 +21,11 @@
 // the 64 x 1024 slice would take all 512 columns and leave no accumulator, and an SS-mode MMA would re-read 128 KB of
 // weights from shared memory every step.  mma.sync with register-resident A reads only h.
 #include "lstm_internal.cuh"
+#include "sm100.cuh"
 #include <cooperative_groups.h>
 
 namespace b2 {
+using namespace sm100;
 
 constexpr int WU = 16;            // units per CTA
 constexpr int WB = 32;            // batch rows per launch (mma N = 4 tiles of 8)
@@ -244,8 +246,17 @@ lstm_wide_bwd_kernel(const WideBwdArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int H = a.H, B = a.B, T = a.T;
   const int HP = H + 8;
-  __nv_bfloat16* zbuf = (__nv_bfloat16*)smem_raw;          // [WB][HP]: one gate's columns of dz_{t'}
-  float* part = (float*)(smem_raw + (size_t)WB * HP * 2);  // [8 warps][16 units][WPP]
+  // three tiles [WB][HP] bf16, each one gate's H columns of dz_{t'}; gate n of the kernel's running count lands in
+  // tile n % 3 (TMA bulk row copies, completion on full[n % 3]); tile reuse is released through empty[]
+  const size_t tile_bytes = (size_t)WB * HP * 2;
+  float* part = (float*)(smem_raw + 3 * tile_bytes);       // [8 warps][16 units][WPP]
+  uint64_t* full = (uint64_t*)(smem_raw + 3 * tile_bytes + (size_t)8 * 16 * WPP * 4);
+  uint64_t* empty = full + 3;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 3; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 8); }
+    fence_mbar_init();
+  }
+  __syncthreads();
   const int NS = H / WU;
   const int dir = blockIdx.x / NS, slice = blockIdx.x % NS;
   const int u0 = slice * WU;
@@ -310,29 +321,45 @@ lstm_wide_bwd_kernel(const WideBwdArgs a) {
     }
     float dh_rec[2] = {0.f, 0.f};
     if (s > 0) {
-      if (tid == 0) {
-        const unsigned want = (unsigned)NS * (unsigned)s;
-        while (ld_acquire_u32(bar) < want) {}
+      const __nv_bfloat16* zsrc = zx_dir + (size_t)((s - 1) & 1) * WB * 4 * H;
+      const unsigned n0 = (unsigned)(s - 1) * 4u;            // running gate-tile count at this step's first tile
+      if (warp == 0) {
+        // every CTA of this direction has published dz_{t'}; make the async proxy see those generic-proxy writes
+        if (lane == 0) {
+          const unsigned want = (unsigned)NS * (unsigned)s;
+          while (ld_acquire_u32(bar) < want) {}
+        }
+        __syncwarp();
+        asm volatile("fence.proxy.async;" ::: "memory");
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          const unsigned n = n0 + g, tl = n % 3u;
+          if (n >= 3u) mbar_wait(empty + tl, ((n / 3u) - 1u) & 1u);      // all 8 warps are done with tile use n-3
+          if (lane == 0) mbar_expect_tx(full + tl, (uint32_t)WB * H * 2);
+          __syncwarp();
+          bulk_g2s(smem_raw + tl * tile_bytes + (size_t)lane * HP * 2, zsrc + (size_t)lane * 4 * H + (size_t)g * H,
+                   (uint32_t)H * 2, full + tl);
+        }
       }
-      __syncthreads();
       float acc[4][4];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
-      const __nv_bfloat16* zsrc = zx_dir + (size_t)((s - 1) & 1) * WB * 4 * H;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        // gate g's H columns of dz_{t'} for all batch rows -> shared memory
-        {
-          const int vec_per_row = H / 8;
-          for (int i = tid; i < WB * vec_per_row; i += WTHREADS) {
-            const int r = i / vec_per_row, cvec = i - r * vec_per_row;
-            const uint4 v = __ldcg((const uint4*)(zsrc + (size_t)r * 4 * H + (size_t)g * H) + cvec);
-            *(uint4*)(zbuf + (size_t)r * HP + cvec * 8) = v;
-          }
+        const unsigned n = n0 + g, tl = n % 3u;
+        if (g == 1 && warp == 0) {
+          // the fourth gate of this step reuses the tile of the first: wait until every warp has released it
+          const unsigned n3 = n0 + 3u, t3 = n3 % 3u;
+          mbar_wait(empty + t3, ((n3 / 3u) - 1u) & 1u);
+          if (lane == 0) mbar_expect_tx(full + t3, (uint32_t)WB * H * 2);
+          __syncwarp();
+          bulk_g2s(smem_raw + t3 * tile_bytes + (size_t)lane * HP * 2, zsrc + (size_t)lane * 4 * H + (size_t)3 * H,
+                   (uint32_t)H * 2, full + t3);
         }
-        __syncthreads();
+        mbar_wait(full + tl, (n / 3u) & 1u);
+        const __nv_bfloat16* zbuf = (const __nv_bfloat16*)(smem_raw + tl * tile_bytes);
 #pragma unroll
         for (int ks = 0; ks < KS8; ++ks) {
           const int k0 = warp * (KS8 * 16) + ks * 16 + 2 * fc;
@@ -342,7 +369,8 @@ lstm_wide_bwd_kernel(const WideBwdArgs a) {
             mma_bf16_16816(acc[nt], afrag[g][ks], *(const uint32_t*)zp, *(const uint32_t*)(zp + 8));
           }
         }
-        __syncthreads();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + tl);
       }
       {
         float* pr = part + (size_t)warp * 16 * WPP;
@@ -451,7 +479,7 @@ int wide_rec_forward(const b2_lstm_desc* d, const b2_lstm_params* fw, const b2_l
 
 template <int KS8>
 static int launch_wide_bwd(WideBwdArgs& a, cudaStream_t stream) {
-  const size_t smem = (size_t)WB * (a.H + 8) * 2 + (size_t)8 * 16 * WPP * 4;
+  const size_t smem = (size_t)3 * WB * (a.H + 8) * 2 + (size_t)8 * 16 * WPP * 4 + 64;
   auto kern = lstm_wide_bwd_kernel<KS8>;
   B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* params[] = {(void*)&a};
