@@ -3,14 +3,18 @@
 // Replaces tf.nn.ctc_loss as called at models/ctc/ctc.py:289-297 (reference
 // arithmetic lives in TensorFlow; semantics restated in oracle/ctc.py).
 //
-// Three kernels, all HBM/latency bound (no GEMM shape anywhere):
-//   K3a ctc_lse_kernel        one warp per (t,b) row: lse[t,b] = logsumexp_c logits
-//   K3b ctc_alpha_beta_kernel one CTA per (utterance, direction): the T-step
-//                             lattice sweep in shared memory, log domain,
-//                             alpha and beta CTAs run concurrently; rows are
-//                             spilled to HBM/L2 ([B,T,S] fp32 each)
-//   K3c ctc_grad_kernel       one warp per (t,b) row: softmax - occupancy,
-//                             occupancy scattered by label in shared memory
+// Kernels, all HBM/latency bound (no GEMM shape anywhere):
+//   short labels (2*Lmax+1 <= 512, every BASELINE config), the fast path:
+//     ctc_ab_team_kernel<SPL>  four warps per (utterance, direction): a thread keeps SPL consecutive lattice
+//                              positions in registers, neighbours come by shuffle (two shared cells across a warp
+//                              boundary) -- no shared-memory column, one block barrier per lattice step; the
+//                              lattice runs on RAW logits (the per-frame normaliser is added by the finaliser),
+//                              emissions prefetched by a cp.async ring; rows spilled [B,T,S_pad] lane-interleaved
+//     ctc_grad_kernel          one warp per (t,b) row: logsumexp of the row (written to lse[t,b]), softmax -
+//                              occupancy (row-local normalisation), occupancy scattered by label in shared memory
+//     ctc_finalize_kernel      loss[b] = -(log p' - sum_t lse[t,b])
+//   long labels (fallback): ctc_lse_kernel, ctc_alpha_beta_kernel (one CTA per (utterance, direction), column in
+//     shared memory), ctc_grad_kernel reading the precomputed lse
 //
 // Algorithmic HBM bytes: 8*T*B*C (read logits, write grad) + 16*T*B*S spill.
 #include "common.cuh"
@@ -247,15 +251,279 @@ ctc_alpha_beta_kernel(const float* __restrict__ logits, const float* __restrict_
   }
 }
 
+// base-2 log-domain helpers of the team sweep: ex2/lg2 are the hardware functions, the .ftz forms carry no
+// denormal range fix-ups (3 instructions per exp, 3 per log in the default forms) -- a term 2^-126 below the column
+// maximum contributes nothing at fp32 anyway
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_ftz(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float l2se3(float a, float b, float c) {
+  const float m = fmaxf(fmaxf(a, fmaxf(b, c)), -1e30f);
+  return m + lg2_ftz(ex2_ftz(a - m) + ex2_ftz(b - m) + ex2_ftz(c - m));
+}
+__device__ __forceinline__ float l2se2(float a, float b) {
+  const float m = fmaxf(fmaxf(a, b), -1e30f);
+  return m + lg2_ftz(ex2_ftz(a - m) + ex2_ftz(b - m));
+}
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// ---------------------------------------------------------------- fast path: four warps per (utterance, direction)
+// Thread `tid` (of kTeam = 128) owns positions s = tid*SPL + k (k < SPL, SPL even: k odd <=> label position) in
+// registers.  Neighbours inside a warp come by shuffle, the two values across a warp boundary through a parity-
+// double-buffered shared cell pair -> ONE block barrier per lattice step, no shared-memory column.  (One warp with
+// 16 positions per lane was measured first: 3 000 cycles per step, issue-bound on a single scheduler.)
+// The lattice is kept in BASE-2 log units (values = log2 of the unnormalised path mass); the spilled rows too.
+// Spill index of position s inside a row: k*kTeam + tid (coalesced); S_pad = kTeam*SPL.
+constexpr int kTeam = 128;
+template <int SPL, bool is_beta>
+__device__ __forceinline__ void
+ctc_ab_team_body(const float* __restrict__ logits, const int* __restrict__ labels_flat,
+                 const int* __restrict__ label_offsets, const int* __restrict__ seq_len, int T, int B, int C,
+                 int blank, int ignore_longer, float* __restrict__ alpha, float* __restrict__ beta,
+                 float* __restrict__ logp_out, int* __restrict__ skip_out, float* __restrict__ loss) {
+  constexpr int S_pad = kTeam * SPL;
+  constexpr int NL = SPL / 2;                 // label positions per thread
+  constexpr int NW = kTeam / 32;
+  constexpr int PF = 8;                       // emission prefetch depth (lattice steps)
+  __shared__ float ring[PF][NL * kTeam + NW]; // [slot][k/2][tid], then the blank's logit (one copy per warp)
+  __shared__ float xch[2][NW][2];             // boundary values of the column of parity p
+  __shared__ float red[NW];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Tb = min(seq_len[b], T);
+  const int off = label_offsets[b];
+  const int L = label_offsets[b + 1] - off;
+  const int S = 2 * L + 1;
+  const int* lab = labels_flat + off;
+
+  if (L > Tb && ignore_longer) {   // skipped utterance: loss 0, grad 0 (ctc.py:296)
+    if (tid == 0 && !is_beta) { loss[b] = 0.f; logp_out[b] = 0.f; skip_out[b] = 1; }
+    return;
+  }
+  if (Tb <= 0) {
+    if (tid == 0 && !is_beta) {
+      loss[b] = (L == 0) ? 0.f : INFINITY;
+      logp_out[b] = (L == 0) ? 0.f : -INFINITY;
+      skip_out[b] = 1;
+    }
+    return;
+  }
+  int cls[NL];
+  bool skip[NL], valid[SPL];
+  bool bad = false;
+#pragma unroll
+  for (int k = 0; k < SPL; ++k) valid[k] = tid * SPL + k < S;
+#pragma unroll
+  for (int j = 0; j < NL; ++j) {
+    const int s = tid * SPL + 2 * j + 1;
+    cls[j] = blank; skip[j] = false;
+    if (s < S) {
+      cls[j] = lab[s >> 1];
+      bad |= (cls[j] < 0) | (cls[j] >= C) | (cls[j] == blank);
+      if (!is_beta) skip[j] = (s >= 3) && (lab[s >> 1] != lab[(s >> 1) - 1]);
+      else          skip[j] = (s + 2 < S) && (lab[(s >> 1) + 1] != lab[s >> 1]);
+    }
+  }
+  if (__syncthreads_or(bad)) {             // see ctc_alpha_beta_kernel: loss NaN, zero gradient
+    if (tid == 0 && !is_beta) { loss[b] = __int_as_float(0x7fc00000); logp_out[b] = 0.f; skip_out[b] = 1; }
+    return;
+  }
+  if (tid == 0 && !is_beta) skip_out[b] = 0;
+
+  float* out = (is_beta ? beta : alpha) + (int64_t)b * T * S_pad;
+  const int t0 = is_beta ? Tb - 1 : 0;
+  const int dt = is_beta ? -1 : 1;
+  float a[SPL];
+  {
+    const float* x = logits + ((int64_t)t0 * B + b) * C;
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) {
+      const int s = tid * SPL + k;
+      const bool init = is_beta ? (s >= S - 2) : (s <= 1);
+      a[k] = -INFINITY;
+      if (valid[k] && init) a[k] = kLog2e * ((k & 1) ? x[cls[k >> 1]] : x[blank]);
+      out[(int64_t)t0 * S_pad + k * kTeam + tid] = a[k];
+    }
+  }
+  // publish the boundary values of column 0 (parity 0)
+  if (!is_beta) { if (lane == 31) { xch[0][warp][0] = a[SPL - 2]; xch[0][warp][1] = a[SPL - 1]; } }
+  else          { if (lane == 0)  { xch[0][warp][0] = a[0];       xch[0][warp][1] = a[1]; } }
+  const int nsteps = Tb - 1;
+  const int64_t lg_stride = (int64_t)dt * B * C;
+  const float* lg_next[NL];
+#pragma unroll
+  for (int j = 0; j < NL; ++j) lg_next[j] = logits + ((int64_t)(t0 + dt) * B + b) * C + cls[j];
+  const float* blank_next = logits + ((int64_t)(t0 + dt) * B + b) * C + blank;
+  int issued = 0;
+  auto issue = [&](int slot) {
+    if (issued < nsteps) {
+#pragma unroll
+      for (int j = 0; j < NL; ++j) {
+        cp_async4(&ring[slot][j * kTeam + tid], lg_next[j]);
+        lg_next[j] += lg_stride;
+      }
+      if (lane == 0) cp_async4(&ring[slot][NL * kTeam + warp], blank_next);
+      blank_next += lg_stride;
+    }
+    ++issued;
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int j = 0; j < PF; ++j) issue(j);
+  float* out_next = out + (int64_t)(t0 + dt) * S_pad + tid;
+  const int64_t out_stride = (int64_t)dt * S_pad;
+  constexpr int kNorm = 16;
+  double offset_sum = 0.0;
+  __syncthreads();
+  for (int i0 = 0; i0 < nsteps; i0 += PF) {
+#pragma unroll
+    for (int jj = 0; jj < PF; ++jj) {
+      const int i = i0 + jj;
+      if (i < nsteps) {                 // uniform across the CTA
+        const int par = i & 1;          // parity of the column being read
+        cp_async_wait<PF - 2>();        // emissions of this step have landed (the refill runs one step late)
+        __syncwarp();
+        const float xb = ring[jj][NL * kTeam + warp];
+        float xl[NL];
+#pragma unroll
+        for (int j = 0; j < NL; ++j) xl[j] = ring[jj][j * kTeam + tid];
+        // neighbours across the thread boundary
+        float e0, e1;       // alpha: positions s-2, s-1 of this thread's first position; beta: s+1, s+2 of its last
+        if (!is_beta) {
+          e0 = __shfl_up_sync(0xffffffffu, a[SPL - 2], 1);
+          e1 = __shfl_up_sync(0xffffffffu, a[SPL - 1], 1);
+          if (lane == 0) {
+            e0 = warp > 0 ? xch[par][warp - 1][0] : -INFINITY;
+            e1 = warp > 0 ? xch[par][warp - 1][1] : -INFINITY;
+          }
+        } else {
+          e0 = __shfl_down_sync(0xffffffffu, a[0], 1);
+          e1 = __shfl_down_sync(0xffffffffu, a[1], 1);
+          if (lane == 31) {
+            e0 = warp < NW - 1 ? xch[par][warp + 1][0] : -INFINITY;
+            e1 = warp < NW - 1 ? xch[par][warp + 1][1] : -INFINITY;
+          }
+        }
+        // refill the slot consumed in the PREVIOUS step (every lane passed that step's block barrier since it
+        // read the slot): independent instructions that fill the latency holes of the chain below
+        if (i > 0) issue((jj + PF - 1) % PF);
+        float v[SPL];
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) {
+          float n1, n2;                        // k is a compile-time constant after unrolling
+          if (!is_beta) {
+            n1 = (k >= 1) ? a[(k + SPL - 1) % SPL] : e1;                     // s-1
+            n2 = (k >= 2) ? a[(k + SPL - 2) % SPL] : (k == 1 ? e1 : e0);     // s-2
+          } else {
+            n1 = (k + 1 < SPL) ? a[(k + 1) % SPL] : e0;                      // s+1
+            n2 = (k + 2 < SPL) ? a[(k + 2) % SPL] : (k + 2 == SPL ? e0 : e1);   // s+2
+          }
+          float r;
+          if (k & 1) r = fmaf(xl[k >> 1], kLog2e, l2se3(a[k], n1, skip[k >> 1] ? n2 : -INFINITY));
+          else       r = fmaf(xb, kLog2e, l2se2(a[k], n1));            // blanks have no skip transition
+          v[k] = valid[k] ? r : -INFINITY;
+        }
+        if ((i % kNorm) == kNorm - 1) {       // uniform: shift the new column by its maximum before publishing it
+          float m = v[0];
+#pragma unroll
+          for (int k = 1; k < SPL; ++k) m = fmaxf(m, v[k]);
+          m = warp_max(m);
+          if (lane == 0) red[warp] = m;
+          __syncthreads();
+          m = red[0];
+#pragma unroll
+          for (int w = 1; w < NW; ++w) m = fmaxf(m, red[w]);
+          if (m != -INFINITY) {
+#pragma unroll
+            for (int k = 0; k < SPL; ++k) v[k] -= m;
+            offset_sum += (double)m;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) { a[k] = v[k]; out_next[k * kTeam] = v[k]; }
+        out_next += out_stride;
+        if (!is_beta) { if (lane == 31) { xch[par ^ 1][warp][0] = a[SPL - 2]; xch[par ^ 1][warp][1] = a[SPL - 1]; } }
+        else          { if (lane == 0)  { xch[par ^ 1][warp][0] = a[0];       xch[par ^ 1][warp][1] = a[1]; } }
+        __syncthreads();
+      }
+    }
+  }
+  if (!is_beta) {
+    float e = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < SPL; ++k) {
+      const int s = tid * SPL + k;
+      if (s == S - 1 || s == S - 2) e = lse2(e, a[k] * kLn2);
+    }
+    // at most two threads hold a finite e (natural log from here on)
+    float m = warp_max(e);
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    m = red[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) m = fmaxf(m, red[w]);
+    __syncthreads();
+    float z = (m != -INFINITY) ? __expf(e - m) : 0.f;
+    z = warp_sum(z);
+    if (lane == 0) red[warp] = z;
+    __syncthreads();
+    if (tid == 0) {
+      float zz = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) zz += red[w];
+      const float lp = (m != -INFINITY) ? m + __logf(zz) : -INFINITY;
+      logp_out[b] = (float)((double)lp + offset_sum * 0.6931471805599453);     // still lacks - sum_t lse[t,b]
+    }
+  }
+}
+
+template <int SPL>
+__global__ void __launch_bounds__(kTeam)
+ctc_ab_team_kernel(const float* __restrict__ logits, const int* __restrict__ labels_flat,
+                   const int* __restrict__ label_offsets, const int* __restrict__ seq_len, int T, int B, int C,
+                   int blank, int ignore_longer, float* __restrict__ alpha, float* __restrict__ beta,
+                   float* __restrict__ logp_out, int* __restrict__ skip_out, float* __restrict__ loss) {
+  // blockIdx.y: 0 alpha, 1 beta -- two instantiations of the body, no per-step direction branches
+  if (blockIdx.y == 0)
+    ctc_ab_team_body<SPL, false>(logits, labels_flat, label_offsets, seq_len, T, B, C, blank, ignore_longer, alpha, beta,
+                                 logp_out, skip_out, loss);
+  else
+    ctc_ab_team_body<SPL, true>(logits, labels_flat, label_offsets, seq_len, T, B, C, blank, ignore_longer, alpha, beta,
+                                logp_out, skip_out, loss);
+}
+
+// loss[b] = -(log p' - sum_{t < T_b} lse[t,b]) for the utterances the sweep did not settle itself
+__global__ void __launch_bounds__(128)
+ctc_finalize_kernel(const float* __restrict__ lse, const int* __restrict__ seq_len,
+                    const int* __restrict__ skip, int T, int B, float* __restrict__ logp,
+                    float* __restrict__ loss) {
+  __shared__ double part[4];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  if (skip[b]) return;
+  const int Tb = min(seq_len[b], T);
+  double acc = 0.0;
+  for (int t = tid; t < Tb; t += 128) acc += (double)__ldg(lse + (int64_t)t * B + b);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((tid & 31) == 0) part[tid >> 5] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    const float lp = (float)((double)logp[b] - (part[0] + part[1] + part[2] + part[3]));
+    logp[b] = lp;
+    loss[b] = -lp;
+  }
+}
+
 // One warp per (t,b) row.  g[c] = softmax_c - sum_{s: l'(s)=c} alpha*beta/(y*Z_t) with the
-// row-local normaliser Z_t = sum_s alpha*beta/y (= p, independent of per-row lattice shifts).
+// row-local normaliser Z_t = sum_s alpha*beta/y (= p, independent of per-row lattice shifts and of whether the lattice
+// ran on normalised or raw logits).  spl > 0: rows of the team sweep (position tid*spl + k at k*nt + tid, lattice on
+// raw logits, this kernel computes and stores the row's logsumexp); spl == 0: linear rows, lse precomputed.
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-ctc_grad_kernel(const float* __restrict__ logits, const float* __restrict__ lse,
+ctc_grad_kernel(const float* __restrict__ logits, float* __restrict__ lse,
                 const int* __restrict__ labels_flat, const int* __restrict__ label_offsets,
                 const int* __restrict__ seq_len, const float* __restrict__ alpha,
-                const float* __restrict__ beta, const float* __restrict__ logp_in,
-                const int* __restrict__ skip_in, int T, int B, int C, int blank, int S_pad,
-                float grad_scale, int warps_per_block, float* __restrict__ grad) {
+                const float* __restrict__ beta, const int* __restrict__ skip_in, int T, int B, int C, int blank,
+                int S_pad, int spl, int nt, float grad_scale, int warps_per_block, float* __restrict__ grad) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * warps_per_block + warp;
@@ -265,51 +533,121 @@ ctc_grad_kernel(const float* __restrict__ logits, const float* __restrict__ lse,
   float* out = grad + row * C;
   const int Tb = min(seq_len[b], T);
   if (t >= Tb || skip_in[b]) {
-    for (int c = lane; c < C; c += 32) out[c] = 0.f;
+    if (grad)
+      for (int c = lane; c < C; c += 32) out[c] = 0.f;
+    if (spl > 0 && lane == 0) lse[row] = 0.f;
     return;
   }
   const float* x = logits + row * C;
-  const float l = lse[row];
-  for (int c = lane; c < C; c += 32) g[c] = __expf(x[c] - l);
+  float l, unit = 1.f;         // g[] holds softmax * unit
+  if (spl > 0) {
+    // the row once through registers (kLd independent 128-byte loads per warp in flight: at C = 3001 the kernel is
+    // HBM-bound and 8 in flight measured 2.2 TB/s) into shared memory, running maximum
+    constexpr int kLd = 24;
+    float m = -INFINITY;
+    for (int c0 = 0; c0 < C; c0 += 32 * kLd) {
+      float v[kLd];
+#pragma unroll
+      for (int j = 0; j < kLd; ++j) {
+        const int c = c0 + j * 32 + lane;
+        v[j] = c < C ? __ldg(x + c) : -INFINITY;
+      }
+#pragma unroll
+      for (int j = 0; j < kLd; ++j) {
+        const int c = c0 + j * 32 + lane;
+        if (c < C) { g[c] = v[j]; m = fmaxf(m, v[j]); }
+      }
+    }
+    m = warp_max(m);
+    __syncwarp();
+    float sum = 0.f;
+    for (int c = lane; c < C; c += 32) { const float e = __expf(g[c] - m); g[c] = e; sum += e; }
+    sum = warp_sum(sum);
+    l = m + __logf(sum);
+    if (lane == 0) lse[row] = l;
+    if (!grad) return;
+    unit = sum;                // normalised in the output pass
+  } else {
+    l = lse[row];
+    for (int c = lane; c < C; c += 32) g[c] = __expf(x[c] - l);
+  }
   __syncwarp();
+  const float out_scale = grad_scale / unit;
   {
     const int off = label_offsets[b];
     const int L = label_offsets[b + 1] - off;
     const int S = 2 * L + 1;
     const float* ar = alpha + ((int64_t)b * T + t) * S_pad;
     const float* br = beta + ((int64_t)b * T + t) * S_pad;
-    auto ix = [&](int s) { return s; };
-    const float xb = x[blank] - l;
-    // pass 1: Z = logsumexp_s (alpha + beta - lp): equals log p up to the per-row shifts
-    float m = -INFINITY;
-    for (int s = lane; s < S; s += 32) {
-      const float lp = (s & 1) ? (x[labels_flat[off + (s >> 1)]] - l) : xb;
-      m = fmaxf(m, ar[ix(s)] + br[ix(s)] - lp);
-    }
-    m = warp_max(m);
-    if (m != -INFINITY) {          // -inf: no alignment passes through this frame -> grad = softmax
-      float z = 0.f;
+    if (spl > 0) {
+      // team-sweep rows (raw-logit lattice, <= 512 stored cells): every lane keeps its <= 16 terms
+      // alpha + beta - x[class] and their classes in registers -- one read of the lattice rows, one label gather
+      constexpr int kMax = 16;
+      const int n_idx = nt * spl;
+      float d[kMax]; int cc[kMax];
+      float m = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < kMax; ++j) {
+        const int i = j * 32 + lane;
+        d[j] = -INFINITY; cc[j] = -1;
+        if (i < n_idx) {
+          const int s = (i & (kTeam - 1)) * spl + (i / kTeam);       // nt == kTeam
+          if (s < S) {
+            cc[j] = (s & 1) ? labels_flat[off + (s >> 1)] : blank;
+            d[j] = fmaf(ar[i] + br[i], kLn2, -__ldg(x + cc[j]));     // rows are in base-2 log units
+            m = fmaxf(m, d[j]);
+          }
+        }
+      }
+      m = warp_max(m);
+      if (m != -INFINITY) {        // -inf: no alignment passes through this frame -> grad = softmax
+        float z = 0.f;
+#pragma unroll
+        for (int j = 0; j < kMax; ++j) { d[j] = __expf(d[j] - m); z += d[j]; }     // exp(-inf) = 0 for the unused cells
+        z = warp_sum(z);
+        const float k = unit / z;
+        float blank_occ = 0.f;
+#pragma unroll
+        for (int j = 0; j < kMax; ++j) {
+          if (cc[j] == blank) blank_occ += d[j];
+          else if (cc[j] >= 0) atomicAdd(&g[cc[j]], -d[j] * k);
+        }
+        blank_occ = warp_sum(blank_occ);
+        __syncwarp();
+        if (lane == 0) g[blank] -= blank_occ * k;
+        __syncwarp();
+      }
+    } else {
+      const float xb = x[blank] - l;
+      // pass 1: Z = logsumexp_s (alpha + beta - lp): equals log p up to the per-row shifts
+      float m = -INFINITY;
       for (int s = lane; s < S; s += 32) {
         const float lp = (s & 1) ? (x[labels_flat[off + (s >> 1)]] - l) : xb;
-        z += __expf(ar[ix(s)] + br[ix(s)] - lp - m);
+        m = fmaxf(m, ar[s] + br[s] - lp);
       }
-      z = warp_sum(z);
-      const float Z = m + __logf(z);
-      float blank_occ = 0.f;
-      // blanks: even s, reduced in registers
-      for (int s = 2 * lane; s < S; s += 64) blank_occ += __expf(ar[ix(s)] + br[ix(s)] - xb - Z);
-      // labels: odd s, scattered with shared-memory atomics
-      for (int s = 2 * lane + 1; s < S; s += 64) {
-        const int c = labels_flat[off + (s >> 1)];
-        atomicAdd(&g[c], -__expf(ar[ix(s)] + br[ix(s)] - (x[c] - l) - Z));
+      m = warp_max(m);
+      if (m != -INFINITY) {
+        float z = 0.f;
+        for (int s = lane; s < S; s += 32) {
+          const float lp = (s & 1) ? (x[labels_flat[off + (s >> 1)]] - l) : xb;
+          z += __expf(ar[s] + br[s] - lp - m);
+        }
+        z = warp_sum(z);
+        const float Z = m + __logf(z);
+        float blank_occ = 0.f;
+        for (int s = 2 * lane; s < S; s += 64) blank_occ += __expf(ar[s] + br[s] - xb - Z);
+        for (int s = 2 * lane + 1; s < S; s += 64) {
+          const int c = labels_flat[off + (s >> 1)];
+          atomicAdd(&g[c], -__expf(ar[s] + br[s] - (x[c] - l) - Z));
+        }
+        blank_occ = warp_sum(blank_occ);
+        __syncwarp();
+        if (lane == 0) g[blank] -= blank_occ;
+        __syncwarp();
       }
-      blank_occ = warp_sum(blank_occ);
-      __syncwarp();
-      if (lane == 0) g[blank] -= blank_occ;
-      __syncwarp();
     }
   }
-  for (int c = lane; c < C; c += 32) out[c] = grad_scale * g[c];
+  for (int c = lane; c < C; c += 32) out[c] = out_scale * g[c];
 }
 
 struct CtcWs {
@@ -317,7 +655,9 @@ struct CtcWs {
 };
 
 static size_t ctc_ws_layout(int T, int B, int max_label_len, void* base, CtcWs* w) {
-  const int S_pad = (int)align_up(2 * (size_t)max_label_len + 1, 32);
+  const int S_max_ = 2 * max_label_len + 1;
+  // team sweep (S <= 512): kTeam * SPL with SPL in {2, 4}; fallback: linear rows
+  const int S_pad = S_max_ <= 2 * kTeam ? 2 * kTeam : (S_max_ <= 4 * kTeam ? 4 * kTeam : (int)align_up((size_t)S_max_, 32));
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
   size_t o_lse = take((size_t)T * B * 4);
@@ -360,11 +700,37 @@ extern "C" int b2_ctc_loss_grad(const float* logits, const int32_t* labels_flat,
     return B2_ERR_WORKSPACE;
   }
   const int64_t rows = (int64_t)T * B;
+  const int S_max = 2 * max_label_len + 1;
+  const bool warp_path = S_max <= 512;
+  int wpb = kWarpsPerBlock;
+  while (wpb > 1 && (size_t)wpb * C * 4 > 160 * 1024) wpb >>= 1;
+  const size_t gsmem = (size_t)wpb * C * 4;
+  B2_CHECK_ARG(gsmem <= 200 * 1024, "b2_ctc_loss_grad: C=%d too large", C);
+  B2_CUDA(cudaFuncSetAttribute(ctc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+
+  if (warp_path) {
+    const int spl = w.S_pad / kTeam;       // 2 or 4
+    dim3 grid(B, 2);
+    if (spl == 2)
+      ctc_ab_team_kernel<2><<<grid, kTeam, 0, stream>>>(logits, labels_flat, label_offsets, seq_len, T, B, C, blank,
+                                                        ignore_longer, w.alpha, w.beta, w.logp, w.skip, loss);
+    else
+      ctc_ab_team_kernel<4><<<grid, kTeam, 0, stream>>>(logits, labels_flat, label_offsets, seq_len, T, B, C, blank,
+                                                        ignore_longer, w.alpha, w.beta, w.logp, w.skip, loss);
+    B2_LAUNCH_CHECK();
+    // row pass: logsumexp of every row (+ gradient when asked for)
+    ctc_grad_kernel<<<cdiv(rows, wpb), wpb * 32, gsmem, stream>>>(
+        logits, w.lse, labels_flat, label_offsets, seq_len, w.alpha, w.beta, w.skip, T, B, C, blank, w.S_pad, spl,
+        kTeam, grad_scale, wpb, grad);
+    B2_LAUNCH_CHECK();
+    ctc_finalize_kernel<<<B, 128, 0, stream>>>(w.lse, seq_len, w.skip, T, B, w.logp, loss);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+  }
+
   ctc_lse_kernel<<<cdiv(rows, kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream>>>(
       logits, seq_len, T, B, C, w.lse);
   B2_LAUNCH_CHECK();
-
-  const int S_max = 2 * max_label_len + 1;
   {
     int NT = (int)align_up((size_t)S_max, 32);
     int spt = 1;
@@ -385,17 +751,10 @@ extern "C" int b2_ctc_loss_grad(const float* logits, const int32_t* labels_flat,
 #undef LAUNCH_AB
     B2_LAUNCH_CHECK();
   }
-
   if (grad) {
-    int wpb = kWarpsPerBlock;
-    while (wpb > 1 && (size_t)wpb * C * 4 > 160 * 1024) wpb >>= 1;
-    const size_t gsmem = (size_t)wpb * C * 4;
-    B2_CHECK_ARG(gsmem <= 200 * 1024, "b2_ctc_loss_grad: C=%d too large", C);
-    B2_CUDA(cudaFuncSetAttribute(ctc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)gsmem));
     ctc_grad_kernel<<<cdiv(rows, wpb), wpb * 32, gsmem, stream>>>(
-        logits, w.lse, labels_flat, label_offsets, seq_len, w.alpha, w.beta, w.logp, w.skip, T,
-        B, C, blank, w.S_pad, grad_scale, wpb, grad);
+        logits, w.lse, labels_flat, label_offsets, seq_len, w.alpha, w.beta, w.skip, T, B, C, blank, w.S_pad, 0,
+        0, grad_scale, wpb, grad);
     B2_LAUNCH_CHECK();
   }
   return B2_OK;
