@@ -309,6 +309,11 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&stfree[c * 2 + p]);
+        if (a.progress) {
+          // this direction has now covered every frame of chunk td / chunk_T (fw ascends, bw descends)
+          const bool done = dir ? (td % a.chunk_T == 0) : ((td + 1) % a.chunk_T == 0 || td == T - 1);
+          if (done && lane == 0) { __threadfence(); atomicAdd(a.progress + td / a.chunk_T, 1u); }
+        }
       }
     }
   } else {
@@ -852,6 +857,12 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
         if (ctid == 0) {
           mbar_arrive(&gempty[c * BGS + stage]);
           if (s + 1 < T) mbar_arrive(&bready[c]);
+          if (a.progress && s > 0) {
+            // every thread of the team passed the barrier above after issuing its dG stores of step s-1
+            const int tdp = dir ? s - 1 : T - s;
+            const bool done = dir ? ((tdp + 1) % a.chunk_T == 0) : (tdp % a.chunk_T == 0);
+            if (done) { __threadfence(); atomicAdd(a.progress + tdp / a.chunk_T, 1u); }
+          }
         }
         // dG (operand of the time-batched weight/input-gradient GEMMs) goes out after the hand-off to the
         // issuers: the stores overlap the step's MMAs instead of delaying them
@@ -924,6 +935,10 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
           a.dbg[6] += b7 - b6;   // fence + bar + sends
         }
 #endif
+      }
+      if (a.progress) {          // the last step's stores complete the outermost chunk of this direction
+        named_bar_sync(1 + c, GTHREADS);
+        if (ctid == 0) { __threadfence(); atomicAdd(a.progress + (dir ? (T - 1) / a.chunk_T : 0), 1u); }
       }
       // flush the register-accumulated bias / peephole gradients (batch quads x chains x clusters)
       if (a.dbias) {

@@ -21,6 +21,9 @@ struct RecFwdArgs {
   float* gates; float* cs;    // reserve ([T,B,2,H,4], [T,B,2,H]) or null
   float* final_state;         // [4,B,H] or null
   long long* dbg;             // optional phase timers (clock64 sums), cluster 0 / CTA 0 only
+  unsigned* progress;         // optional [ceil(T / chunk_T)] counters: +1 per (CTA, chain) once its outputs of every
+  int chunk_T;                //   frame of the chunk [k*chunk_T, (k+1)*chunk_T) are stored (consumer: the next layer's
+                              //   gate GEMM, launched chunk by chunk while this kernel is still running)
 };
 
 struct RecBwdArgs {
@@ -37,6 +40,8 @@ struct RecBwdArgs {
   int wait_mode;              // how the gate warps wait for the peers' partials (see the kernel; B2_REC_WAIT)
   unsigned* resident;         // optional device counter: +1 per cluster once all of its CTAs are running
   long long* dbg;
+  unsigned* progress;         // optional per-chunk counters (see RecFwdArgs): +1 per (CTA, chain) once dG of every frame
+  int chunk_T;                //   of the chunk is stored -> the dX GEMM runs chunk by chunk beside this kernel
 };
 
 bool rec_tc_supported(int H);

@@ -17,6 +17,8 @@ static size_t pad8(size_t x) { return (x + 7) / 8 * 8; }
 
 struct TcWork {
   float* G;                  // [TB, 8H] fp32 gate pre-activations (forward)
+  float* G2;                 // second buffer: consecutive layers alternate, so that layer l+1's chunked gate GEMM can
+                             // fill its G while layer l's recurrence still reads its own
   __nv_bfloat16* dG;         // [TB, 8H] bf16 gate gradients (backward; only when the reserve holds none)
   __nv_bfloat16* xb;         // [TB, pad8(D)] bf16 copy of x when the caller has none
   __nv_bfloat16* wx;         // [D, 8H] packed input weights
@@ -35,6 +37,7 @@ static size_t tc_work_layout(const b2_lstm_desc* d, void* base, TcWork* w) {
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
   // G (forward) and dG (backward) are never live together
   const size_t oG = take(TB * 8 * H * 4);
+  const size_t oG2 = take(TB * 8 * H * 4);
   const size_t oxb = take(TB * pad8(D) * 2);
   const size_t owx = take(D * 8 * H * 2);
   const size_t ob = take(8 * H * 4);
@@ -46,7 +49,7 @@ static size_t tc_work_layout(const b2_lstm_desc* d, void* base, TcWork* w) {
   const size_t odym = d->keep_prob < 1.f ? take(TB * 2 * H * 4) : 0;
   if (w) {
     char* p = (char*)base;
-    w->G = (float*)(p + oG); w->dG = (__nv_bfloat16*)(p + oG); w->xb = (__nv_bfloat16*)(p + oxb);
+    w->G = (float*)(p + oG); w->G2 = (float*)(p + oG2); w->dG = (__nv_bfloat16*)(p + oG); w->xb = (__nv_bfloat16*)(p + oxb);
     w->wx = (__nv_bfloat16*)(p + owx); w->bias = (float*)(p + ob); w->wh = (uint16_t*)(p + owh);
     w->whT = (uint16_t*)(p + owt); w->dwx = (float*)(p + odwx); w->dwh = (float*)(p + odwh);
     w->dbias = (float*)(p + odb);
@@ -305,6 +308,44 @@ static int pack_weights(const b2_lstm_desc* d, const b2_lstm_params* fw, const b
   return B2_OK;
 }
 
+// ------------------------------------------------------------------ forward chunk chain
+// Layer l+1's time-batched gate GEMM needs layer l's outputs of BOTH directions; frame chunk k is complete once the
+// forward direction has passed it from below and the backward direction from above, i.e. the middle chunks first and
+// all but the two outermost ones well before the recurrence kernel ends.  The recurrence kernel counts finished
+// (CTA, chain) pairs per chunk (RecFwdArgs::progress); when the next layer's input IS that kernel's bf16 output, its
+// gate GEMM is issued chunk by chunk on a second stream behind cuStreamWaitValue32 on those counters and runs on the
+// SMs the clusters leave free, so that only the two outermost chunks remain on the critical path.
+struct FwdChain {
+  cudaStream_t s = nullptr;
+  cudaEvent_t ev_launch = nullptr, ev_done = nullptr;
+  unsigned* progress[2] = {nullptr, nullptr};   // [kMaxChunks] each, alternating between consecutive kernels
+  int pp = 0;
+  int gpar = 0;                                 // which G buffer the most recent layer used
+  bool valid = false;
+  const __nv_bfloat16* y_lp = nullptr;          // output of the most recent recurrence launch
+  int T = 0, B = 0, cols = 0, chunk_T = 0, nchunks = 0, free_sms = 0;
+  unsigned expected = 0;
+};
+constexpr int kMaxChunks = 64;
+static FwdChain g_fwd_chain[16];
+static FwdChain* fwd_chain() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  FwdChain* c = &g_fwd_chain[dev & 15];
+  if (!c->s) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    cudaStreamCreateWithPriority(&c->s, cudaStreamNonBlocking, hi);
+    cudaEventCreateWithFlags(&c->ev_launch, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming);
+    for (int i = 0; i < 2; ++i) {
+      cudaMalloc(&c->progress[i], kMaxChunks * sizeof(unsigned));
+      cudaMemset(c->progress[i], 0, kMaxChunks * sizeof(unsigned));
+    }
+  }
+  return c;
+}
+
 int tc_layer_forward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16* x_lp,
                      const int32_t* seq_len, const b2_lstm_params* fw, const b2_lstm_params* bw,
                      float* y, float* final_state, void* reserve, void* workspace,
@@ -318,21 +359,83 @@ int tc_layer_forward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16*
   int rc = tc_backward_join(stream);
   if (rc) return rc;
   if (r.wpack) use_reserve_pack(d, r.wpack, &w);      // backward will reuse this pack (incl. the transposed slices)
-  rc = pack_weights(d, fw, bw, w, r.wpack != nullptr, stream);
-  if (rc) return rc;
-  const __nv_bfloat16* xa = x_lp;
-  int ldx = D;
-  if (!xa || (D % 8)) {
-    ldx = (int)pad8(D);
-    rc = cast_f32_bf16(x, TB, D, D, w.xb, ldx, stream);
+  FwdChain* fc = fwd_chain();
+  fc->gpar ^= 1;
+  float* Gbuf = fc->gpar ? w.G2 : w.G;
+  const int want_chunks = env_int("B2_FWD_CHUNKS", 16);
+  const bool dbg_run = env_int("B2_REC_DBG", 0) != 0;
+  // the chunk chain: this layer's input is the bf16 output of the recurrence launched last (still running, typically)
+  const bool chained = want_chunks > 1 && !dbg_run && stream_wait_value_fn() != nullptr && r.wpack != nullptr &&
+                       fc->valid && x_lp != nullptr && x_lp == fc->y_lp && fc->T == T && fc->B == B && fc->cols == D &&
+                       (D % 8) == 0 && fc->nchunks > 1;
+  if (chained) {
+    cudaStream_t ss = fc->s;
+    B2_CUDA(cudaStreamWaitEvent(ss, fc->ev_launch, 0));      // counters zeroed, weights of this step final
+    rc = pack_weights(d, fw, bw, w, true, ss);
     if (rc) return rc;
-    xa = w.xb;
+    // completion order: chunk k is complete when fw has passed k+1 chunks and bw nchunks-k
+    int order[kMaxChunks];
+    const int K = fc->nchunks;
+    for (int k = 0; k < K; ++k) order[k] = k;
+    for (int i = 1; i < K; ++i)
+      for (int j = i; j > 0; --j) {
+        const int a0 = order[j - 1], a1 = order[j];
+        const int c0 = (a0 + 1 > K - a0) ? a0 + 1 : K - a0, c1 = (a1 + 1 > K - a1) ? a1 + 1 : K - a1;
+        if (c1 < c0) { order[j - 1] = a1; order[j] = a0; } else break;
+      }
+    const unsigned* prog = fc->progress[fc->pp];
+    for (int i = 0; i < K && !rc; ++i) {
+      const int k = order[i];
+      const int t0 = k * fc->chunk_T, t1 = (t0 + fc->chunk_T < T) ? t0 + fc->chunk_T : T;
+      const size_t r0 = (size_t)t0 * B;
+      if (stream_wait_value_fn()(ss, (unsigned long long)(uintptr_t)(prog + k), fc->expected, 0u /* CU_STREAM_WAIT_VALUE_GEQ */) != 0) {
+        set_error("tc_layer_forward: cuStreamWaitValue32 failed");
+        rc = B2_ERR_CUDA;
+        break;
+      }
+      // the two outermost chunks complete only when the recurrence kernel ends: no SM cap for them
+      gemm_set_cta_limit(i + 2 < K ? fc->free_sms : 0);
+      rc = gemm_bf16_tc(0, 1, (t1 - t0) * B, 8 * H, D, 1.f, x_lp + r0 * D, D, w.wx, 8 * H, Gbuf + r0 * 8 * H, 8 * H,
+                        w.bias, EPI_STORE_F32, 0, ss);
+    }
+    gemm_set_cta_limit(0);
+    if (rc) return rc;
+    B2_CUDA(cudaEventRecord(fc->ev_done, ss));
+    B2_CUDA(cudaStreamWaitEvent(stream, fc->ev_done, 0));
+  } else {
+    rc = pack_weights(d, fw, bw, w, r.wpack != nullptr, stream);
+    if (rc) return rc;
+    const __nv_bfloat16* xa = x_lp;
+    int ldx = D;
+    if (!xa || (D % 8)) {
+      ldx = (int)pad8(D);
+      rc = cast_f32_bf16(x, TB, D, D, w.xb, ldx, stream);
+      if (rc) return rc;
+      xa = w.xb;
+    }
+    // G[TB, 8H] = X . Wx_packed + bias_packed   (both directions in one GEMM)
+    rc = gemm_bf16_tc(0, 1, TB, 8 * H, D, 1.f, xa, ldx, w.wx, 8 * H, Gbuf, 8 * H, w.bias,
+                      EPI_STORE_F32, 0, stream);
+    if (rc) return rc;
   }
-  // G[TB, 8H] = X . Wx_packed + bias_packed   (both directions in one GEMM)
-  rc = gemm_bf16_tc(0, 1, TB, 8 * H, D, 1.f, xa, ldx, w.wx, 8 * H, w.G, 8 * H, w.bias,
-                    EPI_STORE_F32, 0, stream);
-  if (rc) return rc;
+  fc->valid = false;
   RecFwdArgs ra;
+  ra.progress = nullptr; ra.chunk_T = 1;
+  if (want_chunks > 1 && !dbg_run && r.y_lp && T >= 4 * want_chunks) {
+    const int K0 = want_chunks < kMaxChunks ? want_chunks : kMaxChunks;
+    const int Tc = cdiv(T, K0);
+    fc->pp ^= 1;
+    B2_CUDA(cudaMemsetAsync(fc->progress[fc->pp], 0, kMaxChunks * sizeof(unsigned), stream));
+    B2_CUDA(cudaEventRecord(fc->ev_launch, stream));
+    ra.progress = fc->progress[fc->pp]; ra.chunk_T = Tc;
+    const int ng = cdiv(B, RN);
+    const int nch_env = env_int("B2_REC_NCHAIN", 0);
+    const int nch = nch_env > 0 ? (nch_env > 2 ? 2 : nch_env) : (ng >= 2 ? 2 : 1);
+    const int rec_ctas = 2 * cdiv(ng, nch) * (H / RU);
+    fc->valid = true; fc->y_lp = r.y_lp; fc->T = T; fc->B = B; fc->cols = 2 * H; fc->chunk_T = Tc;
+    fc->nchunks = cdiv(T, Tc); fc->expected = (unsigned)(2 * ng * (H / RU));
+    fc->free_sms = num_sms() - rec_ctas > 8 ? num_sms() - rec_ctas : 8;
+  }
   ra.T = T; ra.B = B; ra.H = H; ra.NG = 0; ra.seq_len = seq_len; ra.wpack = w.wh;
   const b2_lstm_params* P[2] = {fw, bw};
   for (int dir = 0; dir < 2; ++dir) {
@@ -348,7 +451,7 @@ int tc_layer_forward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16*
     if (!dbg_buf) cudaMalloc(&dbg_buf, 64 * sizeof(long long));
     cudaMemsetAsync(dbg_buf, 0, 64 * sizeof(long long), stream);
     ra.dbg = dbg_buf;
-    rc = rec_tc_forward(ra, w.G, env_int("B2_REC_NCHAIN", 0), env_int("B2_REC_GW", 0), stream);
+    rc = rec_tc_forward(ra, Gbuf, env_int("B2_REC_NCHAIN", 0), env_int("B2_REC_GW", 0), stream);
     long long hb[32];
     cudaMemcpyAsync(hb, dbg_buf, sizeof(hb), cudaMemcpyDeviceToHost, stream);
     cudaStreamSynchronize(stream);
@@ -360,7 +463,7 @@ int tc_layer_forward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16*
     return rc;
   }
   prof_record(0, stream);
-  rc = rec_tc_forward(ra, w.G, env_int("B2_REC_NCHAIN", 0), env_int("B2_REC_GW", 0), stream);
+  rc = rec_tc_forward(ra, Gbuf, env_int("B2_REC_NCHAIN", 0), env_int("B2_REC_GW", 0), stream);
   prof_record(1, stream);
   return rc;
 }
@@ -417,6 +520,22 @@ int tc_layer_backward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16
   const int nch = nchain > 0 ? (nchain > 2 ? 2 : nchain) : (ng >= 2 ? 2 : 1);
   const int nclusters = 2 * cdiv(ng, nch);
   ba.resident = use_side ? sc->resident : nullptr;
+  // dX chunk by chunk beside the BPTT kernel (same scheme as the forward chunk chain, inside one call)
+  FwdChain* fc = fwd_chain();
+  fc->valid = false;
+  const int want_chunks = env_int("B2_BWD_CHUNKS", 16);
+  const bool chunk_dx = want_chunks > 1 && dx != nullptr && stream_wait_value_fn() != nullptr && T >= 4 * want_chunks &&
+                        !env_int("B2_REC_DBG", 0);
+  int dx_chunk_T = T, dx_nchunks = 1;
+  ba.progress = nullptr; ba.chunk_T = 1;
+  if (chunk_dx) {
+    dx_chunk_T = cdiv(T, want_chunks < kMaxChunks ? want_chunks : kMaxChunks);
+    dx_nchunks = cdiv(T, dx_chunk_T);
+    fc->pp ^= 1;
+    B2_CUDA(cudaMemsetAsync(fc->progress[fc->pp], 0, kMaxChunks * sizeof(unsigned), stream));
+    B2_CUDA(cudaEventRecord(fc->ev_launch, stream));
+    ba.progress = fc->progress[fc->pp]; ba.chunk_T = dx_chunk_T;
+  }
   if (env_int("B2_REC_DBG", 0)) {          // phase timers: needs the B2_BUILD_VARIANT=timing library
     static long long* dbg_buf = nullptr;
     if (!dbg_buf) cudaMalloc(&dbg_buf, 64 * sizeof(long long));
@@ -461,7 +580,39 @@ int tc_layer_backward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16
     if (rc) return rc;
     xa = w.xb;
   }
-  if (dx) {
+  if (dx && chunk_dx && dx_nchunks > 1) {
+    cudaStream_t ss = fc->s;
+    B2_CUDA(cudaStreamWaitEvent(ss, fc->ev_launch, 0));      // counters zeroed, dx buffer free
+    const int K = dx_nchunks;
+    int order[kMaxChunks];
+    for (int k = 0; k < K; ++k) order[k] = k;
+    for (int i = 1; i < K; ++i)
+      for (int j = i; j > 0; --j) {
+        const int a0 = order[j - 1], a1 = order[j];
+        const int c0 = (a0 + 1 > K - a0) ? a0 + 1 : K - a0, c1 = (a1 + 1 > K - a1) ? a1 + 1 : K - a1;
+        if (c1 < c0) { order[j - 1] = a1; order[j] = a0; } else break;
+      }
+    const unsigned expected = (unsigned)(2 * ng * (H / RU));
+    int free_sms = num_sms() - nclusters * (H / RU);
+    if (free_sms < 16) free_sms = 16;
+    for (int i = 0; i < K && !rc; ++i) {
+      const int k = order[i];
+      const int t0 = k * dx_chunk_T, t1 = (t0 + dx_chunk_T < T) ? t0 + dx_chunk_T : T;
+      const size_t r0 = (size_t)t0 * B;
+      if (stream_wait_value_fn()(ss, (unsigned long long)(uintptr_t)(ba.progress + k), expected, 0u /* CU_STREAM_WAIT_VALUE_GEQ */) != 0) {
+        set_error("tc_layer_backward: cuStreamWaitValue32 failed");
+        rc = B2_ERR_CUDA;
+        break;
+      }
+      gemm_set_cta_limit(i + 2 < K ? free_sms : 0);
+      rc = gemm_bf16_tc(0, 0, (t1 - t0) * B, D, 8 * H, 1.f, dG + r0 * 8 * H, 8 * H, w.wx, 8 * H, dx + r0 * D, D, nullptr,
+                        EPI_STORE_F32, 0, ss);
+    }
+    gemm_set_cta_limit(0);
+    if (rc) return rc;
+    B2_CUDA(cudaEventRecord(fc->ev_done, ss));
+    B2_CUDA(cudaStreamWaitEvent(stream, fc->ev_done, 0));
+  } else if (dx) {
     rc = gemm_bf16_tc(0, 0, TB, D, 8 * H, 1.f, dG, 8 * H, w.wx, 8 * H, dx, D, nullptr,
                       EPI_STORE_F32, 0, stream);
     if (rc) return rc;

@@ -105,3 +105,36 @@ def test_grid_resident_wide_layer(cuda, T, B, D, H):
         os.environ.pop("B2_WIDE_REC", None)
     # the fallback multiplies h by fp32 recurrent weights, the resident kernel by their bf16 rounding
     assert np.abs(got[0] - old[0]).max() < 2e-2, np.abs(got[0] - old[0]).max()
+
+
+def test_forward_chunk_chain_bit_identical(cuda):
+    """Layer l+1's gate GEMM issued chunk by chunk behind the progress counters of layer l's still-running recurrence
+    (lstm_tc.cu, FwdChain) must give exactly the logits of the unchunked schedule: same GEMM, same K order per output
+    element, only the launch schedule differs.  T = 96 -> 8 chunks of 12 frames, ragged lengths, 4 layers."""
+    import torch
+    from tensorflow_end2end_speech_recognition_b200.models.ctc.ctc import CTC
+    rng = np.random.RandomState(3)
+    B, T, D, H, L, C = 24, 96, 40, 128, 4, 12
+    x = rng.randn(B, T, D).astype(np.float32)
+    seq = rng.randint(T // 2, T + 1, size=B).astype(np.int32)
+    seq[0] = T
+    labels = [list(rng.randint(0, C - 1, size=int(rng.randint(3, 9)))) for _ in range(B)]
+    outs = {}
+    for chunks in ("0", "8", "5"):
+        os.environ["B2_FWD_CHUNKS"] = chunks
+        try:
+            model = CTC(encoder_type="blstm", input_size=D, num_units=H, num_layers=L, num_classes=C,
+                        parameter_init=0.1, clip_grad_norm=5.0, precision="bf16", device=cuda, seed=4)
+            for _ in range(2):          # second pass: the chain state of the first one is stale, must not match
+                loss, logits = model.compute_loss(x, labels, seq, keep_prob=1.0)
+                model._backward()
+            torch.cuda.synchronize()
+            outs[chunks] = (float(loss), logits.cpu().numpy().copy(), model.flat_grads.cpu().numpy().copy())
+        finally:
+            os.environ.pop("B2_FWD_CHUNKS", None)
+    for chunks in ("8", "5"):
+        assert outs[chunks][0] == outs["0"][0]
+        assert np.array_equal(outs[chunks][1], outs["0"][1])
+        # weight gradients are accumulated with split-K atomics: equal up to summation order
+        g0 = outs["0"][2]
+        assert np.abs(outs[chunks][2] - g0).max() <= 1e-5 * np.abs(g0).max()
