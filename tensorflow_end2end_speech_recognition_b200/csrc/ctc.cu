@@ -10,8 +10,11 @@
 //                              boundary) -- no shared-memory column, one block barrier per lattice step; the
 //                              lattice runs on RAW logits (the per-frame normaliser is added by the finaliser),
 //                              emissions prefetched by a cp.async ring; rows spilled [B,T,S_pad] lane-interleaved
-//     ctc_grad_kernel          one warp per (t,b) row: logsumexp of the row (written to lse[t,b]), softmax -
-//                              occupancy (row-local normalisation), occupancy scattered by label in shared memory
+//     ctc_softmax_rows_kernel  one warp per (t,b) row, the row in registers (all of its loads in flight at once):
+//                              logsumexp (written to lse[t,b]), softmax streamed out; on a second stream, BESIDE the
+//                              sweep (it needs no lattice)
+//     ctc_occ_rows_kernel      occupancies (row-local normalisation) subtracted from the stored rows with red.global
+//                              (C > 3072: ctc_grad_kernel, the row in shared memory, does both after the sweep)
 //     ctc_finalize_kernel      loss[b] = -(log p' - sum_t lse[t,b])
 //   long labels (fallback): ctc_lse_kernel, ctc_alpha_beta_kernel (one CTA per (utterance, direction), column in
 //     shared memory), ctc_grad_kernel reading the precomputed lse
@@ -650,6 +653,122 @@ ctc_grad_kernel(const float* __restrict__ logits, float* __restrict__ lse,
   for (int c = lane; c < C; c += 32) out[c] = out_scale * g[c];
 }
 
+// Row passes of the team-sweep path for C <= 32 * NV (NV <= 96).
+// (1) ctc_softmax_rows_kernel: needs no lattice -> runs on a second stream BESIDE the sweep.  The whole row lives in
+//     REGISTERS (every load of the row in flight at once: 12 KB per warp at C = 3001 -- a shared-memory version with
+//     24 x 128 B in flight measured 2.9 TB/s): logsumexp -> lse[t,b], grad_scale * softmax streamed straight out.
+// (2) ctc_occ_rows_kernel, after both: the <= 512 lattice terms of the row cached in registers, occupancies (row-local
+//     normalisation) subtracted from the stored row with red.global.
+template <int NV>
+__global__ void __launch_bounds__(128)
+ctc_softmax_rows_kernel(const float* __restrict__ logits, float* __restrict__ lse, const int* __restrict__ seq_len,
+                        int T, int B, int C, float grad_scale, float* __restrict__ grad) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 4 + warp;
+  if (row >= (int64_t)T * B) return;
+  const int t = (int)(row / B), b = (int)(row % B);
+  float* out = grad + row * C;
+  if (t >= min(seq_len[b], T)) {
+    if (grad)
+      for (int c = lane; c < C; c += 32) out[c] = 0.f;
+    if (lane == 0) lse[row] = 0.f;
+    return;
+  }
+  const float* x = logits + row * C;
+  float v[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = j * 32 + lane;
+    v[j] = c < C ? __ldg(x + c) : -INFINITY;
+  }
+  float m = v[0];
+#pragma unroll
+  for (int j = 1; j < NV; ++j) m = fmaxf(m, v[j]);
+  m = warp_max(m);
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) { v[j] = __expf(v[j] - m); sum += v[j]; }
+  sum = warp_sum(sum);
+  if (lane == 0) lse[row] = m + __logf(sum);
+  if (!grad) return;
+  const float k0 = grad_scale / sum;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = j * 32 + lane;
+    if (c < C) out[c] = v[j] * k0;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+ctc_occ_rows_kernel(const float* __restrict__ logits, const int* __restrict__ labels_flat,
+                    const int* __restrict__ label_offsets, const int* __restrict__ seq_len,
+                    const float* __restrict__ alpha, const float* __restrict__ beta, const int* __restrict__ skip_in,
+                    int T, int B, int C, int blank, int S_pad, int spl, float grad_scale, float* __restrict__ grad) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 4 + warp;
+  if (row >= (int64_t)T * B) return;
+  const int t = (int)(row / B), b = (int)(row % B);
+  float* out = grad + row * C;
+  if (t >= min(seq_len[b], T)) return;
+  if (skip_in[b]) {                  // skipped / rejected utterance: zero gradient (the softmax pass could not know)
+    for (int c = lane; c < C; c += 32) out[c] = 0.f;
+    return;
+  }
+  const float* x = logits + row * C;
+  const int off = label_offsets[b];
+  const int L = label_offsets[b + 1] - off;
+  const int S = 2 * L + 1;
+  const float* ar = alpha + ((int64_t)b * T + t) * S_pad;
+  const float* br = beta + ((int64_t)b * T + t) * S_pad;
+  constexpr int kMax = 16;
+  const int n_idx = kTeam * spl;
+  float d[kMax]; int cc[kMax];
+  float dm = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < kMax; ++j) {
+    const int i = j * 32 + lane;
+    d[j] = -INFINITY; cc[j] = -1;
+    if (i < n_idx) {
+      const int s = (i & (kTeam - 1)) * spl + (i / kTeam);
+      if (s < S) {
+        cc[j] = (s & 1) ? labels_flat[off + (s >> 1)] : blank;
+        d[j] = fmaf(ar[i] + br[i], kLn2, -__ldg(x + cc[j]));     // rows are in base-2 log units, raw logits
+        dm = fmaxf(dm, d[j]);
+      }
+    }
+  }
+  dm = warp_max(dm);
+  if (dm == -INFINITY) return;       // no alignment passes through this frame -> grad = softmax
+  float z = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMax; ++j) { d[j] = __expf(d[j] - dm); z += d[j]; }
+  z = warp_sum(z);
+  const float k1 = -grad_scale / z;
+  float blank_occ = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMax; ++j) {
+    if (cc[j] == blank) blank_occ += d[j];
+    else if (cc[j] >= 0) atomicAdd(out + cc[j], d[j] * k1);
+  }
+  blank_occ = warp_sum(blank_occ);
+  if (lane == 0) atomicAdd(out + blank, blank_occ * k1);
+}
+
+// second stream + fork/join events of the row pass (one set per device)
+struct CtcSide { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static CtcSide g_ctc_side[16];
+static CtcSide* ctc_side() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  CtcSide* c = &g_ctc_side[dev & 15];
+  if (!c->s) {
+    cudaStreamCreateWithFlags(&c->s, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->join, cudaEventDisableTiming);
+  }
+  return c;
+}
+
 struct CtcWs {
   float* lse; float* alpha; float* beta; float* logp; int* skip; int S_pad;
 };
@@ -710,6 +829,10 @@ extern "C" int b2_ctc_loss_grad(const float* logits, const int32_t* labels_flat,
 
   if (warp_path) {
     const int spl = w.S_pad / kTeam;       // 2 or 4
+    const int nv = cdiv(C, 32);
+    const bool rows_regs = nv <= 96;
+    CtcSide* side = rows_regs ? ctc_side() : nullptr;
+    if (side) B2_CUDA(cudaEventRecord(side->fork, stream));
     dim3 grid(B, 2);
     if (spl == 2)
       ctc_ab_team_kernel<2><<<grid, kTeam, 0, stream>>>(logits, labels_flat, label_offsets, seq_len, T, B, C, blank,
@@ -718,11 +841,30 @@ extern "C" int b2_ctc_loss_grad(const float* logits, const int32_t* labels_flat,
       ctc_ab_team_kernel<4><<<grid, kTeam, 0, stream>>>(logits, labels_flat, label_offsets, seq_len, T, B, C, blank,
                                                         ignore_longer, w.alpha, w.beta, w.logp, w.skip, loss);
     B2_LAUNCH_CHECK();
-    // row pass: logsumexp of every row (+ gradient when asked for)
-    ctc_grad_kernel<<<cdiv(rows, wpb), wpb * 32, gsmem, stream>>>(
-        logits, w.lse, labels_flat, label_offsets, seq_len, w.alpha, w.beta, w.skip, T, B, C, blank, w.S_pad, spl,
-        kTeam, grad_scale, wpb, grad);
-    B2_LAUNCH_CHECK();
+    if (rows_regs) {
+      // softmax half of the row pass (logsumexp + grad_scale * softmax): no lattice needed -> beside the sweep
+      B2_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0));
+#define LAUNCH_ROWS(NV)                                                                                     \
+      ctc_softmax_rows_kernel<NV><<<cdiv(rows, 4), 128, 0, side->s>>>(logits, w.lse, seq_len, T, B, C, grad_scale, grad)
+      if (nv <= 1) LAUNCH_ROWS(1); else if (nv <= 2) LAUNCH_ROWS(2); else if (nv <= 4) LAUNCH_ROWS(4);
+      else if (nv <= 8) LAUNCH_ROWS(8); else if (nv <= 16) LAUNCH_ROWS(16); else if (nv <= 32) LAUNCH_ROWS(32);
+      else if (nv <= 64) LAUNCH_ROWS(64); else LAUNCH_ROWS(96);
+#undef LAUNCH_ROWS
+      B2_LAUNCH_CHECK();
+      B2_CUDA(cudaEventRecord(side->join, side->s));
+      B2_CUDA(cudaStreamWaitEvent(stream, side->join, 0));
+      if (grad) {
+        ctc_occ_rows_kernel<<<cdiv(rows, 4), 128, 0, stream>>>(logits, labels_flat, label_offsets, seq_len, w.alpha,
+                                                               w.beta, w.skip, T, B, C, blank, w.S_pad, spl, grad_scale,
+                                                               grad);
+        B2_LAUNCH_CHECK();
+      }
+    } else {
+      ctc_grad_kernel<<<cdiv(rows, wpb), wpb * 32, gsmem, stream>>>(
+          logits, w.lse, labels_flat, label_offsets, seq_len, w.alpha, w.beta, w.skip, T, B, C, blank, w.S_pad, spl,
+          kTeam, grad_scale, wpb, grad);
+      B2_LAUNCH_CHECK();
+    }
     ctc_finalize_kernel<<<B, 128, 0, stream>>>(w.lse, seq_len, w.skip, T, B, w.logp, loss);
     B2_LAUNCH_CHECK();
     return B2_OK;
