@@ -1,0 +1,16 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+N=${1:-4}
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+timeout 600 $TR --master-port 29521 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r2_bench25_n$N.log 2>&1; echo "rc=$?"; grep "^{" gpurun_out/r2_bench25_n$N.log | python -c "
+import json,sys
+for l in sys.stdin:
+    j=json.loads(l); print(j['n_gpus'], round(j['value']), j['ms_per_step'], j['e2e']['ms_per_step'], j['config']['gradient_exchange'], j['scaling'])
+"
+B2_BENCH_SCALING=strong timeout 600 $TR --master-port 29522 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r2_bench25_n${N}s.log 2>&1; echo "rc=$?"; grep "^{" gpurun_out/r2_bench25_n${N}s.log | python -c "
+import json,sys
+for l in sys.stdin:
+    j=json.loads(l); print(j['n_gpus'], round(j['value']), j['ms_per_step'], j['e2e']['ms_per_step'], j['config']['gradient_exchange'], j['scaling'])
+"
+timeout 600 $TR --master-port 29523 tools/dp_check.py > gpurun_out/r2_dp25_n$N.log 2>&1; echo "rc=$?"; grep -v "^\*\*\*\|^$\|OMP_NUM" gpurun_out/r2_dp25_n$N.log | tail -8
