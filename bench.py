@@ -352,7 +352,7 @@ def main():
         # algorithmic bytes = 8*T*B*C (read logits, write grad) + 8*T*B*S alpha spill, S = 2*mean(L)+1
         s_mean = 2.0 * float(np.mean([len(l) for l in labels])) + 1.0
         by = 8.0 * T * B * Cc + 8.0 * T * B * s_mean
-        roof["ctc_alpha_beta"] = {"kernel": "ctc_lse + ctc_alpha_beta + ctc_grad", "bound": "hbm",
+        roof["ctc_alpha_beta"] = {"kernel": "ctc_ab_team + ctc_softmax_rows + ctc_occ_rows + ctc_finalize", "bound": "hbm",
                                   "achieved": by / t_ctc / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                   "frac": by / t_ctc / 1e6 / peaks["hbm_gbs"], "traffic": None, "ms": t_ctc,
                                   "achieved_logits_only": 8.0 * T * B * Cc / t_ctc / 1e6,
@@ -391,15 +391,15 @@ def main():
             roof["blstm_recurrence_fwd"] = {
                 "kernel": "lstm_rec_fwd_kernel<2,32> (persistent cluster/TMEM recurrence, one layer, T=1000)",
                 "bound": "tensor", "achieved": rec_fl / tf_ / 1e9, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": rec_fl / tf_ / 1e9 / peaks["bf16_tflops"], "traffic": 2.71e9, "traffic_src": "static: ncu dram bytes "
-                "read+write of one launch, profiles/prof_rec_fwd_r01_metrics.csv (not re-measured in this run)", "ms": tf_,
+                "frac": rec_fl / tf_ / 1e9 / peaks["bf16_tflops"], "traffic": 2.84e9, "traffic_src": "static: ncu dram bytes "
+                "read+write of one launch, profiles/prof_rec_fwd_r02_final_metrics.csv (not re-measured in this run)", "ms": tf_,
                 "note": "latency-bound: 1000 dependent steps (tensor-pipe issue + DSMEM all-gather + gate math)",
                 "peak_src": peaks["src"] + " burst"}
             roof["blstm_recurrence_bwd"] = {
                 "kernel": "lstm_rec_bwd_kernel<2> (BPTT, one layer)", "bound": "tensor",
                 "achieved": rec_fl / tb_ / 1e9, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": rec_fl / tb_ / 1e9 / peaks["bf16_tflops"], "traffic": 2.08e9, "traffic_src": "static: ncu dram bytes "
-                "read+write of one launch, profiles/prof_rec_bwd_r01_metrics.csv (not re-measured in this run)", "ms": tb_,
+                "read+write of one launch, profiles/prof_rec_bwd_r02_final_metrics.csv (not re-measured in this run)", "ms": tb_,
                 "note": "latency-bound (DSMEM reduce-scatter + gate math + tensor-pipe issue per step)",
                 "peak_src": peaks["src"] + " burst"}
         # whole step against the tensor roofline (algorithmic gate-GEMM FLOPs / step time)
