@@ -348,6 +348,8 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
       int stage = 0; uint32_t gph = 0;
 #if B2_REC_TIMING
       const long long loop_t0 = clock64();
+      unsigned long long loop_g0;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(loop_g0));
 #endif
       for (int t = 0; t < T; ++t) {
         const int td = dir ? T - 1 - t : t;
@@ -478,7 +480,12 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmG, const RecFwdArgs a)
         if (++stage == RGS) { stage = 0; gph ^= 1; }
       }
 #if B2_REC_TIMING
-      if (a.dbg && ctid == 0 && cta == 0) a.dbg[16 + cluster_id * 2 + c] = clock64() - loop_t0;
+      if (a.dbg && ctid == 0 && cta == 0) {
+        a.dbg[16 + cluster_id * 2 + c] = clock64() - loop_t0;
+        unsigned long long loop_g1;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(loop_g1));
+        a.dbg[32 + cluster_id * 2 + c] = (long long)(loop_g1 - loop_g0);      // nanoseconds of the same loop
+      }
 #endif
       if (a.final_state) {
 #pragma unroll
@@ -683,14 +690,27 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
     reg_dealloc<24>();
     if (warp == W_PROD && lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int s = 0; s < T; ++s) {
+      // Progress counters (chunked dX GEMM beside this kernel) are published from HERE, not from the gate-math
+      // warps (one more compare + two live registers in their step loop measured +0.12 ms per layer): a gate team's
+      // arrival on gempty for step s' follows its barrier of step s', which every thread passes after issuing its
+      // dG stores of step s'-1.  bw (frames ascend): frame k*chunk_T - 1 is stored at s' = k*chunk_T; fw (frames
+      // descend): frame k*chunk_T at s' = T - k*chunk_T.  The outermost chunk is flagged by the team after its loop.
+      int flag_s = T + BGS + 1, flag_chunk = 0;
+      if (a.progress) {
+        if (dir) { flag_s = a.chunk_T; flag_chunk = 0; }
+        else { const int k0 = (T - 1) / a.chunk_T; flag_s = T - k0 * a.chunk_T; flag_chunk = k0; }
+      }
+      for (int s = 0; s < T + BGS; ++s) {
         const int td = dir ? s : T - 1 - s;
         const int tp = dir ? td + 1 : td - 1;          // previous step in forward order
+        const bool flag_now = (s - BGS == flag_s) && (s - BGS < T);
 #pragma unroll
         for (int c = 0; c < NCHAIN; ++c) {
           if (gbase + c >= a.NG) continue;
           const int idx = c * BGS + stage;
-          mbar_wait(&gempty[idx], phase ^ 1);
+          mbar_wait(&gempty[idx], phase ^ 1);          // s >= BGS: the team has passed its barrier of step s - BGS
+          if (flag_now) { __threadfence(); atomicAdd(a.progress + flag_chunk, 1u); }
+          if (s >= T) continue;
           mbar_expect_tx(&gfull[idx], BSTAGE);
           uint8_t* st = smem + L::kRingOff + idx * BSTAGE;
           const int row0 = td * B + (gbase + c) * RN;
@@ -700,6 +720,7 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
           tma_load_3d(st + 8192 + 2048, &tmCs, &gfull[idx], cta * RU, dir, rowp);
           tma_load_3d(st + 8192 + 4096, &tmDy, &gfull[idx], cta * RU, dir, row0);
         }
+        if (flag_now) { flag_s += a.chunk_T; flag_chunk += dir ? 1 : -1; }
         if (++stage == BGS) { stage = 0; phase ^= 1; }
       }
     }
@@ -785,11 +806,13 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
           clipz[j] = a.cell_clip > 0.f && fabsf(cc) >= a.cell_clip;
           ccv[j] = cc; cpv[j] = c_prev;
         }
-        if (a.keep_prob < 1.f) {       // DropoutWrapper mask (only when the caller did not pre-mask dy)
+        if (a.keep_prob < 1.f) {       // DropoutWrapper mask (only when the caller did not pre-mask dy); off the
+          const float inv_keep = 1.f / a.keep_prob;    // dependent chain: the partial sums are still in flight
+          const size_t row_base = (size_t)td * B * 2 * H + (size_t)dir * H + u;
 #pragma unroll
           for (int j = 0; j < CPT; ++j) {
-            const size_t oidx = ((size_t)td * B + bidx[j]) * 2 * H + (size_t)dir * H + u;
-            dyq[j] = dropout_keep(a.seed, oidx, a.keep_prob) ? dyq[j] / a.keep_prob : 0.f;
+            const size_t oidx = row_base + (size_t)bidx[j] * 2 * H;
+            dyq[j] = dropout_keep(a.seed, oidx, a.keep_prob) ? dyq[j] * inv_keep : 0.f;
           }
         }
         REC_CLK(b2);
@@ -857,12 +880,6 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmGates, const __grid_co
         if (ctid == 0) {
           mbar_arrive(&gempty[c * BGS + stage]);
           if (s + 1 < T) mbar_arrive(&bready[c]);
-          if (a.progress && s > 0) {
-            // every thread of the team passed the barrier above after issuing its dG stores of step s-1
-            const int tdp = dir ? s - 1 : T - s;
-            const bool done = dir ? ((tdp + 1) % a.chunk_T == 0) : (tdp % a.chunk_T == 0);
-            if (done) { __threadfence(); atomicAdd(a.progress + tdp / a.chunk_T, 1u); }
-          }
         }
         // dG (operand of the time-batched weight/input-gradient GEMMs) goes out after the hand-off to the
         // issuers: the stores overlap the step's MMAs instead of delaying them

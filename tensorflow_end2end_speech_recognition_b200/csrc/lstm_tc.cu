@@ -452,11 +452,13 @@ int tc_layer_forward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16*
     cudaMemsetAsync(dbg_buf, 0, 64 * sizeof(long long), stream);
     ra.dbg = dbg_buf;
     rc = rec_tc_forward(ra, Gbuf, env_int("B2_REC_NCHAIN", 0), env_int("B2_REC_GW", 0), stream);
-    long long hb[32];
+    long long hb[48];
     cudaMemcpyAsync(hb, dbg_buf, sizeof(hb), cudaMemcpyDeviceToHost, stream);
     cudaStreamSynchronize(stream);
     fprintf(stderr, "[rec fwd dbg3] loop cycles per (cluster,chain): %lld %lld | %lld %lld | %lld %lld | %lld %lld\n",
             hb[16], hb[17], hb[18], hb[19], hb[20], hb[21], hb[22], hb[23]);
+    fprintf(stderr, "[rec fwd dbg4] the same loops in ns (globaltimer): %lld %lld | %lld %lld -> clock64 rate %.3f GHz\n",
+            hb[32], hb[33], hb[34], hb[35], hb[32] > 0 ? (double)hb[16] / (double)hb[32] : 0.0);
     fprintf(stderr, "[rec fwd dbg] cycles/step (needs a -DB2_REC_TIMING=1 build): reserve_stores=%lld | wait_acc=%lld "
             "ld+transpose=%lld wait_G=%lld math+stage=%lld fence+bar=%lld arrive+send=%lld\n",
             hb[1] / T, hb[2] / T, hb[3] / T, hb[4] / T, hb[5] / T, hb[6] / T, hb[7] / T);
@@ -502,7 +504,7 @@ int tc_layer_backward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16
   }
   ba.use_peephole = d->use_peephole; ba.cell_clip = d->cell_clip; ba.keep_prob = d->keep_prob;
   ba.seed = d->dropout_seed; ba.gates = r.gates; ba.cs = r.cs; ba.dG = dG; ba.dfinal = d_final_state;
-  if (d->keep_prob < 1.f && (((size_t)TB * 2 * H) % 4 == 0)) {     // mask dy once, outside the recurrence
+  if (d->keep_prob < 1.f && (((size_t)TB * 2 * H) % 4 == 0) && env_int("B2_DY_MASK_PASS", 1)) {     // mask dy once, outside the recurrence
     const int64_t n4 = (int64_t)TB * 2 * H / 4;
     int64_t blocks = (n4 + 255) / 256;
     if (blocks > num_sms() * 16) blocks = num_sms() * 16;
