@@ -70,6 +70,9 @@ lstm_wide_fwd_kernel(const WideFwdArgs a) {
   const int HP = H + 8;                                   // bf16 row pitch of the h tile: conflict-free fragment loads
   __nv_bfloat16* hbuf = (__nv_bfloat16*)smem_raw;          // [WB][HP]
   float* part = (float*)(smem_raw + (size_t)WB * HP * 2);  // [2 K halves][64 rows][WPP]
+  uint64_t* hfull = (uint64_t*)(smem_raw + (size_t)WB * HP * 2 + (size_t)2 * 64 * WPP * 4);   // [2]: one per K half
+  if (threadIdx.x == 0) { mbar_init(hfull, 1); mbar_init(hfull + 1, 1); fence_mbar_init(); }
+  __syncthreads();
   const int NS = H / WU;
   const int dir = blockIdx.x / NS, slice = blockIdx.x % NS;
   const int u0 = slice * WU;
@@ -119,22 +122,23 @@ lstm_wide_fwd_kernel(const WideFwdArgs a) {
 
     if (s > 0) {
       // ---- every CTA of this direction has published h_{s-1}
-      if (tid == 0) {
-        const unsigned want = (unsigned)NS * (unsigned)s;
-        while (ld_acquire_u32(bar) < want) {}
-      }
-      __syncthreads();
-      // h_{s-1} [B, H] bf16 from L2 (cache-global loads: the lines were written by other SMs) into the padded tile
-      {
-        const uint4* src = (const uint4*)(hx_dir + (size_t)((s - 1) & 1) * WB * H);
-        const int vec_per_row = H / 8;
-        for (int i = tid; i < WB * vec_per_row; i += WTHREADS) {
-          const int r = i / vec_per_row, cvec = i - r * vec_per_row;
-          const uint4 v = __ldcg(src + (size_t)r * vec_per_row + cvec);
-          *(uint4*)(hbuf + (size_t)r * HP + cvec * 8) = v;
+      // h_{s-1} [B, H] bf16 from L2 into the padded tile: 2 x 32 TMA bulk row copies (one mbarrier per K half, so the
+      // warps of the first half start while the second is still landing); the tile was last read before the block
+      // barrier that closed the previous step
+      if (warp == 0) {
+        if (lane == 0) {
+          const unsigned want = (unsigned)NS * (unsigned)s;
+          while (ld_acquire_u32(bar) < want) {}
         }
+        __syncwarp();
+        asm volatile("fence.proxy.async;" ::: "memory");      // the peers' generic-proxy stores, now acquired
+        const __nv_bfloat16* src = hx_dir + (size_t)((s - 1) & 1) * WB * H + (size_t)lane * H;
+        if (lane == 0) { mbar_expect_tx(hfull, (uint32_t)WB * H); mbar_expect_tx(hfull + 1, (uint32_t)WB * H); }
+        __syncwarp();
+        bulk_g2s(hbuf + (size_t)lane * HP, src, (uint32_t)H, hfull);
+        bulk_g2s(hbuf + (size_t)lane * HP + H / 2, src + H / 2, (uint32_t)H, hfull + 1);
       }
-      __syncthreads();
+      mbar_wait(hfull + kh, (uint32_t)(s - 1) & 1u);
       // ---- z_rec[64 x 32] = Wslice . h^T : this warp = the 16 rows of gate mt x K half kh x all 32 batch columns
       float acc[4][4];
 #pragma unroll
@@ -202,10 +206,9 @@ lstm_wide_fwd_kernel(const WideFwdArgs a) {
         }
       }
     }
-    // ---- publish: every thread's stores are fenced, then one arrival per CTA
-    __threadfence();
+    // ---- publish: block barrier (every thread's stores precede it), then ONE fence + arrival per CTA
     __syncthreads();
-    if (tid == 0) atomicAdd(bar, 1u);
+    if (tid == 0) { __threadfence(); atomicAdd(bar, 1u); }
   }
   if (a.final_state) {
 #pragma unroll
@@ -418,9 +421,8 @@ lstm_wide_bwd_kernel(const WideBwdArgs a) {
         dz[0] = dzi; dz[H] = dzg; dz[2 * H] = dzf; dz[3 * H] = dzo;
       }
     }
-    __threadfence();
     __syncthreads();
-    if (tid == 0) atomicAdd(bar, 1u);
+    if (tid == 0) { __threadfence(); atomicAdd(bar, 1u); }
   }
 }
 
@@ -441,7 +443,7 @@ size_t wide_rec_workspace_bytes(const b2_lstm_desc* d) {
 
 template <int KSH>
 static int launch_wide_fwd(WideFwdArgs& a, cudaStream_t stream) {
-  const size_t smem = (size_t)WB * (a.H + 8) * 2 + (size_t)2 * 64 * WPP * 4;
+  const size_t smem = (size_t)WB * (a.H + 8) * 2 + (size_t)2 * 64 * WPP * 4 + 64;
   auto kern = lstm_wide_fwd_kernel<KSH>;
   B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* params[] = {(void*)&a};

@@ -46,7 +46,7 @@ def bench(T, B, D, H, backward, label, iters=3):
 
 if __name__ == "__main__":
     T, B = int(os.environ.get("WIDE_T", "1500")), int(os.environ.get("WIDE_B", "32"))
-    for wide in ("1", "0"):
+    for wide in (("1",) if os.environ.get("B2_WIDE_ONLY") else ("1", "0")):
         os.environ["B2_WIDE_REC"] = wide
         tag = "grid-resident" if wide == "1" else "per-frame fallback"
         bench(T, B, 2048, 1024, False, "fwd only, " + tag)
