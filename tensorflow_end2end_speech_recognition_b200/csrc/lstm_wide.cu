@@ -55,6 +55,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *(uint32_t*)&v;
 }
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_u32(unsigned* p, unsigned v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -106,10 +117,17 @@ lstm_wide_fwd_kernel(const WideFwdArgs a) {
   float pwi = 0.f, pwf = 0.f, pwo = 0.f;
   if (a.use_peephole) { pwi = a.wi[dir][u]; pwf = a.wf[dir][u]; pwo = a.wo[dir][u]; }
   __nv_bfloat16* hx_dir = a.hx + (size_t)dir * 2 * WB * H;
-  unsigned* bar = a.bar + dir;
+  unsigned* bar = a.bar + dir * 64;           // one flag per CTA of this direction: steps it has published
+#if B2_REC_TIMING
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define WCLK(x) const long long x = clock64()
+#else
+#define WCLK(x)
+#endif
 
   for (int s = 0; s < T; ++s) {
     const int td = dir ? T - 1 - s : s;
+    WCLK(w0);
     // G_t for this thread's two cells (independent of h: in flight while the barrier is awaited)
     float z[2][4];
 #pragma unroll
@@ -123,22 +141,29 @@ lstm_wide_fwd_kernel(const WideFwdArgs a) {
     if (s > 0) {
       // ---- every CTA of this direction has published h_{s-1}
       // h_{s-1} [B, H] bf16 from L2 into the padded tile: 2 x 32 TMA bulk row copies (one mbarrier per K half, so the
-      // warps of the first half start while the second is still landing); the tile was last read before the block
-      // barrier that closed the previous step
+      // warps of the first half start while the second is still landing).  A warp issues one bulk operation per ~53
+      // cycles whatever the lane (64 copies from one warp measured 4 300 cycles until the tile had landed): every
+      // warp issues 8 of them.  The tile was last read before the block barrier that closed the previous step.
       if (warp == 0) {
-        if (lane == 0) {
-          const unsigned want = (unsigned)NS * (unsigned)s;
-          while (ld_acquire_u32(bar) < want) {}
-        }
+        // every CTA of this direction has published step s-1: lane i polls the flags of CTAs i and i + 32 (own words
+        // of one 256-byte block; no serialised atomics on a shared counter)
+        for (int j = lane; j < NS; j += 32)
+          while (ld_acquire_u32(bar + j) < (unsigned)s) {}
         __syncwarp();
-        asm volatile("fence.proxy.async;" ::: "memory");      // the peers' generic-proxy stores, now acquired
-        const __nv_bfloat16* src = hx_dir + (size_t)((s - 1) & 1) * WB * H + (size_t)lane * H;
         if (lane == 0) { mbar_expect_tx(hfull, (uint32_t)WB * H); mbar_expect_tx(hfull + 1, (uint32_t)WB * H); }
-        __syncwarp();
-        bulk_g2s(hbuf + (size_t)lane * HP, src, (uint32_t)H, hfull);
-        bulk_g2s(hbuf + (size_t)lane * HP + H / 2, src + H / 2, (uint32_t)H, hfull + 1);
+#if B2_REC_TIMING
+        tacc[0] += clock64() - w0;                              // flags acquired
+#endif
+      }
+      __syncthreads();
+      if (lane < 8) {
+        asm volatile("fence.proxy.async;" ::: "memory");      // the peers' generic-proxy stores, acquired by warp 0
+        const int r = warp * 4 + (lane >> 1), half = lane & 1;
+        bulk_g2s(hbuf + (size_t)r * HP + half * (H / 2),
+                 hx_dir + (size_t)((s - 1) & 1) * WB * H + (size_t)r * H + half * (H / 2), (uint32_t)H, hfull + half);
       }
       mbar_wait(hfull + kh, (uint32_t)(s - 1) & 1u);
+      WCLK(w1);
       // ---- z_rec[64 x 32] = Wslice . h^T : this warp = the 16 rows of gate mt x K half kh x all 32 batch columns
       float acc[4][4];
 #pragma unroll
@@ -154,6 +179,7 @@ lstm_wide_fwd_kernel(const WideFwdArgs a) {
           mma_bf16_16816(acc[nt], afrag[ks], *(const uint32_t*)hp, *(const uint32_t*)(hp + 8));
         }
       }
+      WCLK(w2);
       // partial sums of this K half: part[kh][gate*16 + unit][batch]
       {
         float* pr = part + ((size_t)kh * 64 + mt * 16) * WPP;
@@ -170,46 +196,74 @@ lstm_wide_fwd_kernel(const WideFwdArgs a) {
         for (int g = 0; g < 4; ++g)
           z[j][g] += part[((size_t)g * 16 + ul) * WPP + bq + 16 * j] +
                      part[((size_t)64 + g * 16 + ul) * WPP + bq + 16 * j];
+#if B2_REC_TIMING
+      const long long w3 = clock64();
+      tacc[1] += w1 - w0; tacc[2] += w2 - w1; tacc[3] += w3 - w2;
+#endif
     }
-    // ---- gate math (models/recurrent/layers/lstm.py:142-183: i, g(ci), f, o; forget bias; peepholes; clip)
+    WCLK(w4);
+    // ---- gate math (models/recurrent/layers/lstm.py:142-183: i, g(ci), f, o; forget bias; peepholes; clip); the three
+    //      input-side activations share one reciprocal, as in lstm_rec_tc.cu
     __nv_bfloat16* hx_out = hx_dir + (size_t)(s & 1) * WB * H;
+    float4 gsv[2]; float hov[2]; bool act[2];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int b = bq + 16 * j;
       const bool active = td < len[j];
       const float c_prev = cst[j];
-      float gi = 0.f, gg = 0.f, gf = 0.f, go = 0.f, h_out = 0.f, c_new = c_prev;
-      if (active) {
-        float zi = z[j][0], zg = z[j][1], zf = z[j][2] + a.forget_bias, zo = z[j][3];
-        zi = fmaf(pwi, c_prev, zi); zf = fmaf(pwf, c_prev, zf);
-        gi = sigmoidf_(zi); gg = tanhf_(zg); gf = sigmoidf_(zf);
-        c_new = fmaf(gf, c_prev, gi * gg);
-        if (a.cell_clip > 0.f) c_new = fminf(fmaxf(c_new, -a.cell_clip), a.cell_clip);
-        zo = fmaf(pwo, c_new, zo);
-        go = sigmoidf_(zo);
-        h_out = go * tanhf_(c_new);
-        cst[j] = c_new; hst[j] = h_out;
-      }
+      float zi = z[j][0], zg = z[j][1], zf = z[j][2] + a.forget_bias, zo = z[j][3];
+      zi = fmaf(pwi, c_prev, zi); zf = fmaf(pwf, c_prev, zf);
+      const float Ei = __expf(fminf(-zi, 25.f)), Ef = __expf(fminf(-zf, 25.f)), Eg = __expf(fminf(-2.f * zg, 25.f));
+      const float ai = 1.f + Ei, af = 1.f + Ef, ag = 1.f + Eg;
+      const float r = rcp_approx(ai * af * ag);
+      float gi = r * af * ag, gf = r * ai * ag, gg = (1.f - Eg) * r * ai * af;
+      float c_new = fmaf(gf, c_prev, gi * gg);
+      if (a.cell_clip > 0.f) c_new = fminf(fmaxf(c_new, -a.cell_clip), a.cell_clip);
+      zo = fmaf(pwo, c_new, zo);
+      const float Eo = __expf(fminf(-zo, 25.f)), Ec = __expf(fminf(-2.f * c_new, 25.f));
+      const float ao = 1.f + Eo, ac = 1.f + Ec;
+      const float r2 = rcp_approx(ao * ac);
+      float go = r2 * ac;
+      float h_out = go * (1.f - Ec) * r2 * ao;
+      if (active) { cst[j] = c_new; hst[j] = h_out; }
+      else { gi = 0.f; gg = 0.f; gf = 0.f; go = 0.f; h_out = 0.f; }
+      gsv[j] = make_float4(gi, gg, gf, go); hov[j] = h_out; act[j] = active;
       // the carried state h feeds the next step's product (inactive rows keep their last state)
       hx_out[(size_t)b * H + u] = __float2bfloat16(hst[j]);
+    }
+    // ---- publish: block barrier (every thread's h stores precede it), then ONE release store per CTA.  The reserve
+    //      stores come AFTER it: the release has to wait only for the 1 KB of h, not for the 40 KB of gates / y
+    WCLK(w5);
+    __syncthreads();
+    WCLK(w6);
+    if (tid == 0) st_release_u32(bar + slice, (unsigned)(s + 1));
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int b = bq + 16 * j;
       if (b < B) {
         const size_t row = (size_t)td * B + b;
         const size_t oidx = row * 2 * H + (size_t)dir * H + u;
-        float yv = h_out;
-        if (a.keep_prob < 1.f && active) yv = dropout_keep(a.seed, oidx, a.keep_prob) ? h_out / a.keep_prob : 0.f;
+        float yv = hov[j];
+        if (a.keep_prob < 1.f && act[j]) yv = dropout_keep(a.seed, oidx, a.keep_prob) ? hov[j] / a.keep_prob : 0.f;
         a.y[oidx] = yv;
         if (a.gates) {
           const size_t cell = (row * 2 + dir) * H + u;
-          *(float4*)(a.gates + cell * 4) = make_float4(gi, gg, gf, go);
+          *(float4*)(a.gates + cell * 4) = gsv[j];
           a.cs[cell] = cst[j];
-          a.hs[cell] = h_out;
+          a.hs[cell] = hov[j];
         }
       }
     }
-    // ---- publish: block barrier (every thread's stores precede it), then ONE fence + arrival per CTA
-    __syncthreads();
-    if (tid == 0) { __threadfence(); atomicAdd(bar, 1u); }
+#if B2_REC_TIMING
+    tacc[4] += w5 - w4; tacc[5] += w6 - w5; tacc[6] += clock64() - w6; tacc[7] += clock64() - w0;
+#endif
   }
+#if B2_REC_TIMING
+  if (blockIdx.x == 0 && (tid == 0 || tid == 128)) {
+    long long* dbg = (long long*)(a.bar + 128) + (tid ? 8 : 0);
+    for (int i = 0; i < 8; ++i) dbg[i] = tacc[i];
+  }
+#endif
   if (a.final_state) {
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
@@ -299,7 +353,7 @@ lstm_wide_bwd_kernel(const WideBwdArgs a) {
   float pwi = 0.f, pwf = 0.f, pwo = 0.f;
   if (a.use_peephole) { pwi = a.wi[dir][u]; pwf = a.wf[dir][u]; pwo = a.wo[dir][u]; }
   __nv_bfloat16* zx_dir = a.dzx + (size_t)dir * 2 * WB * 4 * H;
-  unsigned* bar = a.bar + dir;
+  unsigned* bar = a.bar + dir * 64;           // one flag per CTA of this direction: steps it has published
 
   for (int s = 0; s < T; ++s) {
     const int td = dir ? s : T - 1 - s;
@@ -327,20 +381,22 @@ lstm_wide_bwd_kernel(const WideBwdArgs a) {
       const __nv_bfloat16* zsrc = zx_dir + (size_t)((s - 1) & 1) * WB * 4 * H;
       const unsigned n0 = (unsigned)(s - 1) * 4u;            // running gate-tile count at this step's first tile
       if (warp == 0) {
-        // every CTA of this direction has published dz_{t'}; make the async proxy see those generic-proxy writes
-        if (lane == 0) {
-          const unsigned want = (unsigned)NS * (unsigned)s;
-          while (ld_acquire_u32(bar) < want) {}
-        }
-        __syncwarp();
-        asm volatile("fence.proxy.async;" ::: "memory");
+        // every CTA of this direction has published step s-1: lane i polls the flags of CTAs i and i + 32
+        for (int j = lane; j < NS; j += 32)
+          while (ld_acquire_u32(bar + j) < (unsigned)s) {}
+      }
+      __syncthreads();
+      // every warp issues 4 of a tile's 32 row copies (a warp issues one bulk operation per ~53 cycles whatever the
+      // lane: 32 from one warp take 1 700 cycles per tile)
+      if (lane < 4) asm volatile("fence.proxy.async;" ::: "memory");   // the peers' generic-proxy stores, acquired above
 #pragma unroll
-        for (int g = 0; g < 3; ++g) {
-          const unsigned n = n0 + g, tl = n % 3u;
-          if (n >= 3u) mbar_wait(empty + tl, ((n / 3u) - 1u) & 1u);      // all 8 warps are done with tile use n-3
-          if (lane == 0) mbar_expect_tx(full + tl, (uint32_t)WB * H * 2);
-          __syncwarp();
-          bulk_g2s(smem_raw + tl * tile_bytes + (size_t)lane * HP * 2, zsrc + (size_t)lane * 4 * H + (size_t)g * H,
+      for (int g = 0; g < 3; ++g) {
+        const unsigned n = n0 + g, tl = n % 3u;
+        if (n >= 3u) mbar_wait(empty + tl, ((n / 3u) - 1u) & 1u);      // all 8 warps are done with tile use n-3
+        if (tid == 0) mbar_expect_tx(full + tl, (uint32_t)WB * H * 2);
+        if (lane < 4) {
+          const int r = warp * 4 + lane;
+          bulk_g2s(smem_raw + tl * tile_bytes + (size_t)r * HP * 2, zsrc + (size_t)r * 4 * H + (size_t)g * H,
                    (uint32_t)H * 2, full + tl);
         }
       }
@@ -352,14 +408,16 @@ lstm_wide_bwd_kernel(const WideBwdArgs a) {
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const unsigned n = n0 + g, tl = n % 3u;
-        if (g == 1 && warp == 0) {
+        if (g == 1) {
           // the fourth gate of this step reuses the tile of the first: wait until every warp has released it
           const unsigned n3 = n0 + 3u, t3 = n3 % 3u;
           mbar_wait(empty + t3, ((n3 / 3u) - 1u) & 1u);
-          if (lane == 0) mbar_expect_tx(full + t3, (uint32_t)WB * H * 2);
-          __syncwarp();
-          bulk_g2s(smem_raw + t3 * tile_bytes + (size_t)lane * HP * 2, zsrc + (size_t)lane * 4 * H + (size_t)3 * H,
-                   (uint32_t)H * 2, full + t3);
+          if (tid == 0) mbar_expect_tx(full + t3, (uint32_t)WB * H * 2);
+          if (lane < 4) {
+            const int r = warp * 4 + lane;
+            bulk_g2s(smem_raw + t3 * tile_bytes + (size_t)r * HP * 2, zsrc + (size_t)r * 4 * H + (size_t)3 * H,
+                     (uint32_t)H * 2, full + t3);
+          }
         }
         mbar_wait(full + tl, (n / 3u) & 1u);
         const __nv_bfloat16* zbuf = (const __nv_bfloat16*)(smem_raw + tl * tile_bytes);
@@ -394,6 +452,7 @@ lstm_wide_bwd_kernel(const WideBwdArgs a) {
     }
     // ---- gate derivatives (the fp32 step kernel's math, lstm.cu::lstm_bwd_step_kernel)
     __nv_bfloat16* zx_out = zx_dir + (size_t)(s & 1) * WB * 4 * H;
+    float4 dzv[2];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int b = bq + 16 * j;
@@ -403,7 +462,8 @@ lstm_wide_bwd_kernel(const WideBwdArgs a) {
         const bool nb_active = s > 0 && tn >= 0 && tn < T && tn < len[j];
         const float dh = dyv[j] + (nb_active ? dh_rec[j] : dfh[j]);
         const float gi = g4[j].x, gg = g4[j].y, gf = g4[j].z, go = g4[j].w;
-        const float tc = tanhf_(cc[j]);
+        const float Ec = __expf(fminf(-2.f * cc[j], 25.f));
+        const float tc = (1.f - Ec) * rcp_approx(1.f + Ec);
         dzo = dh * tc * go * (1.f - go);
         float dc = dcs[j] + dh * go * (1.f - tc * tc);
         dc = fmaf(dzo, pwo, dc);
@@ -416,13 +476,19 @@ lstm_wide_bwd_kernel(const WideBwdArgs a) {
       __nv_bfloat16* zr = zx_out + (size_t)b * 4 * H + u;
       zr[0] = __float2bfloat16(dzi); zr[H] = __float2bfloat16(dzg);
       zr[2 * H] = __float2bfloat16(dzf); zr[3 * H] = __float2bfloat16(dzo);
+      dzv[j] = make_float4(dzi, dzg, dzf, dzo);
+    }
+    // publish first (the release waits only for the exchanged bf16 values), the fp32 dG stores afterwards
+    __syncthreads();
+    if (tid == 0) st_release_u32(bar + slice, (unsigned)(s + 1));
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int b = bq + 16 * j;
       if (b < B) {
         float* dz = a.dG + ((size_t)td * B + b) * 8 * H + (size_t)dir * 4 * H + u;
-        dz[0] = dzi; dz[H] = dzg; dz[2 * H] = dzf; dz[3 * H] = dzo;
+        dz[0] = dzv[j].x; dz[H] = dzv[j].y; dz[2 * H] = dzv[j].z; dz[3 * H] = dzv[j].w;
       }
     }
-    __syncthreads();
-    if (tid == 0) { __threadfence(); atomicAdd(bar, 1u); }
   }
 }
 
@@ -438,7 +504,7 @@ bool wide_rec_supported(const b2_lstm_desc* d) {
 
 size_t wide_rec_workspace_bytes(const b2_lstm_desc* d) {
   // exchange buffer (forward: h [2][2][WB][H]; BPTT: dz [2][2][WB][4H]) + barrier counters
-  return align_up((size_t)2 * 2 * WB * 4 * d->H * 2, 256) + 256;
+  return align_up((size_t)2 * 2 * WB * 4 * d->H * 2, 256) + 1024;
 }
 
 template <int KSH>
@@ -468,7 +534,21 @@ int wide_rec_forward(const b2_lstm_desc* d, const b2_lstm_params* fw, const b2_l
   a.hx = (__nv_bfloat16*)workspace;
   const size_t hx_bytes = align_up((size_t)2 * 2 * WB * 4 * d->H * 2, 256);
   a.bar = (unsigned*)((char*)workspace + hx_bytes);
-  B2_CUDA(cudaMemsetAsync(a.bar, 0, 2 * sizeof(unsigned), stream));
+  B2_CUDA(cudaMemsetAsync(a.bar, 0, 2 * 64 * sizeof(unsigned), stream));
+#if B2_REC_TIMING
+  if (env_int("B2_REC_DBG", 0)) {
+    int rcl = B2_ERR_UNSUPPORTED;
+    if (d->H / 32 == 32) rcl = launch_wide_fwd<32>(a, stream);
+    long long hb[16];
+    cudaMemcpyAsync(hb, (char*)a.bar + 512, sizeof(hb), cudaMemcpyDeviceToHost, stream);
+    cudaStreamSynchronize(stream);
+    for (int w = 0; w < 2; ++w)
+      fprintf(stderr, "[wide fwd dbg warp %d] cycles/step: flags=%lld until_h=%lld mma=%lld part+sync+reduce=%lld gate+stores=%lld "
+              "publish_sync=%lld fence+flag=%lld | step=%lld\n", w * 4, hb[w * 8 + 0] / a.T, hb[w * 8 + 1] / a.T, hb[w * 8 + 2] / a.T,
+              hb[w * 8 + 3] / a.T, hb[w * 8 + 4] / a.T, hb[w * 8 + 5] / a.T, hb[w * 8 + 6] / a.T, hb[w * 8 + 7] / a.T);
+    return rcl;
+  }
+#endif
   switch (d->H / 32) {
     case 20: return launch_wide_fwd<20>(a, stream);
     case 24: return launch_wide_fwd<24>(a, stream);
@@ -505,7 +585,7 @@ int wide_rec_backward(const b2_lstm_desc* d, const b2_lstm_params* fw, const b2_
   a.dzx = (__nv_bfloat16*)workspace;
   const size_t zx_bytes = align_up((size_t)2 * 2 * WB * 4 * d->H * 2, 256);
   a.bar = (unsigned*)((char*)workspace + zx_bytes);
-  B2_CUDA(cudaMemsetAsync(a.bar, 0, 2 * sizeof(unsigned), stream));
+  B2_CUDA(cudaMemsetAsync(a.bar, 0, 2 * 64 * sizeof(unsigned), stream));
   switch (d->H / 128) {
     case 5: return launch_wide_bwd<5>(a, stream);
     case 6: return launch_wide_bwd<6>(a, stream);

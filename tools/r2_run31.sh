@@ -1,7 +1,7 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_lstm_rec_tc_gpu.py -q -k "wide or grid" > gpurun_out/r2_test31.log 2>&1
-echo "rc=$?" >> gpurun_out/r2_test31.log; tail -4 gpurun_out/r2_test31.log
-B2_WIDE_ONLY=1 timeout 600 python tools/bench_wide.py > gpurun_out/r2_wide31.log 2>&1; cat gpurun_out/r2_wide31.log
-timeout 900 python tools/bench_configs.py cfg4 32 1500 > gpurun_out/r2_cfg31.log 2>&1; tail -3 gpurun_out/r2_cfg31.log
+timeout 600 python -m pytest tests/test_lstm_rec_tc_gpu.py -q -k "wide or grid" > gpurun_out/r2_test34.log 2>&1
+echo "rc=$?" >> gpurun_out/r2_test34.log; tail -4 gpurun_out/r2_test31.log
+B2_WIDE_ONLY=1 timeout 600 python tools/bench_wide.py > gpurun_out/r2_wide34.log 2>&1; cat gpurun_out/r2_wide31.log
+timeout 900 python tools/bench_configs.py cfg4 32 1500 > gpurun_out/r2_cfg34.log 2>&1; tail -3 gpurun_out/r2_cfg31.log
