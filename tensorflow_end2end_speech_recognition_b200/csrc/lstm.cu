@@ -540,7 +540,7 @@ extern "C" int b2_blstm_backward_side_wait(b2_stream_t stream_) {
 }
 
 extern "C" const void* b2_blstm_reserve_y_lp(const b2_lstm_desc* d, const void* reserve) {
-  if (!d || !reserve || !tc_layer_supported(d)) return nullptr;
+  if (!d || !reserve || !(tc_layer_supported(d) || wide_rec_supported(d))) return nullptr;
   Reserve r;
   reserve_layout(d, (void*)reserve, &r);
   return r.y_lp;
@@ -579,12 +579,15 @@ extern "C" int b2_blstm_layer_forward(const b2_lstm_desc* d, const float* x, con
   for (int dir = 0; dir < 2; ++dir) {
     float* Gd = w.G + (size_t)dir * 4 * H;
     if (d->precision == B2_PREC_BF16) {
-      const int ldx = (int)pad8z(D);
-      if (dir == 0) { rc = cast_f32_bf16(x, TB, D, D, w.xb, ldx, stream); if (rc) return rc; }
+      // the caller's bf16 shadow of x (the layer below's emitted output) saves the cast pass
+      const bool have_lp = x_lp != nullptr && (D % 8) == 0;
+      const int ldx = have_lp ? D : (int)pad8z(D);
+      const __nv_bfloat16* xa = have_lp ? (const __nv_bfloat16*)x_lp : w.xb;
+      if (dir == 0 && !have_lp) { rc = cast_f32_bf16(x, TB, D, D, w.xb, ldx, stream); if (rc) return rc; }
       __nv_bfloat16* wb = w.wb + (size_t)dir * (D + 0) * 4 * H;
       rc = cast_f32_bf16(P[dir]->kernel, D, 4 * H, 4 * H, wb, 4 * H, stream);
       if (rc) return rc;
-      rc = gemm_bf16_tc(0, 1, TB, 4 * H, D, 1.f, w.xb, ldx, wb, 4 * H, Gd, 8 * H, P[dir]->bias,
+      rc = gemm_bf16_tc(0, 1, TB, 4 * H, D, 1.f, xa, ldx, wb, 4 * H, Gd, 8 * H, P[dir]->bias,
                         0 /*store f32*/, 0, stream);
     } else {
       rc = gemm_simt(0, 0, TB, 4 * H, D, 1.f, x, D, P[dir]->kernel, 4 * H, 0.f, Gd, 8 * H,
@@ -594,7 +597,7 @@ extern "C" int b2_blstm_layer_forward(const b2_lstm_desc* d, const float* x, con
   }
   // 2. recurrence
   if (wide_rec_supported(d))        // wide layer (config 4: H = 1024): ONE cooperative launch, weights register-resident
-    return wide_rec_forward(d, fw, bw, seq_len, w.G, y, r.gates, r.cs, r.hs, final_state, w.wide, stream);
+    return wide_rec_forward(d, fw, bw, seq_len, w.G, y, r.gates, r.cs, r.hs_lp, r.y_lp, final_state, w.wide, stream);
   B2_CUDA(cudaMemsetAsync(w.hstate, 0, (size_t)2 * 2 * B * H * sizeof(float), stream));
   B2_CUDA(cudaMemsetAsync(w.cstate, 0, (size_t)2 * B * H * sizeof(float), stream));
   StepArgs a;
@@ -696,7 +699,7 @@ extern "C" int b2_blstm_layer_backward_ex(const b2_lstm_desc* d, const float* x,
   dim3 grid(cdiv(H, RU), cdiv(B, RB), 2);
   const bool resident = wide_rec_supported(d);     // config 4: ONE cooperative launch for the whole BPTT recurrence
   if (resident) {
-    rc = wide_rec_backward(d, fw, bw, seq_len, dy, r.gates, r.cs, d_final_state, w.G, w.wide, stream);
+    rc = wide_rec_backward(d, fw, bw, seq_len, dy, r.gates, r.cs, d_final_state, w.G, w.gb, w.wide, stream);
     if (rc) return rc;
   }
   for (int i = 0; i < (resident ? 0 : T); ++i) {
@@ -732,10 +735,11 @@ extern "C" int b2_blstm_layer_backward_ex(const b2_lstm_desc* d, const float* x,
 
   // 3. time-batched GEMMs
   const bool tc = d->precision == B2_PREC_BF16;
-  if (tc) {
+  if (tc && !resident) {          // the grid-resident BPTT kernel has written the bf16 copy itself
     rc = cast_f32_bf16(w.G, TB, 8 * H, 8 * H, w.gb, 8 * H, stream);
     if (rc) return rc;
   }
+  const bool have_lp = tc && x_lp != nullptr && (D % 8) == 0;
   for (int dir = 0; dir < 2; ++dir) {
     const float* dGd = w.G + (size_t)dir * 4 * H;
     const __nv_bfloat16* dGb = w.gb + (size_t)dir * 4 * H;
@@ -759,20 +763,27 @@ extern "C" int b2_blstm_layer_backward_ex(const b2_lstm_desc* d, const float* x,
     const float* hs_a = r.hs + (dir == 0 ? 0 : (size_t)B * 2 * H) + (size_t)dir * H;
     const float* dG_h = dGd + (dir == 0 ? (size_t)B * 8 * H : 0);
     if (tc) {
-      const int ldx = (int)pad8z(D);
-      rc = cast_f32_bf16(x, TB, D, D, w.xb, ldx, stream);
-      if (rc) return rc;
-      rc = gemm_bf16_tc(1, 1, D, 4 * H, TB, 1.f, w.xb, ldx, dGb, 8 * H, Gr[dir]->kernel, 4 * H,
+      const int ldx = have_lp ? D : (int)pad8z(D);
+      const __nv_bfloat16* xa = have_lp ? (const __nv_bfloat16*)x_lp : w.xb;
+      if (!have_lp) { rc = cast_f32_bf16(x, TB, D, D, w.xb, ldx, stream); if (rc) return rc; }
+      rc = gemm_bf16_tc(1, 1, D, 4 * H, TB, 1.f, xa, ldx, dGb, 8 * H, Gr[dir]->kernel, 4 * H,
                         nullptr, 1, 0, stream);
       if (rc) return rc;
       if (T > 1) {
-        // bf16 copy of this direction's hs columns, compact [TB, H]
-        rc = cast_f32_bf16(r.hs + (size_t)dir * H, TB, H, 2 * H, w.xb, H, stream);
-        if (rc) return rc;
-        const __nv_bfloat16* ha = w.xb + (dir == 0 ? 0 : (size_t)B * H);
         const __nv_bfloat16* gb = dGb + (dir == 0 ? (size_t)B * 8 * H : 0);
-        rc = gemm_bf16_tc(1, 1, H, 4 * H, (T - 1) * B, 1.f, ha, H, gb, 8 * H,
-                          Gr[dir]->kernel + (size_t)D * 4 * H, 4 * H, nullptr, 1, 0, stream);
+        if (r.hs_lp) {
+          // the recurrence kernel kept h (before dropout) in bf16: [TB, 2H], this direction's columns, one step shifted
+          const __nv_bfloat16* ha = r.hs_lp + (size_t)dir * H + (dir == 0 ? 0 : (size_t)B * 2 * H);
+          rc = gemm_bf16_tc(1, 1, H, 4 * H, (T - 1) * B, 1.f, ha, 2 * H, gb, 8 * H,
+                            Gr[dir]->kernel + (size_t)D * 4 * H, 4 * H, nullptr, 1, 0, stream);
+        } else {
+          // bf16 copy of this direction's hs columns, compact [TB, H]
+          rc = cast_f32_bf16(r.hs + (size_t)dir * H, TB, H, 2 * H, w.xb, H, stream);
+          if (rc) return rc;
+          const __nv_bfloat16* ha = w.xb + (dir == 0 ? 0 : (size_t)B * H);
+          rc = gemm_bf16_tc(1, 1, H, 4 * H, (T - 1) * B, 1.f, ha, H, gb, 8 * H,
+                            Gr[dir]->kernel + (size_t)D * 4 * H, 4 * H, nullptr, 1, 0, stream);
+        }
         if (rc) return rc;
       }
     } else {

@@ -40,18 +40,23 @@ inline size_t tc_pack_bytes(int D, int H) {
   return n;
 }
 
+bool wide_rec_supported(const b2_lstm_desc* d);
+bool tc_layer_supported(const b2_lstm_desc* d);
+
 inline size_t reserve_layout(const b2_lstm_desc* d, void* base, Reserve* r) {
   const size_t n = (size_t)d->T * d->B * 2 * d->H;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
   const size_t og = take(n * 4 * sizeof(float));
   const size_t oc = take(n * sizeof(float));
-  const bool lp = tc_layer_supported(d);   // bf16 shadows only when the tcgen05 recurrence runs
+  // bf16 shadows (h before dropout for the dWh GEMM, the emitted output for the next layer's GEMMs) instead of the fp32
+  // hs when the tcgen05 recurrence or the grid-resident wide-layer recurrence runs: both kernels write them
+  const bool lp = tc_layer_supported(d) || wide_rec_supported(d);
   const size_t oh = lp ? 0 : take(n * sizeof(float));
   const size_t ohl = lp ? take(n * 2) : 0;
   const size_t oyl = lp ? (d->keep_prob < 1.f ? take(n * 2) : ohl) : 0;
   const size_t ohp = d->num_proj > 0 ? take((size_t)d->T * d->B * 2 * d->num_proj * sizeof(float)) : 0;
-  const bool lpb = lp && d->need_backward;
+  const bool lpb = tc_layer_supported(d) && d->need_backward;
   const size_t owp = lpb ? take(tc_pack_bytes(d->D_in, d->H)) : 0;
   const size_t odg = lpb ? take((size_t)d->T * d->B * 8 * d->H * 2) : 0;
   const size_t odwx = lpb ? take((size_t)d->D_in * 8 * d->H * 4) : 0;
@@ -109,12 +114,12 @@ int tc_layer_backward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16
 bool wide_rec_supported(const b2_lstm_desc* d);
 size_t wide_rec_workspace_bytes(const b2_lstm_desc* d);
 int wide_rec_forward(const b2_lstm_desc* d, const b2_lstm_params* fw, const b2_lstm_params* bw, const int32_t* seq_len,
-                     const float* G, float* y, float* gates, float* cs, float* hs, float* final_state, void* workspace,
+                     const float* G, float* y, float* gates, float* cs, __nv_bfloat16* hs_lp, __nv_bfloat16* y_lp, float* final_state, void* workspace,
                      cudaStream_t stream);
 
 int wide_rec_backward(const b2_lstm_desc* d, const b2_lstm_params* fw, const b2_lstm_params* bw, const int32_t* seq_len,
                       const float* dy, const float* gates, const float* cs, const float* d_final_state, float* dG,
-                      void* workspace, cudaStream_t stream);
+                      __nv_bfloat16* dG_lp, void* workspace, cudaStream_t stream);
 int tc_backward_join(cudaStream_t stream);
 int tc_backward_side_wait(cudaStream_t stream);
 void tc_profile_enable(int on);

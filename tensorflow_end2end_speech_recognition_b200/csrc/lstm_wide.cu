@@ -39,7 +39,9 @@ struct WideFwdArgs {
   const int* seq_len;
   const float* G;                 // [T*B, 8H] fp32, column = dir*4H + gate*H + u (TF order), bias included
   float* y;                       // [T,B,2H]
-  float* gates; float* cs; float* hs;   // fp32 reserve ([T,B,2,H,4], [T,B,2,H], [T,B,2,H]) or null
+  float* gates; float* cs;        // fp32 reserve ([T,B,2,H,4], [T,B,2,H]) or null
+  __nv_bfloat16* hs_lp;           // [T*B, 2H] bf16 h before dropout (A operand of the dWh GEMM) or null
+  __nv_bfloat16* y_lp;            // [T*B, 2H] bf16 emitted output (operand of the next layer's GEMMs) or null; may alias hs_lp
   float* final_state;             // [4,B,H] (c_fw, h_fw, c_bw, h_bw) or null
   __nv_bfloat16* hx;              // exchange buffer [2 dir][2 parity][WB][H]
   unsigned* bar;                  // [2] grid-barrier counters (zeroed before the launch)
@@ -246,11 +248,12 @@ lstm_wide_fwd_kernel(const WideFwdArgs a) {
         float yv = hov[j];
         if (a.keep_prob < 1.f && act[j]) yv = dropout_keep(a.seed, oidx, a.keep_prob) ? hov[j] / a.keep_prob : 0.f;
         a.y[oidx] = yv;
+        if (a.hs_lp) a.hs_lp[oidx] = __float2bfloat16(hov[j]);
+        if (a.y_lp && a.y_lp != a.hs_lp) a.y_lp[oidx] = __float2bfloat16(yv);
         if (a.gates) {
           const size_t cell = (row * 2 + dir) * H + u;
           *(float4*)(a.gates + cell * 4) = gsv[j];
           a.cs[cell] = cst[j];
-          a.hs[cell] = hov[j];
         }
       }
     }
@@ -292,6 +295,7 @@ struct WideBwdArgs {
   const float* gates; const float* cs;
   const float* dfinal;            // [4,B,H] or null
   float* dG;                      // [T*B, 8H] fp32, column = dir*4H + gate*H + u
+  __nv_bfloat16* dG_lp;           // the same in bf16 (operand of the time-batched GEMMs) or null
   __nv_bfloat16* dzx;             // exchange buffer [2 dir][2 parity][WB][4H]
   unsigned* bar;                  // [2]
 };
@@ -485,8 +489,14 @@ lstm_wide_bwd_kernel(const WideBwdArgs a) {
     for (int j = 0; j < 2; ++j) {
       const int b = bq + 16 * j;
       if (b < B) {
-        float* dz = a.dG + ((size_t)td * B + b) * 8 * H + (size_t)dir * 4 * H + u;
+        const size_t o = ((size_t)td * B + b) * 8 * H + (size_t)dir * 4 * H + u;
+        float* dz = a.dG + o;
         dz[0] = dzv[j].x; dz[H] = dzv[j].y; dz[2 * H] = dzv[j].z; dz[3 * H] = dzv[j].w;
+        if (a.dG_lp) {
+          __nv_bfloat16* dl = a.dG_lp + o;
+          dl[0] = __float2bfloat16(dzv[j].x); dl[H] = __float2bfloat16(dzv[j].y);
+          dl[2 * H] = __float2bfloat16(dzv[j].z); dl[3 * H] = __float2bfloat16(dzv[j].w);
+        }
       }
     }
   }
@@ -520,7 +530,8 @@ static int launch_wide_fwd(WideFwdArgs& a, cudaStream_t stream) {
 
 // workspace: wide_rec_workspace_bytes(d) bytes (exchange buffer | counters)
 int wide_rec_forward(const b2_lstm_desc* d, const b2_lstm_params* fw, const b2_lstm_params* bw, const int32_t* seq_len,
-                     const float* G, float* y, float* gates, float* cs, float* hs, float* final_state, void* workspace,
+                     const float* G, float* y, float* gates, float* cs, __nv_bfloat16* hs_lp, __nv_bfloat16* y_lp,
+                     float* final_state, void* workspace,
                      cudaStream_t stream) {
   WideFwdArgs a;
   a.T = d->T; a.B = d->B; a.D_in = d->D_in; a.H = d->H;
@@ -530,7 +541,7 @@ int wide_rec_forward(const b2_lstm_desc* d, const b2_lstm_params* fw, const b2_l
   for (int dir = 0; dir < 2; ++dir) {
     a.kernel[dir] = P[dir]->kernel; a.wi[dir] = P[dir]->w_i_diag; a.wf[dir] = P[dir]->w_f_diag; a.wo[dir] = P[dir]->w_o_diag;
   }
-  a.seq_len = seq_len; a.G = G; a.y = y; a.gates = gates; a.cs = cs; a.hs = hs; a.final_state = final_state;
+  a.seq_len = seq_len; a.G = G; a.y = y; a.gates = gates; a.cs = cs; a.hs_lp = hs_lp; a.y_lp = y_lp; a.final_state = final_state;
   a.hx = (__nv_bfloat16*)workspace;
   const size_t hx_bytes = align_up((size_t)2 * 2 * WB * 4 * d->H * 2, 256);
   a.bar = (unsigned*)((char*)workspace + hx_bytes);
@@ -573,7 +584,7 @@ static int launch_wide_bwd(WideBwdArgs& a, cudaStream_t stream) {
 // BPTT recurrence of a wide layer -> dG [T*B, 8H] fp32 (TF column order); same workspace block as the forward pass
 int wide_rec_backward(const b2_lstm_desc* d, const b2_lstm_params* fw, const b2_lstm_params* bw, const int32_t* seq_len,
                       const float* dy, const float* gates, const float* cs, const float* d_final_state, float* dG,
-                      void* workspace, cudaStream_t stream) {
+                      __nv_bfloat16* dG_lp, void* workspace, cudaStream_t stream) {
   WideBwdArgs a;
   a.T = d->T; a.B = d->B; a.D_in = d->D_in; a.H = d->H;
   a.use_peephole = d->use_peephole; a.cell_clip = d->cell_clip; a.keep_prob = d->keep_prob; a.seed = d->dropout_seed;
@@ -581,7 +592,7 @@ int wide_rec_backward(const b2_lstm_desc* d, const b2_lstm_params* fw, const b2_
   for (int dir = 0; dir < 2; ++dir) {
     a.kernel[dir] = P[dir]->kernel; a.wi[dir] = P[dir]->w_i_diag; a.wf[dir] = P[dir]->w_f_diag; a.wo[dir] = P[dir]->w_o_diag;
   }
-  a.seq_len = seq_len; a.dy = dy; a.gates = gates; a.cs = cs; a.dfinal = d_final_state; a.dG = dG;
+  a.seq_len = seq_len; a.dy = dy; a.gates = gates; a.cs = cs; a.dfinal = d_final_state; a.dG = dG; a.dG_lp = dG_lp;
   a.dzx = (__nv_bfloat16*)workspace;
   const size_t zx_bytes = align_up((size_t)2 * 2 * WB * 4 * d->H * 2, 256);
   a.bar = (unsigned*)((char*)workspace + zx_bytes);

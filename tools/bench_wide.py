@@ -32,7 +32,8 @@ def bench(T, B, D, H, backward, label, iters=3):
         if backward:
             ops.blstm_layer_backward(desc, x, seq, P["fw"], P["bw"], dy, res, G["fw"], G["bw"])
             ops.blstm_backward_join()
-    run()
+    for _ in range(4):
+        run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
