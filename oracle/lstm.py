@@ -121,6 +121,21 @@ def blstm_forward(x_btd, seq_len, layers, keep_prob=1.0, dropout_masks=None,
     return x, final
 
 
+def lstm_forward(x_btd, seq_len, layers, keep_prob=1.0, dropout_masks=None, forget_bias=1.0, cell_clip=None):
+    """Unidirectional stack (models/encoders/core/lstm.py:120-166: MultiRNNCell of DropoutWrapper(LSTM cells) under
+    dynamic_rnn with sequence_length).  layers: list of parameter dicts.  -> (outputs [T,B,H] time-major,
+    ((c, h) per layer))."""
+    x = x_btd.transpose(0, 1)
+    states = []
+    for li, p in enumerate(layers):
+        p = {k: torch.as_tensor(v) if not torch.is_tensor(v) else v for k, v in p.items()}
+        x, c, h = _run_direction(x, seq_len, p, False, forget_bias, cell_clip)
+        if dropout_masks is not None and keep_prob < 1.0:
+            x = x * dropout_masks[li] / keep_prob
+        states.append((c, h))
+    return x, tuple(states)
+
+
 def blstm_forward_numpy(x_btd, seq_len, layers, forget_bias=1.0, cell_clip=None):
     """Literal numpy loop (float64), independent of the torch form; used only to
     cross-check ``blstm_forward`` on tiny shapes."""

@@ -31,17 +31,34 @@ def layers_from_variables(variables, num_layers, use_peephole=True):
     return layers
 
 
+def uni_layers_from_variables(variables, num_layers, use_peephole=True):
+    """parameter dicts of the unidirectional stack (MultiRNNCell variable names, encoders/core/lstm.py:127-166)"""
+    layers = []
+    for i in range(num_layers):
+        scope = "multi_lstm/multi_rnn_cell/cell_%d/lstm_cell/" % i
+        p = {"kernel": variables[scope + "kernel"], "bias": variables[scope + "bias"]}
+        if use_peephole:
+            for k in ("w_i_diag", "w_f_diag", "w_o_diag"):
+                p[k] = variables[scope + k]
+        layers.append(p)
+    return layers
+
+
 def ctc_model_forward(variables, inputs_btd, seq_len, labels, num_layers, use_peephole=True,
-                      cell_clip=None, keep_prob=1.0, dropout_masks=None, vgg=None):
+                      cell_clip=None, keep_prob=1.0, dropout_masks=None, vgg=None, unidirectional=False):
     """variables: dict name -> torch tensor.  Returns (mean loss, logits [T,B,C], per-utt losses).
     vgg = (num_channels, width): run the VGG front-end (oracle/vgg.py) before the BLSTM stack
     (encoder_type 'vgg_blstm', ctc.py:135-147)."""
-    layers = layers_from_variables(variables, num_layers, use_peephole)
+    layers = None if unidirectional else layers_from_variables(variables, num_layers, use_peephole)
     if vgg is not None:
         from . import vgg as ovgg
         inputs_btd = ovgg.vgg_frontend(inputs_btd, variables, vgg[0], vgg[1])
-    enc, _ = olstm.blstm_forward(inputs_btd, seq_len, layers, keep_prob=keep_prob,
-                                 dropout_masks=dropout_masks, cell_clip=cell_clip)
+    if unidirectional:          # encoder_type 'lstm' / 'vgg_lstm'
+        enc, _ = olstm.lstm_forward(inputs_btd, seq_len, uni_layers_from_variables(variables, num_layers, use_peephole),
+                                    keep_prob=keep_prob, dropout_masks=dropout_masks, cell_clip=cell_clip)
+    else:
+        enc, _ = olstm.blstm_forward(inputs_btd, seq_len, layers, keep_prob=keep_prob,
+                                     dropout_masks=dropout_masks, cell_clip=cell_clip)
     T, B, E = enc.shape
     feat = enc.reshape(T * B, E)
     if "bottleneck/weights" in variables:                               # ctc.py:200-213 (keep_prob 1)

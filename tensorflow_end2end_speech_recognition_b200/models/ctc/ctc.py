@@ -72,12 +72,12 @@ class CTC(ModelBase):
         self.precision = precision
         self.device = torch.device(device if device is not None else "cuda:0")
 
-        if encoder_type in ["blstm"]:
+        if encoder_type in ["blstm", "lstm"]:
             self.encoder = load(encoder_type)(
                 num_units=num_units, num_proj=self.num_proj, num_layers=num_layers,
                 lstm_impl=lstm_impl, use_peephole=use_peephole, parameter_init=parameter_init,
                 clip_activation=clip_activation, time_major=True, precision=precision)
-        elif encoder_type in ["vgg_blstm"]:
+        elif encoder_type in ["vgg_blstm", "vgg_lstm"]:
             self.encoder = load(encoder_type)(
                 input_size=input_size, splice=splice, num_stack=num_stack, num_units=num_units,
                 num_proj=self.num_proj, num_layers=num_layers, lstm_impl=lstm_impl,
@@ -85,7 +85,8 @@ class CTC(ModelBase):
                 clip_activation=clip_activation, time_major=True, precision=precision)
         else:
             raise NotImplementedError(
-                "encoder_type %r: 'blstm' and 'vgg_blstm' are on the B200 hot path so far" % (encoder_type,))
+                "encoder_type %r: 'blstm', 'lstm', 'vgg_blstm' and 'vgg_lstm' are built on the B200 kernels" %
+                (encoder_type,))
 
         rng = np.random.RandomState(seed)
         named = self.encoder.create_variables(input_size * num_stack * splice, rng)

@@ -310,3 +310,18 @@ def test_seq2seq_oracle_loss_gradient_matches_finite_differences():
         vm[name][idx] -= eps
         fd = (float(loss_of(vp)[0].detach()) - float(loss_of(vm)[0].detach())) / (2 * eps)
         assert abs(fd - float(t[name].grad[idx])) <= 1e-6 + 1e-5 * abs(fd), (name, fd, float(t[name].grad[idx]))
+
+
+def test_unidirectional_oracle_is_the_forward_half_of_the_blstm_oracle():
+    """oracle/lstm.py::lstm_forward (encoder_type 'lstm') against blstm_forward's forward direction, one layer, ragged."""
+    import torch
+    from oracle import lstm as ol
+    layers = ol.init_blstm_params(6, 8, 1, parameter_init=0.3, seed=1)
+    x = torch.tensor(np.random.RandomState(0).randn(3, 7, 6))
+    seq = [7, 4, 6]
+    both = [{d: {k: torch.tensor(v, dtype=torch.float64) for k, v in layers[0][d].items()} for d in layers[0]}]
+    y2, fs2 = ol.blstm_forward(x, seq, both)
+    y1, st = ol.lstm_forward(x, seq, [both[0]["fw"]])
+    assert y1.shape == (7, 3, 8) and len(st) == 1
+    assert float((y1 - y2[:, :, :8]).abs().max()) == 0.0
+    assert float((st[0][0] - fs2[0][0]).abs().max()) == 0.0 and float((st[0][1] - fs2[0][1]).abs().max()) == 0.0
