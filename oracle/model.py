@@ -109,15 +109,16 @@ class OracleTrainer(object):
 
 
 def multitask_ctc_forward(variables, inputs_btd, seq_len, labels_main, labels_sub, num_layers_main,
-                          num_layers_sub, main_task_weight, use_peephole=True):
+                          num_layers_sub, main_task_weight, use_peephole=True, unidirectional=False):
     """Hierarchical CTC (models/ctc/multitask_ctc.py:109-191,225-296): main head on the top BLSTM layer, sub head on
     layer ``num_layers_sub`` (blstm.py:325-331); total = w * mean(ctc_main) + (1 - w) * mean(ctc_sub).
     variables: dict name -> torch tensor.  Returns (total, logits_main [T,B,Cm], logits_sub [T,B,Cs])."""
-    layers = layers_from_variables(variables, num_layers_main, use_peephole)
+    layers = (uni_layers_from_variables if unidirectional else layers_from_variables)(variables, num_layers_main,
+                                                                                      use_peephole)
     x = inputs_btd
     enc_sub = None
     for i, layer in enumerate(layers, 1):
-        y, _ = olstm.blstm_forward(x, seq_len, [layer])
+        y, _ = (olstm.lstm_forward if unidirectional else olstm.blstm_forward)(x, seq_len, [layer])
         if i == num_layers_sub:
             enc_sub = y
         x = y.transpose(0, 1)

@@ -34,8 +34,8 @@ class MultitaskCTC(CTC):
         assert float(weight_decay) >= 0, "weight_decay must not be a negative value."
         if float(main_task_weight) < 0 or float(main_task_weight) > 1:
             raise ValueError("Set main_task_weight between 0 to 1.")                 # multitask_ctc.py:90-91
-        if encoder_type not in ("multitask_blstm",):
-            raise NotImplementedError("encoder_type %r: only 'multitask_blstm' is on the B200 hot path" % (encoder_type,))
+        if encoder_type not in ("multitask_blstm", "multitask_lstm"):
+            raise NotImplementedError("encoder_type %r: 'multitask_blstm' and 'multitask_lstm' are built" % (encoder_type,))
         self.encoder_type, self.input_size, self.splice, self.num_stack = encoder_type, input_size, splice, 1
         self.num_units = num_units
         self.num_proj = int(num_proj) if num_proj not in (None, 0, "0") else None

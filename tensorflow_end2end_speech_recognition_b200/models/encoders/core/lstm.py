@@ -91,9 +91,13 @@ class LSTMEncoder(BLSTMEncoder):
             saved.append((desc, x, reserve, i_layer))
             x = y2[:, :, :H].contiguous()
             states.append((fs[0], fs[1]))
+            if self.num_layers_sub is not None and i_layer == self.num_layers_sub:     # lstm.py: outputs_sub
+                self.sub_outputs, self.sub_final_state = x, tuple(states)
         self._saved = (saved, inputs_seq_len)
         self.output_lp = None
-        self.sub_outputs = self.sub_final_state = self.sub_output_lp = None
+        self.sub_output_lp = None
+        if self.num_layers_sub is None:
+            self.sub_outputs = self.sub_final_state = None
         outputs = x if self.time_major else ops.transpose_01(x)
         return outputs, tuple(states)
 
@@ -101,11 +105,13 @@ class LSTMEncoder(BLSTMEncoder):
     def backward(self, d_outputs, variables, grads, need_dx=False, on_layer_done=None, d_final_state=None,
                  saved=None, d_inject=None):
         """d_outputs [T,B,H] (time-major).  Accumulates into ``grads``; returns d(inputs) [T,B,D] or None."""
-        assert d_final_state is None and not d_inject, "LSTMEncoder: no bridge / sub-task gradient paths"
+        assert d_final_state is None, "LSTMEncoder: no bridge gradient path"
         own = saved is None
         saved, seq_len = self._saved if own else saved
         dy = d_outputs
         for desc, x, reserve, i_layer in reversed(saved):
+            if d_inject and i_layer in d_inject:      # gradient of a head tapped at this layer's output (sub task)
+                dy = ops.add_(dy.contiguous(), d_inject[i_layer])
             pf = self._layer_params(variables, i_layer)
             gf = self._layer_params(grads, i_layer)
             idle, scratch = self._idle_direction(pf)
@@ -118,3 +124,31 @@ class LSTMEncoder(BLSTMEncoder):
         if own:
             self._saved = None
         return dy
+
+
+class MultitaskLSTMEncoder(LSTMEncoder):
+    """``models/encoders/core/multitask_lstm.py``: the unidirectional stack with a second output tapped after layer
+    ``num_layers_sub``; ``enc(...) -> (outputs, final_state, outputs_sub, final_state_sub)``."""
+
+    def __init__(self, num_units, num_proj, num_layers_main, num_layers_sub, lstm_impl, use_peephole,
+                 parameter_init, clip_activation, time_major=False, name="multitask_lstm_encoder",
+                 precision="fp32", tf_version="1.2.0"):
+        super(MultitaskLSTMEncoder, self).__init__(num_units, num_proj, num_layers_main, lstm_impl, use_peephole,
+                                                   parameter_init, clip_activation, time_major=time_major, name=name,
+                                                   precision=precision, tf_version=tf_version)
+        if num_layers_sub < 1 or num_layers_main < num_layers_sub:
+            raise ValueError("Set num_layers_sub between 1 to num_layers_main.")
+        self.num_layers_main, self.num_layers_sub = num_layers_main, num_layers_sub
+
+    def __call__(self, inputs, inputs_seq_len, keep_prob, is_training=True, variables=None, dropout_seed=0):
+        outputs, final_state = super(MultitaskLSTMEncoder, self).__call__(
+            inputs, inputs_seq_len, keep_prob, is_training, variables=variables, dropout_seed=dropout_seed)
+        outputs_sub = self.sub_outputs if self.time_major else ops.transpose_01(self.sub_outputs)
+        return outputs, final_state, outputs_sub, self.sub_final_state
+
+    def backward(self, d_outputs, variables, grads, d_outputs_sub=None, **kw):
+        inject = {self.num_layers_sub: d_outputs_sub} if d_outputs_sub is not None else None
+        if inject and self.num_layers_sub == self.num_layers:
+            d_outputs = ops.add_(d_outputs.contiguous(), d_outputs_sub)
+            inject = None
+        return super(MultitaskLSTMEncoder, self).backward(d_outputs, variables, grads, d_inject=inject, **kw)

@@ -21,11 +21,15 @@ def _batch(rng, B, T, D, Cm, Cs):
 
 @pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 3e-2)])
 @pytest.mark.parametrize("lsub", [1, 2, 3])
-def test_multitask_loss_and_grads(cuda, precision, tol, lsub):
+@pytest.mark.parametrize("encoder_type", ["multitask_blstm", "multitask_lstm"])
+def test_multitask_loss_and_grads(cuda, precision, tol, lsub, encoder_type):
     from tensorflow_end2end_speech_recognition_b200.models.ctc.multitask_ctc import MultitaskCTC
+    if encoder_type == "multitask_lstm" and (precision == "bf16" or lsub == 3):
+        pytest.skip("the unidirectional variant shares every kernel: fp32, two tap positions")
+    uni = encoder_type == "multitask_lstm"
     rng = np.random.RandomState(7 + lsub)
     B, T, D, H, L, Cm, Cs, w = 5, 36, 20, 32, 3, 9, 13, 0.7
-    model = MultitaskCTC(encoder_type="multitask_blstm", input_size=D, num_units=H, num_layers_main=L,
+    model = MultitaskCTC(encoder_type=encoder_type, input_size=D, num_units=H, num_layers_main=L,
                          num_layers_sub=lsub, num_classes_main=Cm, num_classes_sub=Cs, main_task_weight=w,
                          parameter_init=0.1, clip_grad_norm=5.0, precision=precision, device=cuda, seed=5)
     x, seq, lm, ls = _batch(rng, B, T, D, Cm, Cs)
@@ -34,7 +38,8 @@ def test_multitask_loss_and_grads(cuda, precision, tol, lsub):
     torch.cuda.synchronize()
     vs = {v.name: torch.tensor(v.tensor.cpu().numpy(), dtype=torch.float64, requires_grad=True)
           for v in model.trainable_variables()}
-    total, lgm, lgs = omodel.multitask_ctc_forward(vs, torch.tensor(x, dtype=torch.float64), seq, lm, ls, L, lsub, w)
+    total, lgm, lgs = omodel.multitask_ctc_forward(vs, torch.tensor(x, dtype=torch.float64), seq, lm, ls, L, lsub, w,
+                                                   unidirectional=uni)
     total.backward()
     assert abs(float(loss) - float(total)) <= tol * abs(float(total))
     np.testing.assert_allclose(logits_main.cpu().numpy(), lgm.detach().numpy(), rtol=tol, atol=tol)
