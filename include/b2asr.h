@@ -598,6 +598,38 @@ int b2_allreduce_mean(b2_comm_t comm, float* const* buckets, const int64_t* size
 int b2_allreduce_mean_local(const b2_comm_t* comms, float* const* buffers, int64_t n,
                             int ndev, const b2_stream_t* streams);
 
+/* ------------------------------------------------------------------ GRU layers
+ * tf.contrib.rnn.GRUCell under bidirectional_dynamic_rnn (models/encoders/core/gru.py:128-160, BGRUEncoder) or
+ * MultiRNNCell + dynamic_rnn (gru.py:52-73, GRUEncoder: bind an all-zero second direction):
+ *   [r, u] = sigmoid([x, h] . gates_kernel + gates_bias),  c = tanh([x, r*h] . cand_kernel + cand_bias),
+ *   h' = u*h + (1-u)*c;  sequence_length semantics and output dropout as in the LSTM layers.  fp32.
+ *   x [T,B,D_in] time-major; y [T,B,2H] = concat(fw, bw); final_state [2,B,H] = h_fw, h_bw (may be NULL);
+ *   gradients are ACCUMULATED into g_fw / g_bw; dx may be NULL. */
+typedef struct {
+  int32_t T, B, D_in, H;
+  float keep_prob;            /* DropoutWrapper(output_keep_prob); 1 = off */
+  uint64_t dropout_seed;
+  int32_t need_backward;
+} b2_gru_desc;
+typedef struct {
+  const float* gates_kernel;  /* [(D_in+H), 2H] rows = [x; h], columns r | u */
+  const float* gates_bias;    /* [2H] (TF initialises it to 1) */
+  const float* cand_kernel;   /* [(D_in+H), H]  rows = [x; r*h] */
+  const float* cand_bias;     /* [H] */
+} b2_gru_params;
+typedef struct {
+  float* gates_kernel; float* gates_bias; float* cand_kernel; float* cand_bias;
+} b2_gru_grads;
+size_t b2_bgru_reserve_bytes(const b2_gru_desc* d);
+size_t b2_bgru_workspace_bytes(const b2_gru_desc* d);
+int b2_bgru_layer_forward(const b2_gru_desc* d, const float* x, const int32_t* seq_len, const b2_gru_params* fw,
+                          const b2_gru_params* bw, float* y, float* final_state, void* reserve, void* workspace,
+                          size_t workspace_bytes, b2_stream_t stream);
+int b2_bgru_layer_backward(const b2_gru_desc* d, const float* x, const int32_t* seq_len, const b2_gru_params* fw,
+                           const b2_gru_params* bw, const float* dy, const void* reserve, float* dx,
+                           const b2_gru_grads* g_fw, const b2_gru_grads* g_bw, void* workspace,
+                           size_t workspace_bytes, b2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -171,3 +171,43 @@ def blstm_forward_numpy(x_btd, seq_len, layers, forget_bias=1.0, cell_clip=None)
             outs.append(out)
         x = np.concatenate(outs, axis=2)
     return x
+
+
+# ---------------------------------------------------------------- GRU (models/encoders/core/gru.py)
+def gru_cell_step(x, h_prev, p):
+    """tf.contrib.rnn.GRUCell (TF 1.x): [r, u] = sigmoid([x, h] W_g + b_g); c = tanh([x, r*h] W_c + b_c);
+    h' = u*h + (1-u)*c.  p: 'gates/kernel' [(D+H),2H], 'gates/bias', 'candidate/kernel' [(D+H),H], 'candidate/bias'."""
+    H = p["candidate/bias"].shape[0]
+    ru = torch.sigmoid(torch.cat([x, h_prev], 1) @ p["gates/kernel"] + p["gates/bias"])
+    r, u = ru[:, :H], ru[:, H:]
+    c = torch.tanh(torch.cat([x, r * h_prev], 1) @ p["candidate/kernel"] + p["candidate/bias"])
+    return u * h_prev + (1 - u) * c
+
+
+def _run_gru_direction(x_tbd, seq_len, p, reverse):
+    T, B, _ = x_tbd.shape
+    H = p["candidate/bias"].shape[0]
+    h = x_tbd.new_zeros(B, H)
+    outs = [None] * T
+    lens = torch.as_tensor(np.asarray(seq_len), dtype=torch.long)
+    for t in (range(T - 1, -1, -1) if reverse else range(T)):
+        m = (t < lens).to(x_tbd.dtype).unsqueeze(1)
+        h_new = gru_cell_step(x_tbd[t], h, p)
+        outs[t] = h_new * m
+        h = h_new * m + h * (1 - m)
+    return torch.stack(outs, 0), h
+
+
+def gru_forward(x_btd, seq_len, layers, bidirectional):
+    """layers: list of {'fw': params[, 'bw': params]}.  -> (outputs [T,B,H or 2H] time-major, final state of the last
+    layer: (h_fw, h_bw) or h)."""
+    x = x_btd.transpose(0, 1)
+    final = None
+    for layer in layers:
+        of, hf = _run_gru_direction(x, seq_len, layer["fw"], False)
+        if bidirectional:
+            ob, hb = _run_gru_direction(x, seq_len, layer["bw"], True)
+            x, final = torch.cat([of, ob], 2), (hf, hb)
+        else:
+            x, final = of, hf
+    return x, final

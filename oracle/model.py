@@ -44,16 +44,32 @@ def uni_layers_from_variables(variables, num_layers, use_peephole=True):
     return layers
 
 
+def gru_layers_from_variables(variables, num_layers, bidirectional):
+    layers = []
+    for i in range(1, num_layers + 1):
+        layer = {}
+        for d in (("fw", "bw") if bidirectional else ("fw",)):
+            scope = ("bgru_hidden%d/%s/gru_cell/" % (i, d)) if bidirectional else \
+                ("multi_gru/multi_rnn_cell/cell_%d/gru_cell/" % (i - 1))
+            layer[d] = {k: variables[scope + k] for k in ("gates/kernel", "gates/bias", "candidate/kernel",
+                                                          "candidate/bias")}
+        layers.append(layer)
+    return layers
+
+
 def ctc_model_forward(variables, inputs_btd, seq_len, labels, num_layers, use_peephole=True,
-                      cell_clip=None, keep_prob=1.0, dropout_masks=None, vgg=None, unidirectional=False):
+                      cell_clip=None, keep_prob=1.0, dropout_masks=None, vgg=None, unidirectional=False, gru=None):
     """variables: dict name -> torch tensor.  Returns (mean loss, logits [T,B,C], per-utt losses).
     vgg = (num_channels, width): run the VGG front-end (oracle/vgg.py) before the BLSTM stack
     (encoder_type 'vgg_blstm', ctc.py:135-147)."""
-    layers = None if unidirectional else layers_from_variables(variables, num_layers, use_peephole)
+    layers = None if (unidirectional or gru) else layers_from_variables(variables, num_layers, use_peephole)
     if vgg is not None:
         from . import vgg as ovgg
         inputs_btd = ovgg.vgg_frontend(inputs_btd, variables, vgg[0], vgg[1])
-    if unidirectional:          # encoder_type 'lstm' / 'vgg_lstm'
+    if gru:                     # encoder_type 'gru' / 'bgru' (gru = "gru" | "bgru")
+        enc, _ = olstm.gru_forward(inputs_btd, seq_len, gru_layers_from_variables(variables, num_layers, gru == "bgru"),
+                                   gru == "bgru")
+    elif unidirectional:        # encoder_type 'lstm' / 'vgg_lstm'
         enc, _ = olstm.lstm_forward(inputs_btd, seq_len, uni_layers_from_variables(variables, num_layers, use_peephole),
                                     keep_prob=keep_prob, dropout_masks=dropout_masks, cell_clip=cell_clip)
     else:

@@ -30,6 +30,16 @@ class LstmParams(C.Structure):
 LstmGrads = LstmParams  # same layout (non-const pointers)
 
 
+class GruDesc(C.Structure):
+    _fields_ = [("T", C.c_int32), ("B", C.c_int32), ("D_in", C.c_int32), ("H", C.c_int32), ("keep_prob", C.c_float),
+                ("dropout_seed", C.c_uint64), ("need_backward", C.c_int32)]
+
+
+class GruParams(C.Structure):
+    _fields_ = [("gates_kernel", C.c_void_p), ("gates_bias", C.c_void_p), ("cand_kernel", C.c_void_p),
+                ("cand_bias", C.c_void_p)]
+
+
 class VggDesc(C.Structure):
     _fields_ = [("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("keep_prob", C.c_float),
                 ("dropout_seed", C.c_uint64), ("precision", C.c_int32)]
@@ -82,6 +92,12 @@ PROTOTYPES = {
     "b2_gemm": (_i, [_i, _i, _i, _i, _i, _f, _p, _i, _p, _i, _f, _p, _i, _p, _i, _p, _sz, _p]),
     "b2_gemm_lp": (_i, [_i, _i, _i, _i, _i, _f, _p, _i, _p, _i, _p, _i, _f, _p, _i, _p, _i, _p, _sz, _p]),
     "b2_gemm_bf16": (_i, [_i, _i, _i, _i, _i, _f, _p, _i, _p, _i, _p, _i, _p, _i, _i, _p]),
+    "b2_bgru_reserve_bytes": (_sz, [C.POINTER(GruDesc)]),
+    "b2_bgru_workspace_bytes": (_sz, [C.POINTER(GruDesc)]),
+    "b2_bgru_layer_forward": (_i, [C.POINTER(GruDesc), _p, _p, C.POINTER(GruParams), C.POINTER(GruParams), _p, _p, _p,
+                                   _p, _sz, _p]),
+    "b2_bgru_layer_backward": (_i, [C.POINTER(GruDesc), _p, _p, C.POINTER(GruParams), C.POINTER(GruParams), _p, _p, _p,
+                                    C.POINTER(GruParams), C.POINTER(GruParams), _p, _sz, _p]),
     "b2_blstm_reserve_bytes": (_sz, [C.POINTER(LstmDesc)]),
     "b2_blstm_workspace_bytes": (_sz, [C.POINTER(LstmDesc)]),
     "b2_blstm_layer_forward": (_i, [C.POINTER(LstmDesc), _p, _p, _p, C.POINTER(LstmParams),

@@ -77,6 +77,9 @@ class CTC(ModelBase):
                 num_units=num_units, num_proj=self.num_proj, num_layers=num_layers,
                 lstm_impl=lstm_impl, use_peephole=use_peephole, parameter_init=parameter_init,
                 clip_activation=clip_activation, time_major=True, precision=precision)
+        elif encoder_type in ["bgru", "gru"]:                       # ctc.py: GRU encoders take no cell options
+            self.encoder = load(encoder_type)(num_units=num_units, num_layers=num_layers,
+                                              parameter_init=parameter_init, time_major=True, precision=precision)
         elif encoder_type in ["vgg_blstm", "vgg_lstm"]:
             self.encoder = load(encoder_type)(
                 input_size=input_size, splice=splice, num_stack=num_stack, num_units=num_units,
@@ -85,7 +88,7 @@ class CTC(ModelBase):
                 clip_activation=clip_activation, time_major=True, precision=precision)
         else:
             raise NotImplementedError(
-                "encoder_type %r: 'blstm', 'lstm', 'vgg_blstm' and 'vgg_lstm' are built on the B200 kernels" %
+                "encoder_type %r: 'blstm', 'lstm', 'bgru', 'gru', 'vgg_blstm' and 'vgg_lstm' are built on the B200 kernels" %
                 (encoder_type,))
 
         rng = np.random.RandomState(seed)

@@ -1,13 +1,14 @@
 """Encoder registry, same entry point as ``models/encoders/load_encoder.py:26-57``."""
 from .core.blstm import BLSTMEncoder
+from .core.gru import BGRUEncoder, GRUEncoder
 from .core.lstm import LSTMEncoder, MultitaskLSTMEncoder
 from .core.multitask_blstm import MultitaskBLSTMEncoder
 from .core.vgg_blstm import VGGBLSTMEncoder
 from .core.vgg_lstm import VGGLSTMEncoder
 
-# the encoders built on the B200 kernels; the reference's other entries (gru / bgru, cnn_zhang, vgg_wang,
-# pyramid_blstm, cldnn_wang, student_*; load_encoder.py:26-44) are not built
-ENCODERS = {"blstm": BLSTMEncoder, "lstm": LSTMEncoder, "vgg_blstm": VGGBLSTMEncoder, "vgg_lstm": VGGLSTMEncoder,
+# the encoders built on the B200 kernels; the reference's other entries (cnn_zhang, vgg_wang, pyramid_blstm,
+# cldnn_wang, student_*; load_encoder.py:26-44) are not built
+ENCODERS = {"blstm": BLSTMEncoder, "lstm": LSTMEncoder, "bgru": BGRUEncoder, "gru": GRUEncoder, "vgg_blstm": VGGBLSTMEncoder, "vgg_lstm": VGGLSTMEncoder,
             "multitask_blstm": MultitaskBLSTMEncoder, "multitask_lstm": MultitaskLSTMEncoder}
 
 

@@ -332,6 +332,50 @@ def blstm_layer_forward(desc, x, seq_len, p_fw, p_bw, want_final_state=False, x_
     return y, fs, reserve
 
 
+# ---------------------------------------------------------------- GRU layers (csrc/gru.cu)
+def gru_desc(T, B, D_in, H, keep_prob=1.0, dropout_seed=0, need_backward=True):
+    return _lib.GruDesc(T, B, D_in, H, float(keep_prob), int(dropout_seed), int(bool(need_backward)))
+
+
+def _gru_struct(p):
+    return _lib.GruParams(p["gates/kernel"].data_ptr(), p["gates/bias"].data_ptr(), p["candidate/kernel"].data_ptr(),
+                          p["candidate/bias"].data_ptr())
+
+
+def bgru_layer_forward(desc, x, seq_len, p_fw, p_bw, want_final_state=False):
+    """x [T,B,D] -> (y [T,B,2H], final_state [2,B,H] or None, reserve).  Parameter dicts: TF GRUCell variable names
+    ``gates/kernel [(D+H),2H]``, ``gates/bias``, ``candidate/kernel [(D+H),H]``, ``candidate/bias``."""
+    lib = _lib.load()
+    _require_cuda(x, seq_len)
+    dev = x.device
+    y = torch.empty((desc.T, desc.B, 2 * desc.H), dtype=torch.float32, device=dev)
+    fs = torch.empty((2, desc.B, desc.H), dtype=torch.float32, device=dev) if want_final_state else None
+    reserve = torch.empty(lib.b2_bgru_reserve_bytes(C.byref(desc)), dtype=torch.uint8, device=dev)
+    nbytes = lib.b2_bgru_workspace_bytes(C.byref(desc))
+    ws = workspace("gru", nbytes, dev)
+    fw, bw = _gru_struct(p_fw), _gru_struct(p_bw)
+    rc = lib.b2_bgru_layer_forward(C.byref(desc), _ptr(x.contiguous()), _ptr(seq_len), C.byref(fw), C.byref(bw),
+                                   _ptr(y), _ptr(fs), _ptr(reserve), _ptr(ws), nbytes, _stream())
+    _lib.check(rc, "b2_bgru_layer_forward")
+    return y, fs, reserve
+
+
+def bgru_layer_backward(desc, x, seq_len, p_fw, p_bw, dy, reserve, g_fw, g_bw, need_dx=True):
+    """Accumulates into the gradient dicts; returns dx [T,B,D] or None."""
+    lib = _lib.load()
+    _require_cuda(x, dy)
+    dev = x.device
+    dx = torch.empty((desc.T, desc.B, desc.D_in), dtype=torch.float32, device=dev) if need_dx else None
+    nbytes = lib.b2_bgru_workspace_bytes(C.byref(desc))
+    ws = workspace("gru", nbytes, dev)
+    fw, bw, gf, gb = _gru_struct(p_fw), _gru_struct(p_bw), _gru_struct(g_fw), _gru_struct(g_bw)
+    rc = lib.b2_bgru_layer_backward(C.byref(desc), _ptr(x.contiguous()), _ptr(seq_len), C.byref(fw), C.byref(bw),
+                                    _ptr(dy.contiguous()), _ptr(reserve), _ptr(dx), C.byref(gf), C.byref(gb), _ptr(ws),
+                                    nbytes, _stream())
+    _lib.check(rc, "b2_bgru_layer_backward")
+    return dx
+
+
 def blstm_backward_join():
     """current stream waits for the side-stream weight-gradient GEMMs of the bf16 path."""
     _lib.check(_lib.load().b2_blstm_backward_join(_stream()), "b2_blstm_backward_join")
