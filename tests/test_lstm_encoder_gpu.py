@@ -70,4 +70,4 @@ def test_load_encoder_registry():
     from tensorflow_end2end_speech_recognition_b200.models.encoders.load_encoder import load
     assert load("lstm").__name__ == "LSTMEncoder" and load("vgg_lstm").__name__ == "VGGLSTMEncoder"
     with pytest.raises(ValueError):
-        load("gru")
+        load("cnn_zhang")
