@@ -138,3 +138,47 @@ def test_forward_chunk_chain_bit_identical(cuda):
         # weight gradients are accumulated with split-K atomics: equal up to summation order
         g0 = outs["0"][2]
         assert np.abs(outs[chunks][2] - g0).max() <= 1e-5 * np.abs(g0).max()
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 3e-2)])
+def test_encoder_stack_with_dropout_matches_oracle_masks(cuda, precision, tol):
+    """Three BLSTM layers with DropoutWrapper(output_keep_prob = 0.8): every layer's counter-hash mask reproduced for the
+    oracle (tests/util_dropout.py), encoder output and ALL gradients (incl. d(inputs)) vs fp64 autograd -- the backward
+    masks travel through the stack (layer l's dy is layer l+1's dx)."""
+    import torch
+    from oracle import lstm as olstm
+    from tests.util_dropout import dropout_mask
+    from tensorflow_end2end_speech_recognition_b200.models.encoders.core.blstm import BLSTMEncoder
+    rng = np.random.RandomState(17)
+    B, T, D, H, L, keep, dseed = 6, 40, 24, 64, 3, 0.8, 5
+    enc = BLSTMEncoder(H, None, L, "LSTMBlockCell", True, 0.2, None, time_major=True, precision=precision)
+    named = enc.create_variables(D, rng)
+    variables = {n: torch.tensor(a, device=cuda) for n, a in named}
+    grads = {n: torch.zeros_like(v) for n, v in variables.items()}
+    x = rng.randn(B, T, D).astype(np.float32)
+    seq = np.array([T, 31, 40, 22, 36, 27], np.int32)
+    for b in range(B):
+        x[b, seq[b]:] = 0
+    dy = rng.randn(T, B, 2 * H).astype(np.float32)
+    xd, sd = torch.tensor(x, device=cuda), torch.tensor(seq, device=cuda)
+    y, _ = enc(xd, sd, keep, True, variables=variables, dropout_seed=dseed)
+    dx = enc.backward(torch.tensor(dy, device=cuda), variables, grads, need_dx=True)
+    torch.cuda.synchronize()
+    # oracle with the same masks
+    vs = {n: torch.tensor(np.asarray(a, np.float64), requires_grad=True) for n, a in named}
+    layers = []
+    for i in range(1, L + 1):
+        layers.append({d: {k: vs["blstm_hidden%d/%s/lstm_cell/%s" % (i, d, k)]
+                           for k in ("kernel", "bias", "w_i_diag", "w_f_diag", "w_o_diag")} for d in ("fw", "bw")})
+    masks = [torch.tensor(dropout_mask(dseed * 131 + i, T * B * 2 * H, keep).reshape(T, B, 2 * H).astype(np.float64))
+             for i in range(1, L + 1)]
+    xt = torch.tensor(x.astype(np.float64), requires_grad=True)
+    y_ref, _ = olstm.blstm_forward(xt, seq, layers, keep_prob=keep, dropout_masks=masks)
+    (y_ref * torch.tensor(dy.astype(np.float64))).sum().backward()
+    yr = y_ref.detach().numpy()
+    assert np.abs(y.cpu().numpy() - yr).max() <= tol * max(1.0, np.abs(yr).max())
+    g = xt.grad.numpy().transpose(1, 0, 2)
+    assert np.abs(dx.cpu().numpy() - g).max() <= 2 * tol * max(1e-3, np.abs(g).max()), "d(inputs)"
+    for n in vs:
+        g = vs[n].grad.numpy()
+        assert np.abs(grads[n].cpu().numpy() - g).max() <= 2 * tol * max(1e-3, np.abs(g).max()), n
