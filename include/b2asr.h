@@ -167,6 +167,12 @@ typedef struct {
                                  recurrent h is (o*tanh(c)) . projection [H,P]; kernel is [(D_in+P),4H],
                                  y [T,B,2P], final_state = c_fw [B,H], h_fw [B,P], c_bw [B,H], h_bw [B,P];
                                  fp32 CUDA-core path whatever `precision` says */
+  /* backward-only hand-over of DropoutWrapper's mask between stacked layers (0 / 0 / 0 = off; only honoured where
+   * b2_blstm_layer_path() == 1, B2_ERR_UNSUPPORTED elsewhere): */
+  float dx_keep_prob;         /* in (0,1): the dx this call emits is multiplied by the output-dropout mask of the layer
+                                 BELOW (its keep_prob / dropout_seed) inside the GEMM that produces it ...           */
+  uint64_t dx_dropout_seed;
+  int32_t dy_premasked;       /* ... and that layer's own backward call is told that its dy already carries the mask */
 } b2_lstm_desc;
 
 /* parameters of one direction, TF LSTMBlockCell layout:
@@ -189,6 +195,9 @@ typedef struct {
   float* projection;
 } b2_lstm_grads;
 
+/* which implementation a layer of this shape runs on: 0 fp32 CUDA-core step kernels (or the bf16 hybrid with per-frame
+ * recurrence), 1 cluster/TMEM tcgen05 recurrence (lstm_rec_tc.cu), 2 grid-resident wide-layer recurrence (lstm_wide.cu) */
+int b2_blstm_layer_path(const b2_lstm_desc* d);
 size_t b2_blstm_reserve_bytes(const b2_lstm_desc* d);
 size_t b2_blstm_workspace_bytes(const b2_lstm_desc* d);
 

@@ -19,7 +19,9 @@ class LstmDesc(C.Structure):
     _fields_ = [("T", C.c_int32), ("B", C.c_int32), ("D_in", C.c_int32), ("H", C.c_int32),
                 ("use_peephole", C.c_int32), ("forget_bias", C.c_float), ("cell_clip", C.c_float),
                 ("keep_prob", C.c_float), ("dropout_seed", C.c_uint64), ("precision", C.c_int32),
-                ("need_backward", C.c_int32), ("num_proj", C.c_int32)]
+                ("need_backward", C.c_int32), ("num_proj", C.c_int32),
+                # backward-only hand-over of the dropout mask between stacked layers (include/b2asr.h)
+                ("dx_keep_prob", C.c_float), ("dx_dropout_seed", C.c_uint64), ("dy_premasked", C.c_int32)]
 
 
 class LstmParams(C.Structure):
@@ -98,6 +100,7 @@ PROTOTYPES = {
                                    _p, _sz, _p]),
     "b2_bgru_layer_backward": (_i, [C.POINTER(GruDesc), _p, _p, C.POINTER(GruParams), C.POINTER(GruParams), _p, _p, _p,
                                     C.POINTER(GruParams), C.POINTER(GruParams), _p, _sz, _p]),
+    "b2_blstm_layer_path": (_i, [C.POINTER(LstmDesc)]),
     "b2_blstm_reserve_bytes": (_sz, [C.POINTER(LstmDesc)]),
     "b2_blstm_workspace_bytes": (_sz, [C.POINTER(LstmDesc)]),
     "b2_blstm_layer_forward": (_i, [C.POINTER(LstmDesc), _p, _p, _p, C.POINTER(LstmParams),

@@ -36,6 +36,9 @@ struct GemmArgs {
   // implicit convolution over a zero-bordered NHWC buffer (vgg.cu): K block kb belongs to kernel row
   // kb / a_tap_kb; its A tile sits a_tap_rows rows further down and (kb % a_tap_kb) * 64 columns in.  0 = plain GEMM.
   int a_tap_kb, a_tap_rows;
+  // EPI_STORE_F32 only: DropoutWrapper backward mask fused into the store -- C[row, col] is kept (and scaled by
+  // 1/drop_keep) iff dropout_keep(drop_seed, (drop_row0 + row) * ldc + col); drop_keep >= 1: off
+  float drop_keep; unsigned long long drop_seed; long long drop_row0;
 };
 
 template <int BN> struct GemmCfg {
@@ -205,6 +208,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const size_t idx = (size_t)row * args.ldc + col;
           const bool full4 = col + 3 < args.N;
           if (args.epi == EPI_STORE_F32) {
+            if (args.drop_keep < 1.f) {
+              const unsigned long long e = (unsigned long long)(args.drop_row0 + row) * (unsigned long long)args.ldc + col;
+              const float sc = 1.f / args.drop_keep;
+              o.x = dropout_keep(args.drop_seed, e, args.drop_keep) ? o.x * sc : 0.f;
+              o.y = dropout_keep(args.drop_seed, e + 1, args.drop_keep) ? o.y * sc : 0.f;
+              o.z = dropout_keep(args.drop_seed, e + 2, args.drop_keep) ? o.z * sc : 0.f;
+              o.w = dropout_keep(args.drop_seed, e + 3, args.drop_keep) ? o.w * sc : 0.f;
+            }
             float* p = (float*)args.C + idx;
             if (full4 && vec_ok) *(float4*)p = o;
             else {
@@ -316,6 +327,13 @@ int make_tmap_generic(CUtensorMap* tm, int dtype_is_f32, const void* base, int r
 static thread_local int g_cta_limit = 0;
 void gemm_set_cta_limit(int n) { g_cta_limit = n; }
 
+// one-shot epilogue dropout of the next gemm_bf16_tc (EPI_STORE_F32) launches, until reset with keep = 1
+static float g_drop_keep = 1.f;
+static unsigned long long g_drop_seed = 0;
+static long long g_drop_row0 = 0;
+void gemm_set_store_dropout(float keep, unsigned long long seed, long long row0) {
+  g_drop_keep = keep; g_drop_seed = seed; g_drop_row0 = row0;
+}
 static int g_num_sms = 0;
 int num_sms() {
   if (!g_num_sms) {
@@ -359,6 +377,7 @@ int gemm_bf16_tc(int a_mn, int b_mn, int M, int N, int K, float alpha, const __n
   GemmArgs g;
   g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.C = C; g.bias = bias; g.alpha = alpha; g.epi = epi;
   g.a_tap_kb = 0; g.a_tap_rows = 0;
+  g.drop_keep = (epi == EPI_STORE_F32) ? g_drop_keep : 1.f; g.drop_seed = g_drop_seed; g.drop_row0 = g_drop_row0;
   g.m_tiles = cdiv(M, GM); g.n_tiles = cdiv(N, BN);
   g.kblocks = cdiv(K, GK);
   int splits = 1;
@@ -404,6 +423,7 @@ int gemm_bf16_tc_conv(int M, int N, int Ktap, int taps, int tap_rows, const __nv
   GemmArgs g;
   g.M = M; g.N = N; g.K = Ktap * taps; g.ldc = ldc; g.C = C; g.bias = nullptr; g.alpha = 1.f; g.epi = EPI_STORE_F32;
   g.a_tap_kb = Ktap / GK; g.a_tap_rows = tap_rows;
+  g.drop_keep = 1.f; g.drop_seed = 0; g.drop_row0 = 0;
   g.m_tiles = cdiv(M, GM); g.n_tiles = cdiv(N, BN);
   g.kblocks = g.K / GK; g.kb_per_split = g.kblocks; g.k_splits = 1;
   CUtensorMap tmA, tmB;

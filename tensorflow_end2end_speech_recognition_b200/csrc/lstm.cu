@@ -539,6 +539,13 @@ extern "C" int b2_blstm_backward_side_wait(b2_stream_t stream_) {
   return tc_backward_side_wait((cudaStream_t)stream_);
 }
 
+extern "C" int b2_blstm_layer_path(const b2_lstm_desc* d) {
+  if (!d) return 0;
+  if (tc_layer_supported(d)) return 1;
+  if (wide_rec_supported(d)) return 2;
+  return 0;
+}
+
 extern "C" const void* b2_blstm_reserve_y_lp(const b2_lstm_desc* d, const void* reserve) {
   if (!d || !reserve || !(tc_layer_supported(d) || wide_rec_supported(d))) return nullptr;
   Reserve r;
@@ -668,6 +675,10 @@ extern "C" int b2_blstm_layer_backward_ex(const b2_lstm_desc* d, const float* x,
   }
   B2_CHECK_ARG(x && seq_len && fw && bw && dy && reserve && g_fw && g_bw && workspace,
                "blstm_backward: null pointer");
+  if (d->dy_premasked || (d->dx_keep_prob > 0.f && d->dx_keep_prob < 1.f)) {
+    set_error("blstm_backward: dx_keep_prob / dy_premasked need the tcgen05 layer path (b2_blstm_layer_path() == 1)");
+    return B2_ERR_UNSUPPORTED;
+  }
   Work w;
   const size_t need = work_layout(d, workspace, &w);
   if (workspace_bytes < need) { set_error("blstm_backward: workspace %zu < %zu", workspace_bytes, need); return B2_ERR_WORKSPACE; }

@@ -96,6 +96,8 @@ int make_tmap_generic(CUtensorMap* tm, int dtype_is_f32, const void* base, int r
                       int swizzle128);
 int num_sms();
 void gemm_set_cta_limit(int n);
+void gemm_set_store_dropout(float keep, unsigned long long seed, long long row0);   // fused into the fp32 store of
+                                                                                   // the next gemm_bf16_tc launches; keep = 1: off
 
 // bf16 / tcgen05 layer (lstm_tc.cu)
 size_t tc_layer_workspace_bytes(const b2_lstm_desc* d);

@@ -504,7 +504,9 @@ int tc_layer_backward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16
   }
   ba.use_peephole = d->use_peephole; ba.cell_clip = d->cell_clip; ba.keep_prob = d->keep_prob;
   ba.seed = d->dropout_seed; ba.gates = r.gates; ba.cs = r.cs; ba.dG = dG; ba.dfinal = d_final_state;
-  if (d->keep_prob < 1.f && (((size_t)TB * 2 * H) % 4 == 0) && env_int("B2_DY_MASK_PASS", 1)) {     // mask dy once, outside the recurrence
+  if (d->dy_premasked) {
+    ba.keep_prob = 1.f;          // the layer above applied this layer's mask in its dX GEMM epilogue
+  } else if (d->keep_prob < 1.f && (((size_t)TB * 2 * H) % 4 == 0) && env_int("B2_DY_MASK_PASS", 1)) {     // mask dy once, outside the recurrence
     const int64_t n4 = (int64_t)TB * 2 * H / 4;
     int64_t blocks = (n4 + 255) / 256;
     if (blocks > num_sms() * 16) blocks = num_sms() * 16;
@@ -582,6 +584,8 @@ int tc_layer_backward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16
     if (rc) return rc;
     xa = w.xb;
   }
+  // DropoutWrapper backward of the layer below, fused into the store of dX (its own call then skips the mask pass)
+  const bool dx_mask = dx != nullptr && d->dx_keep_prob > 0.f && d->dx_keep_prob < 1.f;
   if (dx && chunk_dx && dx_nchunks > 1) {
     cudaStream_t ss = fc->s;
     B2_CUDA(cudaStreamWaitEvent(ss, fc->ev_launch, 0));      // counters zeroed, dx buffer free
@@ -607,16 +611,20 @@ int tc_layer_backward(const b2_lstm_desc* d, const float* x, const __nv_bfloat16
         break;
       }
       gemm_set_cta_limit(i + 2 < K ? free_sms : 0);
+      if (dx_mask) gemm_set_store_dropout(d->dx_keep_prob, d->dx_dropout_seed, (long long)r0);
       rc = gemm_bf16_tc(0, 0, (t1 - t0) * B, D, 8 * H, 1.f, dG + r0 * 8 * H, 8 * H, w.wx, 8 * H, dx + r0 * D, D, nullptr,
                         EPI_STORE_F32, 0, ss);
     }
     gemm_set_cta_limit(0);
+    gemm_set_store_dropout(1.f, 0, 0);
     if (rc) return rc;
     B2_CUDA(cudaEventRecord(fc->ev_done, ss));
     B2_CUDA(cudaStreamWaitEvent(stream, fc->ev_done, 0));
   } else if (dx) {
+    if (dx_mask) gemm_set_store_dropout(d->dx_keep_prob, d->dx_dropout_seed, 0);
     rc = gemm_bf16_tc(0, 0, TB, D, 8 * H, 1.f, dG, 8 * H, w.wx, 8 * H, dx, D, nullptr,
                       EPI_STORE_F32, 0, stream);
+    gemm_set_store_dropout(1.f, 0, 0);
     if (rc) return rc;
   }
   // 3. off the critical path: weight gradients on packed operands

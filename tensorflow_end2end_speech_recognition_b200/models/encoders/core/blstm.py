@@ -134,7 +134,24 @@ class BLSTMEncoder(object):
         own = saved is None
         saved, seq_len = self._saved if own else saved
         dy = d_outputs
+        # DropoutWrapper backward between two stacked layers that both run the tcgen05 path: layer l+1 applies layer l's
+        # mask in the store of the dX GEMM it computes anyway, layer l then skips its own mask pass over dy (a full
+        # read + write of [T,B,2H] per layer).  Not across a layer whose output also feeds a tapped head (d_inject:
+        # that gradient is added unmasked).
+        by_layer = {s[3]: s[0] for s in saved}
+        fuse_below = {}
+        for i_layer, desc in by_layer.items():
+            lower = by_layer.get(i_layer - 1)
+            fuse_below[i_layer] = bool(
+                lower is not None and 0.0 < lower.keep_prob < 1.0 and not (d_inject and (i_layer - 1) in d_inject)
+                and ops.blstm_layer_path(desc) == 1 and ops.blstm_layer_path(lower) == 1)
         for desc, x, reserve, i_layer, x_lp in reversed(saved):
+            if fuse_below.get(i_layer) or fuse_below.get(i_layer + 1):
+                lower = by_layer.get(i_layer - 1)
+                desc = ops.lstm_desc_with(
+                    desc, dy_premasked=int(bool(fuse_below.get(i_layer + 1))),
+                    dx_keep_prob=float(lower.keep_prob) if fuse_below.get(i_layer) else 0.0,
+                    dx_dropout_seed=int(lower.dropout_seed) if fuse_below.get(i_layer) else 0)
             if d_inject and i_layer in d_inject:      # gradient of a head tapped at this layer's output (sub task)
                 dy = ops.add_(dy.contiguous(), d_inject[i_layer])
             pf = self._layer_params(variables, i_layer, "fw")

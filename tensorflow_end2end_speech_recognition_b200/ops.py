@@ -299,7 +299,20 @@ def lstm_desc(T, B, D_in, H, use_peephole=True, forget_bias=1.0, cell_clip=None,
               dropout_seed=0, precision=PREC_FP32, need_backward=True, num_proj=None):
     return LstmDesc(T, B, D_in, H, int(bool(use_peephole)), float(forget_bias),
                     float(cell_clip) if cell_clip else 0.0, float(keep_prob), int(dropout_seed),
-                    int(precision), int(bool(need_backward)), int(num_proj or 0))
+                    int(precision), int(bool(need_backward)), int(num_proj or 0), 0.0, 0, 0)
+
+
+def lstm_desc_with(desc, **fields):
+    """copy of a layer descriptor with some fields replaced (dx_keep_prob, dx_dropout_seed, dy_premasked, ...)"""
+    d = type(desc).from_buffer_copy(desc)
+    for k, v in fields.items():
+        setattr(d, k, v)
+    return d
+
+
+def blstm_layer_path(desc):
+    """0: fp32 / hybrid step kernels, 1: cluster/TMEM tcgen05 recurrence, 2: grid-resident wide-layer recurrence"""
+    return int(_lib.load().b2_blstm_layer_path(C.byref(desc)))
 
 
 def blstm_layer_forward(desc, x, seq_len, p_fw, p_bw, want_final_state=False, x_lp=0):

@@ -140,23 +140,26 @@ def test_forward_chunk_chain_bit_identical(cuda):
         assert np.abs(outs[chunks][2] - g0).max() <= 1e-5 * np.abs(g0).max()
 
 
+@pytest.mark.parametrize("T", [40, 80])
 @pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 3e-2)])
-def test_encoder_stack_with_dropout_matches_oracle_masks(cuda, precision, tol):
+def test_encoder_stack_with_dropout_matches_oracle_masks(cuda, precision, tol, T):
     """Three BLSTM layers with DropoutWrapper(output_keep_prob = 0.8): every layer's counter-hash mask reproduced for the
     oracle (tests/util_dropout.py), encoder output and ALL gradients (incl. d(inputs)) vs fp64 autograd -- the backward
-    masks travel through the stack (layer l's dy is layer l+1's dx)."""
+    masks travel through the stack (layer l's dy is layer l+1's dx; on the tcgen05 path layer l+1 applies layer l's mask
+    in the store of its dX GEMM, BLSTMEncoder.backward)."""
     import torch
     from oracle import lstm as olstm
     from tests.util_dropout import dropout_mask
     from tensorflow_end2end_speech_recognition_b200.models.encoders.core.blstm import BLSTMEncoder
     rng = np.random.RandomState(17)
-    B, T, D, H, L, keep, dseed = 6, 40, 24, 64, 3, 0.8, 5
+    # T = 80: the chunked dX GEMMs (16 chunks of 5 frames), each storing through the fused mask of the layer below
+    B, D, H, L, keep, dseed = 6, 24, 64, 3, 0.8, 5
     enc = BLSTMEncoder(H, None, L, "LSTMBlockCell", True, 0.2, None, time_major=True, precision=precision)
     named = enc.create_variables(D, rng)
     variables = {n: torch.tensor(a, device=cuda) for n, a in named}
     grads = {n: torch.zeros_like(v) for n, v in variables.items()}
     x = rng.randn(B, T, D).astype(np.float32)
-    seq = np.array([T, 31, 40, 22, 36, 27], np.int32)
+    seq = np.array([T, T - 9, T, T // 2 + 2, T - 4, T - 13], np.int32)
     for b in range(B):
         x[b, seq[b]:] = 0
     dy = rng.randn(T, B, 2 * H).astype(np.float32)
