@@ -607,6 +607,10 @@ int b2_allreduce_mean(b2_comm_t comm, float* const* buckets, const int64_t* size
 int b2_allreduce_mean_local(const b2_comm_t* comms, float* const* buffers, int64_t n,
                             int ndev, const b2_stream_t* streams);
 
+/* CRC-32C (Castagnoli) of a host buffer, continuing from `crc` (0 to start): the checksum of TensorFlow's checkpoint
+ * bundles, used by utils/io/tf_checkpoint.py (the Saver interop of examples/timit/evaluation/eval_ctc.py:70-88). */
+uint32_t b2_crc32c(uint32_t crc, const void* data, size_t n);
+
 /* ------------------------------------------------------------------ GRU layers
  * tf.contrib.rnn.GRUCell under bidirectional_dynamic_rnn (models/encoders/core/gru.py:128-160, BGRUEncoder) or
  * MultiRNNCell + dynamic_rnn (gru.py:52-73, GRUEncoder: bind an all-zero second direction):

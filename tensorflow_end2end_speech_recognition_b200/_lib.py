@@ -94,6 +94,7 @@ PROTOTYPES = {
     "b2_gemm": (_i, [_i, _i, _i, _i, _i, _f, _p, _i, _p, _i, _f, _p, _i, _p, _i, _p, _sz, _p]),
     "b2_gemm_lp": (_i, [_i, _i, _i, _i, _i, _f, _p, _i, _p, _i, _p, _i, _f, _p, _i, _p, _i, _p, _sz, _p]),
     "b2_gemm_bf16": (_i, [_i, _i, _i, _i, _i, _f, _p, _i, _p, _i, _p, _i, _p, _i, _i, _p]),
+    "b2_crc32c": (C.c_uint32, [C.c_uint32, _p, _sz]),
     "b2_bgru_reserve_bytes": (_sz, [C.POINTER(GruDesc)]),
     "b2_bgru_workspace_bytes": (_sz, [C.POINTER(GruDesc)]),
     "b2_bgru_layer_forward": (_i, [C.POINTER(GruDesc), _p, _p, C.POINTER(GruParams), C.POINTER(GruParams), _p, _p, _p,

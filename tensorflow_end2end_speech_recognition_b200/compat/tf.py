@@ -223,10 +223,44 @@ class _CheckpointState(object):
 
 class _Train(object):
     class Saver(object):
-        """Checkpoints = {TF variable name: array} in one .npz (+ a 'checkpoint' index file)."""
+        """Checkpoints = {TF variable name: array} in one .npz (+ a 'checkpoint' index file) and, beside it, the same
+        variables as a TensorFlow checkpoint bundle (``<path>.index`` + ``<path>.data-00000-of-00001``,
+        utils/io/tf_checkpoint.py) with TF's slot names for the optimizer state -- the format the reference's own
+        ``tf.train.Saver`` reads and writes.  ``restore`` takes either: the .npz when it exists, else a TF bundle
+        (e.g. one trained with the reference), matching variables by name (a leading scope prefix is ignored)."""
 
-        def __init__(self, max_to_keep=None, var_list=None):
-            pass
+        # optimizer kind -> TF slot-name suffixes of (state0, state1)
+        _SLOTS = {"adagrad": ("Adagrad", None), "adadelta": ("Adadelta", "Adadelta_1"), "adam": ("Adam", "Adam_1"),
+                  "rmsprop": ("RMSProp", None), "momentum": ("Momentum", None), "nestrov": ("Momentum", None),
+                  "sgd": (None, None)}
+
+        def __init__(self, max_to_keep=None, var_list=None, write_tf_bundle=True):
+            self.write_tf_bundle = write_tf_bundle
+
+        def _bundle_arrays(self, sess):
+            arrays = {}
+            for m in sess.graph.models:
+                opt = getattr(m, "optimizer", None)
+                base = m.flat_params.data_ptr()
+                for v in m.trainable_variables():
+                    if v.name in arrays:
+                        raise ValueError("two models of this session share the variable name %r" % v.name)
+                    arrays[v.name] = v.tensor.detach().cpu().numpy()
+                    if opt is None:
+                        continue
+                    o = (v.tensor.data_ptr() - base) // 4
+                    for st, suffix in zip((opt.state0, opt.state1), self._SLOTS.get(opt.kind, (None, None))):
+                        if st is not None and suffix is not None:
+                            arrays["%s/%s" % (v.name, suffix)] = \
+                                st[o:o + v.tensor.numel()].view(v.tensor.shape).detach().cpu().numpy()
+                    if opt.kind == "rmsprop":          # TF keeps a (here always zero) momentum slot as well
+                        arrays[v.name + "/RMSProp_1"] = np.zeros(tuple(v.tensor.shape), np.float32)
+                if opt is not None:
+                    arrays["global_step"] = np.asarray(opt.global_step, np.int32)
+                    if opt.kind == "adam":             # TF: beta^t after t-1 updates, i.e. beta^(global_step + 1)
+                        arrays["beta1_power"] = np.asarray(0.9 ** (opt.global_step + 1), np.float32)
+                        arrays["beta2_power"] = np.asarray(0.999 ** (opt.global_step + 1), np.float32)
+            return arrays
 
         def save(self, sess, save_path, global_step=None):
             """A TF Saver stores every global variable: the trainable ones, the optimizer slots and the step
@@ -248,12 +282,59 @@ class _Train(object):
                         if st is not None:
                             arrays[pre + k] = st.detach().cpu().numpy()
             np.savez(path + ".npz", **arrays)
+            if self.write_tf_bundle:
+                from ..utils.io import tf_checkpoint
+                tf_checkpoint.save_tf_checkpoint(path, self._bundle_arrays(sess), write_state=False)
             with open(os.path.join(os.path.dirname(path) or ".", "checkpoint"), "w") as f:
                 f.write('model_checkpoint_path: "%s"\n' % path)
             return path
 
+        def _restore_tf_bundle(self, sess, save_path):
+            """variables (and, where the optimizer exists already, its slots) from a TensorFlow checkpoint bundle"""
+            import torch
+            from ..utils.io import tf_checkpoint
+            data = tf_checkpoint.load_tf_checkpoint(save_path)
+
+            def find(name):
+                if name in data:
+                    return data[name]
+                hits = [k for k in data if k.endswith("/" + name)]
+                if len(hits) == 1:
+                    return data[hits[0]]
+                if not hits:
+                    raise KeyError("variable %r is not in the checkpoint %s" % (name, save_path))
+                raise KeyError("variable %r is ambiguous in %s: %s" % (name, save_path, hits))
+            for m in sess.graph.models:
+                for v in m.trainable_variables():
+                    a = find(v.name)
+                    if tuple(a.shape) != tuple(v.tensor.shape):
+                        raise ValueError("%s: checkpoint shape %s, model shape %s" % (v.name, a.shape,
+                                                                                     tuple(v.tensor.shape)))
+                    v.tensor.copy_(torch.as_tensor(a).to(v.tensor.device))
+                m._params_version = getattr(m, "_params_version", 0) + 1
+                opt = getattr(m, "optimizer", None)
+                if opt is None:
+                    continue
+                base = m.flat_params.data_ptr()
+                for st, suffix in zip((opt.state0, opt.state1), self._SLOTS.get(opt.kind, (None, None))):
+                    if st is None or suffix is None:
+                        continue
+                    for v in m.trainable_variables():
+                        try:
+                            a = find("%s/%s" % (v.name, suffix))
+                        except KeyError:
+                            continue
+                        o = (v.tensor.data_ptr() - base) // 4
+                        st[o:o + v.tensor.numel()].copy_(torch.as_tensor(a).reshape(-1).to(st.device))
+                if "global_step" in data:
+                    opt.global_step = int(data["global_step"])
+
         def restore(self, sess, save_path):
             import torch
+            if not os.path.isfile(save_path + ".npz"):
+                from ..utils.io import tf_checkpoint
+                if tf_checkpoint.is_tf_checkpoint(save_path):
+                    return self._restore_tf_bundle(sess, save_path)
             data = np.load(save_path + ".npz")
             for i, m in enumerate(sess.graph.models):
                 for v in m.trainable_variables():

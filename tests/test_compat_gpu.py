@@ -4,6 +4,7 @@ until the synthetic batch is fitted, decode + LER, parameter count, checkpoint r
 import os
 
 import numpy as np
+import torch
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -76,6 +77,29 @@ def test_ctc_graph_style_training(cuda, tmp_path):
                 ckpt = tf.train.get_checkpoint_state(str(tmp_path))
                 saver.restore(sess, ckpt.model_checkpoint_path)
                 assert path == ckpt.model_checkpoint_path
+                assert abs(sess.run(loss_op, feed_dict=feed_dict) - before) < 1e-6
+                # the same checkpoint as a TensorFlow bundle (<path>.index / .data-00000-of-00001), TF slot names
+                from tensorflow_end2end_speech_recognition_b200.utils.io import tf_checkpoint
+                bundle = tf_checkpoint.load_tf_checkpoint(path)
+                name0 = model.trainable_variables()[0].name
+                assert name0 in bundle and name0 + "/Adam" in bundle and name0 + "/Adam_1" in bundle   # adam: m, v slots
+                assert "beta1_power" in bundle and int(bundle["global_step"]) == model.optimizer.global_step
+                os.remove(path + ".npz")
+                state_before, step_before = model.optimizer.state0.clone(), model.optimizer.global_step
+                state1_before = model.optimizer.state1.clone()
+                model.flat_params.mul_(0.5)
+                model.optimizer.state0.add_(1.0)
+                model.optimizer.state1.mul_(3.0)
+                model.optimizer.global_step = 0
+                saver.restore(sess, path)                      # no .npz any more: the TF bundle is read
+                assert abs(sess.run(loss_op, feed_dict=feed_dict) - before) < 1e-6
+                assert torch.equal(model.optimizer.state0, state_before) and model.optimizer.global_step == step_before
+                assert torch.equal(model.optimizer.state1, state1_before)
+                # a bundle written under a scope prefix (as a reference-trained graph may name its variables)
+                pre = os.path.join(str(tmp_path), "scoped.ckpt")
+                tf_checkpoint.save_tf_checkpoint(pre, {"ctc_model/" + k: v for k, v in bundle.items()})
+                model.flat_params.mul_(0.25)
+                saver.restore(sess, pre)
                 assert abs(sess.run(loss_op, feed_dict=feed_dict) - before) < 1e-6
     finally:
         compat.uninstall()
