@@ -4,7 +4,6 @@ import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from tensorflow_end2end_speech_recognition_b200 import ops
-from oracle import decode as odec
 dev = torch.device("cuda:0")
 rng = np.random.RandomState(0)
 Bn, T, C = 256, 1000, 29
@@ -30,15 +29,4 @@ ms_g = timeit(lambda: ops.ctc_greedy_decode(logits_tbc, seq))
 ms_b = timeit(lambda: ops.ctc_beam_decode(lp_d, seq, 20))
 print("greedy: %.3f ms for %d utt -> %.0f utt/s ; beam 20: %.1f ms -> %.0f utt/s" %
       (ms_g, Bn, Bn / ms_g * 1e3, ms_b, Bn / ms_b * 1e3), flush=True)
-# bit-exactness against the oracle on a sample of utterances (the python decoder is slow)
-lab, n, sc = ops.ctc_beam_decode(lp_d, seq, 20)
-lab, n = lab.cpu().numpy(), n.cpu().numpy()
-probs = torch.exp(lp).numpy()
-ok = 0
-for b in range(4):
-    ref, _ = odec.beam_search_decode(probs[b:b + 1], [T], C - 1, 20)
-    ok += int(list(lab[b, :n[b]]) == ref[0])
-g, gn = ops.ctc_greedy_decode(logits_tbc, seq)
-gref = odec.greedy_decode(lp.numpy(), [T] * Bn, C - 1)
-gok = sum(int(list(g[b, :gn[b]].cpu().numpy()) == gref[b]) for b in range(Bn))
-print("beam labels bit-exact vs oracle: %d/4 sampled ; greedy bit-exact: %d/%d" % (ok, gok, Bn), flush=True)
+# (label parity of these decoders vs the oracle / the reference's golden vectors: tests/test_decode_gpu.py)

@@ -7,15 +7,19 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import lstm as olstm  # noqa: E402
 from tensorflow_end2end_speech_recognition_b200 import ops  # noqa: E402
 
 dev = torch.device("cuda:0")
 
 
 def bench(T, B, D, H, prec, backward, iters=5, label="", keep_prob=1.0):
-    layer = olstm.init_blstm_params(D, H, 1, parameter_init=0.1, seed=0)[0]
-    P = {d: {k: torch.tensor(v, device=dev) for k, v in layer[d].items()} for d in layer}
+    rng = np.random.RandomState(0)
+    P = {}
+    for d in ("fw", "bw"):
+        P[d] = {"kernel": torch.tensor(rng.uniform(-0.1, 0.1, (D + H, 4 * H)).astype(np.float32), device=dev),
+                "bias": torch.zeros(4 * H, device=dev)}
+        for k in ("w_i_diag", "w_f_diag", "w_o_diag"):
+            P[d][k] = torch.tensor(rng.uniform(-0.1, 0.1, H).astype(np.float32), device=dev)
     G = {d: {k: torch.zeros_like(v) for k, v in P[d].items()} for d in P}
     x = torch.randn(T, B, D, device=dev)
     dy = torch.randn(T, B, 2 * H, device=dev)
