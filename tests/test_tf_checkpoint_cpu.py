@@ -11,6 +11,13 @@ import pytest
 from tensorflow_end2end_speech_recognition_b200.utils.io import tf_checkpoint as tfc
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _library():
+    """CRC-32C comes from the C-ABI library (host code, loads without a GPU): build it if this is a fresh checkout"""
+    import __graft_entry__
+    __graft_entry__.build()
+
+
 def test_crc32c_known_answers():
     assert tfc.crc32c(b"123456789") == 0xE3069283                  # the CRC catalogue's check value for CRC-32C
     assert tfc.crc32c(b"\x00" * 32) == 0x8A9136AA                  # RFC 3720 B.4: 32 bytes of zeros
